@@ -1,0 +1,37 @@
+// Internal (non-ABI) declarations shared by the kernels and the C-ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/lass_b200.h"
+
+namespace lass {
+
+// ---- error reporting (thread-local message behind lass_last_error()) ----
+int set_error(int code, const char* fmt, ...);
+int set_cuda_error(cudaError_t e, const char* what);
+
+// ---- TMA tensor maps (cuTensorMapEncodeTiled resolved at run time: no link-time libcuda dependency) ----
+// dims / box in elements (innermost first); strides in bytes for dims 1..rank-1.
+int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
+                    const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle);
+
+// ---- K1 stft ----
+int stft_num_ntiles(int n_fft);
+size_t stft_padded_len(int L, int n_fft, int hop);
+size_t stft_workspace_bytes(int B, int L, int n_fft, int hop);
+int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
+                float* mag, float* cosp, float* sinp, int precision_mode, void* workspace, cudaStream_t stream);
+
+// ---- K5 mask + istft ----
+cudaError_t launch_mask_istft(const float* feat, long long feat_bstride, long long feat_cstride, int feat_tstride,
+                              int feat_F, const float* mag, const float* cosp, const float* sinp,
+                              const float* window, const float* tw, float* out, int B, int T, int F, int N,
+                              int hop, int L, cudaStream_t stream);
+
+}  // namespace lass

@@ -1,0 +1,123 @@
+// Debug entry point: one tcgen05.mma tile with caller-controlled shared-memory descriptors.
+//
+// Used by tests/test_umma_probe.py on the B200 to pin down the descriptor rules the implicit-GEMM conv
+// kernel relies on (swizzle modes, 8-row-group stride, start addresses that are shifted by whole rows).
+// A (rows x kc) and B (n x kc) are 16-bit K-major matrices; A is brought into shared memory by ONE TMA box
+// of `a_rows` rows, B by one box of `n` rows; then kc/16 MMAs (M = 128) are issued with
+//   desc_a = make_smem_desc(A_smem + a_start_bytes + ks*32, a_sbo, swizzle, a_base_offset)
+// and the 128 x n fp32 accumulator is written to `out`.
+#include "lass_internal.cuh"
+#include "ptx.cuh"
+
+namespace lass {
+namespace {
+
+struct ProbeParams {
+  CUtensorMap tmA, tmB;
+  float* out;
+  int a_rows, n, kc, swizzle, a_start_bytes, a_sbo, a_base_offset, b_sbo, fmt;
+};
+
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constant__ ProbeParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const int row_bytes = p.kc * 2;
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + ((p.a_rows * row_bytes + 1023) & ~1023);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + ((p.n * row_bytes + 1023) & ~1023));
+  uint64_t* acc_bar = bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (threadIdx.x == 0) {
+    mbar_arrive_expect_tx(bar, (uint32_t)((p.a_rows + p.n) * row_bytes));
+    tma_load_2d(sA, &p.tmA, bar, 0, 0);
+    tma_load_2d(sB, &p.tmB, bar, 0, 0);
+    mbar_wait(bar, 0);
+    tc_fence_after_sync();
+    const uint32_t idesc = make_idesc_f16(p.fmt, p.fmt, 128, p.n);
+    for (int ks = 0; ks < p.kc / 16; ++ks) {
+      const uint64_t da = make_smem_desc(smem_u32(sA) + p.a_start_bytes + ks * 32, p.a_sbo, p.swizzle, p.a_base_offset);
+      const uint64_t db = make_smem_desc(smem_u32(sB) + ks * 32, p.b_sbo, p.swizzle, 0);
+      umma_f16(tmem_acc, da, db, idesc, ks != 0);
+    }
+    umma_commit(acc_bar);
+  }
+  __syncwarp();
+  mbar_wait(acc_bar, 0);
+  tc_fence_after_sync();
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int c = 0; c < p.n; c += 16) {
+    float v[16];
+    tmem_ld_x16(taddr + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) p.out[(size_t)(warp * 32 + lane) * p.n + c + j] = v[j];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_acc, 256);
+  }
+}
+
+}  // namespace
+}  // namespace lass
+
+using namespace lass;
+
+extern "C" int lass_debug_umma_probe(const void* A, int a_rows, const void* Bm, int n, int kc, int swizzle_mode,
+                                              int a_start_bytes, int a_sbo, int a_base_offset, int b_sbo, int fmt_fp16,
+                                              float* out, void* stream) {
+  if (!A || !Bm || !out) return set_error(LASS_ERR_ARG, "probe: null pointer");
+  if (!(kc == 64 || kc == 32) || n % 16 || n < 16 || n > 256 || a_rows < 8 || a_rows > 256 || a_rows % 8)
+    return set_error(LASS_ERR_ARG, "probe: bad shape");
+  ProbeParams p;
+  const CUtensorMapSwizzle sw = swizzle_mode == 2 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : swizzle_mode == 4 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : swizzle_mode == 6 ? CU_TENSOR_MAP_SWIZZLE_32B
+                                                    : CU_TENSOR_MAP_SWIZZLE_NONE;
+  {
+    uint64_t dims[2] = {(uint64_t)kc, (uint64_t)a_rows};
+    uint64_t strides[1] = {(uint64_t)kc * 2};
+    uint32_t box[2] = {(uint32_t)kc, (uint32_t)a_rows};
+    int e = make_tensor_map(&p.tmA, A, 2, 2, dims, strides, box, sw);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)kc, (uint64_t)n};
+    uint64_t strides[1] = {(uint64_t)kc * 2};
+    uint32_t box[2] = {(uint32_t)kc, (uint32_t)n};
+    int e = make_tensor_map(&p.tmB, Bm, 2, 2, dims, strides, box, sw);
+    if (e) return e;
+  }
+  p.out = out;
+  p.a_rows = a_rows;
+  p.n = n;
+  p.kc = kc;
+  p.swizzle = swizzle_mode;
+  p.a_start_bytes = a_start_bytes;
+  p.a_sbo = a_sbo;
+  p.a_base_offset = a_base_offset;
+  p.b_sbo = b_sbo;
+  p.fmt = fmt_fp16 ? kFmtF16 : kFmtBF16;
+  const size_t smem = 1024 + 2 * 256 * 128 + 2048 + 256;
+  cudaError_t e = cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "probe smem attribute");
+  umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
+  return set_cuda_error(cudaGetLastError(), "probe launch");
+}

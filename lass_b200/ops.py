@@ -1,0 +1,72 @@
+"""Tensor-level wrappers over the C ABI (device pointers of torch CUDA tensors, current stream).
+
+These are the per-kernel entry points used by the module in ``lass_b200.models.resunet`` and by the parity
+tests.  Every function requires CUDA tensors and raises otherwise — there is no CPU path.
+"""
+import torch
+
+from . import _cabi
+
+
+def _ptr(t: torch.Tensor) -> int:
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("lass_b200 ops need CUDA tensors (no CPU fallback); got device %s" % t.device)
+        if not t.is_contiguous():
+            raise RuntimeError("lass_b200 ops need contiguous tensors")
+
+
+def stft_fwd(wave: torch.Tensor, basis_hi: torch.Tensor, basis_lo: torch.Tensor, n_fft: int, hop: int,
+             precision_mode: int = 0, workspace: torch.Tensor = None):
+    """wave (B, L) fp32 -> mag, cos, sin (B, 1, T, F) fp32 (reference layout, models/base.py:83-88)."""
+    lib = _cabi.load()
+    _require_cuda(wave, basis_hi, basis_lo)
+    assert wave.dtype == torch.float32 and wave.dim() == 2
+    B, L = wave.shape
+    T, F = L // hop + 1, n_fft // 2 + 1
+    need = lib.lass_stft_workspace_bytes(B, L, n_fft, hop)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=wave.device)
+    out = torch.empty(3, B, 1, T, F, dtype=torch.float32, device=wave.device)
+    _cabi.check(lib.lass_stft_fwd(_ptr(wave), B, L, n_fft, hop, _ptr(basis_hi), _ptr(basis_lo), _ptr(out[0]),
+                                  _ptr(out[1]), _ptr(out[2]), precision_mode, _ptr(workspace),
+                                  workspace.numel() * workspace.element_size(), _stream()))
+    return out[0], out[1], out[2]
+
+
+def mask_istft(feat: torch.Tensor, mag: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, window: torch.Tensor,
+               twiddle: torch.Tensor, n_fft: int, hop: int, length: int, feat_F: int = None):
+    """feat (B, 3, Tf, Ff) fp32 (Tf >= T rows, first ``feat_F`` bins valid) + mixture mag/cos/sin (B, 1, T, F)
+    -> waveform (B, length).  Reference: models/resunet.py:436-519 + torchlibrosa ISTFT."""
+    lib = _cabi.load()
+    _require_cuda(feat, mag, cos, sin, window, twiddle)
+    B, _, T, F = mag.shape
+    assert feat.shape[0] == B and feat.shape[1] == 3 and feat.shape[2] >= T
+    Ff = feat.shape[3]
+    feat_F = min(Ff, F) if feat_F is None else feat_F
+    out = torch.empty(B, length, dtype=torch.float32, device=mag.device)
+    _cabi.check(lib.lass_mask_istft(_ptr(feat), feat.stride(0), feat.stride(1), feat.stride(2), feat_F, _ptr(mag),
+                                    _ptr(cos), _ptr(sin), _ptr(window), _ptr(twiddle), B, T, F, n_fft, hop, length,
+                                    _ptr(out), _stream()))
+    return out
+
+
+def umma_probe(A: torch.Tensor, Bm: torch.Tensor, swizzle_mode: int, a_start_bytes: int, a_sbo: int,
+               a_base_offset: int, b_sbo: int):
+    lib = _cabi.load()
+    _require_cuda(A, Bm)
+    a_rows, kc = A.shape
+    n = Bm.shape[0]
+    out = torch.zeros(128, n, dtype=torch.float32, device=A.device)
+    _cabi.check(lib.lass_debug_umma_probe(_ptr(A), a_rows, _ptr(Bm), n, kc, swizzle_mode, a_start_bytes, a_sbo,
+                                          a_base_offset, b_sbo, 1 if A.dtype == torch.float16 else 0, _ptr(out),
+                                          _stream()))
+    return out

@@ -1,0 +1,55 @@
+"""Host-side packing of reference-keyed parameters into the layouts the sm_100a kernels consume.
+
+Runs once per set of weights (off the hot path) with plain torch ops on whatever device the parameters
+live on.  State-dict keys are the reference's: the frozen DFT matrices
+``base.stft.conv_real.weight`` / ``conv_imag.weight`` are honoured as the forward basis.
+"""
+import math
+
+import torch
+
+
+def split_bf16(x: torch.Tensor):
+    """x (fp32) -> (hi, lo) bf16 with hi + lo ~= x to ~16 mantissa bits."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.to(torch.float32)).to(torch.bfloat16)
+    return hi, lo
+
+
+def pack_stft_basis(conv_real_w: torch.Tensor, conv_imag_w: torch.Tensor):
+    """(F, 1, n_fft) x2 -> (hi, lo) bf16 of shape (ntiles*128, n_fft).
+
+    Tile j holds bins [64j, 64j+64): rows [0,64) real basis, rows [64,128) imaginary basis (kernel K1,
+    ``lass_b200/csrc/stft.cu``).  Rows of bins >= F are zero.
+    """
+    F, _, n_fft = conv_real_w.shape
+    ntiles = (F + 63) // 64
+    re = conv_real_w.reshape(F, n_fft).to(torch.float32)
+    im = conv_imag_w.reshape(F, n_fft).to(torch.float32)
+    full = torch.zeros(ntiles, 2, 64, n_fft, dtype=torch.float32, device=re.device)
+    pad_re = torch.zeros(ntiles * 64, n_fft, dtype=torch.float32, device=re.device)
+    pad_im = torch.zeros_like(pad_re)
+    pad_re[:F] = re
+    pad_im[:F] = im
+    full[:, 0] = pad_re.reshape(ntiles, 64, n_fft)
+    full[:, 1] = pad_im.reshape(ntiles, 64, n_fft)
+    hi, lo = split_bf16(full.reshape(ntiles * 128, n_fft))
+    return hi.contiguous(), lo.contiguous()
+
+
+def hann_periodic(n: int, device=None) -> torch.Tensor:
+    k = torch.arange(n, dtype=torch.float64, device=device)
+    return (0.5 - 0.5 * torch.cos(2.0 * math.pi * k / n)).to(torch.float32)
+
+
+def istft_tables(n_fft: int, win_length: int = None, device=None):
+    """(window (n_fft) fp32, twiddle (n_fft, 2) fp32 = (cos, sin)(2 pi j / n_fft)) for kernel K5."""
+    win_length = n_fft if win_length is None else win_length
+    w = hann_periodic(win_length, device)
+    if win_length < n_fft:
+        lpad = (n_fft - win_length) // 2
+        w = torch.nn.functional.pad(w, (lpad, n_fft - win_length - lpad))
+    j = torch.arange(n_fft, dtype=torch.float64, device=device)
+    ang = 2.0 * math.pi * j / n_fft
+    tw = torch.stack((torch.cos(ang), torch.sin(ang)), dim=-1).to(torch.float32)
+    return w.contiguous(), tw.contiguous()

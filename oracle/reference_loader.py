@@ -1,0 +1,31 @@
+"""TEST INFRASTRUCTURE ONLY — import the UNMODIFIED reference from ``/root/reference``.
+
+``/root/reference`` exists only in the build container (never on the GPU box), so this module is
+used by (i) ``oracle/make_golden.py`` to generate ``tests/golden`` and (ii) the ``not gpu`` tests that
+pin the travelling oracle (``oracle/resunet_oracle.py``) to the reference.  Those tests skip when
+the directory is absent.
+
+The reference's ``models/resunet.py:6`` imports ``torchlibrosa.stft``; the restatement under
+``oracle/torchlibrosa`` is put first on ``sys.path``.
+"""
+import os
+import sys
+
+REFERENCE_ROOT = os.environ.get("LASS_REFERENCE_ROOT", "/root/reference")
+_ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
+
+
+def reference_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "models", "resunet.py"))
+
+
+def import_reference_resunet():
+    """Return the reference's ``models.resunet`` module (unmodified source)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not present at %s" % REFERENCE_ROOT)
+    if _ORACLE_DIR not in sys.path:
+        sys.path.insert(0, _ORACLE_DIR)          # makes `import torchlibrosa` resolve to the restatement
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(1, REFERENCE_ROOT)       # `models` is a namespace package in the reference
+    import importlib
+    return importlib.import_module("models.resunet")
