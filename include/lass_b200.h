@@ -84,6 +84,56 @@ LASS_API int lass_mask_istft(const float* feat3, long long feat_bstride, long lo
                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
+ * K3 / K4  implicit-GEMM convolution on tcgen05  (replaces conv2d 3x3 / 1x1 + conv_transpose2d(kernel = stride)
+ *     of ConvBlockRes / EncoderBlockRes1B / DecoderBlockRes1B, reference models/resunet.py:147-165,186-198,
+ *     240-264, with batch_norm + FiLM + leaky_relu folded into the producer's epilogue, the residual / shortcut
+ *     as a second K-segment, avg_pool2d, torch.cat (channel-slice outputs) and after_conv (:570) fused in)
+ *
+ * Activations are NHWC 16-bit (bf16, or fp16 for the raw residual stream).  All structs are HOST memory.
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct lass_conv_segment {
+  const void* src;     /* (B, H, W, src_cstride) 16-bit; channels [src_coff, src_coff + cin) are read            */
+  int src_cstride;     /* channels per pixel of the source buffer (multiple of 8)                                 */
+  int src_coff;        /* first channel read (multiple of 8)                                                      */
+  int cin;             /* channels of this K-segment (multiple of kc)                                             */
+  int kc;              /* channels per K-chunk: 32 or 64                                                          */
+  int taps;            /* 9 = 3x3 conv with zero padding 1 (tap = ky*3 + kx), 1 = 1x1                             */
+  int fp16;            /* 0 = bf16 source and weights, 1 = fp16 source and weights                                */
+  const void* weights; /* (taps, ncols, cin) 16-bit                                                               */
+} lass_conv_segment;
+
+typedef struct lass_conv_out {
+  void* ptr;           /* (B, Ho, Wo, cstride) 16-bit NHWC; NULL = output disabled                                */
+  int cstride;         /* channels per pixel of the destination buffer                                            */
+  int coff;            /* first channel written                                                                   */
+  int fp16;            /* 1 = saturating fp16, 0 = bf16                                                           */
+  const float* scale;  /* NULL: store the value; else store leaky_relu(scale[c]*v + shift[b*shift_bstride + c])    */
+  const float* shift;
+  int shift_bstride;
+} lass_conv_out;
+
+typedef struct lass_conv_desc {
+  int B, H, W;         /* input grid                                                                              */
+  int ncols;           /* GEMM N: Cout, or up_h*up_w*Cout for a transposed conv (column = (dy, dx, c))            */
+  int nseg;            /* 1 or 2 K-segments accumulated into the same output                                      */
+  lass_conv_segment seg[2];
+  const float* bias;   /* (ncols) fp32 or NULL                                                                    */
+  int up_h, up_w;      /* transposed conv stride (1 or 2); output pixel (h*up_h + dy, w*up_w + dx)                */
+  int group_c;         /* Cout (= ncols / (up_h*up_w))                                                            */
+  lass_conv_out full_raw, full_act;  /* outputs on the (H*up_h, W*up_w) grid                                      */
+  int pool_h, pool_w;  /* average pooling window (1 or 2) for the pooled outputs                                  */
+  lass_conv_out pool_raw, pool_act;  /* outputs on the (H/pool_h, W/pool_w) grid                                  */
+  const float* after_w; /* fused after_conv: (3, ncols) fp32 or NULL                                              */
+  const float* after_b; /* (3)                                                                                    */
+  float* feat;          /* (B, 3, H, W) fp32                                                                      */
+} lass_conv_desc;
+
+LASS_API int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream);
+
+/* Debug: shared-memory halo-tile pitch of the conv kernel, 10 (dense, default) or 16 pixels. */
+LASS_API int lass_debug_set_halo_pitch(int pitch);
+
+/* ------------------------------------------------------------------------------------------------------
  * Debug: one tcgen05.mma tile (M = 128) with caller-controlled shared-memory descriptors; used by the GPU
  * tests to pin the descriptor rules the conv kernel relies on.  A (a_rows, kc) and Bm (n, kc) are 16-bit
  * K-major; out (128, n) fp32.  swizzle_mode: 0 none, 2 = 128 B, 4 = 64 B, 6 = 32 B.

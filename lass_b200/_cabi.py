@@ -70,3 +70,26 @@ def check(code):
     if code != 0:
         msg = load().lass_last_error()
         raise LassError(code, msg.decode("utf-8", "replace") if msg else "")
+
+
+# ---- C structs of include/lass_b200.h (host memory) ----
+class ConvSegment(ctypes.Structure):
+    _fields_ = [("src", c_void_p), ("src_cstride", c_int), ("src_coff", c_int), ("cin", c_int), ("kc", c_int),
+                ("taps", c_int), ("fp16", c_int), ("weights", c_void_p)]
+
+
+class ConvOut(ctypes.Structure):
+    _fields_ = [("ptr", c_void_p), ("cstride", c_int), ("coff", c_int), ("fp16", c_int), ("scale", c_void_p),
+                ("shift", c_void_p), ("shift_bstride", c_int)]
+
+
+class ConvDesc(ctypes.Structure):
+    _fields_ = [("B", c_int), ("H", c_int), ("W", c_int), ("ncols", c_int), ("nseg", c_int),
+                ("seg", ConvSegment * 2), ("bias", c_void_p), ("up_h", c_int), ("up_w", c_int), ("group_c", c_int),
+                ("full_raw", ConvOut), ("full_act", ConvOut), ("pool_h", c_int), ("pool_w", c_int),
+                ("pool_raw", ConvOut), ("pool_act", ConvOut), ("after_w", c_void_p), ("after_b", c_void_p),
+                ("feat", c_void_p)]
+
+
+SIGNATURES["lass_conv_igemm"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p])
+SIGNATURES["lass_debug_set_halo_pitch"] = (c_int, [c_int])

@@ -4,6 +4,7 @@
 
 #include <mutex>
 
+#include "conv.cuh"
 #include "lass_internal.cuh"
 
 namespace lass {
@@ -123,6 +124,22 @@ int lass_mask_istft(const float* feat3, long long feat_bstride, long long feat_c
   return set_cuda_error(launch_mask_istft(feat3, feat_bstride, feat_cstride, feat_tstride, feat_F, mag, cos, sin,
                                           window, twiddle, wave_out, B, T, F, n_fft, hop, L, (cudaStream_t)stream),
                         "mask_istft launch");
+}
+
+int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream) {
+  if (!desc_host) return set_error(LASS_ERR_ARG, "lass_conv_igemm: null descriptor");
+  ConvPrepared* cp = nullptr;
+  int e = conv_prepare(*desc_host, &cp);
+  if (e) return e;
+  e = conv_run(cp, (cudaStream_t)stream);
+  conv_free(cp);
+  return e;
+}
+
+int lass_debug_set_halo_pitch(int pitch) {
+  if (pitch != 10 && pitch != 16) return set_error(LASS_ERR_ARG, "halo pitch must be 10 or 16");
+  conv_set_halo_pitch(pitch);
+  return 0;
 }
 
 }  // extern "C"

@@ -1,0 +1,585 @@
+// K3 / K4: implicit-GEMM convolution on tcgen05 (sm_100a) for the FiLM-conditioned ResUNet30.
+//
+// Replaces (reference, per forward): every conv2d 3x3 / 1x1 and conv_transpose2d (kernel = stride) of
+// `ConvBlockRes` / `EncoderBlockRes1B` / `DecoderBlockRes1B` (models/resunet.py:147-165,186-198,240-264)
+// together with the ops around them: batch_norm + FiLM add + leaky_relu (as the PRODUCER's epilogue),
+// the residual / 1x1 shortcut add (as one more K-segment of the same accumulator), avg_pool2d, torch.cat
+// (outputs are written straight into the concat buffer's channel slice) and after_conv (:570).
+//
+// GEMM view:  D[pixel, cout] = sum over segments, taps (dy,dx), channels  A[pixel + (dy,dx), c] * W[tap][cout][c]
+//   * activations are NHWC 16-bit, already activated by their producer, so the conv's zero padding is the
+//     TMA out-of-bounds zero fill;
+//   * A: ONE 4-D TMA box per K-chunk brings the (16*MT + 2) x 10 pixel halo tile of kc channels into shared
+//     memory (rows = pixels, kc*2 bytes each, hardware swizzle).  The nine taps are nine shared-memory matrix
+//     descriptors into that same tile: start address shifted by (dy*10 + dx) rows, 8-row groups (8 pixels of
+//     one image row) strided by the halo pitch.  tcgen05 applies the swizzle on absolute smem address bits,
+//     so row-shifted starts are legal (verified on B200 by tests/test_gpu_umma_probe.py);
+//   * B: weight tiles (BN couts x kc channels) per (tap, chunk), streamed through a ring — or, when all tiles of
+//     a work item fit in the ring, loaded once and kept resident for the CTA's lifetime;
+//   * D: fp32 accumulators in TMEM, double-buffered (2 x MT x BN columns) so the epilogue of item i overlaps
+//     the MMAs of item i+1.
+// Persistent CTAs (grid = SM count x CTAs/SM), static round-robin over work items
+// (item = pixel tile (16*MT x 8) x N tile).  Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc),
+// 2..5 = epilogue (TMEM -> registers -> fp32 math -> 16-bit NHWC stores).
+#include <string.h>
+
+#include <new>
+
+#include "conv.cuh"
+#include "ptx.cuh"
+
+namespace lass {
+
+namespace {
+
+constexpr int TW = 8;          // pixels per tile row == rows of one 8-row descriptor group
+constexpr int kThreads = 192;
+constexpr int kMaxA = 8;
+constexpr int kMaxB = 40;
+constexpr float kSlope = 0.01f;
+
+struct SegDev {
+  CUtensorMap tmA;  // (C, W, H, B) view of the source channels
+  CUtensorMap tmB;  // (cin, ncols, taps)
+  int nchunks, taps, kc, fmt;
+};
+
+struct OutDev {
+  void* ptr;
+  const float* scale;
+  const float* shift;
+  int cstride, coff, fp16, shift_bstride;
+};
+
+struct ConvParams {
+  SegDev seg[2];
+  OutDev full_raw, full_act, pool_raw, pool_act;
+  const float* bias;
+  const float* after_w;
+  const float* after_b;
+  float* feat;
+  int nseg;
+  int B, H, W, ncols;
+  int tiles_h, tiles_w, pix_tiles, n_tiles, num_items;
+  int a_stages, b_stages, b_resident, halo_pitch;
+  uint32_t a_stage_bytes, b_stage_bytes;
+  int up_h, up_w, group_c;
+  int pool_h, pool_w;
+};
+
+struct Item {
+  int b, h0, w0, n0;
+};
+
+template <int MT>
+__device__ __forceinline__ Item decode_item(const ConvParams& p, int item, int BN) {
+  Item it;
+  const int nt = item / p.pix_tiles;
+  int pix = item - nt * p.pix_tiles;
+  const int per_img = p.tiles_h * p.tiles_w;
+  it.b = pix / per_img;
+  pix -= it.b * per_img;
+  const int th = pix / p.tiles_w;
+  it.h0 = th * (16 * MT);
+  it.w0 = (pix - th * p.tiles_w) * TW;
+  it.n0 = nt * BN;
+  return it;
+}
+
+__device__ __forceinline__ void store16(const OutDev& o, int b, int ho, int wo, int Ho, int Wo, int c,
+                                        const float* v, bool valid) {
+  float y[16];
+  if (o.scale != nullptr) {
+    const float4* sc = reinterpret_cast<const float4*>(o.scale + c);
+    const float4* sh = reinterpret_cast<const float4*>(o.shift + (size_t)b * o.shift_bstride + c);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = __ldg(sc + j);
+      const float4 s = __ldg(sh + j);
+      float t0 = fmaf(a.x, v[4 * j + 0], s.x), t1 = fmaf(a.y, v[4 * j + 1], s.y);
+      float t2 = fmaf(a.z, v[4 * j + 2], s.z), t3 = fmaf(a.w, v[4 * j + 3], s.w);
+      y[4 * j + 0] = t0 > 0.0f ? t0 : kSlope * t0;
+      y[4 * j + 1] = t1 > 0.0f ? t1 : kSlope * t1;
+      y[4 * j + 2] = t2 > 0.0f ? t2 : kSlope * t2;
+      y[4 * j + 3] = t3 > 0.0f ? t3 : kSlope * t3;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = v[j];
+  }
+  uint32_t w[8];
+  if (o.fp16) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = pack_f16x2_sat(y[2 * j], y[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(y[2 * j], y[2 * j + 1]);
+  }
+  if (valid) {
+    uint16_t* base = reinterpret_cast<uint16_t*>(o.ptr) + (((size_t)b * Ho + ho) * Wo + wo) * o.cstride + o.coff + c;
+    uint4* dst = reinterpret_cast<uint4*>(base);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+template <int BN, int MT>
+__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  constexpr int AS = (2 * MT * BN <= 512) ? 2 : 1;
+  constexpr int kTmemCols = (AS * MT * BN <= 32)    ? 32
+                            : (AS * MT * BN <= 64)  ? 64
+                            : (AS * MT * BN <= 128) ? 128
+                            : (AS * MT * BN <= 256) ? 256
+                                                    : 512;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* a_buf = smem;
+  unsigned char* b_buf = smem + (size_t)p.a_stages * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_buf + (size_t)p.b_stages * p.b_stage_bytes);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = a_full + kMaxA;
+  uint64_t* b_full = a_empty + kMaxA;
+  uint64_t* b_empty = b_full + kMaxB;
+  uint64_t* acc_full = b_empty + kMaxB;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < p.nseg; ++s) {
+      tma_prefetch_desc(&p.seg[s].tmA);
+      tma_prefetch_desc(&p.seg[s].tmB);
+    }
+    for (int s = 0; s < p.a_stages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < p.b_stages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
+    }
+    for (int s = 0; s < AS; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0;
+      bool first_item = true;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const Item it = decode_item<MT>(p, item, BN);
+        uint32_t b_slot_res = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const SegDev& sg = p.seg[s];
+          const uint32_t row_bytes = sg.kc * 2;
+          const bool halo = sg.taps == 9;
+          const uint32_t a_bytes = halo ? (uint32_t)(16 * MT + 2) * p.halo_pitch * row_bytes : (uint32_t)(16 * MT) * TW * row_bytes;
+          const uint32_t b_bytes = BN * row_bytes;
+          for (int ch = 0; ch < sg.nchunks; ++ch) {
+            const uint32_t sa = a_it % p.a_stages;
+            mbar_wait(&a_empty[sa], ((a_it / p.a_stages) & 1) ^ 1);
+            mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+            tma_load_4d(a_buf + (size_t)sa * p.a_stage_bytes, &sg.tmA, &a_full[sa], ch * sg.kc,
+                        halo ? it.w0 - 1 : it.w0, halo ? it.h0 - 1 : it.h0, it.b);
+            ++a_it;
+            for (int tp = 0; tp < sg.taps; ++tp) {
+              if (p.b_resident) {
+                if (first_item) {
+                  mbar_arrive_expect_tx(&b_full[b_slot_res], b_bytes);
+                  tma_load_3d(b_buf + (size_t)b_slot_res * p.b_stage_bytes, &sg.tmB, &b_full[b_slot_res],
+                              ch * sg.kc, it.n0, tp);
+                }
+                ++b_slot_res;
+              } else {
+                const uint32_t sb = b_it % p.b_stages;
+                mbar_wait(&b_empty[sb], ((b_it / p.b_stages) & 1) ^ 1);
+                mbar_arrive_expect_tx(&b_full[sb], b_bytes);
+                tma_load_3d(b_buf + (size_t)sb * p.b_stage_bytes, &sg.tmB, &b_full[sb], ch * sg.kc, it.n0, tp);
+                ++b_it;
+              }
+            }
+          }
+        }
+        first_item = false;
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      uint32_t a_it = 0, b_it = 0, acc_it = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const uint32_t as = acc_it % AS;
+        mbar_wait(&acc_empty[as], ((acc_it / AS) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t acc_addr = tmem_base + as * (MT * BN);
+        uint32_t b_slot_res = 0;
+        uint32_t accumulate = 0;
+        for (int s = 0; s < p.nseg; ++s) {
+          const SegDev& sg = p.seg[s];
+          const uint32_t row_bytes = sg.kc * 2;
+          const uint32_t swz = sg.kc == 64 ? kSwizzle128B : kSwizzle64B;
+          const bool halo = sg.taps == 9;
+          const uint32_t pitch = halo ? p.halo_pitch : TW;
+          const uint32_t idesc = make_idesc_f16(sg.fmt, sg.fmt, 128, BN);
+          const int ksteps = sg.kc / 16;
+          for (int ch = 0; ch < sg.nchunks; ++ch) {
+            const uint32_t sa = a_it % p.a_stages;
+            mbar_wait(&a_full[sa], (a_it / p.a_stages) & 1);
+            tc_fence_after_sync();
+            const uint32_t a_addr = smem_u32(a_buf + (size_t)sa * p.a_stage_bytes);
+            for (int tp = 0; tp < sg.taps; ++tp) {
+              uint32_t sb;
+              if (p.b_resident) {
+                sb = b_slot_res++;
+                mbar_wait(&b_full[sb], 0);
+              } else {
+                sb = b_it % p.b_stages;
+                mbar_wait(&b_full[sb], (b_it / p.b_stages) & 1);
+              }
+              tc_fence_after_sync();
+              const uint32_t b_addr = smem_u32(b_buf + (size_t)sb * p.b_stage_bytes);
+              const uint32_t dy = halo ? tp / 3 : 0, dx = halo ? tp % 3 : 0;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint32_t a_tap = a_addr + ((mt * 16 + dy) * pitch + dx) * row_bytes;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                  const uint64_t da = make_smem_desc(a_tap + ks * 32, pitch * row_bytes, swz);
+                  const uint64_t db = make_smem_desc(b_addr + ks * 32, 8 * row_bytes, swz);
+                  umma_f16(acc_addr + mt * BN, da, db, idesc, accumulate | (uint32_t)(ks != 0));
+                }
+              }
+              accumulate = 1;
+              if (!p.b_resident) {
+                umma_commit(&b_empty[sb]);
+                ++b_it;
+              }
+            }
+            umma_commit(&a_empty[sa]);
+            ++a_it;
+          }
+        }
+        umma_commit(&acc_full[as]);
+        ++acc_it;
+      }
+    }
+  } else {
+    // =========================== epilogue ===========================
+    const int q = warp & 3;
+    const int hl = q * 4 + (lane >> 3);
+    const int wl = lane & 7;
+    const int Ho = p.H * p.up_h, Wo = p.W * p.up_w;
+    const int Hp = p.H / p.pool_h, Wp = p.W / p.pool_w;
+    const bool pooling = (p.pool_raw.ptr != nullptr) || (p.pool_act.ptr != nullptr);
+    const float pool_scale = 1.0f / (float)(p.pool_h * p.pool_w);
+    uint32_t acc_it = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      const Item it = decode_item<MT>(p, item, BN);
+      const uint32_t as = acc_it % AS;
+      mbar_wait(&acc_full[as], (acc_it / AS) & 1);
+      tc_fence_after_sync();
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+        const int h = it.h0 + mt * 16 + hl;
+        const int w = it.w0 + wl;
+        const bool valid = (h < p.H) && (w < p.W);
+        const uint32_t taddr = tmem_base + as * (MT * BN) + mt * BN + (static_cast<uint32_t>(q * 32) << 16);
+        float fa0 = 0.0f, fa1 = 0.0f, fa2 = 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 16) {
+          const int n = it.n0 + c0;
+          if (n >= p.ncols) break;
+          float v[16];
+          tmem_ld_x16(taddr + c0, v);
+          tmem_ld_wait();
+          if (p.bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 bb = __ldg(bp + j);
+              v[4 * j + 0] += bb.x;
+              v[4 * j + 1] += bb.y;
+              v[4 * j + 2] += bb.z;
+              v[4 * j + 3] += bb.w;
+            }
+          }
+          int c = n, ho = h, wo = w;
+          if (p.up_h * p.up_w > 1) {
+            const int g = n / p.group_c;
+            c = n - g * p.group_c;
+            const int dy = g / p.up_w;
+            ho = h * p.up_h + dy;
+            wo = w * p.up_w + (g - dy * p.up_w);
+          }
+          if (p.full_raw.ptr != nullptr) store16(p.full_raw, it.b, ho, wo, Ho, Wo, c, v, valid);
+          if (p.full_act.ptr != nullptr) store16(p.full_act, it.b, ho, wo, Ho, Wo, c, v, valid);
+          if (pooling) {
+            float s[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float t = v[j];
+              if (p.pool_w == 2) t += __shfl_xor_sync(0xffffffffu, t, 1);
+              if (p.pool_h == 2) t += __shfl_xor_sync(0xffffffffu, t, 8);
+              s[j] = t * pool_scale;
+            }
+            const bool owner = valid && ((wl & (p.pool_w - 1)) == 0) && ((hl & (p.pool_h - 1)) == 0);
+            if (p.pool_raw.ptr != nullptr) store16(p.pool_raw, it.b, h / p.pool_h, w / p.pool_w, Hp, Wp, c, s, owner);
+            if (p.pool_act.ptr != nullptr) store16(p.pool_act, it.b, h / p.pool_h, w / p.pool_w, Hp, Wp, c, s, owner);
+          }
+          if (p.after_w != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              fa0 = fmaf(__ldg(p.after_w + n + j), v[j], fa0);
+              fa1 = fmaf(__ldg(p.after_w + p.ncols + n + j), v[j], fa1);
+              fa2 = fmaf(__ldg(p.after_w + 2 * p.ncols + n + j), v[j], fa2);
+            }
+          }
+        }
+        if (p.after_w != nullptr && valid) {
+          const size_t plane = (size_t)p.H * p.W;
+          float* fp = p.feat + (size_t)it.b * 3 * plane + (size_t)h * p.W + w;
+          fp[0] = fa0 + __ldg(p.after_b + 0);
+          fp[plane] = fa1 + __ldg(p.after_b + 1);
+          fp[2 * plane] = fa2 + __ldg(p.after_b + 2);
+        }
+      }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      ++acc_it;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+typedef void (*ConvKernelFn)(const ConvParams);
+
+struct KernelChoice {
+  ConvKernelFn fn;
+  int BN, MT;
+};
+
+template <int BN, int MT>
+KernelChoice make_choice() {
+  return KernelChoice{conv_igemm_kernel<BN, MT>, BN, MT};
+}
+
+int g_halo_pitch = 10;   // 10 = dense halo tile; 16 = 1 KiB-aligned image rows (debug alternative)
+int g_num_sms = 0;
+
+}  // namespace
+
+struct ConvPrepared {
+  ConvParams params;
+  ConvKernelFn fn;
+  int grid;
+  size_t smem;
+};
+
+void conv_set_halo_pitch(int pitch) { g_halo_pitch = (pitch == 16) ? 16 : 10; }
+
+double conv_flops(const ConvLaunch& l) {
+  double k = 0;
+  for (int s = 0; s < l.nseg; ++s) k += (double)l.seg[s].cin * l.seg[s].taps;
+  return 2.0 * l.B * l.H * l.W * (double)l.ncols * k;
+}
+
+static void fill_out(OutDev& d, const ConvOut& o) {
+  d.ptr = o.ptr;
+  d.scale = o.scale;
+  d.shift = o.shift;
+  d.cstride = o.cstride;
+  d.coff = o.coff;
+  d.fp16 = o.fp16;
+  d.shift_bstride = o.shift_bstride;
+}
+
+static int check_out(const ConvOut& o, const char* name, int ncols_eff) {
+  if (!o.ptr) return 0;
+  if (o.cstride % 8 || o.coff % 8 || o.coff + ncols_eff > o.cstride)
+    return set_error(LASS_ERR_ARG, "conv: output %s has bad channel slice (cstride %d coff %d cols %d)", name, o.cstride,
+                     o.coff, ncols_eff);
+  if (reinterpret_cast<uintptr_t>(o.ptr) % 16) return set_error(LASS_ERR_ARG, "conv: output %s not 16 B aligned", name);
+  if ((o.scale == nullptr) != (o.shift == nullptr)) return set_error(LASS_ERR_ARG, "conv: output %s needs scale AND shift", name);
+  return 0;
+}
+
+int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
+  *out = nullptr;
+  if (l.B <= 0 || l.H <= 0 || l.W <= 0 || l.ncols <= 0 || l.ncols % 16 || l.nseg < 1 || l.nseg > 2)
+    return set_error(LASS_ERR_ARG, "conv: bad shape B=%d H=%d W=%d ncols=%d nseg=%d", l.B, l.H, l.W, l.ncols, l.nseg);
+  const int up = l.up_h * l.up_w;
+  if (l.up_h < 1 || l.up_w < 1 || l.up_h > 2 || l.up_w > 2 || l.group_c <= 0 || l.group_c % 16 || l.group_c * up != l.ncols)
+    return set_error(LASS_ERR_ARG, "conv: bad upsample spec up=(%d,%d) group_c=%d ncols=%d", l.up_h, l.up_w, l.group_c, l.ncols);
+  if ((l.pool_h != 1 && l.pool_h != 2) || (l.pool_w != 1 && l.pool_w != 2) || l.H % l.pool_h || l.W % l.pool_w)
+    return set_error(LASS_ERR_ARG, "conv: bad pooling (%d,%d) for %dx%d", l.pool_h, l.pool_w, l.H, l.W);
+  if ((l.pool_raw.ptr || l.pool_act.ptr) && up > 1) return set_error(LASS_ERR_ARG, "conv: pooling with upsampling");
+  if (l.after_w && (!l.after_b || !l.feat || l.ncols > 256 || up > 1))
+    return set_error(LASS_ERR_ARG, "conv: fused after_conv needs after_b, feat and a single N tile");
+  int e;
+  if ((e = check_out(l.full_raw, "full_raw", l.group_c))) return e;
+  if ((e = check_out(l.full_act, "full_act", l.group_c))) return e;
+  if ((e = check_out(l.pool_raw, "pool_raw", l.group_c))) return e;
+  if ((e = check_out(l.pool_act, "pool_act", l.group_c))) return e;
+
+  // ---- tile configuration ----
+  int BN;
+  if (l.ncols <= 32) BN = 32;
+  else if (l.ncols <= 64) BN = 64;
+  else if (l.ncols % 256 == 0) BN = 256;
+  else BN = 128;
+  int MT = (BN == 256) ? 1 : 2;
+  if (l.H < 32 || l.H % 32) MT = 1;
+  if (l.after_w && BN < l.ncols) return set_error(LASS_ERR_ARG, "conv: fused after_conv needs ncols <= BN");
+  KernelChoice kc;
+  if (BN == 32) kc = MT == 2 ? make_choice<32, 2>() : make_choice<32, 1>();
+  else if (BN == 64) kc = MT == 2 ? make_choice<64, 2>() : make_choice<64, 1>();
+  else if (BN == 128) kc = MT == 2 ? make_choice<128, 2>() : make_choice<128, 1>();
+  else kc = make_choice<256, 1>();
+
+  ConvPrepared* cp = new (std::nothrow) ConvPrepared();
+  if (!cp) return set_error(LASS_ERR_ARG, "conv: out of host memory");
+  ConvParams& p = cp->params;
+  memset(&p, 0, sizeof(p));
+  p.nseg = l.nseg;
+  p.B = l.B;
+  p.H = l.H;
+  p.W = l.W;
+  p.ncols = l.ncols;
+  p.halo_pitch = g_halo_pitch;
+  p.tiles_h = (l.H + 16 * MT - 1) / (16 * MT);
+  p.tiles_w = (l.W + TW - 1) / TW;
+  p.pix_tiles = l.B * p.tiles_h * p.tiles_w;
+  p.n_tiles = (l.ncols + BN - 1) / BN;
+  p.num_items = p.pix_tiles * p.n_tiles;
+  p.bias = l.bias;
+  p.up_h = l.up_h;
+  p.up_w = l.up_w;
+  p.group_c = l.group_c;
+  p.pool_h = l.pool_h;
+  p.pool_w = l.pool_w;
+  p.after_w = l.after_w;
+  p.after_b = l.after_b;
+  p.feat = l.feat;
+  fill_out(p.full_raw, l.full_raw);
+  fill_out(p.full_act, l.full_act);
+  fill_out(p.pool_raw, l.pool_raw);
+  fill_out(p.pool_act, l.pool_act);
+
+  uint32_t a_stage = 0, b_stage = 0;
+  int b_tiles_per_item = 0;
+  for (int s = 0; s < l.nseg; ++s) {
+    const ConvSegment& sg = l.seg[s];
+    if (!sg.src || !sg.weights || (sg.kc != 32 && sg.kc != 64) || sg.cin <= 0 || sg.cin % sg.kc ||
+        (sg.taps != 9 && sg.taps != 1) || sg.src_cstride % 8 || sg.src_coff % 8 || sg.src_coff + sg.cin > sg.src_cstride) {
+      delete cp;
+      return set_error(LASS_ERR_ARG, "conv: bad segment %d (cin %d kc %d taps %d cstride %d coff %d)", s, sg.cin, sg.kc,
+                       sg.taps, sg.src_cstride, sg.src_coff);
+    }
+    SegDev& d = p.seg[s];
+    d.nchunks = sg.cin / sg.kc;
+    d.taps = sg.taps;
+    d.kc = sg.kc;
+    d.fmt = sg.fp16 ? kFmtF16 : kFmtBF16;
+    const CUtensorMapSwizzle swz = sg.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const bool halo = sg.taps == 9;
+    {
+      const char* base = reinterpret_cast<const char*>(sg.src) + (size_t)sg.src_coff * 2;
+      uint64_t dims[4] = {(uint64_t)sg.cin, (uint64_t)l.W, (uint64_t)l.H, (uint64_t)l.B};
+      uint64_t strides[3] = {(uint64_t)sg.src_cstride * 2, (uint64_t)sg.src_cstride * 2 * l.W,
+                             (uint64_t)sg.src_cstride * 2 * l.W * l.H};
+      uint32_t box[4] = {(uint32_t)sg.kc, (uint32_t)(halo ? p.halo_pitch : TW), (uint32_t)(halo ? 16 * MT + 2 : 16 * MT), 1};
+      if ((e = make_tensor_map(&d.tmA, base, 2, 4, dims, strides, box, swz))) {
+        delete cp;
+        return e;
+      }
+    }
+    {
+      uint64_t dims[3] = {(uint64_t)sg.cin, (uint64_t)l.ncols, (uint64_t)sg.taps};
+      uint64_t strides[2] = {(uint64_t)sg.cin * 2, (uint64_t)sg.cin * 2 * l.ncols};
+      uint32_t box[3] = {(uint32_t)sg.kc, (uint32_t)BN, 1};
+      if ((e = make_tensor_map(&d.tmB, sg.weights, 2, 3, dims, strides, box, swz))) {
+        delete cp;
+        return e;
+      }
+    }
+    const uint32_t row_bytes = sg.kc * 2;
+    const uint32_t a_bytes = halo ? (16 * MT + 2) * p.halo_pitch * row_bytes : 16 * MT * TW * row_bytes;
+    if (a_bytes > a_stage) a_stage = a_bytes;
+    if (BN * row_bytes > b_stage) b_stage = BN * row_bytes;
+    b_tiles_per_item += d.nchunks * d.taps;
+  }
+  p.a_stage_bytes = (a_stage + 1023u) & ~1023u;
+  p.b_stage_bytes = (b_stage + 1023u) & ~1023u;
+
+  // ---- shared-memory budget: weights resident if every tile of an item fits, else a streaming ring ----
+  const size_t kBudget = 220 * 1024;
+  const size_t fixed = 1024 /*alignment slack*/ + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64;
+  const size_t min_a = 2 * (size_t)p.a_stage_bytes;
+  p.b_resident = (p.n_tiles == 1 && b_tiles_per_item <= kMaxB &&
+                  fixed + min_a + (size_t)b_tiles_per_item * p.b_stage_bytes <= kBudget)
+                     ? 1
+                     : 0;
+  if (p.b_resident) {
+    p.b_stages = b_tiles_per_item;
+    size_t rest = kBudget - fixed - (size_t)p.b_stages * p.b_stage_bytes;
+    p.a_stages = (int)(rest / p.a_stage_bytes);
+    if (p.a_stages > 4) p.a_stages = 4;
+  } else {
+    p.a_stages = 2;
+    size_t rest = kBudget - fixed - (size_t)p.a_stages * p.a_stage_bytes;
+    p.b_stages = (int)(rest / p.b_stage_bytes);
+    if (p.b_stages > 12) p.b_stages = 12;
+    if (p.b_stages < 2) {
+      delete cp;
+      return set_error(LASS_ERR_ARG, "conv: tile does not fit in shared memory");
+    }
+  }
+  cp->smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes;
+  cp->fn = kc.fn;
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
+  }
+  // TMEM: AS * MT * BN columns per CTA; co-resident CTAs must fit in 512 columns and in shared memory
+  const int tmem_cols = ((2 * MT * BN <= 512) ? 2 : 1) * MT * BN;
+  int per_sm = 1;
+  if (cp->smem * 2 + 2048 <= 227 * 1024 && tmem_cols * 2 <= 512) per_sm = 2;
+  cp->grid = p.num_items < g_num_sms * per_sm ? p.num_items : g_num_sms * per_sm;
+  cudaError_t ce = cudaFuncSetAttribute(reinterpret_cast<const void*>(kc.fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp->smem);
+  if (ce != cudaSuccess) {
+    delete cp;
+    return set_cuda_error(ce, "conv smem attribute");
+  }
+  *out = cp;
+  return 0;
+}
+
+int conv_run(const ConvPrepared* cp, cudaStream_t stream) {
+  cp->fn<<<cp->grid, kThreads, cp->smem, stream>>>(cp->params);
+  return set_cuda_error(cudaGetLastError(), "conv launch");
+}
+
+void conv_free(ConvPrepared* p) { delete p; }
+
+}  // namespace lass

@@ -3,6 +3,8 @@
 These are the per-kernel entry points used by the module in ``lass_b200.models.resunet`` and by the parity
 tests.  Every function requires CUDA tensors and raises otherwise — there is no CPU path.
 """
+import ctypes
+
 import torch
 
 from . import _cabi
@@ -70,3 +72,64 @@ def umma_probe(A: torch.Tensor, Bm: torch.Tensor, swizzle_mode: int, a_start_byt
                                           a_base_offset, b_sbo, 1 if A.dtype == torch.float16 else 0, _ptr(out),
                                           _stream()))
     return out
+
+
+def make_segment(src: torch.Tensor, coff: int, cin: int, weights: torch.Tensor, taps: int):
+    """src (B, H, W, Cbuf) 16-bit NHWC; weights (taps, ncols, cin) of the same dtype."""
+    _require_cuda(src, weights)
+    assert src.dtype in (torch.bfloat16, torch.float16) and weights.dtype == src.dtype
+    assert weights.shape[0] == taps and weights.shape[2] == cin
+    seg = _cabi.ConvSegment()
+    seg.src = _ptr(src)
+    seg.src_cstride = src.shape[3]
+    seg.src_coff = coff
+    seg.cin = cin
+    seg.kc = 64 if cin % 64 == 0 else 32
+    seg.taps = taps
+    seg.fp16 = 1 if src.dtype == torch.float16 else 0
+    seg.weights = _ptr(weights)
+    return seg
+
+
+def make_out(dst: torch.Tensor = None, coff: int = 0, scale: torch.Tensor = None, shift: torch.Tensor = None):
+    """dst (B, Ho, Wo, Cbuf) 16-bit NHWC (fp16 -> saturating raw store, bf16 otherwise); optional activation
+    lrelu(scale[c]*v + shift[b, c]) with shift a (B, J) table view starting at this layer's first column."""
+    o = _cabi.ConvOut()
+    if dst is None:
+        return o
+    _require_cuda(dst)
+    o.ptr = _ptr(dst)
+    o.cstride = dst.shape[3]
+    o.coff = coff
+    o.fp16 = 1 if dst.dtype == torch.float16 else 0
+    if scale is not None:
+        assert scale.is_cuda and shift.is_cuda and scale.dtype == torch.float32 and shift.dtype == torch.float32
+        o.scale = _ptr(scale)
+        o.shift = _ptr(shift)
+        o.shift_bstride = shift.stride(0)
+    return o
+
+
+def conv_igemm(B, H, W, ncols, segments, bias=None, up=(1, 1), full_raw=None, full_act=None, pool=(1, 1),
+               pool_raw=None, pool_act=None, after_w=None, after_b=None, feat=None):
+    lib = _cabi.load()
+    d = _cabi.ConvDesc()
+    d.B, d.H, d.W, d.ncols, d.nseg = B, H, W, ncols, len(segments)
+    for i, s in enumerate(segments):
+        d.seg[i] = s
+    d.bias = _ptr(bias) if bias is not None else None
+    d.up_h, d.up_w = up
+    d.group_c = ncols // (up[0] * up[1])
+    d.full_raw = full_raw if full_raw is not None else _cabi.ConvOut()
+    d.full_act = full_act if full_act is not None else _cabi.ConvOut()
+    d.pool_h, d.pool_w = pool
+    d.pool_raw = pool_raw if pool_raw is not None else _cabi.ConvOut()
+    d.pool_act = pool_act if pool_act is not None else _cabi.ConvOut()
+    d.after_w = _ptr(after_w) if after_w is not None else None
+    d.after_b = _ptr(after_b) if after_b is not None else None
+    d.feat = _ptr(feat) if feat is not None else None
+    _cabi.check(lib.lass_conv_igemm(ctypes.byref(d), _stream()))
+
+
+def set_halo_pitch(pitch: int):
+    _cabi.check(_cabi.load().lass_debug_set_halo_pitch(pitch))

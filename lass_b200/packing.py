@@ -53,3 +53,16 @@ def istft_tables(n_fft: int, win_length: int = None, device=None):
     ang = 2.0 * math.pi * j / n_fft
     tw = torch.stack((torch.cos(ang), torch.sin(ang)), dim=-1).to(torch.float32)
     return w.contiguous(), tw.contiguous()
+
+
+def pack_conv_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """conv2d weight (Cout, Cin, kh, kw) -> (kh*kw, Cout, Cin) K-major 16-bit (tap = ky*kw + kx)."""
+    cout, cin, kh, kw = w.shape
+    return w.permute(2, 3, 0, 1).reshape(kh * kw, cout, cin).to(dtype).contiguous()
+
+
+def pack_convT_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
+    """conv_transpose2d weight (Cin, Cout, sh, sw) with kernel = stride -> (1, sh*sw*Cout, Cin):
+    GEMM column n = (dy*sw + dx)*Cout + co."""
+    cin, cout, sh, sw = w.shape
+    return w.permute(2, 3, 1, 0).reshape(1, sh * sw * cout, cin).to(dtype).contiguous()

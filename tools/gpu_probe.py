@@ -18,8 +18,13 @@ os.makedirs(OUT, exist_ok=True)
 report = {}
 
 
+WANT = sys.argv[1:]  # section names; empty = all
+
+
 def section(name):
     def deco(fn):
+        if WANT and name not in WANT and name != "env":
+            return fn
         t0 = time.time()
         try:
             report[name] = fn()
@@ -42,7 +47,10 @@ def _err(out, ref):
     return float((out - ref).abs().max())
 
 
-@section("umma_probe")
+RISKY = "umma_probe_risky" in WANT
+
+
+@section("umma_probe_risky" if RISKY else "umma_probe")
 def _probe():
     from lass_b200 import ops
     res = {}
@@ -70,6 +78,14 @@ def _probe():
                 rows = (idx // 8) * 16 + idx % 8
                 out = ops.umma_probe(A, Bm, sw, 0, 2 * atom, 0, atom)
                 res[key + "_sbo2"] = _err(out, full[rows])
+                # dense halo pitch: 10-row groups (SBO = 10 rows), start shifted by dx rows
+                rows10 = (idx // 8) * 10 + idx % 8
+                for dx in (0, 1, 2, 11, 22):
+                    if int(rows10.max()) + dx < 256:
+                        out = ops.umma_probe(A, Bm, sw, rowb * dx, 10 * rowb, 0, atom)
+                        res[key + "_pitch10_shift%d" % dx] = _err(out, full[rows10 + dx])
+                if not RISKY:
+                    continue
                 # E2/E3 row shifts (start address moved by dx rows) with base_offset 0 or dx
                 for dx in (1, 2, 3, 7):
                     for bo in (0, dx):
@@ -155,7 +171,7 @@ def _istft():
               "base.istft.conv_real.weight": istft.conv_real.weight.data, "base.istft.conv_imag.weight": istft.conv_imag.weight.data,
               "base.istft.ola_window": istft.ola_window}
         with torch.no_grad():
-            mag, cos, sin = O.stft_mag_phase(sd, wave, n_fft, hop)
+            mag, cos, sin = [t.contiguous() for t in O.stft_mag_phase(sd, wave, n_fft, hop)]
             g = torch.Generator().manual_seed(7)
             feat = torch.randn(B, 3, mag.shape[2], mag.shape[3], generator=g)
             feat[:, :, :, -1] = 0.0   # models/resunet.py:573 zero Nyquist column
@@ -196,6 +212,6 @@ def _istft():
     return res
 
 
-with open(os.path.join(OUT, "probe.json"), "w") as f:
+with open(os.path.join(OUT, "probe_%s.json" % ("_".join(WANT) or "all")), "w") as f:
     json.dump(report, f, indent=1, default=str)
 print("probe done")
