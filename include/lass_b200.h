@@ -134,6 +134,87 @@ LASS_API int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream);
 LASS_API int lass_debug_set_halo_pitch(int pitch);
 
 /* ------------------------------------------------------------------------------------------------------
+ * K2  FiLM: all FiLM linears of the model (reference models/resunet.py:59-81) with the eval-mode BatchNorm
+ *     shift folded into the bias, as one skinny fp32 GEMM:
+ *        shift[b][j] = film_b[j] + sum_k condition[b][k] * film_w[j][k]         (B, J)
+ *     The conv epilogues then apply leaky_relu(act_scale[j] * x + shift[b][j]).
+ * ---------------------------------------------------------------------------------------------------- */
+LASS_API int lass_film(const float* condition, const float* film_w, const float* film_b, int B, int condition_size,
+                       int J, float* shift_out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Whole-model entry: ResUNet30.forward for input_channels = output_channels = 1 in eval mode
+ * (reference models/resunet.py:522-595,640-653).
+ *
+ * Row order of the FiLM / activation table (J = 8256 rows for condition -> beta; the six dead
+ * `decoder_blockN->beta2` linears are skipped): for encoder block k = 0..6 (encoder_block1..6, conv_block7a):
+ * [conv_block1.bn1 (cin_k), conv_block1.bn2 (cout_k)]; then for decoder block j = 0..5:
+ * [bn1 (cin_j), conv_block2.bn1 (2*cout_j), conv_block2.bn2 (cout_j)].  lass_resunet30_film_offset() returns the
+ * first row of a site: site = 2*k + {0,1} for the encoder, 14 + 3*j + {0,1,2} for the decoder.
+ * Channels: encoder cin = {32,32,64,128,256,384,384}, cout = {32,64,128,256,384,384,384};
+ *           decoder cin = {384,384,384,256,128,64}, cout = {384,384,256,128,64,32}.
+ *
+ * Conv weights are 16-bit, packed (taps, ncols, cin): 3x3 convs bf16 with tap = ky*3+kx; transposed convs bf16
+ * with column (dy*sw + dx)*cout + co; shortcut (1x1) weights fp16 — an identity matrix where the reference has
+ * no shortcut conv (cin == cout).
+ * ---------------------------------------------------------------------------------------------------- */
+typedef struct lass_resunet30_weights {
+  int n_fft, hop, condition_size, film_rows;
+  const void* stft_basis_hi;   /* bf16 (lass_stft_basis_rows(n_fft), n_fft) */
+  const void* stft_basis_lo;
+  const float* istft_window;   /* (n_fft) */
+  const float* istft_twiddle;  /* (n_fft, 2) */
+  const float* bn0_scale;      /* (n_fft/2 + 1) folded bn0: scale, shift */
+  const float* bn0_shift;
+  const float* pre_w;          /* (32) pre_conv weight, bias */
+  const float* pre_b;
+  const float* film_w;         /* (film_rows, condition_size) */
+  const float* film_b;         /* (film_rows)  FiLM bias + folded BN shift */
+  const float* act_scale;      /* (film_rows)  folded BN scale */
+  struct {
+    const void* conv1_w;       /* bf16 (9, cout, cin) */
+    const void* conv2_w;       /* bf16 (9, cout, cout) */
+    const void* sc_w;          /* fp16 (1, cout, cin) shortcut or identity */
+    const float* sc_b;         /* (cout) or NULL */
+  } enc[7];
+  struct {
+    const void* up_w;          /* bf16 (1, sh*sw*cout, cin) */
+    const void* conv1_w;       /* bf16 (9, cout, 2*cout) */
+    const void* conv2_w;       /* bf16 (9, cout, cout) */
+    const void* sc_w;          /* fp16 (1, cout, 2*cout) */
+    const float* sc_b;         /* (cout) */
+  } dec[6];
+  const float* after_w;        /* (3, 32) */
+  const float* after_b;        /* (3) */
+} lass_resunet30_weights;
+
+typedef struct lass_plan lass_plan;
+
+LASS_API int lass_resunet30_film_rows(void);
+LASS_API int lass_resunet30_film_offset(int site);
+/* Bytes of device workspace a plan for (B clips of L samples) needs. */
+LASS_API size_t lass_resunet30_workspace_bytes(int B, int L, int n_fft, int hop);
+/* Build a plan (host object: tensor maps, launch list).  `weights_host` is copied; the device buffers it points
+ * to and `workspace` must stay valid for the plan's lifetime.  workspace: 1024-byte aligned. */
+LASS_API int lass_resunet30_plan_create(const lass_resunet30_weights* weights_host, int B, int L, void* workspace,
+                                        size_t workspace_bytes, lass_plan** plan_out);
+/* mixture (B, 1, L) fp32, condition (B, condition_size) fp32 -> waveform (B, 1, L) fp32.
+ * shift_override: NULL, or a (B, film_rows) fp32 table of precomputed activation shifts (folded BN shift + FiLM
+ *   beta) that replaces the FiLM GEMM — the `base(mixtures=, film_dict=)` call of the reference
+ *   (models/resunet.py:685-688); `condition` may then be NULL.
+ * stft_precision_mode: 0 = fp32-parity STFT, 1 = single-pass bf16 STFT.  Asynchronous on `stream`. */
+LASS_API int lass_resunet30_forward(lass_plan* plan, const float* mixture, const float* condition,
+                                    const float* shift_override, float* waveform, int stft_precision_mode,
+                                    void* stream);
+/* Number of kernel launches one lass_resunet30_forward issues. */
+LASS_API int lass_resunet30_num_launches(const lass_plan* plan);
+/* Debug / test access to intermediates in the workspace: name in {"mag","cos","sin","shift","feat",
+ * "x_raw0".."x_raw6","x_act0".."x_act6","a2_0".."a2_6","cat_raw0".."cat_raw5","cat_act0".."cat_act5",
+ * "d_act1".."d_act6"}; returns a device pointer or NULL; dims = {d0,d1,d2,d3} elements, *elem_bytes 2 or 4. */
+LASS_API void* lass_resunet30_buffer(const lass_plan* plan, const char* name, int dims[4], int* elem_bytes);
+LASS_API void lass_resunet30_plan_destroy(lass_plan* plan);
+
+/* ------------------------------------------------------------------------------------------------------
  * Debug: one tcgen05.mma tile (M = 128) with caller-controlled shared-memory descriptors; used by the GPU
  * tests to pin the descriptor rules the conv kernel relies on.  A (a_rows, kc) and Bm (n, kc) are 16-bit
  * K-major; out (128, n) fp32.  swizzle_mode: 0 none, 2 = 128 B, 4 = 64 B, 6 = 32 B.

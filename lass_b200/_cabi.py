@@ -93,3 +93,47 @@ class ConvDesc(ctypes.Structure):
 
 SIGNATURES["lass_conv_igemm"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p])
 SIGNATURES["lass_debug_set_halo_pitch"] = (c_int, [c_int])
+
+
+# ---- whole-model entry (lass_resunet30_*) ----
+class _EncW(ctypes.Structure):
+    _fields_ = [("conv1_w", ctypes.c_void_p), ("conv2_w", ctypes.c_void_p), ("sc_w", ctypes.c_void_p),
+                ("sc_b", ctypes.c_void_p)]
+
+
+class _DecW(ctypes.Structure):
+    _fields_ = [("up_w", ctypes.c_void_p), ("conv1_w", ctypes.c_void_p), ("conv2_w", ctypes.c_void_p),
+                ("sc_w", ctypes.c_void_p), ("sc_b", ctypes.c_void_p)]
+
+
+class ResUNet30Weights(ctypes.Structure):
+    """Mirror of ``lass_resunet30_weights``."""
+    _fields_ = [("n_fft", ctypes.c_int), ("hop", ctypes.c_int), ("condition_size", ctypes.c_int),
+                ("film_rows", ctypes.c_int),
+                ("stft_basis_hi", ctypes.c_void_p), ("stft_basis_lo", ctypes.c_void_p),
+                ("istft_window", ctypes.c_void_p), ("istft_twiddle", ctypes.c_void_p),
+                ("bn0_scale", ctypes.c_void_p), ("bn0_shift", ctypes.c_void_p),
+                ("pre_w", ctypes.c_void_p), ("pre_b", ctypes.c_void_p),
+                ("film_w", ctypes.c_void_p), ("film_b", ctypes.c_void_p), ("act_scale", ctypes.c_void_p),
+                ("enc", _EncW * 7), ("dec", _DecW * 6),
+                ("after_w", ctypes.c_void_p), ("after_b", ctypes.c_void_p)]
+
+
+SIGNATURES.update({
+    "lass_film": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                 ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
+    "lass_resunet30_film_rows": (ctypes.c_int, []),
+    "lass_resunet30_film_offset": (ctypes.c_int, [ctypes.c_int]),
+    "lass_resunet30_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "lass_resunet30_plan_create": (ctypes.c_int, [ctypes.POINTER(ResUNet30Weights), ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_void_p, ctypes.c_size_t,
+                                                  ctypes.POINTER(ctypes.c_void_p)]),
+    "lass_resunet30_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                              ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "lass_resunet30_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
+    "lass_resunet30_buffer": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int * 4),
+                                                ctypes.POINTER(ctypes.c_int)]),
+    "lass_resunet30_plan_destroy": (None, [ctypes.c_void_p]),
+})
+
+

@@ -566,7 +566,9 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   int per_sm = 1;
   if (cp->smem * 2 + 2048 <= 227 * 1024 && tmem_cols * 2 <= 512) per_sm = 2;
   cp->grid = p.num_items < g_num_sms * per_sm ? p.num_items : g_num_sms * per_sm;
-  cudaError_t ce = cudaFuncSetAttribute(reinterpret_cast<const void*>(kc.fn), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cp->smem);
+  // opt every instantiation in to the full 227 KiB once (a later, smaller request must not lower the limit that
+  // an already prepared launch of the same kernel relies on)
+  cudaError_t ce = cudaFuncSetAttribute(reinterpret_cast<const void*>(kc.fn), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (ce != cudaSuccess) {
     delete cp;
     return set_cuda_error(ce, "conv smem attribute");

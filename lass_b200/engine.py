@@ -1,0 +1,266 @@
+"""Host-side driver of the whole-model C-ABI entry (``lass_resunet30_*`` in ``include/lass_b200.h``).
+
+* packs the module's parameters into the kernel layouts (BatchNorm folded to scale/shift, FiLM linears concatenated
+  into one GEMM with the BN shift folded into its bias, conv weights to (taps, cout, cin) bf16, shortcuts to fp16,
+  DFT basis split hi/lo) — re-packed automatically when any parameter's version counter changes;
+* caches one plan (tensor maps + launch list + workspace) per (batch, length);
+* runs the forward on the current CUDA stream.  No CPU path: inputs must be CUDA tensors.
+"""
+import ctypes
+
+import torch
+
+from . import _cabi, packing
+
+_ENC = ("encoder_block1", "encoder_block2", "encoder_block3", "encoder_block4", "encoder_block5", "encoder_block6",
+        "conv_block7a")
+_DEC = ("decoder_block1", "decoder_block2", "decoder_block3", "decoder_block4", "decoder_block5", "decoder_block6")
+BN_EPS = 1e-5
+
+
+def fold_bn(bn: torch.nn.BatchNorm2d):
+    """eval-mode BatchNorm -> (scale, shift): y = scale * x + shift."""
+    scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
+    shift = bn.bias.detach().float() - bn.running_mean.detach().float() * scale
+    return scale, shift
+
+
+def film_sites(base):
+    """[(bn module, FiLM layer name, channel count)] in the row order of ``include/lass_b200.h``."""
+    sites = []
+    for name in _ENC:
+        cb = getattr(base, name).conv_block1
+        sites.append((cb.bn1, "%s->conv_block1->beta1" % name))
+        sites.append((cb.bn2, "%s->conv_block1->beta2" % name))
+    for name in _DEC:
+        blk = getattr(base, name)
+        sites.append((blk.bn1, "%s->beta1" % name))
+        sites.append((blk.conv_block2.bn1, "%s->conv_block2->beta1" % name))
+        sites.append((blk.conv_block2.bn2, "%s->conv_block2->beta2" % name))
+    return sites
+
+
+class _Plan:
+    def __init__(self, handle, workspace, B, L):
+        self.handle, self.workspace, self.B, self.L = handle, workspace, B, L
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _cabi.load().lass_resunet30_plan_destroy(self.handle)
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, base, film):
+        self.base = base
+        self.film = film
+        self._packed = None
+        self._packed_key = None
+        self._plans = {}
+        self.stft_precision_mode = 0
+
+    # ------------------------------------------------------------------ packing
+    def _version_key(self, device):
+        mods = [self.base] + ([self.film] if self.film is not None else [])
+        key = [str(device)]
+        for m in mods:
+            for t in list(m.parameters()) + list(m.buffers()):
+                key.append((t.data_ptr(), t._version))
+        return tuple(key)
+
+    def _pack(self, device):
+        base = self.base
+        if base.input_channels != 1 or base.output_channels != 1:
+            raise NotImplementedError("the B200 path implements input_channels == output_channels == 1 "
+                                      "(reference config/audiosep_base.yaml:25-28)")
+        lib = _cabi.load()
+        keep = {}
+
+        def dev(t, dtype=torch.float32):
+            return t.detach().to(device=device, dtype=dtype).contiguous()
+
+        w = _cabi.ResUNet30Weights()
+        w.n_fft, w.hop = base.window_size, base.hop_size
+        hi, lo = packing.pack_stft_basis(dev(base.stft.conv_real.weight), dev(base.stft.conv_imag.weight))
+        keep["basis"] = (hi, lo)
+        win, tw = packing.istft_tables(base.window_size, device=device)
+        keep["istft"] = (win, tw)
+        s0, b0 = fold_bn(base.bn0)
+        keep["bn0"] = (dev(s0), dev(b0))
+        keep["pre"] = (dev(base.pre_conv.weight.reshape(-1)), dev(base.pre_conv.bias))
+        # FiLM GEMM + folded BN
+        sites = film_sites(base)
+        rows = lib.lass_resunet30_film_rows()
+        scales, biases, weights = [], [], []
+        cond = None
+        for i, (bn, film_name) in enumerate(sites):
+            assert lib.lass_resunet30_film_offset(i) == sum(x.numel() for x in scales), "FiLM row order mismatch"
+            sc, sh = fold_bn(bn)
+            scales.append(dev(sc))
+            if self.film is not None:
+                lin = getattr(self.film, film_name)
+                cond = lin.in_features
+                weights.append(dev(lin.weight))
+                biases.append(dev(lin.bias) + dev(sh))
+            else:
+                biases.append(dev(sh))
+        act_scale = torch.cat(scales)
+        film_b = torch.cat(biases)
+        assert act_scale.numel() == rows
+        if self.film is not None:
+            film_w = torch.cat(weights, dim=0).contiguous()
+        else:
+            cond = 1
+            film_w = torch.zeros(rows, 1, device=device)
+        keep["film"] = (film_w, film_b, act_scale)
+        w.condition_size, w.film_rows = cond, rows
+        w.stft_basis_hi, w.stft_basis_lo = hi.data_ptr(), lo.data_ptr()
+        w.istft_window, w.istft_twiddle = win.data_ptr(), tw.data_ptr()
+        w.bn0_scale, w.bn0_shift = keep["bn0"][0].data_ptr(), keep["bn0"][1].data_ptr()
+        w.pre_w, w.pre_b = keep["pre"][0].data_ptr(), keep["pre"][1].data_ptr()
+        w.film_w, w.film_b, w.act_scale = film_w.data_ptr(), film_b.data_ptr(), act_scale.data_ptr()
+
+        def block_weights(cb, cin, cout):
+            c1 = packing.pack_conv_weight(dev(cb.conv1.weight), torch.bfloat16)
+            c2 = packing.pack_conv_weight(dev(cb.conv2.weight), torch.bfloat16)
+            if cb.is_shortcut:
+                sc = packing.pack_conv_weight(dev(cb.shortcut.weight), torch.float16)
+                sb = dev(cb.shortcut.bias)
+            else:
+                sc = torch.eye(cout, cin, device=device, dtype=torch.float16).reshape(1, cout, cin).contiguous()
+                sb = None
+            return c1, c2, sc, sb
+
+        for k, name in enumerate(_ENC):
+            cb = getattr(base, name).conv_block1
+            c1, c2, sc, sb = block_weights(cb, cb.conv1.in_channels, cb.conv1.out_channels)
+            keep["enc%d" % k] = (c1, c2, sc, sb)
+            w.enc[k].conv1_w, w.enc[k].conv2_w, w.enc[k].sc_w = c1.data_ptr(), c2.data_ptr(), sc.data_ptr()
+            w.enc[k].sc_b = sb.data_ptr() if sb is not None else None
+        for j, name in enumerate(_DEC):
+            blk = getattr(base, name)
+            up = packing.pack_convT_weight(dev(blk.conv1.weight), torch.bfloat16)
+            cb = blk.conv_block2
+            c1, c2, sc, sb = block_weights(cb, cb.conv1.in_channels, cb.conv1.out_channels)
+            keep["dec%d" % j] = (up, c1, c2, sc, sb)
+            w.dec[j].up_w, w.dec[j].conv1_w, w.dec[j].conv2_w = up.data_ptr(), c1.data_ptr(), c2.data_ptr()
+            w.dec[j].sc_w = sc.data_ptr()
+            w.dec[j].sc_b = sb.data_ptr() if sb is not None else None
+        keep["after"] = (dev(base.after_conv.weight.reshape(3, 32)), dev(base.after_conv.bias))
+        w.after_w, w.after_b = keep["after"][0].data_ptr(), keep["after"][1].data_ptr()
+        keep["struct"] = w
+        keep["bn_shift_rows"] = None
+        return keep
+
+    def _get_packed(self, device):
+        key = self._version_key(device)
+        if self._packed is None or key != self._packed_key:
+            self._packed = self._pack(device)
+            self._packed_key = key
+            self._plans = {}          # plans hold pointers into the packed weights
+        return self._packed
+
+    # ------------------------------------------------------------------ plans
+    def _get_plan(self, B, L, device):
+        packed = self._get_packed(device)
+        plan = self._plans.get((B, L))
+        if plan is not None:
+            return plan
+        lib = _cabi.load()
+        need = lib.lass_resunet30_workspace_bytes(B, L, self.base.window_size, self.base.hop_size)
+        if need == 0:
+            raise ValueError("unsupported geometry: B=%d L=%d n_fft=%d hop=%d (need L > n_fft/2, hop %% 8 == 0)"
+                             % (B, L, self.base.window_size, self.base.hop_size))
+        # one workspace shared by all plans of this engine (plans run one at a time on a stream)
+        ws = getattr(self, "_ws", None)
+        if ws is None or ws.numel() < need or ws.device != device:
+            self._plans = {}
+            ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
+            self._ws = ws
+        base_ptr = (ws.data_ptr() + 1023) // 1024 * 1024
+        handle = ctypes.c_void_p()
+        _cabi.check(lib.lass_resunet30_plan_create(ctypes.byref(packed["struct"]), B, L, base_ptr,
+                                                   ws.numel() - (base_ptr - ws.data_ptr()), ctypes.byref(handle)))
+        plan = _Plan(handle, ws, B, L)
+        if len(self._plans) > 8:
+            self._plans.pop(next(iter(self._plans)))
+        self._plans[(B, L)] = plan
+        return plan
+
+    # ------------------------------------------------------------------ forward
+    def _check_inputs(self, mixtures):
+        if self.base.training:
+            raise NotImplementedError(
+                "lass_b200 implements the eval-mode separation forward; training-mode forward (batch-statistics "
+                "BatchNorm + autograd) is the next tier (SURVEY.md §8f). Call .eval() first.")
+        if not mixtures.is_cuda:
+            raise RuntimeError("lass_b200 has no CPU path: move the module and its inputs to a CUDA device")
+        if mixtures.dim() != 3 or mixtures.shape[1] != 1:
+            raise ValueError("mixture must be (batch, 1, samples); got %s" % (tuple(mixtures.shape),))
+
+    @torch.no_grad()
+    def forward(self, mixtures, conditions):
+        self._check_inputs(mixtures)
+        B, _, L = mixtures.shape
+        device = mixtures.device
+        plan = self._get_plan(B, L, device)
+        x = mixtures.detach().to(torch.float32).contiguous()
+        c = conditions.detach().to(device=device, dtype=torch.float32).contiguous()
+        if c.shape != (B, self._packed["struct"].condition_size):
+            raise ValueError("condition must be (batch, %d); got %s" % (self._packed["struct"].condition_size,
+                                                                       tuple(c.shape)))
+        out = torch.empty(B, 1, L, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _cabi.check(_cabi.load().lass_resunet30_forward(plan.handle, x.data_ptr(), c.data_ptr(), None,
+                                                            out.data_ptr(), self.stft_precision_mode,
+                                                            torch.cuda.current_stream().cuda_stream))
+        return out
+
+    @torch.no_grad()
+    def forward_film_dict(self, mixtures, film_dict):
+        """``base(mixtures=, film_dict=)``: betas supplied by the caller (reference models/resunet.py:685-688)."""
+        self._check_inputs(mixtures)
+        B, _, L = mixtures.shape
+        device = mixtures.device
+        plan = self._get_plan(B, L, device)
+        packed = self._packed
+        if self.film is not None:
+            raise RuntimeError("engine built with a FiLM module; use forward()")
+        betas = []
+        for name in _ENC:
+            d = film_dict[name]["conv_block1"]
+            betas += [d["beta1"], d["beta2"]]
+        for name in _DEC:
+            d = film_dict[name]
+            betas += [d["beta1"], d["conv_block2"]["beta1"], d["conv_block2"]["beta2"]]
+        beta = torch.cat([b.reshape(b.shape[0], -1).to(device=device, dtype=torch.float32).expand(B, -1)
+                          for b in betas], dim=1)
+        shift = (beta + packed["film"][1][None, :]).contiguous()      # + folded BN shift
+        x = mixtures.detach().to(torch.float32).contiguous()
+        out = torch.empty(B, 1, L, dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _cabi.check(_cabi.load().lass_resunet30_forward(plan.handle, x.data_ptr(), None, shift.data_ptr(),
+                                                            out.data_ptr(), self.stft_precision_mode,
+                                                            torch.cuda.current_stream().cuda_stream))
+        return out
+
+    def num_launches(self, B, L, device):
+        return _cabi.load().lass_resunet30_num_launches(self._get_plan(B, L, device).handle)
+
+    def debug_buffer(self, B, L, device, name):
+        """Intermediate tensor of the last forward with this (B, L) — a COPY, for tests."""
+        plan = self._get_plan(B, L, device)
+        dims = (ctypes.c_int * 4)()
+        eb = ctypes.c_int()
+        ptr = _cabi.load().lass_resunet30_buffer(plan.handle, name.encode(), ctypes.byref(dims), ctypes.byref(eb))
+        if not ptr:
+            raise KeyError(name)
+        off = ptr - plan.workspace.data_ptr()
+        n = dims[0] * dims[1] * dims[2] * dims[3] * eb.value
+        raw = plan.workspace[off:off + n].clone()
+        if eb.value == 4:
+            return raw.view(torch.float32).reshape(*dims)
+        dt = torch.float16 if (name.startswith("x_raw") or name.startswith("cat_raw")) else torch.bfloat16
+        return raw.view(dt).reshape(*dims)
