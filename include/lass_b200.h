@@ -202,10 +202,22 @@ LASS_API int lass_resunet30_plan_create(const lass_resunet30_weights* weights_ho
  * shift_override: NULL, or a (B, film_rows) fp32 table of precomputed activation shifts (folded BN shift + FiLM
  *   beta) that replaces the FiLM GEMM — the `base(mixtures=, film_dict=)` call of the reference
  *   (models/resunet.py:685-688); `condition` may then be NULL.
- * stft_precision_mode: 0 = fp32-parity STFT, 1 = single-pass bf16 STFT.  Asynchronous on `stream`. */
+ * stft_precision_mode: 0 = fp32-parity STFT, 1 = single-pass bf16 STFT.  Asynchronous on `stream`.
+ * lass_resunet30_forward_stages runs a subset (bit mask) of the three stages so a caller can bracket them with
+ * its own CUDA events: LASS_STAGE_FRONT (STFT, FiLM, bn0 + pre_conv), LASS_STAGE_UNET (all convolutions),
+ * LASS_STAGE_BACK (mask + iSTFT).  lass_resunet30_forward == all stages. */
+#define LASS_STAGE_FRONT 1
+#define LASS_STAGE_UNET 2
+#define LASS_STAGE_BACK 4
+#define LASS_STAGE_ALL 7
 LASS_API int lass_resunet30_forward(lass_plan* plan, const float* mixture, const float* condition,
                                     const float* shift_override, float* waveform, int stft_precision_mode,
                                     void* stream);
+LASS_API int lass_resunet30_forward_stages(lass_plan* plan, int stage_mask, const float* mixture,
+                                           const float* condition, const float* shift_override, float* waveform,
+                                           int stft_precision_mode, void* stream);
+/* Algorithmic FLOPs (2*M*N*K summed over the plan's convolution launches) and launches of the UNET stage. */
+LASS_API double lass_resunet30_unet_flops(const lass_plan* plan);
 /* Number of kernel launches one lass_resunet30_forward issues. */
 LASS_API int lass_resunet30_num_launches(const lass_plan* plan);
 /* Debug / test access to intermediates in the workspace: name in {"mag","cos","sin","shift","feat",

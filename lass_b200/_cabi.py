@@ -130,6 +130,9 @@ SIGNATURES.update({
                                                   ctypes.POINTER(ctypes.c_void_p)]),
     "lass_resunet30_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                               ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "lass_resunet30_forward_stages": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
+                                                     ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
+    "lass_resunet30_unet_flops": (ctypes.c_double, [ctypes.c_void_p]),
     "lass_resunet30_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
     "lass_resunet30_buffer": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int * 4),
                                                 ctypes.POINTER(ctypes.c_int)]),

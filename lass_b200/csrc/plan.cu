@@ -354,14 +354,26 @@ int lass_resunet30_plan_create(const lass_resunet30_weights* wh, int B, int L, v
 
 int lass_resunet30_forward(lass_plan* p, const float* mixture, const float* condition, const float* shift_override,
                            float* waveform, int stft_precision_mode, void* stream_v) {
-  if (!p || !mixture || (!condition && !shift_override) || !waveform)
-    return set_error(LASS_ERR_ARG, "forward: null pointer");
+  return lass_resunet30_forward_stages(p, LASS_STAGE_ALL, mixture, condition, shift_override, waveform,
+                                       stft_precision_mode, stream_v);
+}
+
+double lass_resunet30_unet_flops(const lass_plan* p) { return p ? p->conv_flops_total : 0.0; }
+
+int lass_resunet30_forward_stages(lass_plan* p, int stage_mask, const float* mixture, const float* condition,
+                                  const float* shift_override, float* waveform, int stft_precision_mode,
+                                  void* stream_v) {
+  if (!p) return set_error(LASS_ERR_ARG, "forward: null plan");
+  if ((stage_mask & LASS_STAGE_FRONT) && (!mixture || (!condition && !shift_override)))
+    return set_error(LASS_ERR_ARG, "forward: null input pointer");
+  if ((stage_mask & LASS_STAGE_BACK) && !waveform) return set_error(LASS_ERR_ARG, "forward: null output pointer");
   cudaStream_t stream = (cudaStream_t)stream_v;
   int e;
   float* mag = reinterpret_cast<float*>(p->mag.ptr);
   float* cs = reinterpret_cast<float*>(p->cosb.ptr);
   float* sn = reinterpret_cast<float*>(p->sinb.ptr);
   float* shift = reinterpret_cast<float*>(p->shift.ptr);
+  if (stage_mask & LASS_STAGE_FRONT) {
   // K1: STFT -> mag / cos / sin
   if ((e = launch_stft(mixture, p->B, p->L, p->w.n_fft, p->w.hop, p->w.stft_basis_hi, p->w.stft_basis_lo, mag, cs, sn,
                        stft_precision_mode, p->stft_ws, stream)))
@@ -382,9 +394,12 @@ int lass_resunet30_forward(lass_plan* p, const float* mixture, const float* cond
                                          p->x_raw[0].ptr, p->x_act[0].ptr, p->B, p->T, p->F, p->Tp, p->Fp, stream),
                           "preconv launch")))
     return e;
+  }
   // K3 / K4: the UNet
-  for (size_t i = 0; i < p->convs.size(); ++i)
-    if ((e = conv_run(p->convs[i], stream))) return e;
+  if (stage_mask & LASS_STAGE_UNET)
+    for (size_t i = 0; i < p->convs.size(); ++i)
+      if ((e = conv_run(p->convs[i], stream))) return e;
+  if (!(stage_mask & LASS_STAGE_BACK)) return 0;
   // K5: mask + iSTFT
   const long long plane = (long long)p->Tp * p->Fp;
   return set_cuda_error(launch_mask_istft(reinterpret_cast<const float*>(p->feat.ptr), 3 * plane, plane, p->Fp, p->Fp, mag,

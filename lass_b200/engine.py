@@ -18,6 +18,11 @@ _DEC = ("decoder_block1", "decoder_block2", "decoder_block3", "decoder_block4", 
 BN_EPS = 1e-5
 
 
+def _dev_key(device):
+    device = torch.device(device)
+    return (device.type, device.index if device.index is not None else torch.cuda.current_device())
+
+
 def fold_bn(bn: torch.nn.BatchNorm2d):
     """eval-mode BatchNorm -> (scale, shift): y = scale * x + shift."""
     scale = bn.weight.detach().float() / torch.sqrt(bn.running_var.detach().float() + bn.eps)
@@ -64,7 +69,7 @@ class Engine:
     # ------------------------------------------------------------------ packing
     def _version_key(self, device):
         mods = [self.base] + ([self.film] if self.film is not None else [])
-        key = [str(device)]
+        key = [_dev_key(device)]
         for m in mods:
             for t in list(m.parameters()) + list(m.buffers()):
                 key.append((t.data_ptr(), t._version))
@@ -175,7 +180,7 @@ class Engine:
                              % (B, L, self.base.window_size, self.base.hop_size))
         # one workspace shared by all plans of this engine (plans run one at a time on a stream)
         ws = getattr(self, "_ws", None)
-        if ws is None or ws.numel() < need or ws.device != device:
+        if ws is None or ws.numel() < need or _dev_key(ws.device) != _dev_key(device):
             self._plans = {}
             ws = torch.empty(need + 1024, dtype=torch.uint8, device=device)
             self._ws = ws
@@ -245,6 +250,18 @@ class Engine:
                                                             out.data_ptr(), self.stft_precision_mode,
                                                             torch.cuda.current_stream().cuda_stream))
         return out
+
+    @torch.no_grad()
+    def forward_stages(self, mixtures, conditions, out, stage_mask):
+        """Run a subset of the stages (bench.py brackets them with CUDA events). Inputs as in forward()."""
+        B, _, L = mixtures.shape
+        plan = self._get_plan(B, L, mixtures.device)
+        _cabi.check(_cabi.load().lass_resunet30_forward_stages(
+            plan.handle, stage_mask, mixtures.data_ptr(), conditions.data_ptr(), None, out.data_ptr(),
+            self.stft_precision_mode, torch.cuda.current_stream().cuda_stream))
+
+    def unet_flops(self, B, L, device):
+        return _cabi.load().lass_resunet30_unet_flops(self._get_plan(B, L, device).handle)
 
     def num_launches(self, B, L, device):
         return _cabi.load().lass_resunet30_num_launches(self._get_plan(B, L, device).handle)

@@ -9,7 +9,7 @@ with exactly those rounding points inserted, so that
 * per-layer GPU outputs can be compared against a model that should agree to ~1 bf16 ulp.
 
 Stored tensors per ConvBlockRes (see DESIGN.md "Data layout"):
-  raw(x)  bf16   input of the shortcut / residual tap
+  raw(x)  fp16   input of the shortcut / residual tap (saturating; 11-bit mantissa keeps the residual stream accurate)
   act(x)  bf16   lrelu(bn1(x) + beta1), computed from the fp32 value *before* rounding
 """
 import math
@@ -22,6 +22,11 @@ from . import resunet_oracle as O
 
 def bf16(x: torch.Tensor) -> torch.Tensor:
     return x.to(torch.bfloat16).to(torch.float32)
+
+
+def fp16(x: torch.Tensor) -> torch.Tensor:
+    """Raw residual / skip stream: saturating fp16 (DESIGN.md "Numerics")."""
+    return x.clamp(-65504.0, 65504.0).to(torch.float16).to(torch.float32)
 
 
 def fold_bn(sd, prefix):
@@ -46,14 +51,14 @@ def _block(sd, prefix, film_prefix, cond, raw_b, act_b):
     a2 = _act(sd, prefix + ".bn2", film_prefix + "->beta2", cond, h)
     h2 = F.conv2d(a2, bf16(sd[prefix + ".conv2.weight"]), None, padding=1)
     if (prefix + ".shortcut.weight") in sd:
-        res = F.conv2d(raw_b, bf16(sd[prefix + ".shortcut.weight"]), sd[prefix + ".shortcut.bias"])
+        res = F.conv2d(raw_b, fp16(sd[prefix + ".shortcut.weight"]), sd[prefix + ".shortcut.bias"])
     else:
         res = raw_b
     return res + h2
 
 
 @torch.no_grad()
-def forward(sd, mixture, condition, hop=160, taps=None, feat_bf16=False):
+def forward(sd, mixture, condition, hop=160, taps=None):
     n_fft = O.infer_stft_params(sd)
     length = mixture.shape[2]
     mag, cos_in, sin_in = O.stft_mag_phase(sd, mixture[:, 0], n_fft, hop)
@@ -67,7 +72,7 @@ def forward(sd, mixture, condition, hop=160, taps=None, feat_bf16=False):
     for name, _ci, _co, pool in O.ENCODERS:
         p = "base.%s.conv_block1" % name
         fp = "%s->conv_block1" % name
-        raw_b = bf16(x32)
+        raw_b = fp16(x32)
         act_b = _act(sd, p + ".bn1", fp + "->beta1", condition, x32)
         full32 = _block(sd, p, fp, condition, raw_b, act_b)
         if taps is not None:
@@ -83,7 +88,7 @@ def forward(sd, mixture, condition, hop=160, taps=None, feat_bf16=False):
         s32 = skips.pop()
         cb = p + ".conv_block2"
         fp = name + "->conv_block2"
-        raw_b = torch.cat((bf16(u32), bf16(s32)), dim=1)
+        raw_b = torch.cat((fp16(u32), fp16(s32)), dim=1)
         act_b = torch.cat((_act(sd, cb + ".bn1", fp + "->beta1", condition, u32, 0, cout),
                            _act(sd, cb + ".bn1", fp + "->beta1", condition, s32, cout, 2 * cout)), dim=1)
         x32 = _block(sd, cb, fp, condition, raw_b, act_b)
@@ -91,8 +96,6 @@ def forward(sd, mixture, condition, hop=160, taps=None, feat_bf16=False):
             taps[cb + ":out"] = x32
 
     feat = F.conv2d(x32, sd["base.after_conv.weight"], sd["base.after_conv.bias"])
-    if feat_bf16:
-        feat = bf16(feat)
     feat = F.pad(feat, (0, 1))[:, :, :frames, :]
     if taps is not None:
         taps["feat"] = feat

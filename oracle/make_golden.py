@@ -1,0 +1,71 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference/models/resunet.py through the torchlibrosa restatement) in the build container.
+
+    python -m oracle.make_golden
+
+The fixtures pin (i) the travelling oracle ``oracle/resunet_oracle.py`` and (ii) the B200 path to outputs of the
+reference itself; they are small (a few hundred kB) and committed.  Weights are not stored: they are regenerated
+from ``oracle.factory.fill_state_dict`` (key-seeded), whose per-key checksums ARE stored so a mismatch is loud.
+"""
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import factory
+from .reference_loader import import_reference_resunet
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    ref_mod = import_reference_resunet()
+    torch.manual_seed(0)
+    net = ref_mod.ResUNet30(input_channels=1, output_channels=1, condition_size=512).eval()
+    sd = factory.fill_state_dict(net.state_dict(), seed=0)
+    net.load_state_dict(sd)
+
+    # weight-factory checksums (float64 sums, every key)
+    sums = {k: [float(v.double().sum()), float(v.double().abs().sum())] for k, v in sd.items()}
+    with open(os.path.join(GOLDEN_DIR, "factory_seed0_checksums.json"), "w") as f:
+        json.dump(sums, f, indent=0, sort_keys=True)
+
+    # whole forward, reference shapes (n_fft 1024 / hop 160), three clips incl. the two edge clips
+    B, L = 3, 24000
+    mix, cond = factory.make_inputs(B, L, seed=1234)
+    with torch.no_grad():
+        wav = net({"mixture": mix, "condition": cond})["waveform"]
+        # intermediates through the reference's own methods
+        mag, cos, sin = net.base.wav_to_spectrogram_phase(mix)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "resunet30_fwd_b3_l24000.npz"),
+                        waveform=wav.numpy(), mag=mag.numpy().astype(np.float32),
+                        cos_clip0=cos[0].numpy(), sin_clip0=sin[0].numpy(),
+                        meta=np.array([B, L, 1024, 160, 1234, 0]))
+
+    # chunk_inference of the reference (RATE is hard-coded to 32000 there: models/resunet.py:661);
+    # 7.2 s at "32 kHz" gives two full windows plus a truncated tail window
+    Lc = 230000
+    mixc, condc = factory.make_inputs(1, Lc, seed=77, edge_clips=False)
+    with torch.no_grad():
+        out = net.chunk_inference({"mixture": mixc, "condition": condc})
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "chunk_inference_l230000.npz"),
+                        waveform=out.astype(np.float32), meta=np.array([1, Lc, 77]))
+
+    # spectral round trip of the reference's STFT / ISTFT objects (mask = identity) for both shape sets
+    from torchlibrosa.stft import ISTFT, STFT
+    for n_fft, hop in ((1024, 160), (2048, 320), (512, 160), (256, 160)):
+        stft = STFT(n_fft=n_fft, hop_length=hop, win_length=n_fft, window="hann", center=True, pad_mode="reflect")
+        istft = ISTFT(n_fft=n_fft, hop_length=hop, win_length=n_fft, window="hann", center=True, pad_mode="reflect")
+        wave, _ = factory.make_inputs(2, 8000, seed=5, edge_clips=False)
+        with torch.no_grad():
+            re, im = stft(wave[:, 0])
+            back = istft(re, im, 8000)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "stft_%d_%d_l8000.npz" % (n_fft, hop)),
+                            real=re.numpy(), imag=im.numpy(), roundtrip=back.numpy())
+    print("golden fixtures written to", GOLDEN_DIR)
+
+
+if __name__ == "__main__":
+    main()

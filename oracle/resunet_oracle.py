@@ -180,3 +180,27 @@ def resunet30_forward(sd: Dict[str, torch.Tensor], mixture: torch.Tensor, condit
     if taps is not None:
         taps["feat"] = feat
     return mask_to_wave(sd, feat, mag, cos_in, sin_in, length, n_fft, hop)
+
+
+@torch.no_grad()
+def chunk_inference(sd, mixture, condition, hop: int = 160, rate: int = 32000):
+    """Serial restatement of ``ResUNet30.chunk_inference`` (reference models/resunet.py:655-714): 5 s windows
+    (NL = 1 s, NC = 3 s, NR = 1 s at the hard-coded RATE = 32000), hop NC, numpy stitching, batch 1."""
+    import numpy as np
+    NL, NC, NR = int(1.0 * rate), int(3.0 * rate), int(1.0 * rate)
+    L = mixture.shape[2]
+    out = np.zeros([1, L])
+    WINDOW = NL + NC + NR
+    cur = 0
+    while cur + WINDOW < L:
+        chunk = resunet30_forward(sd, mixture[:, :, cur:cur + WINDOW], condition, hop=hop)[0].numpy()
+        if cur == 0:
+            out[:, cur:cur + WINDOW - NR] = chunk[:, :-NR] if NR != 0 else chunk
+        else:
+            out[:, cur + NL:cur + WINDOW - NR] = chunk[:, NL:-NR] if NR != 0 else chunk[:, NL:]
+        cur += NC
+        if cur < L:
+            chunk = resunet30_forward(sd, mixture[:, :, cur:cur + WINDOW], condition, hop=hop)[0].numpy()
+            seg_len = chunk.shape[1]
+            out[:, cur + NL:cur + seg_len] = chunk[:, NL:]
+    return out
