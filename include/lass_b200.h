@@ -130,8 +130,14 @@ typedef struct lass_conv_desc {
 
 LASS_API int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream);
 
-/* Debug: shared-memory halo-tile pitch of the conv kernel, 10 (dense, default) or 16 pixels. */
-LASS_API int lass_debug_set_halo_pitch(int pitch);
+/* Debug: timing experiments on the conv kernel (results become wrong): bit 0 = epilogue skips math and stores,
+ * bit 1 = no tcgen05.mma issued, bit 2 = no activation (A) TMA loads.  0 = normal operation. */
+LASS_API int lass_debug_set_conv_flags(int flags);
+/* Debug: per-CTA role profile of subsequently PREPARED conv launches.  device_counters: >= 16 int64 per CTA
+ * (<= 296 CTAs), clock cycles: [0] producer waits for a free A stage, [1] for a free B stage, [2] producer total,
+ * [3] MMA issuer waits for a free accumulator, [4] for A data, [5] for B data, [6] MMA issuer total,
+ * [7] epilogue waits for an accumulator, [8] epilogue total, [9] items processed.  NULL switches it off. */
+LASS_API int lass_debug_set_conv_profile(long long* device_counters);
 
 /* ------------------------------------------------------------------------------------------------------
  * K2  FiLM: all FiLM linears of the model (reference models/resunet.py:59-81) with the eval-mode BatchNorm

@@ -136,9 +136,13 @@ int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream) {
   return e;
 }
 
-int lass_debug_set_halo_pitch(int pitch) {
-  if (pitch != 10 && pitch != 16) return set_error(LASS_ERR_ARG, "halo pitch must be 10 or 16");
-  conv_set_halo_pitch(pitch);
+int lass_debug_set_conv_profile(long long* device_counters) {
+  conv_set_profile_buffer(device_counters);
+  return 0;
+}
+
+int lass_debug_set_conv_flags(int flags) {
+  conv_set_debug_flags(flags);
   return 0;
 }
 

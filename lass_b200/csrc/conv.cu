@@ -33,6 +33,11 @@ namespace lass {
 namespace {
 
 constexpr int TW = 8;          // pixels per tile row == rows of one 8-row descriptor group
+constexpr int kHaloPitch = TW + 2;  // pixels per image row of the halo tile in shared memory
+template <int V>
+struct IntTag {
+  static constexpr int value = V;
+};
 constexpr int kThreads = 192;
 constexpr int kMaxA = 8;
 constexpr int kMaxB = 40;
@@ -58,13 +63,15 @@ struct ConvParams {
   const float* after_w;
   const float* after_b;
   float* feat;
+  long long* prof;  // optional per-CTA cycle counters (kProfSlots each), nullptr = off
   int nseg;
   int B, H, W, ncols;
   int tiles_h, tiles_w, pix_tiles, n_tiles, num_items;
-  int a_stages, b_stages, b_resident, halo_pitch;
+  int a_stages, b_stages, b_resident;
   uint32_t a_stage_bytes, b_stage_bytes;
   int up_h, up_w, group_c;
   int pool_h, pool_w;
+  int debug_flags;  // timing experiments only: 1 epilogue idle, 2 no MMA, 4 no A loads, 8 no pooled outputs, 16 no stores
 };
 
 struct Item {
@@ -86,42 +93,100 @@ __device__ __forceinline__ Item decode_item(const ConvParams& p, int item, int B
   return it;
 }
 
-__device__ __forceinline__ void store16(const OutDev& o, int b, int ho, int wo, int Ho, int Wo, int c,
-                                        const float* v, bool valid) {
-  float y[16];
-  if (o.scale != nullptr) {
-    const float4* sc = reinterpret_cast<const float4*>(o.scale + c);
-    const float4* sh = reinterpret_cast<const float4*>(o.shift + (size_t)b * o.shift_bstride + c);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 a = __ldg(sc + j);
-      const float4 s = __ldg(sh + j);
-      float t0 = fmaf(a.x, v[4 * j + 0], s.x), t1 = fmaf(a.y, v[4 * j + 1], s.y);
-      float t2 = fmaf(a.z, v[4 * j + 2], s.z), t3 = fmaf(a.w, v[4 * j + 3], s.w);
-      y[4 * j + 0] = t0 > 0.0f ? t0 : kSlope * t0;
-      y[4 * j + 1] = t1 > 0.0f ? t1 : kSlope * t1;
-      y[4 * j + 2] = t2 > 0.0f ? t2 : kSlope * t2;
-      y[4 * j + 3] = t3 > 0.0f ? t3 : kSlope * t3;
-    }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) y[j] = v[j];
-  }
-  uint32_t w[8];
-  if (o.fp16) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) w[j] = pack_f16x2_sat(y[2 * j], y[2 * j + 1]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) w[j] = pack_bf16x2(y[2 * j], y[2 * j + 1]);
-  }
+// Epilogue parameters of the current (clip, N tile), staged in shared memory once per change so that the
+// per-column-chunk code reads them with broadcast LDS instead of dependent global loads.
+template <int BN>
+struct EpiTables {
+  float bias[BN];
+  float sc_full[BN], sh_full[BN];
+  float sc_pool[BN], sh_pool[BN];
+  float after_w[3 * 32];
+  float after_b[4];
+};
+
+__device__ __forceinline__ void store32(const OutDev& o, int b, int ho, int wo, int Ho, int Wo, int c, const uint32_t* w,
+                                        bool valid) {
   if (valid) {
     uint16_t* base = reinterpret_cast<uint16_t*>(o.ptr) + (((size_t)b * Ho + ho) * Wo + wo) * o.cstride + o.coff + c;
     uint4* dst = reinterpret_cast<uint4*>(base);
     dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    dst[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    dst[3] = make_uint4(w[12], w[13], w[14], w[15]);
   }
 }
+
+// raw output: the value itself as saturating fp16 (residual / skip stream)
+__device__ __forceinline__ void out_raw32(const OutDev& o, int b, int ho, int wo, int Ho, int Wo, int c, const float* v,
+                                          bool valid) {
+  uint32_t w[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) w[j] = pack_f16x2_sat(v[2 * j], v[2 * j + 1]);
+  store32(o, b, ho, wo, Ho, Wo, c, w, valid);
+}
+
+// activated output: lrelu(sc * v + sh) as bf16 (operand of the next convolution)
+__device__ __forceinline__ void out_act32(const OutDev& o, const float* sc, const float* sh, int b, int ho, int wo,
+                                          int Ho, int Wo, int c, const float* v, bool valid) {
+  uint32_t w[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(sc + j);
+    const float4 s = *reinterpret_cast<const float4*>(sh + j);
+    const float t0 = fmaf(a.x, v[j + 0], s.x), t1 = fmaf(a.y, v[j + 1], s.y);
+    const float t2 = fmaf(a.z, v[j + 2], s.z), t3 = fmaf(a.w, v[j + 3], s.w);
+    w[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
+    w[j / 2 + 1] = pack_bf16x2(fmaxf(t2, kSlope * t2), fmaxf(t3, kSlope * t3));
+  }
+  store32(o, b, ho, wo, Ho, Wo, c, w, valid);
+}
+
+// One tcgen05.mma with descriptors given as (low word = start address >> 4 | LBO, high word = SBO | version | swizzle).
+__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Per-segment constants of the MMA issuer (uniform registers).
+struct SegMma {
+  uint32_t a_hi, b_hi;      // descriptor high words
+  uint32_t idesc;
+};
+
+// All MMAs of one (chunk, tap) for MT m-tiles: KSTEPS k-steps of 16 channels each.  a_lo / b_lo already contain the
+// LBO field; start addresses advance by 2 (x16 B) per k-step and by mt_step16 per m-tile.
+template <int MT, int BN, int KSTEPS>
+__device__ __forceinline__ void issue_tap(uint32_t acc, uint32_t a_lo, uint32_t mt_step16, uint32_t b_lo, const SegMma& g,
+                                          uint32_t accumulate) {
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ++ks)
+      umma_lohi(acc + mt * BN, a_lo + mt * mt_step16 + 2 * ks, g.a_hi, b_lo + 2 * ks, g.b_hi, g.idesc,
+                ks == 0 ? accumulate : 1u);
+  }
+}
+
+// profiling slots (clock cycles, per CTA); documented at lass_debug_set_conv_profile in include/lass_b200.h
+enum { kProfProdAEmpty = 0, kProfProdBEmpty, kProfProdTotal, kProfMmaAccEmpty, kProfMmaAFull, kProfMmaBFull, kProfMmaTotal,
+       kProfEpiAccFull, kProfEpiTotal, kProfItems, kProfSlots = 16 };
+
+#define LASS_TIMED_WAIT(bar, parity, slot)              \
+  do {                                                  \
+    const long long _t = prof ? clock64() : 0;          \
+    mbar_wait(bar, parity);                             \
+    if (prof) pc[slot] += clock64() - _t;               \
+  } while (0)
 
 template <int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
@@ -143,9 +208,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   uint64_t* acc_full = b_empty + kMaxB;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  EpiTables<BN>* tabs = reinterpret_cast<EpiTables<BN>*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);  // [2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool prof = p.prof != nullptr;
+  long long pc[kProfSlots];
+#pragma unroll
+  for (int i = 0; i < kProfSlots; ++i) pc[i] = 0;
+  const long long t_start = prof ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -177,7 +248,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 
   if (warp == 0) {
     // =========================== TMA producer ===========================
-    if (lane == 0) {
+    // warp-uniform loop; the elected lane issues the TMA loads
+    {
       uint32_t a_it = 0, b_it = 0;
       bool first_item = true;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
@@ -187,28 +259,42 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           const SegDev& sg = p.seg[s];
           const uint32_t row_bytes = sg.kc * 2;
           const bool halo = sg.taps == 9;
-          const uint32_t a_bytes = halo ? (uint32_t)(16 * MT + 2) * p.halo_pitch * row_bytes : (uint32_t)(16 * MT) * TW * row_bytes;
+          const uint32_t a_bytes = halo ? (uint32_t)(16 * MT + 2) * kHaloPitch * row_bytes : (uint32_t)(16 * MT) * TW * row_bytes;
           const uint32_t b_bytes = BN * row_bytes;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             const uint32_t sa = a_it % p.a_stages;
-            mbar_wait(&a_empty[sa], ((a_it / p.a_stages) & 1) ^ 1);
-            mbar_arrive_expect_tx(&a_full[sa], a_bytes);
-            tma_load_4d(a_buf + (size_t)sa * p.a_stage_bytes, &sg.tmA, &a_full[sa], ch * sg.kc,
-                        halo ? it.w0 - 1 : it.w0, halo ? it.h0 - 1 : it.h0, it.b);
-            ++a_it;
-            for (int tp = 0; tp < sg.taps; ++tp) {
-              if (p.b_resident) {
-                if (first_item) {
-                  mbar_arrive_expect_tx(&b_full[b_slot_res], b_bytes);
-                  tma_load_3d(b_buf + (size_t)b_slot_res * p.b_stage_bytes, &sg.tmB, &b_full[b_slot_res],
-                              ch * sg.kc, it.n0, tp);
-                }
-                ++b_slot_res;
+            LASS_TIMED_WAIT(&a_empty[sa], ((a_it / p.a_stages) & 1) ^ 1, kProfProdAEmpty);
+            if (elect_one()) {
+              if (p.debug_flags & 4) {
+                mbar_arrive(&a_full[sa]);
               } else {
+                mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+                tma_load_4d(a_buf + (size_t)sa * p.a_stage_bytes, &sg.tmA, &a_full[sa], ch * sg.kc,
+                            halo ? it.w0 - 1 : it.w0, halo ? it.h0 - 1 : it.h0, it.b);
+              }
+            }
+            __syncwarp();
+            ++a_it;
+            if (p.b_resident) {
+              if (first_item) {
+                for (int tp = 0; tp < sg.taps; ++tp, ++b_slot_res) {
+                  if (elect_one()) {
+                    mbar_arrive_expect_tx(&b_full[b_slot_res], b_bytes);
+                    tma_load_3d(b_buf + (size_t)b_slot_res * p.b_stage_bytes, &sg.tmB, &b_full[b_slot_res], ch * sg.kc,
+                                it.n0, tp);
+                  }
+                  __syncwarp();
+                }
+              }
+            } else {
+              for (int tp = 0; tp < sg.taps; ++tp) {
                 const uint32_t sb = b_it % p.b_stages;
-                mbar_wait(&b_empty[sb], ((b_it / p.b_stages) & 1) ^ 1);
-                mbar_arrive_expect_tx(&b_full[sb], b_bytes);
-                tma_load_3d(b_buf + (size_t)sb * p.b_stage_bytes, &sg.tmB, &b_full[sb], ch * sg.kc, it.n0, tp);
+                LASS_TIMED_WAIT(&b_empty[sb], ((b_it / p.b_stages) & 1) ^ 1, kProfProdBEmpty);
+                if (elect_one()) {
+                  mbar_arrive_expect_tx(&b_full[sb], b_bytes);
+                  tma_load_3d(b_buf + (size_t)sb * p.b_stage_bytes, &sg.tmB, &b_full[sb], ch * sg.kc, it.n0, tp);
+                }
+                __syncwarp();
                 ++b_it;
               }
             }
@@ -216,104 +302,178 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         }
         first_item = false;
       }
+      if (prof && lane == 0) {
+        long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
+        dst[kProfProdAEmpty] = pc[kProfProdAEmpty];
+        dst[kProfProdBEmpty] = pc[kProfProdBEmpty];
+        dst[kProfProdTotal] = clock64() - t_start;
+      }
     }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
-    if (lane == 0) {
-      uint32_t a_it = 0, b_it = 0, acc_it = 0;
+    // The whole warp runs the (warp-uniform) loop so that descriptors live in uniform registers; only the elected
+    // lane issues tcgen05.mma / tcgen05.commit.  Loops are kept rolled: the instruction footprint matters more
+    // than a few uniform-datapath adds per tap.
+    {
+      constexpr uint32_t kLbo = 1u << 16;
+      const uint32_t a_base16 = smem_u32(a_buf) >> 4, a_stage16 = p.a_stage_bytes >> 4;
+      const uint32_t b_base16 = smem_u32(b_buf) >> 4, b_stage16 = p.b_stage_bytes >> 4;
+      const uint32_t n_a = p.a_stages, n_b = p.b_stages;
+      const bool resident = p.b_resident != 0;
+      const bool no_mma = (p.debug_flags & 2) != 0;
+      uint32_t sa = 0, pa = 0;          // A ring: stage, phase
+      uint32_t sb = 0, pb = 0;          // B ring (streaming mode)
+      uint32_t as = 0, pacc = 0;        // accumulator ring
+      uint32_t n_items = 0;
+      bool first_item = true;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const uint32_t as = acc_it % AS;
-        mbar_wait(&acc_empty[as], ((acc_it / AS) & 1) ^ 1);
+        LASS_TIMED_WAIT(&acc_empty[as], pacc ^ 1, kProfMmaAccEmpty);
         tc_fence_after_sync();
         const uint32_t acc_addr = tmem_base + as * (MT * BN);
-        uint32_t b_slot_res = 0;
         uint32_t accumulate = 0;
+        if (resident) sb = 0;
+#pragma unroll 1
         for (int s = 0; s < p.nseg; ++s) {
-          const SegDev& sg = p.seg[s];
-          const uint32_t row_bytes = sg.kc * 2;
-          const uint32_t swz = sg.kc == 64 ? kSwizzle128B : kSwizzle64B;
-          const bool halo = sg.taps == 9;
-          const uint32_t pitch = halo ? p.halo_pitch : TW;
-          const uint32_t idesc = make_idesc_f16(sg.fmt, sg.fmt, 128, BN);
-          const int ksteps = sg.kc / 16;
-          for (int ch = 0; ch < sg.nchunks; ++ch) {
-            const uint32_t sa = a_it % p.a_stages;
-            mbar_wait(&a_full[sa], (a_it / p.a_stages) & 1);
+          const uint32_t kc = p.seg[s].kc;
+          const uint32_t row16 = kc >> 3;                       // row bytes / 16
+          const bool halo = p.seg[s].taps == 9;
+          const uint32_t pitch = halo ? kHaloPitch : TW;
+          const uint32_t swz = kc == 64 ? kSwizzle128B : kSwizzle64B;
+          SegMma gs;
+          gs.a_hi = static_cast<uint32_t>(make_smem_desc(0, pitch * row16 * 16, swz) >> 32);
+          gs.b_hi = static_cast<uint32_t>(make_smem_desc(0, 8 * row16 * 16, swz) >> 32);
+          gs.idesc = make_idesc_f16(p.seg[s].fmt, p.seg[s].fmt, 128, BN);
+          const uint32_t mt_step16 = 16 * pitch * row16;
+          const uint32_t nchunks = p.seg[s].nchunks, taps = p.seg[s].taps;
+#pragma unroll 1
+          for (uint32_t ch = 0; ch < nchunks; ++ch) {
+            LASS_TIMED_WAIT(&a_full[sa], pa, kProfMmaAFull);
             tc_fence_after_sync();
-            const uint32_t a_addr = smem_u32(a_buf + (size_t)sa * p.a_stage_bytes);
-            for (int tp = 0; tp < sg.taps; ++tp) {
-              uint32_t sb;
-              if (p.b_resident) {
-                sb = b_slot_res++;
-                mbar_wait(&b_full[sb], 0);
-              } else {
-                sb = b_it % p.b_stages;
-                mbar_wait(&b_full[sb], (b_it / p.b_stages) & 1);
+            uint32_t a_lo = (a_base16 + sa * a_stage16) | kLbo;   // advanced tap by tap: (dy*pitch + dx) rows
+            uint32_t dx = 0;
+#pragma unroll 1
+            for (uint32_t tp = 0; tp < taps; ++tp) {
+              if (!resident || first_item) {
+                LASS_TIMED_WAIT(&b_full[sb], resident ? 0u : pb, kProfMmaBFull);
+                tc_fence_after_sync();
               }
-              tc_fence_after_sync();
-              const uint32_t b_addr = smem_u32(b_buf + (size_t)sb * p.b_stage_bytes);
-              const uint32_t dy = halo ? tp / 3 : 0, dx = halo ? tp % 3 : 0;
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const uint32_t a_tap = a_addr + ((mt * 16 + dy) * pitch + dx) * row_bytes;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                  const uint64_t da = make_smem_desc(a_tap + ks * 32, pitch * row_bytes, swz);
-                  const uint64_t db = make_smem_desc(b_addr + ks * 32, 8 * row_bytes, swz);
-                  umma_f16(acc_addr + mt * BN, da, db, idesc, accumulate | (uint32_t)(ks != 0));
+              const uint32_t b_lo = (b_base16 + sb * b_stage16) | kLbo;
+              if (!no_mma && elect_one()) {
+                if (kc == 64) issue_tap<MT, BN, 4>(acc_addr, a_lo, mt_step16, b_lo, gs, accumulate);
+                else issue_tap<MT, BN, 2>(acc_addr, a_lo, mt_step16, b_lo, gs, accumulate);
+              }
+              __syncwarp();
+              accumulate = 1;
+              if (resident) {
+                ++sb;
+              } else {
+                if (elect_one()) umma_commit(&b_empty[sb]);
+                __syncwarp();
+                if (++sb == n_b) {
+                  sb = 0;
+                  pb ^= 1;
                 }
               }
-              accumulate = 1;
-              if (!p.b_resident) {
-                umma_commit(&b_empty[sb]);
-                ++b_it;
+              a_lo += row16;
+              if (++dx == 3) {
+                dx = 0;
+                a_lo += (pitch - 3) * row16;
               }
             }
-            umma_commit(&a_empty[sa]);
-            ++a_it;
+            if (elect_one()) umma_commit(&a_empty[sa]);
+            __syncwarp();
+            if (++sa == n_a) {
+              sa = 0;
+              pa ^= 1;
+            }
           }
         }
-        umma_commit(&acc_full[as]);
-        ++acc_it;
+        if (elect_one()) umma_commit(&acc_full[as]);
+        __syncwarp();
+        if (++as == AS) {
+          as = 0;
+          pacc ^= 1;
+        }
+        ++n_items;
+        first_item = false;
+      }
+      if (prof && lane == 0) {
+        long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
+        dst[kProfMmaAccEmpty] = pc[kProfMmaAccEmpty];
+        dst[kProfMmaAFull] = pc[kProfMmaAFull];
+        dst[kProfMmaBFull] = pc[kProfMmaBFull];
+        dst[kProfMmaTotal] = clock64() - t_start;
+        dst[kProfItems] = n_items;
       }
     }
   } else {
     // =========================== epilogue ===========================
     const int q = warp & 3;
+    const int et = threadIdx.x - 64;  // 0..127
     const int hl = q * 4 + (lane >> 3);
     const int wl = lane & 7;
     const int Ho = p.H * p.up_h, Wo = p.W * p.up_w;
     const int Hp = p.H / p.pool_h, Wp = p.W / p.pool_w;
-    const bool pooling = (p.pool_raw.ptr != nullptr) || (p.pool_act.ptr != nullptr);
+    const bool pooling = ((p.pool_raw.ptr != nullptr) || (p.pool_act.ptr != nullptr)) && !(p.debug_flags & 8);
+    const bool no_store = (p.debug_flags & 16) != 0;
     const float pool_scale = 1.0f / (float)(p.pool_h * p.pool_w);
     uint32_t acc_it = 0;
+    int tab_b = -1, tab_n0 = -1;
+    uint32_t tab_sel = 0;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
       const Item it = decode_item<MT>(p, item, BN);
+      // ---- (re)stage the per-(clip, N tile) tables; double-buffered so one named barrier per change suffices ----
+      if (it.b != tab_b || it.n0 != tab_n0) {
+        tab_sel ^= 1u;
+        EpiTables<BN>& t = tabs[tab_sel];
+        for (int c = et; c < BN; c += 128) {
+          const int n = it.n0 + c;
+          const bool in = n < p.ncols;
+          const int cc = (p.up_h * p.up_w > 1) ? n % p.group_c : n;
+          t.bias[c] = (in && p.bias) ? __ldg(p.bias + n) : 0.0f;
+          t.sc_full[c] = (in && p.full_act.scale) ? __ldg(p.full_act.scale + cc) : 0.0f;
+          t.sh_full[c] = (in && p.full_act.scale) ? __ldg(p.full_act.shift + (size_t)it.b * p.full_act.shift_bstride + cc) : 0.0f;
+          t.sc_pool[c] = (in && p.pool_act.scale) ? __ldg(p.pool_act.scale + cc) : 0.0f;
+          t.sh_pool[c] = (in && p.pool_act.scale) ? __ldg(p.pool_act.shift + (size_t)it.b * p.pool_act.shift_bstride + cc) : 0.0f;
+        }
+        if (p.after_w != nullptr && et < 3 * 32)
+          t.after_w[et] = (et % 32 < p.ncols) ? __ldg(p.after_w + (et / 32) * p.ncols + et % 32) : 0.0f;
+        if (p.after_w != nullptr && et < 3) t.after_b[et] = __ldg(p.after_b + et);
+        tab_b = it.b;
+        tab_n0 = it.n0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const EpiTables<BN>& tb = tabs[tab_sel];
       const uint32_t as = acc_it % AS;
+      if (q == 0 && lane == 0) {
+        LASS_TIMED_WAIT(&acc_full[as], (acc_it / AS) & 1, kProfEpiAccFull);
+      }
+      __syncwarp();
       mbar_wait(&acc_full[as], (acc_it / AS) & 1);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int h = it.h0 + mt * 16 + hl;
         const int w = it.w0 + wl;
-        const bool valid = (h < p.H) && (w < p.W);
+        const bool valid = (h < p.H) && (w < p.W) && !(no_store && h >= 0);
         const uint32_t taddr = tmem_base + as * (MT * BN) + mt * BN + (static_cast<uint32_t>(q * 32) << 16);
         float fa0 = 0.0f, fa1 = 0.0f, fa2 = 0.0f;
 #pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 16) {
+        for (int c0 = 0; c0 < BN; c0 += 32) {
           const int n = it.n0 + c0;
           if (n >= p.ncols) break;
-          float v[16];
-          tmem_ld_x16(taddr + c0, v);
+          float v[32];
+          tmem_ld_x32(taddr + c0, v);
           tmem_ld_wait();
+          if (p.debug_flags & 1) continue;
           if (p.bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float4 bb = __ldg(bp + j);
-              v[4 * j + 0] += bb.x;
-              v[4 * j + 1] += bb.y;
-              v[4 * j + 2] += bb.z;
-              v[4 * j + 3] += bb.w;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bb = *reinterpret_cast<const float4*>(tb.bias + c0 + j);
+              v[j + 0] += bb.x;
+              v[j + 1] += bb.y;
+              v[j + 2] += bb.z;
+              v[j + 3] += bb.w;
             }
           }
           int c = n, ho = h, wo = w;
@@ -324,42 +484,48 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             ho = h * p.up_h + dy;
             wo = w * p.up_w + (g - dy * p.up_w);
           }
-          if (p.full_raw.ptr != nullptr) store16(p.full_raw, it.b, ho, wo, Ho, Wo, c, v, valid);
-          if (p.full_act.ptr != nullptr) store16(p.full_act, it.b, ho, wo, Ho, Wo, c, v, valid);
-          if (pooling) {
-            float s[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float t = v[j];
-              if (p.pool_w == 2) t += __shfl_xor_sync(0xffffffffu, t, 1);
-              if (p.pool_h == 2) t += __shfl_xor_sync(0xffffffffu, t, 8);
-              s[j] = t * pool_scale;
-            }
-            const bool owner = valid && ((wl & (p.pool_w - 1)) == 0) && ((hl & (p.pool_h - 1)) == 0);
-            if (p.pool_raw.ptr != nullptr) store16(p.pool_raw, it.b, h / p.pool_h, w / p.pool_w, Hp, Wp, c, s, owner);
-            if (p.pool_act.ptr != nullptr) store16(p.pool_act, it.b, h / p.pool_h, w / p.pool_w, Hp, Wp, c, s, owner);
-          }
+          if (p.full_raw.ptr != nullptr) out_raw32(p.full_raw, it.b, ho, wo, Ho, Wo, c, v, valid);
+          if (p.full_act.ptr != nullptr) out_act32(p.full_act, tb.sc_full + c0, tb.sh_full + c0, it.b, ho, wo, Ho, Wo, c, v, valid);
           if (p.after_w != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              fa0 = fmaf(__ldg(p.after_w + n + j), v[j], fa0);
-              fa1 = fmaf(__ldg(p.after_w + p.ncols + n + j), v[j], fa1);
-              fa2 = fmaf(__ldg(p.after_w + 2 * p.ncols + n + j), v[j], fa2);
+            for (int j = 0; j < 32; ++j) {
+              fa0 = fmaf(tb.after_w[j], v[j], fa0);
+              fa1 = fmaf(tb.after_w[32 + j], v[j], fa1);
+              fa2 = fmaf(tb.after_w[64 + j], v[j], fa2);
             }
           }
+          if (pooling) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);   // pool_w is always 2
+            if (p.pool_h == 2) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 8);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= pool_scale;
+            const bool owner = valid && ((wl & (p.pool_w - 1)) == 0) && ((hl & (p.pool_h - 1)) == 0);
+            if (p.pool_raw.ptr != nullptr) out_raw32(p.pool_raw, it.b, h / p.pool_h, w / p.pool_w, Hp, Wp, c, v, owner);
+            if (p.pool_act.ptr != nullptr)
+              out_act32(p.pool_act, tb.sc_pool + c0, tb.sh_pool + c0, it.b, h / p.pool_h, w / p.pool_w, Hp, Wp, c, v, owner);
+          }
         }
-        if (p.after_w != nullptr && valid) {
+        if (p.after_w != nullptr && valid && !(p.debug_flags & 1)) {
           const size_t plane = (size_t)p.H * p.W;
           float* fp = p.feat + (size_t)it.b * 3 * plane + (size_t)h * p.W + w;
-          fp[0] = fa0 + __ldg(p.after_b + 0);
-          fp[plane] = fa1 + __ldg(p.after_b + 1);
-          fp[2 * plane] = fa2 + __ldg(p.after_b + 2);
+          fp[0] = fa0 + tb.after_b[0];
+          fp[plane] = fa1 + tb.after_b[1];
+          fp[2 * plane] = fa2 + tb.after_b[2];
         }
       }
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       ++acc_it;
+    }
+    if (prof && q == 0 && lane == 0) {
+      long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
+      dst[kProfEpiAccFull] = pc[kProfEpiAccFull];
+      dst[kProfEpiTotal] = clock64() - t_start;
     }
   }
   tc_fence_before_sync();
@@ -383,7 +549,8 @@ KernelChoice make_choice() {
   return KernelChoice{conv_igemm_kernel<BN, MT>, BN, MT};
 }
 
-int g_halo_pitch = 10;   // 10 = dense halo tile; 16 = 1 KiB-aligned image rows (debug alternative)
+int g_debug_flags = 0;
+long long* g_prof_buffer = nullptr;
 int g_num_sms = 0;
 
 }  // namespace
@@ -395,7 +562,8 @@ struct ConvPrepared {
   size_t smem;
 };
 
-void conv_set_halo_pitch(int pitch) { g_halo_pitch = (pitch == 16) ? 16 : 10; }
+void conv_set_debug_flags(int flags) { g_debug_flags = flags; }
+void conv_set_profile_buffer(long long* buf) { g_prof_buffer = buf; }
 
 double conv_flops(const ConvLaunch& l) {
   double k = 0;
@@ -420,6 +588,9 @@ static int check_out(const ConvOut& o, const char* name, int ncols_eff) {
                      o.coff, ncols_eff);
   if (reinterpret_cast<uintptr_t>(o.ptr) % 16) return set_error(LASS_ERR_ARG, "conv: output %s not 16 B aligned", name);
   if ((o.scale == nullptr) != (o.shift == nullptr)) return set_error(LASS_ERR_ARG, "conv: output %s needs scale AND shift", name);
+  const bool is_raw = name[5] == 'r';   // "full_raw" / "pool_raw"
+  if (is_raw && (!o.fp16 || o.scale)) return set_error(LASS_ERR_ARG, "conv: %s must be fp16 without activation", name);
+  if (!is_raw && (o.fp16 || !o.scale)) return set_error(LASS_ERR_ARG, "conv: %s must be bf16 with an activation table", name);
   return 0;
 }
 
@@ -433,6 +604,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   if ((l.pool_h != 1 && l.pool_h != 2) || (l.pool_w != 1 && l.pool_w != 2) || l.H % l.pool_h || l.W % l.pool_w)
     return set_error(LASS_ERR_ARG, "conv: bad pooling (%d,%d) for %dx%d", l.pool_h, l.pool_w, l.H, l.W);
   if ((l.pool_raw.ptr || l.pool_act.ptr) && up > 1) return set_error(LASS_ERR_ARG, "conv: pooling with upsampling");
+  if ((l.pool_raw.ptr || l.pool_act.ptr) && l.pool_w != 2) return set_error(LASS_ERR_ARG, "conv: pooled outputs need pool_w == 2");
   if (l.after_w && (!l.after_b || !l.feat || l.ncols > 256 || up > 1))
     return set_error(LASS_ERR_ARG, "conv: fused after_conv needs after_b, feat and a single N tile");
   int e;
@@ -465,7 +637,8 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   p.H = l.H;
   p.W = l.W;
   p.ncols = l.ncols;
-  p.halo_pitch = g_halo_pitch;
+  p.debug_flags = g_debug_flags;
+  p.prof = g_prof_buffer;
   p.tiles_h = (l.H + 16 * MT - 1) / (16 * MT);
   p.tiles_w = (l.W + TW - 1) / TW;
   p.pix_tiles = l.B * p.tiles_h * p.tiles_w;
@@ -507,7 +680,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
       uint64_t dims[4] = {(uint64_t)sg.cin, (uint64_t)l.W, (uint64_t)l.H, (uint64_t)l.B};
       uint64_t strides[3] = {(uint64_t)sg.src_cstride * 2, (uint64_t)sg.src_cstride * 2 * l.W,
                              (uint64_t)sg.src_cstride * 2 * l.W * l.H};
-      uint32_t box[4] = {(uint32_t)sg.kc, (uint32_t)(halo ? p.halo_pitch : TW), (uint32_t)(halo ? 16 * MT + 2 : 16 * MT), 1};
+      uint32_t box[4] = {(uint32_t)sg.kc, (uint32_t)(halo ? kHaloPitch : TW), (uint32_t)(halo ? 16 * MT + 2 : 16 * MT), 1};
       if ((e = make_tensor_map(&d.tmA, base, 2, 4, dims, strides, box, swz))) {
         delete cp;
         return e;
@@ -523,7 +696,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
       }
     }
     const uint32_t row_bytes = sg.kc * 2;
-    const uint32_t a_bytes = halo ? (16 * MT + 2) * p.halo_pitch * row_bytes : 16 * MT * TW * row_bytes;
+    const uint32_t a_bytes = halo ? (16 * MT + 2) * kHaloPitch * row_bytes : 16 * MT * TW * row_bytes;
     if (a_bytes > a_stage) a_stage = a_bytes;
     if (BN * row_bytes > b_stage) b_stage = BN * row_bytes;
     b_tiles_per_item += d.nchunks * d.taps;
@@ -533,7 +706,8 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
 
   // ---- shared-memory budget: weights resident if every tile of an item fits, else a streaming ring ----
   const size_t kBudget = 220 * 1024;
-  const size_t fixed = 1024 /*alignment slack*/ + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64;
+  const size_t fixed = 1024 /*alignment slack*/ + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 +
+                       2 * ((size_t)5 * BN + 3 * 32 + 4) * sizeof(float) + 64;
   const size_t min_a = 2 * (size_t)p.a_stage_bytes;
   p.b_resident = (p.n_tiles == 1 && b_tiles_per_item <= kMaxB &&
                   fixed + min_a + (size_t)b_tiles_per_item * p.b_stage_bytes <= kBudget)
@@ -561,18 +735,21 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
   }
-  // TMEM: AS * MT * BN columns per CTA; co-resident CTAs must fit in 512 columns and in shared memory
-  const int tmem_cols = ((2 * MT * BN <= 512) ? 2 : 1) * MT * BN;
-  int per_sm = 1;
-  if (cp->smem * 2 + 2048 <= 227 * 1024 && tmem_cols * 2 <= 512) per_sm = 2;
-  cp->grid = p.num_items < g_num_sms * per_sm ? p.num_items : g_num_sms * per_sm;
-  // opt every instantiation in to the full 227 KiB once (a later, smaller request must not lower the limit that
-  // an already prepared launch of the same kernel relies on)
+  // opt every instantiation in to the full 227 KiB (a later, smaller request must not lower the limit that an
+  // already prepared launch of the same kernel relies on)
   cudaError_t ce = cudaFuncSetAttribute(reinterpret_cast<const void*>(kc.fn), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (ce != cudaSuccess) {
     delete cp;
     return set_cuda_error(ce, "conv smem attribute");
   }
+  // CTAs per SM: limited by shared memory / registers (occupancy query) and by TMEM (AS * MT * BN columns each)
+  const int tmem_cols = ((2 * MT * BN <= 512) ? 2 : 1) * MT * BN;
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(kc.fn), kThreads, cp->smem) != cudaSuccess || per_sm < 1)
+    per_sm = 1;
+  if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+  if (per_sm > 2) per_sm = 2;
+  cp->grid = p.num_items < g_num_sms * per_sm ? p.num_items : g_num_sms * per_sm;
   *out = cp;
   return 0;
 }

@@ -15,6 +15,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out);
 int conv_run(const ConvPrepared* p, cudaStream_t stream);
 void conv_free(ConvPrepared* p);
 double conv_flops(const ConvLaunch& l);
-void conv_set_halo_pitch(int pitch);
+void conv_set_debug_flags(int flags);
+void conv_set_profile_buffer(long long* buf);  // device buffer, >= grid * 16 int64; nullptr = off
 
 }  // namespace lass

@@ -66,21 +66,38 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a pipeline bug must become a trap (CUDA error), never a hung GPU.
-#ifndef LASS_MBAR_TIMEOUT_NS
-#define LASS_MBAR_TIMEOUT_NS 4000000000ull
+// Bounded wait: a pipeline bug must become a trap (CUDA error), never a hung GPU.  The bound is counted in
+// SM clock cycles (clock64 is a cheap per-SM register read; %globaltimer is not).
+#ifndef LASS_MBAR_TIMEOUT_CYCLES
+#define LASS_MBAR_TIMEOUT_CYCLES (8ll << 30)   // ~4 s at 2 GHz
 #endif
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const uint64_t t0 = globaltimer_ns();
+// slow path kept out of line: every inlined copy of the timeout handler (printf argument marshalling) would
+// otherwise bloat the instruction footprint of the persistent kernels
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
+  const long long t0 = clock64();
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0u && globaltimer_ns() - t0 > LASS_MBAR_TIMEOUT_NS) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0xfffu) == 0u && clock64() - t0 > LASS_MBAR_TIMEOUT_CYCLES) {
       printf("lass: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+             blockIdx.z, threadIdx.x, bar_addr, parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(smem_u32(bar), parity);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -129,7 +129,3 @@ def conv_igemm(B, H, W, ncols, segments, bias=None, up=(1, 1), full_raw=None, fu
     d.after_b = _ptr(after_b) if after_b is not None else None
     d.feat = _ptr(feat) if feat is not None else None
     _cabi.check(lib.lass_conv_igemm(ctypes.byref(d), _stream()))
-
-
-def set_halo_pitch(pitch: int):
-    _cabi.check(_cabi.load().lass_debug_set_halo_pitch(pitch))

@@ -17,12 +17,9 @@ def _cases():
     return sorted(gpu_conv_probe.CASES)
 
 
-@pytest.mark.parametrize("pitch", [10])
 @pytest.mark.parametrize("name", _cases())
-def test_conv_case(name, pitch):
+def test_conv_case(name):
     import gpu_conv_probe
-    from lass_b200 import ops
-    ops.set_halo_pitch(pitch)
     res = gpu_conv_probe.run_case(name, **gpu_conv_probe.CASES[name])
     for k, v in res.items():
         if k == "raw_untouched":

@@ -136,9 +136,8 @@ CASES = {
 }
 
 if __name__ == "__main__":
-    pitch = int(sys.argv[1])
+    pitch = int(sys.argv[1])   # kept for the log name; the halo pitch is fixed at 10 pixels
     names = sys.argv[2:] or list(CASES)
-    ops.set_halo_pitch(pitch)
     report = {}
     for n in names:
         try:
