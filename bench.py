@@ -275,7 +275,9 @@ def main():
     # ---------------- timed region 1: device-resident inputs (value) ----------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    time.sleep(0.3)
+    t_s = time.time()
+    while not sampler.samples and time.time() - t_s < 3.0:     # nvidia-smi needs a moment before its first sample
+        time.sleep(0.05)
     barrier()
     t_wall0 = time.time()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

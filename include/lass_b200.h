@@ -241,6 +241,12 @@ LASS_API int lass_debug_umma_probe(const void* A, int a_rows, const void* Bm, in
                                    int a_start_bytes, int a_sbo, int a_base_offset, int b_sbo, int fmt_fp16,
                                    float* out, void* stream);
 
+/* Debug: tcgen05.mma issue/execute throughput for a given operand layout: `iters` back-to-back MMAs (M = 128,
+ * N = n, K = 16) over zeroed shared memory, `nacc` accumulators round-robin; cycles_out[grid] receives the SM
+ * clock cycles from first issue to completion. */
+LASS_API int lass_debug_umma_bench(int n, int kc, int swizzle_mode, int a_start_bytes, int a_sbo, int iters, int nacc,
+                                   int grid, long long* cycles_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,6 +94,7 @@ class ConvDesc(ctypes.Structure):
 SIGNATURES["lass_conv_igemm"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p])
 SIGNATURES["lass_debug_set_conv_flags"] = (c_int, [c_int])
 SIGNATURES["lass_debug_set_conv_profile"] = (c_int, [c_void_p])
+SIGNATURES["lass_debug_umma_bench"] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
 
 
 # ---- whole-model entry (lass_resunet30_*) ----

@@ -38,7 +38,7 @@ template <int V>
 struct IntTag {
   static constexpr int value = V;
 };
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
 constexpr int kMaxA = 8;
 constexpr int kMaxB = 40;
 constexpr float kSlope = 0.01f;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   uint64_t* acc_full = b_empty + kMaxB;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  EpiTables<BN>* tabs = reinterpret_cast<EpiTables<BN>*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);  // [2]
+  EpiTables<BN>* tabs = reinterpret_cast<EpiTables<BN>*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);  // [group][2]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -312,8 +312,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     // The whole warp runs the (warp-uniform) loop so that descriptors live in uniform registers; only the elected
-    // lane issues tcgen05.mma / tcgen05.commit.  Loops are kept rolled: the instruction footprint matters more
-    // than a few uniform-datapath adds per tap.
+    // lane issues tcgen05.mma / tcgen05.commit.  Steady state with resident weights: one wait + one elected region
+    // per K-chunk that issues all taps back to back (compile-time tap offsets); streaming weights: per-tap
+    // full/empty handshake on the B ring.
     {
       constexpr uint32_t kLbo = 1u << 16;
       const uint32_t a_base16 = smem_u32(a_buf) >> 4, a_stage16 = p.a_stage_bytes >> 4;
@@ -321,8 +322,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       const uint32_t n_a = p.a_stages, n_b = p.b_stages;
       const bool resident = p.b_resident != 0;
       const bool no_mma = (p.debug_flags & 2) != 0;
+      // per-segment constants, hoisted out of the item loop
+      SegMma g[2];
+      uint32_t seg_kc[2], seg_chunks[2], seg_halo[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const bool on = s < p.nseg;
+        const uint32_t kc = on ? p.seg[s].kc : 64;
+        const uint32_t halo = (on && p.seg[s].taps == 9) ? 1u : 0u;
+        const uint32_t swz = kc == 64 ? kSwizzle128B : kSwizzle64B;
+        g[s].a_hi = static_cast<uint32_t>(make_smem_desc(0, (halo ? kHaloPitch : TW) * kc * 2, swz) >> 32);
+        g[s].b_hi = static_cast<uint32_t>(make_smem_desc(0, 8 * kc * 2, swz) >> 32);
+        g[s].idesc = make_idesc_f16(on ? p.seg[s].fmt : 0, on ? p.seg[s].fmt : 0, 128, BN);
+        seg_kc[s] = kc;
+        seg_chunks[s] = on ? p.seg[s].nchunks : 0;
+        seg_halo[s] = halo;
+      }
       uint32_t sa = 0, pa = 0;          // A ring: stage, phase
-      uint32_t sb = 0, pb = 0;          // B ring (streaming mode)
+      uint32_t sb = 0, pb = 0;          // B ring (streaming mode) / running slot (resident mode)
       uint32_t as = 0, pacc = 0;        // accumulator ring
       uint32_t n_items = 0;
       bool first_item = true;
@@ -332,52 +349,72 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const uint32_t acc_addr = tmem_base + as * (MT * BN);
         uint32_t accumulate = 0;
         if (resident) sb = 0;
-#pragma unroll 1
-        for (int s = 0; s < p.nseg; ++s) {
-          const uint32_t kc = p.seg[s].kc;
+        const bool need_wait = !resident || first_item;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const SegMma gs = g[s];
+          const uint32_t kc = seg_kc[s];
+          const bool halo = seg_halo[s] != 0;
           const uint32_t row16 = kc >> 3;                       // row bytes / 16
-          const bool halo = p.seg[s].taps == 9;
           const uint32_t pitch = halo ? kHaloPitch : TW;
-          const uint32_t swz = kc == 64 ? kSwizzle128B : kSwizzle64B;
-          SegMma gs;
-          gs.a_hi = static_cast<uint32_t>(make_smem_desc(0, pitch * row16 * 16, swz) >> 32);
-          gs.b_hi = static_cast<uint32_t>(make_smem_desc(0, 8 * row16 * 16, swz) >> 32);
-          gs.idesc = make_idesc_f16(p.seg[s].fmt, p.seg[s].fmt, 128, BN);
           const uint32_t mt_step16 = 16 * pitch * row16;
-          const uint32_t nchunks = p.seg[s].nchunks, taps = p.seg[s].taps;
 #pragma unroll 1
-          for (uint32_t ch = 0; ch < nchunks; ++ch) {
+          for (uint32_t ch = 0; ch < seg_chunks[s]; ++ch) {
             LASS_TIMED_WAIT(&a_full[sa], pa, kProfMmaAFull);
             tc_fence_after_sync();
-            uint32_t a_lo = (a_base16 + sa * a_stage16) | kLbo;   // advanced tap by tap: (dy*pitch + dx) rows
-            uint32_t dx = 0;
-#pragma unroll 1
-            for (uint32_t tp = 0; tp < taps; ++tp) {
-              if (!resident || first_item) {
-                LASS_TIMED_WAIT(&b_full[sb], resident ? 0u : pb, kProfMmaBFull);
-                tc_fence_after_sync();
-              }
+            uint32_t a_lo = (a_base16 + sa * a_stage16) | kLbo;
+            if (!need_wait) {
+              // ---- resident weights, steady state: all taps of the chunk in one elected region ----
               const uint32_t b_lo = (b_base16 + sb * b_stage16) | kLbo;
               if (!no_mma && elect_one()) {
-                if (kc == 64) issue_tap<MT, BN, 4>(acc_addr, a_lo, mt_step16, b_lo, gs, accumulate);
-                else issue_tap<MT, BN, 2>(acc_addr, a_lo, mt_step16, b_lo, gs, accumulate);
+                if (halo) {
+                  if (kc == 64) {
+#pragma unroll
+                    for (int tp = 0; tp < 9; ++tp)
+                      issue_tap<MT, BN, 4>(acc_addr, a_lo + ((tp / 3) * kHaloPitch + tp % 3) * 8, 16 * kHaloPitch * 8,
+                                           b_lo + tp * b_stage16, gs, (tp == 0) ? accumulate : 1u);
+                  } else {
+#pragma unroll
+                    for (int tp = 0; tp < 9; ++tp)
+                      issue_tap<MT, BN, 2>(acc_addr, a_lo + ((tp / 3) * kHaloPitch + tp % 3) * 4, 16 * kHaloPitch * 4,
+                                           b_lo + tp * b_stage16, gs, (tp == 0) ? accumulate : 1u);
+                  }
+                } else {
+                  if (kc == 64) issue_tap<MT, BN, 4>(acc_addr, a_lo, 16 * TW * 8, b_lo, gs, accumulate);
+                  else issue_tap<MT, BN, 2>(acc_addr, a_lo, 16 * TW * 4, b_lo, gs, accumulate);
+                }
               }
               __syncwarp();
               accumulate = 1;
-              if (resident) {
-                ++sb;
-              } else {
-                if (elect_one()) umma_commit(&b_empty[sb]);
-                __syncwarp();
-                if (++sb == n_b) {
-                  sb = 0;
-                  pb ^= 1;
+              sb += halo ? 9u : 1u;
+            } else {
+              const uint32_t tap_rows = halo ? 3u : 1u;
+#pragma unroll 1
+              for (uint32_t dy = 0; dy < tap_rows; ++dy) {
+#pragma unroll
+                for (uint32_t dx = 0; dx < 3; ++dx) {
+                  if (dx > 0 && !halo) break;
+                  LASS_TIMED_WAIT(&b_full[sb], resident ? 0u : pb, kProfMmaBFull);
+                  tc_fence_after_sync();
+                  const uint32_t b_lo = (b_base16 + sb * b_stage16) | kLbo;
+                  if (!no_mma && elect_one()) {
+                    if (kc == 64) issue_tap<MT, BN, 4>(acc_addr, a_lo + dx * 8, mt_step16, b_lo, gs, accumulate);
+                    else issue_tap<MT, BN, 2>(acc_addr, a_lo + dx * 4, mt_step16, b_lo, gs, accumulate);
+                  }
+                  __syncwarp();
+                  accumulate = 1;
+                  if (resident) {
+                    ++sb;
+                  } else {
+                    if (elect_one()) umma_commit(&b_empty[sb]);
+                    __syncwarp();
+                    if (++sb == n_b) {
+                      sb = 0;
+                      pb ^= 1;
+                    }
+                  }
                 }
-              }
-              a_lo += row16;
-              if (++dx == 3) {
-                dx = 0;
-                a_lo += (pitch - 3) * row16;
+                a_lo += pitch * row16;
               }
             }
             if (elect_one()) umma_commit(&a_empty[sa]);
@@ -408,8 +445,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     }
   } else {
     // =========================== epilogue ===========================
-    const int q = warp & 3;
-    const int et = threadIdx.x - 64;  // 0..127
+    // Two groups of four warps; group g drains accumulator stage g (items g, g + 2, ... of this CTA), so two
+    // items are in the epilogue at once and every SM sub-partition has two epilogue warps to overlap latencies.
+    const int grp = (warp - 2) >> 2;
+    const int q = warp & 3;                          // TMEM lane quarter this warp may access
+    const int et = (threadIdx.x - 64) & 127;         // thread index within the group
     const int hl = q * 4 + (lane >> 3);
     const int wl = lane & 7;
     const int Ho = p.H * p.up_h, Wo = p.W * p.up_w;
@@ -417,15 +457,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const bool pooling = ((p.pool_raw.ptr != nullptr) || (p.pool_act.ptr != nullptr)) && !(p.debug_flags & 8);
     const bool no_store = (p.debug_flags & 16) != 0;
     const float pool_scale = 1.0f / (float)(p.pool_h * p.pool_w);
-    uint32_t acc_it = 0;
+    const uint32_t as = (AS == 2) ? (uint32_t)grp : 0u;
+    EpiTables<BN>* gtabs = tabs + 2 * grp;
+    uint32_t uses = 0;                               // completed uses of accumulator stage `as` by this group
     int tab_b = -1, tab_n0 = -1;
     uint32_t tab_sel = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+    for (int item = blockIdx.x + (AS == 2 ? grp : 0) * (int)gridDim.x; item < p.num_items;
+         item += (AS == 2 ? 2 : 1) * (int)gridDim.x) {
+      if (AS == 1 && grp == 1) break;
       const Item it = decode_item<MT>(p, item, BN);
       // ---- (re)stage the per-(clip, N tile) tables; double-buffered so one named barrier per change suffices ----
       if (it.b != tab_b || it.n0 != tab_n0) {
         tab_sel ^= 1u;
-        EpiTables<BN>& t = tabs[tab_sel];
+        EpiTables<BN>& t = gtabs[tab_sel];
         for (int c = et; c < BN; c += 128) {
           const int n = it.n0 + c;
           const bool in = n < p.ncols;
@@ -441,15 +485,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         if (p.after_w != nullptr && et < 3) t.after_b[et] = __ldg(p.after_b + et);
         tab_b = it.b;
         tab_n0 = it.n0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
-      const EpiTables<BN>& tb = tabs[tab_sel];
-      const uint32_t as = acc_it % AS;
-      if (q == 0 && lane == 0) {
-        LASS_TIMED_WAIT(&acc_full[as], (acc_it / AS) & 1, kProfEpiAccFull);
+      const EpiTables<BN>& tb = gtabs[tab_sel];
+      if (q == 0 && lane == 0 && grp == 0) {
+        LASS_TIMED_WAIT(&acc_full[as], uses & 1, kProfEpiAccFull);
       }
       __syncwarp();
-      mbar_wait(&acc_full[as], (acc_it / AS) & 1);
+      mbar_wait(&acc_full[as], uses & 1);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
@@ -495,18 +539,75 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             }
           }
           if (pooling) {
+            // Butterfly transpose-reduce: after exchanging with the horizontal neighbour (lane ^ 1) each lane owns the
+            // pair sums of 16 of the 32 channels; after the vertical exchange (lane ^ 8) the 2x2 sums of 8 channels.
+            // Every lane then finishes and stores its own 8 (or 16) channels of the pooled pixel.
+            const bool odd_w = (lane & 1) != 0;
+            float s1[16];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 1);   // pool_w is always 2
-            if (p.pool_h == 2) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], 8);
+            for (int j = 0; j < 16; ++j) {
+              const float send = odd_w ? v[j] : v[16 + j];
+              const float mine = odd_w ? v[16 + j] : v[j];
+              s1[j] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
             }
+            const int hp = h / p.pool_h, wp = w >> 1;
+            if (p.pool_h == 2) {
+              const bool odd_h = (lane & 8) != 0;
+              float s2[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] *= pool_scale;
-            const bool owner = valid && ((wl & (p.pool_w - 1)) == 0) && ((hl & (p.pool_h - 1)) == 0);
-            if (p.pool_raw.ptr != nullptr) out_raw32(p.pool_raw, it.b, h / p.pool_h, w / p.pool_w, Hp, Wp, c, v, owner);
-            if (p.pool_act.ptr != nullptr)
-              out_act32(p.pool_act, tb.sc_pool + c0, tb.sh_pool + c0, it.b, h / p.pool_h, w / p.pool_w, Hp, Wp, c, v, owner);
+              for (int j = 0; j < 8; ++j) {
+                const float send = odd_h ? s1[j] : s1[8 + j];
+                const float mine = odd_h ? s1[8 + j] : s1[j];
+                s2[j] = (mine + __shfl_xor_sync(0xffffffffu, send, 8)) * pool_scale;
+              }
+              const int cb = (odd_w ? 16 : 0) + (odd_h ? 8 : 0);     // first of this lane's 8 channels within the chunk
+              if (valid) {
+                if (p.pool_raw.ptr != nullptr) {
+                  uint16_t* base = reinterpret_cast<uint16_t*>(p.pool_raw.ptr) +
+                                   (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_raw.cstride + p.pool_raw.coff + c + cb;
+                  *reinterpret_cast<uint4*>(base) = make_uint4(pack_f16x2_sat(s2[0], s2[1]), pack_f16x2_sat(s2[2], s2[3]),
+                                                               pack_f16x2_sat(s2[4], s2[5]), pack_f16x2_sat(s2[6], s2[7]));
+                }
+                if (p.pool_act.ptr != nullptr) {
+                  uint32_t wv[4];
+#pragma unroll
+                  for (int j = 0; j < 8; j += 2) {
+                    const float t0 = fmaf(tb.sc_pool[c0 + cb + j], s2[j], tb.sh_pool[c0 + cb + j]);
+                    const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], s2[j + 1], tb.sh_pool[c0 + cb + j + 1]);
+                    wv[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
+                  }
+                  uint16_t* base = reinterpret_cast<uint16_t*>(p.pool_act.ptr) +
+                                   (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_act.cstride + p.pool_act.coff + c + cb;
+                  *reinterpret_cast<uint4*>(base) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                }
+              }
+            } else {
+              const int cb = odd_w ? 16 : 0;                        // this lane's 16 channels within the chunk
+              if (valid) {
+                if (p.pool_raw.ptr != nullptr) {
+                  uint32_t wv[8];
+#pragma unroll
+                  for (int j = 0; j < 16; j += 2) wv[j / 2] = pack_f16x2_sat(s1[j] * pool_scale, s1[j + 1] * pool_scale);
+                  uint16_t* base = reinterpret_cast<uint16_t*>(p.pool_raw.ptr) +
+                                   (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_raw.cstride + p.pool_raw.coff + c + cb;
+                  reinterpret_cast<uint4*>(base)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                  reinterpret_cast<uint4*>(base)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+                }
+                if (p.pool_act.ptr != nullptr) {
+                  uint32_t wv[8];
+#pragma unroll
+                  for (int j = 0; j < 16; j += 2) {
+                    const float t0 = fmaf(tb.sc_pool[c0 + cb + j], s1[j] * pool_scale, tb.sh_pool[c0 + cb + j]);
+                    const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], s1[j + 1] * pool_scale, tb.sh_pool[c0 + cb + j + 1]);
+                    wv[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
+                  }
+                  uint16_t* base = reinterpret_cast<uint16_t*>(p.pool_act.ptr) +
+                                   (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_act.cstride + p.pool_act.coff + c + cb;
+                  reinterpret_cast<uint4*>(base)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                  reinterpret_cast<uint4*>(base)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+                }
+              }
+            }
           }
         }
         if (p.after_w != nullptr && valid && !(p.debug_flags & 1)) {
@@ -520,9 +621,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
-      ++acc_it;
+      ++uses;
     }
-    if (prof && q == 0 && lane == 0) {
+    if (prof && q == 0 && lane == 0 && grp == 0) {
       long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
       dst[kProfEpiAccFull] = pc[kProfEpiAccFull];
       dst[kProfEpiTotal] = clock64() - t_start;
@@ -707,7 +808,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   // ---- shared-memory budget: weights resident if every tile of an item fits, else a streaming ring ----
   const size_t kBudget = 220 * 1024;
   const size_t fixed = 1024 /*alignment slack*/ + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 +
-                       2 * ((size_t)5 * BN + 3 * 32 + 4) * sizeof(float) + 64;
+                       4 * ((size_t)5 * BN + 3 * 32 + 4) * sizeof(float) + 64;
   const size_t min_a = 2 * (size_t)p.a_stage_bytes;
   p.b_resident = (p.n_tiles == 1 && b_tiles_per_item <= kMaxB &&
                   fixed + min_a + (size_t)b_tiles_per_item * p.b_stage_bytes <= kBudget)

@@ -75,10 +75,73 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constan
   }
 }
 
+// Throughput microbenchmark: `iters` back-to-back tcgen05.mma (M = 128) with the given operand layout, alternating
+// between `nacc` accumulators and advancing K by 32 B per instruction like a real k-loop (4 steps, then wrap).
+__global__ void __launch_bounds__(128, 1) umma_bench_kernel(int n, int kc, int swizzle, int a_start_bytes, int a_sbo,
+                                                            int iters, int nacc, long long* cycles_out) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = smem;               // 64 KiB of (zero) operand data
+  unsigned char* sB = smem + 64 * 1024;   // 32 KiB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 32 * 1024);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int warp = threadIdx.x >> 5;
+  for (int i = threadIdx.x; i < 96 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  fence_proxy_async_smem();
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_acc = *tmem_slot;
+  if (warp == 0) {
+    const uint32_t idesc = make_idesc_f16(kFmtBF16, kFmtBF16, 128, n);
+    const int row_bytes = kc * 2;
+    const int ksteps = kc / 16;
+    const uint64_t da0 = make_smem_desc(smem_u32(sA) + a_start_bytes, a_sbo, swizzle, 0);
+    const uint64_t db0 = make_smem_desc(smem_u32(sB), 8 * row_bytes, swizzle, 0);
+    const long long t0 = clock64();
+    if (elect_one()) {
+      for (int i = 0; i < iters; ++i) {
+        const int ks = i % ksteps;
+        umma_f16(tmem_acc + (i % nacc) * n, da0 + 2 * ks, db0 + 2 * ks, idesc, 1);
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+    mbar_wait(bar, 0);
+    const long long t1 = clock64();
+    if (threadIdx.x == 0) cycles_out[blockIdx.x] = t1 - t0;
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_acc, 512);
+  }
+}
+
 }  // namespace
 }  // namespace lass
 
 using namespace lass;
+
+extern "C" int lass_debug_umma_bench(int n, int kc, int swizzle_mode, int a_start_bytes, int a_sbo, int iters, int nacc,
+                                     int grid, long long* cycles_out, void* stream) {
+  if (!cycles_out || n % 16 || n < 16 || n > 256 || (kc != 32 && kc != 64) || nacc < 1 || nacc * n > 512 || grid < 1)
+    return set_error(LASS_ERR_ARG, "umma_bench: bad arguments");
+  const size_t smem = 1024 + 96 * 1024 + 256;
+  cudaError_t e = cudaFuncSetAttribute(umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "umma_bench smem attribute");
+  umma_bench_kernel<<<grid, 128, smem, (cudaStream_t)stream>>>(n, kc, swizzle_mode, a_start_bytes, a_sbo, iters, nacc, cycles_out);
+  return set_cuda_error(cudaGetLastError(), "umma_bench launch");
+}
 
 extern "C" int lass_debug_umma_probe(const void* A, int a_rows, const void* Bm, int n, int kc, int swizzle_mode,
                                               int a_start_bytes, int a_sbo, int a_base_offset, int b_sbo, int fmt_fp16,
