@@ -42,6 +42,8 @@ constexpr int kThreads = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps
 constexpr int kMaxA = 8;
 constexpr int kMaxB = 40;
 constexpr float kSlope = 0.01f;
+constexpr int kStageWarpBytes = 6 * 1024;   // per epilogue warp: full_raw 2K | full_act 2K | pool_raw 1K | pool_act 1K
+constexpr int kEpiWarps = 8;
 
 struct SegDev {
   CUtensorMap tmA;  // (C, W, H, B) view of the source channels
@@ -58,6 +60,8 @@ struct OutDev {
 
 struct ConvParams {
   SegDev seg[2];
+  // TMA-store tensor maps: [0,1] full_raw (dy = 0,1), [2,3] full_act (dy = 0,1), [4] pool_raw, [5] pool_act
+  CUtensorMap tm_out[6];
   OutDev full_raw, full_act, pool_raw, pool_act;
   const float* bias;
   const float* after_w;
@@ -68,10 +72,12 @@ struct ConvParams {
   int B, H, W, ncols;
   int tiles_h, tiles_w, pix_tiles, n_tiles, num_items;
   int a_stages, b_stages, b_resident;
+  int tma_store;   // 1: 16-bit outputs leave through per-warp shared-memory staging + TMA stores
   uint32_t a_stage_bytes, b_stage_bytes;
   int up_h, up_w, group_c;
   int pool_h, pool_w;
-  int debug_flags;  // timing experiments only: 1 epilogue idle, 2 no MMA, 4 no A loads, 8 no pooled outputs, 16 no stores
+  int debug_flags;  // timing experiments only: 1 epilogue idle, 2 no MMA, 4 no A loads, 8 no pooled outputs, 16 no stores,
+                    // 32 (host side) direct global stores instead of TMA stores
 };
 
 struct Item {
@@ -117,18 +123,13 @@ __device__ __forceinline__ void store32(const OutDev& o, int b, int ho, int wo, 
 }
 
 // raw output: the value itself as saturating fp16 (residual / skip stream)
-__device__ __forceinline__ void out_raw32(const OutDev& o, int b, int ho, int wo, int Ho, int Wo, int c, const float* v,
-                                          bool valid) {
-  uint32_t w[16];
+__device__ __forceinline__ void pack_raw32(const float* v, uint32_t* w) {
 #pragma unroll
   for (int j = 0; j < 16; ++j) w[j] = pack_f16x2_sat(v[2 * j], v[2 * j + 1]);
-  store32(o, b, ho, wo, Ho, Wo, c, w, valid);
 }
 
 // activated output: lrelu(sc * v + sh) as bf16 (operand of the next convolution)
-__device__ __forceinline__ void out_act32(const OutDev& o, const float* sc, const float* sh, int b, int ho, int wo,
-                                          int Ho, int Wo, int c, const float* v, bool valid) {
-  uint32_t w[16];
+__device__ __forceinline__ void pack_act32(const float* sc, const float* sh, const float* v, uint32_t* w) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 a = *reinterpret_cast<const float4*>(sc + j);
@@ -138,7 +139,16 @@ __device__ __forceinline__ void out_act32(const OutDev& o, const float* sc, cons
     w[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
     w[j / 2 + 1] = pack_bf16x2(fmaxf(t2, kSlope * t2), fmaxf(t3, kSlope * t3));
   }
-  store32(o, b, ho, wo, Ho, Wo, c, w, valid);
+}
+
+// Staging tile of one warp: rows of 64 B (32 channels), CU_TENSOR_MAP_SWIZZLE_64B pattern (16 B chunk index XOR
+// address bits [7,8]) so that 32 lanes writing one row each are bank-conflict free.
+__device__ __forceinline__ uint4* stage_slot(unsigned char* tile, int row, int piece) {
+  return reinterpret_cast<uint4*>(tile + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+}
+__device__ __forceinline__ void stage_row32(unsigned char* tile, int row, const uint32_t* w) {
+#pragma unroll
+  for (int pc = 0; pc < 4; ++pc) *stage_slot(tile, row, pc) = make_uint4(w[4 * pc], w[4 * pc + 1], w[4 * pc + 2], w[4 * pc + 3]);
 }
 
 // One tcgen05.mma with descriptors given as (low word = start address >> 4 | LBO, high word = SBO | version | swizzle).
@@ -209,6 +219,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
   EpiTables<BN>* tabs = reinterpret_cast<EpiTables<BN>*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);  // [group][2]
+  unsigned char* stage_base = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(tabs + 4) + 1023) & ~uintptr_t(1023));                                     // [8 warps][6 KiB]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -459,6 +471,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const float pool_scale = 1.0f / (float)(p.pool_h * p.pool_w);
     const uint32_t as = (AS == 2) ? (uint32_t)grp : 0u;
     EpiTables<BN>* gtabs = tabs + 2 * grp;
+    const bool tma_store = p.tma_store != 0;
+    unsigned char* stg = stage_base + (size_t)(warp - 2) * kStageWarpBytes;
     uint32_t uses = 0;                               // completed uses of accumulator stage `as` by this group
     int tab_b = -1, tab_n0 = -1;
     uint32_t tab_sel = 0;
@@ -528,8 +542,40 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             ho = h * p.up_h + dy;
             wo = w * p.up_w + (g - dy * p.up_w);
           }
-          if (p.full_raw.ptr != nullptr) out_raw32(p.full_raw, it.b, ho, wo, Ho, Wo, c, v, valid);
-          if (p.full_act.ptr != nullptr) out_act32(p.full_act, tb.sc_full + c0, tb.sh_full + c0, it.b, ho, wo, Ho, Wo, c, v, valid);
+          const int hw0 = it.h0 + mt * 16 + q * 4;            // first image row of this warp's 4 x 8 pixel patch
+          int grp_dy = 0, grp_dx = 0;
+          if (p.up_h * p.up_w > 1) {
+            const int g = n / p.group_c;
+            grp_dy = g / p.up_w;
+            grp_dx = g - grp_dy * p.up_w;
+          }
+          if (tma_store) {
+            // staging buffers are reused chunk after chunk: wait until the previous TMA stores have read them
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
+          if (p.full_raw.ptr != nullptr) {
+            uint32_t wv[16];
+            pack_raw32(v, wv);
+            if (tma_store) stage_row32(stg, lane, wv);
+            else store32(p.full_raw, it.b, ho, wo, Ho, Wo, c, wv, valid);
+          }
+          if (p.full_act.ptr != nullptr) {
+            uint32_t wv[16];
+            pack_act32(tb.sc_full + c0, tb.sh_full + c0, v, wv);
+            if (tma_store) stage_row32(stg + 2048, lane, wv);
+            else store32(p.full_act, it.b, ho, wo, Ho, Wo, c, wv, valid);
+          }
+          if (tma_store && (p.full_raw.ptr != nullptr || p.full_act.ptr != nullptr)) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+              if (p.full_raw.ptr != nullptr) tma_store_5d(&p.tm_out[grp_dy], stg, c, grp_dx, it.w0, hw0, it.b);
+              if (p.full_act.ptr != nullptr) tma_store_5d(&p.tm_out[2 + grp_dy], stg + 2048, c, grp_dx, it.w0, hw0, it.b);
+              if (!pooling) tma_store_commit();
+            }
+            __syncwarp();
+          }
           if (p.after_w != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -561,52 +607,76 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 s2[j] = (mine + __shfl_xor_sync(0xffffffffu, send, 8)) * pool_scale;
               }
               const int cb = (odd_w ? 16 : 0) + (odd_h ? 8 : 0);     // first of this lane's 8 channels within the chunk
-              if (valid) {
-                if (p.pool_raw.ptr != nullptr) {
-                  uint16_t* base = reinterpret_cast<uint16_t*>(p.pool_raw.ptr) +
-                                   (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_raw.cstride + p.pool_raw.coff + c + cb;
-                  *reinterpret_cast<uint4*>(base) = make_uint4(pack_f16x2_sat(s2[0], s2[1]), pack_f16x2_sat(s2[2], s2[3]),
-                                                               pack_f16x2_sat(s2[4], s2[5]), pack_f16x2_sat(s2[6], s2[7]));
-                }
-                if (p.pool_act.ptr != nullptr) {
-                  uint32_t wv[4];
+              const int pp = ((lane >> 4) << 2) + (wl >> 1);         // pooled pixel within the warp's 2 x 4 pooled patch
+              uint4 praw, pact;
+              praw = make_uint4(pack_f16x2_sat(s2[0], s2[1]), pack_f16x2_sat(s2[2], s2[3]), pack_f16x2_sat(s2[4], s2[5]),
+                                pack_f16x2_sat(s2[6], s2[7]));
+              {
+                uint32_t wv[4];
 #pragma unroll
-                  for (int j = 0; j < 8; j += 2) {
-                    const float t0 = fmaf(tb.sc_pool[c0 + cb + j], s2[j], tb.sh_pool[c0 + cb + j]);
-                    const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], s2[j + 1], tb.sh_pool[c0 + cb + j + 1]);
-                    wv[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
-                  }
-                  uint16_t* base = reinterpret_cast<uint16_t*>(p.pool_act.ptr) +
-                                   (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_act.cstride + p.pool_act.coff + c + cb;
-                  *reinterpret_cast<uint4*>(base) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+                for (int j = 0; j < 8; j += 2) {
+                  const float t0 = fmaf(tb.sc_pool[c0 + cb + j], s2[j], tb.sh_pool[c0 + cb + j]);
+                  const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], s2[j + 1], tb.sh_pool[c0 + cb + j + 1]);
+                  wv[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
                 }
+                pact = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+              }
+              if (tma_store) {
+                if (p.pool_raw.ptr != nullptr) *stage_slot(stg + 4096, pp, cb >> 3) = praw;
+                if (p.pool_act.ptr != nullptr) *stage_slot(stg + 5120, pp, cb >> 3) = pact;
+              } else if (valid) {
+                if (p.pool_raw.ptr != nullptr)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.pool_raw.ptr) +
+                                            (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_raw.cstride + p.pool_raw.coff + c + cb) = praw;
+                if (p.pool_act.ptr != nullptr)
+                  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.pool_act.ptr) +
+                                            (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_act.cstride + p.pool_act.coff + c + cb) = pact;
               }
             } else {
               const int cb = odd_w ? 16 : 0;                        // this lane's 16 channels within the chunk
-              if (valid) {
-                if (p.pool_raw.ptr != nullptr) {
-                  uint32_t wv[8];
+              const int pp = ((lane >> 3) << 2) + (wl >> 1);         // pooled pixel within the warp's 4 x 4 pooled patch
+              uint32_t wr[8], wa[8];
 #pragma unroll
-                  for (int j = 0; j < 16; j += 2) wv[j / 2] = pack_f16x2_sat(s1[j] * pool_scale, s1[j + 1] * pool_scale);
-                  uint16_t* base = reinterpret_cast<uint16_t*>(p.pool_raw.ptr) +
-                                   (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_raw.cstride + p.pool_raw.coff + c + cb;
-                  reinterpret_cast<uint4*>(base)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-                  reinterpret_cast<uint4*>(base)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+              for (int j = 0; j < 16; j += 2) {
+                const float u0 = s1[j] * pool_scale, u1 = s1[j + 1] * pool_scale;
+                wr[j / 2] = pack_f16x2_sat(u0, u1);
+                const float t0 = fmaf(tb.sc_pool[c0 + cb + j], u0, tb.sh_pool[c0 + cb + j]);
+                const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], u1, tb.sh_pool[c0 + cb + j + 1]);
+                wa[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
+              }
+              if (tma_store) {
+                if (p.pool_raw.ptr != nullptr) {
+                  *stage_slot(stg + 4096, pp, cb >> 3) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
+                  *stage_slot(stg + 4096, pp, (cb >> 3) + 1) = make_uint4(wr[4], wr[5], wr[6], wr[7]);
                 }
                 if (p.pool_act.ptr != nullptr) {
-                  uint32_t wv[8];
-#pragma unroll
-                  for (int j = 0; j < 16; j += 2) {
-                    const float t0 = fmaf(tb.sc_pool[c0 + cb + j], s1[j] * pool_scale, tb.sh_pool[c0 + cb + j]);
-                    const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], s1[j + 1] * pool_scale, tb.sh_pool[c0 + cb + j + 1]);
-                    wv[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
-                  }
-                  uint16_t* base = reinterpret_cast<uint16_t*>(p.pool_act.ptr) +
-                                   (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_act.cstride + p.pool_act.coff + c + cb;
-                  reinterpret_cast<uint4*>(base)[0] = make_uint4(wv[0], wv[1], wv[2], wv[3]);
-                  reinterpret_cast<uint4*>(base)[1] = make_uint4(wv[4], wv[5], wv[6], wv[7]);
+                  *stage_slot(stg + 5120, pp, cb >> 3) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+                  *stage_slot(stg + 5120, pp, (cb >> 3) + 1) = make_uint4(wa[4], wa[5], wa[6], wa[7]);
+                }
+              } else if (valid) {
+                if (p.pool_raw.ptr != nullptr) {
+                  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.pool_raw.ptr) +
+                                                        (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_raw.cstride + p.pool_raw.coff + c + cb);
+                  dst[0] = make_uint4(wr[0], wr[1], wr[2], wr[3]);
+                  dst[1] = make_uint4(wr[4], wr[5], wr[6], wr[7]);
+                }
+                if (p.pool_act.ptr != nullptr) {
+                  uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.pool_act.ptr) +
+                                                        (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_act.cstride + p.pool_act.coff + c + cb);
+                  dst[0] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
+                  dst[1] = make_uint4(wa[4], wa[5], wa[6], wa[7]);
                 }
               }
+            }
+            if (tma_store) {
+              fence_proxy_async_smem();
+              __syncwarp();
+              if (elect_one()) {
+                if (p.pool_raw.ptr != nullptr) tma_store_4d(&p.tm_out[4], stg + 4096, c, it.w0 >> 1, hw0 / p.pool_h, it.b);
+                if (p.pool_act.ptr != nullptr) tma_store_4d(&p.tm_out[5], stg + 5120, c, it.w0 >> 1, hw0 / p.pool_h, it.b);
+                tma_store_commit();
+              }
+              __syncwarp();
             }
           }
         }
@@ -623,6 +693,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       ++uses;
     }
+    if (tma_store && lane == 0) tma_store_wait_all();
     if (prof && q == 0 && lane == 0 && grp == 0) {
       long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
       dst[kProfEpiAccFull] = pc[kProfEpiAccFull];
@@ -805,29 +876,68 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   p.a_stage_bytes = (a_stage + 1023u) & ~1023u;
   p.b_stage_bytes = (b_stage + 1023u) & ~1023u;
 
-  // ---- shared-memory budget: weights resident if every tile of an item fits, else a streaming ring ----
+  // ---- shared-memory budget: weights resident if every tile of an item fits, else a streaming ring; the per-warp
+  //      TMA-store staging (48 KiB) is taken when it still leaves a healthy pipeline ----
   const size_t kBudget = 220 * 1024;
-  const size_t fixed = 1024 /*alignment slack*/ + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 +
-                       4 * ((size_t)5 * BN + 3 * 32 + 4) * sizeof(float) + 64;
-  const size_t min_a = 2 * (size_t)p.a_stage_bytes;
-  p.b_resident = (p.n_tiles == 1 && b_tiles_per_item <= kMaxB &&
-                  fixed + min_a + (size_t)b_tiles_per_item * p.b_stage_bytes <= kBudget)
-                     ? 1
-                     : 0;
-  if (p.b_resident) {
-    p.b_stages = b_tiles_per_item;
-    size_t rest = kBudget - fixed - (size_t)p.b_stages * p.b_stage_bytes;
-    p.a_stages = (int)(rest / p.a_stage_bytes);
-    if (p.a_stages > 4) p.a_stages = 4;
-  } else {
+  const size_t fixed_base = 1024 /*alignment slack*/ + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 +
+                            4 * ((size_t)5 * BN + 3 * 32 + 4) * sizeof(float) + 64;
+  const size_t stage_bytes = 1024 + (size_t)kEpiWarps * kStageWarpBytes;
+  const bool has_16bit_out = l.full_raw.ptr || l.full_act.ptr || l.pool_raw.ptr || l.pool_act.ptr;
+  size_t fixed = fixed_base;
+  const bool want_tma = has_16bit_out && !(g_debug_flags & 32);
+  // preference order: resident weights + TMA stores, resident weights, streaming + TMA stores, streaming
+  for (int attempt = 0; attempt < 4; ++attempt) {
+    const bool try_resident = attempt < 2;
+    p.tma_store = ((attempt & 1) == 0 && want_tma) ? 1 : 0;
+    if ((attempt & 1) == 0 && !want_tma) continue;
+    fixed = fixed_base + (p.tma_store ? stage_bytes : 0);
+    const size_t min_a = 2 * (size_t)p.a_stage_bytes;
+    if (try_resident) {
+      if (!(p.n_tiles == 1 && b_tiles_per_item <= kMaxB &&
+            fixed + min_a + (size_t)b_tiles_per_item * p.b_stage_bytes <= kBudget))
+        continue;
+      p.b_resident = 1;
+      p.b_stages = b_tiles_per_item;
+      size_t rest = kBudget - fixed - (size_t)p.b_stages * p.b_stage_bytes;
+      p.a_stages = (int)(rest / p.a_stage_bytes);
+      if (p.a_stages > 4) p.a_stages = 4;
+      break;
+    }
+    p.b_resident = 0;
     p.a_stages = 2;
-    size_t rest = kBudget - fixed - (size_t)p.a_stages * p.a_stage_bytes;
+    size_t rest = kBudget > fixed + min_a ? kBudget - fixed - min_a : 0;
     p.b_stages = (int)(rest / p.b_stage_bytes);
     if (p.b_stages > 12) p.b_stages = 12;
-    if (p.b_stages < 2) {
-      delete cp;
-      return set_error(LASS_ERR_ARG, "conv: tile does not fit in shared memory");
+    if (p.b_stages >= 5 || !p.tma_store) break;      // staging would starve the weight ring: fall back to direct stores
+  }
+  if (!p.b_resident && p.b_stages < 2) {
+    delete cp;
+    return set_error(LASS_ERR_ARG, "conv: tile does not fit in shared memory");
+  }
+  if (p.tma_store) {
+    const int Ho = l.H * l.up_h, Wo = l.W * l.up_w;
+    auto full_map = [&](CUtensorMap* tm, const ConvOut& o, int dy) -> int {
+      const char* base = reinterpret_cast<const char*>(o.ptr) + (size_t)o.coff * 2 + (size_t)dy * Wo * o.cstride * 2;
+      uint64_t dims[5] = {(uint64_t)l.group_c, (uint64_t)l.up_w, (uint64_t)l.W, (uint64_t)l.H, (uint64_t)l.B};
+      uint64_t strides[4] = {(uint64_t)o.cstride * 2, (uint64_t)l.up_w * o.cstride * 2,
+                             (uint64_t)l.up_h * Wo * o.cstride * 2, (uint64_t)Ho * Wo * o.cstride * 2};
+      uint32_t box[5] = {32, 1, TW, 4, 1};
+      return make_tensor_map(tm, base, 2, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    };
+    auto pool_map = [&](CUtensorMap* tm, const ConvOut& o) -> int {
+      const int Hp = l.H / l.pool_h, Wp = l.W / l.pool_w;
+      const char* base = reinterpret_cast<const char*>(o.ptr) + (size_t)o.coff * 2;
+      uint64_t dims[4] = {(uint64_t)l.ncols, (uint64_t)Wp, (uint64_t)Hp, (uint64_t)l.B};
+      uint64_t strides[3] = {(uint64_t)o.cstride * 2, (uint64_t)o.cstride * 2 * Wp, (uint64_t)o.cstride * 2 * Wp * Hp};
+      uint32_t box[4] = {32, TW / 2, (uint32_t)(l.pool_h == 2 ? 2 : 4), 1};
+      return make_tensor_map(tm, base, 2, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    };
+    for (int dy = 0; dy < l.up_h; ++dy) {
+      if (l.full_raw.ptr && (e = full_map(&p.tm_out[dy], l.full_raw, dy))) { delete cp; return e; }
+      if (l.full_act.ptr && (e = full_map(&p.tm_out[2 + dy], l.full_act, dy))) { delete cp; return e; }
     }
+    if (l.pool_raw.ptr && (e = pool_map(&p.tm_out[4], l.pool_raw))) { delete cp; return e; }
+    if (l.pool_act.ptr && (e = pool_map(&p.tm_out[5], l.pool_act))) { delete cp; return e; }
   }
   cp->smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes;
   cp->fn = kc.fn;

@@ -20,7 +20,8 @@ namespace lass {
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
 
 struct MaskIstftArgs {
   const float* feat;  // 3 planes
@@ -33,26 +34,32 @@ struct MaskIstftArgs {
   const float* window;  // [N] synthesis window (periodic Hann), NOT scaled
   const cpx* tw;        // [N] exp(+2 pi i j / N)
   float* out;           // (B, L)
-  int T, F, N, log2M, hop, L, FR, G;
+  int T, F, N, log2M, hop, L, FR;
 };
 
-__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// Fast-math forms (errors ~1e-6 relative, far inside the 1e-4 bar; checked by tests/test_gpu_spectral.py).
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float t = __expf(-2.0f * fabsf(x));
+  return copysignf(__fdividef(1.0f - t, 1.0f + t), x);
+}
 
+// One warp per frame: mask math -> half spectrum -> Hermitian pack -> Stockham inverse FFT, all in the warp's own
+// shared-memory buffers with __syncwarp only; block barriers only around the overlap-add of each round of kWarps frames.
 __global__ void __launch_bounds__(kThreads) mask_istft_kernel(const MaskIstftArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.N, M = N >> 1, hop = a.hop;
   const int S = a.FR * hop;
-  const int G = a.G;
-  // smem carve-up
   cpx* tw = reinterpret_cast<cpx*>(smem_raw);          // N
   float* win = reinterpret_cast<float*>(tw + N);       // N
   float* ola = win + N;                                // S
-  cpx* bufA = reinterpret_cast<cpx*>(ola + S);         // G * M
-  cpx* bufB = bufA + (size_t)G * M;                    // G * (M + 1)   (also holds the half spectrum X)
+  cpx* bufs = reinterpret_cast<cpx*>(ola + S);         // kWarps * (2M + 2)
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  cpx* bufA = bufs + (size_t)warp * (2 * M + 2);
+  cpx* bufB = bufA + M;                                // M + 1 (+1 pad): half spectrum X, then FFT ping-pong
 
-  const int tid = threadIdx.x;
   const int b = blockIdx.y;
-  const long long pos0 = (long long)blockIdx.x * S;  // first padded sample owned by this CTA
+  const long long pos0 = (long long)blockIdx.x * S;    // first padded-signal sample owned by this CTA
 
   for (int i = tid; i < N; i += kThreads) {
     tw[i] = a.tw[i];
@@ -63,7 +70,7 @@ __global__ void __launch_bounds__(kThreads) mask_istft_kernel(const MaskIstftArg
   // frames overlapping [pos0, pos0 + S): t*hop + N > pos0  and  t*hop < pos0 + S
   long long t_lo = (pos0 - N) / hop + 1;
   if (pos0 - N < 0) t_lo = 0;
-  long long t_hi = (pos0 + S - 1) / hop;  // inclusive
+  long long t_hi = (pos0 + S - 1) / hop;               // inclusive
   if (t_hi > a.T - 1) t_hi = a.T - 1;
   __syncthreads();
 
@@ -72,66 +79,78 @@ __global__ void __launch_bounds__(kThreads) mask_istft_kernel(const MaskIstftArg
   const float* sinb = a.sinp + (size_t)b * a.T * a.F;
   const float* featb = a.feat + (size_t)b * a.feat_bstride;
   const int passes = fft_num_passes(a.log2M);
+  const bool result_in_A = (passes & 1) == 0;
 
-  for (long long tb = t_lo; tb <= t_hi; tb += G) {
-    const int g_cnt = (int)((t_hi - tb + 1 < G) ? (t_hi - tb + 1) : G);
-    // 1. masked half spectrum X[k], k in [0, M]  (models/resunet.py:469-495)
-    cpx* X = bufB;
-    for (int i = tid; i < g_cnt * (M + 1); i += kThreads) {
-      const int g = i / (M + 1), k = i - g * (M + 1);
-      const size_t t = (size_t)(tb + g);
-      cpx y{0.0f, 0.0f};
-      if (k < a.F) {
-        float x0 = 0.0f, x1 = 0.0f, x2 = 0.0f;
-        if (k < a.feat_F) {
-          const float* fp = featb + t * a.feat_tstride + k;
-          x0 = __ldg(fp);
-          x1 = __ldg(fp + a.feat_cstride);
-          x2 = __ldg(fp + 2 * a.feat_cstride);
+  for (long long tb = t_lo; tb <= t_hi; tb += kWarps) {
+    const long long t = tb + warp;
+    if (t <= t_hi) {
+      // 1. masked half spectrum X[k], k in [0, M]  (models/resunet.py:469-495)
+      cpx* X = bufB;
+      const float* fp = featb + (size_t)t * a.feat_tstride;
+      const size_t o = (size_t)t * a.F;
+      // four bins per lane per iteration, all 24 loads issued before any math (memory-level parallelism)
+      for (int k0 = lane; k0 <= M; k0 += 128) {
+        float x0[4], x1[4], x2[4], sp[4], cs[4], sn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + 32 * u;
+          const bool inF = k < a.F, inX = k < a.feat_F;
+          x0[u] = inX ? __ldg(fp + k) : 0.0f;
+          x1[u] = inX ? __ldg(fp + a.feat_cstride + k) : 0.0f;
+          x2[u] = inX ? __ldg(fp + 2 * a.feat_cstride + k) : 0.0f;
+          sp[u] = inF ? __ldg(magb + o + k) : 0.0f;
+          cs[u] = inF ? __ldg(cosb + o + k) : 0.0f;
+          sn[u] = inF ? __ldg(sinb + o + k) : 0.0f;
         }
-        const size_t o = t * a.F + k;
-        const float sp = __ldg(magb + o), cs = __ldg(cosb + o), sn = __ldg(sinb + o);
-        const float mask_mag = sigmoidf_acc(x0);
-        const float mr = tanhf(x1), mi = tanhf(x2);
-        // torchlibrosa magphase: clamp(|m|, 1e-10)
-        const float mm = fmaxf(sqrtf(mr * mr + mi * mi), 1e-10f);
-        const float mc = mr / mm, ms = mi / mm;
-        const float oc = cs * mc - sn * ms;
-        const float os = sn * mc + cs * ms;
-        const float om = fmaxf(sp * mask_mag, 0.0f);
-        y.x = om * oc;
-        y.y = om * os;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = k0 + 32 * u;
+          if (k > M) break;
+          const float mr = tanh_fast(x1[u]), mi = tanh_fast(x2[u]);
+          // torchlibrosa magphase: clamp(|m|, 1e-10)
+          const float inv = __fdividef(1.0f, fmaxf(sqrtf(mr * mr + mi * mi), 1e-10f));
+          const float mc = mr * inv, ms = mi * inv;
+          const float om = fmaxf(sp[u] * sigmoid_fast(x0[u]), 0.0f);   // sp = 0 for bins >= F
+          X[k] = cpx{om * (cs[u] * mc - sn[u] * ms), om * (sn[u] * mc + cs[u] * ms)};
+        }
       }
-      X[(size_t)g * (M + 1) + k] = y;
+      __syncwarp();
+      // 2. Hermitian pack -> bufA
+      for (int k = lane; k < M; k += 32) bufA[k] = irfft_pack(X, tw, M, k);
+      __syncwarp();
+      // 3. inverse FFT passes (ping-pong A -> B -> A ...)
+      cpx* src = bufA;
+      cpx* dst = bufB;
+      for (int p = 0; p < passes; ++p) {
+        const int nb = fft_pass_butterflies(a.log2M, p);
+        for (int j = lane; j < nb; j += 32) ifft_butterfly(src, dst, tw, a.log2M, p, j);
+        __syncwarp();
+        cpx* tmp = src;
+        src = dst;
+        dst = tmp;
+      }
     }
     __syncthreads();
-    // 2. Hermitian pack -> bufA
-    for (int i = tid; i < g_cnt * M; i += kThreads) {
-      const int g = i / M, k = i - g * M;
-      bufA[(size_t)g * M + k] = irfft_pack(X + (size_t)g * (M + 1), tw, M, k);
-    }
-    __syncthreads();
-    // 3. inverse FFT passes (ping-pong A -> B -> A ...); B rows use stride M here (X no longer needed)
-    cpx* src = bufA;
-    cpx* dst = bufB;
-    for (int p = 0; p < passes; ++p) {
-      const int nb = fft_pass_butterflies(a.log2M, p);
-      for (int i = tid; i < g_cnt * nb; i += kThreads) {
-        const int g = i / nb, j = i - g * nb;
-        ifft_butterfly(src + (size_t)g * M, dst + (size_t)g * M, tw, a.log2M, p, j);
-      }
-      __syncthreads();
-      cpx* tmp = src;
-      src = dst;
-      dst = tmp;
-    }
-    // 4. windowed overlap-add: every thread owns output positions tid, tid + 256, ...
-    const float* z = reinterpret_cast<const float*>(src);  // interleaved: x[2m] = Re z[m], x[2m+1] = Im z[m]
-    for (int pos = tid; pos < S; pos += kThreads) {
+    // 4. windowed overlap-add: every thread owns output positions tid, tid + kThreads, ... (deterministic, no atomics)
+    const int cnt = (int)((t_hi - tb + 1 < kWarps) ? (t_hi - tb + 1) : kWarps);
+    // only the positions this round's frames touch: [tb*hop, (tb+cnt-1)*hop + N) clipped to the CTA's range
+    long long w0 = tb * hop - pos0;
+    if (w0 < 0) w0 = 0;
+    long long w1 = (tb + cnt - 1) * hop + N - pos0;
+    if (w1 > S) w1 = S;
+    const float* zbase = reinterpret_cast<const float*>(bufs + (result_in_A ? 0 : M));
+    const int zstride = 2 * (2 * M + 2);                 // floats between consecutive warps' buffers
+    for (int pos = (int)w0 + tid; pos < (int)w1; pos += kThreads) {
       float acc = ola[pos];
-      for (int g = 0; g < g_cnt; ++g) {
-        const long long n = pos0 + pos - (tb + g) * hop;
-        if (n >= 0 && n < N) acc += z[(size_t)g * N + n] * win[n];
+      const int rel = (int)(pos0 + pos - tb * hop);      // sample offset relative to frame tb's start (>= 0)
+      // frames g with 0 <= rel - g*hop < N
+      int g_hi = rel / hop;
+      if (g_hi > cnt - 1) g_hi = cnt - 1;
+      int g_lo = (rel - N) / hop + 1;
+      if (rel - N < 0) g_lo = 0;
+      for (int g = g_lo; g <= g_hi; ++g) {
+        const int n = rel - g * hop;
+        acc += zbase[(size_t)g * zstride + n] * win[n];  // interleaved: x[2m] = Re z[m], x[2m+1] = Im z[m]
       }
       ola[pos] = acc;
     }
@@ -159,10 +178,9 @@ __global__ void __launch_bounds__(kThreads) mask_istft_kernel(const MaskIstftArg
 
 }  // namespace
 
-size_t mask_istft_smem_bytes(int N, int hop, int FR, int G) {
+size_t mask_istft_smem_bytes(int N, int hop, int FR) {
   const int M = N / 2;
-  return (size_t)N * sizeof(cpx) + (size_t)N * 4 + (size_t)FR * hop * 4 + (size_t)G * M * sizeof(cpx) +
-         (size_t)G * (M + 1) * sizeof(cpx) + 16;
+  return (size_t)N * sizeof(cpx) + (size_t)N * 4 + (size_t)FR * hop * 4 + (size_t)kWarps * (2 * M + 2) * sizeof(cpx) + 16;
 }
 
 cudaError_t launch_mask_istft(const float* feat, long long feat_bstride, long long feat_cstride, int feat_tstride,
@@ -189,13 +207,12 @@ cudaError_t launch_mask_istft(const float* feat, long long feat_bstride, long lo
   int log2N = 0;
   while ((1 << log2N) < N) ++log2N;
   a.log2M = log2N - 1;
-  // chunk of FR hops per CTA; G frames transformed together
-  a.FR = 32;
-  a.G = 4;
-  size_t smem = mask_istft_smem_bytes(N, hop, a.FR, a.G);
-  while (smem > 200 * 1024 && a.FR > 4) {
-    a.FR /= 2;
-    smem = mask_istft_smem_bytes(N, hop, a.FR, a.G);
+  // CTA = FR hops of output; as large as fits two CTAs per SM (halo frames are recomputed: ~n_fft/hop per CTA)
+  a.FR = 64;
+  size_t smem = mask_istft_smem_bytes(N, hop, a.FR);
+  while (smem > 110 * 1024 && a.FR > 8) {
+    a.FR -= 8;
+    smem = mask_istft_smem_bytes(N, hop, a.FR);
   }
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   static size_t configured = 0;

@@ -13,6 +13,8 @@ from lass_b200 import _cabi, ops, packing  # noqa: E402
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 dev = "cuda"
 LAYERS = {
+    "dec5.up 64->32x4 @512x256": (512, 256, 64, 32, 0, 2, False, (2, 2)),
+    "dec4.up 128->64x4 @256x128": (256, 128, 128, 64, 0, 2, False, (2, 2)),
     "enc0.c2 32->32+id @1024x512 4out": (1024, 512, 32, 32, 32, 2, True),
     # name: (H, W, cin, cout, shortcut_cin, n_outputs(act only=1), pool)
     "enc0.c1 32->32 @1024x512": (1024, 512, 32, 32, 0, 1, False),
@@ -25,10 +27,15 @@ LAYERS = {
 }
 
 
-def bench_layer(H, W, cin, cout, sc, nout, pool):
+def bench_layer(H, W, cin, cout, sc, nout, pool, up=(1, 1)):
     src = torch.randn(B, H, W, cin, device=dev).to(torch.bfloat16)
-    w = packing.pack_conv_weight(torch.randn(cout, cin, 3, 3, device=dev) / (3 * cin ** 0.5), torch.bfloat16)
-    segs = [ops.make_segment(src, 0, cin, w, 9)]
+    nup = up[0] * up[1]
+    if nup == 1:
+        w = packing.pack_conv_weight(torch.randn(cout, cin, 3, 3, device=dev) / (3 * cin ** 0.5), torch.bfloat16)
+        segs = [ops.make_segment(src, 0, cin, w, 9)]
+    else:
+        w = packing.pack_convT_weight(torch.randn(cin, cout, up[0], up[1], device=dev) / cin ** 0.5, torch.bfloat16)
+        segs = [ops.make_segment(src, 0, cin, w, 1)]
     keep = [src, w]
     if sc:
         raw = torch.randn(B, H, W, sc, device=dev).to(torch.float16)
@@ -37,10 +44,11 @@ def bench_layer(H, W, cin, cout, sc, nout, pool):
         keep += [raw, wsc]
     scale = torch.rand(cout, device=dev) + 0.5
     shift = torch.randn(B, cout, device=dev) * 0.1
-    act = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device=dev)
-    kw = dict(full_act=ops.make_out(act, 0, scale, shift))
+    cbuf = cout * (2 if nup > 1 else 1)
+    act = torch.empty(B, H * up[0], W * up[1], cbuf, dtype=torch.bfloat16, device=dev)
+    kw = dict(full_act=ops.make_out(act, 0, scale, shift), up=up)
     if nout > 1:
-        rawo = torch.empty(B, H, W, cout, dtype=torch.float16, device=dev)
+        rawo = torch.empty(B, H * up[0], W * up[1], cbuf, dtype=torch.float16, device=dev)
         kw["full_raw"] = ops.make_out(rawo, 0)
         keep.append(rawo)
     if pool:
@@ -53,7 +61,7 @@ def bench_layer(H, W, cin, cout, sc, nout, pool):
     prof = torch.zeros(296 * 16, dtype=torch.int64, device=dev)
     lib = _cabi.load()
     lib.lass_debug_set_conv_profile(prof.data_ptr())
-    ops.conv_igemm(B, H, W, cout, segs, **kw)
+    ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
     torch.cuda.synchronize()
     lib.lass_debug_set_conv_profile(None)
     pr = prof.view(296, 16).cpu().double()
@@ -64,19 +72,19 @@ def bench_layer(H, W, cin, cout, sc, nout, pool):
     res["profile_cyc_per_item"] = {n: round(pr[:, i].mean().item() / items) for i, n in enumerate(names)}
     res["items_per_cta"] = items
     res["ctas"] = int(pr.shape[0])
-    for flags in (0, 1, 2, 3, 7, 8, 16, 24):
+    for flags in (0, 32, 1, 2, 3, 8):
         _cabi.load().lass_debug_set_conv_flags(flags)
         for _ in range(2):
-            ops.conv_igemm(B, H, W, cout, segs, **kw)
+            ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(3):
-            ops.conv_igemm(B, H, W, cout, segs, **kw)
+            ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
         e1.record()
         torch.cuda.synchronize()
         res["flags%d" % flags] = round(e0.elapsed_time(e1) / 3, 4)
     _cabi.load().lass_debug_set_conv_flags(0)
-    flops = 2.0 * B * H * W * cout * (9 * cin + sc)
+    flops = 2.0 * B * H * W * cout * nup * ((9 if nup == 1 else 1) * cin + sc)
     res["tflops_normal"] = round(flops / (res["flags0"] * 1e-3) / 1e12, 1)
     return res
 
