@@ -884,7 +884,12 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   const size_t stage_bytes = 1024 + (size_t)kEpiWarps * kStageWarpBytes;
   const bool has_16bit_out = l.full_raw.ptr || l.full_act.ptr || l.pool_raw.ptr || l.pool_act.ptr;
   size_t fixed = fixed_base;
-  const bool want_tma = has_16bit_out && !(g_debug_flags & 32);
+  // Measured (tools/gpu_conv_timing.py, whole-model launch lists): the per-warp TMA-store path wins where a warp's
+  // destination is scattered — transposed convs (64 B pieces at a 2-pixel stride, -30 %) and channel slices of the
+  // concat buffers (-15 %) — and loses a few per cent against direct 16 B stores for whole-pixel outputs, where loads
+  // and stores then compete for the SM's TMA request rate (~1 box row / 4 clk).
+  const bool sliced = (l.full_raw.ptr && l.full_raw.cstride != l.group_c) || (l.full_act.ptr && l.full_act.cstride != l.group_c);
+  const bool want_tma = has_16bit_out && (up > 1 || sliced) && !(g_debug_flags & 32);
   // preference order: resident weights + TMA stores, resident weights, streaming + TMA stores, streaming
   for (int attempt = 0; attempt < 4; ++attempt) {
     const bool try_resident = attempt < 2;

@@ -123,6 +123,7 @@ CASES = {
     "c256_384": dict(B=1, H=32, W=8, cin=256, cout=384),
     "c768_384": dict(B=1, H=32, W=16, cin=768, cout=384, want_raw=False),
     "c256_256": dict(B=1, H=32, W=16, cin=256, cout=256, want_raw=False),
+    "pool32_wide": dict(B=2, H=64, W=24, cin=32, cout=32, shortcut_cin=32, want_pool=True, pool=(2, 2)),
     "sc_pool": dict(B=2, H=32, W=16, cin=64, cout=64, shortcut_cin=32, bias=True, want_pool=True, pool=(2, 2)),
     "sc_pool12": dict(B=1, H=32, W=16, cin=384, cout=384, shortcut_cin=384, bias=True, want_pool=True, pool=(1, 2)),
     "sc_big": dict(B=1, H=32, W=16, cin=128, cout=128, shortcut_cin=256, bias=True),
