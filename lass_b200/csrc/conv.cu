@@ -793,6 +793,26 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   else BN = 128;
   int MT = (BN == 256) ? 1 : 2;
   if (l.H < 32 || l.H % 32) MT = 1;
+  if (MT == 2 && l.ncols <= BN) {
+    // Resident weights (no per-tap ring handshake in the MMA issuer) beat the larger tile: if the weights of an item
+    // fit next to two A stages only with one m-tile per item, take MT = 1 (measured on the 128 -> 64 decoder conv).
+    size_t b_stage_max = 0, a2 = 0, a1 = 0;
+    int tiles = 0;
+    for (int s = 0; s < l.nseg; ++s) {
+      const size_t row = (size_t)l.seg[s].kc * 2;
+      const bool halo = l.seg[s].taps == 9;
+      const size_t t2 = ((halo ? (size_t)34 * kHaloPitch : (size_t)32 * TW) * row + 1023) & ~size_t(1023);
+      const size_t t1 = ((halo ? (size_t)18 * kHaloPitch : (size_t)16 * TW) * row + 1023) & ~size_t(1023);
+      if (t2 > a2) a2 = t2;
+      if (t1 > a1) a1 = t1;
+      const size_t bt = ((size_t)BN * row + 1023) & ~size_t(1023);
+      if (bt > b_stage_max) b_stage_max = bt;
+      if (l.seg[s].kc > 0) tiles += (l.seg[s].cin / l.seg[s].kc) * l.seg[s].taps;
+    }
+    const size_t avail = 220 * 1024 - (12 * 1024 + 4 * ((size_t)5 * BN + 100) * sizeof(float));
+    const size_t bw = (size_t)tiles * b_stage_max;
+    if (tiles <= kMaxB && 2 * a2 + bw > avail && 2 * a1 + bw <= avail) MT = 1;
+  }
   if (l.after_w && BN < l.ncols) return set_error(LASS_ERR_ARG, "conv: fused after_conv needs ncols <= BN");
   KernelChoice kc;
   if (BN == 32) kc = MT == 2 ? make_choice<32, 2>() : make_choice<32, 1>();
