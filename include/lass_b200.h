@@ -126,6 +126,17 @@ typedef struct lass_conv_desc {
   const float* after_w; /* fused after_conv: (3, ncols) fp32 or NULL                                              */
   const float* after_b; /* (3)                                                                                    */
   float* feat;          /* (B, 3, H, W) fp32                                                                      */
+  /* Optional rank-1 residual regenerated from a 1-channel fp32 map (the identity residual of encoder_block1, whose
+   * input is pre_conv(bn0(mag)), reference models/resunet.py:537-556): for every output pixel (b, h, w), column n
+   *   out += resid_w[n] * x + resid_b[n],   x = h < resid_T ? resid_in_scale[w] * resid_src[(b*resid_T + h)*resid_F + w]
+   *                                                         + resid_in_shift[w] : 0
+   * NULL resid_src disables it. */
+  const float* resid_src;
+  const float* resid_in_scale;
+  const float* resid_in_shift;
+  const float* resid_w;
+  const float* resid_b;
+  int resid_T, resid_F;
 } lass_conv_desc;
 
 LASS_API int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream);

@@ -88,7 +88,9 @@ class ConvDesc(ctypes.Structure):
                 ("seg", ConvSegment * 2), ("bias", c_void_p), ("up_h", c_int), ("up_w", c_int), ("group_c", c_int),
                 ("full_raw", ConvOut), ("full_act", ConvOut), ("pool_h", c_int), ("pool_w", c_int),
                 ("pool_raw", ConvOut), ("pool_act", ConvOut), ("after_w", c_void_p), ("after_b", c_void_p),
-                ("feat", c_void_p)]
+                ("feat", c_void_p), ("resid_src", c_void_p), ("resid_in_scale", c_void_p),
+                ("resid_in_shift", c_void_p), ("resid_w", c_void_p), ("resid_b", c_void_p), ("resid_T", c_int),
+                ("resid_F", c_int)]
 
 
 SIGNATURES["lass_conv_igemm"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p])

@@ -65,17 +65,20 @@ __global__ void __launch_bounds__(256) preconv_kernel(const float* __restrict__ 
     const float y = fmaf(__ldg(act_scale + c), r[j], __ldg(act_shift + (size_t)b * shift_bstride + c));
     a[j] = y > 0.0f ? y : 0.01f * y;
   }
-  uint4 pr, pa;
-  pr.x = pack_f16x2_sat(r[0], r[1]);
-  pr.y = pack_f16x2_sat(r[2], r[3]);
-  pr.z = pack_f16x2_sat(r[4], r[5]);
-  pr.w = pack_f16x2_sat(r[6], r[7]);
+  uint4 pa;
   pa.x = pack_bf16x2(a[0], a[1]);
   pa.y = pack_bf16x2(a[2], a[3]);
   pa.z = pack_bf16x2(a[4], a[5]);
   pa.w = pack_bf16x2(a[6], a[7]);
-  *reinterpret_cast<uint4*>(raw + pix * 32 + cg) = pr;
   *reinterpret_cast<uint4*>(act + pix * 32 + cg) = pa;
+  if (raw != nullptr) {   // the fused path regenerates the raw tensor where it is needed (conv epilogue) and passes NULL
+    uint4 pr;
+    pr.x = pack_f16x2_sat(r[0], r[1]);
+    pr.y = pack_f16x2_sat(r[2], r[3]);
+    pr.z = pack_f16x2_sat(r[4], r[5]);
+    pr.w = pack_f16x2_sat(r[6], r[7]);
+    *reinterpret_cast<uint4*>(raw + pix * 32 + cg) = pr;
+  }
 }
 
 }  // namespace

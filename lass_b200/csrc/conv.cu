@@ -67,6 +67,12 @@ struct ConvParams {
   const float* after_w;
   const float* after_b;
   float* feat;
+  const float* resid_src;       // rank-1 residual from a 1-channel fp32 map (see lass_conv_desc)
+  const float* resid_in_scale;
+  const float* resid_in_shift;
+  const float* resid_w;
+  const float* resid_b;
+  int resid_T, resid_F;
   long long* prof;  // optional per-CTA cycle counters (kProfSlots each), nullptr = off
   int nseg;
   int B, H, W, ncols;
@@ -106,6 +112,7 @@ struct EpiTables {
   float bias[BN];
   float sc_full[BN], sh_full[BN];
   float sc_pool[BN], sh_pool[BN];
+  float resid_w[BN];
   float after_w[3 * 32];
   float after_b[4];
 };
@@ -488,7 +495,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           const int n = it.n0 + c;
           const bool in = n < p.ncols;
           const int cc = (p.up_h * p.up_w > 1) ? n % p.group_c : n;
-          t.bias[c] = (in && p.bias) ? __ldg(p.bias + n) : 0.0f;
+          t.bias[c] = ((in && p.bias) ? __ldg(p.bias + n) : 0.0f) + ((in && p.resid_src) ? __ldg(p.resid_b + n) : 0.0f);
+          t.resid_w[c] = (in && p.resid_src) ? __ldg(p.resid_w + n) : 0.0f;
           t.sc_full[c] = (in && p.full_act.scale) ? __ldg(p.full_act.scale + cc) : 0.0f;
           t.sh_full[c] = (in && p.full_act.scale) ? __ldg(p.full_act.shift + (size_t)it.b * p.full_act.shift_bstride + cc) : 0.0f;
           t.sc_pool[c] = (in && p.pool_act.scale) ? __ldg(p.pool_act.scale + cc) : 0.0f;
@@ -503,6 +511,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
       const EpiTables<BN>& tb = gtabs[tab_sel];
+      // rank-1 residual operand of this thread's pixels: loaded before the accumulator wait so the latency is hidden
+      float resid_xs[MT];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        resid_xs[mt] = 0.0f;
+        const int hh = it.h0 + mt * 16 + hl, ww = it.w0 + wl;
+        if (p.resid_src != nullptr && hh < p.resid_T && ww < p.W)
+          resid_xs[mt] = fmaf(__ldg(p.resid_in_scale + ww), __ldg(p.resid_src + ((size_t)it.b * p.resid_T + hh) * p.resid_F + ww),
+                              __ldg(p.resid_in_shift + ww));
+      }
       if (q == 0 && lane == 0 && grp == 0) {
         LASS_TIMED_WAIT(&acc_full[as], uses & 1, kProfEpiAccFull);
       }
@@ -516,6 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         const bool valid = (h < p.H) && (w < p.W) && !(no_store && h >= 0);
         const uint32_t taddr = tmem_base + as * (MT * BN) + mt * BN + (static_cast<uint32_t>(q * 32) << 16);
         float fa0 = 0.0f, fa1 = 0.0f, fa2 = 0.0f;
+        const float resid_x = (MT == 2 && mt == 1) ? resid_xs[MT - 1] : resid_xs[0];
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 32) {
           const int n = it.n0 + c0;
@@ -524,7 +543,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           tmem_ld_x32(taddr + c0, v);
           tmem_ld_wait();
           if (p.debug_flags & 1) continue;
-          if (p.bias != nullptr) {
+          if (p.resid_src != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 rw = *reinterpret_cast<const float4*>(tb.resid_w + c0 + j);
+              v[j + 0] = fmaf(rw.x, resid_x, v[j + 0]);
+              v[j + 1] = fmaf(rw.y, resid_x, v[j + 1]);
+              v[j + 2] = fmaf(rw.z, resid_x, v[j + 2]);
+              v[j + 3] = fmaf(rw.w, resid_x, v[j + 3]);
+            }
+          }
+          if (p.bias != nullptr || p.resid_src != nullptr) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 bb = *reinterpret_cast<const float4*>(tb.bias + c0 + j);
@@ -779,6 +808,9 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   if ((l.pool_raw.ptr || l.pool_act.ptr) && l.pool_w != 2) return set_error(LASS_ERR_ARG, "conv: pooled outputs need pool_w == 2");
   if (l.after_w && (!l.after_b || !l.feat || l.ncols > 256 || up > 1))
     return set_error(LASS_ERR_ARG, "conv: fused after_conv needs after_b, feat and a single N tile");
+  if (l.resid_src && (!l.resid_in_scale || !l.resid_in_shift || !l.resid_w || !l.resid_b || up > 1 || l.resid_T <= 0 ||
+                      l.resid_T > l.H || l.resid_F < l.W))
+    return set_error(LASS_ERR_ARG, "conv: bad rank-1 residual spec");
   int e;
   if ((e = check_out(l.full_raw, "full_raw", l.group_c))) return e;
   if ((e = check_out(l.full_act, "full_act", l.group_c))) return e;
@@ -809,7 +841,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
       if (bt > b_stage_max) b_stage_max = bt;
       if (l.seg[s].kc > 0) tiles += (l.seg[s].cin / l.seg[s].kc) * l.seg[s].taps;
     }
-    const size_t avail = 220 * 1024 - (12 * 1024 + 4 * ((size_t)5 * BN + 100) * sizeof(float));
+    const size_t avail = 220 * 1024 - (12 * 1024 + 4 * ((size_t)6 * BN + 100) * sizeof(float));
     const size_t bw = (size_t)tiles * b_stage_max;
     if (tiles <= kMaxB && 2 * a2 + bw > avail && 2 * a1 + bw <= avail) MT = 1;
   }
@@ -845,6 +877,13 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   p.after_w = l.after_w;
   p.after_b = l.after_b;
   p.feat = l.feat;
+  p.resid_src = l.resid_src;
+  p.resid_in_scale = l.resid_in_scale;
+  p.resid_in_shift = l.resid_in_shift;
+  p.resid_w = l.resid_w;
+  p.resid_b = l.resid_b;
+  p.resid_T = l.resid_T;
+  p.resid_F = l.resid_F;
   fill_out(p.full_raw, l.full_raw);
   fill_out(p.full_act, l.full_act);
   fill_out(p.pool_raw, l.pool_raw);
@@ -900,7 +939,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   //      TMA-store staging (48 KiB) is taken when it still leaves a healthy pipeline ----
   const size_t kBudget = 220 * 1024;
   const size_t fixed_base = 1024 /*alignment slack*/ + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 +
-                            4 * ((size_t)5 * BN + 3 * 32 + 4) * sizeof(float) + 64;
+                            4 * ((size_t)6 * BN + 3 * 32 + 4) * sizeof(float) + 64;
   const size_t stage_bytes = 1024 + (size_t)kEpiWarps * kStageWarpBytes;
   const bool has_16bit_out = l.full_raw.ptr || l.full_act.ptr || l.pool_raw.ptr || l.pool_act.ptr;
   size_t fixed = fixed_base;

@@ -135,7 +135,7 @@ size_t layout(lass_plan* p, int B, const Geometry& g, int n_fft, int hop, int L,
   place(p ? &p->shift : nullptr, B, 1, 1, sites().rows, 4);
   place(p ? &p->feat : nullptr, B, 3, g.Tp, g.Fp, 4);
   for (int k = 0; k < 7; ++k) {
-    place(p ? &p->x_raw[k] : nullptr, B, g.H[k], g.W[k], kEncCin[k], 2);
+    if (k > 0) place(p ? &p->x_raw[k] : nullptr, B, g.H[k], g.W[k], kEncCin[k], 2);   // x_raw[0] is never materialised
     place(p ? &p->x_act[k] : nullptr, B, g.H[k], g.W[k], kEncCin[k], 2);
     place(p ? &p->a2[k] : nullptr, B, g.H[k], g.W[k], kEncCout[k], 2);
   }
@@ -210,7 +210,7 @@ int build_launches(lass_plan* p) {
   // ---------------- encoder ----------------
   for (int k = 0; k < 7; ++k) {
     const int cin = kEncCin[k], cout = kEncCout[k];
-    if (!p->w.enc[k].conv1_w || !p->w.enc[k].conv2_w || !p->w.enc[k].sc_w)
+    if (!p->w.enc[k].conv1_w || !p->w.enc[k].conv2_w || (k > 0 && !p->w.enc[k].sc_w))
       return set_error(LASS_ERR_ARG, "plan: encoder block %d weights missing", k);
     {  // conv1: act(x) -> a2 = lrelu(bn2(.) + beta2)
       ConvLaunch l = base_launch(p, k, cout);
@@ -221,10 +221,23 @@ int build_launches(lass_plan* p) {
     }
     {  // conv2 + shortcut(raw x): block output
       ConvLaunch l = base_launch(p, k, cout);
-      l.nseg = 2;
       l.seg[0] = seg_spec(p->a2[k], cout, 9, false, p->w.enc[k].conv2_w);
-      l.seg[1] = seg_spec(p->x_raw[k], cin, 1, true, p->w.enc[k].sc_w);
-      l.bias = p->w.enc[k].sc_b;
+      if (k == 0) {
+        // encoder_block1 has no shortcut conv and its input is pre_conv(bn0(mag)): the identity residual is regenerated
+        // in the epilogue from the 1-channel magnitude (exact fp32), so x_raw[0] is never written or read
+        l.nseg = 1;
+        l.resid_src = reinterpret_cast<const float*>(p->mag.ptr);
+        l.resid_in_scale = p->w.bn0_scale;
+        l.resid_in_shift = p->w.bn0_shift;
+        l.resid_w = p->w.pre_w;
+        l.resid_b = p->w.pre_b;
+        l.resid_T = p->T;
+        l.resid_F = p->F;
+      } else {
+        l.nseg = 2;
+        l.seg[1] = seg_spec(p->x_raw[k], cin, 1, true, p->w.enc[k].sc_w);
+        l.bias = p->w.enc[k].sc_b;
+      }
       if (k < 6) {
         const int j = 5 - k;  // decoder block that consumes this skip (its output lives on level k)
         l.full_raw = out_spec(p->cat_raw[k], cout, true, p, -1, 0);

@@ -111,7 +111,8 @@ def make_out(dst: torch.Tensor = None, coff: int = 0, scale: torch.Tensor = None
 
 
 def conv_igemm(B, H, W, ncols, segments, bias=None, up=(1, 1), full_raw=None, full_act=None, pool=(1, 1),
-               pool_raw=None, pool_act=None, after_w=None, after_b=None, feat=None):
+               pool_raw=None, pool_act=None, after_w=None, after_b=None, feat=None, resid=None):
+    """resid: optional (src (B, T, F) fp32, in_scale (F), in_shift (F), w (ncols), b (ncols)) rank-1 residual."""
     lib = _cabi.load()
     d = _cabi.ConvDesc()
     d.B, d.H, d.W, d.ncols, d.nseg = B, H, W, ncols, len(segments)
@@ -128,4 +129,10 @@ def conv_igemm(B, H, W, ncols, segments, bias=None, up=(1, 1), full_raw=None, fu
     d.after_w = _ptr(after_w) if after_w is not None else None
     d.after_b = _ptr(after_b) if after_b is not None else None
     d.feat = _ptr(feat) if feat is not None else None
+    if resid is not None:
+        src, isc, ish, rw, rb = resid
+        _require_cuda(src, isc, ish, rw, rb)
+        d.resid_src, d.resid_in_scale, d.resid_in_shift = _ptr(src), _ptr(isc), _ptr(ish)
+        d.resid_w, d.resid_b = _ptr(rw), _ptr(rb)
+        d.resid_T, d.resid_F = src.shape[1], src.shape[2]
     _cabi.check(lib.lass_conv_igemm(ctypes.byref(d), _stream()))

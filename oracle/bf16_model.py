@@ -72,7 +72,8 @@ def forward(sd, mixture, condition, hop=160, taps=None):
     for name, _ci, _co, pool in O.ENCODERS:
         p = "base.%s.conv_block1" % name
         fp = "%s->conv_block1" % name
-        raw_b = fp16(x32)
+        # encoder_block1's identity residual is regenerated from the fp32 magnitude in the conv epilogue (exact)
+        raw_b = x32 if name == "encoder_block1" else fp16(x32)
         act_b = _act(sd, p + ".bn1", fp + "->beta1", condition, x32)
         full32 = _block(sd, p, fp, condition, raw_b, act_b)
         if taps is not None:

@@ -27,7 +27,7 @@ def lrelu_affine(v, scale, shift):  # v (B,C,H,W); scale (C); shift (B,C)
 
 def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0, up=(1, 1), pool=(1, 1),
              want_raw=True, want_act=True, want_pool=False, after=False, bias=False, out_cstride_mult=1, out_coff=0,
-             src_extra=0, seed=0):
+             src_extra=0, seed=0, resid=False):
     g = torch.Generator(device="cpu").manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=g)
     taps = 9 if up == (1, 1) else 1
@@ -56,6 +56,18 @@ def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0,
         segs.append(ops.make_segment(sc_src, 0, shortcut_cin, wscp, 1))
         ref = ref + F.conv2d(sc_src_full.float().to(dev), wsc.float().to(dev), None)
         keep += [sc_src, wscp]
+    resid_arg = None
+    if resid:
+        # rank-1 residual regenerated from a 1-channel map with T < H (zero rows after the input affine) and F = W + 1
+        T, Fm = H - 5, W + 1
+        r_src = r(B, T, Fm).to(dev)
+        r_isc, r_ish = (0.5 + torch.rand(Fm, generator=g)).to(dev), (0.1 * r(Fm)).to(dev)
+        r_w, r_b = r(cout).to(dev), (0.1 * r(cout)).to(dev)
+        xmap = torch.zeros(B, H, W, device=dev)
+        xmap[:, :T] = (r_src * r_isc + r_ish)[:, :, :W]
+        ref = ref + r_w[None, :, None, None] * xmap[:, None] + r_b[None, :, None, None]
+        resid_arg = (r_src, r_isc, r_ish, r_w, r_b)
+        keep += list(resid_arg)
     bias_t = None
     if bias:
         bias_t = (0.1 * r(cout * nup)).to(dev)
@@ -87,7 +99,7 @@ def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0,
         outs["feat"] = torch.full((B, 3, H, W), 7.0, dtype=torch.float32, device=dev)
         kw.update(after_w=aw, after_b=ab, feat=outs["feat"])
     # shift tensor must be addressable with a row stride: pass the strided view directly
-    ops.conv_igemm(B, H, W, cout * nup, segs, bias=bias_t, up=up, **kw)
+    ops.conv_igemm(B, H, W, cout * nup, segs, bias=bias_t, up=up, resid=resid_arg, **kw)
     torch.cuda.synchronize()
     res = {}
     refn = nhwc(ref)
@@ -124,6 +136,7 @@ CASES = {
     "c768_384": dict(B=1, H=32, W=16, cin=768, cout=384, want_raw=False),
     "c256_256": dict(B=1, H=32, W=16, cin=256, cout=256, want_raw=False),
     "pool32_wide": dict(B=2, H=64, W=24, cin=32, cout=32, shortcut_cin=32, want_pool=True, pool=(2, 2)),
+    "resid_pool": dict(B=2, H=64, W=16, cin=32, cout=32, resid=True, want_pool=True, pool=(2, 2), out_cstride_mult=2, out_coff=32),
     "sc_pool": dict(B=2, H=32, W=16, cin=64, cout=64, shortcut_cin=32, bias=True, want_pool=True, pool=(2, 2)),
     "sc_pool12": dict(B=1, H=32, W=16, cin=384, cout=384, shortcut_cin=384, bias=True, want_pool=True, pool=(1, 2)),
     "sc_big": dict(B=1, H=32, W=16, cin=128, cout=128, shortcut_cin=256, bias=True),
