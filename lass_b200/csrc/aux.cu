@@ -40,44 +40,57 @@ __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ con
   }
 }
 
-// 4 threads per pixel, 8 channels each (one 16 B store per tensor per thread)
+// 4 threads per pixel, 8 channels each (one 16 B store per tensor per thread).  A CTA works on one clip, so every
+// per-channel constant (pre_conv weight / bias, folded BN scale, FiLM shift of that clip) is loaded once per thread and
+// the thread then walks over kPixIter pixels.
+constexpr int kPixIter = 16;
 __global__ void __launch_bounds__(256) preconv_kernel(const float* __restrict__ mag, const float* __restrict__ bn0_scale,
                                                       const float* __restrict__ bn0_shift, const float* __restrict__ pre_w,
                                                       const float* __restrict__ pre_b, const float* __restrict__ act_scale,
                                                       const float* __restrict__ act_shift, int shift_bstride,
                                                       __half* __restrict__ raw, __nv_bfloat16* __restrict__ act, int T,
-                                                      int F, int Tp, int Fp, long long total_pixels) {
-  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long pix = gid >> 2;
-  if (pix >= total_pixels) return;
-  const int cg = (int)(gid & 3) * 8;
-  const int f = (int)(pix % Fp);
-  const long long bt = pix / Fp;
-  const int t = (int)(bt % Tp);
-  const int b = (int)(bt / Tp);
-  float v = 0.0f;  // time-padding rows are zero AFTER bn0 (models/resunet.py:548)
-  if (t < T) v = fmaf(__ldg(bn0_scale + f), __ldg(mag + ((size_t)b * T + t) * F + f), __ldg(bn0_shift + f));
-  float r[8], a[8];
+                                                      int F, int Tp, int Fp) {
+  const int b = blockIdx.y;
+  const int cg = (threadIdx.x & 3) * 8;
+  float pw[8], pb[8], as[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int c = cg + j;
-    r[j] = fmaf(__ldg(pre_w + c), v, __ldg(pre_b + c));
-    const float y = fmaf(__ldg(act_scale + c), r[j], __ldg(act_shift + (size_t)b * shift_bstride + c));
-    a[j] = y > 0.0f ? y : 0.01f * y;
+    pw[j] = __ldg(pre_w + cg + j);
+    pb[j] = __ldg(pre_b + cg + j);
+    as[j] = __ldg(act_scale + cg + j);
+    sh[j] = __ldg(act_shift + (size_t)b * shift_bstride + cg + j);
   }
-  uint4 pa;
-  pa.x = pack_bf16x2(a[0], a[1]);
-  pa.y = pack_bf16x2(a[2], a[3]);
-  pa.z = pack_bf16x2(a[4], a[5]);
-  pa.w = pack_bf16x2(a[6], a[7]);
-  *reinterpret_cast<uint4*>(act + pix * 32 + cg) = pa;
-  if (raw != nullptr) {   // the fused path regenerates the raw tensor where it is needed (conv epilogue) and passes NULL
-    uint4 pr;
-    pr.x = pack_f16x2_sat(r[0], r[1]);
-    pr.y = pack_f16x2_sat(r[2], r[3]);
-    pr.z = pack_f16x2_sat(r[4], r[5]);
-    pr.w = pack_f16x2_sat(r[6], r[7]);
-    *reinterpret_cast<uint4*>(raw + pix * 32 + cg) = pr;
+  const int pix_per_clip = Tp * Fp;
+  const int pix0 = blockIdx.x * (64 * kPixIter) + (threadIdx.x >> 2);
+#pragma unroll 4
+  for (int it = 0; it < kPixIter; ++it) {
+    const int pix = pix0 + it * 64;
+    if (pix >= pix_per_clip) break;
+    const int t = pix / Fp, f = pix - t * Fp;
+    float v = 0.0f;  // time-padding rows are zero AFTER bn0 (models/resunet.py:548)
+    if (t < T) v = fmaf(__ldg(bn0_scale + f), __ldg(mag + ((size_t)b * T + t) * F + f), __ldg(bn0_shift + f));
+    float r[8], a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      r[j] = fmaf(pw[j], v, pb[j]);
+      const float y = fmaf(as[j], r[j], sh[j]);
+      a[j] = fmaxf(y, 0.01f * y);
+    }
+    const size_t o = ((size_t)b * pix_per_clip + pix) * 32 + cg;
+    uint4 pa;
+    pa.x = pack_bf16x2(a[0], a[1]);
+    pa.y = pack_bf16x2(a[2], a[3]);
+    pa.z = pack_bf16x2(a[4], a[5]);
+    pa.w = pack_bf16x2(a[6], a[7]);
+    *reinterpret_cast<uint4*>(act + o) = pa;
+    if (raw != nullptr) {   // the fused path regenerates the raw tensor where it is needed (conv epilogue) and passes NULL
+      uint4 pr;
+      pr.x = pack_f16x2_sat(r[0], r[1]);
+      pr.y = pack_f16x2_sat(r[2], r[3]);
+      pr.z = pack_f16x2_sat(r[4], r[5]);
+      pr.w = pack_f16x2_sat(r[6], r[7]);
+      *reinterpret_cast<uint4*>(raw + o) = pr;
+    }
   }
 }
 
@@ -93,11 +106,11 @@ cudaError_t launch_film(const float* cond, const float* W, const float* bias, fl
 cudaError_t launch_preconv(const float* mag, const float* bn0_scale, const float* bn0_shift, const float* pre_w,
                            const float* pre_b, const float* act_scale, const float* act_shift, int shift_bstride,
                            void* raw, void* act, int B, int T, int F, int Tp, int Fp, cudaStream_t stream) {
-  const long long pixels = (long long)B * Tp * Fp;
-  const long long threads = pixels * 4;
-  preconv_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
-      mag, bn0_scale, bn0_shift, pre_w, pre_b, act_scale, act_shift, shift_bstride, reinterpret_cast<__half*>(raw),
-      reinterpret_cast<__nv_bfloat16*>(act), T, F, Tp, Fp, pixels);
+  const int pix_per_clip = Tp * Fp;
+  dim3 grid((unsigned)((pix_per_clip + 64 * kPixIter - 1) / (64 * kPixIter)), (unsigned)B);
+  preconv_kernel<<<grid, 256, 0, stream>>>(mag, bn0_scale, bn0_shift, pre_w, pre_b, act_scale, act_shift, shift_bstride,
+                                           reinterpret_cast<__half*>(raw), reinterpret_cast<__nv_bfloat16*>(act), T, F, Tp,
+                                           Fp);
   return cudaGetLastError();
 }
 

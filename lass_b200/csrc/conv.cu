@@ -78,7 +78,8 @@ struct ConvParams {
   int B, H, W, ncols;
   int tiles_h, tiles_w, pix_tiles, n_tiles, num_items;
   int a_stages, b_stages, b_resident;
-  int tma_store;   // 1: 16-bit outputs leave through per-warp shared-memory staging + TMA stores
+  int tma_store;   // 1: full-resolution 16-bit outputs leave through per-warp shared-memory staging + TMA stores
+  int tma_pool;    // 1: pooled outputs too (only when they are channel slices; whole-pixel pooled outputs store directly)
   uint32_t a_stage_bytes, b_stage_bytes;
   int up_h, up_w, group_c;
   int pool_h, pool_w;
@@ -479,6 +480,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const uint32_t as = (AS == 2) ? (uint32_t)grp : 0u;
     EpiTables<BN>* gtabs = tabs + 2 * grp;
     const bool tma_store = p.tma_store != 0;
+    const bool tma_pool = p.tma_pool != 0;
     unsigned char* stg = stage_base + (size_t)(warp - 2) * kStageWarpBytes;
     uint32_t uses = 0;                               // completed uses of accumulator stage `as` by this group
     int tab_b = -1, tab_n0 = -1;
@@ -601,7 +603,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
             if (elect_one()) {
               if (p.full_raw.ptr != nullptr) tma_store_5d(&p.tm_out[grp_dy], stg, c, grp_dx, it.w0, hw0, it.b);
               if (p.full_act.ptr != nullptr) tma_store_5d(&p.tm_out[2 + grp_dy], stg + 2048, c, grp_dx, it.w0, hw0, it.b);
-              if (!pooling) tma_store_commit();
+              if (!(pooling && tma_pool)) tma_store_commit();
             }
             __syncwarp();
           }
@@ -650,7 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 }
                 pact = make_uint4(wv[0], wv[1], wv[2], wv[3]);
               }
-              if (tma_store) {
+              if (tma_pool) {
                 if (p.pool_raw.ptr != nullptr) *stage_slot(stg + 4096, pp, cb >> 3) = praw;
                 if (p.pool_act.ptr != nullptr) *stage_slot(stg + 5120, pp, cb >> 3) = pact;
               } else if (valid) {
@@ -673,7 +675,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], u1, tb.sh_pool[c0 + cb + j + 1]);
                 wa[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
               }
-              if (tma_store) {
+              if (tma_pool) {
                 if (p.pool_raw.ptr != nullptr) {
                   *stage_slot(stg + 4096, pp, cb >> 3) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
                   *stage_slot(stg + 4096, pp, (cb >> 3) + 1) = make_uint4(wr[4], wr[5], wr[6], wr[7]);
@@ -697,7 +699,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 }
               }
             }
-            if (tma_store) {
+            if (tma_pool) {
               fence_proxy_async_smem();
               __syncwarp();
               if (elect_one()) {
@@ -978,6 +980,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     delete cp;
     return set_error(LASS_ERR_ARG, "conv: tile does not fit in shared memory");
   }
+  p.tma_pool = (p.tma_store && ((l.pool_raw.ptr && l.pool_raw.cstride != l.ncols) || (l.pool_act.ptr && l.pool_act.cstride != l.ncols))) ? 1 : 0;
   if (p.tma_store) {
     const int Ho = l.H * l.up_h, Wo = l.W * l.up_w;
     auto full_map = [&](CUtensorMap* tm, const ConvOut& o, int dy) -> int {
@@ -1000,8 +1003,8 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
       if (l.full_raw.ptr && (e = full_map(&p.tm_out[dy], l.full_raw, dy))) { delete cp; return e; }
       if (l.full_act.ptr && (e = full_map(&p.tm_out[2 + dy], l.full_act, dy))) { delete cp; return e; }
     }
-    if (l.pool_raw.ptr && (e = pool_map(&p.tm_out[4], l.pool_raw))) { delete cp; return e; }
-    if (l.pool_act.ptr && (e = pool_map(&p.tm_out[5], l.pool_act))) { delete cp; return e; }
+    if (p.tma_pool && l.pool_raw.ptr && (e = pool_map(&p.tm_out[4], l.pool_raw))) { delete cp; return e; }
+    if (p.tma_pool && l.pool_act.ptr && (e = pool_map(&p.tm_out[5], l.pool_act))) { delete cp; return e; }
   }
   cp->smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes;
   cp->fn = kc.fn;
