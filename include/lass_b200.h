@@ -56,14 +56,17 @@ LASS_API const char* lass_last_error(void);
  *             reference's frozen `stft.conv_real/conv_imag.weight` by lass_b200.packing.pack_stft_basis)
  *   mag, cos, sin   (B, T, F) fp32 out, T = L/hop + 1, F = n_fft/2 + 1
  *   precision_mode  0 = fp32-parity (3 bf16 MMAs per product, max rel. err ~5e-6), 1 = fast (single bf16 pass)
+ *   magphase_mode   0 = Base.spectrogram_phase semantics (mag = clamp(re^2+im^2, 1e-10)**0.5, models/base.py:85-87);
+ *                   1 = torchlibrosa.stft.magphase semantics (mag unclamped, cos/sin divided by clamp(mag, 1e-10)) as used by
+ *                       the multi-resolution front end (reference scripts/precompute_stfts.py:19-58)
  *   workspace       >= lass_stft_workspace_bytes(B, L, n_fft, hop) bytes, 256-byte aligned
  * Requirements: n_fft % 64 == 0, hop % 8 == 0, L > n_fft/2 (reflect padding).
  * ---------------------------------------------------------------------------------------------------- */
 LASS_API int lass_stft_basis_rows(int n_fft);
 LASS_API size_t lass_stft_workspace_bytes(int B, int L, int n_fft, int hop);
 LASS_API int lass_stft_fwd(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
-                  float* mag, float* cos, float* sin, int precision_mode, void* workspace, size_t workspace_bytes,
-                  void* stream);
+                  float* mag, float* cos, float* sin, int precision_mode, int magphase_mode, void* workspace,
+                  size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K5  complex mask + inverse STFT  (replaces ResUNet30_Base.feature_maps_to_wav, reference

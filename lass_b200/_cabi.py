@@ -31,7 +31,7 @@ SIGNATURES = {
     "lass_stft_basis_rows": (c_int, [c_int]),
     "lass_stft_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "lass_stft_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                              c_void_p, c_int, c_void_p, c_size_t, c_void_p]),
+                              c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "lass_mask_istft": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "lass_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,

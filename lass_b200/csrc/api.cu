@@ -93,8 +93,8 @@ size_t lass_stft_workspace_bytes(int B, int L, int n_fft, int hop) {
 }
 
 int lass_stft_fwd(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
-                  float* mag, float* cos, float* sin, int precision_mode, void* workspace, size_t workspace_bytes,
-                  void* stream) {
+                  float* mag, float* cos, float* sin, int precision_mode, int magphase_mode, void* workspace,
+                  size_t workspace_bytes, void* stream) {
   if (!wave || !basis_hi || !mag || !cos || !sin || !workspace)
     return set_error(LASS_ERR_ARG, "lass_stft_fwd: null pointer");
   if (precision_mode == 0 && !basis_lo) return set_error(LASS_ERR_ARG, "lass_stft_fwd: basis_lo required in mode 0");
@@ -106,7 +106,7 @@ int lass_stft_fwd(const float* wave, int B, int L, int n_fft, int hop, const voi
                      stft_workspace_bytes(B, L, n_fft, hop));
   if (reinterpret_cast<uintptr_t>(workspace) % 256) return set_error(LASS_ERR_ARG, "lass_stft_fwd: workspace not 256 B aligned");
   return launch_stft(wave, B, L, n_fft, hop, basis_hi, precision_mode == 0 ? basis_lo : basis_hi, mag, cos, sin,
-                     precision_mode, workspace, (cudaStream_t)stream);
+                     precision_mode, magphase_mode, workspace, (cudaStream_t)stream);
 }
 
 int lass_mask_istft(const float* feat3, long long feat_bstride, long long feat_cstride, int feat_tstride,

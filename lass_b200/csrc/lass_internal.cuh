@@ -26,7 +26,8 @@ int stft_num_ntiles(int n_fft);
 size_t stft_padded_len(int L, int n_fft, int hop);
 size_t stft_workspace_bytes(int B, int L, int n_fft, int hop);
 int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
-                float* mag, float* cosp, float* sinp, int precision_mode, void* workspace, cudaStream_t stream);
+                float* mag, float* cosp, float* sinp, int precision_mode, int magphase_mode, void* workspace,
+                cudaStream_t stream);
 
 // ---- K5 mask + istft ----
 cudaError_t launch_mask_istft(const float* feat, long long feat_bstride, long long feat_cstride, int feat_tstride,

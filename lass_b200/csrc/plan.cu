@@ -389,7 +389,7 @@ int lass_resunet30_forward_stages(lass_plan* p, int stage_mask, const float* mix
   if (stage_mask & LASS_STAGE_FRONT) {
   // K1: STFT -> mag / cos / sin
   if ((e = launch_stft(mixture, p->B, p->L, p->w.n_fft, p->w.hop, p->w.stft_basis_hi, p->w.stft_basis_lo, mag, cs, sn,
-                       stft_precision_mode, p->stft_ws, stream)))
+                       stft_precision_mode, 0, p->stft_ws, stream)))
     return e;
   // K2: FiLM + folded BN shifts (or the caller's precomputed table)
   if (shift_override) {

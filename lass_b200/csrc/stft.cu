@@ -39,6 +39,7 @@ struct StftParams {
   float* cosp;
   float* sinp;
   int T, F, n_fft, split;
+  int magphase_mode;  // 0: Base.spectrogram_phase (clamp(re^2+im^2, 1e-10)**0.5, re/mag); 1: torchlibrosa.magphase
 };
 
 __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_constant__ StftParams p) {
@@ -141,11 +142,20 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
-        // models/base.py:85-87: mag = clamp(re^2 + im^2, 1e-10) ** 0.5 ; cos = re / mag ; sin = im / mag
-        const float m = sqrtf(fmaxf(re[j] * re[j] + im[j] * im[j], 1e-10f));
+        const float p2 = re[j] * re[j] + im[j] * im[j];
+        float m, d;
+        if (p.magphase_mode == 0) {
+          // models/base.py:85-87: mag = clamp(re^2 + im^2, 1e-10) ** 0.5 ; cos = re / mag ; sin = im / mag
+          m = sqrtf(fmaxf(p2, 1e-10f));
+          d = m;
+        } else {
+          // torchlibrosa.stft.magphase: mag = (re^2 + im^2) ** 0.5 ; cos = re / clamp(mag, 1e-10) ; sin likewise
+          m = sqrtf(p2);
+          d = fmaxf(m, 1e-10f);
+        }
         s_mag[lane * kStagePad + c + j] = m;
-        s_cos[lane * kStagePad + c + j] = re[j] / m;
-        s_sin[lane * kStagePad + c + j] = im[j] / m;
+        s_cos[lane * kStagePad + c + j] = re[j] / d;
+        s_sin[lane * kStagePad + c + j] = im[j] / d;
       }
     }
     __syncwarp();
@@ -204,7 +214,8 @@ size_t stft_workspace_bytes(int B, int L, int n_fft, int hop) {
 }
 
 int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
-                float* mag, float* cosp, float* sinp, int precision_mode, void* workspace, cudaStream_t stream) {
+                float* mag, float* cosp, float* sinp, int precision_mode, int magphase_mode, void* workspace,
+                cudaStream_t stream) {
   if (n_fft % BK != 0 || hop % 8 != 0 || L <= n_fft / 2) return LASS_ERR_ARG;
   const int T = L / hop + 1;
   const int F = n_fft / 2 + 1;
@@ -243,6 +254,7 @@ int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void*
   p.F = F;
   p.n_fft = n_fft;
   p.split = precision_mode == 0 ? 1 : 0;
+  p.magphase_mode = magphase_mode ? 1 : 0;
   const size_t smem = (size_t)kStages * kStageBytes + 1024 + 256;
   static bool configured = false;
   if (!configured) {

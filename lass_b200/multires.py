@@ -1,0 +1,45 @@
+"""Multi-resolution STFT front end (BASELINE config 5's runnable part).
+
+Mirrors reference ``scripts/precompute_stfts.py:19-58`` (``calculate_stft_components``): for each window length
+``n_fft = win_length in {256, 512, 2048}`` with hop 160 it returns magnitude, cos and sin of the torchlibrosa STFT with
+``magphase`` semantics, each ``(B, 1, T, n_fft//2 + 1)``.  Every resolution is one launch of kernel K1 (``lass_stft_fwd``,
+tcgen05 DFT-GEMM) with ``magphase_mode = 1``; there is no PyTorch fallback.  The reference's multi-resolution trunk
+(``models/resunet_with_multistft.py``) is non-functional as shipped, so only the front end is offered.
+"""
+from typing import Dict, Sequence, Tuple
+
+import torch
+
+from . import ops, packing
+from .models.spectral import STFT
+
+_BASIS_CACHE: Dict[Tuple[int, int, str], Tuple[torch.Tensor, torch.Tensor]] = {}
+
+
+def _basis(n_fft: int, hop: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    key = (n_fft, hop, str(device))
+    if key not in _BASIS_CACHE:
+        stft = STFT(n_fft=n_fft, hop_length=hop, win_length=n_fft)
+        _BASIS_CACHE[key] = packing.pack_stft_basis(stft.conv_real.weight.data.to(device),
+                                                     stft.conv_imag.weight.data.to(device))
+    return _BASIS_CACHE[key]
+
+
+def calculate_stft_components(waveform: torch.Tensor, n_fft: int, hop_length: int, win_length: int = None,
+                              window: str = "hann", center: bool = True, pad_mode: str = "reflect"):
+    """Same contract as reference ``scripts/precompute_stfts.py:19-58``: waveform (B, 1, L) or (B, L) on a CUDA
+    device -> (magnitude, cos_phase, sin_phase), each (B, 1, T, n_fft//2 + 1) fp32 contiguous."""
+    if win_length is not None and win_length != n_fft:
+        raise NotImplementedError("the reference only uses n_fft == win_length (scripts/precompute_stfts.py:573-582)")
+    if window != "hann" or not center or pad_mode != "reflect":
+        raise NotImplementedError("only the reference's STFT configuration (hann, center, reflect)")
+    if waveform.dim() == 3:
+        waveform = waveform.squeeze(1)
+    waveform = waveform.float().contiguous()
+    hi, lo = _basis(n_fft, hop_length, waveform.device)
+    return ops.stft_fwd(waveform, hi, lo, n_fft, hop_length, precision_mode=0, magphase_mode=1)
+
+
+def multires_stft(waveform: torch.Tensor, win_lengths: Sequence[int] = (256, 512, 2048), hop_length: int = 160):
+    """{win_length: (mag, cos, sin)} for the reference's three resolutions (``config/audiosep_base.yaml:17-21``)."""
+    return {int(w): calculate_stft_components(waveform, int(w), hop_length) for w in win_lengths}

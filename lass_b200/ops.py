@@ -27,8 +27,9 @@ def _require_cuda(*tensors):
 
 
 def stft_fwd(wave: torch.Tensor, basis_hi: torch.Tensor, basis_lo: torch.Tensor, n_fft: int, hop: int,
-             precision_mode: int = 0, workspace: torch.Tensor = None):
-    """wave (B, L) fp32 -> mag, cos, sin (B, 1, T, F) fp32 (reference layout, models/base.py:83-88)."""
+             precision_mode: int = 0, workspace: torch.Tensor = None, magphase_mode: int = 0):
+    """wave (B, L) fp32 -> mag, cos, sin (B, 1, T, F) fp32 (reference layout, models/base.py:83-88;
+    magphase_mode = 1 gives torchlibrosa.stft.magphase semantics instead)."""
     lib = _cabi.load()
     _require_cuda(wave, basis_hi, basis_lo)
     assert wave.dtype == torch.float32 and wave.dim() == 2
@@ -39,7 +40,7 @@ def stft_fwd(wave: torch.Tensor, basis_hi: torch.Tensor, basis_lo: torch.Tensor,
         workspace = torch.empty(need, dtype=torch.uint8, device=wave.device)
     out = torch.empty(3, B, 1, T, F, dtype=torch.float32, device=wave.device)
     _cabi.check(lib.lass_stft_fwd(_ptr(wave), B, L, n_fft, hop, _ptr(basis_hi), _ptr(basis_lo), _ptr(out[0]),
-                                  _ptr(out[1]), _ptr(out[2]), precision_mode, _ptr(workspace),
+                                  _ptr(out[1]), _ptr(out[2]), precision_mode, magphase_mode, _ptr(workspace),
                                   workspace.numel() * workspace.element_size(), _stream()))
     return out[0], out[1], out[2]
 

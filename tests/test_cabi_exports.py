@@ -35,7 +35,7 @@ def test_version_and_error_calls_work_without_gpu():
     assert lib.lass_stft_basis_rows(1024) == 9 * 128
     assert lib.lass_stft_workspace_bytes(2, 160000, 1024, 160) >= 2 * 2 * 161024 * 2
     # argument validation happens before any CUDA call
-    rc = lib.lass_stft_fwd(None, 1, 100, 1024, 160, None, None, None, None, None, 0, None, 0, None)
+    rc = lib.lass_stft_fwd(None, 1, 100, 1024, 160, None, None, None, None, None, 0, 0, None, 0, None)
     assert rc == -1 and b"null" in lib.lass_last_error()
 
 
