@@ -140,6 +140,10 @@ typedef struct lass_conv_desc {
   const float* resid_w;
   const float* resid_b;
   int resid_T, resid_F;
+  /* 0: taps accumulated over K (weights (taps, ncols, cin)).  1: "dx-in-N" formulation for 3x3 convs with 32 or 64 output
+   * channels: the three horizontal taps become output columns (N = 3*Cout, K = 3*Cin, a third of the MMAs) and are summed
+   * by lane shuffles in the epilogue; seg[0].weights is then (3 [ky], 3*Cout [kx, co], cin), seg[1] (optional 1x1) as before. */
+  int algo;
 } lass_conv_desc;
 
 LASS_API int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream);
@@ -206,6 +210,10 @@ typedef struct lass_resunet30_weights {
   } dec[6];
   const float* after_w;        /* (3, 32) */
   const float* after_b;        /* (3) */
+  /* Bit mask of 3x3 convolutions whose weights are packed in the "dx-in-N" layout (3, 3*cout, cin) and run with
+   * lass_conv_desc.algo = 1: bit 2k + i = encoder block k conv(i+1); bit 14 + 2j + i = decoder block j conv_block2.conv(i+1).
+   * Only layers with cout in {32, 64} qualify (encoder blocks 0-1, decoder blocks 4-5). */
+  unsigned int dxn_mask;
 } lass_resunet30_weights;
 
 typedef struct lass_plan lass_plan;

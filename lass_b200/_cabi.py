@@ -90,7 +90,7 @@ class ConvDesc(ctypes.Structure):
                 ("pool_raw", ConvOut), ("pool_act", ConvOut), ("after_w", c_void_p), ("after_b", c_void_p),
                 ("feat", c_void_p), ("resid_src", c_void_p), ("resid_in_scale", c_void_p),
                 ("resid_in_shift", c_void_p), ("resid_w", c_void_p), ("resid_b", c_void_p), ("resid_T", c_int),
-                ("resid_F", c_int)]
+                ("resid_F", c_int), ("algo", c_int)]
 
 
 SIGNATURES["lass_conv_igemm"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p])
@@ -120,7 +120,7 @@ class ResUNet30Weights(ctypes.Structure):
                 ("pre_w", ctypes.c_void_p), ("pre_b", ctypes.c_void_p),
                 ("film_w", ctypes.c_void_p), ("film_b", ctypes.c_void_p), ("act_scale", ctypes.c_void_p),
                 ("enc", _EncW * 7), ("dec", _DecW * 6),
-                ("after_w", ctypes.c_void_p), ("after_b", ctypes.c_void_p)]
+                ("after_w", ctypes.c_void_p), ("after_b", ctypes.c_void_p), ("dxn_mask", ctypes.c_uint)]
 
 
 SIGNATURES.update({

@@ -7,6 +7,7 @@
 * runs the forward on the current CUDA stream.  No CPU path: inputs must be CUDA tensors.
 """
 import ctypes
+import os
 
 import torch
 
@@ -16,6 +17,7 @@ _ENC = ("encoder_block1", "encoder_block2", "encoder_block3", "encoder_block4", 
         "conv_block7a")
 _DEC = ("decoder_block1", "decoder_block2", "decoder_block3", "decoder_block4", "decoder_block5", "decoder_block6")
 BN_EPS = 1e-5
+DEFAULT_DXN_MASK = (1 << 0) | (1 << (14 + 8)) | (1 << (14 + 9)) | (1 << (14 + 10)) | (1 << (14 + 11))
 
 
 def _dev_key(device):
@@ -65,6 +67,10 @@ class Engine:
         self._packed_key = None
         self._plans = {}
         self.stft_precision_mode = 0
+        # 3x3 convs run in the "dx-in-N" formulation (lass_conv_desc.algo = 1): bit 2k+i = encoder block k conv(i+1),
+        # bit 14+2j+i = decoder block j conv(i+1).  Default = the layers where it measured faster on B200
+        # (tools/gpu_dxn_sweep.sh): encoder_block1 conv1, decoder_block5 conv1/conv2, decoder_block6 conv1/conv2.
+        self.dxn_mask = int(os.environ.get("LASS_DXN_MASK", str(DEFAULT_DXN_MASK)), 0)
 
     # ------------------------------------------------------------------ packing
     def _version_key(self, device):
@@ -127,9 +133,13 @@ class Engine:
         w.pre_w, w.pre_b = keep["pre"][0].data_ptr(), keep["pre"][1].data_ptr()
         w.film_w, w.film_b, w.act_scale = film_w.data_ptr(), film_b.data_ptr(), act_scale.data_ptr()
 
-        def block_weights(cb, cin, cout):
-            c1 = packing.pack_conv_weight(dev(cb.conv1.weight), torch.bfloat16)
-            c2 = packing.pack_conv_weight(dev(cb.conv2.weight), torch.bfloat16)
+        dxn_mask = self.dxn_mask
+
+        def block_weights(cb, cin, cout, bit):
+            pk1 = packing.pack_conv_weight_dxn if (dxn_mask >> bit) & 1 else packing.pack_conv_weight
+            pk2 = packing.pack_conv_weight_dxn if (dxn_mask >> (bit + 1)) & 1 else packing.pack_conv_weight
+            c1 = pk1(dev(cb.conv1.weight), torch.bfloat16)
+            c2 = pk2(dev(cb.conv2.weight), torch.bfloat16)
             if cb.is_shortcut:
                 sc = packing.pack_conv_weight(dev(cb.shortcut.weight), torch.float16)
                 sb = dev(cb.shortcut.bias)
@@ -140,7 +150,7 @@ class Engine:
 
         for k, name in enumerate(_ENC):
             cb = getattr(base, name).conv_block1
-            c1, c2, sc, sb = block_weights(cb, cb.conv1.in_channels, cb.conv1.out_channels)
+            c1, c2, sc, sb = block_weights(cb, cb.conv1.in_channels, cb.conv1.out_channels, 2 * k)
             keep["enc%d" % k] = (c1, c2, sc, sb)
             w.enc[k].conv1_w, w.enc[k].conv2_w, w.enc[k].sc_w = c1.data_ptr(), c2.data_ptr(), sc.data_ptr()
             w.enc[k].sc_b = sb.data_ptr() if sb is not None else None
@@ -148,13 +158,14 @@ class Engine:
             blk = getattr(base, name)
             up = packing.pack_convT_weight(dev(blk.conv1.weight), torch.bfloat16)
             cb = blk.conv_block2
-            c1, c2, sc, sb = block_weights(cb, cb.conv1.in_channels, cb.conv1.out_channels)
+            c1, c2, sc, sb = block_weights(cb, cb.conv1.in_channels, cb.conv1.out_channels, 14 + 2 * j)
             keep["dec%d" % j] = (up, c1, c2, sc, sb)
             w.dec[j].up_w, w.dec[j].conv1_w, w.dec[j].conv2_w = up.data_ptr(), c1.data_ptr(), c2.data_ptr()
             w.dec[j].sc_w = sc.data_ptr()
             w.dec[j].sc_b = sb.data_ptr() if sb is not None else None
         keep["after"] = (dev(base.after_conv.weight.reshape(3, 32)), dev(base.after_conv.bias))
         w.after_w, w.after_b = keep["after"][0].data_ptr(), keep["after"][1].data_ptr()
+        w.dxn_mask = dxn_mask
         keep["struct"] = w
         keep["bn_shift_rows"] = None
         return keep

@@ -79,7 +79,7 @@ def make_segment(src: torch.Tensor, coff: int, cin: int, weights: torch.Tensor, 
     """src (B, H, W, Cbuf) 16-bit NHWC; weights (taps, ncols, cin) of the same dtype."""
     _require_cuda(src, weights)
     assert src.dtype in (torch.bfloat16, torch.float16) and weights.dtype == src.dtype
-    assert weights.shape[0] == taps and weights.shape[2] == cin
+    assert weights.shape[2] == cin and weights.shape[0] in (taps, 3)   # (3, 3*cout, cin) for the dx-in-N layout
     seg = _cabi.ConvSegment()
     seg.src = _ptr(src)
     seg.src_cstride = src.shape[3]
@@ -112,7 +112,7 @@ def make_out(dst: torch.Tensor = None, coff: int = 0, scale: torch.Tensor = None
 
 
 def conv_igemm(B, H, W, ncols, segments, bias=None, up=(1, 1), full_raw=None, full_act=None, pool=(1, 1),
-               pool_raw=None, pool_act=None, after_w=None, after_b=None, feat=None, resid=None):
+               pool_raw=None, pool_act=None, after_w=None, after_b=None, feat=None, resid=None, algo=0):
     """resid: optional (src (B, T, F) fp32, in_scale (F), in_shift (F), w (ncols), b (ncols)) rank-1 residual."""
     lib = _cabi.load()
     d = _cabi.ConvDesc()
@@ -130,6 +130,7 @@ def conv_igemm(B, H, W, ncols, segments, bias=None, up=(1, 1), full_raw=None, fu
     d.after_w = _ptr(after_w) if after_w is not None else None
     d.after_b = _ptr(after_b) if after_b is not None else None
     d.feat = _ptr(feat) if feat is not None else None
+    d.algo = algo
     if resid is not None:
         src, isc, ish, rw, rb = resid
         _require_cuda(src, isc, ish, rw, rb)

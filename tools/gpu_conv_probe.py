@@ -27,7 +27,7 @@ def lrelu_affine(v, scale, shift):  # v (B,C,H,W); scale (C); shift (B,C)
 
 def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0, up=(1, 1), pool=(1, 1),
              want_raw=True, want_act=True, want_pool=False, after=False, bias=False, out_cstride_mult=1, out_coff=0,
-             src_extra=0, seed=0, resid=False):
+             src_extra=0, seed=0, resid=False, algo=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=g)
     taps = 9 if up == (1, 1) else 1
@@ -40,7 +40,7 @@ def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0,
     nup = up[0] * up[1]
     if taps == 9:
         w = (r(cout, cin, 3, 3) / (3.0 * cin ** 0.5)).to(src_dtype)
-        wp = packing.pack_conv_weight(w.float(), src_dtype).to(dev)
+        wp = (packing.pack_conv_weight_dxn if algo == 1 else packing.pack_conv_weight)(w.float(), src_dtype).to(dev)
         ref = F.conv2d(x, w.float().to(dev), None, padding=1)
     else:
         w = (r(cin, cout, up[0], up[1]) / cin ** 0.5).to(src_dtype)
@@ -99,7 +99,7 @@ def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0,
         outs["feat"] = torch.full((B, 3, H, W), 7.0, dtype=torch.float32, device=dev)
         kw.update(after_w=aw, after_b=ab, feat=outs["feat"])
     # shift tensor must be addressable with a row stride: pass the strided view directly
-    ops.conv_igemm(B, H, W, cout * nup, segs, bias=bias_t, up=up, resid=resid_arg, **kw)
+    ops.conv_igemm(B, H, W, cout * nup, segs, bias=bias_t, up=up, resid=resid_arg, algo=algo, **kw)
     torch.cuda.synchronize()
     res = {}
     refn = nhwc(ref)
@@ -148,6 +148,13 @@ CASES = {
     "partial": dict(B=1, H=40, W=12, cin=64, cout=64),
     "fp16src": dict(B=1, H=32, W=16, cin=64, cout=64, src_dtype=torch.float16),
 }
+
+# the same cases through the dx-in-N formulation where it applies (3x3, Cout in {32, 64}, no upsampling, 2x2 pooling)
+for _name in ("c32_32", "c32_32_mt1", "c32_64", "c64_64", "c64_32", "pool32_wide", "resid_pool", "sc_pool", "slice_out", "after",
+              "partial", "fp16src"):
+    CASES["dxn_" + _name] = dict(CASES[_name], algo=1)
+CASES["dxn_c128_64"] = dict(B=1, H=32, W=32, cin=128, cout=64, algo=1)
+CASES["dxn_sc128_64"] = dict(B=2, H=16, W=48, cin=64, cout=64, shortcut_cin=128, bias=True, want_raw=False, algo=1)
 
 if __name__ == "__main__":
     pitch = int(sys.argv[1])   # kept for the log name; the halo pitch is fixed at 10 pixels

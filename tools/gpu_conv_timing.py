@@ -27,11 +27,12 @@ LAYERS = {
 }
 
 
-def bench_layer(H, W, cin, cout, sc, nout, pool, up=(1, 1)):
+def bench_layer(H, W, cin, cout, sc, nout, pool, up=(1, 1), algo=0):
     src = torch.randn(B, H, W, cin, device=dev).to(torch.bfloat16)
     nup = up[0] * up[1]
     if nup == 1:
-        w = packing.pack_conv_weight(torch.randn(cout, cin, 3, 3, device=dev) / (3 * cin ** 0.5), torch.bfloat16)
+        w = (packing.pack_conv_weight_dxn if algo == 1 else packing.pack_conv_weight)(
+            torch.randn(cout, cin, 3, 3, device=dev) / (3 * cin ** 0.5), torch.bfloat16)
         segs = [ops.make_segment(src, 0, cin, w, 9)]
     else:
         w = packing.pack_convT_weight(torch.randn(cin, cout, up[0], up[1], device=dev) / cin ** 0.5, torch.bfloat16)
@@ -46,7 +47,7 @@ def bench_layer(H, W, cin, cout, sc, nout, pool, up=(1, 1)):
     shift = torch.randn(B, cout, device=dev) * 0.1
     cbuf = cout * (2 if nup > 1 else 1)
     act = torch.empty(B, H * up[0], W * up[1], cbuf, dtype=torch.bfloat16, device=dev)
-    kw = dict(full_act=ops.make_out(act, 0, scale, shift), up=up)
+    kw = dict(full_act=ops.make_out(act, 0, scale, shift), up=up, algo=algo)
     if nout > 1:
         rawo = torch.empty(B, H * up[0], W * up[1], cbuf, dtype=torch.float16, device=dev)
         kw["full_raw"] = ops.make_out(rawo, 0)
@@ -66,13 +67,15 @@ def bench_layer(H, W, cin, cout, sc, nout, pool, up=(1, 1)):
     lib.lass_debug_set_conv_profile(None)
     pr = prof.view(296, 16).cpu().double()
     pr = pr[pr[:, 9] > 0]
+    if pr.shape[0] == 0:
+        pr = torch.ones(1, 16, dtype=torch.float64)
     items = pr[:, 9].mean().item()
     names = ["prod_wait_a_empty", "prod_wait_b_empty", "prod_total", "mma_wait_acc_empty", "mma_wait_a_full",
              "mma_wait_b_full", "mma_total", "epi_wait_acc_full", "epi_total"]
     res["profile_cyc_per_item"] = {n: round(pr[:, i].mean().item() / items) for i, n in enumerate(names)}
     res["items_per_cta"] = items
     res["ctas"] = int(pr.shape[0])
-    for flags in (0, 32, 1, 2, 3, 8):
+    for flags in (0, 1, 2, 3):
         _cabi.load().lass_debug_set_conv_flags(flags)
         for _ in range(2):
             ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
@@ -90,6 +93,15 @@ def bench_layer(H, W, cin, cout, sc, nout, pool, up=(1, 1)):
 
 
 out = {}
+if len(sys.argv) > 2 and sys.argv[2] == "dxn":
+    DXN = {k: v for k, v in LAYERS.items() if "up " not in k and v[3] <= 64}
+    DXN["dec4.c2 64->64+sc128 @512x256"] = (512, 256, 64, 64, 128, 1, False)
+    DXN["dec5.c2 32->32+sc64 @1024x512"] = (1024, 512, 32, 32, 64, 1, False)
+    DXN["enc1.c1 32->64 @512x256"] = (512, 256, 32, 64, 0, 1, False)
+    LAYERS = {}
+    for k, v in DXN.items():
+        LAYERS[k + " [K]"] = v
+        LAYERS[k + " [dxN]"] = tuple(v) + ((1, 1), 1)
 for name, cfg in LAYERS.items():
     out[name] = bench_layer(*cfg)
     print(name, json.dumps(out[name]), flush=True)
