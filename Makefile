@@ -18,7 +18,18 @@ $(LIB): $(OBJ)
 	@mkdir -p lass_b200/_lib
 	$(NVCC) -shared $(ARCH) -o $@ $(OBJ) -cudart static
 
+# second library with the conv role profiler compiled in (tools/gpu_conv_timing.py; LASS_B200_LIB selects it)
+PROF_OBJ  := $(patsubst lass_b200/csrc/%.cu,build/prof/%.o,$(SRC))
+PROF_LIB  := lass_b200/_lib/liblass_b200_prof.so
+build/prof/%.o: lass_b200/csrc/%.cu $(HDR)
+	@mkdir -p build/prof
+	$(NVCC) $(NVCCFLAGS) -DLASS_CONV_PROFILE -c $< -o $@ 2> build/prof/$*.ptxas.log || (cat build/prof/$*.ptxas.log; exit 1)
+$(PROF_LIB): $(PROF_OBJ)
+	@mkdir -p lass_b200/_lib
+	$(NVCC) -shared $(ARCH) -o $@ $(PROF_OBJ) -cudart static
+prof: $(PROF_LIB)
+
 clean:
 	rm -rf build $(LIB)
 
-.PHONY: all clean
+.PHONY: all clean prof

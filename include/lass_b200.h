@@ -246,6 +246,10 @@ LASS_API int lass_resunet30_forward_stages(lass_plan* plan, int stage_mask, cons
                                            int stft_precision_mode, void* stream);
 /* Algorithmic FLOPs (2*M*N*K summed over the plan's convolution launches) and launches of the UNET stage. */
 LASS_API double lass_resunet30_unet_flops(const lass_plan* plan);
+/* Debug: runs the UNET stage once with a CUDA event between launches; ms_out[i] / flops_out[i] (optional) receive the
+ * duration and algorithmic FLOPs of launch i (encoder blocks 1..7: conv1, conv2; decoder blocks 1..6: transposed conv,
+ * conv1, conv2).  Returns the number of launches (<= capacity) or a negative error.  Synchronises the stream. */
+LASS_API int lass_debug_time_unet_launches(lass_plan* plan, float* ms_out, double* flops_out, int capacity, void* stream);
 /* Number of kernel launches one lass_resunet30_forward issues. */
 LASS_API int lass_resunet30_num_launches(const lass_plan* plan);
 /* Debug / test access to intermediates in the workspace: name in {"mag","cos","sin","shift","feat",
@@ -268,6 +272,14 @@ LASS_API int lass_debug_umma_probe(const void* A, int a_rows, const void* Bm, in
  * clock cycles from first issue to completion. */
 LASS_API int lass_debug_umma_bench(int n, int kc, int swizzle_mode, int a_start_bytes, int a_sbo, int iters, int nacc,
                                    int grid, long long* cycles_out, void* stream);
+/* Same measurement with the issue loop unrolled 8x (about two instructions per MMA from the issuing thread), so
+ * that MMAs shorter than the first version's loop overhead are resolved.  nacc in {1, 2}; iters % 8 == 0. */
+LASS_API int lass_debug_umma_bench2(int n, int kc, int swizzle_mode, int a_start_bytes, int a_sbo, int iters, int nacc,
+                                    int grid, long long* cycles_out, void* stream);
+/* Issue-rate benchmark of the conv kernel's own steady-state MMA issue code (one halo chunk = 9 taps x mt m-tiles x
+ * ksteps k-steps per item, nothing else running); mode 0 = running descriptors, 1 = per-tap re-derived descriptors. */
+LASS_API int lass_debug_umma_bench3(int mt, int bn, int ksteps, int mode, int iters, int grid, long long* cycles_out,
+                                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_lib", "liblass_b200.so")
+# LASS_B200_LIB selects another BUILD of the same library (e.g. `make prof`); there is still no fallback of any kind.
+LIB_PATH = os.environ.get("LASS_B200_LIB") or os.path.join(_HERE, "_lib", "liblass_b200.so")
 
 c_void_p, c_int, c_size_t, c_longlong = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_longlong
 
@@ -97,6 +98,8 @@ SIGNATURES["lass_conv_igemm"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p])
 SIGNATURES["lass_debug_set_conv_flags"] = (c_int, [c_int])
 SIGNATURES["lass_debug_set_conv_profile"] = (c_int, [c_void_p])
 SIGNATURES["lass_debug_umma_bench"] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
+SIGNATURES["lass_debug_umma_bench3"] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
+SIGNATURES["lass_debug_umma_bench2"] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
 
 
 # ---- whole-model entry (lass_resunet30_*) ----
@@ -137,6 +140,8 @@ SIGNATURES.update({
     "lass_resunet30_forward_stages": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p,
                                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]),
     "lass_resunet30_unet_flops": (ctypes.c_double, [ctypes.c_void_p]),
+    "lass_debug_time_unet_launches": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                                     ctypes.c_void_p]),
     "lass_resunet30_num_launches": (ctypes.c_int, [ctypes.c_void_p]),
     "lass_resunet30_buffer": (ctypes.c_void_p, [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int * 4),
                                                 ctypes.POINTER(ctypes.c_int)]),

@@ -137,6 +137,10 @@ int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream) {
 }
 
 int lass_debug_set_conv_profile(long long* device_counters) {
+#ifndef LASS_CONV_PROFILE
+  if (device_counters)
+    return set_error(LASS_ERR_ARG, "conv profile: this build has no role profiler (make prof, LASS_B200_LIB=.../liblass_b200_prof.so)");
+#endif
   conv_set_profile_buffer(device_counters);
   return 0;
 }

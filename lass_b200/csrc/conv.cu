@@ -26,19 +26,25 @@
 #include <new>
 
 #include "conv.cuh"
+#include "conv_issue.cuh"
 #include "ptx.cuh"
 
 namespace lass {
 
 namespace {
 
-constexpr int TW = 8;          // pixels per tile row == rows of one 8-row descriptor group
-constexpr int kHaloPitch = TW + 2;  // pixels per image row of the halo tile in shared memory
 template <int V>
 struct IntTag {
   static constexpr int value = V;
 };
-constexpr int kThreads = 320;   // warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
+constexpr int kThreads = 320;   // conv_dxn_kernel: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
+constexpr int kThreadsK = 352;  // conv_igemm_kernel: warp 0 TMA producer, warps 1-2 MMA issuers, warps 3-6 / 7-10 epilogue groups
+// accumulator stages / TMEM columns of conv_igemm_kernel<BN, MT>
+constexpr int acc_stages(int BN, int MT) { return (4 * MT * BN <= 256) ? 4 : 2; }
+constexpr int tmem_cols(int BN, int MT) {
+  const int c = acc_stages(BN, MT) * MT * BN;
+  return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
+}
 constexpr int kMaxA = 8;
 constexpr int kMaxB = 40;
 constexpr float kSlope = 0.01f;
@@ -78,6 +84,8 @@ struct ConvParams {
   int B, H, W, ncols;
   int tiles_h, tiles_w, pix_tiles, n_tiles, num_items;
   int a_stages, b_stages, b_resident;
+  int epi_mode;    // conv_igemm_kernel: 1 = lean epilogue (one activated bf16 output, direct stores), 0 = generic
+  int dual_issue;  // conv_igemm_kernel: two MMA-issuing warps, each with half of the A ring (resident weights, >= 4 A stages)
   int tma_store;   // 1: full-resolution 16-bit outputs leave through per-warp shared-memory staging + TMA stores
   int tma_pool;    // 1: pooled outputs too (only when they are channel slices; whole-pixel pooled outputs store directly)
   uint32_t a_stage_bytes, b_stage_bytes;
@@ -159,45 +167,17 @@ __device__ __forceinline__ void stage_row32(unsigned char* tile, int row, const 
   for (int pc = 0; pc < 4; ++pc) *stage_slot(tile, row, pc) = make_uint4(w[4 * pc], w[4 * pc + 1], w[4 * pc + 2], w[4 * pc + 3]);
 }
 
-// One tcgen05.mma with descriptors given as (low word = start address >> 4 | LBO, high word = SBO | version | swizzle).
-__device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
-                                          uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t"
-      ".reg .pred p;\n\t"
-      ".reg .b64 da, db;\n\t"
-      "mov.b64 da, {%1, %2};\n\t"
-      "mov.b64 db, {%3, %4};\n\t"
-      "setp.ne.b32 p, %6, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
-      "}\n" ::"r"(tmem_d),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// Per-segment constants of the MMA issuer (uniform registers).
-struct SegMma {
-  uint32_t a_hi, b_hi;      // descriptor high words
-  uint32_t idesc;
-};
-
-// All MMAs of one (chunk, tap) for MT m-tiles: KSTEPS k-steps of 16 channels each.  a_lo / b_lo already contain the
-// LBO field; start addresses advance by 2 (x16 B) per k-step and by mt_step16 per m-tile.
-template <int MT, int BN, int KSTEPS>
-__device__ __forceinline__ void issue_tap(uint32_t acc, uint32_t a_lo, uint32_t mt_step16, uint32_t b_lo, const SegMma& g,
-                                          uint32_t accumulate) {
-#pragma unroll
-  for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks)
-      umma_lohi(acc + mt * BN, a_lo + mt * mt_step16 + 2 * ks, g.a_hi, b_lo + 2 * ks, g.b_hi, g.idesc,
-                ks == 0 ? accumulate : 1u);
-  }
-}
-
 // profiling slots (clock cycles, per CTA); documented at lass_debug_set_conv_profile in include/lass_b200.h
 enum { kProfProdAEmpty = 0, kProfProdBEmpty, kProfProdTotal, kProfMmaAccEmpty, kProfMmaAFull, kProfMmaBFull, kProfMmaTotal,
        kProfEpiAccFull, kProfEpiTotal, kProfItems, kProfSlots = 16 };
+
+// The role profiler is compiled in only with -DLASS_CONV_PROFILE (make prof -> liblass_b200_prof.so): even switched off
+// at run time its counters cost registers and a few per cent in the epilogue-bound layers.
+#ifdef LASS_CONV_PROFILE
+#define LASS_PROF_ON(p) ((p).prof != nullptr)
+#else
+#define LASS_PROF_ON(p) false
+#endif
 
 #define LASS_TIMED_WAIT(bar, parity, slot)              \
   do {                                                  \
@@ -206,14 +186,39 @@ enum { kProfProdAEmpty = 0, kProfProdBEmpty, kProfProdTotal, kProfMmaAccEmpty, k
     if (prof) pc[slot] += clock64() - _t;               \
   } while (0)
 
+// 16-byte shared-memory load by 32-bit shared address.  Volatile: stays where it is written relative to the named
+// barriers that publish the epilogue tables and to the TMEM loads it is meant to overlap with.
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr));
+  return r;
+}
+
+// y = lrelu(sc * v + sh) for 32 channels of one pixel, packed to bf16 and stored as 4 x 16 B.
+__device__ __forceinline__ void act_store32(const float* v, const float4* sc, const float4* sh, uint16_t* dst, bool valid) {
+  uint32_t w[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float t0 = fmaf(sc[j].x, v[4 * j + 0], sh[j].x), t1 = fmaf(sc[j].y, v[4 * j + 1], sh[j].y);
+    const float t2 = fmaf(sc[j].z, v[4 * j + 2], sh[j].z), t3 = fmaf(sc[j].w, v[4 * j + 3], sh[j].w);
+    w[2 * j] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
+    w[2 * j + 1] = pack_bf16x2(fmaxf(t2, kSlope * t2), fmaxf(t3, kSlope * t3));
+  }
+  if (valid) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+    d[2] = make_uint4(w[8], w[9], w[10], w[11]);
+    d[3] = make_uint4(w[12], w[13], w[14], w[15]);
+  }
+}
+
 template <int BN, int MT>
-__global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  constexpr int AS = (2 * MT * BN <= 512) ? 2 : 1;
-  constexpr int kTmemCols = (AS * MT * BN <= 32)    ? 32
-                            : (AS * MT * BN <= 64)  ? 64
-                            : (AS * MT * BN <= 128) ? 128
-                            : (AS * MT * BN <= 256) ? 256
-                                                    : 512;
+__global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  // accumulator ring: item n of this CTA uses stage n % NS; MMA warp (n & 1) issues it, epilogue group (n & 1) drains it.
+  // Four stages where they fit in 256 columns, so that the MMAs of item n + 2 do not have to wait for the epilogue of item n.
+  constexpr int NS = acc_stages(BN, MT);
+  constexpr int kTmemCols = tmem_cols(BN, MT);
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* a_buf = smem;
@@ -224,15 +229,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   uint64_t* b_full = a_empty + kMaxA;
   uint64_t* b_empty = b_full + kMaxB;
   uint64_t* acc_full = b_empty + kMaxB;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* acc_empty = acc_full + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 4);
   EpiTables<BN>* tabs = reinterpret_cast<EpiTables<BN>*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);  // [group][2]
   unsigned char* stage_base = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(tabs + 4) + 1023) & ~uintptr_t(1023));                                     // [8 warps][6 KiB]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const bool prof = p.prof != nullptr;
+  const bool prof = LASS_PROF_ON(p);
   long long pc[kProfSlots];
 #pragma unroll
   for (int i = 0; i < kProfSlots; ++i) pc[i] = 0;
@@ -251,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    for (int s = 0; s < AS; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);
     }
@@ -266,15 +271,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  const bool mma_only = (p.debug_flags & 64) != 0;   // timing experiment: the MMA issuer runs free, nothing else runs
+  if (warp == 0 && !mma_only) {
     // =========================== TMA producer ===========================
     // warp-uniform loop; the elected lane issues the TMA loads
     {
-      uint32_t a_it = 0, b_it = 0;
+      // with two MMA issuers the A ring is split in two halves, items alternate between them
+      const bool dual = p.dual_issue != 0;
+      const uint32_t ring_n = dual ? (uint32_t)p.a_stages >> 1 : (uint32_t)p.a_stages;
+      uint32_t a_its[2] = {0, 0};
+      uint32_t b_it = 0, n = 0;
       bool first_item = true;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
         const Item it = decode_item<MT>(p, item, BN);
         uint32_t b_slot_res = 0;
+        const uint32_t ring = dual ? (n & 1u) : 0u;
+        uint32_t a_it = ring ? a_its[1] : a_its[0];
         for (int s = 0; s < p.nseg; ++s) {
           const SegDev& sg = p.seg[s];
           const uint32_t row_bytes = sg.kc * 2;
@@ -282,8 +294,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           const uint32_t a_bytes = halo ? (uint32_t)(16 * MT + 2) * kHaloPitch * row_bytes : (uint32_t)(16 * MT) * TW * row_bytes;
           const uint32_t b_bytes = BN * row_bytes;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
-            const uint32_t sa = a_it % p.a_stages;
-            LASS_TIMED_WAIT(&a_empty[sa], ((a_it / p.a_stages) & 1) ^ 1, kProfProdAEmpty);
+            const uint32_t sa = ring * ring_n + a_it % ring_n;
+            LASS_TIMED_WAIT(&a_empty[sa], ((a_it / ring_n) & 1) ^ 1, kProfProdAEmpty);
             if (elect_one()) {
               if (p.debug_flags & 4) {
                 mbar_arrive(&a_full[sa]);
@@ -321,6 +333,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           }
         }
         first_item = false;
+        if (ring) a_its[1] = a_it;
+        else a_its[0] = a_it;
       }
       if (prof && lane == 0) {
         long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
@@ -329,8 +343,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         dst[kProfProdTotal] = clock64() - t_start;
       }
     }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
+  } else if (warp == 1 || warp == 2) {
+    // =========================== MMA issuers ===========================
+    // With p.dual_issue there are TWO issuing warps: warp 1 takes this CTA's items 0, 2, 4, ..., warp 2 the items
+    // 1, 3, 5, ...  Measured on B200 (tools/gpu_umma_bench3.py, lass_debug_set_conv_flags 64): the tensor pipe does not
+    // run ahead of the issuing thread, so everything a single issuer does between two items (commits, barrier polls, loop
+    // bookkeeping, descriptor set-up: 500-700 cycles) shows up as idle tensor pipe -- a third of the time when an item is
+    // 36 MMAs of 40 cycles.  With two issuers that work hides behind the other warp's MMAs.  The items of the two warps
+    // accumulate into different TMEM stages, so their relative order in the pipe does not matter.  Each issuer owns HALF of
+    // the A ring (the producer alternates halves per item): a shared ring would make a warp poll an mbarrier phase whose
+    // predecessor has not completed yet, which a parity wait cannot express.
     // The whole warp runs the (warp-uniform) loop so that descriptors live in uniform registers; only the elected
     // lane issues tcgen05.mma / tcgen05.commit.  Steady state with resident weights: one wait + one elected region
     // per K-chunk that issues all taps back to back (compile-time tap offsets); streaming weights: per-tap
@@ -339,7 +361,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       constexpr uint32_t kLbo = 1u << 16;
       const uint32_t a_base16 = smem_u32(a_buf) >> 4, a_stage16 = p.a_stage_bytes >> 4;
       const uint32_t b_base16 = smem_u32(b_buf) >> 4, b_stage16 = p.b_stage_bytes >> 4;
-      const uint32_t n_a = p.a_stages, n_b = p.b_stages;
+      const bool dual = p.dual_issue != 0;
+      const uint32_t mw = (uint32_t)warp - 1u;     // which of the two issuers
+      const uint32_t n_a = dual ? (uint32_t)p.a_stages >> 1 : (uint32_t)p.a_stages, n_b = p.b_stages;
+      const uint32_t ring0 = dual ? mw * n_a : 0u;   // first stage of this issuer's part of the A ring
       const bool resident = p.b_resident != 0;
       const bool no_mma = (p.debug_flags & 2) != 0;
       // per-segment constants, hoisted out of the item loop
@@ -358,18 +383,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         seg_chunks[s] = on ? p.seg[s].nchunks : 0;
         seg_halo[s] = halo;
       }
-      uint32_t sa = 0, pa = 0;          // A ring: stage, phase
+      uint32_t sa = 0, pa = 0;          // A ring (this issuer's part): stage, phase
       uint32_t sb = 0, pb = 0;          // B ring (streaming mode) / running slot (resident mode)
-      uint32_t as = 0, pacc = 0;        // accumulator ring
       uint32_t n_items = 0;
       bool first_item = true;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        LASS_TIMED_WAIT(&acc_empty[as], pacc ^ 1, kProfMmaAccEmpty);
+      const int step = dual ? 2 : 1;
+      uint32_t n = dual ? mw : 0u;      // index of the item within this CTA's sequence
+      for (int item = (dual || mw == 0) ? (int)blockIdx.x + (int)n * (int)gridDim.x : p.num_items; item < p.num_items;
+           item += step * (int)gridDim.x, n += step) {
+        const uint32_t as = n % NS, pacc = (n / NS) & 1u;
+        if (!mma_only) LASS_TIMED_WAIT(&acc_empty[as], pacc ^ 1, kProfMmaAccEmpty);
         tc_fence_after_sync();
         const uint32_t acc_addr = tmem_base + as * (MT * BN);
         uint32_t accumulate = 0;
         if (resident) sb = 0;
-        const bool need_wait = !resident || first_item;
+        const bool need_wait = !resident || (first_item && !mma_only);
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           const SegMma gs = g[s];
@@ -380,25 +408,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
           const uint32_t mt_step16 = 16 * pitch * row16;
 #pragma unroll 1
           for (uint32_t ch = 0; ch < seg_chunks[s]; ++ch) {
-            LASS_TIMED_WAIT(&a_full[sa], pa, kProfMmaAFull);
+            if (!mma_only) LASS_TIMED_WAIT(&a_full[ring0 + sa], pa, kProfMmaAFull);
             tc_fence_after_sync();
-            uint32_t a_lo = (a_base16 + sa * a_stage16) | kLbo;
+            uint32_t a_lo = (a_base16 + (ring0 + sa) * a_stage16) | kLbo;
             if (!need_wait) {
               // ---- resident weights, steady state: all taps of the chunk in one elected region ----
               const uint32_t b_lo = (b_base16 + sb * b_stage16) | kLbo;
               if (!no_mma && elect_one()) {
                 if (halo) {
-                  if (kc == 64) {
-#pragma unroll
-                    for (int tp = 0; tp < 9; ++tp)
-                      issue_tap<MT, BN, 4>(acc_addr, a_lo + ((tp / 3) * kHaloPitch + tp % 3) * 8, 16 * kHaloPitch * 8,
-                                           b_lo + tp * b_stage16, gs, (tp == 0) ? accumulate : 1u);
-                  } else {
-#pragma unroll
-                    for (int tp = 0; tp < 9; ++tp)
-                      issue_tap<MT, BN, 2>(acc_addr, a_lo + ((tp / 3) * kHaloPitch + tp % 3) * 4, 16 * kHaloPitch * 4,
-                                           b_lo + tp * b_stage16, gs, (tp == 0) ? accumulate : 1u);
-                  }
+                  if (kc == 64) issue_halo_chunk_running<MT, BN, 4>(acc_addr, a_lo, b_lo, b_stage16, gs, accumulate);
+                  else issue_halo_chunk_running<MT, BN, 2>(acc_addr, a_lo, b_lo, b_stage16, gs, accumulate);
                 } else {
                   if (kc == 64) issue_tap<MT, BN, 4>(acc_addr, a_lo, 16 * TW * 8, b_lo, gs, accumulate);
                   else issue_tap<MT, BN, 2>(acc_addr, a_lo, 16 * TW * 4, b_lo, gs, accumulate);
@@ -414,7 +433,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
 #pragma unroll
                 for (uint32_t dx = 0; dx < 3; ++dx) {
                   if (dx > 0 && !halo) break;
-                  LASS_TIMED_WAIT(&b_full[sb], resident ? 0u : pb, kProfMmaBFull);
+                  if (!mma_only) LASS_TIMED_WAIT(&b_full[sb], resident ? 0u : pb, kProfMmaBFull);
                   tc_fence_after_sync();
                   const uint32_t b_lo = (b_base16 + sb * b_stage16) | kLbo;
                   if (!no_mma && elect_one()) {
@@ -437,7 +456,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                 a_lo += pitch * row16;
               }
             }
-            if (elect_one()) umma_commit(&a_empty[sa]);
+            if (elect_one()) umma_commit(&a_empty[ring0 + sa]);
             __syncwarp();
             if (++sa == n_a) {
               sa = 0;
@@ -447,14 +466,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         }
         if (elect_one()) umma_commit(&acc_full[as]);
         __syncwarp();
-        if (++as == AS) {
-          as = 0;
-          pacc ^= 1;
-        }
         ++n_items;
         first_item = false;
       }
-      if (prof && lane == 0) {
+      if (mma_only) {
+        // all MMAs done before the TMEM is released: one more commit on a barrier nobody else uses in this mode
+        if (elect_one()) umma_commit(&b_empty[mw]);
+        __syncwarp();
+        mbar_wait(&b_empty[mw], 0);
+      }
+      if (prof && lane == 0 && mw == 0) {
         long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
         dst[kProfMmaAccEmpty] = pc[kProfMmaAccEmpty];
         dst[kProfMmaAFull] = pc[kProfMmaAFull];
@@ -463,13 +484,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
         dst[kProfItems] = n_items;
       }
     }
-  } else {
+  } else if (!mma_only) {
     // =========================== epilogue ===========================
     // Two groups of four warps; group g drains accumulator stage g (items g, g + 2, ... of this CTA), so two
     // items are in the epilogue at once and every SM sub-partition has two epilogue warps to overlap latencies.
-    const int grp = (warp - 2) >> 2;
+    const int grp = (warp - 3) >> 2;
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int et = (threadIdx.x - 64) & 127;         // thread index within the group
+    const int et = (threadIdx.x - 96) & 127;         // thread index within the group
     const int hl = q * 4 + (lane >> 3);
     const int wl = lane & 7;
     const int Ho = p.H * p.up_h, Wo = p.W * p.up_w;
@@ -477,17 +498,76 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
     const bool pooling = ((p.pool_raw.ptr != nullptr) || (p.pool_act.ptr != nullptr)) && !(p.debug_flags & 8);
     const bool no_store = (p.debug_flags & 16) != 0;
     const float pool_scale = 1.0f / (float)(p.pool_h * p.pool_w);
-    const uint32_t as = (AS == 2) ? (uint32_t)grp : 0u;
     EpiTables<BN>* gtabs = tabs + 2 * grp;
     const bool tma_store = p.tma_store != 0;
     const bool tma_pool = p.tma_pool != 0;
-    unsigned char* stg = stage_base + (size_t)(warp - 2) * kStageWarpBytes;
-    uint32_t uses = 0;                               // completed uses of accumulator stage `as` by this group
+    unsigned char* stg = stage_base + (size_t)(warp - 3) * kStageWarpBytes;
+    uint32_t n = (uint32_t)grp;                      // index of the item within this CTA's sequence
     int tab_b = -1, tab_n0 = -1;
     uint32_t tab_sel = 0;
-    for (int item = blockIdx.x + (AS == 2 ? grp : 0) * (int)gridDim.x; item < p.num_items;
-         item += (AS == 2 ? 2 : 1) * (int)gridDim.x) {
-      if (AS == 1 && grp == 1) break;
+    if (p.epi_mode == 1) {
+      // ---- lean path: ONE activated bf16 output written with direct stores (first conv of every block, decoder conv2) ----
+      // The generic loop below spends ~450 instructions per 32 pixels x 32 channels on run-time feature tests; this one
+      // ~150, and the table reads (ld.shared, issued before tcgen05.wait::ld) overlap the TMEM load.
+      uint16_t* const out = reinterpret_cast<uint16_t*>(p.full_act.ptr) + p.full_act.coff;
+      const int cstride = p.full_act.cstride;
+      const bool idle = (p.debug_flags & 1) != 0;
+      for (int item = blockIdx.x + grp * (int)gridDim.x; item < p.num_items; item += 2 * (int)gridDim.x, n += 2) {
+        const uint32_t as = n % NS, acc_parity = (n / NS) & 1u;
+        const Item it = decode_item<MT>(p, item, BN);
+        if (it.b != tab_b || it.n0 != tab_n0) {
+          tab_sel ^= 1u;
+          EpiTables<BN>& t = gtabs[tab_sel];
+          for (int c = et; c < BN; c += 128) {
+            const int nn = it.n0 + c;
+            const bool in = nn < p.ncols;
+            const float scv = in ? __ldg(p.full_act.scale + nn) : 0.0f;
+            const float shv = in ? __ldg(p.full_act.shift + (size_t)it.b * p.full_act.shift_bstride + nn) : 0.0f;
+            t.sc_full[c] = scv;
+            t.sh_full[c] = fmaf(scv, (in && p.bias) ? __ldg(p.bias + nn) : 0.0f, shv);   // conv bias folded into the shift
+          }
+          tab_b = it.b;
+          tab_n0 = it.n0;
+          if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+          else asm volatile("bar.sync 2, 128;" ::: "memory");
+        }
+        const uint32_t sc_addr = smem_u32(gtabs[tab_sel].sc_full), sh_addr = smem_u32(gtabs[tab_sel].sh_full);
+        const int w = it.w0 + wl;
+        uint16_t* dst[MT];
+        bool valid[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const int h = it.h0 + mt * 16 + hl;
+          valid[mt] = (h < p.H) && (w < p.W) && !no_store;
+          dst[mt] = out + (((size_t)it.b * p.H + h) * p.W + w) * cstride + it.n0;
+        }
+        const uint32_t taddr = tmem_base + as * (MT * BN) + (static_cast<uint32_t>(q * 32) << 16);
+        const int nchunk = min(BN, p.ncols - it.n0);
+        mbar_wait(&acc_full[as], acc_parity);
+        tc_fence_after_sync();
+#pragma unroll 1
+        for (int c0 = 0; c0 < nchunk; c0 += 32) {
+          float v[MT][32];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) tmem_ld_x32(taddr + mt * BN + c0, v[mt]);
+          float4 sc[8], sh[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            sc[j] = lds128(sc_addr + (c0 + 4 * j) * 4);
+            sh[j] = lds128(sh_addr + (c0 + 4 * j) * 4);
+          }
+          tmem_ld_wait();
+          if (idle) continue;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) act_store32(v[mt], sc, sh, dst[mt] + c0, valid[mt]);
+        }
+        tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[as]);
+      }
+    } else
+    for (int item = blockIdx.x + grp * (int)gridDim.x; item < p.num_items; item += 2 * (int)gridDim.x, n += 2) {
+      const uint32_t as = n % NS, acc_parity = (n / NS) & 1u;
       const Item it = decode_item<MT>(p, item, BN);
       // ---- (re)stage the per-(clip, N tile) tables; double-buffered so one named barrier per change suffices ----
       if (it.b != tab_b || it.n0 != tab_n0) {
@@ -524,10 +604,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
                               __ldg(p.resid_in_shift + ww));
       }
       if (q == 0 && lane == 0 && grp == 0) {
-        LASS_TIMED_WAIT(&acc_full[as], uses & 1, kProfEpiAccFull);
+        LASS_TIMED_WAIT(&acc_full[as], acc_parity, kProfEpiAccFull);
       }
       __syncwarp();
-      mbar_wait(&acc_full[as], uses & 1);
+      mbar_wait(&acc_full[as], acc_parity);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
@@ -722,7 +802,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_igemm_kernel(const __grid_co
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
-      ++uses;
     }
     if (tma_store && lane == 0) tma_store_wait_all();
     if (prof && q == 0 && lane == 0 && grp == 0) {
@@ -790,6 +869,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const bool prof = LASS_PROF_ON(p);
+  long long pc[kProfSlots];
+#pragma unroll
+  for (int i = 0; i < kProfSlots; ++i) pc[i] = 0;
+  const long long t_start = prof ? clock64() : 0;
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
@@ -831,11 +915,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_cons
         const uint32_t b_bytes = (uint32_t)(halo ? N3 : COUT) * row_bytes;
         for (int ch = 0; ch < sg.nchunks; ++ch) {
           const uint32_t sa = a_it % p.a_stages;
-          mbar_wait(&a_empty[sa], ((a_it / p.a_stages) & 1) ^ 1);
+          LASS_TIMED_WAIT(&a_empty[sa], ((a_it / p.a_stages) & 1) ^ 1, kProfProdAEmpty);
           if (elect_one()) {
-            mbar_arrive_expect_tx(&a_full[sa], a_bytes);
-            tma_load_4d(a_buf + (size_t)sa * p.a_stage_bytes, &sg.tmA, &a_full[sa], ch * sg.kc, it.w0 - 1,
-                        halo ? it.h0 - 1 : it.h0, it.b);
+            if (p.debug_flags & 4) {
+              mbar_arrive(&a_full[sa]);
+            } else {
+              mbar_arrive_expect_tx(&a_full[sa], a_bytes);
+              tma_load_4d(a_buf + (size_t)sa * p.a_stage_bytes, &sg.tmA, &a_full[sa], ch * sg.kc, it.w0 - 1,
+                          halo ? it.h0 - 1 : it.h0, it.b);
+            }
           }
           __syncwarp();
           ++a_it;
@@ -853,6 +941,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_cons
       }
       first_item = false;
     }
+    if (prof && lane == 0) {
+      long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
+      dst[kProfProdAEmpty] = pc[kProfProdAEmpty];
+      dst[kProfProdTotal] = clock64() - t_start;
+    }
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     constexpr uint32_t kLbo = 1u << 16;
@@ -860,9 +953,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_cons
     const uint32_t b_base16 = smem_u32(b_buf) >> 4, b_stage16 = p.b_stage_bytes >> 4;
     const uint32_t n_a = p.a_stages;
     uint32_t sa = 0, pa = 0, as = 0, pacc = 0;
+    uint32_t n_items = 0;
+    const bool no_mma = (p.debug_flags & 2) != 0;
     bool first_item = true;
     for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      mbar_wait(&acc_empty[as], pacc ^ 1);
+      LASS_TIMED_WAIT(&acc_empty[as], pacc ^ 1, kProfMmaAccEmpty);
       tc_fence_after_sync();
       const uint32_t acc_addr = tmem_base + as * (MT * N3);
       uint32_t b_slot = 0;
@@ -883,7 +978,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_cons
         const uint32_t nchunks = p.seg[s].nchunks;
 #pragma unroll 1
         for (uint32_t ch = 0; ch < nchunks; ++ch) {
-          mbar_wait(&a_full[sa], pa);
+          LASS_TIMED_WAIT(&a_full[sa], pa, kProfMmaAFull);
           tc_fence_after_sync();
           const uint32_t a_lo = (a_base16 + sa * a_stage16) | kLbo;
           const uint32_t ndy = halo ? 3u : 1u;
@@ -891,7 +986,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_cons
             for (uint32_t dy = 0; dy < ndy; ++dy) mbar_wait(&b_full[b_slot + dy], 0);
             tc_fence_after_sync();
           }
-          if (elect_one()) {
+          if (!no_mma && elect_one()) {
 #pragma unroll 1
             for (uint32_t dy = 0; dy < ndy; ++dy) {
               const uint32_t b_lo = (b_base16 + (b_slot + dy) * b_stage16) | kLbo;
@@ -918,6 +1013,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_cons
         pacc ^= 1;
       }
       first_item = false;
+      ++n_items;
+    }
+    if (prof && lane == 0) {
+      long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
+      dst[kProfMmaAccEmpty] = pc[kProfMmaAccEmpty];
+      dst[kProfMmaAFull] = pc[kProfMmaAFull];
+      dst[kProfMmaTotal] = clock64() - t_start;
+      dst[kProfItems] = n_items;
     }
   } else {
     // =========================== epilogue ===========================
@@ -967,12 +1070,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_cons
           resid_xs[mt] = fmaf(__ldg(p.resid_in_scale + w), __ldg(p.resid_src + ((size_t)it.b * p.resid_T + hh) * p.resid_F + w),
                               __ldg(p.resid_in_shift + w));
       }
+      if (q == 0 && lane == 0 && grp == 0) {
+        LASS_TIMED_WAIT(&acc_full[as], uses & 1, kProfEpiAccFull);
+      }
+      __syncwarp();
       mbar_wait(&acc_full[as], uses & 1);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int h = it.h0 + mt * 8 + hr;
-        const bool valid = col_ok && (h < p.H) && (w < p.W);
+        const bool valid = col_ok && (h < p.H) && (w < p.W) && !(p.debug_flags & 16);
         const uint32_t taddr = tmem_base + as * (MT * N3) + mt * N3 + (static_cast<uint32_t>(q * 32) << 16);
         const float resid_x = (MT == 2 && mt == 1) ? resid_xs[MT - 1] : resid_xs[0];
         float fa0 = 0.0f, fa1 = 0.0f, fa2 = 0.0f;
@@ -982,6 +1089,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_cons
           tmem_ld_x32(taddr + COUT + c0, v);         // dx = 1: this position
           tmem_ld_x32(taddr + c0, t);                // dx = 0: contribution computed at the left neighbour
           tmem_ld_wait();
+          if (p.debug_flags & 1) continue;
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += __shfl_up_sync(0xffffffffu, t[j], 1);
           tmem_ld_x32(taddr + 2 * COUT + c0, t);     // dx = 2: right neighbour
@@ -1066,6 +1174,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_cons
       if (lane == 0) mbar_arrive(&acc_empty[as]);
       ++uses;
     }
+    if (prof && q == 0 && lane == 0 && grp == 0) {
+      long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
+      dst[kProfEpiAccFull] = pc[kProfEpiAccFull];
+      dst[kProfEpiTotal] = clock64() - t_start;
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -1098,6 +1211,7 @@ struct ConvPrepared {
   ConvParams params;
   ConvKernelFn fn;
   int grid;
+  int threads;
   size_t smem;
 };
 
@@ -1174,6 +1288,7 @@ static int conv_prepare_dxn(const ConvLaunch& l, ConvPrepared** out) {
   p.resid_T = l.resid_T;
   p.resid_F = l.resid_F;
   p.debug_flags = g_debug_flags;
+  p.prof = g_prof_buffer;
   fill_out(p.full_raw, l.full_raw);
   fill_out(p.full_act, l.full_act);
   fill_out(p.pool_raw, l.pool_raw);
@@ -1229,7 +1344,7 @@ static int conv_prepare_dxn(const ConvLaunch& l, ConvPrepared** out) {
   p.b_resident = 1;
   p.b_stages = b_tiles;
   const size_t kBudget = 220 * 1024;
-  const size_t fixed = 1024 + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 + 4 * ((size_t)6 * cout + 3 * 32 + 4) * sizeof(float) + 64;
+  const size_t fixed = 1024 + (2 * kMaxA + 2 * kMaxB + 8) * 8 + 64 + 4 * ((size_t)6 * cout + 3 * 32 + 4) * sizeof(float) + 64;
   if (b_tiles > kMaxB || fixed + (size_t)b_tiles * p.b_stage_bytes + 2 * (size_t)p.a_stage_bytes > kBudget) {
     delete cp;
     return set_error(LASS_ERR_ARG, "conv(dxn): weights (%d tiles of %u B) do not fit in shared memory", b_tiles, p.b_stage_bytes);
@@ -1238,6 +1353,7 @@ static int conv_prepare_dxn(const ConvLaunch& l, ConvPrepared** out) {
   if (p.a_stages > 4) p.a_stages = 4;
   cp->smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes;
   cp->fn = cout == 32 ? conv_dxn_kernel<32, 2> : conv_dxn_kernel<64, 1>;
+  cp->threads = kThreads;
   if (g_num_sms == 0) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1397,7 +1513,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   // ---- shared-memory budget: weights resident if every tile of an item fits, else a streaming ring; the per-warp
   //      TMA-store staging (48 KiB) is taken when it still leaves a healthy pipeline ----
   const size_t kBudget = 220 * 1024;
-  const size_t fixed_base = 1024 /*alignment slack*/ + (2 * kMaxA + 2 * kMaxB + 4) * 8 + 64 +
+  const size_t fixed_base = 1024 /*alignment slack*/ + (2 * kMaxA + 2 * kMaxB + 8) * 8 + 64 +
                             4 * ((size_t)6 * BN + 3 * 32 + 4) * sizeof(float) + 64;
   const size_t stage_bytes = 1024 + (size_t)kEpiWarps * kStageWarpBytes;
   const bool has_16bit_out = l.full_raw.ptr || l.full_act.ptr || l.pool_raw.ptr || l.pool_act.ptr;
@@ -1424,6 +1540,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
       size_t rest = kBudget - fixed - (size_t)p.b_stages * p.b_stage_bytes;
       p.a_stages = (int)(rest / p.a_stage_bytes);
       if (p.a_stages > 4) p.a_stages = 4;
+      p.dual_issue = (p.a_stages == 4 && !(g_debug_flags & 128)) ? 1 : 0;
       break;
     }
     p.b_resident = 0;
@@ -1437,6 +1554,10 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     delete cp;
     return set_error(LASS_ERR_ARG, "conv: tile does not fit in shared memory");
   }
+  p.epi_mode = (!p.tma_store && l.full_act.ptr && !l.full_raw.ptr && !l.pool_raw.ptr && !l.pool_act.ptr && !l.after_w &&
+                !l.resid_src && up == 1 && !(g_debug_flags & 256))
+                   ? 1
+                   : 0;
   p.tma_pool = (p.tma_store && ((l.pool_raw.ptr && l.pool_raw.cstride != l.ncols) || (l.pool_act.ptr && l.pool_act.cstride != l.ncols))) ? 1 : 0;
   if (p.tma_store) {
     const int Ho = l.H * l.up_h, Wo = l.W * l.up_w;
@@ -1478,11 +1599,12 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     return set_cuda_error(ce, "conv smem attribute");
   }
   // CTAs per SM: limited by shared memory / registers (occupancy query) and by TMEM (AS * MT * BN columns each)
-  const int tmem_cols = ((2 * MT * BN <= 512) ? 2 : 1) * MT * BN;
+  const int tmem_need = tmem_cols(BN, MT);
   int per_sm = 1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(kc.fn), kThreads, cp->smem) != cudaSuccess || per_sm < 1)
+  cp->threads = kThreadsK;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(kc.fn), kThreadsK, cp->smem) != cudaSuccess || per_sm < 1)
     per_sm = 1;
-  if (per_sm > 512 / tmem_cols) per_sm = 512 / tmem_cols;
+  if (per_sm > 512 / tmem_need) per_sm = 512 / tmem_need;
   if (per_sm > 2) per_sm = 2;
   cp->grid = p.num_items < g_num_sms * per_sm ? p.num_items : g_num_sms * per_sm;
   *out = cp;
@@ -1490,7 +1612,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
 }
 
 int conv_run(const ConvPrepared* cp, cudaStream_t stream) {
-  cp->fn<<<cp->grid, kThreads, cp->smem, stream>>>(cp->params);
+  cp->fn<<<cp->grid, cp->threads, cp->smem, stream>>>(cp->params);
   return set_cuda_error(cudaGetLastError(), "conv launch");
 }
 

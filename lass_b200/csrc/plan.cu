@@ -85,6 +85,7 @@ struct lass_plan {
   Buf mag, cosb, sinb, shift, feat;
   Buf x_raw[7], x_act[7], a2[7], cat_raw[6], cat_act[6], d_act[7];
   std::vector<ConvPrepared*> convs;
+  std::vector<double> conv_flops;
   double conv_flops_total = 0;
 };
 
@@ -201,6 +202,7 @@ int add_conv(lass_plan* p, const ConvLaunch& l) {
   int e = conv_prepare(l, &cp);
   if (e) return e;
   p->convs.push_back(cp);
+  p->conv_flops.push_back(conv_flops(l));
   p->conv_flops_total += conv_flops(l);
   return 0;
 }
@@ -426,6 +428,32 @@ int lass_resunet30_forward_stages(lass_plan* p, int stage_mask, const float* mix
 }
 
 int lass_resunet30_num_launches(const lass_plan* p) { return p ? (int)p->convs.size() + 5 : 0; }
+
+int lass_debug_time_unet_launches(lass_plan* p, float* ms_out, double* flops_out, int capacity, void* stream_v) {
+  if (!p || !ms_out) return set_error(LASS_ERR_ARG, "time_unet_launches: null pointer");
+  const int n = (int)p->convs.size();
+  if (capacity < n) return set_error(LASS_ERR_ARG, "time_unet_launches: capacity %d < %d launches", capacity, n);
+  cudaStream_t stream = (cudaStream_t)stream_v;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (int i = 0; i <= n; ++i)
+    if (cudaEventCreate(&ev[i]) != cudaSuccess) return set_cuda_error(cudaGetLastError(), "event create");
+  int e = 0;
+  cudaEventRecord(ev[0], stream);
+  for (int i = 0; i < n && !e; ++i) {
+    e = conv_run(p->convs[i], stream);
+    cudaEventRecord(ev[i + 1], stream);
+  }
+  cudaError_t ce = cudaStreamSynchronize(stream);
+  for (int i = 0; i < n; ++i) {
+    ms_out[i] = 0.0f;
+    if (!e && ce == cudaSuccess) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+    if (flops_out) flops_out[i] = p->conv_flops[i];
+  }
+  for (int i = 0; i <= n; ++i) cudaEventDestroy(ev[i]);
+  if (e) return e;
+  if (ce != cudaSuccess) return set_cuda_error(ce, "time_unet_launches sync");
+  return n;
+}
 
 void* lass_resunet30_buffer(const lass_plan* p, const char* name, int dims[4], int* elem_bytes) {
   if (!p || !name) return nullptr;

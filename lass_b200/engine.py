@@ -17,7 +17,7 @@ _ENC = ("encoder_block1", "encoder_block2", "encoder_block3", "encoder_block4", 
         "conv_block7a")
 _DEC = ("decoder_block1", "decoder_block2", "decoder_block3", "decoder_block4", "decoder_block5", "decoder_block6")
 BN_EPS = 1e-5
-DEFAULT_DXN_MASK = (1 << 0) | (1 << (14 + 8)) | (1 << (14 + 9)) | (1 << (14 + 10)) | (1 << (14 + 11))
+DEFAULT_DXN_MASK = 0   # dx-in-N kernel off: since the dual-issuer tap-in-K kernel it loses on every layer (tools/gpu_layer_times.py)
 
 
 def _dev_key(device):
@@ -273,6 +273,17 @@ class Engine:
 
     def unet_flops(self, B, L, device):
         return _cabi.load().lass_resunet30_unet_flops(self._get_plan(B, L, device).handle)
+
+    def time_unet_launches(self, B, L, device):
+        """Per-launch (ms, algorithmic FLOPs) of the UNET stage over the workspace's current contents (debug / profiling)."""
+        plan = self._get_plan(B, L, device)
+        ms = (ctypes.c_float * 64)()
+        fl = (ctypes.c_double * 64)()
+        with torch.cuda.device(device):
+            n = _cabi.load().lass_debug_time_unet_launches(plan.handle, ms, fl, 64, torch.cuda.current_stream().cuda_stream)
+        if n < 0:
+            _cabi.check(n)
+        return [(ms[i], fl[i]) for i in range(n)]
 
     def num_launches(self, B, L, device):
         return _cabi.load().lass_resunet30_num_launches(self._get_plan(B, L, device).handle)

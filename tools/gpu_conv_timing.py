@@ -8,9 +8,11 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("LASS_B200_LIB", os.path.join(ROOT, "lass_b200", "_lib", "liblass_b200_prof.so"))   # `make prof`
 from lass_b200 import _cabi, ops, packing  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+FLAGS = (0, 1, 2, 256)
 dev = "cuda"
 LAYERS = {
     "dec5.up 64->32x4 @512x256": (512, 256, 64, 32, 0, 2, False, (2, 2)),
@@ -61,10 +63,11 @@ def bench_layer(H, W, cin, cout, sc, nout, pool, up=(1, 1), algo=0):
     # role profile (cycles per item, averaged over CTAs)
     prof = torch.zeros(296 * 16, dtype=torch.int64, device=dev)
     lib = _cabi.load()
-    lib.lass_debug_set_conv_profile(prof.data_ptr())
-    ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
-    torch.cuda.synchronize()
-    lib.lass_debug_set_conv_profile(None)
+    if not os.environ.get("LASS_NO_PROFILE_RUN"):
+        _cabi.check(lib.lass_debug_set_conv_profile(prof.data_ptr()))
+        ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
+        torch.cuda.synchronize()
+        lib.lass_debug_set_conv_profile(None)
     pr = prof.view(296, 16).cpu().double()
     pr = pr[pr[:, 9] > 0]
     if pr.shape[0] == 0:
@@ -75,7 +78,7 @@ def bench_layer(H, W, cin, cout, sc, nout, pool, up=(1, 1), algo=0):
     res["profile_cyc_per_item"] = {n: round(pr[:, i].mean().item() / items) for i, n in enumerate(names)}
     res["items_per_cta"] = items
     res["ctas"] = int(pr.shape[0])
-    for flags in (0, 1, 2, 3):
+    for flags in FLAGS:
         _cabi.load().lass_debug_set_conv_flags(flags)
         for _ in range(2):
             ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
@@ -86,6 +89,17 @@ def bench_layer(H, W, cin, cout, sc, nout, pool, up=(1, 1), algo=0):
         e1.record()
         torch.cuda.synchronize()
         res["flags%d" % flags] = round(e0.elapsed_time(e1) / 3, 4)
+        if flags in (1, 64) and not os.environ.get("LASS_NO_PROFILE_RUN"):
+            prof.zero_()
+            lib.lass_debug_set_conv_profile(prof.data_ptr())
+            ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
+            torch.cuda.synchronize()
+            lib.lass_debug_set_conv_profile(None)
+            pr = prof.view(296, 16).cpu().double()
+            pr = pr[pr[:, 9] > 0]
+            if pr.shape[0]:
+                it = pr[:, 9].mean().item()
+                res["profile_flags%d" % flags] = {n: round(pr[:, i].mean().item() / it) for i, n in enumerate(names)}
     _cabi.load().lass_debug_set_conv_flags(0)
     flops = 2.0 * B * H * W * cout * nup * ((9 if nup == 1 else 1) * cin + sc)
     res["tflops_normal"] = round(flops / (res["flags0"] * 1e-3) / 1e12, 1)
