@@ -33,9 +33,21 @@ namespace lass {
 
 namespace {
 
-template <int V>
-struct IntTag {
-  static constexpr int value = V;
+template <uint32_t V>
+struct UTag {
+  static constexpr uint32_t value = V;
+};
+// epilogue features of conv_igemm_kernel (compile-time sets for the launch shapes of the ResUNet30 plan)
+enum : uint32_t {
+  kFRaw = 1u, kFAct = 2u, kFTma = 4u, kFTmaPool = 8u, kFPool = 16u, kFPoolH2 = 32u, kFPoolRaw = 64u, kFPoolAct = 128u,
+  kFAfter = 256u, kFResid = 512u, kFBias = 1024u, kFUp = 2048u, kFGeneric = 0x80000000u,
+  // encoder conv2: raw + activated skip into the concat buffers (TMA stores) + pooled raw / activated block output
+  kFEnc2Common = kFRaw | kFAct | kFTma | kFPool | kFPoolRaw | kFPoolAct,
+  kFEnc2Resid = kFEnc2Common | kFPoolH2 | kFResid,       // encoder_block1 (rank-1 identity residual)
+  kFEnc2Bias = kFEnc2Common | kFPoolH2 | kFBias,         // encoder_block2..5 (1x1 shortcut segment, bias)
+  kFEnc2BiasP12 = kFEnc2Common | kFBias,                 // encoder_block6 (pooling (1, 2))
+  kFUpconv = kFRaw | kFAct | kFTma | kFUp,               // transposed convs into the concat buffers
+  kFAfterBias = kFAfter | kFBias,                        // decoder_block6 conv2 + after_conv
 };
 constexpr int kThreads = 320;   // conv_dxn_kernel: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
 constexpr int kThreadsK = 352;  // conv_igemm_kernel: warp 0 TMA producer, warps 1-2 MMA issuers, warps 3-6 / 7-10 epilogue groups
@@ -84,7 +96,8 @@ struct ConvParams {
   int B, H, W, ncols;
   int tiles_h, tiles_w, pix_tiles, n_tiles, num_items;
   int a_stages, b_stages, b_resident;
-  int epi_mode;    // conv_igemm_kernel: 1 = lean epilogue (one activated bf16 output, direct stores), 0 = generic
+  int epi_mode;    // conv_igemm_kernel: 0 = generic epilogue (run-time feature tests), 1 = lean path (one activated bf16 output,
+                   // direct stores), 2..6 = generic code specialised at compile time for a feature set (see kFEnc2Resid ...)
   int dual_issue;  // conv_igemm_kernel: two MMA-issuing warps, each with half of the A ring (resident weights, >= 4 A stages)
   int tma_store;   // 1: full-resolution 16-bit outputs leave through per-warp shared-memory staging + TMA stores
   int tma_pool;    // 1: pooled outputs too (only when they are channel slices; whole-pixel pooled outputs store directly)
@@ -565,7 +578,12 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
         __syncwarp();
         if (lane == 0) mbar_arrive(&acc_empty[as]);
       }
-    } else
+    } else {
+    auto generic_items = [&](auto ftag) {
+    // F == kFGeneric: every feature is tested at run time; otherwise F is the exact feature set of the launch and the
+    // tests fold away (the specialised copies run ~2x fewer instructions per output tile)
+    constexpr uint32_t F = decltype(ftag)::value;
+#define FEAT(bit, cond) ((F == kFGeneric) ? (cond) : ((F & (bit)) != 0u))
     for (int item = blockIdx.x + grp * (int)gridDim.x; item < p.num_items; item += 2 * (int)gridDim.x, n += 2) {
       const uint32_t as = n % NS, acc_parity = (n / NS) & 1u;
       const Item it = decode_item<MT>(p, item, BN);
@@ -576,30 +594,31 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
         for (int c = et; c < BN; c += 128) {
           const int n = it.n0 + c;
           const bool in = n < p.ncols;
-          const int cc = (p.up_h * p.up_w > 1) ? n % p.group_c : n;
-          t.bias[c] = ((in && p.bias) ? __ldg(p.bias + n) : 0.0f) + ((in && p.resid_src) ? __ldg(p.resid_b + n) : 0.0f);
-          t.resid_w[c] = (in && p.resid_src) ? __ldg(p.resid_w + n) : 0.0f;
-          t.sc_full[c] = (in && p.full_act.scale) ? __ldg(p.full_act.scale + cc) : 0.0f;
-          t.sh_full[c] = (in && p.full_act.scale) ? __ldg(p.full_act.shift + (size_t)it.b * p.full_act.shift_bstride + cc) : 0.0f;
-          t.sc_pool[c] = (in && p.pool_act.scale) ? __ldg(p.pool_act.scale + cc) : 0.0f;
-          t.sh_pool[c] = (in && p.pool_act.scale) ? __ldg(p.pool_act.shift + (size_t)it.b * p.pool_act.shift_bstride + cc) : 0.0f;
+          const int cc = (FEAT(kFUp, p.up_h * p.up_w > 1)) ? n % p.group_c : n;
+          t.bias[c] = ((in && FEAT(kFBias, p.bias != nullptr)) ? __ldg(p.bias + n) : 0.0f) + ((in && FEAT(kFResid, p.resid_src != nullptr)) ? __ldg(p.resid_b + n) : 0.0f);
+          t.resid_w[c] = (in && FEAT(kFResid, p.resid_src != nullptr)) ? __ldg(p.resid_w + n) : 0.0f;
+          t.sc_full[c] = (in && FEAT(kFAct, p.full_act.scale != nullptr)) ? __ldg(p.full_act.scale + cc) : 0.0f;
+          t.sh_full[c] = (in && FEAT(kFAct, p.full_act.scale != nullptr)) ? __ldg(p.full_act.shift + (size_t)it.b * p.full_act.shift_bstride + cc) : 0.0f;
+          t.sc_pool[c] = (in && FEAT(kFPoolAct, p.pool_act.scale != nullptr)) ? __ldg(p.pool_act.scale + cc) : 0.0f;
+          t.sh_pool[c] = (in && FEAT(kFPoolAct, p.pool_act.scale != nullptr)) ? __ldg(p.pool_act.shift + (size_t)it.b * p.pool_act.shift_bstride + cc) : 0.0f;
         }
-        if (p.after_w != nullptr && et < 3 * 32)
+        if (FEAT(kFAfter, p.after_w != nullptr) && et < 3 * 32)
           t.after_w[et] = (et % 32 < p.ncols) ? __ldg(p.after_w + (et / 32) * p.ncols + et % 32) : 0.0f;
-        if (p.after_w != nullptr && et < 3) t.after_b[et] = __ldg(p.after_b + et);
+        if (FEAT(kFAfter, p.after_w != nullptr) && et < 3) t.after_b[et] = __ldg(p.after_b + et);
         tab_b = it.b;
         tab_n0 = it.n0;
         if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
         else asm volatile("bar.sync 2, 128;" ::: "memory");
       }
       const EpiTables<BN>& tb = gtabs[tab_sel];
+      __builtin_assume(__isShared(&tb));   // table reads become ld.shared instead of generic loads
       // rank-1 residual operand of this thread's pixels: loaded before the accumulator wait so the latency is hidden
       float resid_xs[MT];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
         resid_xs[mt] = 0.0f;
         const int hh = it.h0 + mt * 16 + hl, ww = it.w0 + wl;
-        if (p.resid_src != nullptr && hh < p.resid_T && ww < p.W)
+        if (FEAT(kFResid, p.resid_src != nullptr) && hh < p.resid_T && ww < p.W)
           resid_xs[mt] = fmaf(__ldg(p.resid_in_scale + ww), __ldg(p.resid_src + ((size_t)it.b * p.resid_T + hh) * p.resid_F + ww),
                               __ldg(p.resid_in_shift + ww));
       }
@@ -625,7 +644,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           tmem_ld_x32(taddr + c0, v);
           tmem_ld_wait();
           if (p.debug_flags & 1) continue;
-          if (p.resid_src != nullptr) {
+          if (FEAT(kFResid, p.resid_src != nullptr)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 rw = *reinterpret_cast<const float4*>(tb.resid_w + c0 + j);
@@ -635,7 +654,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
               v[j + 3] = fmaf(rw.w, resid_x, v[j + 3]);
             }
           }
-          if (p.bias != nullptr || p.resid_src != nullptr) {
+          if (FEAT(kFBias, p.bias != nullptr) || FEAT(kFResid, p.resid_src != nullptr)) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               const float4 bb = *reinterpret_cast<const float4*>(tb.bias + c0 + j);
@@ -646,7 +665,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
             }
           }
           int c = n, ho = h, wo = w;
-          if (p.up_h * p.up_w > 1) {
+          if (FEAT(kFUp, p.up_h * p.up_w > 1)) {
             const int g = n / p.group_c;
             c = n - g * p.group_c;
             const int dy = g / p.up_w;
@@ -655,39 +674,17 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           }
           const int hw0 = it.h0 + mt * 16 + q * 4;            // first image row of this warp's 4 x 8 pixel patch
           int grp_dy = 0, grp_dx = 0;
-          if (p.up_h * p.up_w > 1) {
+          if (FEAT(kFUp, p.up_h * p.up_w > 1)) {
             const int g = n / p.group_c;
             grp_dy = g / p.up_w;
             grp_dx = g - grp_dy * p.up_w;
           }
-          if (tma_store) {
-            // staging buffers are reused chunk after chunk: wait until the previous TMA stores have read them
+          if (FEAT(kFTma, tma_store) && FEAT(kFTmaPool, tma_pool)) {
+            // pooled outputs are staged too: the staging buffers must be free before the pooling block below
             if (lane == 0) tma_store_wait_read();
             __syncwarp();
           }
-          if (p.full_raw.ptr != nullptr) {
-            uint32_t wv[16];
-            pack_raw32(v, wv);
-            if (tma_store) stage_row32(stg, lane, wv);
-            else store32(p.full_raw, it.b, ho, wo, Ho, Wo, c, wv, valid);
-          }
-          if (p.full_act.ptr != nullptr) {
-            uint32_t wv[16];
-            pack_act32(tb.sc_full + c0, tb.sh_full + c0, v, wv);
-            if (tma_store) stage_row32(stg + 2048, lane, wv);
-            else store32(p.full_act, it.b, ho, wo, Ho, Wo, c, wv, valid);
-          }
-          if (tma_store && (p.full_raw.ptr != nullptr || p.full_act.ptr != nullptr)) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (elect_one()) {
-              if (p.full_raw.ptr != nullptr) tma_store_5d(&p.tm_out[grp_dy], stg, c, grp_dx, it.w0, hw0, it.b);
-              if (p.full_act.ptr != nullptr) tma_store_5d(&p.tm_out[2 + grp_dy], stg + 2048, c, grp_dx, it.w0, hw0, it.b);
-              if (!(pooling && tma_pool)) tma_store_commit();
-            }
-            __syncwarp();
-          }
-          if (p.after_w != nullptr) {
+          if (FEAT(kFAfter, p.after_w != nullptr)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               fa0 = fmaf(tb.after_w[j], v[j], fa0);
@@ -695,7 +692,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
               fa2 = fmaf(tb.after_w[64 + j], v[j], fa2);
             }
           }
-          if (pooling) {
+          if (FEAT(kFPool, pooling)) {
             // Butterfly transpose-reduce: after exchanging with the horizontal neighbour (lane ^ 1) each lane owns the
             // pair sums of 16 of the 32 channels; after the vertical exchange (lane ^ 8) the 2x2 sums of 8 channels.
             // Every lane then finishes and stores its own 8 (or 16) channels of the pooled pixel.
@@ -708,7 +705,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
               s1[j] = mine + __shfl_xor_sync(0xffffffffu, send, 1);
             }
             const int hp = h / p.pool_h, wp = w >> 1;
-            if (p.pool_h == 2) {
+            if (FEAT(kFPoolH2, p.pool_h == 2)) {
               const bool odd_h = (lane & 8) != 0;
               float s2[8];
 #pragma unroll
@@ -732,14 +729,14 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                 }
                 pact = make_uint4(wv[0], wv[1], wv[2], wv[3]);
               }
-              if (tma_pool) {
-                if (p.pool_raw.ptr != nullptr) *stage_slot(stg + 4096, pp, cb >> 3) = praw;
-                if (p.pool_act.ptr != nullptr) *stage_slot(stg + 5120, pp, cb >> 3) = pact;
+              if (FEAT(kFTmaPool, tma_pool)) {
+                if (FEAT(kFPoolRaw, p.pool_raw.ptr != nullptr)) *stage_slot(stg + 4096, pp, cb >> 3) = praw;
+                if (FEAT(kFPoolAct, p.pool_act.ptr != nullptr)) *stage_slot(stg + 5120, pp, cb >> 3) = pact;
               } else if (valid) {
-                if (p.pool_raw.ptr != nullptr)
+                if (FEAT(kFPoolRaw, p.pool_raw.ptr != nullptr))
                   *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.pool_raw.ptr) +
                                             (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_raw.cstride + p.pool_raw.coff + c + cb) = praw;
-                if (p.pool_act.ptr != nullptr)
+                if (FEAT(kFPoolAct, p.pool_act.ptr != nullptr))
                   *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.pool_act.ptr) +
                                             (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_act.cstride + p.pool_act.coff + c + cb) = pact;
               }
@@ -755,23 +752,23 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                 const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], u1, tb.sh_pool[c0 + cb + j + 1]);
                 wa[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
               }
-              if (tma_pool) {
-                if (p.pool_raw.ptr != nullptr) {
+              if (FEAT(kFTmaPool, tma_pool)) {
+                if (FEAT(kFPoolRaw, p.pool_raw.ptr != nullptr)) {
                   *stage_slot(stg + 4096, pp, cb >> 3) = make_uint4(wr[0], wr[1], wr[2], wr[3]);
                   *stage_slot(stg + 4096, pp, (cb >> 3) + 1) = make_uint4(wr[4], wr[5], wr[6], wr[7]);
                 }
-                if (p.pool_act.ptr != nullptr) {
+                if (FEAT(kFPoolAct, p.pool_act.ptr != nullptr)) {
                   *stage_slot(stg + 5120, pp, cb >> 3) = make_uint4(wa[0], wa[1], wa[2], wa[3]);
                   *stage_slot(stg + 5120, pp, (cb >> 3) + 1) = make_uint4(wa[4], wa[5], wa[6], wa[7]);
                 }
               } else if (valid) {
-                if (p.pool_raw.ptr != nullptr) {
+                if (FEAT(kFPoolRaw, p.pool_raw.ptr != nullptr)) {
                   uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.pool_raw.ptr) +
                                                         (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_raw.cstride + p.pool_raw.coff + c + cb);
                   dst[0] = make_uint4(wr[0], wr[1], wr[2], wr[3]);
                   dst[1] = make_uint4(wr[4], wr[5], wr[6], wr[7]);
                 }
-                if (p.pool_act.ptr != nullptr) {
+                if (FEAT(kFPoolAct, p.pool_act.ptr != nullptr)) {
                   uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.pool_act.ptr) +
                                                         (((size_t)it.b * Hp + hp) * Wp + wp) * p.pool_act.cstride + p.pool_act.coff + c + cb);
                   dst[0] = make_uint4(wa[0], wa[1], wa[2], wa[3]);
@@ -779,19 +776,47 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                 }
               }
             }
-            if (tma_pool) {
+            if (FEAT(kFTmaPool, tma_pool)) {
               fence_proxy_async_smem();
               __syncwarp();
               if (elect_one()) {
-                if (p.pool_raw.ptr != nullptr) tma_store_4d(&p.tm_out[4], stg + 4096, c, it.w0 >> 1, hw0 / p.pool_h, it.b);
-                if (p.pool_act.ptr != nullptr) tma_store_4d(&p.tm_out[5], stg + 5120, c, it.w0 >> 1, hw0 / p.pool_h, it.b);
+                if (FEAT(kFPoolRaw, p.pool_raw.ptr != nullptr)) tma_store_4d(&p.tm_out[4], stg + 4096, c, it.w0 >> 1, hw0 / p.pool_h, it.b);
+                if (FEAT(kFPoolAct, p.pool_act.ptr != nullptr)) tma_store_4d(&p.tm_out[5], stg + 5120, c, it.w0 >> 1, hw0 / p.pool_h, it.b);
                 tma_store_commit();
               }
               __syncwarp();
             }
           }
+          // Full-resolution outputs LAST: their staging buffers are reused chunk after chunk, and the pooling work above
+          // gives the previous chunk's TMA stores time to read them before this wait.
+          if (FEAT(kFTma, tma_store) && !FEAT(kFTmaPool, tma_pool)) {
+            if (lane == 0) tma_store_wait_read();
+            __syncwarp();
+          }
+          if (FEAT(kFRaw, p.full_raw.ptr != nullptr)) {
+            uint32_t wv[16];
+            pack_raw32(v, wv);
+            if (FEAT(kFTma, tma_store)) stage_row32(stg, lane, wv);
+            else store32(p.full_raw, it.b, ho, wo, Ho, Wo, c, wv, valid);
+          }
+          if (FEAT(kFAct, p.full_act.ptr != nullptr)) {
+            uint32_t wv[16];
+            pack_act32(tb.sc_full + c0, tb.sh_full + c0, v, wv);
+            if (FEAT(kFTma, tma_store)) stage_row32(stg + 2048, lane, wv);
+            else store32(p.full_act, it.b, ho, wo, Ho, Wo, c, wv, valid);
+          }
+          if (FEAT(kFTma, tma_store) && (FEAT(kFRaw, p.full_raw.ptr != nullptr) || FEAT(kFAct, p.full_act.ptr != nullptr))) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (elect_one()) {
+              if (FEAT(kFRaw, p.full_raw.ptr != nullptr)) tma_store_5d(&p.tm_out[grp_dy], stg, c, grp_dx, it.w0, hw0, it.b);
+              if (FEAT(kFAct, p.full_act.ptr != nullptr)) tma_store_5d(&p.tm_out[2 + grp_dy], stg + 2048, c, grp_dx, it.w0, hw0, it.b);
+              tma_store_commit();
+            }
+            __syncwarp();
+          }
         }
-        if (p.after_w != nullptr && valid && !(p.debug_flags & 1)) {
+        if (FEAT(kFAfter, p.after_w != nullptr) && valid && !(p.debug_flags & 1)) {
           const size_t plane = (size_t)p.H * p.W;
           float* fp = p.feat + (size_t)it.b * 3 * plane + (size_t)h * p.W + w;
           fp[0] = fa0 + tb.after_b[0];
@@ -802,6 +827,17 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[as]);
+    }
+#undef FEAT
+    };
+    switch (p.epi_mode) {
+      case 2: generic_items(UTag<kFEnc2Resid>{}); break;
+      case 3: generic_items(UTag<kFEnc2Bias>{}); break;
+      case 4: generic_items(UTag<kFEnc2BiasP12>{}); break;
+      case 5: generic_items(UTag<kFUpconv>{}); break;
+      case 6: generic_items(UTag<kFAfterBias>{}); break;
+      default: generic_items(UTag<kFGeneric>{}); break;
+    }
     }
     if (tma_store && lane == 0) tma_store_wait_all();
     if (prof && q == 0 && lane == 0 && grp == 0) {
@@ -1554,11 +1590,32 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     delete cp;
     return set_error(LASS_ERR_ARG, "conv: tile does not fit in shared memory");
   }
-  p.epi_mode = (!p.tma_store && l.full_act.ptr && !l.full_raw.ptr && !l.pool_raw.ptr && !l.pool_act.ptr && !l.after_w &&
-                !l.resid_src && up == 1 && !(g_debug_flags & 256))
-                   ? 1
-                   : 0;
   p.tma_pool = (p.tma_store && ((l.pool_raw.ptr && l.pool_raw.cstride != l.ncols) || (l.pool_act.ptr && l.pool_act.cstride != l.ncols))) ? 1 : 0;
+  {
+    // epilogue specialisation: the exact feature set of this launch, matched against the compile-time sets of the kernel
+    const bool pooling = (l.pool_raw.ptr || l.pool_act.ptr) && !(g_debug_flags & 8);
+    uint32_t f = 0;
+    if (l.full_raw.ptr) f |= kFRaw;
+    if (l.full_act.ptr) f |= kFAct;
+    if (p.tma_store) f |= kFTma;
+    if (p.tma_pool) f |= kFTmaPool;
+    if (pooling) f |= kFPool;
+    if (pooling && l.pool_h == 2) f |= kFPoolH2;
+    if (l.pool_raw.ptr) f |= kFPoolRaw;
+    if (l.pool_act.ptr) f |= kFPoolAct;
+    if (l.after_w) f |= kFAfter;
+    if (l.resid_src) f |= kFResid;
+    if (l.bias) f |= kFBias;
+    if (up > 1) f |= kFUp;
+    if (g_debug_flags & 256) p.epi_mode = 0;
+    else if ((f & ~(uint32_t)kFBias) == kFAct) p.epi_mode = 1;          // lean path: one activated output, direct stores
+    else if (f == kFEnc2Resid) p.epi_mode = 2;
+    else if (f == kFEnc2Bias) p.epi_mode = 3;
+    else if (f == kFEnc2BiasP12) p.epi_mode = 4;
+    else if (f == kFUpconv) p.epi_mode = 5;
+    else if (f == kFAfterBias) p.epi_mode = 6;
+    else p.epi_mode = 0;
+  }
   if (p.tma_store) {
     const int Ho = l.H * l.up_h, Wo = l.W * l.up_w;
     auto full_map = [&](CUtensorMap* tm, const ConvOut& o, int dy) -> int {
