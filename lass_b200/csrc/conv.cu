@@ -50,7 +50,7 @@ enum : uint32_t {
   kFAfterBias = kFAfter | kFBias,                        // decoder_block6 conv2 + after_conv
 };
 constexpr int kThreads = 320;   // conv_dxn_kernel: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
-constexpr int kThreadsK = 352;  // conv_igemm_kernel: warp 0 TMA producer, warps 1-2 MMA issuers, warps 3-6 / 7-10 epilogue groups
+constexpr int kThreadsK = 384;  // conv_igemm_kernel: warps 0-1 TMA producers, 2-3 MMA issuers, 4-7 / 8-11 epilogue groups
 // accumulator stages / TMEM columns of conv_igemm_kernel<BN, MT>
 constexpr int acc_stages(int BN, int MT) { return (4 * MT * BN <= 256) ? 4 : 2; }
 constexpr int tmem_cols(int BN, int MT) {
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
     }
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == 2) {
     tmem_alloc(tmem_slot, kTmemCols);
     tmem_relinquish();
   }
@@ -285,21 +285,23 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
   const uint32_t tmem_base = *tmem_slot;
 
   const bool mma_only = (p.debug_flags & 64) != 0;   // timing experiment: the MMA issuer runs free, nothing else runs
-  if (warp == 0 && !mma_only) {
-    // =========================== TMA producer ===========================
-    // warp-uniform loop; the elected lane issues the TMA loads
-    {
-      // with two MMA issuers the A ring is split in two halves, items alternate between them
-      const bool dual = p.dual_issue != 0;
-      const uint32_t ring_n = dual ? (uint32_t)p.a_stages >> 1 : (uint32_t)p.a_stages;
-      uint32_t a_its[2] = {0, 0};
-      uint32_t b_it = 0, n = 0;
-      bool first_item = true;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
+  if (warp < 2) {
+    // =========================== TMA producers ===========================
+    // Two producer warps, one per MMA issuer: producer w loads this CTA's items w, w + 2, ... into ITS half of the A ring
+    // (and of the weight ring when the weights are streamed), so the two item streams advance independently.  Without
+    // p.dual_issue producer 0 owns the whole rings and producer 1 idles.  Warp-uniform loops; the elected lane issues.
+    const bool dual = p.dual_issue != 0;
+    const uint32_t pw = (uint32_t)warp;
+    if (!mma_only && (dual || pw == 0)) {
+      const uint32_t ring_a = dual ? (uint32_t)p.a_stages >> 1 : (uint32_t)p.a_stages;
+      const uint32_t ring_b = dual ? (uint32_t)p.b_stages >> 1 : (uint32_t)p.b_stages;
+      const uint32_t a0 = dual ? pw * ring_a : 0u, b0 = dual ? pw * ring_b : 0u;
+      const int step = dual ? 2 : 1;
+      uint32_t a_it = 0, b_it = 0;
+      bool first_item = (pw == 0);     // resident weights are loaded once, by producer 0
+      for (int item = (int)blockIdx.x + (dual ? (int)pw : 0) * (int)gridDim.x; item < p.num_items; item += step * (int)gridDim.x) {
         const Item it = decode_item<MT>(p, item, BN);
         uint32_t b_slot_res = 0;
-        const uint32_t ring = dual ? (n & 1u) : 0u;
-        uint32_t a_it = ring ? a_its[1] : a_its[0];
         for (int s = 0; s < p.nseg; ++s) {
           const SegDev& sg = p.seg[s];
           const uint32_t row_bytes = sg.kc * 2;
@@ -307,8 +309,8 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           const uint32_t a_bytes = halo ? (uint32_t)(16 * MT + 2) * kHaloPitch * row_bytes : (uint32_t)(16 * MT) * TW * row_bytes;
           const uint32_t b_bytes = BN * row_bytes;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
-            const uint32_t sa = ring * ring_n + a_it % ring_n;
-            LASS_TIMED_WAIT(&a_empty[sa], ((a_it / ring_n) & 1) ^ 1, kProfProdAEmpty);
+            const uint32_t sa = a0 + a_it % ring_a;
+            LASS_TIMED_WAIT(&a_empty[sa], ((a_it / ring_a) & 1) ^ 1, kProfProdAEmpty);
             if (elect_one()) {
               if (p.debug_flags & 4) {
                 mbar_arrive(&a_full[sa]);
@@ -333,8 +335,8 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
               }
             } else {
               for (int tp = 0; tp < sg.taps; ++tp) {
-                const uint32_t sb = b_it % p.b_stages;
-                LASS_TIMED_WAIT(&b_empty[sb], ((b_it / p.b_stages) & 1) ^ 1, kProfProdBEmpty);
+                const uint32_t sb = b0 + b_it % ring_b;
+                LASS_TIMED_WAIT(&b_empty[sb], ((b_it / ring_b) & 1) ^ 1, kProfProdBEmpty);
                 if (elect_one()) {
                   mbar_arrive_expect_tx(&b_full[sb], b_bytes);
                   tma_load_3d(b_buf + (size_t)sb * p.b_stage_bytes, &sg.tmB, &b_full[sb], ch * sg.kc, it.n0, tp);
@@ -346,26 +348,24 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           }
         }
         first_item = false;
-        if (ring) a_its[1] = a_it;
-        else a_its[0] = a_it;
       }
-      if (prof && lane == 0) {
+      if (prof && lane == 0 && pw == 0) {
         long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
         dst[kProfProdAEmpty] = pc[kProfProdAEmpty];
         dst[kProfProdBEmpty] = pc[kProfProdBEmpty];
         dst[kProfProdTotal] = clock64() - t_start;
       }
     }
-  } else if (warp == 1 || warp == 2) {
+  } else if (warp < 4) {
     // =========================== MMA issuers ===========================
-    // With p.dual_issue there are TWO issuing warps: warp 1 takes this CTA's items 0, 2, 4, ..., warp 2 the items
+    // With p.dual_issue there are TWO issuing warps: warp 2 takes this CTA's items 0, 2, 4, ..., warp 3 the items
     // 1, 3, 5, ...  Measured on B200 (tools/gpu_umma_bench3.py, lass_debug_set_conv_flags 64): the tensor pipe does not
     // run ahead of the issuing thread, so everything a single issuer does between two items (commits, barrier polls, loop
     // bookkeeping, descriptor set-up: 500-700 cycles) shows up as idle tensor pipe -- a third of the time when an item is
     // 36 MMAs of 40 cycles.  With two issuers that work hides behind the other warp's MMAs.  The items of the two warps
     // accumulate into different TMEM stages, so their relative order in the pipe does not matter.  Each issuer owns HALF of
-    // the A ring (the producer alternates halves per item): a shared ring would make a warp poll an mbarrier phase whose
-    // predecessor has not completed yet, which a parity wait cannot express.
+    // the A ring and of the streamed-weight ring, filled by its own producer warp: a shared ring would make a warp poll an
+    // mbarrier phase whose predecessor has not completed yet, which a parity wait cannot express.
     // The whole warp runs the (warp-uniform) loop so that descriptors live in uniform registers; only the elected
     // lane issues tcgen05.mma / tcgen05.commit.  Steady state with resident weights: one wait + one elected region
     // per K-chunk that issues all taps back to back (compile-time tap offsets); streaming weights: per-tap
@@ -375,9 +375,11 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       const uint32_t a_base16 = smem_u32(a_buf) >> 4, a_stage16 = p.a_stage_bytes >> 4;
       const uint32_t b_base16 = smem_u32(b_buf) >> 4, b_stage16 = p.b_stage_bytes >> 4;
       const bool dual = p.dual_issue != 0;
-      const uint32_t mw = (uint32_t)warp - 1u;     // which of the two issuers
-      const uint32_t n_a = dual ? (uint32_t)p.a_stages >> 1 : (uint32_t)p.a_stages, n_b = p.b_stages;
+      const uint32_t mw = (uint32_t)warp - 2u;     // which of the two issuers
+      const uint32_t n_a = dual ? (uint32_t)p.a_stages >> 1 : (uint32_t)p.a_stages;
+      const uint32_t n_b = (dual && p.b_resident == 0) ? (uint32_t)p.b_stages >> 1 : (uint32_t)p.b_stages;
       const uint32_t ring0 = dual ? mw * n_a : 0u;   // first stage of this issuer's part of the A ring
+      const uint32_t bring0 = (dual && p.b_resident == 0) ? mw * n_b : 0u;   // ... and of the streamed-weight ring
       const bool resident = p.b_resident != 0;
       const bool no_mma = (p.debug_flags & 2) != 0;
       // per-segment constants, hoisted out of the item loop
@@ -446,9 +448,9 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
 #pragma unroll
                 for (uint32_t dx = 0; dx < 3; ++dx) {
                   if (dx > 0 && !halo) break;
-                  if (!mma_only) LASS_TIMED_WAIT(&b_full[sb], resident ? 0u : pb, kProfMmaBFull);
+                  if (!mma_only) LASS_TIMED_WAIT(&b_full[bring0 + sb], resident ? 0u : pb, kProfMmaBFull);
                   tc_fence_after_sync();
-                  const uint32_t b_lo = (b_base16 + sb * b_stage16) | kLbo;
+                  const uint32_t b_lo = (b_base16 + (bring0 + sb) * b_stage16) | kLbo;
                   if (!no_mma && elect_one()) {
                     if (kc == 64) issue_tap<MT, BN, 4>(acc_addr, a_lo + dx * 8, mt_step16, b_lo, gs, accumulate);
                     else issue_tap<MT, BN, 2>(acc_addr, a_lo + dx * 4, mt_step16, b_lo, gs, accumulate);
@@ -458,7 +460,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                   if (resident) {
                     ++sb;
                   } else {
-                    if (elect_one()) umma_commit(&b_empty[sb]);
+                    if (elect_one()) umma_commit(&b_empty[bring0 + sb]);
                     __syncwarp();
                     if (++sb == n_b) {
                       sb = 0;
@@ -501,9 +503,9 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
     // =========================== epilogue ===========================
     // Two groups of four warps; group g drains accumulator stage g (items g, g + 2, ... of this CTA), so two
     // items are in the epilogue at once and every SM sub-partition has two epilogue warps to overlap latencies.
-    const int grp = (warp - 3) >> 2;
+    const int grp = (warp - 4) >> 2;
     const int q = warp & 3;                          // TMEM lane quarter this warp may access
-    const int et = (threadIdx.x - 96) & 127;         // thread index within the group
+    const int et = threadIdx.x & 127;                // thread index within the group
     const int hl = q * 4 + (lane >> 3);
     const int wl = lane & 7;
     const int Ho = p.H * p.up_h, Wo = p.W * p.up_w;
@@ -514,7 +516,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
     EpiTables<BN>* gtabs = tabs + 2 * grp;
     const bool tma_store = p.tma_store != 0;
     const bool tma_pool = p.tma_pool != 0;
-    unsigned char* stg = stage_base + (size_t)(warp - 3) * kStageWarpBytes;
+    unsigned char* stg = stage_base + (size_t)(warp - 4) * kStageWarpBytes;
     uint32_t n = (uint32_t)grp;                      // index of the item within this CTA's sequence
     int tab_b = -1, tab_n0 = -1;
     uint32_t tab_sel = 0;
@@ -848,7 +850,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 2) {
     __syncwarp();
     tc_fence_after_sync();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -1576,7 +1578,6 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
       size_t rest = kBudget - fixed - (size_t)p.b_stages * p.b_stage_bytes;
       p.a_stages = (int)(rest / p.a_stage_bytes);
       if (p.a_stages > 4) p.a_stages = 4;
-      p.dual_issue = (p.a_stages == 4 && !(g_debug_flags & 128)) ? 1 : 0;
       break;
     }
     p.b_resident = 0;
@@ -1585,6 +1586,19 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     p.b_stages = (int)(rest / p.b_stage_bytes);
     if (p.b_stages > 12) p.b_stages = 12;
     if (p.b_stages >= 5 || !p.tma_store) break;      // staging would starve the weight ring: fall back to direct stores
+  }
+  // Two MMA issuers + two producers, each pair with half of the rings.  Measured per layer (tools/gpu_conv_timing.py):
+  // a win when every issuer keeps two A stages (resident weights, >= 4 stages), and for streamed weights with N <= 128 and
+  // long items (>= 36 weight tiles: the second issuer hides the per-tap ring handshakes); a loss with one A stage per
+  // issuer and short items, and for N = 256 tiles, where a weight ring of two 32 KiB stages per issuer is too shallow.
+  p.dual_issue = 0;
+  if (!(g_debug_flags & 128)) {
+    if (p.b_resident) p.dual_issue = p.a_stages >= 4 ? 1 : 0;
+    else p.dual_issue = (BN <= 128 && p.b_stages >= 4 && b_tiles_per_item >= 36) ? 1 : 0;
+  }
+  if (p.dual_issue) {
+    p.a_stages &= ~1;
+    if (!p.b_resident) p.b_stages &= ~1;
   }
   if (!p.b_resident && p.b_stages < 2) {
     delete cp;

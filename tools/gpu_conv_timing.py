@@ -1,5 +1,7 @@
-"""Timing experiments on single conv layers (B200): which role of the kernel bounds a layer?
-Usage: python tools/gpu_conv_timing.py [B]"""
+"""Timing experiments on single conv launches configured exactly like the ResUNet30 plan's (B200): which role of the
+kernel bounds a layer?  Usage: python tools/gpu_conv_timing.py [B] [name-substring ...]
+Debug flags (lass_debug_set_conv_flags): 1 epilogue idle, 2 no MMA, 4 no A loads, 16 no stores, 64 MMA issuers only,
+128 single MMA issuer, 256 generic (unspecialised) epilogue."""
 import json
 import os
 import sys
@@ -11,113 +13,130 @@ sys.path.insert(0, ROOT)
 os.environ.setdefault("LASS_B200_LIB", os.path.join(ROOT, "lass_b200", "_lib", "liblass_b200_prof.so"))   # `make prof`
 from lass_b200 import _cabi, ops, packing  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-FLAGS = (0, 1, 2, 256)
+B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 16
+FILTER = [a for a in sys.argv[2:]]
+FLAGS = tuple(int(x) for x in os.environ.get("LASS_TIMING_FLAGS", "0,1,2,256").split(","))
 dev = "cuda"
+# kind: c1 = first conv of a block (one activated output), enc2 = encoder conv2 (+1x1 shortcut or rank-1 residual; raw + act
+# skip into the concat buffers, pooled raw + act), dec2 = decoder conv2 (+ shortcut over the raw concat), up = transposed
+# conv into the concat buffers, last = decoder_block6 conv2 + after_conv
 LAYERS = {
-    "dec5.up 64->32x4 @512x256": (512, 256, 64, 32, 0, 2, False, (2, 2)),
-    "dec4.up 128->64x4 @256x128": (256, 128, 128, 64, 0, 2, False, (2, 2)),
-    "enc0.c2 32->32+id @1024x512 4out": (1024, 512, 32, 32, 32, 2, True),
-    # name: (H, W, cin, cout, shortcut_cin, n_outputs(act only=1), pool)
-    "enc0.c1 32->32 @1024x512": (1024, 512, 32, 32, 0, 1, False),
-    "dec5.c1 64->32 @1024x512": (1024, 512, 64, 32, 0, 1, False),
-    "enc1.c2 64->64+sc32 @512x256 4out": (512, 256, 64, 64, 32, 2, True),
-    "dec4.c1 128->64 @512x256": (512, 256, 128, 64, 0, 1, False),
-    "enc2.c2 128->128+sc64 @256x128 4out": (256, 128, 128, 128, 64, 2, True),
-    "dec3.c1 256->128 @256x128": (256, 128, 256, 128, 0, 1, False),
-    "dec2.c1 512->256 @128x64": (128, 64, 512, 256, 0, 1, False),
+    "enc0.c1 32->32 @1024x512": dict(kind="c1", H=1024, W=512, cin=32, cout=32),
+    "enc0.c2 32->32+resid @1024x512": dict(kind="enc2", H=1024, W=512, cin=32, cout=32, sc=0),
+    "enc1.c1 32->64 @512x256": dict(kind="c1", H=512, W=256, cin=32, cout=64),
+    "enc1.c2 64->64+sc32 @512x256": dict(kind="enc2", H=512, W=256, cin=64, cout=64, sc=32),
+    "enc2.c1 64->128 @256x128": dict(kind="c1", H=256, W=128, cin=64, cout=128),
+    "enc2.c2 128->128+sc64 @256x128": dict(kind="enc2", H=256, W=128, cin=128, cout=128, sc=64),
+    "dec2.c1 512->256 @128x64": dict(kind="c1", H=128, W=64, cin=512, cout=256),
+    "dec3.up 256->128x4 @64x32": dict(kind="up", H=64, W=32, cin=256, cout=128),
+    "dec3.c1 256->128 @256x128": dict(kind="c1", H=256, W=128, cin=256, cout=128),
+    "dec3.c2 128->128+sc256 @256x128": dict(kind="dec2", H=256, W=128, cin=128, cout=128, sc=256),
+    "dec4.up 128->64x4 @256x128": dict(kind="up", H=256, W=128, cin=128, cout=64),
+    "dec4.c1 128->64 @512x256": dict(kind="c1", H=512, W=256, cin=128, cout=64),
+    "dec4.c2 64->64+sc128 @512x256": dict(kind="dec2", H=512, W=256, cin=64, cout=64, sc=128),
+    "dec5.up 64->32x4 @512x256": dict(kind="up", H=512, W=256, cin=64, cout=32),
+    "dec5.c1 64->32 @1024x512": dict(kind="c1", H=1024, W=512, cin=64, cout=32),
+    "dec5.c2 32->32+sc64+after @1024x512": dict(kind="last", H=1024, W=512, cin=32, cout=32, sc=64),
 }
+NAMES = ["prod_wait_a_empty", "prod_wait_b_empty", "prod_total", "mma_wait_acc_empty", "mma_wait_a_full",
+         "mma_wait_b_full", "mma_total", "epi_wait_acc_full", "epi_total"]
 
 
-def bench_layer(H, W, cin, cout, sc, nout, pool, up=(1, 1), algo=0):
+def build_layer(kind, H, W, cin, cout, sc=0):
+    """-> (ncols, segments, kwargs, flops, keep-alive list)"""
+    keep = []
     src = torch.randn(B, H, W, cin, device=dev).to(torch.bfloat16)
-    nup = up[0] * up[1]
-    if nup == 1:
-        w = (packing.pack_conv_weight_dxn if algo == 1 else packing.pack_conv_weight)(
-            torch.randn(cout, cin, 3, 3, device=dev) / (3 * cin ** 0.5), torch.bfloat16)
-        segs = [ops.make_segment(src, 0, cin, w, 9)]
-    else:
-        w = packing.pack_convT_weight(torch.randn(cin, cout, up[0], up[1], device=dev) / cin ** 0.5, torch.bfloat16)
-        segs = [ops.make_segment(src, 0, cin, w, 1)]
-    keep = [src, w]
-    if sc:
-        raw = torch.randn(B, H, W, sc, device=dev).to(torch.float16)
-        wsc = packing.pack_conv_weight(torch.randn(cout, sc, 1, 1, device=dev) / sc ** 0.5, torch.float16)
-        segs.append(ops.make_segment(raw, 0, sc, wsc, 1))
-        keep += [raw, wsc]
     scale = torch.rand(cout, device=dev) + 0.5
     shift = torch.randn(B, cout, device=dev) * 0.1
-    cbuf = cout * (2 if nup > 1 else 1)
-    act = torch.empty(B, H * up[0], W * up[1], cbuf, dtype=torch.bfloat16, device=dev)
-    kw = dict(full_act=ops.make_out(act, 0, scale, shift), up=up, algo=algo)
-    if nout > 1:
-        rawo = torch.empty(B, H * up[0], W * up[1], cbuf, dtype=torch.float16, device=dev)
-        kw["full_raw"] = ops.make_out(rawo, 0)
-        keep.append(rawo)
-    if pool:
+    keep += [src, scale, shift]
+    kw = {}
+    if kind == "up":
+        w = packing.pack_convT_weight(torch.randn(cin, cout, 2, 2, device=dev) / cin ** 0.5, torch.bfloat16)
+        segs = [ops.make_segment(src, 0, cin, w, 1)]
+        raw = torch.empty(B, 2 * H, 2 * W, 2 * cout, dtype=torch.float16, device=dev)
+        act = torch.empty(B, 2 * H, 2 * W, 2 * cout, dtype=torch.bfloat16, device=dev)
+        kw.update(up=(2, 2), full_raw=ops.make_out(raw, 0), full_act=ops.make_out(act, 0, scale, shift))
+        keep += [w, raw, act]
+        return 4 * cout, segs, kw, 2.0 * B * H * W * 4 * cout * cin, keep
+    w = packing.pack_conv_weight(torch.randn(cout, cin, 3, 3, device=dev) / (3 * cin ** 0.5), torch.bfloat16)
+    segs = [ops.make_segment(src, 0, cin, w, 9)]
+    keep.append(w)
+    if sc:
+        rawin = torch.randn(B, H, W, sc, device=dev).to(torch.float16)
+        wsc = packing.pack_conv_weight(torch.randn(cout, sc, 1, 1, device=dev) / sc ** 0.5, torch.float16)
+        segs.append(ops.make_segment(rawin, 0, sc, wsc, 1))
+        kw["bias"] = torch.randn(cout, device=dev) * 0.1
+        keep += [rawin, wsc, kw["bias"]]
+    flops = 2.0 * B * H * W * cout * (9 * cin + sc)
+    if kind in ("c1", "dec2"):
+        act = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device=dev)
+        kw["full_act"] = ops.make_out(act, 0, scale, shift)
+        keep.append(act)
+    elif kind == "enc2":
+        raw = torch.empty(B, H, W, 2 * cout, dtype=torch.float16, device=dev)
+        act = torch.empty(B, H, W, 2 * cout, dtype=torch.bfloat16, device=dev)
         pr = torch.empty(B, H // 2, W // 2, cout, dtype=torch.float16, device=dev)
         pa = torch.empty(B, H // 2, W // 2, cout, dtype=torch.bfloat16, device=dev)
-        kw.update(pool=(2, 2), pool_raw=ops.make_out(pr, 0), pool_act=ops.make_out(pa, 0, scale, shift))
-        keep += [pr, pa]
-    res = {}
-    # role profile (cycles per item, averaged over CTAs)
-    prof = torch.zeros(296 * 16, dtype=torch.int64, device=dev)
+        kw.update(full_raw=ops.make_out(raw, cout), full_act=ops.make_out(act, cout, scale, shift), pool=(2, 2),
+                  pool_raw=ops.make_out(pr, 0), pool_act=ops.make_out(pa, 0, scale, shift))
+        keep += [raw, act, pr, pa]
+        if not sc:   # encoder_block1: rank-1 identity residual regenerated from the magnitude
+            T, F = H - 23, W + 1
+            r = (torch.randn(B, T, F, device=dev), torch.rand(F, device=dev) + 0.5, torch.randn(F, device=dev) * 0.1,
+                 torch.randn(cout, device=dev), torch.randn(cout, device=dev) * 0.1)
+            kw["resid"] = r
+            keep += list(r)
+    elif kind == "last":
+        aw, ab = torch.randn(3, cout, device=dev) * 0.2, torch.randn(3, device=dev) * 0.1
+        feat = torch.empty(B, 3, H, W, device=dev)
+        kw.update(after_w=aw, after_b=ab, feat=feat)
+        keep += [aw, ab, feat]
+    return cout, segs, kw, flops, keep
+
+
+def bench_layer(cfg):
+    ncols, segs, kw, flops, keep = build_layer(**cfg)
+    H, W = cfg["H"], cfg["W"]
     lib = _cabi.load()
-    if not os.environ.get("LASS_NO_PROFILE_RUN"):
-        _cabi.check(lib.lass_debug_set_conv_profile(prof.data_ptr()))
-        ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
-        torch.cuda.synchronize()
-        lib.lass_debug_set_conv_profile(None)
-    pr = prof.view(296, 16).cpu().double()
-    pr = pr[pr[:, 9] > 0]
-    if pr.shape[0] == 0:
-        pr = torch.ones(1, 16, dtype=torch.float64)
-    items = pr[:, 9].mean().item()
-    names = ["prod_wait_a_empty", "prod_wait_b_empty", "prod_total", "mma_wait_acc_empty", "mma_wait_a_full",
-             "mma_wait_b_full", "mma_total", "epi_wait_acc_full", "epi_total"]
-    res["profile_cyc_per_item"] = {n: round(pr[:, i].mean().item() / items) for i, n in enumerate(names)}
-    res["items_per_cta"] = items
-    res["ctas"] = int(pr.shape[0])
+    res = {}
+    prof = torch.zeros(296 * 16, dtype=torch.int64, device=dev)
+    profiling = not os.environ.get("LASS_NO_PROFILE_RUN")
     for flags in FLAGS:
-        _cabi.load().lass_debug_set_conv_flags(flags)
+        lib.lass_debug_set_conv_flags(flags)
         for _ in range(2):
-            ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
+            ops.conv_igemm(B, H, W, ncols, segs, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(3):
-            ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
+            ops.conv_igemm(B, H, W, ncols, segs, **kw)
         e1.record()
         torch.cuda.synchronize()
         res["flags%d" % flags] = round(e0.elapsed_time(e1) / 3, 4)
-        if flags in (1, 64) and not os.environ.get("LASS_NO_PROFILE_RUN"):
+        if profiling and flags in (0, 1, 64):
             prof.zero_()
-            lib.lass_debug_set_conv_profile(prof.data_ptr())
-            ops.conv_igemm(B, H, W, cout * nup, segs, **kw)
+            _cabi.check(lib.lass_debug_set_conv_profile(prof.data_ptr()))
+            ops.conv_igemm(B, H, W, ncols, segs, **kw)
             torch.cuda.synchronize()
             lib.lass_debug_set_conv_profile(None)
             pr = prof.view(296, 16).cpu().double()
             pr = pr[pr[:, 9] > 0]
             if pr.shape[0]:
                 it = pr[:, 9].mean().item()
-                res["profile_flags%d" % flags] = {n: round(pr[:, i].mean().item() / it) for i, n in enumerate(names)}
-    _cabi.load().lass_debug_set_conv_flags(0)
-    flops = 2.0 * B * H * W * cout * nup * ((9 if nup == 1 else 1) * cin + sc)
-    res["tflops_normal"] = round(flops / (res["flags0"] * 1e-3) / 1e12, 1)
+                res["profile_flags%d" % flags] = {n: round(pr[:, i].mean().item() / it) for i, n in enumerate(NAMES)}
+                res["items_per_cta"] = it
+    lib.lass_debug_set_conv_flags(0)
+    res["tflops"] = round(flops / (res["flags0"] * 1e-3) / 1e12, 1)
     return res
 
 
-out = {}
-if len(sys.argv) > 2 and sys.argv[2] == "dxn":
-    DXN = {k: v for k, v in LAYERS.items() if "up " not in k and v[3] <= 64}
-    DXN["dec4.c2 64->64+sc128 @512x256"] = (512, 256, 64, 64, 128, 1, False)
-    DXN["dec5.c2 32->32+sc64 @1024x512"] = (1024, 512, 32, 32, 64, 1, False)
-    DXN["enc1.c1 32->64 @512x256"] = (512, 256, 32, 64, 0, 1, False)
-    LAYERS = {}
-    for k, v in DXN.items():
-        LAYERS[k + " [K]"] = v
-        LAYERS[k + " [dxN]"] = tuple(v) + ((1, 1), 1)
-for name, cfg in LAYERS.items():
-    out[name] = bench_layer(*cfg)
-    print(name, json.dumps(out[name]), flush=True)
-os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-json.dump(out, open(os.path.join(ROOT, "gpurun_out", "conv_timing_b%d.json" % B), "w"), indent=1)
+if __name__ == "__main__":
+    out = {}
+    for name, cfg in LAYERS.items():
+        if FILTER and not any(f in name for f in FILTER):
+            continue
+        out[name] = bench_layer(cfg)
+        r = out[name]
+        print("%-38s" % name, " ".join("%s=%.3f" % (k[5:], v) for k, v in r.items() if k.startswith("flags")), "TF=%.0f" % r["tflops"],
+              flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(out, open(os.path.join(ROOT, "gpurun_out", "conv_timing_b%d.json" % B), "w"), indent=1)
