@@ -40,7 +40,7 @@ struct UTag {
 // epilogue features of conv_igemm_kernel (compile-time sets for the launch shapes of the ResUNet30 plan)
 enum : uint32_t {
   kFRaw = 1u, kFAct = 2u, kFTma = 4u, kFTmaPool = 8u, kFPool = 16u, kFPoolH2 = 32u, kFPoolRaw = 64u, kFPoolAct = 128u,
-  kFAfter = 256u, kFResid = 512u, kFBias = 1024u, kFUp = 2048u, kFGeneric = 0x80000000u,
+  kFAfter = 256u, kFResid = 512u, kFBias = 1024u, kFUp = 2048u, kFCoal = 4096u, kFGeneric = 0x80000000u,
   // encoder conv2: raw + activated skip into the concat buffers (TMA stores) + pooled raw / activated block output
   kFEnc2Common = kFRaw | kFAct | kFTma | kFPool | kFPoolRaw | kFPoolAct,
   kFEnc2Resid = kFEnc2Common | kFPoolH2 | kFResid,       // encoder_block1 (rank-1 identity residual)
@@ -791,9 +791,10 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           }
           // Full-resolution outputs LAST: their staging buffers are reused chunk after chunk, and the pooling work above
           // gives the previous chunk's TMA stores time to read them before this wait.
+          const bool coal = FEAT(kFCoal, p.tma_store == 2);   // staged, but written with coalesced st.global instead of TMA
           if (FEAT(kFTma, tma_store) && !FEAT(kFTmaPool, tma_pool)) {
-            if (lane == 0) tma_store_wait_read();
-            __syncwarp();
+            if (!coal && lane == 0) tma_store_wait_read();
+            __syncwarp();                                     // (coal: the previous chunk's staging reads are done)
           }
           if (FEAT(kFRaw, p.full_raw.ptr != nullptr)) {
             uint32_t wv[16];
@@ -807,7 +808,27 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
             if (FEAT(kFTma, tma_store)) stage_row32(stg + 2048, lane, wv);
             else store32(p.full_act, it.b, ho, wo, Ho, Wo, c, wv, valid);
           }
-          if (FEAT(kFTma, tma_store) && (FEAT(kFRaw, p.full_raw.ptr != nullptr) || FEAT(kFAct, p.full_act.ptr != nullptr))) {
+          if (FEAT(kFTma, tma_store) && coal) {
+            // The warp's 4 x 8 pixel patch sits in shared memory, one 64 B row per pixel.  Four lanes now write the four
+            // 16 B pieces of ONE pixel, so every st.global covers whole 32 B sectors (8 pixels x 64 B per instruction) --
+            // the SM's TMA engine moves only about one 64 B box row per 4-5 cycles, which bounded these launches.
+            __syncwarp();
+            const int pc = lane & 3, col = lane >> 2;
+            const int wpx = it.w0 + col;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int hpx = hw0 + i;
+              if (hpx < p.H && wpx < p.W && !no_store) {
+                const size_t pix = ((size_t)it.b * Ho + (size_t)(hpx * p.up_h + grp_dy)) * Wo + (size_t)(wpx * p.up_w + grp_dx);
+                if (FEAT(kFRaw, p.full_raw.ptr != nullptr))
+                  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.full_raw.ptr) + pix * p.full_raw.cstride + p.full_raw.coff + c + pc * 8) =
+                      *stage_slot(stg, i * 8 + col, pc);
+                if (FEAT(kFAct, p.full_act.ptr != nullptr))
+                  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.full_act.ptr) + pix * p.full_act.cstride + p.full_act.coff + c + pc * 8) =
+                      *stage_slot(stg + 2048, i * 8 + col, pc);
+              }
+            }
+          } else if (FEAT(kFTma, tma_store) && (FEAT(kFRaw, p.full_raw.ptr != nullptr) || FEAT(kFAct, p.full_act.ptr != nullptr))) {
             fence_proxy_async_smem();
             __syncwarp();
             if (elect_one()) {
@@ -1605,6 +1626,9 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     return set_error(LASS_ERR_ARG, "conv: tile does not fit in shared memory");
   }
   p.tma_pool = (p.tma_store && ((l.pool_raw.ptr && l.pool_raw.cstride != l.ncols) || (l.pool_act.ptr && l.pool_act.cstride != l.ncols))) ? 1 : 0;
+  // debug flag 512: staged outputs leave through coalesced st.global (mode 2) instead of TMA stores.  Measured slower
+  // than the TMA stores on every launch of the plan (enc conv2 +20 %, transposed convs +5..20 %), kept for experiments.
+  if (p.tma_store && !p.tma_pool && (g_debug_flags & 512)) p.tma_store = 2;
   {
     // epilogue specialisation: the exact feature set of this launch, matched against the compile-time sets of the kernel
     const bool pooling = (l.pool_raw.ptr || l.pool_act.ptr) && !(g_debug_flags & 8);
@@ -1612,6 +1636,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     if (l.full_raw.ptr) f |= kFRaw;
     if (l.full_act.ptr) f |= kFAct;
     if (p.tma_store) f |= kFTma;
+    if (p.tma_store == 2) f |= kFCoal;
     if (p.tma_pool) f |= kFTmaPool;
     if (pooling) f |= kFPool;
     if (pooling && l.pool_h == 2) f |= kFPoolH2;
@@ -1630,7 +1655,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     else if (f == kFAfterBias) p.epi_mode = 6;
     else p.epi_mode = 0;
   }
-  if (p.tma_store) {
+  if (p.tma_store == 1) {
     const int Ho = l.H * l.up_h, Wo = l.W * l.up_w;
     auto full_map = [&](CUtensorMap* tm, const ConvOut& o, int dy) -> int {
       const char* base = reinterpret_cast<const char*>(o.ptr) + (size_t)o.coff * 2 + (size_t)dy * Wo * o.cstride * 2;
