@@ -13,6 +13,8 @@
 // -> each thread accumulates its own output positions (no atomics).
 //
 // Algorithmic HBM bytes per clip: 6 planes * 4 B * T * F (feat x3, mag, cos, sin) + 4 B * L.
+#include <stdlib.h>
+
 #include "fft.cuh"
 #include "lass_internal.cuh"
 
@@ -176,6 +178,326 @@ __global__ void __launch_bounds__(kThreads) mask_istft_kernel(const MaskIstftArg
   }
 }
 
+// =====================================================================================================================
+// v2 (n_fft = 1024 / 2048): the warp's frame lives in REGISTERS.  M = n_fft/2 = 32 * E complex points, lane b holds
+// Z[32 a + b], a < E (the coalesced load order of the bins).  Cooley-Tukey with k = 32 a + b, n = n1 + E n2:
+//     T[b][n1]       = sum_a Z[32 a + b] W_E^(a n1)          E-point inverse DFT inside each lane (radix-4 x radix-4 [x 2])
+//     U[b][n1]       = T[b][n1] W_M^(b n1)                    twiddle table tw2[n1][b] in shared memory
+//     z[n1 + E n2]   = sum_b U[b][n1] W_32^(b n2)             32-point inverse DFT across lanes: ONE transposition through
+//                                                             shared memory (row pitch 33: conflict-free), then again in
+//                                                             registers (E = 32: one lane per n1; E = 16: two lanes per n1
+//                                                             take the even / odd b and combine with 32 shuffles)
+// against v1's five shared-memory Stockham passes.  Measured instruction count per frame: ~1.6 k warp instructions
+// (v1: 5.6 k), no shared-memory bank conflicts.  Same CTA decomposition, overlap-add and normalisation as v1.
+// =====================================================================================================================
+__device__ __forceinline__ void r4_inv(float& ar, float& ai, float& br, float& bi, float& cr, float& ci, float& dr, float& di) {
+  // (a, b, c, d) -> (a+b+c+d, a+ib-c-id, a-b+c-d, a-ib-c+id): 4-point inverse DFT, in place
+  const float s0r = ar + cr, s0i = ai + ci, s1r = ar - cr, s1i = ai - ci;
+  const float s2r = br + dr, s2i = bi + di, s3r = br - dr, s3i = bi - di;
+  ar = s0r + s2r; ai = s0i + s2i;
+  cr = s0r - s2r; ci = s0i - s2i;
+  br = s1r - s3i; bi = s1i + s3r;
+  dr = s1r + s3i; di = s1i - s3r;
+}
+
+// y[n] = sum_{a<16} x[a] exp(+2 pi i a n / 16); x at re[OFF + STR * a]; result y[n] written to (yr[n], yi[n])
+template <int OFF, int STR, int NREG>
+__device__ __forceinline__ void fft16_inv(float (&re)[NREG], float (&im)[NREG], float (&yr)[16], float (&yi)[16]) {
+  constexpr float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, c2 = 0.70710678118654752f;
+#pragma unroll
+  for (int a0 = 0; a0 < 4; ++a0)
+    r4_inv(re[OFF + STR * a0], im[OFF + STR * a0], re[OFF + STR * (4 + a0)], im[OFF + STR * (4 + a0)],
+           re[OFF + STR * (8 + a0)], im[OFF + STR * (8 + a0)], re[OFF + STR * (12 + a0)], im[OFF + STR * (12 + a0)]);
+  // now element 4 q + a0 holds P[a0][q]; twiddle W16^(a0 q)
+  auto rot = [&](int idx, float c, float s) {
+    float& xr = re[OFF + STR * idx];
+    float& xi = im[OFF + STR * idx];
+    const float tr = xr * c - xi * s, ti = xr * s + xi * c;
+    xr = tr;
+    xi = ti;
+  };
+  rot(4 * 1 + 1, c1, s1);     // W16^1
+  rot(4 * 2 + 1, c2, c2);     // W16^2
+  rot(4 * 3 + 1, s1, c1);     // W16^3
+  rot(4 * 1 + 2, c2, c2);     // W16^2
+  {                           // W16^4 = i
+    float& xr = re[OFF + STR * (4 * 2 + 2)];
+    float& xi = im[OFF + STR * (4 * 2 + 2)];
+    const float t = xr;
+    xr = -xi;
+    xi = t;
+  }
+  rot(4 * 3 + 2, -c2, c2);    // W16^6
+  rot(4 * 1 + 3, s1, c1);     // W16^3
+  rot(4 * 2 + 3, -c2, c2);    // W16^6
+  rot(4 * 3 + 3, -c1, -s1);   // W16^9
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    r4_inv(re[OFF + STR * (4 * q + 0)], im[OFF + STR * (4 * q + 0)], re[OFF + STR * (4 * q + 1)], im[OFF + STR * (4 * q + 1)],
+           re[OFF + STR * (4 * q + 2)], im[OFF + STR * (4 * q + 2)], re[OFF + STR * (4 * q + 3)], im[OFF + STR * (4 * q + 3)]);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      yr[q + 4 * r] = re[OFF + STR * (4 * q + r)];
+      yi[q + 4 * r] = im[OFF + STR * (4 * q + r)];
+    }
+  }
+}
+
+// E-point inverse DFT of (re, im)[0..E) in place (natural order in, natural order out)
+template <int E>
+__device__ __forceinline__ void fftE_inv(float (&re)[E], float (&im)[E]) {
+  if constexpr (E == 16) {
+    float yr[16], yi[16];
+    fft16_inv<0, 1, 16>(re, im, yr, yi);
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      re[n] = yr[n];
+      im[n] = yi[n];
+    }
+  } else {
+    // radix-2: even / odd inputs -> two 16-point transforms, y[n] = F0[n] + W32^n F1[n], y[n + 16] = F0[n] - W32^n F1[n]
+    float f0r[16], f0i[16], f1r[16], f1i[16];
+    fft16_inv<0, 2, 32>(re, im, f0r, f0i);
+    fft16_inv<1, 2, 32>(re, im, f1r, f1i);
+    constexpr float kc[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
+                              0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.0f, -0.19509032201612825f,
+                              -0.38268343236508977f, -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
+                              -0.92387953251128674f, -0.98078528040323043f};
+    constexpr float ks[16] = {0.0f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f, 0.70710678118654752f,
+                              0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f, 1.0f, 0.98078528040323043f,
+                              0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
+                              0.38268343236508977f, 0.19509032201612825f};
+#pragma unroll
+    for (int n = 0; n < 16; ++n) {
+      const float tr = f1r[n] * kc[n] - f1i[n] * ks[n], ti = f1r[n] * ks[n] + f1i[n] * kc[n];
+      re[n] = f0r[n] + tr;
+      im[n] = f0i[n] + ti;
+      re[n + 16] = f0r[n] - tr;
+      im[n + 16] = f0i[n] - ti;
+    }
+  }
+}
+
+// masked spectrum value of one bin (models/resunet.py:469-495; torchlibrosa magphase clamp 1e-10)
+__device__ __forceinline__ cpx mask_bin(float x0, float x1, float x2, float sp, float cs, float sn) {
+  // tanh(x) = sgn(x) (1 - t) / (1 + t), t = exp(-2 |x|).  The unit phasor (mc, ms) = (mr, mi) / |m| only needs the RATIO
+  // of the two tanh values: (p, q) = (s1 (1 - t1)(1 + t2), s2 (1 - t2)(1 + t1)) is (mr, mi) scaled by (1 + t1)(1 + t2) in [1, 4].
+  const float t1 = exp2f(-2.8853900817779268f * fabsf(x1)), t2 = exp2f(-2.8853900817779268f * fabsf(x2));
+  const float pm = copysignf((1.0f - t1) * (1.0f + t2), x1), qm = copysignf((1.0f - t2) * (1.0f + t1), x2);
+  const float inv = fminf(rsqrtf(pm * pm + qm * qm), 1e10f);      // |m| clamp: exact zeros (padded Nyquist column) give 0
+  const float mc = pm * inv, ms = qm * inv;
+  const float sig = __fdividef(1.0f, 1.0f + exp2f(-1.4426950408889634f * x0));
+  const float om = fmaxf(sp * sig, 0.0f);
+  return cpx{om * (cs * mc - sn * ms), om * (sn * mc + cs * ms)};
+}
+
+template <int E>
+__global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIstftArgs a) {
+  constexpr int M = 32 * E, N = 2 * M;
+  constexpr int kPitch = 33;                      // transposition rows of 32 lanes, padded
+  constexpr int kBuf = kPitch * E;                // complex slots per warp buffer (>= M + 1)
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int hop = a.hop;
+  const int S = a.FR * hop;
+  cpx* tw2 = reinterpret_cast<cpx*>(smem_raw);    // [E][32]: exp(+2 pi i b n1 / M)
+  float* ola = reinterpret_cast<float*>(tw2 + E * 32);
+  cpx* bufs = reinterpret_cast<cpx*>(ola + ((S + 1) & ~1));
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  cpx* buf = bufs + (size_t)warp * kBuf;
+  const int b = blockIdx.y;
+  const long long pos0 = (long long)blockIdx.x * S;
+  const float2* win2 = reinterpret_cast<const float2*>(a.window);
+
+  for (int i = tid; i < E * 32; i += kThreads) {
+    const float2 w = __ldg(reinterpret_cast<const float2*>(a.tw) + ((2 * (i & 31) * (i >> 5)) & (N - 1)));
+    tw2[i] = cpx{w.x, w.y};
+  }
+  for (int i = tid; i < S; i += kThreads) ola[i] = 0.0f;
+  long long t_lo = (pos0 - N) / hop + 1;
+  if (pos0 - N < 0) t_lo = 0;
+  long long t_hi = (pos0 + S - 1) / hop;
+  if (t_hi > a.T - 1) t_hi = a.T - 1;
+  __syncthreads();
+
+  const float* magb = a.mag + (size_t)b * a.T * a.F;
+  const float* cosb = a.cosp + (size_t)b * a.T * a.F;
+  const float* sinb = a.sinp + (size_t)b * a.T * a.F;
+  const float* featb = a.feat + (size_t)b * a.feat_bstride;
+
+  for (long long tb = t_lo; tb <= t_hi; tb += kWarps) {
+    const long long t = tb + warp;
+    if (t <= t_hi) {
+      float zr[E], zi[E];
+      const float* fp = featb + (size_t)t * a.feat_tstride;
+      const size_t o = (size_t)t * a.F;
+      // ---- 1. masked half spectrum X[32 a + lane]; bins >= feat_F behave as x = 0, bins >= F (never for k < M) as mag = 0 ----
+#pragma unroll
+      for (int a0 = 0; a0 < E; a0 += 4) {
+        float x0[4], x1[4], x2[4], sp[4], cs[4], sn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int k = 32 * (a0 + u) + lane;
+          const bool inX = k < a.feat_F;
+          x0[u] = inX ? __ldg(fp + k) : 0.0f;
+          x1[u] = inX ? __ldg(fp + a.feat_cstride + k) : 0.0f;
+          x2[u] = inX ? __ldg(fp + 2 * a.feat_cstride + k) : 0.0f;
+          sp[u] = __ldg(magb + o + k);
+          cs[u] = __ldg(cosb + o + k);
+          sn[u] = __ldg(sinb + o + k);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const cpx X = mask_bin(x0[u], x1[u], x2[u], sp[u], cs[u], sn[u]);
+          zr[a0 + u] = X.x;
+          zi[a0 + u] = X.y;
+          buf[32 * (a0 + u) + lane] = X;
+        }
+      }
+      if (lane == 0) {   // Nyquist bin k = M
+        const bool inX = M < a.feat_F;
+        const cpx X = mask_bin(inX ? __ldg(fp + M) : 0.0f, inX ? __ldg(fp + a.feat_cstride + M) : 0.0f,
+                               inX ? __ldg(fp + 2 * a.feat_cstride + M) : 0.0f, __ldg(magb + o + M), __ldg(cosb + o + M),
+                               __ldg(sinb + o + M));
+        buf[M] = X;
+      }
+      __syncwarp();
+      // ---- 2. Hermitian pack Z[k] = (X[k] + conj X[M-k]) + i tw[k] (X[k] - conj X[M-k]) ----
+#pragma unroll
+      for (int aa = 0; aa < E; ++aa) {
+        const int k = 32 * aa + lane;
+        cpx xa = cpx{zr[aa], zi[aa]};
+        cpx xb = buf[M - k];
+        if (k == 0) {        // Im X[0], Im X[M] do not contribute (see irfft_pack)
+          xa.y = 0.0f;
+          xb.y = 0.0f;
+        }
+        const float2 w = __ldg(reinterpret_cast<const float2*>(a.tw) + k);
+        const float er = xa.x + xb.x, ei = xa.y - xb.y;      // X[k] + conj(X[M-k])
+        const float dr = xa.x - xb.x, di = xa.y + xb.y;      // X[k] - conj(X[M-k])
+        const float orr = w.x * dr - w.y * di, oi = w.x * di + w.y * dr;
+        zr[aa] = er - oi;                                     // e + i o
+        zi[aa] = ei + orr;
+      }
+      // ---- 3. E-point inverse DFT inside the lane, twiddle, transposition ----
+      fftE_inv<E>(zr, zi);
+      __syncwarp();                                           // all reads of X[M-k] done before buf is overwritten
+#pragma unroll
+      for (int n1 = 0; n1 < E; ++n1) {
+        const cpx w = tw2[n1 * 32 + lane];
+        buf[n1 * kPitch + lane] = cpx{zr[n1] * w.x - zi[n1] * w.y, zr[n1] * w.y + zi[n1] * w.x};
+      }
+      __syncwarp();
+      // ---- 4. 32-point inverse DFT across the former lanes, window, result to the warp buffer (interleaved samples) ----
+      if constexpr (E == 32) {
+#pragma unroll
+        for (int bb = 0; bb < 32; ++bb) {
+          const cpx v = buf[lane * kPitch + bb];
+          zr[bb] = v.x;
+          zi[bb] = v.y;
+        }
+        fftE_inv<32>(zr, zi);
+        __syncwarp();
+#pragma unroll
+        for (int n2 = 0; n2 < 32; ++n2) {
+          const int m = lane + 32 * n2;
+          const float2 w = __ldg(win2 + m);
+          buf[m] = cpx{zr[n2] * w.x, zi[n2] * w.y};
+        }
+      } else {
+        const int n1 = lane & 15, h = lane >> 4;
+        float fr[16], fi[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const cpx v = buf[n1 * kPitch + 2 * j + h];
+          zr[j] = v.x;
+          zi[j] = v.y;
+        }
+        fft16_inv<0, 1, 16>(zr, zi, fr, fi);
+        __syncwarp();
+        constexpr float kc[16] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
+                                  0.55557023301960218f, 0.38268343236508977f, 0.19509032201612825f, 0.0f, -0.19509032201612825f,
+                                  -0.38268343236508977f, -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
+                                  -0.92387953251128674f, -0.98078528040323043f};
+        constexpr float ks[16] = {0.0f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f, 0.70710678118654752f,
+                                  0.83146961230254524f, 0.92387953251128674f, 0.98078528040323043f, 1.0f, 0.98078528040323043f,
+                                  0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
+                                  0.38268343236508977f, 0.19509032201612825f};
+#pragma unroll
+        for (int n2 = 0; n2 < 16; ++n2) {
+          // lanes with h = 1 hold F1: pre-multiply by W32^n2; then z = F0 + W F1 (h = 0), F0 - W F1 (h = 1)
+          const float gr = h ? fr[n2] * kc[n2] - fi[n2] * ks[n2] : fr[n2];
+          const float gi = h ? fr[n2] * ks[n2] + fi[n2] * kc[n2] : fi[n2];
+          const float pr = __shfl_xor_sync(0xffffffffu, gr, 16), pi = __shfl_xor_sync(0xffffffffu, gi, 16);
+          const float vr = h ? pr - gr : gr + pr, vi = h ? pi - gi : gi + pi;
+          const int m = n1 + 16 * (n2 + 16 * h);
+          const float2 w = __ldg(win2 + m);
+          buf[m] = cpx{vr * w.x, vi * w.y};
+        }
+      }
+    }
+    __syncthreads();
+    // ---- 5. overlap-add of this round's (already windowed) frames; each thread owns its positions: deterministic ----
+    const int cnt = (int)((t_hi - tb + 1 < kWarps) ? (t_hi - tb + 1) : kWarps);
+    long long w0 = tb * hop - pos0;
+    if (w0 < 0) w0 = 0;
+    long long w1 = (tb + cnt - 1) * hop + N - pos0;
+    if (w1 > S) w1 = S;
+    const float* zbase = reinterpret_cast<const float*>(bufs);
+    constexpr int zstride = 2 * kBuf;
+    for (int pos = (int)w0 + tid; pos < (int)w1; pos += kThreads) {
+      float acc = ola[pos];
+      const int rel = (int)(pos0 + pos - tb * hop);
+      int g_hi = rel / hop;
+      if (g_hi > cnt - 1) g_hi = cnt - 1;
+      int g_lo = (rel - N) / hop + 1;
+      if (rel - N < 0) g_lo = 0;
+      for (int g = g_lo; g <= g_hi; ++g) acc += zbase[(size_t)g * zstride + (rel - g * hop)];
+      ola[pos] = acc;
+    }
+    __syncthreads();
+  }
+
+  // ---- 6. window-sum normalisation (folded hann^2, clamp 1e-11), 1/N, trim n_fft/2 ----
+  const float invN = 1.0f / (float)N;
+  for (int pos = tid; pos < S; pos += kThreads) {
+    const long long np = pos0 + pos;
+    const long long no = np - (N >> 1);
+    if (no < 0 || no >= a.L) continue;
+    long long ta = (np - N) / hop + 1;
+    if (np - N < 0) ta = 0;
+    long long tz = np / hop;
+    if (tz > a.T - 1) tz = a.T - 1;
+    float ws = 0.0f;
+    for (long long t = ta; t <= tz; ++t) {
+      const float w = __ldg(a.window + (np - t * hop));
+      ws += w * w;
+    }
+    a.out[(size_t)b * a.L + no] = (ola[pos] * invN) / fmaxf(ws, 1e-11f);
+  }
+}
+
+template <int E>
+cudaError_t launch_v2(MaskIstftArgs a, int B, int T, cudaStream_t stream) {
+  constexpr int N = 64 * E;
+  const size_t fixed = (size_t)E * 32 * sizeof(cpx) + (size_t)kWarps * 33 * E * sizeof(cpx) + 16;
+  // CTA = FR hops of output, as many as keep two CTAs per SM (halo frames are recomputed: ~n_fft/hop per CTA)
+  a.FR = 64;
+  while (fixed + (size_t)((a.FR * a.hop + 1) & ~1) * 4 > 112 * 1024 && a.FR > 8) a.FR -= 8;
+  const size_t smem = fixed + (size_t)((a.FR * a.hop + 1) & ~1) * 4;
+  if (smem > 227 * 1024) return cudaErrorInvalidValue;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(mask_istft_v2_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = smem;
+  }
+  const long long P = (long long)(T - 1) * a.hop + N;
+  const int S = a.FR * a.hop;
+  dim3 grid((unsigned)((P + S - 1) / S), (unsigned)B);
+  mask_istft_v2_kernel<E><<<grid, kThreads, smem, stream>>>(a);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 size_t mask_istft_smem_bytes(int N, int hop, int FR) {
@@ -207,6 +529,13 @@ cudaError_t launch_mask_istft(const float* feat, long long feat_bstride, long lo
   int log2N = 0;
   while ((1 << log2N) < N) ++log2N;
   a.log2M = log2N - 1;
+  a.FR = 0;
+  // register-FFT kernel for the two model shapes (hop must keep the window-table reads 8-byte aligned: always true)
+  const char* force_v1 = getenv("LASS_ISTFT_V1");
+  if (!(force_v1 && force_v1[0] == '1')) {
+    if (N == 1024) return launch_v2<16>(a, B, T, stream);
+    if (N == 2048) return launch_v2<32>(a, B, T, stream);
+  }
   // CTA = FR hops of output; as large as fits two CTAs per SM (halo frames are recomputed: ~n_fft/hop per CTA)
   a.FR = 64;
   size_t smem = mask_istft_smem_bytes(N, hop, a.FR);
