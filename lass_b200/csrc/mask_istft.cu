@@ -296,12 +296,14 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
   constexpr int M = 32 * E, N = 2 * M;
   constexpr int kPitch = 33;                      // transposition rows of 32 lanes, padded
   constexpr int kBuf = kPitch * E;                // complex slots per warp buffer (>= M + 1)
+  constexpr int kLoadBatch = 8;                   // bins per lane whose 6 loads each are in flight together
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int hop = a.hop;
   const int S = a.FR * hop;
   cpx* tw2 = reinterpret_cast<cpx*>(smem_raw);    // [E][32]: exp(+2 pi i b n1 / M)
-  float* ola = reinterpret_cast<float*>(tw2 + E * 32);
-  cpx* bufs = reinterpret_cast<cpx*>(ola + ((S + 1) & ~1));
+  float* ola = reinterpret_cast<float*>(tw2 + E * 32);     // S (a multiple of 8)
+  float* wsum = ola + S;                                   // hop: window-sum of the interior, by position mod hop
+  cpx* bufs = reinterpret_cast<cpx*>(wsum + hop);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   cpx* buf = bufs + (size_t)warp * kBuf;
   const int b = blockIdx.y;
@@ -313,6 +315,15 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
     tw2[i] = cpx{w.x, w.y};
   }
   for (int i = tid; i < S; i += kThreads) ola[i] = 0.0f;
+  for (int r = tid; r < hop; r += kThreads) {
+    float ws = 0.0f;
+    for (int n = r; n < N; n += hop) {
+      const float w = __ldg(a.window + n);
+      ws += w * w;
+    }
+    wsum[r] = ws;
+  }
+  const uint32_t hop_magic = (uint32_t)((0x100000000ull + (uint32_t)hop - 1) / (uint32_t)hop);   // x / hop == umulhi(x, magic) for x * hop < 2^32
   long long t_lo = (pos0 - N) / hop + 1;
   if (pos0 - N < 0) t_lo = 0;
   long long t_hi = (pos0 + S - 1) / hop;
@@ -332,10 +343,10 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
       const size_t o = (size_t)t * a.F;
       // ---- 1. masked half spectrum X[32 a + lane]; bins >= feat_F behave as x = 0, bins >= F (never for k < M) as mag = 0 ----
 #pragma unroll
-      for (int a0 = 0; a0 < E; a0 += 4) {
-        float x0[4], x1[4], x2[4], sp[4], cs[4], sn[4];
+      for (int a0 = 0; a0 < E; a0 += kLoadBatch) {
+        float x0[kLoadBatch], x1[kLoadBatch], x2[kLoadBatch], sp[kLoadBatch], cs[kLoadBatch], sn[kLoadBatch];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kLoadBatch; ++u) {
           const int k = 32 * (a0 + u) + lane;
           const bool inX = k < a.feat_F;
           x0[u] = inX ? __ldg(fp + k) : 0.0f;
@@ -346,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
           sn[u] = __ldg(sinb + o + k);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < kLoadBatch; ++u) {
           const cpx X = mask_bin(x0[u], x1[u], x2[u], sp[u], cs[u], sn[u]);
           zr[a0 + u] = X.x;
           zi[a0 + u] = X.y;
@@ -444,33 +455,47 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
     if (w1 > S) w1 = S;
     const float* zbase = reinterpret_cast<const float*>(bufs);
     constexpr int zstride = 2 * kBuf;
-    for (int pos = (int)w0 + tid; pos < (int)w1; pos += kThreads) {
-      float acc = ola[pos];
-      const int rel = (int)(pos0 + pos - tb * hop);
-      int g_hi = rel / hop;
+    // four consecutive samples per thread and step: hop, N and every frame offset are multiples of 4
+    for (int pos = (int)w0 + 4 * tid; pos < (int)w1; pos += 4 * kThreads) {
+      float4 acc = *reinterpret_cast<const float4*>(ola + pos);
+      const int rel = (int)(pos0 + pos - tb * hop);       // offset from frame tb's start, >= 0
+      int g_hi = (int)__umulhi((uint32_t)rel, hop_magic);
       if (g_hi > cnt - 1) g_hi = cnt - 1;
-      int g_lo = (rel - N) / hop + 1;
-      if (rel - N < 0) g_lo = 0;
-      for (int g = g_lo; g <= g_hi; ++g) acc += zbase[(size_t)g * zstride + (rel - g * hop)];
-      ola[pos] = acc;
+      const int g_lo = rel < N ? 0 : (int)__umulhi((uint32_t)(rel - N), hop_magic) + 1;
+      for (int g = g_lo; g <= g_hi; ++g) {
+        const float4 v = *reinterpret_cast<const float4*>(zbase + (size_t)g * zstride + (rel - g * hop));
+        acc.x += v.x;
+        acc.y += v.y;
+        acc.z += v.z;
+        acc.w += v.w;
+      }
+      *reinterpret_cast<float4*>(ola + pos) = acc;
     }
     __syncthreads();
   }
 
   // ---- 6. window-sum normalisation (folded hann^2, clamp 1e-11), 1/N, trim n_fft/2 ----
   const float invN = 1.0f / (float)N;
+  const long long interior_hi = (long long)a.T * hop;
   for (int pos = tid; pos < S; pos += kThreads) {
     const long long np = pos0 + pos;
     const long long no = np - (N >> 1);
     if (no < 0 || no >= a.L) continue;
-    long long ta = (np - N) / hop + 1;
-    if (np - N < 0) ta = 0;
-    long long tz = np / hop;
-    if (tz > a.T - 1) tz = a.T - 1;
-    float ws = 0.0f;
-    for (long long t = ta; t <= tz; ++t) {
-      const float w = __ldg(a.window + (np - t * hop));
-      ws += w * w;
+    float ws;
+    if (np >= N - hop && np < interior_hi) {
+      // every frame that can cover this sample exists: the sum depends on the position modulo hop only
+      const uint32_t q = __umulhi((uint32_t)pos, hop_magic);
+      ws = wsum[pos - (int)q * hop];                       // pos0 is a multiple of hop
+    } else {
+      long long ta = (np - N) / hop + 1;
+      if (np - N < 0) ta = 0;
+      long long tz = np / hop;
+      if (tz > a.T - 1) tz = a.T - 1;
+      ws = 0.0f;
+      for (long long t = ta; t <= tz; ++t) {
+        const float w = __ldg(a.window + (np - t * hop));
+        ws += w * w;
+      }
     }
     a.out[(size_t)b * a.L + no] = (ola[pos] * invN) / fmaxf(ws, 1e-11f);
   }
@@ -482,8 +507,8 @@ cudaError_t launch_v2(MaskIstftArgs a, int B, int T, cudaStream_t stream) {
   const size_t fixed = (size_t)E * 32 * sizeof(cpx) + (size_t)kWarps * 33 * E * sizeof(cpx) + 16;
   // CTA = FR hops of output, as many as keep two CTAs per SM (halo frames are recomputed: ~n_fft/hop per CTA)
   a.FR = 64;
-  while (fixed + (size_t)((a.FR * a.hop + 1) & ~1) * 4 > 112 * 1024 && a.FR > 8) a.FR -= 8;
-  const size_t smem = fixed + (size_t)((a.FR * a.hop + 1) & ~1) * 4;
+  while (fixed + (size_t)(a.FR * a.hop + a.hop) * 4 > 112 * 1024 && a.FR > 8) a.FR -= 8;
+  const size_t smem = fixed + (size_t)(a.FR * a.hop + a.hop) * 4;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   static size_t configured = 0;
   if (smem > configured) {
