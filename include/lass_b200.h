@@ -51,16 +51,17 @@ LASS_API const char* lass_last_error(void);
  *     reference models/base.py:83-88, constructed at models/resunet.py:284-292)
  *
  *   wave      (B, L) fp32
- *   basis_hi / basis_lo   bf16 (ntiles*128, n_fft): windowed DFT basis split hi/lo, 64-bin tiles with rows
- *             [0,64) = real basis and [64,128) = imaginary basis (see lass_stft_basis_rows; packed from the
- *             reference's frozen `stft.conv_real/conv_imag.weight` by lass_b200.packing.pack_stft_basis)
+ *   basis_hi / basis_lo   bf16 (ntiles*256, n_fft): windowed DFT basis split hi/lo, 128-bin tiles with rows
+ *             [0,128) = real basis and [128,256) = imaginary basis; row 128 of tile 0 (Im X[0] == 0) carries the real
+ *             basis of the Nyquist bin n_fft/2 (see lass_stft_basis_rows; packed from the reference's frozen
+ *             `stft.conv_real/conv_imag.weight` by lass_b200.packing.pack_stft_basis)
  *   mag, cos, sin   (B, T, F) fp32 out, T = L/hop + 1, F = n_fft/2 + 1
  *   precision_mode  0 = fp32-parity (3 bf16 MMAs per product, max rel. err ~5e-6), 1 = fast (single bf16 pass)
  *   magphase_mode   0 = Base.spectrogram_phase semantics (mag = clamp(re^2+im^2, 1e-10)**0.5, models/base.py:85-87);
  *                   1 = torchlibrosa.stft.magphase semantics (mag unclamped, cos/sin divided by clamp(mag, 1e-10)) as used by
  *                       the multi-resolution front end (reference scripts/precompute_stfts.py:19-58)
  *   workspace       >= lass_stft_workspace_bytes(B, L, n_fft, hop) bytes, 256-byte aligned
- * Requirements: n_fft % 64 == 0, hop % 8 == 0, L > n_fft/2 (reflect padding).
+ * Requirements: n_fft % 256 == 0, hop % 8 == 0, L > n_fft/2 (reflect padding).
  * ---------------------------------------------------------------------------------------------------- */
 LASS_API int lass_stft_basis_rows(int n_fft);
 LASS_API size_t lass_stft_workspace_bytes(int B, int L, int n_fft, int hop);

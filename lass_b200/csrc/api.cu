@@ -85,7 +85,7 @@ int lass_version(void) { return LASS_B200_VERSION; }
 
 const char* lass_last_error(void) { return g_err; }
 
-int lass_stft_basis_rows(int n_fft) { return stft_num_ntiles(n_fft) * 128; }
+int lass_stft_basis_rows(int n_fft) { return stft_num_ntiles(n_fft) * 256; }
 
 size_t lass_stft_workspace_bytes(int B, int L, int n_fft, int hop) {
   if (B <= 0 || L <= 0 || n_fft <= 0 || hop <= 0) return 0;

@@ -10,13 +10,17 @@
 //       two bf16 arrays (hi, lo = x - hi); a 3-D TMA tensor map with OVERLAPPING rows
 //       (dim0 = k stride 1, dim1 = t stride hop, dim2 = clip) fetches 128-frame x 64-sample K-major tiles.
 //   B = windowed DFT basis (the reference's frozen conv_real / conv_imag weights), split hi/lo bf16,
-//       row-interleaved per 64-bin tile: rows [0,64) = real basis, rows [64,128) = imag basis of the same
-//       bins, so one thread of the epilogue holds re and im of a bin.
+//       row-interleaved per 128-bin tile: rows [0,128) = real basis, rows [128,256) = imag basis of the same
+//       bins, so one thread of the epilogue holds re and im of a bin.  Im X[0] is identically zero; its row
+//       carries the real basis of the Nyquist bin n_fft/2 instead (whose imaginary part is zero as well), so
+//       n_fft/2 + 1 bins fit n_fft/256 tiles exactly.
 //   fp32-parity mode (split = 1): hi*hi + hi*lo + lo*hi, three bf16 MMAs into one fp32 TMEM accumulator
 //       (max rel. error ~5e-6); fast mode (split = 0): hi*hi only.
 //
-// CTA = one 128-frame x 64-bin output tile: warp 0 TMA producer, warp 1 TMEM alloc + MMA issue,
-// warps 2..5 epilogue (TMEM -> registers -> smem transpose -> coalesced fp32 stores).
+// Persistent CTAs, item = 128-frame x 128-bin output tile (M = 128, N = 256, K = n_fft): warp 0 TMA producer,
+// warp 1 TMEM alloc + MMA issue, warps 2..9 epilogue (TMEM -> registers -> smem transpose -> coalesced fp32 stores),
+// two TMEM accumulator stages.  Operand traffic per MMA cycle is 1.4x lower than with 128 x 128 tiles (the kernel is
+// bound by the L2 -> shared-memory rate of the TMA loads, not by the tensor pipe).
 #include "lass_internal.cuh"
 #include "ptx.cuh"
 
@@ -25,13 +29,17 @@ namespace lass {
 namespace {
 
 constexpr int BM = 128;   // frames per tile
-constexpr int BN = 128;   // 64 bins x (re, im)
+constexpr int BN = 256;   // 128 bins x (re, im)
 constexpr int BK = 64;    // samples per pipeline stage (128 B rows, SWIZZLE_128B)
-constexpr int kStages = 3;
-constexpr int kTileBytes = BM * BK * 2;  // 16 KiB (A and B tiles have the same size)
-constexpr int kStageBytes = 4 * kTileBytes;
-constexpr int kThreads = 192;
-constexpr int kStagePad = 65;  // epilogue transpose row pitch (floats)
+constexpr int kBinsPerTile = BN / 2;
+constexpr int kStages = 2;
+constexpr int kATile = BM * BK * 2;       // 16 KiB
+constexpr int kBTile = BN * BK * 2;       // 32 KiB
+constexpr int kStageBytes = 2 * kATile + 2 * kBTile;   // A hi | A lo | B hi | B lo = 96 KiB
+constexpr int kEpiWarps = 8;              // two per TMEM lane quarter, each takes half of the tile's bins
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr int kTrPitch = 33;              // epilogue transpose row pitch (floats)
+constexpr int kTrFloats = 32 * kTrPitch;  // per epilogue warp
 
 struct StftParams {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
@@ -40,22 +48,38 @@ struct StftParams {
   float* sinp;
   int T, F, n_fft, split;
   int magphase_mode;  // 0: Base.spectrogram_phase (clamp(re^2+im^2, 1e-10)**0.5, re/mag); 1: torchlibrosa.magphase
+  int n_tiles, m_tiles, num_items;
 };
 
+// magnitude and unit phasor of one bin.  One MUFU.RSQ (2 ulp) instead of sqrt + two divisions: errors of a few 1e-7
+// relative, against the 1e-4 parity bar (tests/test_gpu_spectral.py).
+__device__ __forceinline__ void magphase(float re, float im, int mode, float& m, float& c, float& sn) {
+  const float p2 = re * re + im * im;
+  // mode 0, models/base.py:85-87: mag = clamp(re^2 + im^2, 1e-10) ** 0.5 ; cos = re / mag ; sin = im / mag
+  // mode 1, torchlibrosa.stft.magphase: mag = (re^2 + im^2) ** 0.5 ; cos = re / clamp(mag, 1e-10) ; sin likewise
+  const float q = fmaxf(p2, mode == 0 ? 1e-10f : 1e-20f);
+  const float r = rsqrtf(q);
+  m = (mode == 0 ? q : p2) * r;
+  c = re * r;
+  sn = im * r;
+}
+
+// Persistent CTAs over (clip, 128-frame tile, 128-bin tile) items, bin tile fastest so that the CTAs running
+// concurrently share the frame tile in L2.  Warp 0 TMA producer, warp 1 TMEM alloc + MMA issue (two 256-column
+// accumulator stages: the epilogue of item i overlaps the MMAs of item i + 1), warps 2..9 epilogue.
 __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_constant__ StftParams p) {
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B tiles need 1024 B alignment
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  float* tr_base = reinterpret_cast<float*>(smem + kStages * kStageBytes);                 // [kEpiWarps][32][33]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tr_base + kEpiWarps * kTrFloats);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* acc_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* acc_full = empty_bar + kStages;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x;
-  const int m0 = blockIdx.y * BM;
-  const int b = blockIdx.z;
   const int KB = p.n_fft / BK;
 
   if (warp == 0 && lane == 0) {
@@ -69,117 +93,139 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(acc_bar, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], kEpiWarps);
+    }
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
-  const uint32_t tmem_acc = *tmem_slot;
+  const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t stage_tx = p.split ? 4 * kTileBytes : 2 * kTileBytes;
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        unsigned char* st = smem + s * kStageBytes;
-        mbar_arrive_expect_tx(&full_bar[s], stage_tx);
-        tma_load_3d(st, &p.tmA_hi, &full_bar[s], kb * BK, m0, b);
-        tma_load_2d(st + 2 * kTileBytes, &p.tmB_hi, &full_bar[s], kb * BK, n_tile * BN);
-        if (p.split) {
-          tma_load_3d(st + kTileBytes, &p.tmA_lo, &full_bar[s], kb * BK, m0, b);
-          tma_load_2d(st + 3 * kTileBytes, &p.tmB_lo, &full_bar[s], kb * BK, n_tile * BN);
+      const uint32_t stage_tx = p.split ? kStageBytes : kATile + kBTile;
+      uint32_t it = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        const int n_tile = item % p.n_tiles;
+        const int rest = item / p.n_tiles;
+        const int m0 = (rest % p.m_tiles) * BM, b = rest / p.m_tiles;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+          unsigned char* st = smem + s * kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+          tma_load_3d(st, &p.tmA_hi, &full_bar[s], kb * BK, m0, b);
+          tma_load_2d(st + 2 * kATile, &p.tmB_hi, &full_bar[s], kb * BK, n_tile * BN);
+          if (p.split) {
+            tma_load_3d(st + kATile, &p.tmA_lo, &full_bar[s], kb * BK, m0, b);
+            tma_load_2d(st + 2 * kATile + kBTile, &p.tmB_lo, &full_bar[s], kb * BK, n_tile * BN);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kFmtBF16, kFmtBF16, BM, BN);
-      for (int kb = 0; kb < KB; ++kb) {
-        const int s = kb % kStages;
-        const uint32_t ph = (kb / kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t it = 0, n = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
+        const uint32_t as = n & 1u;
+        mbar_wait(&acc_empty[as], ((n >> 1) & 1u) ^ 1u);
         tc_fence_after_sync();
-        const uint32_t st = smem_u32(smem + s * kStageBytes);
+        const uint32_t tmem_acc = tmem_base + as * BN;
+        for (int kb = 0; kb < KB; ++kb, ++it) {
+          const int s = it % kStages;
+          mbar_wait(&full_bar[s], (it / kStages) & 1);
+          tc_fence_after_sync();
+          const uint32_t st = smem_u32(smem + s * kStageBytes);
 #pragma unroll
-        for (int ks = 0; ks < BK / 16; ++ks) {
-          const uint64_t a_hi = make_smem_desc(st + ks * 32, 1024, kSwizzle128B);
-          const uint64_t b_hi = make_smem_desc(st + 2 * kTileBytes + ks * 32, 1024, kSwizzle128B);
-          umma_f16(tmem_acc, a_hi, b_hi, idesc, (kb | ks) != 0);
-          if (p.split) {
-            const uint64_t a_lo = make_smem_desc(st + kTileBytes + ks * 32, 1024, kSwizzle128B);
-            const uint64_t b_lo = make_smem_desc(st + 3 * kTileBytes + ks * 32, 1024, kSwizzle128B);
-            umma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
-            umma_f16(tmem_acc, a_lo, b_hi, idesc, 1);
+          for (int ks = 0; ks < BK / 16; ++ks) {
+            const uint64_t a_hi = make_smem_desc(st + ks * 32, 1024, kSwizzle128B);
+            const uint64_t b_hi = make_smem_desc(st + 2 * kATile + ks * 32, 1024, kSwizzle128B);
+            umma_f16(tmem_acc, a_hi, b_hi, idesc, (kb | ks) != 0);
+            if (p.split) {
+              const uint64_t a_lo = make_smem_desc(st + kATile + ks * 32, 1024, kSwizzle128B);
+              const uint64_t b_lo = make_smem_desc(st + 2 * kATile + kBTile + ks * 32, 1024, kSwizzle128B);
+              umma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
+              umma_f16(tmem_acc, a_lo, b_hi, idesc, 1);
+            }
           }
+          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+        umma_commit(&acc_full[as]);    // accumulator complete
       }
-      umma_commit(acc_bar);  // accumulator complete
     }
   } else {
-    // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4) ----
+    // ---- epilogue: warps 2..9; TMEM lane quarter = warp % 4, bin half = (warp - 2) / 4 ----
     const int q = warp & 3;
-    mbar_wait(acc_bar, 0);
-    tc_fence_after_sync();
-    // all MMAs (and therefore all TMA loads) are done: the pipeline stages are free for the transpose
-    float* stage_f = reinterpret_cast<float*>(smem) + (size_t)q * 3 * 32 * kStagePad;
-    float* s_mag = stage_f;
-    float* s_cos = stage_f + 32 * kStagePad;
-    float* s_sin = stage_f + 2 * 32 * kStagePad;
-    const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll
-    for (int c = 0; c < 64; c += 16) {
-      float re[16], im[16];
-      tmem_ld_x16(taddr + c, re);
-      tmem_ld_x16(taddr + 64 + c, im);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const float p2 = re[j] * re[j] + im[j] * im[j];
-        float m, d;
-        if (p.magphase_mode == 0) {
-          // models/base.py:85-87: mag = clamp(re^2 + im^2, 1e-10) ** 0.5 ; cos = re / mag ; sin = im / mag
-          m = sqrtf(fmaxf(p2, 1e-10f));
-          d = m;
-        } else {
-          // torchlibrosa.stft.magphase: mag = (re^2 + im^2) ** 0.5 ; cos = re / clamp(mag, 1e-10) ; sin likewise
-          m = sqrtf(p2);
-          d = fmaxf(m, 1e-10f);
+    const int hsel = (warp - 2) >> 2;
+    float* tr = tr_base + (warp - 2) * kTrFloats;
+    const int half = p.n_fft / 2;
+    uint32_t n = 0;
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
+      const int n_tile = item % p.n_tiles;
+      const int rest = item / p.n_tiles;
+      const int m0 = (rest % p.m_tiles) * BM, b = rest / p.m_tiles;
+      const uint32_t as = n & 1u;
+      mbar_wait(&acc_full[as], (n >> 1) & 1u);
+      tc_fence_after_sync();
+      const uint32_t taddr = tmem_base + as * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const int t_row0 = m0 + q * 32;                       // first frame of this warp's 32 rows
+      const int t_mine = t_row0 + lane;
+      const int rows = min(32, p.T - t_row0);               // valid frames among them (<= 0: none)
+      const size_t row0_off = ((size_t)b * p.T + t_row0) * p.F;
+#pragma unroll 1
+      for (int cc = 0; cc < kBinsPerTile / 2; cc += 32) {
+        const int c = hsel * (kBinsPerTile / 2) + cc;
+        float re[32], im[32], cs[32];
+        tmem_ld_x32(taddr + c, re);
+        tmem_ld_x32(taddr + kBinsPerTile + c, im);
+        tmem_ld_wait();
+        const int f0 = n_tile * kBinsPerTile + c;
+        if (n_tile == 0 && c == 0) {
+          // bin 0 has no imaginary part; its slot in the basis carries the (purely real) Nyquist bin n_fft/2
+          float m, c1, s1;
+          magphase(im[0], 0.0f, p.magphase_mode, m, c1, s1);
+          if (t_mine < p.T) {
+            const size_t o = row0_off + (size_t)lane * p.F + half;
+            p.mag[o] = m;
+            p.cosp[o] = c1;
+            p.sinp[o] = s1;
+          }
+          im[0] = 0.0f;
         }
-        s_mag[lane * kStagePad + c + j] = m;
-        s_cos[lane * kStagePad + c + j] = re[j] / d;
-        s_sin[lane * kStagePad + c + j] = im[j] / d;
-      }
-    }
-    __syncwarp();
-    const int f0 = n_tile * 64;
-    for (int r = 0; r < 32; ++r) {
-      const int t = m0 + q * 32 + r;
-      if (t >= p.T) break;
-      const size_t row = ((size_t)b * p.T + t) * p.F;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int f = f0 + h * 32 + lane;
-        if (f < p.F) {
-          p.mag[row + f] = s_mag[r * kStagePad + h * 32 + lane];
-          p.cosp[row + f] = s_cos[r * kStagePad + h * 32 + lane];
-          p.sinp[row + f] = s_sin[r * kStagePad + h * 32 + lane];
+        for (int j = 0; j < 32; ++j) magphase(re[j], im[j], p.magphase_mode, re[j], cs[j], im[j]);   // re <- mag, im <- sin
+        // three transposes through the warp's 32 x 33 buffer: lane = frame  ->  lane = bin, 128 B rows to global memory
+#pragma unroll
+        for (int which = 0; which < 3; ++which) {
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tr[lane * kTrPitch + j] = which == 0 ? re[j] : (which == 1 ? cs[j] : im[j]);
+          __syncwarp();
+          float* dst = (which == 0 ? p.mag : (which == 1 ? p.cosp : p.sinp)) + row0_off + f0 + lane;
+#pragma unroll 8
+          for (int r = 0; r < 32; ++r) {
+            if (r < rows) dst[(size_t)r * p.F] = tr[r * kTrPitch + lane];
+          }
         }
       }
+      tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
     }
-    tc_fence_before_sync();
   }
+  tc_fence_before_sync();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_acc, BN);
+    tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -203,7 +249,8 @@ __global__ void stft_prep_kernel(const float* __restrict__ wave, __nv_bfloat16* 
 
 }  // namespace
 
-int stft_num_ntiles(int n_fft) { return (n_fft / 2 + 1 + 63) / 64; }
+// 128 bins per tile; the Nyquist bin travels in the (empty) imaginary slot of bin 0, so n_fft/2 bins need tiles
+int stft_num_ntiles(int n_fft) { return (n_fft / 2 + kBinsPerTile - 1) / kBinsPerTile; }
 
 // Row pitch of the padded waveform.  cuTensorMapEncodeTiled wants every stride to be a multiple of 16 B and
 // of the preceding stride, so the clip pitch is rounded up to a multiple of hop (hop % 8 == 0).
@@ -216,7 +263,7 @@ size_t stft_workspace_bytes(int B, int L, int n_fft, int hop) {
 int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
                 float* mag, float* cosp, float* sinp, int precision_mode, int magphase_mode, void* workspace,
                 cudaStream_t stream) {
-  if (n_fft % BK != 0 || hop % 8 != 0 || L <= n_fft / 2) return LASS_ERR_ARG;
+  if (n_fft % BK != 0 || (n_fft / 2) % kBinsPerTile != 0 || hop % 8 != 0 || L <= n_fft / 2) return LASS_ERR_ARG;
   const int T = L / hop + 1;
   const int F = n_fft / 2 + 1;
   const size_t Lp = stft_padded_len(L, n_fft, hop);
@@ -255,14 +302,23 @@ int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void*
   p.n_fft = n_fft;
   p.split = precision_mode == 0 ? 1 : 0;
   p.magphase_mode = magphase_mode ? 1 : 0;
-  const size_t smem = (size_t)kStages * kStageBytes + 1024 + 256;
+  p.n_tiles = ntn;
+  p.m_tiles = (T + BM - 1) / BM;
+  p.num_items = ntn * p.m_tiles * B;
+  const size_t smem = (size_t)kStages * kStageBytes + kEpiWarps * kTrFloats * sizeof(float) + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return set_cuda_error(e, "stft smem attribute");
     configured = true;
   }
-  dim3 grid((unsigned)ntn, (unsigned)((T + BM - 1) / BM), (unsigned)B);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
+  }
+  const int grid = p.num_items < num_sms ? p.num_items : num_sms;
   stft_gemm_kernel<<<grid, kThreads, smem, stream>>>(p);
   return set_cuda_error(cudaGetLastError(), "stft launch");
 }

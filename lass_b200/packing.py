@@ -17,23 +17,24 @@ def split_bf16(x: torch.Tensor):
 
 
 def pack_stft_basis(conv_real_w: torch.Tensor, conv_imag_w: torch.Tensor):
-    """(F, 1, n_fft) x2 -> (hi, lo) bf16 of shape (ntiles*128, n_fft).
+    """(F, 1, n_fft) x2 -> (hi, lo) bf16 of shape (ntiles*256, n_fft), F = n_fft/2 + 1.
 
-    Tile j holds bins [64j, 64j+64): rows [0,64) real basis, rows [64,128) imaginary basis (kernel K1,
-    ``lass_b200/csrc/stft.cu``).  Rows of bins >= F are zero.
+    Tile j holds bins [128j, 128j+128): rows [0,128) real basis, rows [128,256) imaginary basis (kernel K1,
+    ``lass_b200/csrc/stft.cu``).  The imaginary basis of bin 0 is identically zero (sin 0); its row (row 128 of
+    tile 0) carries the REAL basis of the Nyquist bin n_fft/2 instead, whose imaginary basis is zero as well
+    (sin(pi k)), so the n_fft/2 + 1 bins fit n_fft/256 tiles exactly.
     """
     F, _, n_fft = conv_real_w.shape
-    ntiles = (F + 63) // 64
+    half = n_fft // 2
+    assert F == half + 1 and half % 128 == 0, "K1 needs n_fft a multiple of 256 and the full half spectrum"
+    ntiles = half // 128
     re = conv_real_w.reshape(F, n_fft).to(torch.float32)
     im = conv_imag_w.reshape(F, n_fft).to(torch.float32)
-    full = torch.zeros(ntiles, 2, 64, n_fft, dtype=torch.float32, device=re.device)
-    pad_re = torch.zeros(ntiles * 64, n_fft, dtype=torch.float32, device=re.device)
-    pad_im = torch.zeros_like(pad_re)
-    pad_re[:F] = re
-    pad_im[:F] = im
-    full[:, 0] = pad_re.reshape(ntiles, 64, n_fft)
-    full[:, 1] = pad_im.reshape(ntiles, 64, n_fft)
-    hi, lo = split_bf16(full.reshape(ntiles * 128, n_fft))
+    full = torch.zeros(ntiles, 2, 128, n_fft, dtype=torch.float32, device=re.device)
+    full[:, 0] = re[:half].reshape(ntiles, 128, n_fft)
+    full[:, 1] = im[:half].reshape(ntiles, 128, n_fft)
+    full[0, 1, 0] = re[half]
+    hi, lo = split_bf16(full.reshape(ntiles * 256, n_fft))
     return hi.contiguous(), lo.contiguous()
 
 

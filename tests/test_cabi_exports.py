@@ -32,7 +32,7 @@ def test_header_symbols_are_exported_and_bound(repo_root):
 def test_version_and_error_calls_work_without_gpu():
     lib = _cabi.load()
     assert lib.lass_version() == 100
-    assert lib.lass_stft_basis_rows(1024) == 9 * 128
+    assert lib.lass_stft_basis_rows(1024) == 4 * 256
     assert lib.lass_stft_workspace_bytes(2, 160000, 1024, 160) >= 2 * 2 * 161024 * 2
     # argument validation happens before any CUDA call
     rc = lib.lass_stft_fwd(None, 1, 100, 1024, 160, None, None, None, None, None, 0, 0, None, 0, None)
