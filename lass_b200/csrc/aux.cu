@@ -11,45 +11,69 @@ namespace lass {
 
 namespace {
 
-// One warp per table row j: shift[b][j] = bias[j] + sum_k cond[b][k] * W[j][k]
+// shift[b][j] = bias[j] + sum_k cond[b][k] * W[j][k] as a shared-memory tiled fp32 GEMM: CTA = 64 table rows x 64 clips,
+// K in chunks of 64, thread (tx, ty) accumulates the 4 x 4 outputs (j = ty + 16 u, b = tx + 16 v).
+constexpr int kFilmTile = 64;
+constexpr int kFilmPitch = kFilmTile + 1;
 __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ cond, const float* __restrict__ W,
                                                    const float* __restrict__ bias, float* __restrict__ shift,
                                                    int B, int K, int J) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int j = blockIdx.x * 8 + warp;
-  if (j >= J) return;
-  // K <= 1024: up to 32 weights per lane in registers
-  float w[32];
-  const int per = (K + 31) / 32;
+  __shared__ float Ws[kFilmTile * kFilmPitch];
+  __shared__ float Cs[kFilmTile * kFilmPitch];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int j0 = blockIdx.x * kFilmTile, b0 = blockIdx.y * kFilmTile;
+  float acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    const int k = i * 32 + lane;
-    w[i] = (i < per && k < K) ? __ldg(W + (size_t)j * K + k) : 0.0f;
-  }
-  const float bj = __ldg(bias + j);
-  for (int b = 0; b < B; ++b) {
-    float acc = 0.0f;
+  for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      const int k = i * 32 + lane;
-      if (i < per && k < K) acc = fmaf(w[i], __ldg(cond + (size_t)b * K + k), acc);
+    for (int v = 0; v < 4; ++v) acc[u][v] = 0.0f;
+  for (int k0 = 0; k0 < K; k0 += kFilmTile) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int e = tid + 256 * i, r = e >> 6, c = e & 63;
+      const bool kin = k0 + c < K;
+      Ws[r * kFilmPitch + c] = (kin && j0 + r < J) ? __ldg(W + (size_t)(j0 + r) * K + k0 + c) : 0.0f;
+      Cs[r * kFilmPitch + c] = (kin && b0 + r < B) ? __ldg(cond + (size_t)(b0 + r) * K + k0 + c) : 0.0f;
     }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < kFilmTile; ++c) {
+      float wv[4], cv[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) shift[(size_t)b * J + j] = acc + bj;
+      for (int u = 0; u < 4; ++u) {
+        wv[u] = Ws[(ty + 16 * u) * kFilmPitch + c];
+        cv[u] = Cs[(tx + 16 * u) * kFilmPitch + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(wv[u], cv[v], acc[u][v]);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int j = j0 + ty + 16 * u;
+    if (j >= J) continue;
+    const float bj = __ldg(bias + j);
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int b = b0 + tx + 16 * v;
+      if (b < B) shift[(size_t)b * J + j] = acc[u][v] + bj;
+    }
   }
 }
 
 // 4 threads per pixel, 8 channels each (one 16 B store per tensor per thread).  A CTA works on one clip, so every
 // per-channel constant (pre_conv weight / bias, folded BN scale, FiLM shift of that clip) is loaded once per thread and
 // the thread then walks over kPixIter pixels.
-constexpr int kPixIter = 16;
+constexpr int kPixIter = 8;
 __global__ void __launch_bounds__(256) preconv_kernel(const float* __restrict__ mag, const float* __restrict__ bn0_scale,
                                                       const float* __restrict__ bn0_shift, const float* __restrict__ pre_w,
                                                       const float* __restrict__ pre_b, const float* __restrict__ act_scale,
                                                       const float* __restrict__ act_shift, int shift_bstride,
                                                       __half* __restrict__ raw, __nv_bfloat16* __restrict__ act, int T,
-                                                      int F, int Tp, int Fp) {
+                                                      int F, int Tp, int Fp, int log2Fp) {
   const int b = blockIdx.y;
   const int cg = (threadIdx.x & 3) * 8;
   float pw[8], pb[8], as[8], sh[8];
@@ -62,13 +86,21 @@ __global__ void __launch_bounds__(256) preconv_kernel(const float* __restrict__ 
   }
   const int pix_per_clip = Tp * Fp;
   const int pix0 = blockIdx.x * (64 * kPixIter) + (threadIdx.x >> 2);
-#pragma unroll 4
+  const float* magb = mag + (size_t)b * T * F;
+  // all of a thread's magnitude loads are issued before any of its stores (memory-level parallelism)
+  float vs[kPixIter];
+#pragma unroll
+  for (int it = 0; it < kPixIter; ++it) {
+    const int pix = pix0 + it * 64;
+    const int t = pix >> log2Fp, f = pix & (Fp - 1);
+    vs[it] = 0.0f;  // time-padding rows are zero AFTER bn0 (models/resunet.py:548)
+    if (pix < pix_per_clip && t < T) vs[it] = fmaf(__ldg(bn0_scale + f), __ldg(magb + (size_t)t * F + f), __ldg(bn0_shift + f));
+  }
+#pragma unroll
   for (int it = 0; it < kPixIter; ++it) {
     const int pix = pix0 + it * 64;
     if (pix >= pix_per_clip) break;
-    const int t = pix / Fp, f = pix - t * Fp;
-    float v = 0.0f;  // time-padding rows are zero AFTER bn0 (models/resunet.py:548)
-    if (t < T) v = fmaf(__ldg(bn0_scale + f), __ldg(mag + ((size_t)b * T + t) * F + f), __ldg(bn0_shift + f));
+    const float v = vs[it];
     float r[8], a[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -98,8 +130,8 @@ __global__ void __launch_bounds__(256) preconv_kernel(const float* __restrict__ 
 
 cudaError_t launch_film(const float* cond, const float* W, const float* bias, float* shift, int B, int K, int J,
                         cudaStream_t stream) {
-  if (K > 1024) return cudaErrorInvalidValue;
-  film_kernel<<<(J + 7) / 8, 256, 0, stream>>>(cond, W, bias, shift, B, K, J);
+  dim3 grid((unsigned)((J + kFilmTile - 1) / kFilmTile), (unsigned)((B + kFilmTile - 1) / kFilmTile));
+  film_kernel<<<grid, 256, 0, stream>>>(cond, W, bias, shift, B, K, J);
   return cudaGetLastError();
 }
 
@@ -107,10 +139,13 @@ cudaError_t launch_preconv(const float* mag, const float* bn0_scale, const float
                            const float* pre_b, const float* act_scale, const float* act_shift, int shift_bstride,
                            void* raw, void* act, int B, int T, int F, int Tp, int Fp, cudaStream_t stream) {
   const int pix_per_clip = Tp * Fp;
+  int log2Fp = 0;
+  while ((1 << log2Fp) < Fp) ++log2Fp;
+  if ((1 << log2Fp) != Fp) return cudaErrorInvalidValue;   // Fp = n_fft / 2 is a power of two
   dim3 grid((unsigned)((pix_per_clip + 64 * kPixIter - 1) / (64 * kPixIter)), (unsigned)B);
   preconv_kernel<<<grid, 256, 0, stream>>>(mag, bn0_scale, bn0_shift, pre_w, pre_b, act_scale, act_shift, shift_bstride,
                                            reinterpret_cast<__half*>(raw), reinterpret_cast<__nv_bfloat16*>(act), T, F, Tp,
-                                           Fp);
+                                           Fp, log2Fp);
   return cudaGetLastError();
 }
 
