@@ -52,7 +52,7 @@ enum : uint32_t {
 constexpr int kThreads = 320;   // conv_dxn_kernel: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
 constexpr int kThreadsK = 384;  // conv_igemm_kernel: warps 0-1 TMA producers, 2-3 MMA issuers, 4-7 / 8-11 epilogue groups
 // accumulator stages / TMEM columns of conv_igemm_kernel<BN, MT>
-constexpr int acc_stages(int BN, int MT) { return (4 * MT * BN <= 256) ? 4 : 2; }
+constexpr int acc_stages(int BN, int MT) { return (4 * MT * BN <= 256) ? 4 : (2 * MT * BN <= 512) ? 2 : 1; }
 constexpr int tmem_cols(int BN, int MT) {
   const int c = acc_stages(BN, MT) * MT * BN;
   return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512;
@@ -232,6 +232,10 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
   // Four stages where they fit in 256 columns, so that the MMAs of item n + 2 do not have to wait for the epilogue of item n.
   constexpr int NS = acc_stages(BN, MT);
   constexpr int kTmemCols = tmem_cols(BN, MT);
+  // With a single accumulator stage (N = 256, two m-tiles) both epilogue groups work on EVERY item, one m-tile each:
+  // groups that alternate items would have to poll a phase of the one acc_full barrier whose predecessor is still open.
+  constexpr bool kSplitMT = (NS == 1);
+  static_assert(!kSplitMT || MT == 2, "single-stage accumulators are split between the two epilogue groups by m-tile");
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* a_buf = smem;
@@ -271,7 +275,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
     }
     for (int s = 0; s < NS; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
+      mbar_init(&acc_empty[s], kSplitMT ? 8 : 4);
     }
     fence_mbar_init();
   }
@@ -527,7 +531,9 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       uint16_t* const out = reinterpret_cast<uint16_t*>(p.full_act.ptr) + p.full_act.coff;
       const int cstride = p.full_act.cstride;
       const bool idle = (p.debug_flags & 1) != 0;
-      for (int item = blockIdx.x + grp * (int)gridDim.x; item < p.num_items; item += 2 * (int)gridDim.x, n += 2) {
+      if (kSplitMT) n = 0;
+      for (int item = blockIdx.x + (kSplitMT ? 0 : grp) * (int)gridDim.x; item < p.num_items;
+           item += (kSplitMT ? 1 : 2) * (int)gridDim.x, n += (kSplitMT ? 1 : 2)) {
         const uint32_t as = n % NS, acc_parity = (n / NS) & 1u;
         const Item it = decode_item<MT>(p, item, BN);
         if (it.b != tab_b || it.n0 != tab_n0) {
@@ -564,7 +570,8 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
         for (int c0 = 0; c0 < nchunk; c0 += 32) {
           float v[MT][32];
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) tmem_ld_x32(taddr + mt * BN + c0, v[mt]);
+          for (int mt = 0; mt < MT; ++mt)
+            if (!kSplitMT || mt == grp) tmem_ld_x32(taddr + mt * BN + c0, v[mt]);
           float4 sc[8], sh[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -574,7 +581,8 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           tmem_ld_wait();
           if (idle) continue;
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) act_store32(v[mt], sc, sh, dst[mt] + c0, valid[mt]);
+          for (int mt = 0; mt < MT; ++mt)
+            if (!kSplitMT || mt == grp) act_store32(v[mt], sc, sh, dst[mt] + c0, valid[mt]);
         }
         tc_fence_before_sync();
         __syncwarp();
@@ -586,7 +594,9 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
     // tests fold away (the specialised copies run ~2x fewer instructions per output tile)
     constexpr uint32_t F = decltype(ftag)::value;
 #define FEAT(bit, cond) ((F == kFGeneric) ? (cond) : ((F & (bit)) != 0u))
-    for (int item = blockIdx.x + grp * (int)gridDim.x; item < p.num_items; item += 2 * (int)gridDim.x, n += 2) {
+    if (kSplitMT) n = 0;
+    for (int item = blockIdx.x + (kSplitMT ? 0 : grp) * (int)gridDim.x; item < p.num_items;
+         item += (kSplitMT ? 1 : 2) * (int)gridDim.x, n += (kSplitMT ? 1 : 2)) {
       const uint32_t as = n % NS, acc_parity = (n / NS) & 1u;
       const Item it = decode_item<MT>(p, item, BN);
       // ---- (re)stage the per-(clip, N tile) tables; double-buffered so one named barrier per change suffices ----
@@ -631,7 +641,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       mbar_wait(&acc_full[as], acc_parity);
       tc_fence_after_sync();
 #pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
+      for (int mt = kSplitMT ? grp : 0; mt < (kSplitMT ? grp + 1 : MT); ++mt) {
         const int h = it.h0 + mt * 16 + hl;
         const int w = it.w0 + wl;
         const bool valid = (h < p.H) && (w < p.W) && !(no_store && h >= 0);
@@ -1457,7 +1467,14 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   else if (l.ncols <= 64) BN = 64;
   else if (l.ncols % 256 == 0) BN = 256;
   else BN = 128;
-  int MT = (BN == 256) ? 1 : 2;
+  // N = 256 tiles take one m-tile.  Two m-tiles (one 512-column accumulator, epilogue not overlapped; debug flag 1024)
+  // halve the weight traffic from L2 but are not faster (measured: 512 -> 256 conv 0.228 vs 0.222 ms): at N = 256 the MMA
+  // operand reads alone take 96 of the 128 B/clk of shared-memory bandwidth, and the TMA fill needs most of the rest --
+  // the fix for these layers is cta_group::2 (each CTA holds half of the weight tile), not a larger tile.
+  int big_tiles = 0;
+  for (int s = 0; s < l.nseg; ++s)
+    if (l.seg[s].kc > 0) big_tiles += (l.seg[s].cin / l.seg[s].kc) * l.seg[s].taps;
+  int MT = (BN == 256) ? ((big_tiles >= 36 && (g_debug_flags & 1024)) ? 2 : 1) : 2;
   if (l.H < 32 || l.H % 32) MT = 1;
   if (MT == 2 && l.ncols <= BN) {
     // Resident weights (no per-tap ring handshake in the MMA issuer) beat the larger tile: if the weights of an item
@@ -1484,7 +1501,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   if (BN == 32) kc = MT == 2 ? make_choice<32, 2>() : make_choice<32, 1>();
   else if (BN == 64) kc = MT == 2 ? make_choice<64, 2>() : make_choice<64, 1>();
   else if (BN == 128) kc = MT == 2 ? make_choice<128, 2>() : make_choice<128, 1>();
-  else kc = make_choice<256, 1>();
+  else kc = MT == 2 ? make_choice<256, 2>() : make_choice<256, 1>();
 
   ConvPrepared* cp = new (std::nothrow) ConvPrepared();
   if (!cp) return set_error(LASS_ERR_ARG, "conv: out of host memory");
