@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(256) film_kernel(const float* __restrict__ con
 // 4 threads per pixel, 8 channels each (one 16 B store per tensor per thread).  A CTA works on one clip, so every
 // per-channel constant (pre_conv weight / bias, folded BN scale, FiLM shift of that clip) is loaded once per thread and
 // the thread then walks over kPixIter pixels.
-constexpr int kPixIter = 8;
+constexpr int kPixIter = 16;
 __global__ void __launch_bounds__(256) preconv_kernel(const float* __restrict__ mag, const float* __restrict__ bn0_scale,
                                                       const float* __restrict__ bn0_shift, const float* __restrict__ pre_w,
                                                       const float* __restrict__ pre_b, const float* __restrict__ act_scale,
@@ -76,13 +76,15 @@ __global__ void __launch_bounds__(256) preconv_kernel(const float* __restrict__ 
                                                       int F, int Tp, int Fp, int log2Fp) {
   const int b = blockIdx.y;
   const int cg = (threadIdx.x & 3) * 8;
-  float pw[8], pb[8], as[8], sh[8];
+  // activated output = lrelu(as * (pw * v + pb) + sh) = lrelu(ca * v + cb): one FMA per channel in the pixel loop
+  float pw[8], pb[8], ca[8], cb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     pw[j] = __ldg(pre_w + cg + j);
     pb[j] = __ldg(pre_b + cg + j);
-    as[j] = __ldg(act_scale + cg + j);
-    sh[j] = __ldg(act_shift + (size_t)b * shift_bstride + cg + j);
+    const float as = __ldg(act_scale + cg + j);
+    ca[j] = as * pw[j];
+    cb[j] = fmaf(as, pb[j], __ldg(act_shift + (size_t)b * shift_bstride + cg + j));
   }
   const int pix_per_clip = Tp * Fp;
   const int pix0 = blockIdx.x * (64 * kPixIter) + (threadIdx.x >> 2);
@@ -101,11 +103,10 @@ __global__ void __launch_bounds__(256) preconv_kernel(const float* __restrict__ 
     const int pix = pix0 + it * 64;
     if (pix >= pix_per_clip) break;
     const float v = vs[it];
-    float r[8], a[8];
+    float a[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      r[j] = fmaf(pw[j], v, pb[j]);
-      const float y = fmaf(as[j], r[j], sh[j]);
+      const float y = fmaf(ca[j], v, cb[j]);
       a[j] = fmaxf(y, 0.01f * y);
     }
     const size_t o = ((size_t)b * pix_per_clip + pix) * 32 + cg;
@@ -116,6 +117,9 @@ __global__ void __launch_bounds__(256) preconv_kernel(const float* __restrict__ 
     pa.w = pack_bf16x2(a[6], a[7]);
     *reinterpret_cast<uint4*>(act + o) = pa;
     if (raw != nullptr) {   // the fused path regenerates the raw tensor where it is needed (conv epilogue) and passes NULL
+      float r[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] = fmaf(pw[j], v, pb[j]);
       uint4 pr;
       pr.x = pack_f16x2_sat(r[0], r[1]);
       pr.y = pack_f16x2_sat(r[2], r[3]);

@@ -1,15 +1,20 @@
 #!/bin/bash
-# Round profile: (1) per-launch duration + DRAM bytes of one step, (2) `ncu --set full` of three representative conv
-# launches (store-bound enc0.c2, MMA-count-bound dec5.c1, tensor-bound dec2.c1) and of the spectral kernels.
+# Round profile: (1) plain bench line, (2) per-launch duration + DRAM bytes of one step (ncu, --clock-control none),
+# (3) `ncu --set full` of representative launches: epilogue/TMA-store-bound enc0.c2, MMA-issue-bound dec5.c1, smem-bandwidth-
+# bound dec2.c1 (single-layer runs of tools/gpu_one_layer.py at batch 16) and the spectral kernels K1 / K5.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
+TAG=${1:-r1d}
+python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err || { echo bench failed; tail -5 gpurun_out/bench_$TAG.err; exit 1; }
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${TAG}_reference.json 2>> gpurun_out/bench_$TAG.err
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-spectral"
-$CMD > gpurun_out/bench_plain.json 2> gpurun_out/bench_plain.err || { echo plain run failed; tail -5 gpurun_out/bench_plain.err; exit 1; }
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -k regex:"conv_igemm|stft|mask_istft|film|preconv" -s 111 -c 37 --csv --log-file gpurun_out/step_dram.csv $CMD > gpurun_out/ncu_a.log 2>&1
-echo "ncu a $?"
-# conv launch indices within a step (0-based among conv launches): enc0.c2 = 1, dec5.c1 = 30, dec2.c1 = 21
-ncu --set full --clock-control none --import-source on -k regex:"conv_igemm" -s 97 -c 1 -f -o gpurun_out/prof_enc0c2 $CMD > gpurun_out/ncu_b.log 2>&1; echo "ncu b $?"
-ncu --set full --clock-control none --import-source on -k regex:"conv_igemm" -s 126 -c 1 -f -o gpurun_out/prof_dec5c1 $CMD > gpurun_out/ncu_c.log 2>&1; echo "ncu c $?"
-ncu --set full --clock-control none --import-source on -k regex:"conv_igemm" -s 117 -c 1 -f -o gpurun_out/prof_dec2c1 $CMD > gpurun_out/ncu_d.log 2>&1; echo "ncu d $?"
-ls -la gpurun_out
+    -k regex:"conv_igemm|stft|mask_istft|film|preconv" -s 111 -c 37 --csv --log-file gpurun_out/step_launches_$TAG.csv $CMD > gpurun_out/ncu_a.log 2>&1
+echo "ncu launch list $?"
+for spec in "enc0c2|enc0.c2" "dec5c1|dec5.c1" "dec2c1|dec2.c1"; do
+  tag=${spec%%|*}; L=${spec#*|}
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:"conv_igemm" -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_$tag python tools/gpu_one_layer.py "$L" 16 > gpurun_out/ncu_$tag.log 2>&1; echo "ncu $tag $?"
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"stft_gemm" -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_k1 python tools/gpu_spectral_bench.py 1024 160 > gpurun_out/ncu_k1.log 2>&1; echo "ncu k1 $?"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mask_istft" -s 3 -c 1 -f -o gpurun_out/prof_${TAG}_k5 python tools/gpu_spectral_bench.py 1024 160 > gpurun_out/ncu_k5.log 2>&1; echo "ncu k5 $?"
+ls -la gpurun_out | tail -15
