@@ -145,6 +145,21 @@ typedef struct lass_conv_desc {
    * channels: the three horizontal taps become output columns (N = 3*Cout, K = 3*Cin, a third of the MMAs) and are summed
    * by lane shuffles in the epilogue; seg[0].weights is then (3 [ky], 3*Cout [kx, co], cin), seg[1] (optional 1x1) as before. */
   int algo;
+  /* Optional GENERATED A operand for seg[0] (the first conv of encoder_block1, whose input is the activated pre_conv output
+   * of the 1-channel magnitude, reference models/resunet.py:537-556 + ConvBlockRes.bn1): instead of reading seg[0].src the
+   * kernel computes, for every input pixel (b, h, w) of the H x W grid and channel c < 32,
+   *    x    = h < gen_T ? gen_in_scale[w] * gen_src[(b*gen_T + h)*gen_F + w] + gen_in_shift[w] : 0      (bn0, zero time padding)
+   *    a[c] = leaky_relu(gen_scale[c] * (gen_w[c] * x + gen_b[c]) + gen_shift[b*gen_shift_bstride + c])  (pre_conv, BN, FiLM)
+   * as bf16 (zero outside the grid).  Needs seg[0] = {cin 32, kc 32, taps 9, bf16}; seg[0].src is ignored.  NULL gen_src
+   * disables it. */
+  const float* gen_src;
+  const float* gen_in_scale;
+  const float* gen_in_shift;
+  const float* gen_w;
+  const float* gen_b;
+  const float* gen_scale;
+  const float* gen_shift;
+  int gen_shift_bstride, gen_T, gen_F;
 } lass_conv_desc;
 
 LASS_API int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream);

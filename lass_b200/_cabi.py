@@ -91,7 +91,9 @@ class ConvDesc(ctypes.Structure):
                 ("pool_raw", ConvOut), ("pool_act", ConvOut), ("after_w", c_void_p), ("after_b", c_void_p),
                 ("feat", c_void_p), ("resid_src", c_void_p), ("resid_in_scale", c_void_p),
                 ("resid_in_shift", c_void_p), ("resid_w", c_void_p), ("resid_b", c_void_p), ("resid_T", c_int),
-                ("resid_F", c_int), ("algo", c_int)]
+                ("resid_F", c_int), ("algo", c_int), ("gen_src", c_void_p), ("gen_in_scale", c_void_p),
+                ("gen_in_shift", c_void_p), ("gen_w", c_void_p), ("gen_b", c_void_p), ("gen_scale", c_void_p),
+                ("gen_shift", c_void_p), ("gen_shift_bstride", c_int), ("gen_T", c_int), ("gen_F", c_int)]
 
 
 SIGNATURES["lass_conv_igemm"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p])

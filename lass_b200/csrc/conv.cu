@@ -91,6 +91,15 @@ struct ConvParams {
   const float* resid_w;
   const float* resid_b;
   int resid_T, resid_F;
+  // generated A operand of segment 0 (lass_conv_desc.gen_src)
+  const float* gen_src;
+  const float* gen_in_scale;
+  const float* gen_in_shift;
+  const float* gen_w;
+  const float* gen_b;
+  const float* gen_scale;
+  const float* gen_shift;
+  int gen_shift_bstride, gen_T, gen_F;
   long long* prof;  // optional per-CTA cycle counters (kProfSlots each), nullptr = off
   int nseg;
   int B, H, W, ncols;
@@ -175,9 +184,17 @@ __device__ __forceinline__ void pack_act32(const float* sc, const float* sh, con
 __device__ __forceinline__ uint4* stage_slot(unsigned char* tile, int row, int piece) {
   return reinterpret_cast<uint4*>(tile + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
 }
+// explicit st.shared (a store through a generic pointer into the shared window is several times slower)
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t stage_slot_addr(uint32_t tile_addr, int row, int piece) {
+  return tile_addr + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4);
+}
 __device__ __forceinline__ void stage_row32(unsigned char* tile, int row, const uint32_t* w) {
+  const uint32_t t = smem_u32(tile);
 #pragma unroll
-  for (int pc = 0; pc < 4; ++pc) *stage_slot(tile, row, pc) = make_uint4(w[4 * pc], w[4 * pc + 1], w[4 * pc + 2], w[4 * pc + 3]);
+  for (int pc = 0; pc < 4; ++pc) sts128(stage_slot_addr(t, row, pc), w[4 * pc], w[4 * pc + 1], w[4 * pc + 2], w[4 * pc + 3]);
 }
 
 // profiling slots (clock cycles, per CTA); documented at lass_debug_set_conv_profile in include/lass_b200.h
@@ -196,6 +213,12 @@ enum { kProfProdAEmpty = 0, kProfProdBEmpty, kProfProdTotal, kProfMmaAccEmpty, k
   do {                                                  \
     const long long _t = prof ? clock64() : 0;          \
     mbar_wait(bar, parity);                             \
+    if (prof) pc[slot] += clock64() - _t;               \
+  } while (0)
+#define LASS_TIMED_WAIT_RELAXED(bar, parity, slot)      \
+  do {                                                  \
+    const long long _t = prof ? clock64() : 0;          \
+    mbar_wait_relaxed(bar, parity);                     \
     if (prof) pc[slot] += clock64() - _t;               \
   } while (0)
 
@@ -262,7 +285,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < p.nseg; ++s) {
-      tma_prefetch_desc(&p.seg[s].tmA);
+      if (!(s == 0 && p.gen_src != nullptr)) tma_prefetch_desc(&p.seg[s].tmA);
       tma_prefetch_desc(&p.seg[s].tmB);
     }
     for (int s = 0; s < p.a_stages; ++s) {
@@ -303,6 +326,28 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       const int step = dual ? 2 : 1;
       uint32_t a_it = 0, b_it = 0;
       bool first_item = (pw == 0);     // resident weights are loaded once, by producer 0
+      uint32_t gen_ca[16], gen_cb[16]; // generated-A mode: per-clip affine of the 32 channels, packed bf16 pairs
+      int gen_b = -1;
+      constexpr int kGenRows = (16 * MT + 2) * kHaloPitch;          // 64 B rows (32 channels) of the halo tile
+      constexpr int kGenPer = (kGenRows + 31) / 32;
+      // raw loads of this lane's pixels of the item about to be generated; they are only CONSUMED (bn0 affine) one item
+      // later, so the in-order warp never waits for them
+      float gen_m[kGenPer], gen_s[kGenPer], gen_t[kGenPer];
+      bool gen_have = false;
+      auto gen_load = [&](const Item& gi) {
+        const float* srcb = p.gen_src + (size_t)gi.b * p.gen_T * p.gen_F;
+#pragma unroll
+        for (int i = 0; i < kGenPer; ++i) {
+          const int r = lane + 32 * i;
+          const int hh = (r * 205) >> 11, ww = r - hh * kHaloPitch;   // r / 10 for r < 1029
+          const int h = gi.h0 - 1 + hh, w = gi.w0 - 1 + ww;
+          const bool inside = r < kGenRows && h >= 0 && h < p.H && w >= 0 && w < p.W;
+          const bool live = inside && h < p.gen_T;                    // zero time padding AFTER bn0 (models/resunet.py:548)
+          gen_m[i] = live ? __ldg(srcb + (size_t)h * p.gen_F + w) : 0.0f;
+          gen_s[i] = live ? __ldg(p.gen_in_scale + w) : 0.0f;
+          gen_t[i] = inside ? (live ? __ldg(p.gen_in_shift + w) : 0.0f) : __int_as_float(0x7fc00000);   // NaN = outside the grid
+        }
+      };
       for (int item = (int)blockIdx.x + (dual ? (int)pw : 0) * (int)gridDim.x; item < p.num_items; item += step * (int)gridDim.x) {
         const Item it = decode_item<MT>(p, item, BN);
         uint32_t b_slot_res = 0;
@@ -314,8 +359,63 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           const uint32_t b_bytes = BN * row_bytes;
           for (int ch = 0; ch < sg.nchunks; ++ch) {
             const uint32_t sa = a0 + a_it % ring_a;
-            LASS_TIMED_WAIT(&a_empty[sa], ((a_it / ring_a) & 1) ^ 1, kProfProdAEmpty);
-            if (elect_one()) {
+            LASS_TIMED_WAIT_RELAXED(&a_empty[sa], ((a_it / ring_a) & 1) ^ 1, kProfProdAEmpty);
+            if (s == 0 && p.gen_src != nullptr) {
+              // ---- generated A tile: activated pre_conv output of the 1-channel magnitude, written by this warp ----
+              if (it.b != gen_b) {
+                gen_b = it.b;
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                  float ca[2], cb[2];
+#pragma unroll
+                  for (int u = 0; u < 2; ++u) {
+                    const float as = __ldg(p.gen_scale + c + u);
+                    ca[u] = as * __ldg(p.gen_w + c + u);
+                    cb[u] = fmaf(as, __ldg(p.gen_b + c + u), __ldg(p.gen_shift + (size_t)it.b * p.gen_shift_bstride + c + u));
+                  }
+                  gen_ca[c / 2] = pack_bf16x2(ca[0], ca[1]);
+                  gen_cb[c / 2] = pack_bf16x2(cb[0], cb[1]);
+                }
+              }
+              const uint32_t tile = smem_u32(a_buf + (size_t)sa * p.a_stage_bytes);
+              if (!gen_have) gen_load(it);                                 // first item: nothing was prefetched
+              float xs[kGenPer];
+#pragma unroll
+              for (int i = 0; i < kGenPer; ++i) xs[i] = fmaf(gen_s[i], gen_m[i], gen_t[i]);
+              {
+                // prefetch the magnitudes of this producer's NEXT item: their latency hides behind the tile written below
+                const int nxt = item + step * (int)gridDim.x;
+                gen_have = nxt < p.num_items;
+                if (gen_have) gen_load(decode_item<MT>(p, nxt, BN));
+              }
+#pragma unroll
+              for (int i = 0; i < kGenPer; ++i) {
+                const int r = lane + 32 * i;
+                if (r < kGenRows) {
+                  const float x = xs[i];
+                  if (x == x) {
+                    // Packed bf16 arithmetic (3 instructions per channel pair; the fp32 form needs 5 and the two producer
+                    // warps cannot keep up with the tensor pipe): x, scale and shift are rounded to bf16 before the fused
+                    // multiply-add, i.e. this operand carries about three bf16 roundings instead of one.
+                    const uint32_t xx = pack_bf16x2(x, x);
+#pragma unroll
+                    for (int pc = 0; pc < 4; ++pc) {
+                      uint32_t wv[4];
+#pragma unroll
+                      for (int j = 0; j < 4; ++j) wv[j] = affine_lrelu_bf16x2(gen_ca[4 * pc + j], xx, gen_cb[4 * pc + j]);
+                      sts128(stage_slot_addr(tile, r, pc), wv[0], wv[1], wv[2], wv[3]);
+                    }
+                  } else {                       // outside the grid: the convolution's zero padding
+#pragma unroll
+                    for (int pc = 0; pc < 4; ++pc) sts128(stage_slot_addr(tile, r, pc), 0u, 0u, 0u, 0u);
+                  }
+                }
+              }
+              fence_proxy_async_smem();        // generic-proxy writes -> visible to the tensor core's operand reads
+              __syncwarp();
+              if (elect_one()) mbar_arrive(&a_full[sa]);
+              __syncwarp();
+            } else if (elect_one()) {
               if (p.debug_flags & 4) {
                 mbar_arrive(&a_full[sa]);
               } else {
@@ -340,7 +440,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
             } else {
               for (int tp = 0; tp < sg.taps; ++tp) {
                 const uint32_t sb = b0 + b_it % ring_b;
-                LASS_TIMED_WAIT(&b_empty[sb], ((b_it / ring_b) & 1) ^ 1, kProfProdBEmpty);
+                LASS_TIMED_WAIT_RELAXED(&b_empty[sb], ((b_it / ring_b) & 1) ^ 1, kProfProdBEmpty);
                 if (elect_one()) {
                   mbar_arrive_expect_tx(&b_full[sb], b_bytes);
                   tma_load_3d(b_buf + (size_t)sb * p.b_stage_bytes, &sg.tmB, &b_full[sb], ch * sg.kc, it.n0, tp);
@@ -564,7 +664,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
         }
         const uint32_t taddr = tmem_base + as * (MT * BN) + (static_cast<uint32_t>(q * 32) << 16);
         const int nchunk = min(BN, p.ncols - it.n0);
-        mbar_wait(&acc_full[as], acc_parity);
+        mbar_wait_relaxed(&acc_full[as], acc_parity);
         tc_fence_after_sync();
 #pragma unroll 1
         for (int c0 = 0; c0 < nchunk; c0 += 32) {
@@ -635,10 +735,10 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                               __ldg(p.resid_in_shift + ww));
       }
       if (q == 0 && lane == 0 && grp == 0) {
-        LASS_TIMED_WAIT(&acc_full[as], acc_parity, kProfEpiAccFull);
+        LASS_TIMED_WAIT_RELAXED(&acc_full[as], acc_parity, kProfEpiAccFull);
       }
       __syncwarp();
-      mbar_wait(&acc_full[as], acc_parity);
+      mbar_wait_relaxed(&acc_full[as], acc_parity);
       tc_fence_after_sync();
 #pragma unroll 1
       for (int mt = kSplitMT ? grp : 0; mt < (kSplitMT ? grp + 1 : MT); ++mt) {
@@ -802,6 +902,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           // Full-resolution outputs LAST: their staging buffers are reused chunk after chunk, and the pooling work above
           // gives the previous chunk's TMA stores time to read them before this wait.
           const bool coal = FEAT(kFCoal, p.tma_store == 2);   // staged, but written with coalesced st.global instead of TMA
+          const bool act_direct = p.tma_store == 3;           // hybrid: raw tensor through TMA, activated tensor st.global
           if (FEAT(kFTma, tma_store) && !FEAT(kFTmaPool, tma_pool)) {
             if (!coal && lane == 0) tma_store_wait_read();
             __syncwarp();                                     // (coal: the previous chunk's staging reads are done)
@@ -815,7 +916,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           if (FEAT(kFAct, p.full_act.ptr != nullptr)) {
             uint32_t wv[16];
             pack_act32(tb.sc_full + c0, tb.sh_full + c0, v, wv);
-            if (FEAT(kFTma, tma_store)) stage_row32(stg + 2048, lane, wv);
+            if (FEAT(kFTma, tma_store) && !act_direct) stage_row32(stg + 2048, lane, wv);
             else store32(p.full_act, it.b, ho, wo, Ho, Wo, c, wv, valid);
           }
           if (FEAT(kFTma, tma_store) && coal) {
@@ -843,7 +944,8 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
             __syncwarp();
             if (elect_one()) {
               if (FEAT(kFRaw, p.full_raw.ptr != nullptr)) tma_store_5d(&p.tm_out[grp_dy], stg, c, grp_dx, it.w0, hw0, it.b);
-              if (FEAT(kFAct, p.full_act.ptr != nullptr)) tma_store_5d(&p.tm_out[2 + grp_dy], stg + 2048, c, grp_dx, it.w0, hw0, it.b);
+              if (FEAT(kFAct, p.full_act.ptr != nullptr) && !act_direct)
+                tma_store_5d(&p.tm_out[2 + grp_dy], stg + 2048, c, grp_dx, it.w0, hw0, it.b);
               tma_store_commit();
             }
             __syncwarp();
@@ -1535,6 +1637,23 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   p.resid_b = l.resid_b;
   p.resid_T = l.resid_T;
   p.resid_F = l.resid_F;
+  if (l.gen_src) {
+    if (!l.gen_in_scale || !l.gen_in_shift || !l.gen_w || !l.gen_b || !l.gen_scale || !l.gen_shift || l.gen_T <= 0 ||
+        l.gen_T > l.H || l.gen_F < l.W || l.seg[0].cin != 32 || l.seg[0].kc != 32 || l.seg[0].taps != 9 || l.seg[0].fp16) {
+      delete cp;
+      return set_error(LASS_ERR_ARG, "conv: bad generated-A spec (needs a 32-channel bf16 3x3 segment 0)");
+    }
+    p.gen_src = l.gen_src;
+    p.gen_in_scale = l.gen_in_scale;
+    p.gen_in_shift = l.gen_in_shift;
+    p.gen_w = l.gen_w;
+    p.gen_b = l.gen_b;
+    p.gen_scale = l.gen_scale;
+    p.gen_shift = l.gen_shift;
+    p.gen_shift_bstride = l.gen_shift_bstride;
+    p.gen_T = l.gen_T;
+    p.gen_F = l.gen_F;
+  }
   fill_out(p.full_raw, l.full_raw);
   fill_out(p.full_act, l.full_act);
   fill_out(p.pool_raw, l.pool_raw);
@@ -1544,8 +1663,10 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   int b_tiles_per_item = 0;
   for (int s = 0; s < l.nseg; ++s) {
     const ConvSegment& sg = l.seg[s];
-    if (!sg.src || !sg.weights || (sg.kc != 32 && sg.kc != 64) || sg.cin <= 0 || sg.cin % sg.kc ||
-        (sg.taps != 9 && sg.taps != 1) || sg.src_cstride % 8 || sg.src_coff % 8 || sg.src_coff + sg.cin > sg.src_cstride) {
+    const bool generated = (s == 0 && l.gen_src != nullptr);
+    if ((!sg.src && !generated) || !sg.weights || (sg.kc != 32 && sg.kc != 64) || sg.cin <= 0 || sg.cin % sg.kc ||
+        (sg.taps != 9 && sg.taps != 1) ||
+        (!generated && (sg.src_cstride % 8 || sg.src_coff % 8 || sg.src_coff + sg.cin > sg.src_cstride))) {
       delete cp;
       return set_error(LASS_ERR_ARG, "conv: bad segment %d (cin %d kc %d taps %d cstride %d coff %d)", s, sg.cin, sg.kc,
                        sg.taps, sg.src_cstride, sg.src_coff);
@@ -1557,7 +1678,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     d.fmt = sg.fp16 ? kFmtF16 : kFmtBF16;
     const CUtensorMapSwizzle swz = sg.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
     const bool halo = sg.taps == 9;
-    {
+    if (!generated) {
       const char* base = reinterpret_cast<const char*>(sg.src) + (size_t)sg.src_coff * 2;
       uint64_t dims[4] = {(uint64_t)sg.cin, (uint64_t)l.W, (uint64_t)l.H, (uint64_t)l.B};
       uint64_t strides[3] = {(uint64_t)sg.src_cstride * 2, (uint64_t)sg.src_cstride * 2 * l.W,
@@ -1646,6 +1767,8 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   // debug flag 512: staged outputs leave through coalesced st.global (mode 2) instead of TMA stores.  Measured slower
   // than the TMA stores on every launch of the plan (enc conv2 +20 %, transposed convs +5..20 %), kept for experiments.
   if (p.tma_store && !p.tma_pool && (g_debug_flags & 512)) p.tma_store = 2;
+  // debug flag 2048: hybrid -- the raw tensor through TMA stores, the activated one with per-lane st.global
+  if (p.tma_store == 1 && !p.tma_pool && (g_debug_flags & 2048) && l.full_raw.ptr && l.full_act.ptr) p.tma_store = 3;
   {
     // epilogue specialisation: the exact feature set of this launch, matched against the compile-time sets of the kernel
     const bool pooling = (l.pool_raw.ptr || l.pool_act.ptr) && !(g_debug_flags & 8);
@@ -1672,7 +1795,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     else if (f == kFAfterBias) p.epi_mode = 6;
     else p.epi_mode = 0;
   }
-  if (p.tma_store == 1) {
+  if (p.tma_store == 1 || p.tma_store == 3) {
     const int Ho = l.H * l.up_h, Wo = l.W * l.up_w;
     auto full_map = [&](CUtensorMap* tm, const ConvOut& o, int dy) -> int {
       const char* base = reinterpret_cast<const char*>(o.ptr) + (size_t)o.coff * 2 + (size_t)dy * Wo * o.cstride * 2;

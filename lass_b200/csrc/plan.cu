@@ -23,9 +23,6 @@ namespace lass {
 
 cudaError_t launch_film(const float* cond, const float* W, const float* bias, float* shift, int B, int K, int J,
                         cudaStream_t stream);
-cudaError_t launch_preconv(const float* mag, const float* bn0_scale, const float* bn0_shift, const float* pre_w,
-                           const float* pre_b, const float* act_scale, const float* act_shift, int shift_bstride,
-                           void* raw, void* act, int B, int T, int F, int Tp, int Fp, cudaStream_t stream);
 
 namespace {
 
@@ -136,8 +133,10 @@ size_t layout(lass_plan* p, int B, const Geometry& g, int n_fft, int hop, int L,
   place(p ? &p->shift : nullptr, B, 1, 1, sites().rows, 4);
   place(p ? &p->feat : nullptr, B, 3, g.Tp, g.Fp, 4);
   for (int k = 0; k < 7; ++k) {
-    if (k > 0) place(p ? &p->x_raw[k] : nullptr, B, g.H[k], g.W[k], kEncCin[k], 2);   // x_raw[0] is never materialised
-    place(p ? &p->x_act[k] : nullptr, B, g.H[k], g.W[k], kEncCin[k], 2);
+    if (k > 0) {   // x_raw[0] / x_act[0] are never materialised (regenerated from the magnitude inside encoder_block1's convs)
+      place(p ? &p->x_raw[k] : nullptr, B, g.H[k], g.W[k], kEncCin[k], 2);
+      place(p ? &p->x_act[k] : nullptr, B, g.H[k], g.W[k], kEncCin[k], 2);
+    }
     place(p ? &p->a2[k] : nullptr, B, g.H[k], g.W[k], kEncCout[k], 2);
   }
   for (int k = 0; k < 6; ++k) {
@@ -218,6 +217,23 @@ int build_launches(lass_plan* p) {
       ConvLaunch l = base_launch(p, k, cout);
       l.nseg = 1;
       l.seg[0] = seg_spec(p->x_act[k], cin, 9, false, p->w.enc[k].conv1_w);
+      if (k == 0) {
+        // encoder_block1's input is lrelu(bn1(pre_conv(bn0(mag))) + beta1), a function of ONE scalar per pixel: the conv's
+        // producer warps generate the activated 32-channel operand tile in shared memory from the magnitude, so neither
+        // x_act[0] (33.5 MB per clip written and read back) nor a pre_conv kernel exists
+        l.seg[0].src = nullptr;
+        l.seg[0].src_cstride = cin;
+        l.gen_src = reinterpret_cast<const float*>(p->mag.ptr);
+        l.gen_in_scale = p->w.bn0_scale;
+        l.gen_in_shift = p->w.bn0_shift;
+        l.gen_w = p->w.pre_w;
+        l.gen_b = p->w.pre_b;
+        l.gen_scale = p->w.act_scale + sites().off[0];
+        l.gen_shift = reinterpret_cast<const float*>(p->shift.ptr) + sites().off[0];
+        l.gen_shift_bstride = sites().rows;
+        l.gen_T = p->T;
+        l.gen_F = p->F;
+      }
       l.algo = (p->w.dxn_mask >> (2 * k)) & 1u;
       l.full_act = out_spec(p->a2[k], 0, false, p, 2 * k + 1, 0);
       if ((e = add_conv(p, l))) return e;
@@ -407,12 +423,6 @@ int lass_resunet30_forward_stages(lass_plan* p, int stage_mask, const float* mix
                                              sites().rows, stream),
                                  "film launch")))
     return e;
-  // bn0 + pad + pre_conv -> encoder_block1 input
-  if ((e = set_cuda_error(launch_preconv(mag, p->w.bn0_scale, p->w.bn0_shift, p->w.pre_w, p->w.pre_b,
-                                         p->w.act_scale + sites().off[0], shift + sites().off[0], sites().rows,
-                                         p->x_raw[0].ptr, p->x_act[0].ptr, p->B, p->T, p->F, p->Tp, p->Fp, stream),
-                          "preconv launch")))
-    return e;
   }
   // K3 / K4: the UNet
   if (stage_mask & LASS_STAGE_UNET)
@@ -427,7 +437,7 @@ int lass_resunet30_forward_stages(lass_plan* p, int stage_mask, const float* mix
                         "mask_istft launch");
 }
 
-int lass_resunet30_num_launches(const lass_plan* p) { return p ? (int)p->convs.size() + 5 : 0; }
+int lass_resunet30_num_launches(const lass_plan* p) { return p ? (int)p->convs.size() + 4 : 0; }
 
 int lass_debug_time_unet_launches(lass_plan* p, float* ms_out, double* flops_out, int capacity, void* stream_v) {
   if (!p || !ms_out) return set_error(LASS_ERR_ARG, "time_unet_launches: null pointer");

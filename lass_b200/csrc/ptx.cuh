@@ -100,6 +100,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   mbar_wait_slow(smem_u32(bar), parity);
 }
+// Wait of a role that is NOT on the critical path (producers waiting for a free stage, epilogue warps waiting for an
+// accumulator): sleeps between polls so that it does not compete for issue slots with a busy warp of the same scheduler.
+static __device__ __noinline__ void mbar_wait_relaxed_slow(uint32_t bar_addr, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    if (ok) return;
+    __nanosleep(64);
+    if ((++spins & 0xfffu) == 0u && clock64() - t0 > LASS_MBAR_TIMEOUT_CYCLES) {
+      printf("lass: mbarrier timeout (relaxed) block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
+             blockIdx.z, threadIdx.x, bar_addr, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_relaxed_slow(smem_u32(bar), parity);
+}
 
 // ------------------------------------------------------------------------------------------------
 // proxy fences
@@ -266,6 +295,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+// leaky_relu(y, 0.01) of two bf16 values at once: max(y, 0.01 * y).  The slope is bf16(0.01) = 0.010009766 and the product is
+// rounded to bf16, i.e. the NEGATIVE side carries ~1.5 ulp of error instead of the 0.5 ulp of rounding an fp32 result;
+// negative outputs are 100x smaller than positive ones, so this is far below the bf16 storage noise of the tensor.
+__device__ __forceinline__ uint32_t lrelu_bf16x2(uint32_t y) {
+  uint32_t r;
+  asm("{\n\t"
+      ".reg .b32 t;\n\t"
+      "mul.rn.bf16x2 t, %1, %2;\n\t"
+      "max.bf16x2 %0, %1, t;\n\t"
+      "}\n"
+      : "=r"(r)
+      : "r"(y), "r"(0x3c243c24u));
+  return r;
+}
+// leaky_relu(a * x + b) of two channels in packed bf16 arithmetic (one rounding of the fused multiply-add, then lrelu_bf16x2)
+__device__ __forceinline__ uint32_t affine_lrelu_bf16x2(uint32_t a, uint32_t x, uint32_t b) {
+  uint32_t y;
+  asm("fma.rn.bf16x2 %0, %1, %2, %3;" : "=r"(y) : "r"(a), "r"(x), "r"(b));
+  return lrelu_bf16x2(y);
 }
 // fp16 with saturation to +-65504 (the raw residual stream must never become inf)
 __device__ __forceinline__ uint32_t pack_f16x2_sat(float lo, float hi) {

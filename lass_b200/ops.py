@@ -112,8 +112,10 @@ def make_out(dst: torch.Tensor = None, coff: int = 0, scale: torch.Tensor = None
 
 
 def conv_igemm(B, H, W, ncols, segments, bias=None, up=(1, 1), full_raw=None, full_act=None, pool=(1, 1),
-               pool_raw=None, pool_act=None, after_w=None, after_b=None, feat=None, resid=None, algo=0):
-    """resid: optional (src (B, T, F) fp32, in_scale (F), in_shift (F), w (ncols), b (ncols)) rank-1 residual."""
+               pool_raw=None, pool_act=None, after_w=None, after_b=None, feat=None, resid=None, algo=0, gen=None):
+    """resid: optional (src (B, T, F) fp32, in_scale (F), in_shift (F), w (ncols), b (ncols)) rank-1 residual.
+    gen: optional (src (B, T, F) fp32, in_scale (F), in_shift (F), w (32), b (32), scale (32), shift (B, >=32 strided))
+    generated A operand of segment 0 (see lass_conv_desc.gen_src)."""
     lib = _cabi.load()
     d = _cabi.ConvDesc()
     d.B, d.H, d.W, d.ncols, d.nseg = B, H, W, ncols, len(segments)
@@ -137,4 +139,12 @@ def conv_igemm(B, H, W, ncols, segments, bias=None, up=(1, 1), full_raw=None, fu
         d.resid_src, d.resid_in_scale, d.resid_in_shift = _ptr(src), _ptr(isc), _ptr(ish)
         d.resid_w, d.resid_b = _ptr(rw), _ptr(rb)
         d.resid_T, d.resid_F = src.shape[1], src.shape[2]
+    if gen is not None:
+        src, isc, ish, gw, gb, gsc, gsh = gen
+        _require_cuda(src, isc, ish, gw, gb, gsc)
+        assert gsh.is_cuda and gsh.stride(1) == 1   # a row-strided view of the shift table is fine
+        d.gen_src, d.gen_in_scale, d.gen_in_shift = _ptr(src), _ptr(isc), _ptr(ish)
+        d.gen_w, d.gen_b, d.gen_scale, d.gen_shift = _ptr(gw), _ptr(gb), _ptr(gsc), _ptr(gsh)
+        d.gen_shift_bstride = gsh.stride(0)
+        d.gen_T, d.gen_F = src.shape[1], src.shape[2]
     _cabi.check(lib.lass_conv_igemm(ctypes.byref(d), _stream()))

@@ -27,7 +27,7 @@ def lrelu_affine(v, scale, shift):  # v (B,C,H,W); scale (C); shift (B,C)
 
 def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0, up=(1, 1), pool=(1, 1),
              want_raw=True, want_act=True, want_pool=False, after=False, bias=False, out_cstride_mult=1, out_coff=0,
-             src_extra=0, seed=0, resid=False, algo=0):
+             src_extra=0, seed=0, resid=False, algo=0, gen=False):
     g = torch.Generator(device="cpu").manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=g)
     taps = 9 if up == (1, 1) else 1
@@ -46,6 +46,23 @@ def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0,
         w = (r(cin, cout, up[0], up[1]) / cin ** 0.5).to(src_dtype)
         wp = packing.pack_convT_weight(w.float(), src_dtype).to(dev)
         ref = F.conv_transpose2d(x, w.float().to(dev), None, stride=up)
+    gen_arg = None
+    if gen:
+        # generated A operand: x (B, cin = 32, H, W) = bf16(lrelu(gsc * (gw * m + gb) + gsh[b])) of a 1-channel map m with
+        # T < H valid rows (zero rows after the input affine) and F = W + 1 columns; the conv then reads no activation tensor
+        assert cin == 32 and taps == 9 and src_dtype == torch.bfloat16
+        T, Fm = H - 3, W + 1
+        g_src = r(B, T, Fm).to(dev)
+        g_isc, g_ish = (0.5 + torch.rand(Fm, generator=g)).to(dev), (0.1 * r(Fm)).to(dev)
+        g_w, g_b = r(cin).to(dev), (0.1 * r(cin)).to(dev)
+        g_sc = (0.5 + torch.rand(cin, generator=g)).to(dev)
+        g_sh = (0.2 * r(B, cin + 16)).to(dev)[:, 8:8 + cin]
+        m = torch.zeros(B, H, W, device=dev)
+        m[:, :T] = (g_src * g_isc + g_ish)[:, :, :W]
+        pre = g_w[None, :, None, None] * m[:, None] + g_b[None, :, None, None]
+        x = lrelu_affine(pre, g_sc, g_sh).to(torch.bfloat16).float()
+        ref = F.conv2d(x, w.float().to(dev), None, padding=1)
+        gen_arg = (g_src, g_isc, g_ish, g_w, g_b, g_sc, g_sh)
     segs = [ops.make_segment(src, coff, cin, wp, taps)]
     keep = [src, wp]
     if shortcut_cin:
@@ -99,7 +116,7 @@ def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0,
         outs["feat"] = torch.full((B, 3, H, W), 7.0, dtype=torch.float32, device=dev)
         kw.update(after_w=aw, after_b=ab, feat=outs["feat"])
     # shift tensor must be addressable with a row stride: pass the strided view directly
-    ops.conv_igemm(B, H, W, cout * nup, segs, bias=bias_t, up=up, resid=resid_arg, algo=algo, **kw)
+    ops.conv_igemm(B, H, W, cout * nup, segs, bias=bias_t, up=up, resid=resid_arg, algo=algo, gen=gen_arg, **kw)
     torch.cuda.synchronize()
     res = {}
     refn = nhwc(ref)
@@ -147,6 +164,8 @@ CASES = {
     "after": dict(B=2, H=32, W=16, cin=32, cout=32, shortcut_cin=64, bias=True, after=True, want_raw=False, want_act=False),
     "partial": dict(B=1, H=40, W=12, cin=64, cout=64),
     "fp16src": dict(B=1, H=32, W=16, cin=64, cout=64, src_dtype=torch.float16),
+    "gen_a": dict(B=3, H=64, W=24, cin=32, cout=32, gen=True, want_raw=False),
+    "gen_a_mt1": dict(B=2, H=48, W=12, cin=32, cout=32, gen=True, want_raw=False),
 }
 
 # the same cases through the dx-in-N formulation where it applies (3x3, Cout in {32, 64}, no upsampling, 2x2 pooling)

@@ -22,6 +22,7 @@ dev = "cuda"
 # conv into the concat buffers, last = decoder_block6 conv2 + after_conv
 LAYERS = {
     "enc0.c1 32->32 @1024x512": dict(kind="c1", H=1024, W=512, cin=32, cout=32),
+    "enc0.c1gen 1->32->32 @1024x512": dict(kind="c1", H=1024, W=512, cin=32, cout=32, gen=True),
     "enc0.c2 32->32+resid @1024x512": dict(kind="enc2", H=1024, W=512, cin=32, cout=32, sc=0),
     "enc1.c1 32->64 @512x256": dict(kind="c1", H=512, W=256, cin=32, cout=64),
     "enc1.c2 64->64+sc32 @512x256": dict(kind="enc2", H=512, W=256, cin=64, cout=64, sc=32),
@@ -42,7 +43,7 @@ NAMES = ["prod_wait_a_empty", "prod_wait_b_empty", "prod_total", "mma_wait_acc_e
          "mma_wait_b_full", "mma_total", "epi_wait_acc_full", "epi_total"]
 
 
-def build_layer(kind, H, W, cin, cout, sc=0):
+def build_layer(kind, H, W, cin, cout, sc=0, gen=False):
     """-> (ncols, segments, kwargs, flops, keep-alive list)"""
     keep = []
     src = torch.randn(B, H, W, cin, device=dev).to(torch.bfloat16)
@@ -68,6 +69,13 @@ def build_layer(kind, H, W, cin, cout, sc=0):
         kw["bias"] = torch.randn(cout, device=dev) * 0.1
         keep += [rawin, wsc, kw["bias"]]
     flops = 2.0 * B * H * W * cout * (9 * cin + sc)
+    if gen:   # encoder_block1 conv1: operand generated from the magnitude (bn0 + pre_conv + BN + FiLM + lrelu)
+        T, F = H - 23, W + 1
+        g = (torch.randn(B, T, F, device=dev), torch.rand(F, device=dev) + 0.5, torch.randn(F, device=dev) * 0.1,
+             torch.randn(cin, device=dev), torch.randn(cin, device=dev) * 0.1, torch.rand(cin, device=dev) + 0.5,
+             torch.randn(B, cin, device=dev) * 0.1)
+        kw["gen"] = g
+        keep += list(g)
     if kind in ("c1", "dec2"):
         act = torch.empty(B, H, W, cout, dtype=torch.bfloat16, device=dev)
         kw["full_act"] = ops.make_out(act, 0, scale, shift)
