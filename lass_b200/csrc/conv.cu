@@ -334,18 +334,41 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       // later, so the in-order warp never waits for them
       float gen_m[kGenPer], gen_s[kGenPer], gen_t[kGenPer];
       bool gen_have = false;
-      auto gen_load = [&](const Item& gi) {
-        const float* srcb = p.gen_src + (size_t)gi.b * p.gen_T * p.gen_F;
+      // per-lane constants of the kGenPer pixels this lane generates: (row, column) inside the halo tile and the element
+      // offset of the magnitude relative to the tile's first pixel -- the per-item address work is then one add per load
+      int gen_hh[kGenPer], gen_ww[kGenPer], gen_off[kGenPer];
 #pragma unroll
-        for (int i = 0; i < kGenPer; ++i) {
-          const int r = lane + 32 * i;
-          const int hh = (r * 205) >> 11, ww = r - hh * kHaloPitch;   // r / 10 for r < 1029
-          const int h = gi.h0 - 1 + hh, w = gi.w0 - 1 + ww;
-          const bool inside = r < kGenRows && h >= 0 && h < p.H && w >= 0 && w < p.W;
-          const bool live = inside && h < p.gen_T;                    // zero time padding AFTER bn0 (models/resunet.py:548)
-          gen_m[i] = live ? __ldg(srcb + (size_t)h * p.gen_F + w) : 0.0f;
-          gen_s[i] = live ? __ldg(p.gen_in_scale + w) : 0.0f;
-          gen_t[i] = inside ? (live ? __ldg(p.gen_in_shift + w) : 0.0f) : __int_as_float(0x7fc00000);   // NaN = outside the grid
+      for (int i = 0; i < kGenPer; ++i) {
+        const int r = lane + 32 * i;
+        gen_hh[i] = (r * 205) >> 11;                           // r / 10 for r < 1029
+        gen_ww[i] = r - gen_hh[i] * kHaloPitch;
+        gen_off[i] = gen_hh[i] * p.gen_F + gen_ww[i];
+      }
+      auto gen_load = [&](const Item& gi) {
+        const int h1 = gi.h0 - 1, w1 = gi.w0 - 1;              // first pixel of the halo tile
+        const float* base = p.gen_src + ((size_t)gi.b * p.gen_T + h1) * p.gen_F + w1;
+        const float* sc = p.gen_in_scale + w1;
+        const float* sh = p.gen_in_shift + w1;
+        // interior tile (every halo pixel inside the grid and above the time padding): no per-pixel tests
+        const bool interior = h1 >= 0 && w1 >= 0 && w1 + kHaloPitch <= p.W && h1 + 16 * MT + 2 <= min(p.H, p.gen_T);
+        if (interior) {
+#pragma unroll
+          for (int i = 0; i < kGenPer; ++i) {
+            const bool on = lane + 32 * i < kGenRows;
+            gen_m[i] = on ? __ldg(base + gen_off[i]) : 0.0f;
+            gen_s[i] = on ? __ldg(sc + gen_ww[i]) : 0.0f;
+            gen_t[i] = on ? __ldg(sh + gen_ww[i]) : 0.0f;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < kGenPer; ++i) {
+            const int h = h1 + gen_hh[i], w = w1 + gen_ww[i];
+            const bool inside = lane + 32 * i < kGenRows && h >= 0 && h < p.H && w >= 0 && w < p.W;
+            const bool live = inside && h < p.gen_T;                    // zero time padding AFTER bn0 (models/resunet.py:548)
+            gen_m[i] = live ? __ldg(base + gen_off[i]) : 0.0f;
+            gen_s[i] = live ? __ldg(sc + gen_ww[i]) : 0.0f;
+            gen_t[i] = inside ? (live ? __ldg(sh + gen_ww[i]) : 0.0f) : __int_as_float(0x7fc00000);   // NaN = outside the grid
+          }
         }
       };
       for (int item = (int)blockIdx.x + (dual ? (int)pw : 0) * (int)gridDim.x; item < p.num_items; item += step * (int)gridDim.x) {
