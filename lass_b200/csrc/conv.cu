@@ -174,8 +174,8 @@ __device__ __forceinline__ void pack_act32(const float* sc, const float* sh, con
     const float4 s = *reinterpret_cast<const float4*>(sh + j);
     const float t0 = fmaf(a.x, v[j + 0], s.x), t1 = fmaf(a.y, v[j + 1], s.y);
     const float t2 = fmaf(a.z, v[j + 2], s.z), t3 = fmaf(a.w, v[j + 3], s.w);
-    w[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
-    w[j / 2 + 1] = pack_bf16x2(fmaxf(t2, kSlope * t2), fmaxf(t3, kSlope * t3));
+    w[j / 2] = lrelu_bf16x2(pack_bf16x2(t0, t1));          // fp32 affine, LeakyReLU on the packed bf16 pair
+    w[j / 2 + 1] = lrelu_bf16x2(pack_bf16x2(t2, t3));
   }
 }
 
@@ -237,8 +237,8 @@ __device__ __forceinline__ void act_store32(const float* v, const float4* sc, co
   for (int j = 0; j < 8; ++j) {
     const float t0 = fmaf(sc[j].x, v[4 * j + 0], sh[j].x), t1 = fmaf(sc[j].y, v[4 * j + 1], sh[j].y);
     const float t2 = fmaf(sc[j].z, v[4 * j + 2], sh[j].z), t3 = fmaf(sc[j].w, v[4 * j + 3], sh[j].w);
-    w[2 * j] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
-    w[2 * j + 1] = pack_bf16x2(fmaxf(t2, kSlope * t2), fmaxf(t3, kSlope * t3));
+    w[2 * j] = lrelu_bf16x2(pack_bf16x2(t0, t1));          // fp32 affine, LeakyReLU on the packed bf16 pair
+    w[2 * j + 1] = lrelu_bf16x2(pack_bf16x2(t2, t3));
   }
   if (valid) {
     uint4* d = reinterpret_cast<uint4*>(dst);
@@ -860,7 +860,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                 for (int j = 0; j < 8; j += 2) {
                   const float t0 = fmaf(tb.sc_pool[c0 + cb + j], s2[j], tb.sh_pool[c0 + cb + j]);
                   const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], s2[j + 1], tb.sh_pool[c0 + cb + j + 1]);
-                  wv[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
+                  wv[j / 2] = lrelu_bf16x2(pack_bf16x2(t0, t1));
                 }
                 pact = make_uint4(wv[0], wv[1], wv[2], wv[3]);
               }
@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                 wr[j / 2] = pack_f16x2_sat(u0, u1);
                 const float t0 = fmaf(tb.sc_pool[c0 + cb + j], u0, tb.sh_pool[c0 + cb + j]);
                 const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], u1, tb.sh_pool[c0 + cb + j + 1]);
-                wa[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
+                wa[j / 2] = lrelu_bf16x2(pack_bf16x2(t0, t1));
               }
               if (FEAT(kFTmaPool, tma_pool)) {
                 if (FEAT(kFPoolRaw, p.pool_raw.ptr != nullptr)) {
