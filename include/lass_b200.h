@@ -248,7 +248,7 @@ LASS_API int lass_resunet30_plan_create(const lass_resunet30_weights* weights_ho
  *   (models/resunet.py:685-688); `condition` may then be NULL.
  * stft_precision_mode: 0 = fp32-parity STFT, 1 = single-pass bf16 STFT.  Asynchronous on `stream`.
  * lass_resunet30_forward_stages runs a subset (bit mask) of the three stages so a caller can bracket them with
- * its own CUDA events: LASS_STAGE_FRONT (STFT, FiLM, bn0 + pre_conv), LASS_STAGE_UNET (all convolutions),
+ * its own CUDA events: LASS_STAGE_FRONT (STFT, FiLM), LASS_STAGE_UNET (all convolutions, incl. the fused bn0 + pre_conv),
  * LASS_STAGE_BACK (mask + iSTFT).  lass_resunet30_forward == all stages. */
 #define LASS_STAGE_FRONT 1
 #define LASS_STAGE_UNET 2

@@ -1,4 +1,6 @@
 #!/bin/bash
+# dev loop for the conv kernel: conv + forward parity tests, knock-out timings of plan-configured launches
+# (TFLAGS / TFILTER), per-launch times of the whole model and a short bench.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_forward.py -x -q > gpurun_out/pytest_conv.log 2>&1; tail -3 gpurun_out/pytest_conv.log

@@ -1,4 +1,5 @@
 #!/bin/bash
+# dev loop: forward parity tests with the SNR printed, per-launch times, short bench.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_conv.py tests/test_gpu_forward.py -x -q -s 2>&1 | grep -i "snr\|passed\|failed" | cut -c1-200
