@@ -1775,7 +1775,10 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   // issuer and short items, and for N = 256 tiles, where a weight ring of two 32 KiB stages per issuer is too shallow.
   p.dual_issue = 0;
   if (!(g_debug_flags & 128)) {
-    if (p.b_resident) p.dual_issue = p.a_stages >= 4 ? 1 : 0;
+    // ... or, with one A stage per issuer, for the longer resident items without pooled outputs (measured: the 128 -> 64
+    // decoder conv -10 %, the 64 -> 64 + shortcut one -3 %; the encoder conv2 launches and short items lose)
+    if (p.b_resident)
+      p.dual_issue = (p.a_stages >= 4 || (p.a_stages >= 2 && b_tiles_per_item >= 11 && !l.pool_raw.ptr && !l.pool_act.ptr)) ? 1 : 0;
     else p.dual_issue = (BN <= 128 && p.b_stages >= 4 && b_tiles_per_item >= 36) ? 1 : 0;
   }
   if (p.dual_issue) {
