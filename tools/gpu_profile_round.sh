@@ -9,7 +9,7 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${TAG}_reference.json 2>> gpurun_out/bench_$TAG.err
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-spectral"
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
-    -k regex:"conv_igemm|stft|mask_istft|film|preconv" -s 111 -c 37 --csv --log-file gpurun_out/step_launches_$TAG.csv $CMD > gpurun_out/ncu_a.log 2>&1
+    -k regex:"conv_igemm|stft|mask_istft|film|preconv" -s 108 -c 36 --csv --log-file gpurun_out/step_launches_$TAG.csv $CMD > gpurun_out/ncu_a.log 2>&1
 echo "ncu launch list $?"
 for spec in "enc0c2|enc0.c2" "dec5c1|dec5.c1" "dec2c1|dec2.c1"; do
   tag=${spec%%|*}; L=${spec#*|}
