@@ -107,6 +107,7 @@ struct ConvParams {
   int a_stages, b_stages, b_resident;
   int epi_mode;    // conv_igemm_kernel: 0 = generic epilogue (run-time feature tests), 1 = lean path (one activated bf16 output,
                    // direct stores), 2..6 = generic code specialised at compile time for a feature set (see kFEnc2Resid ...)
+  int cg2;         // conv_igemm_kernel: CTA pairs (cluster of 2, tcgen05 cta_group::2) -- streamed weights, N >= 128
   int dual_issue;  // conv_igemm_kernel: two MMA-issuing warps, each with half of the A ring (resident weights, >= 4 A stages)
   int tma_store;   // 1: full-resolution 16-bit outputs leave through per-warp shared-memory staging + TMA stores
   int tma_pool;    // 1: pooled outputs too (only when they are channel slices; whole-pixel pooled outputs store directly)
@@ -249,8 +250,9 @@ __device__ __forceinline__ void act_store32(const float* v, const float4* sc, co
   }
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool CG2 = false>
 __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+  static_assert(!CG2 || BN >= 128, "CTA pairs are instantiated for the N >= 128 tiles only");
   // accumulator ring: item n of this CTA uses stage n % NS; MMA warp (n & 1) issues it, epilogue group (n & 1) drains it.
   // Four stages where they fit in 256 columns, so that the MMAs of item n + 2 do not have to wait for the epilogue of item n.
   constexpr int NS = acc_stages(BN, MT);
@@ -277,6 +279,25 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA-pair mode (p.cg2, thread-block cluster of 2, tcgen05 cta_group::2): the two CTAs take two pixel tiles of the SAME
+  // N tile; every MMA covers both (M = 256) and each CTA holds only half of the weight rows, so the operand reads per CTA
+  // drop from 4 KiB + 32 N to 4 KiB + 16 N bytes per MMA (shared-memory bandwidth is what bounds the N >= 128 layers).  The
+  // leader CTA (rank 0) issues the MMAs and owns the full / acc_empty barriers; both CTAs load, and drain their own TMEM.
+  constexpr bool cg2 = CG2;        // compile time: the single-CTA instantiations carry none of the pair code
+  const uint32_t crank = cg2 ? cluster_ctarank() : 0u;
+  // the item loops below run over VIRTUAL indices: a pair shares one index and decodes it to two neighbouring pixel tiles
+  const int vbid = cg2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int vgrid = cg2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int vitems = cg2 ? p.num_items >> 1 : p.num_items;
+  auto dec = [&](int v) {
+    int item = v;
+    if (cg2) {
+      const int half = p.pix_tiles >> 1;
+      const int nt = v / half;
+      item = nt * p.pix_tiles + 2 * (v - nt * half) + (int)crank;
+    }
+    return decode_item<MT>(p, item, BN);
+  };
   const bool prof = LASS_PROF_ON(p);
   long long pc[kProfSlots];
 #pragma unroll
@@ -298,13 +319,19 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
     }
     for (int s = 0; s < NS; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kSplitMT ? 8 : 4);
+      mbar_init(&acc_empty[s], (kSplitMT ? 8 : 4) * (cg2 ? 2 : 1));     // pair: the epilogue warps of both CTAs arrive
     }
     fence_mbar_init();
   }
+  if (cg2) cluster_sync_all();      // both CTAs' barriers exist before any remote arrive / transaction lands on them
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (cg2) {
+      tmem_alloc_cg2(tmem_slot, kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -371,8 +398,8 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           }
         }
       };
-      for (int item = (int)blockIdx.x + (dual ? (int)pw : 0) * (int)gridDim.x; item < p.num_items; item += step * (int)gridDim.x) {
-        const Item it = decode_item<MT>(p, item, BN);
+      for (int item = vbid + (dual ? (int)pw : 0) * vgrid; item < vitems; item += step * vgrid) {
+        const Item it = dec(item);
         uint32_t b_slot_res = 0;
         for (int s = 0; s < p.nseg; ++s) {
           const SegDev& sg = p.seg[s];
@@ -407,9 +434,9 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
               for (int i = 0; i < kGenPer; ++i) xs[i] = fmaf(gen_s[i], gen_m[i], gen_t[i]);
               {
                 // prefetch the magnitudes of this producer's NEXT item: their latency hides behind the tile written below
-                const int nxt = item + step * (int)gridDim.x;
-                gen_have = nxt < p.num_items;
-                if (gen_have) gen_load(decode_item<MT>(p, nxt, BN));
+                const int nxt = item + step * vgrid;
+                gen_have = nxt < vitems;
+                if (gen_have) gen_load(dec(nxt));
               }
 #pragma unroll
               for (int i = 0; i < kGenPer; ++i) {
@@ -441,6 +468,11 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
             } else if (elect_one()) {
               if (p.debug_flags & 4) {
                 mbar_arrive(&a_full[sa]);
+              } else if (cg2) {
+                // both CTAs load their own tile; the bytes of both are counted on the LEADER's barrier
+                if (crank == 0) mbar_arrive_expect_tx(&a_full[sa], 2 * a_bytes);
+                tma_load_4d_cg2(a_buf + (size_t)sa * p.a_stage_bytes, &sg.tmA, mapa_shared(smem_u32(&a_full[sa]), 0), ch * sg.kc,
+                                halo ? it.w0 - 1 : it.w0, halo ? it.h0 - 1 : it.h0, it.b);
               } else {
                 mbar_arrive_expect_tx(&a_full[sa], a_bytes);
                 tma_load_4d(a_buf + (size_t)sa * p.a_stage_bytes, &sg.tmA, &a_full[sa], ch * sg.kc,
@@ -465,8 +497,15 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                 const uint32_t sb = b0 + b_it % ring_b;
                 LASS_TIMED_WAIT_RELAXED(&b_empty[sb], ((b_it / ring_b) & 1) ^ 1, kProfProdBEmpty);
                 if (elect_one()) {
-                  mbar_arrive_expect_tx(&b_full[sb], b_bytes);
-                  tma_load_3d(b_buf + (size_t)sb * p.b_stage_bytes, &sg.tmB, &b_full[sb], ch * sg.kc, it.n0, tp);
+                  if (cg2) {
+                    // each CTA holds half of the tile's weight rows: rows [n0 + rank * BN/2, + BN/2)
+                    if (crank == 0) mbar_arrive_expect_tx(&b_full[sb], b_bytes);
+                    tma_load_3d_cg2(b_buf + (size_t)sb * p.b_stage_bytes, &sg.tmB, mapa_shared(smem_u32(&b_full[sb]), 0),
+                                    ch * sg.kc, it.n0 + (int)crank * (BN / 2), tp);
+                  } else {
+                    mbar_arrive_expect_tx(&b_full[sb], b_bytes);
+                    tma_load_3d(b_buf + (size_t)sb * p.b_stage_bytes, &sg.tmB, &b_full[sb], ch * sg.kc, it.n0, tp);
+                  }
                 }
                 __syncwarp();
                 ++b_it;
@@ -507,7 +546,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       const uint32_t n_b = (dual && p.b_resident == 0) ? (uint32_t)p.b_stages >> 1 : (uint32_t)p.b_stages;
       const uint32_t ring0 = dual ? mw * n_a : 0u;   // first stage of this issuer's part of the A ring
       const uint32_t bring0 = (dual && p.b_resident == 0) ? mw * n_b : 0u;   // ... and of the streamed-weight ring
-      const bool resident = p.b_resident != 0;
+      const bool resident = !cg2 && p.b_resident != 0;     // CTA pairs always stream their weights
       const bool no_mma = (p.debug_flags & 2) != 0;
       // per-segment constants, hoisted out of the item loop
       SegMma g[2];
@@ -520,7 +559,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
         const uint32_t swz = kc == 64 ? kSwizzle128B : kSwizzle64B;
         g[s].a_hi = static_cast<uint32_t>(make_smem_desc(0, (halo ? kHaloPitch : TW) * kc * 2, swz) >> 32);
         g[s].b_hi = static_cast<uint32_t>(make_smem_desc(0, 8 * kc * 2, swz) >> 32);
-        g[s].idesc = make_idesc_f16(on ? p.seg[s].fmt : 0, on ? p.seg[s].fmt : 0, 128, BN);
+        g[s].idesc = make_idesc_f16(on ? p.seg[s].fmt : 0, on ? p.seg[s].fmt : 0, cg2 ? 256 : 128, BN);
         seg_kc[s] = kc;
         seg_chunks[s] = on ? p.seg[s].nchunks : 0;
         seg_halo[s] = halo;
@@ -531,8 +570,8 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       bool first_item = true;
       const int step = dual ? 2 : 1;
       uint32_t n = dual ? mw : 0u;      // index of the item within this CTA's sequence
-      for (int item = (dual || mw == 0) ? (int)blockIdx.x + (int)n * (int)gridDim.x : p.num_items; item < p.num_items;
-           item += step * (int)gridDim.x, n += step) {
+      for (int item = ((dual || mw == 0) && crank == 0) ? vbid + (int)n * vgrid : vitems; item < vitems;
+           item += step * vgrid, n += step) {
         const uint32_t as = n % NS, pacc = (n / NS) & 1u;
         if (!mma_only) LASS_TIMED_WAIT(&acc_empty[as], pacc ^ 1, kProfMmaAccEmpty);
         tc_fence_after_sync();
@@ -579,15 +618,23 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                   tc_fence_after_sync();
                   const uint32_t b_lo = (b_base16 + (bring0 + sb) * b_stage16) | kLbo;
                   if (!no_mma && elect_one()) {
-                    if (kc == 64) issue_tap<MT, BN, 4>(acc_addr, a_lo + dx * 8, mt_step16, b_lo, gs, accumulate);
-                    else issue_tap<MT, BN, 2>(acc_addr, a_lo + dx * 4, mt_step16, b_lo, gs, accumulate);
+                    if (cg2) {
+                      if (kc == 64) issue_tap<MT, BN, 4, true>(acc_addr, a_lo + dx * 8, mt_step16, b_lo, gs, accumulate);
+                      else issue_tap<MT, BN, 2, true>(acc_addr, a_lo + dx * 4, mt_step16, b_lo, gs, accumulate);
+                    } else {
+                      if (kc == 64) issue_tap<MT, BN, 4>(acc_addr, a_lo + dx * 8, mt_step16, b_lo, gs, accumulate);
+                      else issue_tap<MT, BN, 2>(acc_addr, a_lo + dx * 4, mt_step16, b_lo, gs, accumulate);
+                    }
                   }
                   __syncwarp();
                   accumulate = 1;
                   if (resident) {
                     ++sb;
                   } else {
-                    if (elect_one()) umma_commit(&b_empty[bring0 + sb]);
+                    if (elect_one()) {
+                      if (cg2) umma_commit_cg2(&b_empty[bring0 + sb]);
+                      else umma_commit(&b_empty[bring0 + sb]);
+                    }
                     __syncwarp();
                     if (++sb == n_b) {
                       sb = 0;
@@ -598,7 +645,10 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                 a_lo += pitch * row16;
               }
             }
-            if (elect_one()) umma_commit(&a_empty[ring0 + sa]);
+            if (elect_one()) {
+              if (cg2) umma_commit_cg2(&a_empty[ring0 + sa]);
+              else umma_commit(&a_empty[ring0 + sa]);
+            }
             __syncwarp();
             if (++sa == n_a) {
               sa = 0;
@@ -606,7 +656,10 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
             }
           }
         }
-        if (elect_one()) umma_commit(&acc_full[as]);
+        if (elect_one()) {
+          if (cg2) umma_commit_cg2(&acc_full[as]);
+          else umma_commit(&acc_full[as]);
+        }
         __syncwarp();
         ++n_items;
         first_item = false;
@@ -655,10 +708,10 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       const int cstride = p.full_act.cstride;
       const bool idle = (p.debug_flags & 1) != 0;
       if (kSplitMT) n = 0;
-      for (int item = blockIdx.x + (kSplitMT ? 0 : grp) * (int)gridDim.x; item < p.num_items;
-           item += (kSplitMT ? 1 : 2) * (int)gridDim.x, n += (kSplitMT ? 1 : 2)) {
+      for (int item = vbid + (kSplitMT ? 0 : grp) * vgrid; item < vitems;
+           item += (kSplitMT ? 1 : 2) * vgrid, n += (kSplitMT ? 1 : 2)) {
         const uint32_t as = n % NS, acc_parity = (n / NS) & 1u;
-        const Item it = decode_item<MT>(p, item, BN);
+        const Item it = dec(item);
         if (it.b != tab_b || it.n0 != tab_n0) {
           tab_sel ^= 1u;
           EpiTables<BN>& t = gtabs[tab_sel];
@@ -709,7 +762,10 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
         }
         tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[as]);
+        if (lane == 0) {
+          if (cg2 && crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[as]), 0));   // the leader's barrier
+          else mbar_arrive(&acc_empty[as]);
+        }
       }
     } else {
     auto generic_items = [&](auto ftag) {
@@ -718,10 +774,10 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
     constexpr uint32_t F = decltype(ftag)::value;
 #define FEAT(bit, cond) ((F == kFGeneric) ? (cond) : ((F & (bit)) != 0u))
     if (kSplitMT) n = 0;
-    for (int item = blockIdx.x + (kSplitMT ? 0 : grp) * (int)gridDim.x; item < p.num_items;
-         item += (kSplitMT ? 1 : 2) * (int)gridDim.x, n += (kSplitMT ? 1 : 2)) {
+    for (int item = vbid + (kSplitMT ? 0 : grp) * vgrid; item < vitems;
+         item += (kSplitMT ? 1 : 2) * vgrid, n += (kSplitMT ? 1 : 2)) {
       const uint32_t as = n % NS, acc_parity = (n / NS) & 1u;
-      const Item it = decode_item<MT>(p, item, BN);
+      const Item it = dec(item);
       // ---- (re)stage the per-(clip, N tile) tables; double-buffered so one named barrier per change suffices ----
       if (it.b != tab_b || it.n0 != tab_n0) {
         tab_sel ^= 1u;
@@ -984,7 +1040,10 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (lane == 0) {
+          if (cg2 && crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[as]), 0));   // the leader's barrier
+          else mbar_arrive(&acc_empty[as]);
+        }
     }
 #undef FEAT
     };
@@ -1006,10 +1065,12 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (cg2) cluster_sync_all();      // the peer's MMAs / remote arrivals are done before shared memory and TMEM go away
   if (warp == 2) {
     __syncwarp();
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (cg2) tmem_dealloc_cg2(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -1390,9 +1451,9 @@ struct KernelChoice {
   int BN, MT;
 };
 
-template <int BN, int MT>
+template <int BN, int MT, bool CG2 = false>
 KernelChoice make_choice() {
-  return KernelChoice{conv_igemm_kernel<BN, MT>, BN, MT};
+  return KernelChoice{conv_igemm_kernel<BN, MT, CG2>, BN, MT};
 }
 
 int g_debug_flags = 0;
@@ -1406,6 +1467,7 @@ struct ConvPrepared {
   ConvKernelFn fn;
   int grid;
   int threads;
+  int cluster;   // 2: launched as thread-block clusters of two CTAs (params.cg2)
   size_t smem;
 };
 
@@ -1627,6 +1689,10 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   else if (BN == 64) kc = MT == 2 ? make_choice<64, 2>() : make_choice<64, 1>();
   else if (BN == 128) kc = MT == 2 ? make_choice<128, 2>() : make_choice<128, 1>();
   else kc = MT == 2 ? make_choice<256, 2>() : make_choice<256, 1>();
+  // CTA-pair variants (cta_group::2) of the N >= 128 tiles, taken below when the weights are streamed
+  KernelChoice kc_pair = kc;
+  if (BN == 128) kc_pair = MT == 2 ? make_choice<128, 2, true>() : make_choice<128, 1, true>();
+  else if (BN == 256 && MT == 1) kc_pair = make_choice<256, 1, true>();
 
   ConvPrepared* cp = new (std::nothrow) ConvPrepared();
   if (!cp) return set_error(LASS_ERR_ARG, "conv: out of host memory");
@@ -1769,6 +1835,39 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     if (p.b_stages > 12) p.b_stages = 12;
     if (p.b_stages >= 5 || !p.tma_store) break;      // staging would starve the weight ring: fall back to direct stores
   }
+  // CTA pairs for streamed weights with N >= 128 (debug flag 4096 switches them off): two neighbouring pixel tiles of one
+  // N tile per pair, every MMA M = 256 over both CTAs, each CTA streams and holds only HALF of every weight tile -- the
+  // operand reads per CTA and MMA drop from 4 KiB + 32 N to 4 KiB + 16 N bytes and the weight fill per CTA halves.
+  p.cg2 = 0;
+  // Not for the transposed convs: they are bound by their stores, and the coupled pair loses (measured +12 %).
+  if (!p.b_resident && BN >= 128 && kc_pair.fn != kc.fn && (p.pix_tiles % 2) == 0 && !l.gen_src && !(g_debug_flags & 4096) &&
+      l.ncols % BN == 0 && up == 1) {
+    p.cg2 = 1;
+    uint32_t b_half = 0;
+    for (int s = 0; s < l.nseg; ++s) {
+      const ConvSegment& sg = l.seg[s];
+      const CUtensorMapSwizzle swz = sg.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+      uint64_t dims[3] = {(uint64_t)sg.cin, (uint64_t)l.ncols, (uint64_t)sg.taps};
+      uint64_t strides[2] = {(uint64_t)sg.cin * 2, (uint64_t)sg.cin * 2 * l.ncols};
+      uint32_t box[3] = {(uint32_t)sg.kc, (uint32_t)(BN / 2), 1};
+      if ((e = make_tensor_map(&p.seg[s].tmB, sg.weights, 2, 3, dims, strides, box, swz))) {
+        delete cp;
+        return e;
+      }
+      if ((uint32_t)(BN / 2) * sg.kc * 2 > b_half) b_half = (uint32_t)(BN / 2) * sg.kc * 2;
+    }
+    p.b_stage_bytes = (b_half + 1023u) & ~1023u;
+    const size_t min_a = 2 * (size_t)p.a_stage_bytes;
+    size_t rest = kBudget > fixed + min_a ? kBudget - fixed - min_a : 0;
+    // what the halved weight stages free goes to a third A stage first, then to a deeper weight ring
+    if (rest >= (size_t)p.a_stage_bytes + 8 * (size_t)p.b_stage_bytes) {
+      p.a_stages = 3;
+      rest -= p.a_stage_bytes;
+    }
+    p.b_stages = (int)(rest / p.b_stage_bytes);
+    if (p.b_stages > 16) p.b_stages = 16;
+    kc = kc_pair;
+  }
   // Two MMA issuers + two producers, each pair with half of the rings.  Measured per layer (tools/gpu_conv_timing.py):
   // a win when every issuer keeps two A stages (resident weights, >= 4 stages), and for streamed weights with N <= 128 and
   // long items (>= 36 weight tiles: the second issuer hides the per-tap ring handshakes); a loss with one A stage per
@@ -1779,7 +1878,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     // decoder conv -10 %, the 64 -> 64 + shortcut one -3 %; the encoder conv2 launches and short items lose)
     if (p.b_resident)
       p.dual_issue = (p.a_stages >= 4 || (p.a_stages >= 2 && b_tiles_per_item >= 11 && !l.pool_raw.ptr && !l.pool_act.ptr)) ? 1 : 0;
-    else p.dual_issue = (BN <= 128 && p.b_stages >= 4 && b_tiles_per_item >= 36) ? 1 : 0;
+    else p.dual_issue = ((BN <= 128 || (p.cg2 && (g_debug_flags & 8192))) && p.b_stages >= 4 && b_tiles_per_item >= 36) ? 1 : 0;
   }
   if (p.dual_issue) {
     p.a_stages &= ~1;
@@ -1869,11 +1968,52 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   if (per_sm > 512 / tmem_need) per_sm = 512 / tmem_need;
   if (per_sm > 2) per_sm = 2;
   cp->grid = p.num_items < g_num_sms * per_sm ? p.num_items : g_num_sms * per_sm;
+  cp->cluster = 1;
+  if (p.cg2) {
+    // one pair per TPC: as many clusters as the device keeps resident at once (persistent CTAs, static round robin)
+    cp->cluster = 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (unsigned)(g_num_sms / 2), 1, 1);
+    cfg.blockDim = dim3(kThreadsK, 1, 1);
+    cfg.dynamicSmemBytes = cp->smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    int pairs = 0;
+    if (cudaOccupancyMaxActiveClusters(&pairs, reinterpret_cast<const void*>(kc.fn), &cfg) != cudaSuccess || pairs < 1) {
+      cudaGetLastError();
+      pairs = g_num_sms / 2;
+    }
+    if (pairs > g_num_sms / 2) pairs = g_num_sms / 2;
+    const int vitems = p.num_items / 2;
+    cp->grid = 2 * (vitems < pairs ? vitems : pairs);
+  }
   *out = cp;
   return 0;
 }
 
 int conv_run(const ConvPrepared* cp, cudaStream_t stream) {
+  if (cp->cluster == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)cp->grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)cp->threads, 1, 1);
+    cfg.dynamicSmemBytes = cp->smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return set_cuda_error(cudaLaunchKernelEx(&cfg, cp->fn, cp->params), "conv launch (CTA pairs)");
+  }
   cp->fn<<<cp->grid, cp->threads, cp->smem, stream>>>(cp->params);
   return set_cuda_error(cudaGetLastError(), "conv launch");
 }

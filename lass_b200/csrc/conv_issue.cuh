@@ -23,6 +23,23 @@ __device__ __forceinline__ void umma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32
       : "memory");
 }
 
+// The same for a CTA pair (cta_group::2, M = 256: 128 rows from each CTA's shared memory at these offsets, each CTA holds
+// half of the N weight rows); issued by the leader CTA only.
+__device__ __forceinline__ void umma_lohi_cg2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Per-segment constants of the MMA issuer (uniform registers).
 struct SegMma {
   uint32_t a_hi, b_hi;      // descriptor high words
@@ -31,15 +48,20 @@ struct SegMma {
 
 // All MMAs of one (chunk, tap) for MT m-tiles: KSTEPS k-steps of 16 channels each.  a_lo / b_lo already contain the
 // LBO field; start addresses advance by 2 (x16 B) per k-step and by mt_step16 per m-tile.
-template <int MT, int BN, int KSTEPS>
+template <int MT, int BN, int KSTEPS, bool CG2 = false>
 __device__ __forceinline__ void issue_tap(uint32_t acc, uint32_t a_lo, uint32_t mt_step16, uint32_t b_lo, const SegMma& g,
                                           uint32_t accumulate) {
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
-    for (int ks = 0; ks < KSTEPS; ++ks)
-      umma_lohi(acc + mt * BN, a_lo + mt * mt_step16 + 2 * ks, g.a_hi, b_lo + 2 * ks, g.b_hi, g.idesc,
-                ks == 0 ? accumulate : 1u);
+    for (int ks = 0; ks < KSTEPS; ++ks) {
+      if (CG2)
+        umma_lohi_cg2(acc + mt * BN, a_lo + mt * mt_step16 + 2 * ks, g.a_hi, b_lo + 2 * ks, g.b_hi, g.idesc,
+                      ks == 0 ? accumulate : 1u);
+      else
+        umma_lohi(acc + mt * BN, a_lo + mt * mt_step16 + 2 * ks, g.a_hi, b_lo + 2 * ks, g.b_hi, g.idesc,
+                  ks == 0 ? accumulate : 1u);
+    }
   }
 }
 

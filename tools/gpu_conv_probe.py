@@ -10,7 +10,7 @@ import torch.nn.functional as F
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from lass_b200 import ops, packing  # noqa: E402
+from lass_b200 import _cabi, ops, packing  # noqa: E402
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -27,7 +27,7 @@ def lrelu_affine(v, scale, shift):  # v (B,C,H,W); scale (C); shift (B,C)
 
 def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0, up=(1, 1), pool=(1, 1),
              want_raw=True, want_act=True, want_pool=False, after=False, bias=False, out_cstride_mult=1, out_coff=0,
-             src_extra=0, seed=0, resid=False, algo=0, gen=False):
+             src_extra=0, seed=0, resid=False, algo=0, gen=False, flags=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=g)
     taps = 9 if up == (1, 1) else 1
@@ -116,8 +116,14 @@ def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0,
         outs["feat"] = torch.full((B, 3, H, W), 7.0, dtype=torch.float32, device=dev)
         kw.update(after_w=aw, after_b=ab, feat=outs["feat"])
     # shift tensor must be addressable with a row stride: pass the strided view directly
-    ops.conv_igemm(B, H, W, cout * nup, segs, bias=bias_t, up=up, resid=resid_arg, algo=algo, gen=gen_arg, **kw)
-    torch.cuda.synchronize()
+    if flags:
+        _cabi.check(_cabi.load().lass_debug_set_conv_flags(flags))   # e.g. 4096: no CTA pairs (the single-CTA streamed path)
+    try:
+        ops.conv_igemm(B, H, W, cout * nup, segs, bias=bias_t, up=up, resid=resid_arg, algo=algo, gen=gen_arg, **kw)
+        torch.cuda.synchronize()
+    finally:
+        if flags:
+            _cabi.check(_cabi.load().lass_debug_set_conv_flags(0))
     res = {}
     refn = nhwc(ref)
     sl = slice(out_coff, out_coff + cout)
@@ -174,6 +180,16 @@ for _name in ("c32_32", "c32_32_mt1", "c32_64", "c64_64", "c64_32", "pool32_wide
     CASES["dxn_" + _name] = dict(CASES[_name], algo=1)
 CASES["dxn_c128_64"] = dict(B=1, H=32, W=32, cin=128, cout=64, algo=1)
 CASES["dxn_sc128_64"] = dict(B=2, H=16, W=48, cin=64, cout=64, shortcut_cin=128, bias=True, want_raw=False, algo=1)
+
+# Streamed weights with N >= 128 run as CTA pairs (tcgen05 cta_group::2) when the pixel tiles pair up: longer item
+# sequences per pair, several N tiles, pooled / sliced / transposed outputs -- and the single-CTA streamed path (debug flag 4096)
+CASES["pair_c128_128_long"] = dict(B=6, H=128, W=64, cin=128, cout=128, want_raw=False)
+CASES["pair_c256_256_long"] = dict(B=5, H=64, W=64, cin=256, cout=256, want_raw=False)
+CASES["pair_c512_256"] = dict(B=2, H=32, W=32, cin=512, cout=256, shortcut_cin=512, bias=True)
+CASES["pair_c384_384_sc"] = dict(B=4, H=32, W=16, cin=384, cout=384, shortcut_cin=256, bias=True, want_pool=True, pool=(2, 2))
+CASES["pair_slice"] = dict(B=2, H=32, W=32, cin=256, cout=128, out_cstride_mult=2, out_coff=128)
+for _name in ("c128_128", "c768_384", "c256_256", "sc_pool12", "sc_big", "pair_c384_384_sc", "pair_c512_256"):
+    CASES["nopair_" + _name] = dict(CASES[_name], flags=4096)
 
 if __name__ == "__main__":
     pitch = int(sys.argv[1])   # kept for the log name; the halo pitch is fixed at 10 pixels

@@ -10,6 +10,9 @@ from oracle import factory
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 tag = sys.argv[2] if len(sys.argv) > 2 else "cur"
 L = 160000
+if os.environ.get("LASS_CONV_FLAGS"):      # debug flags of the conv kernel, read when the launches are prepared (e.g. 4096: no CTA pairs)
+    from lass_b200 import _cabi
+    _cabi.check(_cabi.load().lass_debug_set_conv_flags(int(os.environ["LASS_CONV_FLAGS"], 0)))
 torch.manual_seed(0)
 m = ResUNet30(1, 1, 512).eval()
 m.load_state_dict(factory.fill_state_dict(m.state_dict(), seed=0))
