@@ -165,7 +165,9 @@ typedef struct lass_conv_desc {
 LASS_API int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream);
 
 /* Debug: timing experiments on the conv kernel (results become wrong): bit 0 = epilogue skips math and stores,
- * bit 1 = no tcgen05.mma issued, bit 2 = no activation (A) TMA loads.  0 = normal operation. */
+ * bit 1 = no tcgen05.mma issued, bit 2 = no activation (A) TMA loads.  Bit 12 (4096) keeps results correct: launches
+ * prepared while it is set do not use CTA pairs (tcgen05 cta_group::2), i.e. streamed weights take the single-CTA path --
+ * used by the parity tests to cover both.  0 = normal operation. */
 LASS_API int lass_debug_set_conv_flags(int flags);
 /* Debug: per-CTA role profile of subsequently PREPARED conv launches.  device_counters: >= 16 int64 per CTA
  * (<= 296 CTAs), clock cycles: [0] producer waits for a free A stage, [1] for a free B stage, [2] producer total,

@@ -1858,12 +1858,8 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     }
     p.b_stage_bytes = (b_half + 1023u) & ~1023u;
     const size_t min_a = 2 * (size_t)p.a_stage_bytes;
-    size_t rest = kBudget > fixed + min_a ? kBudget - fixed - min_a : 0;
-    // what the halved weight stages free goes to a third A stage first, then to a deeper weight ring
-    if (rest >= (size_t)p.a_stage_bytes + 8 * (size_t)p.b_stage_bytes) {
-      p.a_stages = 3;
-      rest -= p.a_stage_bytes;
-    }
+    const size_t rest = kBudget > fixed + min_a ? kBudget - fixed - min_a : 0;
+    // what the halved weight stages free goes to a deeper weight ring (a third A stage instead: no gain, measured)
     p.b_stages = (int)(rest / p.b_stage_bytes);
     if (p.b_stages > 16) p.b_stages = 16;
     kc = kc_pair;
@@ -1878,7 +1874,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     // decoder conv -10 %, the 64 -> 64 + shortcut one -3 %; the encoder conv2 launches and short items lose)
     if (p.b_resident)
       p.dual_issue = (p.a_stages >= 4 || (p.a_stages >= 2 && b_tiles_per_item >= 11 && !l.pool_raw.ptr && !l.pool_act.ptr)) ? 1 : 0;
-    else p.dual_issue = ((BN <= 128 || (p.cg2 && (g_debug_flags & 8192))) && p.b_stages >= 4 && b_tiles_per_item >= 36) ? 1 : 0;
+    else p.dual_issue = (BN <= 128 && p.b_stages >= 4 && b_tiles_per_item >= 36) ? 1 : 0;
   }
   if (p.dual_issue) {
     p.a_stages &= ~1;
