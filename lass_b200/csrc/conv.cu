@@ -105,6 +105,8 @@ struct ConvParams {
   int B, H, W, ncols;
   int tiles_h, tiles_w, pix_tiles, n_tiles, num_items;
   int a_stages, b_stages, b_resident;
+  int b_tps;       // streamed weights: taps per weight stage of a 3x3 segment (1, or 3 = the three taps of a kernel row in one
+                   // TMA box and one full / empty handshake)
   int epi_mode;    // conv_igemm_kernel: 0 = generic epilogue (run-time feature tests), 1 = lean path (one activated bf16 output,
                    // direct stores), 2..6 = generic code specialised at compile time for a feature set (see kFEnc2Resid ...)
   int cg2;         // conv_igemm_kernel: CTA pairs (cluster of 2, tcgen05 cta_group::2) -- streamed weights, N >= 128
@@ -493,17 +495,18 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                 }
               }
             } else {
-              for (int tp = 0; tp < sg.taps; ++tp) {
+              const int tps = halo ? p.b_tps : 1;         // taps per stage: the box of tmB covers tps taps
+              for (int tp = 0; tp < sg.taps; tp += tps) {
                 const uint32_t sb = b0 + b_it % ring_b;
                 LASS_TIMED_WAIT_RELAXED(&b_empty[sb], ((b_it / ring_b) & 1) ^ 1, kProfProdBEmpty);
                 if (elect_one()) {
                   if (cg2) {
                     // each CTA holds half of the tile's weight rows: rows [n0 + rank * BN/2, + BN/2)
-                    if (crank == 0) mbar_arrive_expect_tx(&b_full[sb], b_bytes);
+                    if (crank == 0) mbar_arrive_expect_tx(&b_full[sb], (uint32_t)tps * b_bytes);
                     tma_load_3d_cg2(b_buf + (size_t)sb * p.b_stage_bytes, &sg.tmB, mapa_shared(smem_u32(&b_full[sb]), 0),
                                     ch * sg.kc, it.n0 + (int)crank * (BN / 2), tp);
                   } else {
-                    mbar_arrive_expect_tx(&b_full[sb], b_bytes);
+                    mbar_arrive_expect_tx(&b_full[sb], (uint32_t)tps * b_bytes);
                     tma_load_3d(b_buf + (size_t)sb * p.b_stage_bytes, &sg.tmB, &b_full[sb], ch * sg.kc, it.n0, tp);
                   }
                 }
@@ -587,6 +590,8 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           const uint32_t row16 = kc >> 3;                       // row bytes / 16
           const uint32_t pitch = halo ? kHaloPitch : TW;
           const uint32_t mt_step16 = 16 * pitch * row16;
+          const bool row_stage = !resident && halo && p.b_tps == 3;
+          const uint32_t b_tile16 = (cg2 ? BN / 2 : BN) * row16;       // one tap's weight tile inside a row stage
 #pragma unroll 1
           for (uint32_t ch = 0; ch < seg_chunks[s]; ++ch) {
             if (!mma_only) LASS_TIMED_WAIT(&a_full[ring0 + sa], pa, kProfMmaAFull);
@@ -614,9 +619,10 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
 #pragma unroll
                 for (uint32_t dx = 0; dx < 3; ++dx) {
                   if (dx > 0 && !halo) break;
-                  if (!mma_only) LASS_TIMED_WAIT(&b_full[bring0 + sb], resident ? 0u : pb, kProfMmaBFull);
+                  // row_stage: the three taps of this kernel row share one weight stage (one wait, one commit)
+                  if (!mma_only && (!row_stage || dx == 0)) LASS_TIMED_WAIT(&b_full[bring0 + sb], resident ? 0u : pb, kProfMmaBFull);
                   tc_fence_after_sync();
-                  const uint32_t b_lo = (b_base16 + (bring0 + sb) * b_stage16) | kLbo;
+                  const uint32_t b_lo = (b_base16 + (bring0 + sb) * b_stage16 + (row_stage ? dx * b_tile16 : 0u)) | kLbo;
                   if (!no_mma && elect_one()) {
                     if (cg2) {
                       if (kc == 64) issue_tap<MT, BN, 4, true>(acc_addr, a_lo + dx * 8, mt_step16, b_lo, gs, accumulate);
@@ -630,7 +636,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                   accumulate = 1;
                   if (resident) {
                     ++sb;
-                  } else {
+                  } else if (!row_stage || dx == 2) {
                     if (elect_one()) {
                       if (cg2) umma_commit_cg2(&b_empty[bring0 + sb]);
                       else umma_commit(&b_empty[bring0 + sb]);
@@ -1839,30 +1845,63 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   // N tile per pair, every MMA M = 256 over both CTAs, each CTA streams and holds only HALF of every weight tile -- the
   // operand reads per CTA and MMA drop from 4 KiB + 32 N to 4 KiB + 16 N bytes and the weight fill per CTA halves.
   p.cg2 = 0;
+  p.b_tps = 1;
+  // weight tensor maps for `rows` couts and `tps` taps per box; returns the largest stage (bytes) over the segments
+  auto weight_maps = [&](int rows, int tps, uint32_t* stage_out) -> int {
+    uint32_t stage = 0;
+    for (int s = 0; s < l.nseg; ++s) {
+      const ConvSegment& sg = l.seg[s];
+      const CUtensorMapSwizzle swz = sg.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+      const int t = sg.taps == 9 ? tps : 1;
+      uint64_t dims[3] = {(uint64_t)sg.cin, (uint64_t)l.ncols, (uint64_t)sg.taps};
+      uint64_t strides[2] = {(uint64_t)sg.cin * 2, (uint64_t)sg.cin * 2 * l.ncols};
+      uint32_t box[3] = {(uint32_t)sg.kc, (uint32_t)rows, (uint32_t)t};
+      int err = make_tensor_map(&p.seg[s].tmB, sg.weights, 2, 3, dims, strides, box, swz);
+      if (err) return err;
+      const uint32_t bytes = (uint32_t)t * rows * sg.kc * 2;
+      if (bytes > stage) stage = bytes;
+    }
+    *stage_out = (stage + 1023u) & ~1023u;
+    return 0;
+  };
   // Not for the transposed convs: they are bound by their stores, and the coupled pair loses (measured +12 %).
   if (!p.b_resident && BN >= 128 && kc_pair.fn != kc.fn && (p.pix_tiles % 2) == 0 && !l.gen_src && !(g_debug_flags & 4096) &&
       l.ncols % BN == 0 && up == 1) {
     p.cg2 = 1;
-    uint32_t b_half = 0;
-    for (int s = 0; s < l.nseg; ++s) {
-      const ConvSegment& sg = l.seg[s];
-      const CUtensorMapSwizzle swz = sg.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-      uint64_t dims[3] = {(uint64_t)sg.cin, (uint64_t)l.ncols, (uint64_t)sg.taps};
-      uint64_t strides[2] = {(uint64_t)sg.cin * 2, (uint64_t)sg.cin * 2 * l.ncols};
-      uint32_t box[3] = {(uint32_t)sg.kc, (uint32_t)(BN / 2), 1};
-      if ((e = make_tensor_map(&p.seg[s].tmB, sg.weights, 2, 3, dims, strides, box, swz))) {
-        delete cp;
-        return e;
-      }
-      if ((uint32_t)(BN / 2) * sg.kc * 2 > b_half) b_half = (uint32_t)(BN / 2) * sg.kc * 2;
+    if ((e = weight_maps(BN / 2, 1, &p.b_stage_bytes))) {
+      delete cp;
+      return e;
     }
-    p.b_stage_bytes = (b_half + 1023u) & ~1023u;
     const size_t min_a = 2 * (size_t)p.a_stage_bytes;
     const size_t rest = kBudget > fixed + min_a ? kBudget - fixed - min_a : 0;
     // what the halved weight stages free goes to a deeper weight ring (a third A stage instead: no gain, measured)
     p.b_stages = (int)(rest / p.b_stage_bytes);
     if (p.b_stages > 16) p.b_stages = 16;
     kc = kc_pair;
+  }
+  // Row stages for streamed 3x3 weights (debug flag 8192 switches them off): the three taps of a kernel row arrive in one
+  // TMA box and cost the MMA issuer one full / empty handshake instead of three -- what it does between two MMAs is exposed
+  // tensor-pipe time.  Taken when at least three such stages fit.
+  if (!p.b_resident && !(g_debug_flags & 8192)) {
+    const int rows = p.cg2 ? BN / 2 : BN;
+    bool any9 = false;
+    uint32_t stage3 = 0;
+    for (int s = 0; s < l.nseg; ++s) {
+      any9 = any9 || l.seg[s].taps == 9;
+      const uint32_t bytes = (uint32_t)(l.seg[s].taps == 9 ? 3 : 1) * rows * l.seg[s].kc * 2;
+      if (bytes > stage3) stage3 = bytes;
+    }
+    stage3 = (stage3 + 1023u) & ~1023u;
+    const size_t used = fixed + (size_t)p.a_stages * p.a_stage_bytes;
+    const int n3 = kBudget > used ? (int)((kBudget - used) / stage3) : 0;
+    if (any9 && n3 >= 3) {
+      p.b_tps = 3;
+      if ((e = weight_maps(rows, 3, &p.b_stage_bytes))) {
+        delete cp;
+        return e;
+      }
+      p.b_stages = n3 > 8 ? 8 : n3;
+    }
   }
   // Two MMA issuers + two producers, each pair with half of the rings.  Measured per layer (tools/gpu_conv_timing.py):
   // a win when every issuer keeps two A stages (resident weights, >= 4 stages), and for streamed weights with N <= 128 and
@@ -1874,7 +1913,8 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     // decoder conv -10 %, the 64 -> 64 + shortcut one -3 %; the encoder conv2 launches and short items lose)
     if (p.b_resident)
       p.dual_issue = (p.a_stages >= 4 || (p.a_stages >= 2 && b_tiles_per_item >= 11 && !l.pool_raw.ptr && !l.pool_act.ptr)) ? 1 : 0;
-    else p.dual_issue = (BN <= 128 && p.b_stages >= 4 && b_tiles_per_item >= 36) ? 1 : 0;
+    // (CTA pairs: one issuer with the whole ring beats two with half each by 15-30 %, measured on every eligible layer)
+    else p.dual_issue = (!p.cg2 && BN <= 128 && p.b_stages >= 4 && b_tiles_per_item >= 36) ? 1 : 0;
   }
   if (p.dual_issue) {
     p.a_stages &= ~1;

@@ -190,6 +190,11 @@ CASES["pair_c384_384_sc"] = dict(B=4, H=32, W=16, cin=384, cout=384, shortcut_ci
 CASES["pair_slice"] = dict(B=2, H=32, W=32, cin=256, cout=128, out_cstride_mult=2, out_coff=128)
 for _name in ("c128_128", "c768_384", "c256_256", "sc_pool12", "sc_big", "pair_c384_384_sc", "pair_c512_256"):
     CASES["nopair_" + _name] = dict(CASES[_name], flags=4096)
+# streamed 3x3 weights move in row stages (three taps per TMA box / handshake) where three such stages fit; flag 8192: one tap
+# per stage (pairs and single CTAs)
+for _name in ("c128_128", "c256_256", "sc_big", "pair_c384_384_sc", "pair_c512_256"):
+    CASES["tapstage_" + _name] = dict(CASES[_name], flags=8192)
+    CASES["nopair_tapstage_" + _name] = dict(CASES[_name], flags=4096 | 8192)
 
 if __name__ == "__main__":
     pitch = int(sys.argv[1])   # kept for the log name; the halo pitch is fixed at 10 pixels

@@ -1,12 +1,25 @@
 #!/bin/bash
-# dev loop for the CTA-pair (cta_group::2) conv path: parity of the pair cases first (short timeout: a protocol bug hangs),
-# then per-launch times of the whole model with and without pairs.
+# dev loop for the streamed-weight conv paths (CTA pairs, row stages): parity of the affected cases first (short timeout: a
+# protocol bug hangs), then per-launch times of the whole model under the flag settings given as arguments.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-PAIR_CASES="c128_128 nopair_c128_128 c256_256 sc_big sc_pool12 c768_384 pair_c128_128_long pair_c256_256_long pair_c512_256 pair_c384_384_sc pair_slice nopair_pair_c512_256"
-timeout 150 python tools/gpu_conv_probe.py 10 $PAIR_CASES > gpurun_out/pair_probe.log 2>&1
+timeout 240 python - > gpurun_out/pair_probe.log 2>&1 <<'PY'
+import json, sys
+sys.path.insert(0, 'tools')
+import gpu_conv_probe as g
+names = [n for n in g.CASES if n.startswith(('pair_', 'nopair_', 'tapstage_')) or n in ('c128_128', 'c256_256', 'c256_384', 'c768_384', 'sc_big', 'sc_pool12', 'convT22_big')]
+bad = 0
+for n in names:
+    r = g.run_case(n, **g.CASES[n])
+    ok = all((v is True) or (isinstance(v, float) and v < 6e-3) for v in r.values())
+    bad += not ok
+    print(n, 'ok' if ok else 'BAD', json.dumps(r), flush=True)
+print('cases', len(names), 'bad', bad)
+sys.exit(1 if bad else 0)
+PY
 rc=$?
-cat gpurun_out/pair_probe.log | cut -c1-220
-if [ $rc -ne 0 ] || grep -q error gpurun_out/pair_probe.log; then echo "pair probe failed rc=$rc"; nvidia-smi --query-gpu=name,memory.used --format=csv; exit 0; fi
-timeout 300 python tools/gpu_layer_times.py 64 pair > gpurun_out/layer_times_pair.log 2>&1; tail -33 gpurun_out/layer_times_pair.log
-LASS_CONV_FLAGS=4096 timeout 300 python tools/gpu_layer_times.py 64 nopair > gpurun_out/layer_times_nopair.log 2>&1; tail -1 gpurun_out/layer_times_nopair.log
+tail -45 gpurun_out/pair_probe.log | cut -c1-200
+if [ $rc -ne 0 ]; then echo "probe failed rc=$rc"; exit 0; fi
+for f in "$@"; do
+  LASS_CONV_FLAGS=$f timeout 300 python tools/gpu_layer_times.py 64 f$f > gpurun_out/layer_times_f$f.log 2>&1; echo "flags $f: $(tail -1 gpurun_out/layer_times_f$f.log)"
+done
