@@ -254,7 +254,6 @@ __device__ __forceinline__ void act_store32(const float* v, const float4* sc, co
 
 template <int BN, int MT, bool CG2 = false>
 __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-  static_assert(!CG2 || BN >= 128, "CTA pairs are instantiated for the N >= 128 tiles only");
   // accumulator ring: item n of this CTA uses stage n % NS; MMA warp (n & 1) issues it, epilogue group (n & 1) drains it.
   // Four stages where they fit in 256 columns, so that the MMAs of item n + 2 do not have to wait for the epilogue of item n.
   constexpr int NS = acc_stages(BN, MT);
@@ -487,9 +486,15 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
               if (first_item) {
                 for (int tp = 0; tp < sg.taps; ++tp, ++b_slot_res) {
                   if (elect_one()) {
-                    mbar_arrive_expect_tx(&b_full[b_slot_res], b_bytes);
-                    tma_load_3d(b_buf + (size_t)b_slot_res * p.b_stage_bytes, &sg.tmB, &b_full[b_slot_res], ch * sg.kc,
-                                it.n0, tp);
+                    if (cg2) {
+                      if (crank == 0) mbar_arrive_expect_tx(&b_full[b_slot_res], b_bytes);
+                      tma_load_3d_cg2(b_buf + (size_t)b_slot_res * p.b_stage_bytes, &sg.tmB,
+                                      mapa_shared(smem_u32(&b_full[b_slot_res]), 0), ch * sg.kc, it.n0 + (int)crank * (BN / 2), tp);
+                    } else {
+                      mbar_arrive_expect_tx(&b_full[b_slot_res], b_bytes);
+                      tma_load_3d(b_buf + (size_t)b_slot_res * p.b_stage_bytes, &sg.tmB, &b_full[b_slot_res], ch * sg.kc,
+                                  it.n0, tp);
+                    }
                   }
                   __syncwarp();
                 }
@@ -549,7 +554,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       const uint32_t n_b = (dual && p.b_resident == 0) ? (uint32_t)p.b_stages >> 1 : (uint32_t)p.b_stages;
       const uint32_t ring0 = dual ? mw * n_a : 0u;   // first stage of this issuer's part of the A ring
       const uint32_t bring0 = (dual && p.b_resident == 0) ? mw * n_b : 0u;   // ... and of the streamed-weight ring
-      const bool resident = !cg2 && p.b_resident != 0;     // CTA pairs always stream their weights
+      const bool resident = p.b_resident != 0;
       const bool no_mma = (p.debug_flags & 2) != 0;
       // per-segment constants, hoisted out of the item loop
       SegMma g[2];
@@ -602,11 +607,11 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
               const uint32_t b_lo = (b_base16 + sb * b_stage16) | kLbo;
               if (!no_mma && elect_one()) {
                 if (halo) {
-                  if (kc == 64) issue_halo_chunk_running<MT, BN, 4>(acc_addr, a_lo, b_lo, b_stage16, gs, accumulate);
-                  else issue_halo_chunk_running<MT, BN, 2>(acc_addr, a_lo, b_lo, b_stage16, gs, accumulate);
+                  if (kc == 64) issue_halo_chunk_running<MT, BN, 4, cg2>(acc_addr, a_lo, b_lo, b_stage16, gs, accumulate);
+                  else issue_halo_chunk_running<MT, BN, 2, cg2>(acc_addr, a_lo, b_lo, b_stage16, gs, accumulate);
                 } else {
-                  if (kc == 64) issue_tap<MT, BN, 4>(acc_addr, a_lo, 16 * TW * 8, b_lo, gs, accumulate);
-                  else issue_tap<MT, BN, 2>(acc_addr, a_lo, 16 * TW * 4, b_lo, gs, accumulate);
+                  if (kc == 64) issue_tap<MT, BN, 4, cg2>(acc_addr, a_lo, 16 * TW * 8, b_lo, gs, accumulate);
+                  else issue_tap<MT, BN, 2, cg2>(acc_addr, a_lo, 16 * TW * 4, b_lo, gs, accumulate);
                 }
               }
               __syncwarp();
@@ -624,13 +629,8 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
                   tc_fence_after_sync();
                   const uint32_t b_lo = (b_base16 + (bring0 + sb) * b_stage16 + (row_stage ? dx * b_tile16 : 0u)) | kLbo;
                   if (!no_mma && elect_one()) {
-                    if (cg2) {
-                      if (kc == 64) issue_tap<MT, BN, 4, true>(acc_addr, a_lo + dx * 8, mt_step16, b_lo, gs, accumulate);
-                      else issue_tap<MT, BN, 2, true>(acc_addr, a_lo + dx * 4, mt_step16, b_lo, gs, accumulate);
-                    } else {
-                      if (kc == 64) issue_tap<MT, BN, 4>(acc_addr, a_lo + dx * 8, mt_step16, b_lo, gs, accumulate);
-                      else issue_tap<MT, BN, 2>(acc_addr, a_lo + dx * 4, mt_step16, b_lo, gs, accumulate);
-                    }
+                    if (kc == 64) issue_tap<MT, BN, 4, cg2>(acc_addr, a_lo + dx * 8, mt_step16, b_lo, gs, accumulate);
+                    else issue_tap<MT, BN, 2, cg2>(acc_addr, a_lo + dx * 4, mt_step16, b_lo, gs, accumulate);
                   }
                   __syncwarp();
                   accumulate = 1;
@@ -1699,6 +1699,8 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   KernelChoice kc_pair = kc;
   if (BN == 128) kc_pair = MT == 2 ? make_choice<128, 2, true>() : make_choice<128, 1, true>();
   else if (BN == 256 && MT == 1) kc_pair = make_choice<256, 1, true>();
+  else if (BN == 64) kc_pair = MT == 2 ? make_choice<64, 2, true>() : make_choice<64, 1, true>();
+  else if (BN == 32 && MT == 2) kc_pair = make_choice<32, 2, true>();
 
   ConvPrepared* cp = new (std::nothrow) ConvPrepared();
   if (!cp) return set_error(LASS_ERR_ARG, "conv: out of host memory");
@@ -1865,14 +1867,35 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     return 0;
   };
   // Not for the transposed convs: they are bound by their stores, and the coupled pair loses (measured +12 %).
-  if (!p.b_resident && BN >= 128 && kc_pair.fn != kc.fn && (p.pix_tiles % 2) == 0 && !l.gen_src && !(g_debug_flags & 4096) &&
-      l.ncols % BN == 0 && up == 1) {
+  const bool pair_ok = kc_pair.fn != kc.fn && (p.pix_tiles % 2) == 0 && !l.gen_src && !(g_debug_flags & 4096) &&
+                       l.ncols % BN == 0 && up == 1;
+  // Resident weights (half of every tile per CTA) pair up only where the MMA issue rate is the bound -- activated-output-only
+  // launches with N <= 64 and >= 36 MMAs per m-tile: the decoder's 128 -> 64 conv1 (-15 %), its conv2 (-17 %) and the 64 -> 32
+  // conv1 (-5 %).  Launches bound by their epilogue or stores lose 10-60 % in a coupled pair (measured; flag 32768 forces it).
+  int mmas_per_mtile = 0;
+  for (int s = 0; s < l.nseg; ++s) mmas_per_mtile += (l.seg[s].cin / 16) * l.seg[s].taps;
+  const bool act_only = l.full_act.ptr && !l.full_raw.ptr && !l.pool_raw.ptr && !l.pool_act.ptr && !l.after_w && !l.resid_src;
+  if (p.b_resident && pair_ok && ((act_only && BN <= 64 && mmas_per_mtile >= 36) || (g_debug_flags & 32768))) {
     p.cg2 = 1;
     if ((e = weight_maps(BN / 2, 1, &p.b_stage_bytes))) {
       delete cp;
       return e;
     }
-    const size_t min_a = 2 * (size_t)p.a_stage_bytes;
+    const size_t rest = kBudget - fixed - (size_t)p.b_stages * p.b_stage_bytes;
+    p.a_stages = (int)(rest / p.a_stage_bytes);
+    if (p.a_stages > 4) p.a_stages = 4;
+    kc = kc_pair;
+  }
+  if (!p.b_resident && BN >= 128 && pair_ok) {
+    p.cg2 = 1;
+    if ((e = weight_maps(BN / 2, 1, &p.b_stage_bytes))) {
+      delete cp;
+      return e;
+    }
+    // a decoder conv2's shortcut segment (1x1 over the 2C-channel concat) moves twice the activation bytes of the 3x3 segment
+    // for an eighth of its MMAs: a third A stage keeps its loads ahead (measured -5..-9 %; +2 % on the other launches)
+    if (l.nseg == 2 && l.seg[1].taps == 1 && l.seg[1].cin > l.seg[0].cin) p.a_stages = 3;
+    const size_t min_a = (size_t)p.a_stages * p.a_stage_bytes;
     const size_t rest = kBudget > fixed + min_a ? kBudget - fixed - min_a : 0;
     // what the halved weight stages free goes to a deeper weight ring (a third A stage instead: no gain, measured)
     p.b_stages = (int)(rest / p.b_stage_bytes);
@@ -1912,7 +1935,8 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     // ... or, with one A stage per issuer, for the longer resident items without pooled outputs (measured: the 128 -> 64
     // decoder conv -10 %, the 64 -> 64 + shortcut one -3 %; the encoder conv2 launches and short items lose)
     if (p.b_resident)
-      p.dual_issue = (p.a_stages >= 4 || (p.a_stages >= 2 && b_tiles_per_item >= 11 && !l.pool_raw.ptr && !l.pool_act.ptr)) ? 1 : 0;
+      p.dual_issue = ((p.a_stages >= 4 || (p.a_stages >= 2 && b_tiles_per_item >= 11 && !l.pool_raw.ptr && !l.pool_act.ptr)) &&
+                      !(p.cg2 && l.nseg == 2)) ? 1 : 0;      // (a pair with a shortcut segment: one issuer, measured)
     // (CTA pairs: one issuer with the whole ring beats two with half each by 15-30 %, measured on every eligible layer)
     else p.dual_issue = (!p.cg2 && BN <= 128 && p.b_stages >= 4 && b_tiles_per_item >= 36) ? 1 : 0;
   }

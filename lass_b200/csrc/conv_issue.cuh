@@ -40,6 +40,13 @@ __device__ __forceinline__ void umma_lohi_cg2(uint32_t tmem_d, uint32_t a_lo, ui
       : "memory");
 }
 
+template <bool CG2>
+__device__ __forceinline__ void umma_sel(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  if (CG2) umma_lohi_cg2(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+  else umma_lohi(tmem_d, a_lo, a_hi, b_lo, b_hi, idesc, accumulate);
+}
+
 // Per-segment constants of the MMA issuer (uniform registers).
 struct SegMma {
   uint32_t a_hi, b_hi;      // descriptor high words
@@ -75,17 +82,17 @@ __device__ __forceinline__ void desc_add(uint32_t& lo) {
 __device__ __forceinline__ void desc_add_r(uint32_t& lo, uint32_t d) {
   asm volatile("add.s32 %0, %0, %1;" : "+r"(lo) : "r"(d));
 }
-template <int MT, int BN, int KSTEPS, int TP>
+template <int MT, int BN, int KSTEPS, int TP, bool CG2>
 __device__ __forceinline__ void issue_halo_tap_running(uint32_t acc, uint32_t& a, uint32_t& b, uint32_t b_next_tap,
                                                        const SegMma& g, uint32_t accumulate) {
   constexpr int ROW16 = 2 * KSTEPS;                       // bytes of one pixel row / 16
   constexpr int MT_STEP = 16 * kHaloPitch * ROW16;
 #pragma unroll
   for (int ks = 0; ks < KSTEPS; ++ks) {
-    umma_lohi(acc, a, g.a_hi, b, g.b_hi, g.idesc, (TP == 0 && ks == 0) ? accumulate : 1u);
+    umma_sel<CG2>(acc, a, g.a_hi, b, g.b_hi, g.idesc, (TP == 0 && ks == 0) ? accumulate : 1u);
     if (MT == 2) {
       desc_add<MT_STEP>(a);
-      umma_lohi(acc + BN, a, g.a_hi, b, g.b_hi, g.idesc, (TP == 0 && ks == 0) ? accumulate : 1u);
+      umma_sel<CG2>(acc + BN, a, g.a_hi, b, g.b_hi, g.idesc, (TP == 0 && ks == 0) ? accumulate : 1u);
     }
     if (ks + 1 < KSTEPS) {
       desc_add<2 - (MT - 1) * MT_STEP>(a);
@@ -99,20 +106,20 @@ __device__ __forceinline__ void issue_halo_tap_running(uint32_t acc, uint32_t& a
     desc_add_r(b, b_next_tap);
   }
 }
-template <int MT, int BN, int KSTEPS>
+template <int MT, int BN, int KSTEPS, bool CG2 = false>
 __device__ __forceinline__ void issue_halo_chunk_running(uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t b_stage16,
                                                          const SegMma& g, uint32_t accumulate) {
   uint32_t a = a_lo, b = b_lo;
   const uint32_t b_next_tap = b_stage16 - 2 * (KSTEPS - 1);
-  issue_halo_tap_running<MT, BN, KSTEPS, 0>(acc, a, b, b_next_tap, g, accumulate);
-  issue_halo_tap_running<MT, BN, KSTEPS, 1>(acc, a, b, b_next_tap, g, accumulate);
-  issue_halo_tap_running<MT, BN, KSTEPS, 2>(acc, a, b, b_next_tap, g, accumulate);
-  issue_halo_tap_running<MT, BN, KSTEPS, 3>(acc, a, b, b_next_tap, g, accumulate);
-  issue_halo_tap_running<MT, BN, KSTEPS, 4>(acc, a, b, b_next_tap, g, accumulate);
-  issue_halo_tap_running<MT, BN, KSTEPS, 5>(acc, a, b, b_next_tap, g, accumulate);
-  issue_halo_tap_running<MT, BN, KSTEPS, 6>(acc, a, b, b_next_tap, g, accumulate);
-  issue_halo_tap_running<MT, BN, KSTEPS, 7>(acc, a, b, b_next_tap, g, accumulate);
-  issue_halo_tap_running<MT, BN, KSTEPS, 8>(acc, a, b, b_next_tap, g, accumulate);
+  issue_halo_tap_running<MT, BN, KSTEPS, 0, CG2>(acc, a, b, b_next_tap, g, accumulate);
+  issue_halo_tap_running<MT, BN, KSTEPS, 1, CG2>(acc, a, b, b_next_tap, g, accumulate);
+  issue_halo_tap_running<MT, BN, KSTEPS, 2, CG2>(acc, a, b, b_next_tap, g, accumulate);
+  issue_halo_tap_running<MT, BN, KSTEPS, 3, CG2>(acc, a, b, b_next_tap, g, accumulate);
+  issue_halo_tap_running<MT, BN, KSTEPS, 4, CG2>(acc, a, b, b_next_tap, g, accumulate);
+  issue_halo_tap_running<MT, BN, KSTEPS, 5, CG2>(acc, a, b, b_next_tap, g, accumulate);
+  issue_halo_tap_running<MT, BN, KSTEPS, 6, CG2>(acc, a, b, b_next_tap, g, accumulate);
+  issue_halo_tap_running<MT, BN, KSTEPS, 7, CG2>(acc, a, b, b_next_tap, g, accumulate);
+  issue_halo_tap_running<MT, BN, KSTEPS, 8, CG2>(acc, a, b, b_next_tap, g, accumulate);
 }
 
 }  // namespace lass

@@ -195,6 +195,11 @@ for _name in ("c128_128", "c768_384", "c256_256", "sc_pool12", "sc_big", "pair_c
 for _name in ("c128_128", "c256_256", "sc_big", "pair_c384_384_sc", "pair_c512_256"):
     CASES["tapstage_" + _name] = dict(CASES[_name], flags=8192)
     CASES["nopair_tapstage_" + _name] = dict(CASES[_name], flags=4096 | 8192)
+# resident weights in CTA pairs (experimental, debug flag 32768)
+for _name in ("c32_32", "c64_64", "c64_32", "pool32_wide", "resid_pool", "sc_pool", "after", "fp16src", "slice_out", "c32_64"):
+    CASES["respair_" + _name] = dict(CASES[_name], flags=32768)
+CASES["respair_c128_64_long"] = dict(B=4, H=64, W=64, cin=128, cout=64, want_raw=False, flags=32768)
+CASES["respair_c64_32_long"] = dict(B=4, H=128, W=64, cin=64, cout=32, want_raw=False, flags=32768)
 
 if __name__ == "__main__":
     pitch = int(sys.argv[1])   # kept for the log name; the halo pitch is fixed at 10 pixels
