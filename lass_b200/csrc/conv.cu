@@ -16,11 +16,11 @@
 //     so row-shifted starts are legal (verified on B200 by tests/test_gpu_umma_probe.py);
 //   * B: weight tiles (BN couts x kc channels) per (tap, chunk), streamed through a ring — or, when all tiles of
 //     a work item fit in the ring, loaded once and kept resident for the CTA's lifetime;
-//   * D: fp32 accumulators in TMEM, double-buffered (2 x MT x BN columns) so the epilogue of item i overlaps
-//     the MMAs of item i+1.
+//   * D: fp32 accumulators in TMEM, a ring of 4 (or 2) stages so the epilogue of item i overlaps the MMAs of items i+1, i+2.
 // Persistent CTAs (grid = SM count x CTAs/SM), static round-robin over work items
-// (item = pixel tile (16*MT x 8) x N tile).  Warp roles: 0 = TMA producer, 1 = MMA issuer (+ TMEM alloc),
-// 2..5 = epilogue (TMEM -> registers -> fp32 math -> 16-bit NHWC stores).
+// (item = pixel tile (16*MT x 8) x N tile).  Warp roles (384 threads): 0-1 = TMA producers, 2-3 = MMA issuers (+ TMEM
+// alloc), 4-7 / 8-11 = two epilogue groups (TMEM -> registers -> fp32 math -> 16-bit NHWC stores / TMA stores).
+// CG2 instantiations run as CTA pairs (cluster of 2, tcgen05 cta_group::2, M = 256): see the comment at `cg2` in the kernel.
 #include <string.h>
 
 #include <new>
@@ -1833,7 +1833,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
       p.b_stages = b_tiles_per_item;
       size_t rest = kBudget - fixed - (size_t)p.b_stages * p.b_stage_bytes;
       p.a_stages = (int)(rest / p.a_stage_bytes);
-      if (p.a_stages > 4) p.a_stages = 4;
+      if (p.a_stages > kMaxA) p.a_stages = kMaxA;      // deep A rings where the weights leave room (enc0.c2 -5 % vs 4 stages)
       break;
     }
     p.b_resident = 0;

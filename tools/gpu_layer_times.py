@@ -33,10 +33,22 @@ for rep in range(3):
     r = eng.time_unet_launches(B, L, mix.device)
     best = r if best is None else [(min(a[0], b[0]), a[1]) for a, b in zip(best, r)]
 tot = sum(x[0] for x in best)
+# the same 32 launches back to back between two events: the difference to the sum is launch gaps / tails
+out_d = torch.empty(B, 1, L, device="cuda")
+stage = 1e9
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        eng.forward_stages(mix, cond, out_d, 2)
+    e1.record()
+    torch.cuda.synchronize()
+    stage = min(stage, e0.elapsed_time(e1) / 3)
 out = {}
 for nme, (ms, fl) in zip(names, best):
     out[nme] = {"ms": round(ms, 4), "tflops": round(fl / ms / 1e9, 1)}
     print("%-9s %8.4f ms  %7.1f TFLOP/s" % (nme, ms, fl / ms / 1e9))
+print("stage back to back %.3f ms" % stage)
 print("total %.3f ms" % tot)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump({"B": B, "total_ms": tot, "layers": out}, open(os.path.join(ROOT, "gpurun_out", "layer_times_%s.json" % tag), "w"), indent=1)
