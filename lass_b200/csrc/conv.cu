@@ -47,6 +47,7 @@ enum : uint32_t {
   kFEnc2Bias = kFEnc2Common | kFPoolH2 | kFBias,         // encoder_block2..5 (1x1 shortcut segment, bias)
   kFEnc2BiasP12 = kFEnc2Common | kFBias,                 // encoder_block6 (pooling (1, 2))
   kFUpconv = kFRaw | kFAct | kFTma | kFUp,               // transposed convs into the concat buffers
+  kFUpDirect = kFRaw | kFAct | kFUp,                     // the last one (32 channels): 32-byte direct stores
   kFAfterBias = kFAfter | kFBias,                        // decoder_block6 conv2 + after_conv
 };
 constexpr int kThreads = 320;   // conv_dxn_kernel: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
@@ -74,6 +75,7 @@ struct OutDev {
   const float* scale;
   const float* shift;
   int cstride, coff, fp16, shift_bstride;
+  int st256;   // every 32-channel piece of this output is 32 B aligned: direct stores use 32-byte st.global
 };
 
 struct ConvParams {
@@ -155,6 +157,15 @@ __device__ __forceinline__ void store32(const OutDev& o, int b, int ho, int wo, 
                                         bool valid) {
   if (valid) {
     uint16_t* base = reinterpret_cast<uint16_t*>(o.ptr) + (((size_t)b * Ho + ho) * Wo + wo) * o.cstride + o.coff + c;
+    if (o.st256) {
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(base), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                   "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                   : "memory");
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(base + 16), "r"(w[8]), "r"(w[9]), "r"(w[10]),
+                   "r"(w[11]), "r"(w[12]), "r"(w[13]), "r"(w[14]), "r"(w[15])
+                   : "memory");
+      return;
+    }
     uint4* dst = reinterpret_cast<uint4*>(base);
     dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
     dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -233,8 +244,17 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return r;
 }
 
-// y = lrelu(sc * v + sh) for 32 channels of one pixel, packed to bf16 and stored as 4 x 16 B.
-__device__ __forceinline__ void act_store32(const float* v, const float4* sc, const float4* sh, uint16_t* dst, bool valid) {
+// 32-byte global store (sm_100 STG.256): a lane's piece covers whole 32 B sectors.  The per-lane pieces of these epilogues lie
+// one pixel (>= 64 B) apart, so a 16 B store writes HALF a sector per lane and costs twice the LSU transactions.
+__device__ __forceinline__ void stg256(void* dst, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+               "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+
+// y = lrelu(sc * v + sh) for 32 channels of one pixel, packed to bf16 and stored as 2 x 32 B (st256) or 4 x 16 B.
+__device__ __forceinline__ void act_store32(const float* v, const float4* sc, const float4* sh, uint16_t* dst, bool valid,
+                                            bool st256) {
   uint32_t w[16];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -244,11 +264,16 @@ __device__ __forceinline__ void act_store32(const float* v, const float4* sc, co
     w[2 * j + 1] = lrelu_bf16x2(pack_bf16x2(t2, t3));
   }
   if (valid) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
-    d[0] = make_uint4(w[0], w[1], w[2], w[3]);
-    d[1] = make_uint4(w[4], w[5], w[6], w[7]);
-    d[2] = make_uint4(w[8], w[9], w[10], w[11]);
-    d[3] = make_uint4(w[12], w[13], w[14], w[15]);
+    if (st256) {
+      stg256(dst, w);
+      stg256(dst + 16, w + 8);
+    } else {
+      uint4* d = reinterpret_cast<uint4*>(dst);
+      d[0] = make_uint4(w[0], w[1], w[2], w[3]);
+      d[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      d[2] = make_uint4(w[8], w[9], w[10], w[11]);
+      d[3] = make_uint4(w[12], w[13], w[14], w[15]);
+    }
   }
 }
 
@@ -713,6 +738,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       uint16_t* const out = reinterpret_cast<uint16_t*>(p.full_act.ptr) + p.full_act.coff;
       const int cstride = p.full_act.cstride;
       const bool idle = (p.debug_flags & 1) != 0;
+      const bool st256 = p.full_act.st256 != 0;
       if (kSplitMT) n = 0;
       for (int item = vbid + (kSplitMT ? 0 : grp) * vgrid; item < vitems;
            item += (kSplitMT ? 1 : 2) * vgrid, n += (kSplitMT ? 1 : 2)) {
@@ -764,7 +790,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           if (idle) continue;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt)
-            if (!kSplitMT || mt == grp) act_store32(v[mt], sc, sh, dst[mt] + c0, valid[mt]);
+            if (!kSplitMT || mt == grp) act_store32(v[mt], sc, sh, dst[mt] + c0, valid[mt], st256);
         }
         tc_fence_before_sync();
         __syncwarp();
@@ -1059,6 +1085,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       case 4: generic_items(UTag<kFEnc2BiasP12>{}); break;
       case 5: generic_items(UTag<kFUpconv>{}); break;
       case 6: generic_items(UTag<kFAfterBias>{}); break;
+      case 7: generic_items(UTag<kFUpDirect>{}); break;
       default: generic_items(UTag<kFGeneric>{}); break;
     }
     }
@@ -1494,6 +1521,10 @@ static void fill_out(OutDev& d, const ConvOut& o) {
   d.coff = o.coff;
   d.fp16 = o.fp16;
   d.shift_bstride = o.shift_bstride;
+  // (transposed convs write group_c-channel pieces at channel offsets that are multiples of 32 within cstride, so the same
+  // test covers them; debug flag 16384 keeps 16-byte stores)
+  d.st256 = (o.ptr && o.cstride % 16 == 0 && o.coff % 16 == 0 && reinterpret_cast<uintptr_t>(o.ptr) % 32 == 0 &&
+             !(g_debug_flags & 16384)) ? 1 : 0;
 }
 
 static int check_out(const ConvOut& o, const char* name, int ncols_eff) {
@@ -1817,7 +1848,10 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   // concat buffers (-15 %) — and loses a few per cent against direct 16 B stores for whole-pixel outputs, where loads
   // and stores then compete for the SM's TMA request rate (~1 box row / 4 clk).
   const bool sliced = (l.full_raw.ptr && l.full_raw.cstride != l.group_c) || (l.full_act.ptr && l.full_act.cstride != l.group_c);
-  const bool want_tma = has_16bit_out && (up > 1 || sliced) && !(g_debug_flags & 32);
+  // ... except the 32-channel transposed conv: its 64 B pieces are bound by the TMA row rate, and two 32-byte st.global per
+  // piece (whole sectors) beat it (-7 %); with 16-byte stores they did not.
+  const bool up32_direct = up > 1 && l.group_c == 32 && (!l.full_raw.ptr || p.full_raw.st256) && (!l.full_act.ptr || p.full_act.st256);
+  const bool want_tma = has_16bit_out && (up > 1 || sliced) && !up32_direct && !(g_debug_flags & 32);
   // preference order: resident weights + TMA stores, resident weights, streaming + TMA stores, streaming
   for (int attempt = 0; attempt < 4; ++attempt) {
     const bool try_resident = attempt < 2;
@@ -1978,6 +2012,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     else if (f == kFEnc2BiasP12) p.epi_mode = 4;
     else if (f == kFUpconv) p.epi_mode = 5;
     else if (f == kFAfterBias) p.epi_mode = 6;
+    else if (f == kFUpDirect) p.epi_mode = 7;
     else p.epi_mode = 0;
   }
   if (p.tma_store == 1 || p.tma_store == 3) {
