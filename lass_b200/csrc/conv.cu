@@ -1850,7 +1850,8 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   const bool sliced = (l.full_raw.ptr && l.full_raw.cstride != l.group_c) || (l.full_act.ptr && l.full_act.cstride != l.group_c);
   // ... except the 32-channel transposed conv: its 64 B pieces are bound by the TMA row rate, and two 32-byte st.global per
   // piece (whole sectors) beat it (-7 %); with 16-byte stores they did not.
-  const bool up32_direct = up > 1 && l.group_c == 32 && (!l.full_raw.ptr || p.full_raw.st256) && (!l.full_act.ptr || p.full_act.st256);
+  const bool up32_direct = up > 1 && l.group_c == 32 && (!l.full_raw.ptr || p.full_raw.st256) && (!l.full_act.ptr || p.full_act.st256) &&
+                           !(g_debug_flags & 65536);
   const bool want_tma = has_16bit_out && (up > 1 || sliced) && !up32_direct && !(g_debug_flags & 32);
   // preference order: resident weights + TMA stores, resident weights, streaming + TMA stores, streaming
   for (int attempt = 0; attempt < 4; ++attempt) {
