@@ -164,10 +164,14 @@ typedef struct lass_conv_desc {
 
 LASS_API int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream);
 
-/* Debug: timing experiments on the conv kernel (results become wrong): bit 0 = epilogue skips math and stores,
- * bit 1 = no tcgen05.mma issued, bit 2 = no activation (A) TMA loads.  Bit 12 (4096) keeps results correct: launches
- * prepared while it is set do not use CTA pairs (tcgen05 cta_group::2), i.e. streamed weights take the single-CTA path --
- * used by the parity tests to cover both.  0 = normal operation. */
+/* Debug: experiments on the conv kernel; read when a launch is PREPARED (lass_conv_igemm, plan creation).  0 = normal operation.
+ * Knock-outs, results become wrong: 1 = epilogue skips math and stores, 2 = no tcgen05.mma issued, 4 = no activation (A) TMA
+ * loads, 8 = no pooled outputs, 16 = no direct stores, 64 = MMA issuers only.
+ * Configuration switches, results stay correct (the parity tests use them to cover both sides of a choice): 32 = direct global
+ * stores instead of TMA stores, 128 = single MMA issuer, 256 = generic (unspecialised) epilogue, 512 / 2048 = staged outputs
+ * through coalesced / hybrid st.global, 1024 = N 256 x 2 m-tiles, 4096 = no CTA pairs (tcgen05 cta_group::2), 8192 = one tap
+ * per streamed weight stage, 16384 = 16-byte instead of 32-byte direct stores, 32768 = CTA pairs for every resident-weight
+ * launch, 65536 = the 32-channel transposed conv through TMA stores. */
 LASS_API int lass_debug_set_conv_flags(int flags);
 /* Debug: per-CTA role profile of subsequently PREPARED conv launches.  device_counters: >= 16 int64 per CTA
  * (<= 296 CTAs), clock cycles: [0] producer waits for a free A stage, [1] for a free B stage, [2] producer total,
