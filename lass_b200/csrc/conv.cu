@@ -806,6 +806,20 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
     constexpr uint32_t F = decltype(ftag)::value;
 #define FEAT(bit, cond) ((F == kFGeneric) ? (cond) : ((F & (bit)) != 0u))
     if (kSplitMT) n = 0;
+    constexpr bool every = kSplitMT;
+    // prefetched operands of the rank-1 residual (see below)
+    float pf_s[MT], pf_m[MT], pf_t[MT];
+    bool pf_have = false;
+    auto resid_load = [&](const Item& gi) {
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int hh = gi.h0 + mt * 16 + hl, ww = gi.w0 + wl;
+        const bool on = hh < p.resid_T && ww < p.W;
+        pf_s[mt] = on ? __ldg(p.resid_in_scale + ww) : 0.0f;
+        pf_m[mt] = on ? __ldg(p.resid_src + ((size_t)gi.b * p.resid_T + hh) * p.resid_F + ww) : 0.0f;
+        pf_t[mt] = on ? __ldg(p.resid_in_shift + ww) : 0.0f;
+      }
+    };
     for (int item = vbid + (kSplitMT ? 0 : grp) * vgrid; item < vitems;
          item += (kSplitMT ? 1 : 2) * vgrid, n += (kSplitMT ? 1 : 2)) {
       const uint32_t as = n % NS, acc_parity = (n / NS) & 1u;
@@ -835,15 +849,19 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
       }
       const EpiTables<BN>& tb = gtabs[tab_sel];
       __builtin_assume(__isShared(&tb));   // table reads become ld.shared instead of generic loads
-      // rank-1 residual operand of this thread's pixels: loaded before the accumulator wait so the latency is hidden
+      // rank-1 residual operand of this thread's pixels.  The magnitudes come from DRAM (they were last touched two launches
+      // ago): they are loaded one ITEM ahead and only consumed here, because an in-order warp that multiplies them right
+      // after the load sits out the full memory latency -- 36 % of this epilogue's time in the ncu source view
       float resid_xs[MT];
 #pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        resid_xs[mt] = 0.0f;
-        const int hh = it.h0 + mt * 16 + hl, ww = it.w0 + wl;
-        if (FEAT(kFResid, p.resid_src != nullptr) && hh < p.resid_T && ww < p.W)
-          resid_xs[mt] = fmaf(__ldg(p.resid_in_scale + ww), __ldg(p.resid_src + ((size_t)it.b * p.resid_T + hh) * p.resid_F + ww),
-                              __ldg(p.resid_in_shift + ww));
+      for (int mt = 0; mt < MT; ++mt) resid_xs[mt] = 0.0f;
+      if (FEAT(kFResid, p.resid_src != nullptr)) {
+        if (!pf_have) resid_load(it);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) resid_xs[mt] = fmaf(pf_s[mt], pf_m[mt], pf_t[mt]);
+        const int nxt = item + (every ? 1 : 2) * vgrid;
+        pf_have = nxt < vitems;
+        if (pf_have) resid_load(dec(nxt));
       }
       if (q == 0 && lane == 0 && grp == 0) {
         LASS_TIMED_WAIT_RELAXED(&acc_full[as], acc_parity, kProfEpiAccFull);
