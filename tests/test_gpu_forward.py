@@ -105,3 +105,28 @@ def test_full_size_batch_properties(model_sd):
     assert torch.equal(one[0], out[5])
     ref = O.resunet30_forward(sd, mix[5:6], cond[5:6])
     snr_ok(ref, out[5:6].cpu(), MIN_SNR_DB)
+
+
+def test_forward_is_cuda_graph_capturable(model_sd):
+    """the whole-graph C-ABI entry must be capturable -- no allocation, host synchronisation or default-stream
+    work inside (the cluster launches of the CTA-pair conv kernels included).  Replay must reproduce the eager result bit
+    for bit."""
+    model, sd = model_sd
+    mix, cond = factory.make_inputs(4, 32000, seed=5)
+    mix, cond = mix.cuda(), cond.cuda()
+    eager = model({"mixture": mix, "condition": cond})["waveform"].clone()
+    engine = model.base._get_engine(model.film)
+    out = torch.zeros_like(eager)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        engine.forward_stages(mix, cond, out, 7)          # plan + weights exist before the capture
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        engine.forward_stages(mix, cond, out, 7)
+    out.zero_()
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, eager)
