@@ -64,7 +64,40 @@ def main():
             back = istft(re, im, 8000)
         np.savez_compressed(os.path.join(GOLDEN_DIR, "stft_%d_%d_l8000.npz" % (n_fft, hop)),
                             real=re.numpy(), imag=im.numpy(), roundtrip=back.numpy())
+    make_train_golden(ref_mod)
     print("golden fixtures written to", GOLDEN_DIR)
+
+
+def make_train_golden(ref_mod=None):
+    """Training step of the UNMODIFIED reference (``.train()`` forward, reference models/audiosep.py:99-100, + l1_wav,
+    losses.py:4-9, + backward): loss, per-parameter gradient norms / first entries, two updated running statistics.
+    Full gradients are 100 MB, so only this summary is stored; the travelling oracle reproduces them in full."""
+    from . import train_oracle
+    ref_mod = ref_mod or import_reference_resunet()
+    torch.manual_seed(0)
+    net = ref_mod.ResUNet30(input_channels=1, output_channels=1, condition_size=512)
+    sd = factory.fill_state_dict(net.state_dict(), seed=0)
+    net.load_state_dict(sd)
+    net.train()
+    B, L = 2, 16000
+    mix, cond = factory.make_inputs(B, L, seed=1234, edge_clips=False)
+    tgt, _ = factory.make_inputs(B, L, seed=4321, edge_clips=False)
+    tgt = 0.5 * tgt
+    out = net({"mixture": mix, "condition": cond})["waveform"]
+    loss = torch.mean(torch.abs(out.squeeze() - tgt.squeeze()))
+    loss.backward()
+    keys = [k for k, p in net.named_parameters() if p.requires_grad and p.grad is not None]
+    assert all(not train_oracle.is_dead_key(k) for k in keys)
+    grads = dict((k, p.grad) for k, p in net.named_parameters() if p.grad is not None)
+    new_sd = net.state_dict()
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "train_step_b2_l16000.npz"),
+                        loss=np.float64(float(loss.detach())), keys=np.array(keys),
+                        grad_norms=np.array([float(grads[k].double().norm()) for k in keys]),
+                        grad_first=np.array([float(grads[k].reshape(-1)[0]) for k in keys]),
+                        grad_absmax=np.array([float(grads[k].abs().max()) for k in keys]),
+                        bn0_running_mean=new_sd["base.bn0.running_mean"].numpy(),
+                        enc3_bn2_running_var=new_sd["base.encoder_block3.conv_block1.bn2.running_var"].numpy(),
+                        waveform=out.detach().numpy(), meta=np.array([B, L, 1234, 4321]))
 
 
 if __name__ == "__main__":

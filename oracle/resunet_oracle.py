@@ -46,9 +46,16 @@ DECODERS = (
 TIME_DOWNSAMPLE = 32  # reference models/resunet.py:282
 
 
-def _bn(sd, prefix, x):
+BN_MOMENTUM = 0.01  # reference models/resunet.py:275
+
+
+def _bn(sd, prefix, x, train=False):
+    """eval: running statistics.  train: batch statistics (biased variance) and an in-place update of
+    ``sd[prefix + '.running_*']`` with momentum 0.01 / unbiased variance, as nn.BatchNorm2d does in .train()."""
+    if train:
+        sd[prefix + ".num_batches_tracked"] += 1
     return F.batch_norm(x, sd[prefix + ".running_mean"], sd[prefix + ".running_var"],
-                        sd[prefix + ".weight"], sd[prefix + ".bias"], False, 0.0, BN_EPS)
+                        sd[prefix + ".weight"], sd[prefix + ".bias"], train, BN_MOMENTUM if train else 0.0, BN_EPS)
 
 
 def _film(sd, cond, name):
@@ -58,13 +65,13 @@ def _film(sd, cond, name):
     return F.linear(cond, w, b)[:, :, None, None]
 
 
-def _conv_block_res(sd, prefix, film_prefix, x, cond, taps=None):
+def _conv_block_res(sd, prefix, film_prefix, x, cond, taps=None, train=False):
     # reference models/resunet.py:147-165
     b1 = _film(sd, cond, film_prefix + "->beta1")
     b2 = _film(sd, cond, film_prefix + "->beta2")
-    a1 = F.leaky_relu(_bn(sd, prefix + ".bn1", x) + b1, LRELU_SLOPE)
+    a1 = F.leaky_relu(_bn(sd, prefix + ".bn1", x, train) + b1, LRELU_SLOPE)
     h = F.conv2d(a1, sd[prefix + ".conv1.weight"], None, padding=1)
-    a2 = F.leaky_relu(_bn(sd, prefix + ".bn2", h) + b2, LRELU_SLOPE)
+    a2 = F.leaky_relu(_bn(sd, prefix + ".bn2", h, train) + b2, LRELU_SLOPE)
     h2 = F.conv2d(a2, sd[prefix + ".conv2.weight"], None, padding=1)
     if (prefix + ".shortcut.weight") in sd:
         res = F.conv2d(x, sd[prefix + ".shortcut.weight"], sd[prefix + ".shortcut.bias"])
@@ -133,13 +140,13 @@ def infer_stft_params(sd, prefix="base."):
     return int(w.shape[2])
 
 
-@torch.no_grad()
-def resunet30_forward(sd: Dict[str, torch.Tensor], mixture: torch.Tensor, condition: torch.Tensor,
-                      hop: int = 160, taps: Optional[dict] = None) -> torch.Tensor:
-    """Eval-mode ``ResUNet30.forward`` for input_channels = output_channels = 1.
+def resunet30_forward_impl(sd: Dict[str, torch.Tensor], mixture: torch.Tensor, condition: torch.Tensor,
+                           hop: int = 160, taps: Optional[dict] = None, train: bool = False) -> torch.Tensor:
+    """``ResUNet30.forward`` for input_channels = output_channels = 1; autograd-transparent.
 
     sd: reference-keyed state dict (``base.*``, ``film.*``); mixture (B, 1, L); condition (B, 512).
-    Returns waveform (B, 1, L).  ``taps`` (optional dict) receives named intermediates.
+    Returns waveform (B, 1, L).  ``taps`` (optional dict) receives named intermediates.  ``train`` = the module in
+    ``.train()`` (reference ``models/audiosep.py:99-100``): BatchNorm batch statistics, running stats in ``sd`` updated.
     """
     assert mixture.shape[1] == 1, "oracle restates the single-channel configuration (config yaml: 1/1/512)"
     n_fft = infer_stft_params(sd)
@@ -147,7 +154,11 @@ def resunet30_forward(sd: Dict[str, torch.Tensor], mixture: torch.Tensor, condit
     mag, cos_in, sin_in = stft_mag_phase(sd, mixture[:, 0], n_fft, hop)
 
     # bn0 runs over the frequency axis (models/resunet.py:537-539)
-    x = _bn(sd, "base.bn0", mag.transpose(1, 3)).transpose(1, 3)
+    # (mag.contiguous(): torch 2.11's CPU batch_norm BACKWARD returns wrong weight / bias gradients when its input and the
+    #  incoming gradient have different memory formats, which happens for this (B, F, T, 1) view when `mag` keeps the
+    #  F-major strides of the conv1d output while the gradient arrives (B, 1, T, F)-contiguous.  The reference's `mag` comes
+    #  out of torch.cat, i.e. contiguous, and its gradients agree with fp64 finite differences; same layout here.)
+    x = _bn(sd, "base.bn0", mag.contiguous().transpose(1, 3), train).transpose(1, 3)
     frames = x.shape[2]
     pad = int(math.ceil(frames / TIME_DOWNSAMPLE)) * TIME_DOWNSAMPLE - frames
     x = F.pad(x, (0, 0, 0, pad))
@@ -158,7 +169,7 @@ def resunet30_forward(sd: Dict[str, torch.Tensor], mixture: torch.Tensor, condit
 
     skips = []
     for name, _cin, _cout, pool in ENCODERS:
-        full = _conv_block_res(sd, "base.%s.conv_block1" % name, "%s->conv_block1" % name, x, condition, taps)
+        full = _conv_block_res(sd, "base.%s.conv_block1" % name, "%s->conv_block1" % name, x, condition, taps, train)
         skips.append(full)
         x = F.avg_pool2d(full, kernel_size=pool)
     # conv_block7a's pooled output (pool 1x1 == identity) feeds the decoder; its `full` is unused
@@ -168,18 +179,24 @@ def resunet30_forward(sd: Dict[str, torch.Tensor], mixture: torch.Tensor, condit
         p = "base." + name
         b1 = _film(sd, condition, name + "->beta1")
         # NB: default negative_slope (0.01) at reference models/resunet.py:255
-        a = F.leaky_relu(_bn(sd, p + ".bn1", x) + b1, LRELU_SLOPE)
+        a = F.leaky_relu(_bn(sd, p + ".bn1", x, train) + b1, LRELU_SLOPE)
         u = F.conv_transpose2d(a, sd[p + ".conv1.weight"], None, stride=up)
         cat = torch.cat((u, skips.pop()), dim=1)
         if taps is not None:
             taps[p + ":up"] = u
-        x = _conv_block_res(sd, p + ".conv_block2", name + "->conv_block2", cat, condition, taps)
+        x = _conv_block_res(sd, p + ".conv_block2", name + "->conv_block2", cat, condition, taps, train)
 
     feat = F.conv2d(x, sd["base.after_conv.weight"], sd["base.after_conv.bias"])
     feat = F.pad(feat, (0, 1))[:, :, :frames, :]
     if taps is not None:
         taps["feat"] = feat
     return mask_to_wave(sd, feat, mag, cos_in, sin_in, length, n_fft, hop)
+
+
+@torch.no_grad()
+def resunet30_forward(sd, mixture, condition, hop: int = 160, taps: Optional[dict] = None) -> torch.Tensor:
+    """Eval-mode forward (reference ``dcase_evaluator.py:104``)."""
+    return resunet30_forward_impl(sd, mixture, condition, hop, taps, False)
 
 
 @torch.no_grad()
