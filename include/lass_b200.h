@@ -164,6 +164,98 @@ typedef struct lass_conv_desc {
 
 LASS_API int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream);
 
+/* Prepared launches of lass_conv_igemm: tensor maps are encoded and the tile configuration chosen ONCE; lass_conv_run only
+ * launches (CUDA-graph capturable).  The device buffers named by the descriptor must stay valid for the handle's life. */
+typedef struct lass_conv lass_conv;
+LASS_API int lass_conv_prepare(const lass_conv_desc* desc_host, lass_conv** conv_out);
+LASS_API int lass_conv_run(const lass_conv* conv, void* stream);
+LASS_API void lass_conv_destroy(lass_conv* conv);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Training step (BASELINE config 4): what the reference runs per step and rank through autograd --
+ * models/audiosep.py:99-111 (ss_model.train(): BatchNorm batch statistics, momentum 0.01; forward; l1_wav, losses.py:4-9;
+ * loss.backward()), models/audiosep.py:118-130 (AdamW, amsgrad) -- as explicit kernels.  Convolutions (forward and
+ * backward-data) run on lass_conv_*; the entries below are the rest.  Host driver: lass_b200/training.py.
+ *
+ * Tensors: NHWC 16-bit `x` with `cstride` channels per pixel, channels [coff, coff + C) addressed; `fp16` = 1 for fp16
+ * (raw conv outputs and, in training, activations), 0 for bf16 (gradients).  C, cstride, coff multiples of 8.
+ * bnp: per-BatchNorm-site block of 6*C floats [scale | shift | mean | rstd | coefA | coefB].
+ * ---------------------------------------------------------------------------------------------------- */
+/* sums (2, C) float64 = per-channel sum and sum of squares over all pixels (zeroed inside). */
+LASS_API int lass_bn_stats(const void* x, int fp16, long long npix, int C, int cstride, int coff, double* sums, void* stream);
+/* bn0 runs over the frequency axis (models/resunet.py:537-539): mag (B, T, F) fp32, sums (2, F) over (B, T). */
+LASS_API int lass_bn0_stats(const float* mag, int B, int T, int F, double* sums, void* stream);
+/* Batch statistics -> bnp[0 .. 4C) = gamma*rstd, beta - mean*gamma*rstd, mean, rstd (biased variance, eps inside the sqrt);
+ * running_mean / running_var updated in place with `momentum` and the unbiased variance, like nn.BatchNorm2d in train(). */
+LASS_API int lass_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, float momentum, float eps, int C, float* bnp, void* stream);
+/* out = leaky_relu(scale*x + shift + beta[b]) (slope 0.01): BatchNorm + FiLM beta + activation, models/resunet.py:159-160. */
+LASS_API int lass_bn_act(const void* x, int x_fp16, int x_cstride, int x_coff, void* out, int out_fp16, int out_cstride,
+                         int out_coff, int B, long long pix_per_clip, int C, const float* bnp, const float* beta,
+                         int beta_bstride, void* stream);
+/* Backward of the same site.  With g' = dact * leaky_relu'(scale*x + shift + beta):
+ *   reduce:   sums (B, C, 2) fp32 = per clip [sum g', sum g'*(x - mean)]                       (zeroed inside)
+ *   finalize: dgamma = rstd * sum g'(x-mean), dbeta = sum g', dfilm[b] = per-clip sum g' (the FiLM beta gradient, may be NULL),
+ *             bnp[4C .. 6C) = coefA, coefB
+ *   apply:    dx = scale*g' + coefA*(x - mean) + coefB (+ add)      (native_batch_norm_backward, batch statistics) */
+LASS_API int lass_bn_bwd_reduce(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride,
+                                int x_coff, int B, long long pix_per_clip, int C, const float* bnp, const float* beta,
+                                int beta_bstride, float* sums, void* stream);
+LASS_API int lass_bn_bwd_finalize(const float* sums, int B, int C, double count, const float* gamma, float* bnp,
+                                  float* dgamma, float* dbeta, float* dfilm, int dfilm_bstride, void* stream);
+LASS_API int lass_bn_bwd_apply(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride,
+                               int x_coff, const void* add, int add_cstride, int add_coff, void* dx, int dx_cstride,
+                               int dx_coff, int B, long long pix_per_clip, int C, const float* bnp, const float* beta,
+                               int beta_bstride, void* stream);
+/* avg_pool2d backward + skip-connection add (models/resunet.py:196-198): dy (B, H, W, C) = dskip + up(dpool) / (ph*pw). */
+LASS_API int lass_pool_bwd(const void* dpool, const void* dskip, int dskip_cstride, int dskip_coff, void* dy, int B, int H,
+                           int W, int C, int ph, int pw, void* stream);
+/* Gather for the transposed conv's backward (kernel = stride, models/resunet.py:216-224,256): dst (B, H, W, uh*uw*C) with
+ * dst[.., (dy*uw+dx)*C + c] = src[b, h*uh+dy, w*uw+dx, coff + c]; dgrad / wgrad of the transposed conv are then 1x1 GEMMs. */
+LASS_API int lass_unshuffle(const void* src, int src_cstride, int src_coff, void* dst, int B, int H, int W, int C, int uh,
+                            int uw, void* stream);
+/* out (C) fp32 = sum over pixels (bias gradient of the 1x1 shortcut convs). */
+LASS_API int lass_channel_sum(const void* x, long long npix, int C, int cstride, int coff, float* out, void* stream);
+/* Weight gradient dw (taps, co, ci) fp32 (overwritten) = sum_p dy[p, co] * x[p + tap, ci]; taps 9 (3x3, zero padding 1) or 1;
+ * dy bf16, x bf16 or fp16 (x_fp16); co, ci multiples of 32.  mma.sync bf16, fp32 accumulate, split over pixel ranges. */
+LASS_API int lass_wgrad(const void* dy, int dy_cstride, int dy_coff, int co, const void* x, int x_fp16, int x_cstride,
+                        int x_coff, int ci, int B, int H, int W, int taps, float* dw, void* stream);
+/* bn0 + zero time padding + Nyquist drop + pre_conv (models/resunet.py:537-555): x0 (B, Tp, Fp, 32) fp16; and its backward
+ * from dx0 (bf16): dpre_w, dpre_b (32), dgamma0, dbeta0 (F; the dropped Nyquist bin gets 0).  bnp0 = 6*F block of bn0. */
+LASS_API int lass_pre_fwd(const float* mag, int B, int T, int F, int Tp, int Fp, const float* bnp0, const float* pre_w,
+                          const float* pre_b, void* x0, void* stream);
+LASS_API int lass_pre_bwd(const void* dx0, const float* mag, int B, int T, int F, int Tp, int Fp, const float* bnp0,
+                          const float* pre_w, float* dpre_w, float* dpre_b, float* dgamma0, float* dbeta0, void* stream);
+/* after_conv (models/resunet.py:570) backward: dfeat (B, 3, npix) fp32, y (B, npix, 32) fp16 -> dy bf16, dw (3, 32), db (3). */
+LASS_API int lass_after_bwd(const float* dfeat, const void* y, const float* after_w, void* dy, float* dw, float* db, int B,
+                            long long npix, void* stream);
+/* Adjoint of torchlibrosa ISTFT.forward (Hermitian extension, IDFT * window, overlap-add, / window-sum, trim) up to the
+ * factor c_f / n_fft (applied by lass_mask_bwd): dre, dim (B, T, F) = STFT without padding of the zero-extended
+ * dwave / window-sum, on kernel K1 (fp32-parity mode).  Workspace as lass_stft_fwd. */
+LASS_API int lass_istft_bwd(const float* dwave, int B, int L, int n_fft, int hop, int T, const float* window,
+                            const void* basis_hi, const void* basis_lo, float* dre, float* dim, void* workspace,
+                            size_t workspace_bytes, void* stream);
+/* Backward of the mask of feature_maps_to_wav (models/resunet.py:457-505): feat / dfeat (B, 3, Tp, Fp) fp32. */
+LASS_API int lass_mask_bwd(const float* feat, const float* mag, const float* cos, const float* sin, const float* dre,
+                           const float* dim, float* dfeat, int B, int T, int F, int Tp, int Fp, int n_fft, void* stream);
+/* l1_wav (losses.py:4-9): *loss_sum += sum |wave - target|, dwave = sign(wave - target) * scale. */
+LASS_API int lass_l1_loss(const float* wave, const float* target, long long n, float* loss_sum, float* dwave, float scale,
+                          void* stream);
+/* FiLM linears backward (models/resunet.py:51-57): dw (J, K) = dbeta^T cond, db (J) = column sums of dbeta (B, J). */
+LASS_API int lass_film_bwd(const float* dbeta, const float* cond, float* dw, float* db, int B, int J, int K, void* stream);
+/* torch.optim.AdamW(amsgrad=True) single-tensor update over flat fp32 buffers (models/audiosep.py:122-130); step >= 1;
+ * the gradient is multiplied by grad_scale first (1 / world size after the NCCL sum). */
+LASS_API int lass_adamw_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, long long n, float lr, float beta1,
+                                float beta2, float eps, float weight_decay, int step, float grad_scale, void* stream);
+/* fp32 parameter in torch layout -> 16-bit kernel layouts (either may be NULL).  kind 0: conv (co, ci, taps) -> fwd
+ * (taps, co, ci) [fp16 if fwd_fp16 else bf16] and dgrad (taps, ci, co) bf16 with flipped taps; kind 1: transposed conv
+ * (ci, co, taps) -> fwd (taps*co, ci), dgrad (ci, taps*co).  lass_unpack_grad: packed (taps, co, ci) fp32 -> torch layout. */
+LASS_API int lass_pack_weight(const float* w, int kind, int co, int ci, int taps, void* fwd, int fwd_fp16, void* dgrad,
+                              void* stream);
+LASS_API int lass_unpack_grad(const float* dw, int kind, int co, int ci, int taps, float* grad, void* stream);
+/* Debug: 1 = the shared-memory Stockham iSTFT kernel for every n_fft (default: register-FFT kernel for 1024 / 2048). */
+LASS_API int lass_debug_set_istft_v1(int on);
+
 /* Debug: experiments on the conv kernel; read when a launch is PREPARED (lass_conv_igemm, plan creation).  0 = normal operation.
  * Knock-outs, results become wrong: 1 = epilogue skips math and stores, 2 = no tcgen05.mma issued, 4 = no activation (A) TMA
  * loads, 8 = no pooled outputs, 16 = no direct stores, 64 = MMA issuers only.

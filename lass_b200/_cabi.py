@@ -150,4 +150,32 @@ SIGNATURES.update({
     "lass_resunet30_plan_destroy": (None, [ctypes.c_void_p]),
 })
 
-
+# ---- prepared convs + training step ----
+_v, _i, _ll, _f, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double
+SIGNATURES.update({
+    "lass_conv_prepare": (_i, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_void_p)]),
+    "lass_conv_run": (_i, [_v, _v]),
+    "lass_conv_destroy": (None, [_v]),
+    "lass_bn_stats": (_i, [_v, _i, _ll, _i, _i, _i, _v, _v]),
+    "lass_bn0_stats": (_i, [_v, _i, _i, _i, _v, _v]),
+    "lass_bn_finalize": (_i, [_v, _d, _v, _v, _v, _v, _f, _f, _i, _v, _v]),
+    "lass_bn_act": (_i, [_v, _i, _i, _i, _v, _i, _i, _i, _i, _ll, _i, _v, _v, _i, _v]),
+    "lass_bn_bwd_reduce": (_i, [_v, _i, _i, _v, _i, _i, _i, _i, _ll, _i, _v, _v, _i, _v, _v]),
+    "lass_bn_bwd_finalize": (_i, [_v, _i, _i, _d, _v, _v, _v, _v, _v, _i, _v]),
+    "lass_bn_bwd_apply": (_i, [_v, _i, _i, _v, _i, _i, _i, _v, _i, _i, _v, _i, _i, _i, _ll, _i, _v, _v, _i, _v]),
+    "lass_pool_bwd": (_i, [_v, _v, _i, _i, _v, _i, _i, _i, _i, _i, _i, _v]),
+    "lass_unshuffle": (_i, [_v, _i, _i, _v, _i, _i, _i, _i, _i, _i, _v]),
+    "lass_channel_sum": (_i, [_v, _ll, _i, _i, _i, _v, _v]),
+    "lass_wgrad": (_i, [_v, _i, _i, _i, _v, _i, _i, _i, _i, _i, _i, _i, _i, _v, _v]),
+    "lass_pre_fwd": (_i, [_v, _i, _i, _i, _i, _i, _v, _v, _v, _v, _v]),
+    "lass_pre_bwd": (_i, [_v, _v, _i, _i, _i, _i, _i, _v, _v, _v, _v, _v, _v, _v]),
+    "lass_after_bwd": (_i, [_v, _v, _v, _v, _v, _v, _i, _ll, _v]),
+    "lass_istft_bwd": (_i, [_v, _i, _i, _i, _i, _i, _v, _v, _v, _v, _v, _v, ctypes.c_size_t, _v]),
+    "lass_mask_bwd": (_i, [_v, _v, _v, _v, _v, _v, _v, _i, _i, _i, _i, _i, _i, _v]),
+    "lass_l1_loss": (_i, [_v, _v, _ll, _v, _v, _f, _v]),
+    "lass_film_bwd": (_i, [_v, _v, _v, _v, _i, _i, _i, _v]),
+    "lass_adamw_amsgrad": (_i, [_v, _v, _v, _v, _v, _ll, _f, _f, _f, _f, _f, _i, _f, _v]),
+    "lass_pack_weight": (_i, [_v, _i, _i, _i, _i, _v, _i, _v, _v]),
+    "lass_unpack_grad": (_i, [_v, _i, _i, _i, _i, _v, _v]),
+    "lass_debug_set_istft_v1": (_i, [_i]),
+})

@@ -42,6 +42,20 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+int device_sm_count() {
+  static std::mutex mu;
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
 int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank, const uint64_t* dims,
                     const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
   EncodeTiledFn fn = get_encode_fn();
@@ -136,12 +150,45 @@ int lass_conv_igemm(const lass_conv_desc* desc_host, void* stream) {
   return e;
 }
 
+int lass_conv_prepare(const lass_conv_desc* desc_host, lass_conv** out) {
+  if (!desc_host || !out) return set_error(LASS_ERR_ARG, "lass_conv_prepare: null pointer");
+  ConvPrepared* cp = nullptr;
+  int e = conv_prepare(*desc_host, &cp);
+  *out = reinterpret_cast<lass_conv*>(cp);
+  return e;
+}
+
+int lass_conv_run(const lass_conv* conv, void* stream) {
+  if (!conv) return set_error(LASS_ERR_ARG, "lass_conv_run: null handle");
+  return conv_run(reinterpret_cast<const ConvPrepared*>(conv), (cudaStream_t)stream);
+}
+
+void lass_conv_destroy(lass_conv* conv) {
+  if (conv) conv_free(reinterpret_cast<ConvPrepared*>(conv));
+}
+
+int lass_istft_bwd(const float* dwave, int B, int L, int n_fft, int hop, int T, const float* window, const void* basis_hi,
+                   const void* basis_lo, float* dre, float* dim, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!dwave || !window || !basis_hi || !basis_lo || !dre || !dim || !workspace)
+    return set_error(LASS_ERR_ARG, "lass_istft_bwd: null pointer");
+  if (B <= 0 || n_fft < 256 || (n_fft & (n_fft - 1)) || hop <= 0 || hop % 8 || L <= n_fft / 2 || T != L / hop + 1)
+    return set_error(LASS_ERR_ARG, "lass_istft_bwd: bad shape B=%d L=%d n_fft=%d hop=%d T=%d", B, L, n_fft, hop, T);
+  if (workspace_bytes < stft_workspace_bytes(B, L, n_fft, hop)) return set_error(LASS_ERR_WORKSPACE, "lass_istft_bwd: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return set_error(LASS_ERR_ARG, "lass_istft_bwd: workspace not 256 B aligned");
+  return launch_stft(dwave, B, L, n_fft, hop, basis_hi, basis_lo, dre, nullptr, dim, 0, 2, workspace, (cudaStream_t)stream, window);
+}
+
 int lass_debug_set_conv_profile(long long* device_counters) {
 #ifndef LASS_CONV_PROFILE
   if (device_counters)
     return set_error(LASS_ERR_ARG, "conv profile: this build has no role profiler (make prof, LASS_B200_LIB=.../liblass_b200_prof.so)");
 #endif
   conv_set_profile_buffer(device_counters);
+  return 0;
+}
+
+int lass_debug_set_istft_v1(int on) {
+  mask_istft_force_v1(on);
   return 0;
 }
 

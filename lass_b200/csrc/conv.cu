@@ -174,10 +174,16 @@ __device__ __forceinline__ void store32(const OutDev& o, int b, int ho, int wo, 
   }
 }
 
-// raw output: the value itself as saturating fp16 (residual / skip stream)
-__device__ __forceinline__ void pack_raw32(const float* v, uint32_t* w) {
+// raw output: the value itself as saturating fp16 (residual / skip stream), or as bf16 (backward-data launches of the
+// training step: gradients span too many decades for fp16)
+__device__ __forceinline__ void pack_raw32(const float* v, uint32_t* w, bool f16 = true) {
+  if (f16) {
 #pragma unroll
-  for (int j = 0; j < 16; ++j) w[j] = pack_f16x2_sat(v[2 * j], v[2 * j + 1]);
+    for (int j = 0; j < 16; ++j) w[j] = pack_f16x2_sat(v[2 * j], v[2 * j + 1]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+  }
 }
 
 // activated output: lrelu(sc * v + sh) as bf16 (operand of the next convolution)
@@ -1038,7 +1044,7 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
           }
           if (FEAT(kFRaw, p.full_raw.ptr != nullptr)) {
             uint32_t wv[16];
-            pack_raw32(v, wv);
+            pack_raw32(v, wv, p.full_raw.fp16 != 0);
             if (FEAT(kFTma, tma_store)) stage_row32(stg, lane, wv);
             else store32(p.full_raw, it.b, ho, wo, Ho, Wo, c, wv, valid);
           }
@@ -1509,7 +1515,6 @@ KernelChoice make_choice() {
 
 int g_debug_flags = 0;
 long long* g_prof_buffer = nullptr;
-int g_num_sms = 0;
 
 }  // namespace
 
@@ -1553,7 +1558,8 @@ static int check_out(const ConvOut& o, const char* name, int ncols_eff) {
   if (reinterpret_cast<uintptr_t>(o.ptr) % 16) return set_error(LASS_ERR_ARG, "conv: output %s not 16 B aligned", name);
   if ((o.scale == nullptr) != (o.shift == nullptr)) return set_error(LASS_ERR_ARG, "conv: output %s needs scale AND shift", name);
   const bool is_raw = name[5] == 'r';   // "full_raw" / "pool_raw"
-  if (is_raw && (!o.fp16 || o.scale)) return set_error(LASS_ERR_ARG, "conv: %s must be fp16 without activation", name);
+  // (bf16 raw stores exist for the full-resolution output only: the backward-data launches of the training step)
+  if (is_raw && ((!o.fp16 && name[0] != 'f') || o.scale)) return set_error(LASS_ERR_ARG, "conv: %s must be fp16 without activation", name);
   if (!is_raw && (o.fp16 || !o.scale)) return set_error(LASS_ERR_ARG, "conv: %s must be bf16 with an activation table", name);
   return 0;
 }
@@ -1665,11 +1671,7 @@ static int conv_prepare_dxn(const ConvLaunch& l, ConvPrepared** out) {
   cp->smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes;
   cp->fn = cout == 32 ? conv_dxn_kernel<32, 2> : conv_dxn_kernel<64, 1>;
   cp->threads = kThreads;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
-  }
+  const int g_num_sms = device_sm_count();   // of the current device (per-device cache in api.cu)
   cudaError_t ce = cudaFuncSetAttribute(reinterpret_cast<const void*>(cp->fn), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (ce != cudaSuccess) {
     delete cp;
@@ -2061,11 +2063,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   }
   cp->smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes;
   cp->fn = kc.fn;
-  if (g_num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || g_num_sms <= 0) g_num_sms = 148;
-  }
+  const int g_num_sms = device_sm_count();   // of the current device (per-device cache in api.cu)
   // opt every instantiation in to the full 227 KiB (a later, smaller request must not lower the limit that an
   // already prepared launch of the same kernel relies on)
   cudaError_t ce = cudaFuncSetAttribute(reinterpret_cast<const void*>(kc.fn), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);

@@ -27,12 +27,17 @@ size_t stft_padded_len(int L, int n_fft, int hop);
 size_t stft_workspace_bytes(int B, int L, int n_fft, int hop);
 int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
                 float* mag, float* cosp, float* sinp, int precision_mode, int magphase_mode, void* workspace,
-                cudaStream_t stream);
+                cudaStream_t stream, const float* adjoint_window = nullptr);
+
+// SM count of the CURRENT device (cached per device ordinal; thread-safe)
+int device_sm_count();
 
 // ---- K5 mask + istft ----
 cudaError_t launch_mask_istft(const float* feat, long long feat_bstride, long long feat_cstride, int feat_tstride,
                               int feat_F, const float* mag, const float* cosp, const float* sinp,
                               const float* window, const float* tw, float* out, int B, int T, int F, int N,
                               int hop, int L, cudaStream_t stream);
+
+void mask_istft_force_v1(int on);
 
 }  // namespace lass

@@ -510,11 +510,9 @@ cudaError_t launch_v2(MaskIstftArgs a, int B, int T, cudaStream_t stream) {
   while (fixed + (size_t)(a.FR * a.hop + a.hop) * 4 > 112 * 1024 && a.FR > 8) a.FR -= 8;
   const size_t smem = fixed + (size_t)(a.FR * a.hop + a.hop) * 4;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(mask_istft_v2_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {  // per-device attribute, cheap: opted in to the full 227 KiB on every launch for the current device (no process-wide cache)
+    cudaError_t e = cudaFuncSetAttribute(mask_istft_v2_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   const long long P = (long long)(T - 1) * a.hop + N;
   const int S = a.FR * a.hop;
@@ -524,6 +522,10 @@ cudaError_t launch_v2(MaskIstftArgs a, int B, int T, cudaStream_t stream) {
 }
 
 }  // namespace
+
+// debug switch (lass_debug_set_istft_v1): the shared-memory Stockham kernel for every n_fft
+static int g_force_v1 = 0;
+void mask_istft_force_v1(int on) { g_force_v1 = on ? 1 : 0; }
 
 size_t mask_istft_smem_bytes(int N, int hop, int FR) {
   const int M = N / 2;
@@ -556,8 +558,7 @@ cudaError_t launch_mask_istft(const float* feat, long long feat_bstride, long lo
   a.log2M = log2N - 1;
   a.FR = 0;
   // register-FFT kernel for the two model shapes (hop must keep the window-table reads 8-byte aligned: always true)
-  const char* force_v1 = getenv("LASS_ISTFT_V1");
-  if (!(force_v1 && force_v1[0] == '1')) {
+  if (!g_force_v1) {
     if (N == 1024) return launch_v2<16>(a, B, T, stream);
     if (N == 2048) return launch_v2<32>(a, B, T, stream);
   }
@@ -569,11 +570,9 @@ cudaError_t launch_mask_istft(const float* feat, long long feat_bstride, long lo
     smem = mask_istft_smem_bytes(N, hop, a.FR);
   }
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  {
+    cudaError_t e = cudaFuncSetAttribute(mask_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
-    configured = smem;
   }
   const long long P = (long long)(T - 1) * hop + N;
   const int S = a.FR * hop;

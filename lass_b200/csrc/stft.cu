@@ -54,6 +54,12 @@ struct StftParams {
 // magnitude and unit phasor of one bin.  One MUFU.RSQ (2 ulp) instead of sqrt + two divisions: errors of a few 1e-7
 // relative, against the 1e-4 parity bar (tests/test_gpu_spectral.py).
 __device__ __forceinline__ void magphase(float re, float im, int mode, float& m, float& c, float& sn) {
+  if (mode == 2) {      // raw real / imaginary parts (the ISTFT adjoint of the training step, lass_istft_bwd)
+    m = re;
+    c = 0.0f;
+    sn = im;
+    return;
+  }
   const float p2 = re * re + im * im;
   // mode 0, models/base.py:85-87: mag = clamp(re^2 + im^2, 1e-10) ** 0.5 ; cos = re / mag ; sin = im / mag
   // mode 1, torchlibrosa.stft.magphase: mag = (re^2 + im^2) ** 0.5 ; cos = re / clamp(mag, 1e-10) ; sin likewise
@@ -195,7 +201,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
           if (t_mine < p.T) {
             const size_t o = row0_off + (size_t)lane * p.F + half;
             p.mag[o] = m;
-            p.cosp[o] = c1;
+            if (p.cosp) p.cosp[o] = c1;
             p.sinp[o] = s1;
           }
           im[0] = 0.0f;
@@ -205,6 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
         // three transposes through the warp's 32 x 33 buffer: lane = frame  ->  lane = bin, 128 B rows to global memory
 #pragma unroll
         for (int which = 0; which < 3; ++which) {
+          if (which == 1 && !p.cosp) continue;
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 32; ++j) tr[lane * kTrPitch + j] = which == 0 ? re[j] : (which == 1 ? cs[j] : im[j]);
@@ -247,6 +254,34 @@ __global__ void stft_prep_kernel(const float* __restrict__ wave, __nv_bfloat16* 
   xlo[(size_t)b * Lp + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
+// Adjoint of torchlibrosa ISTFT.forward's overlap-add: the waveform gradient, zero-extended to the frame grid and divided by
+// the window-sum (clamped at 1e-11 like the forward), split to bf16 hi / lo.  Sample i of the padded signal is position
+// i of y_full (frame t covers [t*hop, t*hop + n_fft)); the forward returned y_full[half : half + L] / wsum.
+__global__ void istft_bwd_prep_kernel(const float* __restrict__ dwave, const float* __restrict__ window,
+                                      __nv_bfloat16* __restrict__ xhi, __nv_bfloat16* __restrict__ xlo, int L, int Lp, int half,
+                                      int n_fft, int hop, int T) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Lp) return;
+  float v = 0.0f;
+  const int src = i - half;
+  if (src >= 0 && src < L) {
+    int ta = (i - n_fft) / hop + 1;
+    if (i - n_fft < 0) ta = 0;
+    int tz = i / hop;
+    if (tz > T - 1) tz = T - 1;
+    float ws = 0.0f;
+    for (int t = ta; t <= tz; ++t) {
+      const float w = __ldg(window + (i - t * hop));
+      ws = fmaf(w, w, ws);
+    }
+    v = dwave[(size_t)b * L + src] / fmaxf(ws, 1e-11f);
+  }
+  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+  xhi[(size_t)b * Lp + i] = hi;
+  xlo[(size_t)b * Lp + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
 }  // namespace
 
 // 128 bins per tile; the Nyquist bin travels in the (empty) imaginary slot of bin 0, so n_fft/2 bins need tiles
@@ -262,7 +297,7 @@ size_t stft_workspace_bytes(int B, int L, int n_fft, int hop) {
 
 int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
                 float* mag, float* cosp, float* sinp, int precision_mode, int magphase_mode, void* workspace,
-                cudaStream_t stream) {
+                cudaStream_t stream, const float* adjoint_window) {
   if (n_fft % BK != 0 || (n_fft / 2) % kBinsPerTile != 0 || hop % 8 != 0 || L <= n_fft / 2) return LASS_ERR_ARG;
   const int T = L / hop + 1;
   const int F = n_fft / 2 + 1;
@@ -271,7 +306,10 @@ int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void*
   __nv_bfloat16* xlo = xhi + (size_t)B * Lp;
   {
     dim3 grid((unsigned)((Lp + 255) / 256), (unsigned)B);
-    stft_prep_kernel<<<grid, 256, 0, stream>>>(wave, xhi, xlo, L, (int)Lp, n_fft / 2);
+    if (adjoint_window)
+      istft_bwd_prep_kernel<<<grid, 256, 0, stream>>>(wave, adjoint_window, xhi, xlo, L, (int)Lp, n_fft / 2, n_fft, hop, T);
+    else
+      stft_prep_kernel<<<grid, 256, 0, stream>>>(wave, xhi, xlo, L, (int)Lp, n_fft / 2);
   }
   StftParams p;
   const int ntn = stft_num_ntiles(n_fft);
@@ -301,23 +339,15 @@ int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void*
   p.F = F;
   p.n_fft = n_fft;
   p.split = precision_mode == 0 ? 1 : 0;
-  p.magphase_mode = magphase_mode ? 1 : 0;
+  p.magphase_mode = magphase_mode;
   p.n_tiles = ntn;
   p.m_tiles = (T + BM - 1) / BM;
   p.num_items = ntn * p.m_tiles * B;
   const size_t smem = (size_t)kStages * kStageBytes + kEpiWarps * kTrFloats * sizeof(float) + 1024 + 256;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return set_cuda_error(e, "stft smem attribute");
-    configured = true;
-  }
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || num_sms <= 0) num_sms = 148;
-  }
+  // the opt-in is per device and cheap: set it on every launch for the CURRENT device (no process-wide cache)
+  cudaError_t ea = cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ea != cudaSuccess) return set_cuda_error(ea, "stft smem attribute");
+  const int num_sms = device_sm_count();
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
   stft_gemm_kernel<<<grid, kThreads, smem, stream>>>(p);
   return set_cuda_error(cudaGetLastError(), "stft launch");

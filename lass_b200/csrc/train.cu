@@ -1,0 +1,835 @@
+// Training step: the memory-bound kernels around the convolutions (BASELINE config 4).
+//
+// Replaces, per training step of the reference (models/audiosep.py:99-111 with ss_model.train(), autograd, AdamW):
+//   nn.BatchNorm2d in batch-statistics mode (33 sites) + FiLM add + leaky_relu  -> bn_stats / bn_finalize / bn_act
+//   their autograd backward (native_batch_norm_backward, leaky_relu_backward)     -> bn_bwd_reduce / finalize / apply
+//   avg_pool2d backward + the skip-connection gradient add                         -> pool_bwd
+//   conv_transpose2d(kernel = stride) backward's gather                            -> unshuffle (the GEMMs run in conv.cu / wgrad.cu)
+//   bn0 + pad + pre_conv forward / backward (models/resunet.py:537-555)            -> bn0_stats / pre_fwd / pre_bwd
+//   after_conv backward (:570), mask backward (:457-505), ISTFT adjoint            -> after_bwd / mask_bwd / istft_bwd (stft.cu)
+//   l1_wav (losses.py:4-9), FiLM linears backward, AdamW(amsgrad) (models/audiosep.py:122-130)
+//
+// Tensors: NHWC 16-bit with a channel stride / offset (slices of the concat buffers), fp16 or bf16 per flag; all math fp32.
+// Every kernel maps one thread to a 16-byte vector of 8 channels, consecutive threads to consecutive vectors.
+#include "lass_internal.cuh"
+
+namespace lass {
+namespace {
+
+constexpr float kSlope = 0.01f;
+constexpr int kRedThreads = 384;   // divisible by C/8 for every channel count of the model (4 .. 96 vectors)
+
+struct V8 {
+  float v[8];
+};
+
+__device__ __forceinline__ V8 load8(const void* base, size_t elem_off, int fp16) {
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + elem_off));
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  V8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (fp16) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      r.v[2 * i] = f.x;
+      r.v[2 * i + 1] = f.y;
+    } else {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  return r;
+}
+
+__device__ __forceinline__ void store8(void* base, size_t elem_off, int fp16, const V8& r) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (fp16) {
+      const float a = fminf(fmaxf(r.v[2 * i], -65504.0f), 65504.0f), b = fminf(fmaxf(r.v[2 * i + 1], -65504.0f), 65504.0f);
+      const __half2 h = __floats2half2_rn(a, b);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    } else {
+      const __nv_bfloat162 h = __floats2bfloat162_rn(r.v[2 * i], r.v[2 * i + 1]);
+      w[i] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+  }
+  *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(base) + elem_off) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__device__ __forceinline__ V8 ldf8(const float* p) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  V8 r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// per-channel reductions over pixels: block = 384 threads = R pixel rows x CV channel vectors
+// ---------------------------------------------------------------------------------------------------------------
+// NACC accumulators per channel.  After the grid-stride loop the R partial rows of a block are summed through shared memory.
+template <int NACC>
+__device__ __forceinline__ void block_reduce_rows(float (&acc)[NACC][8], int CV, int R, int cv, int prow, float* red /* [R][CV*8*NACC] */) {
+  const int width = CV * 8 * NACC;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[prow * width + (a * CV + cv) * 8 + i] = acc[a][i];
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(const void* __restrict__ x, int fp16, long long npix, int C, int cstride,
+                                                               int coff, double* __restrict__ sums) {
+  extern __shared__ float red[];
+  const int CV = C / 8, R = kRedThreads / CV;
+  const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.0f;
+  for (long long p = (long long)blockIdx.x * R + prow; p < npix; p += (long long)gridDim.x * R) {
+    const V8 v = load8(x, (size_t)p * cstride + coff + cv * 8, fp16);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[0][i] += v.v[i];
+      acc[1][i] = fmaf(v.v[i], v.v[i], acc[1][i]);
+    }
+  }
+  block_reduce_rows<2>(acc, CV, R, cv, prow, red);
+  const int width = C * 2;
+  for (int e = threadIdx.x; e < width; e += kRedThreads) {
+    double s = 0.0;
+    for (int r = 0; r < R; ++r) s += (double)red[r * width + e];
+    atomicAdd(&sums[e], s);          // e < C: sum, e >= C: sum of squares  (layout (2, C))
+  }
+}
+
+__global__ void bn0_stats_kernel(const float* __restrict__ mag, int rows, int F, int rows_per_block, double* __restrict__ sums) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  const int r0 = blockIdx.y * rows_per_block;
+  const int r1 = min(rows, r0 + rows_per_block);
+  float s = 0.0f, q = 0.0f;
+  for (int r = r0; r < r1; ++r) {
+    const float v = __ldg(mag + (size_t)r * F + f);
+    s += v;
+    q = fmaf(v, v, q);
+  }
+  atomicAdd(&sums[f], (double)s);
+  atomicAdd(&sums[F + f], (double)q);
+}
+
+// bnp = [scale | shift | mean | rstd | coefA | coefB] x C
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float momentum, float eps, int C, float* __restrict__ bnp) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const double scale = (double)gamma[c] * rstd;
+  bnp[c] = (float)scale;
+  bnp[C + c] = (float)((double)beta[c] - mean * scale);
+  bnp[2 * C + c] = (float)mean;
+  bnp[3 * C + c] = (float)rstd;
+  const double unbiased = var * (count / fmax(count - 1.0, 1.0));
+  running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+  running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+}
+
+__global__ void __launch_bounds__(256) bn_act_kernel(const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
+                                                     void* __restrict__ out, int out_fp16, int out_cstride, int out_coff,
+                                                     long long pix_per_clip, long long nvec, int C, const float* __restrict__ bnp,
+                                                     const float* __restrict__ beta, int beta_bstride) {
+  const int CV = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / CV;
+    const int c = (int)(i - p * CV) * 8;
+    const int b = (int)(p / pix_per_clip);
+    const V8 v = load8(x, (size_t)p * x_cstride + x_coff + c, x_fp16);
+    const V8 sc = ldf8(bnp + c), sh = ldf8(bnp + C + c), be = ldf8(beta + (size_t)b * beta_bstride + c);
+    V8 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float pre = fmaf(sc.v[k], v.v[k], sh.v[k]) + be.v[k];
+      r.v[k] = pre > 0.0f ? pre : kSlope * pre;
+    }
+    store8(out, (size_t)p * out_cstride + out_coff + c, out_fp16, r);
+  }
+}
+
+// sums (B, C, 2): [sum g', sum g' (x - mean)] per clip; grid.y = clip
+__global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
+                                                                    const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
+                                                                    long long pix_per_clip, int C, const float* __restrict__ bnp,
+                                                                    const float* __restrict__ beta, int beta_bstride,
+                                                                    float* __restrict__ sums) {
+  extern __shared__ float red[];
+  const int CV = C / 8, R = kRedThreads / CV;
+  const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
+  const int b = blockIdx.y, c = cv * 8;
+  const V8 sc = ldf8(bnp + c), sh = ldf8(bnp + C + c), mean = ldf8(bnp + 2 * C + c), be = ldf8(beta + (size_t)b * beta_bstride + c);
+  float acc[2][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.0f;
+  for (long long q = (long long)blockIdx.x * R + prow; q < pix_per_clip; q += (long long)gridDim.x * R) {
+    const size_t p = (size_t)b * pix_per_clip + q;
+    const V8 xv = load8(x, p * x_cstride + x_coff + c, x_fp16);
+    const V8 dv = load8(dact, p * d_cstride + d_coff + c, 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float pre = fmaf(sc.v[i], xv.v[i], sh.v[i]) + be.v[i];
+      const float g = pre > 0.0f ? dv.v[i] : kSlope * dv.v[i];
+      acc[0][i] += g;
+      acc[1][i] = fmaf(g, xv.v[i] - mean.v[i], acc[1][i]);
+    }
+  }
+  block_reduce_rows<2>(acc, CV, R, cv, prow, red);
+  const int width = C * 2;
+  for (int e = threadIdx.x; e < width; e += kRedThreads) {
+    float s = 0.0f;
+    for (int r = 0; r < R; ++r) s += red[r * width + e];
+    const int a = e / C, ch = e - a * C;
+    atomicAdd(&sums[((size_t)b * C + ch) * 2 + a], s);
+  }
+}
+
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int B, int C, double count, const float* __restrict__ gamma,
+                                       float* __restrict__ bnp, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                       float* __restrict__ dfilm, int dfilm_bstride) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double t1 = 0.0, t2 = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float s1 = sums[((size_t)b * C + c) * 2], s2 = sums[((size_t)b * C + c) * 2 + 1];
+    t1 += (double)s1;
+    t2 += (double)s2;
+    if (dfilm) dfilm[(size_t)b * dfilm_bstride + c] = s1;
+  }
+  const double scale = (double)bnp[c], rstd = (double)bnp[3 * C + c];
+  dbeta[c] = (float)t1;
+  dgamma[c] = (float)(rstd * t2);
+  bnp[4 * C + c] = (float)(-scale * rstd * rstd * t2 / count);
+  bnp[5 * C + c] = (float)(-scale * t1 / count);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
+                                                           const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
+                                                           const void* __restrict__ add, int add_cstride, int add_coff,
+                                                           void* __restrict__ dx, int dx_cstride, int dx_coff, long long pix_per_clip,
+                                                           long long nvec, int C, const float* __restrict__ bnp,
+                                                           const float* __restrict__ beta, int beta_bstride) {
+  const int CV = C / 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / CV;
+    const int c = (int)(i - p * CV) * 8;
+    const int b = (int)(p / pix_per_clip);
+    const V8 xv = load8(x, (size_t)p * x_cstride + x_coff + c, x_fp16);
+    const V8 dv = load8(dact, (size_t)p * d_cstride + d_coff + c, 0);
+    const V8 sc = ldf8(bnp + c), sh = ldf8(bnp + C + c), mean = ldf8(bnp + 2 * C + c), ca = ldf8(bnp + 4 * C + c),
+             cb = ldf8(bnp + 5 * C + c), be = ldf8(beta + (size_t)b * beta_bstride + c);
+    V8 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float pre = fmaf(sc.v[k], xv.v[k], sh.v[k]) + be.v[k];
+      const float g = pre > 0.0f ? dv.v[k] : kSlope * dv.v[k];
+      r.v[k] = fmaf(sc.v[k], g, fmaf(ca.v[k], xv.v[k] - mean.v[k], cb.v[k]));
+    }
+    if (add) {
+      const V8 av = load8(add, (size_t)p * add_cstride + add_coff + c, 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r.v[k] += av.v[k];
+    }
+    store8(dx, (size_t)p * dx_cstride + dx_coff + c, 0, r);
+  }
+}
+
+__global__ void __launch_bounds__(256) pool_bwd_kernel(const void* __restrict__ dpool, const void* __restrict__ dskip, int s_cstride,
+                                                       int s_coff, void* __restrict__ dy, int B, int H, int W, int C, int ph, int pw) {
+  const int CV = C / 8;
+  const long long nvec = (long long)B * H * W * CV;
+  const float inv = 1.0f / (float)(ph * pw);
+  const int Hp = H / ph, Wp = W / pw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const long long p = i / CV;
+    const int c = (int)(i - p * CV) * 8;
+    const int w = (int)(p % W);
+    const long long t = p / W;
+    const int h = (int)(t % H), b = (int)(t / H);
+    const V8 dp = load8(dpool, (((size_t)b * Hp + h / ph) * Wp + w / pw) * C + c, 0);
+    V8 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = dp.v[k] * inv;
+    if (dskip) {
+      const V8 ds = load8(dskip, (size_t)p * s_cstride + s_coff + c, 0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) r.v[k] += ds.v[k];
+    }
+    store8(dy, (size_t)p * C + c, 0, r);
+  }
+}
+
+// dst (B, H, W, uh*uw*C)[(dy*uw + dx)*C + c] = src (B, H*uh, W*uw, cstride)[h*uh + dy, w*uw + dx, coff + c]   (16-byte copies)
+__global__ void __launch_bounds__(256) unshuffle_kernel(const uint16_t* __restrict__ src, int cstride, int coff, uint16_t* __restrict__ dst,
+                                                        int B, int H, int W, int C, int uh, int uw) {
+  const int CV = C / 8, G = uh * uw;
+  const long long nvec = (long long)B * H * W * G * CV;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i % CV);
+    long long t = i / CV;
+    const int g = (int)(t % G);
+    t /= G;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H), b = (int)(t / H);
+    const int dy = g / uw, dx = g - dy * uw;
+    const size_t sp = (((size_t)b * H * uh + (size_t)h * uh + dy) * (size_t)(W * uw) + (size_t)w * uw + dx);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src + sp * cstride + coff + cv * 8));
+    *reinterpret_cast<uint4*>(dst + (size_t)i * 8) = q;
+  }
+}
+
+__global__ void __launch_bounds__(kRedThreads) channel_sum_kernel(const void* __restrict__ x, long long npix, int C, int cstride, int coff,
+                                                                  float* __restrict__ out) {
+  extern __shared__ float red[];
+  const int CV = C / 8, R = kRedThreads / CV;
+  const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
+  float acc[1][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[0][i] = 0.0f;
+  for (long long p = (long long)blockIdx.x * R + prow; p < npix; p += (long long)gridDim.x * R) {
+    const V8 v = load8(x, (size_t)p * cstride + coff + cv * 8, 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[0][i] += v.v[i];
+  }
+  block_reduce_rows<1>(acc, CV, R, cv, prow, red);
+  for (int e = threadIdx.x; e < C; e += kRedThreads) {
+    float s = 0.0f;
+    for (int r = 0; r < R; ++r) s += red[r * C + e];
+    atomicAdd(&out[e], s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// bn0 + zero time padding + Nyquist drop + pre_conv (1 -> 32), reference models/resunet.py:537-555
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pre_fwd_kernel(const float* __restrict__ mag, int B, int T, int F, int Tp, int Fp,
+                                                      const float* __restrict__ bnp0, const float* __restrict__ pre_w,
+                                                      const float* __restrict__ pre_b, void* __restrict__ x0) {
+  const long long nvec = (long long)B * Tp * Fp * 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    const int cv = (int)(i & 3);
+    const long long p = i >> 2;
+    const int w = (int)(p % Fp);
+    const long long t = p / Fp;
+    const int h = (int)(t % Tp), b = (int)(t / Tp);
+    float xbn = 0.0f;
+    if (h < T) xbn = fmaf(__ldg(bnp0 + w), __ldg(mag + ((size_t)b * T + h) * F + w), __ldg(bnp0 + F + w));
+    const V8 wv = ldf8(pre_w + cv * 8), bv = ldf8(pre_b + cv * 8);
+    V8 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = fmaf(wv.v[k], xbn, bv.v[k]);
+    store8(x0, (size_t)p * 32 + cv * 8, 1, r);
+  }
+}
+
+// One thread per (pixel, 8-channel vector); a block covers kPreRows image rows x 64 columns (256 threads = 64 px x 4 vectors).
+// Outputs (all accumulated with atomics into zeroed buffers): dpre_w[32], dpre_b[32], dgamma0[F], dbeta0[F].
+constexpr int kPreRows = 16;
+__global__ void __launch_bounds__(256) pre_bwd_kernel(const void* __restrict__ dx0, const float* __restrict__ mag, int B, int T, int F, int Tp,
+                                                      int Fp, const float* __restrict__ bnp0, const float* __restrict__ pre_w,
+                                                      float* __restrict__ dpre_w, float* __restrict__ dpre_b,
+                                                      float* __restrict__ dgamma0, float* __restrict__ dbeta0) {
+  __shared__ float red[2][8][32];     // [w|b][warp][channel]
+  const int cv = threadIdx.x & 3, col = threadIdx.x >> 2;
+  const int w = blockIdx.x * 64 + col;
+  const int b = blockIdx.z;
+  const int h0 = blockIdx.y * kPreRows;
+  const V8 pw = ldf8(pre_w + cv * 8);
+  float aw[8], ab[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) aw[k] = ab[k] = 0.0f;
+  float dg = 0.0f, db = 0.0f;
+  const bool wok = w < Fp;
+  const float sc0 = wok ? __ldg(bnp0 + w) : 0.0f, sh0 = wok ? __ldg(bnp0 + F + w) : 0.0f;
+  const float mean0 = wok ? __ldg(bnp0 + 2 * F + w) : 0.0f, rstd0 = wok ? __ldg(bnp0 + 3 * F + w) : 0.0f;
+  for (int h = h0; h < min(Tp, h0 + kPreRows); ++h) {
+    float part = 0.0f, xbn = 0.0f, xhat = 0.0f;
+    if (wok) {
+      const V8 d = load8(dx0, (((size_t)b * Tp + h) * Fp + w) * 32 + cv * 8, 0);
+      if (h < T) {
+        const float m = __ldg(mag + ((size_t)b * T + h) * F + w);
+        xbn = fmaf(sc0, m, sh0);
+        xhat = (m - mean0) * rstd0;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        ab[k] += d.v[k];
+        aw[k] = fmaf(d.v[k], xbn, aw[k]);
+        part = fmaf(d.v[k], pw.v[k], part);
+      }
+    }
+    // dxbn of the pixel = sum over its four channel vectors (lanes cv = 0..3 are adjacent)
+    part += __shfl_xor_sync(0xffffffffu, part, 1);
+    part += __shfl_xor_sync(0xffffffffu, part, 2);
+    if (h < T) {
+      dg = fmaf(part, xhat, dg);
+      db += part;
+    }
+  }
+  if (wok && cv == 0) {
+    atomicAdd(&dgamma0[w], dg);
+    atomicAdd(&dbeta0[w], db);
+  }
+  // channel sums: reduce over the 8 pixels of a warp (lanes with equal cv), then over the 8 warps through shared memory
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      aw[k] += __shfl_xor_sync(0xffffffffu, aw[k], o);
+      ab[k] += __shfl_xor_sync(0xffffffffu, ab[k], o);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 4) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[0][warp][lane * 8 + k] = aw[k];
+      red[1][warp][lane * 8 + k] = ab[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int which = threadIdx.x >> 5, c = threadIdx.x & 31;
+    float s = 0.0f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) s += red[which][wp][c];
+    atomicAdd(which == 0 ? &dpre_w[c] : &dpre_b[c], s);
+  }
+}
+
+// after_conv (32 -> 3, 1x1) backward: thread = (pixel, 8-channel vector), 64 pixels per 256-thread block iteration
+__global__ void __launch_bounds__(256) after_bwd_kernel(const float* __restrict__ dfeat, const void* __restrict__ y,
+                                                        const float* __restrict__ after_w, void* __restrict__ dy,
+                                                        float* __restrict__ dw, float* __restrict__ db, int B, long long npix) {
+  __shared__ float red[8][4][27];
+  const int cv = threadIdx.x & 3;
+  V8 w[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) w[k] = ldf8(after_w + k * 32 + cv * 8);
+  float aw[3][8], ab[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aw[k][i] = 0.0f;
+  const long long total = (long long)B * npix;
+  for (long long p = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); p < total; p += (long long)gridDim.x * 64) {
+    const long long b = p / npix, q = p - b * npix;
+    float df[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) df[k] = __ldg(dfeat + ((size_t)b * 3 + k) * npix + q);
+    const V8 yv = load8(y, (size_t)p * 32 + cv * 8, 1);
+    V8 r;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      r.v[i] = df[0] * w[0].v[i] + df[1] * w[1].v[i] + df[2] * w[2].v[i];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) aw[k][i] = fmaf(df[k], yv.v[i], aw[k][i]);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) ab[k] += df[k];
+    store8(dy, (size_t)p * 32 + cv * 8, 0, r);
+  }
+  // reduce over the 8 pixels of a warp (lanes with equal cv), then over warps
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      ab[k] += __shfl_xor_sync(0xffffffffu, ab[k], o);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) aw[k][i] += __shfl_xor_sync(0xffffffffu, aw[k][i], o);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 4) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[warp][lane][k * 8 + i] = aw[k][i];
+      red[warp][lane][24 + k] = ab[k];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 96) {
+    const int k = threadIdx.x / 32, c = threadIdx.x % 32;
+    float s = 0.0f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) s += red[wp][c >> 3][k * 8 + (c & 7)];
+    atomicAdd(&dw[k * 32 + c], s);
+  } else if (threadIdx.x < 99) {
+    const int k = threadIdx.x - 96;
+    float s = 0.0f;
+#pragma unroll
+    for (int wp = 0; wp < 8; ++wp) s += red[wp][0][24 + k];
+    atomicAdd(&db[k], s);
+  }
+}
+
+// backward of feature_maps_to_wav's mask (reference models/resunet.py:457-505) for one (b, t, f < Fp)
+__global__ void __launch_bounds__(256) mask_bwd_kernel(const float* __restrict__ feat, const float* __restrict__ mag,
+                                                       const float* __restrict__ cosp, const float* __restrict__ sinp,
+                                                       const float* __restrict__ dre, const float* __restrict__ dim_,
+                                                       float* __restrict__ dfeat, int B, int T, int F, int Tp, int Fp, float inv_n) {
+  const long long total = (long long)B * Tp * Fp;
+  const size_t plane = (size_t)Tp * Fp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % Fp);
+    const long long tt = i / Fp;
+    const int t = (int)(tt % Tp), b = (int)(tt / Tp);
+    const size_t fo = (size_t)b * 3 * plane + (size_t)t * Fp + f;
+    float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+    if (t < T) {
+      const size_t so = ((size_t)b * T + t) * F + f;
+      const float cf = (f == 0 ? 1.0f : 2.0f) * inv_n;      // bins 1 .. n/2-1 appear twice in the Hermitian extension (f < Fp = n/2)
+      const float gre = __ldg(dre + so) * cf, gim = __ldg(dim_ + so) * cf;
+      const float x0 = __ldg(feat + fo), x1 = __ldg(feat + fo + plane), x2 = __ldg(feat + fo + 2 * plane);
+      const float mg = __ldg(mag + so), cs = __ldg(cosp + so), sn = __ldg(sinp + so);
+      const float m = 1.0f / (1.0f + __expf(-x0));
+      const float a = tanhf(x1), bb = tanhf(x2);
+      const float r = sqrtf(a * a + bb * bb);
+      const float rc = fmaxf(r, 1e-10f);
+      const float mc = a / rc, ms = bb / rc;
+      const float cy = cs * mc - sn * ms, sy = sn * mc + cs * ms;
+      const float absy = mg * m;
+      const float dabs = gre * cy + gim * sy;
+      const float dcy = gre * absy, dsy = gim * absy;
+      const float dmc = dcy * cs + dsy * sn, dms = -dcy * sn + dsy * cs;
+      float da, dbb;
+      if (r > 1e-10f) {
+        const float inv3 = 1.0f / (rc * rc * rc);
+        da = bb * inv3 * (dmc * bb - dms * a);
+        dbb = a * inv3 * (dms * a - dmc * bb);
+      } else {
+        da = dmc * 1e10f;
+        dbb = dms * 1e10f;
+      }
+      d0 = dabs * mg * m * (1.0f - m);
+      d1 = da * (1.0f - a * a);
+      d2 = dbb * (1.0f - bb * bb);
+    }
+    dfeat[fo] = d0;
+    dfeat[fo + plane] = d1;
+    dfeat[fo + 2 * plane] = d2;
+  }
+}
+
+__global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ wave, const float* __restrict__ target, long long n,
+                                                      float* __restrict__ loss_sum, float* __restrict__ dwave, float scale) {
+  __shared__ float red[8];
+  float s = 0.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = wave[i] - target[i];
+    s += fabsf(d);
+    dwave[i] = d > 0.0f ? scale : (d < 0.0f ? -scale : 0.0f);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.0f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(loss_sum, t);
+  }
+}
+
+// dw (J, K) = dbeta^T cond ; db (J) = column sums of dbeta.  Thread = (j, 4 consecutive k).
+__global__ void __launch_bounds__(128) film_bwd_kernel(const float* __restrict__ dbeta, const float* __restrict__ cond,
+                                                       float* __restrict__ dw, float* __restrict__ db, int B, int J, int K) {
+  const int j = blockIdx.x;
+  float s = 0.0f;
+  for (int k0 = threadIdx.x * 4; k0 < K; k0 += 128 * 4) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) {
+      const float d = __ldg(dbeta + (size_t)b * J + j);
+      const float4 c = __ldg(reinterpret_cast<const float4*>(cond + (size_t)b * K + k0));
+      acc.x = fmaf(d, c.x, acc.x);
+      acc.y = fmaf(d, c.y, acc.y);
+      acc.z = fmaf(d, c.z, acc.z);
+      acc.w = fmaf(d, c.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(dw + (size_t)j * K + k0) = acc;
+  }
+  if (threadIdx.x == 0) {
+    for (int b = 0; b < B; ++b) s += __ldg(dbeta + (size_t)b * J + j);
+    db[j] = s;
+  }
+}
+
+// Same operation order as torch.optim.adamw's single-tensor path (see oracle/train_oracle.py::adamw_amsgrad_step).
+__global__ void __launch_bounds__(256) adamw_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                            float* __restrict__ v, float* __restrict__ vmax, long long n, float decay,
+                                                            float one_minus_b1, float b2, float one_minus_b2, float bc2_sqrt, float eps,
+                                                            float neg_step_size, float grad_scale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = __fmul_rn(g[i], grad_scale);
+    float pi = __fmul_rn(p[i], decay);
+    float mi = m[i];
+    mi = __fadd_rn(mi, __fmul_rn(one_minus_b1, __fsub_rn(gi, mi)));                         // lerp_
+    float vi = __fmul_rn(v[i], b2);
+    vi = __fadd_rn(vi, __fmul_rn(__fmul_rn(one_minus_b2, gi), gi));                         // addcmul_
+    const float vm = fmaxf(vmax[i], vi);
+    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vm), bc2_sqrt), eps);
+    pi = __fadd_rn(pi, __fmul_rn(neg_step_size, __fdiv_rn(mi, denom)));                     // addcdiv_
+    p[i] = pi;
+    m[i] = mi;
+    v[i] = vi;
+    vmax[i] = vm;
+  }
+}
+
+// fp32 parameter (torch layout) -> 16-bit kernel layouts; thread per source element
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int kind, int co, int ci, int taps,
+                                                          void* __restrict__ fwd, int fwd_fp16, void* __restrict__ dgrad) {
+  const long long n = (long long)co * ci * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const long long r = i / taps;
+    int o, c;
+    size_t fi, di;
+    if (kind == 0) {            // conv (co, ci, taps): fwd (taps, co, ci); dgrad (taps, ci, co) with flipped taps
+      c = (int)(r % ci);
+      o = (int)(r / ci);
+      fi = ((size_t)t * co + o) * ci + c;
+      di = ((size_t)(taps - 1 - t) * ci + c) * co + o;
+    } else {                    // transposed conv (ci, co, taps): fwd (taps*co, ci); dgrad (ci, taps*co)
+      o = (int)(r % co);
+      c = (int)(r / co);
+      fi = ((size_t)t * co + o) * ci + c;
+      di = (size_t)c * taps * co + (size_t)t * co + o;
+    }
+    const float val = w[i];
+    if (fwd) {
+      if (fwd_fp16) reinterpret_cast<__half*>(fwd)[fi] = __float2half_rn(fminf(fmaxf(val, -65504.0f), 65504.0f));
+      else reinterpret_cast<__nv_bfloat16*>(fwd)[fi] = __float2bfloat16_rn(val);
+    }
+    if (dgrad) reinterpret_cast<__nv_bfloat16*>(dgrad)[di] = __float2bfloat16_rn(val);
+  }
+}
+
+// packed fp32 gradient (taps, co, ci) -> torch layout; thread per destination element
+__global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restrict__ dw, int kind, int co, int ci, int taps,
+                                                          float* __restrict__ grad) {
+  const long long n = (long long)co * ci * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int t = (int)(i % taps);
+    const long long r = i / taps;
+    int o, c;
+    if (kind == 0) {
+      c = (int)(r % ci);
+      o = (int)(r / ci);
+    } else {
+      o = (int)(r % co);
+      c = (int)(r / co);
+    }
+    grad[i] = dw[((size_t)t * co + o) * ci + c];
+  }
+}
+
+int grid_for(long long work_items, int threads, int max_blocks = 148 * 8) {
+  long long b = (work_items + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return (int)b;
+}
+
+bool chan_ok(int C, int cstride, int coff) { return C > 0 && C % 8 == 0 && cstride % 8 == 0 && coff % 8 == 0 && coff + C <= cstride && kRedThreads % (C / 8) == 0; }
+
+}  // namespace
+}  // namespace lass
+
+using namespace lass;
+
+#define LASS_LAUNCH_CHECK(what) return set_cuda_error(cudaGetLastError(), what)
+
+extern "C" {
+
+int lass_bn_stats(const void* x, int fp16, long long npix, int C, int cstride, int coff, double* sums, void* stream_v) {
+  if (!x || !sums || npix <= 0 || !chan_ok(C, cstride, coff)) return set_error(LASS_ERR_ARG, "lass_bn_stats: bad argument (C=%d cstride=%d coff=%d)", C, cstride, coff);
+  cudaStream_t s = (cudaStream_t)stream_v;
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
+  const int R = kRedThreads / (C / 8);
+  const int grid = grid_for(npix, R * 8, 148 * 4);
+  bn_stats_kernel<<<grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), s>>>(x, fp16, npix, C, cstride, coff, sums);
+  LASS_LAUNCH_CHECK("bn_stats launch");
+}
+
+int lass_bn0_stats(const float* mag, int B, int T, int F, double* sums, void* stream_v) {
+  if (!mag || !sums || B <= 0 || T <= 0 || F <= 0) return set_error(LASS_ERR_ARG, "lass_bn0_stats: bad argument");
+  cudaStream_t s = (cudaStream_t)stream_v;
+  cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F, s);
+  const int rows = B * T, rpb = 64;
+  dim3 grid((unsigned)((F + 127) / 128), (unsigned)((rows + rpb - 1) / rpb));
+  bn0_stats_kernel<<<grid, 128, 0, s>>>(mag, rows, F, rpb, sums);
+  LASS_LAUNCH_CHECK("bn0_stats launch");
+}
+
+int lass_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
+                     float* running_var, float momentum, float eps, int C, float* bnp, void* stream_v) {
+  if (!sums || !gamma || !beta || !running_mean || !running_var || !bnp || C <= 0 || count <= 0) return set_error(LASS_ERR_ARG, "lass_bn_finalize: bad argument");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(sums, count, gamma, beta, running_mean, running_var, momentum, eps, C, bnp);
+  LASS_LAUNCH_CHECK("bn_finalize launch");
+}
+
+int lass_bn_act(const void* x, int x_fp16, int x_cstride, int x_coff, void* out, int out_fp16, int out_cstride, int out_coff, int B,
+                long long pix_per_clip, int C, const float* bnp, const float* beta, int beta_bstride, void* stream_v) {
+  if (!x || !out || !bnp || !beta || B <= 0 || pix_per_clip <= 0 || !chan_ok(C, x_cstride, x_coff) || !chan_ok(C, out_cstride, out_coff) || beta_bstride % 4)
+    return set_error(LASS_ERR_ARG, "lass_bn_act: bad argument");
+  const long long nvec = (long long)B * pix_per_clip * (C / 8);
+  bn_act_kernel<<<grid_for(nvec, 256), 256, 0, (cudaStream_t)stream_v>>>(x, x_fp16, x_cstride, x_coff, out, out_fp16, out_cstride, out_coff,
+                                                                         pix_per_clip, nvec, C, bnp, beta, beta_bstride);
+  LASS_LAUNCH_CHECK("bn_act launch");
+}
+
+int lass_bn_bwd_reduce(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride, int x_coff, int B,
+                       long long pix_per_clip, int C, const float* bnp, const float* beta, int beta_bstride, float* sums, void* stream_v) {
+  if (!dact || !x || !bnp || !beta || !sums || B <= 0 || pix_per_clip <= 0 || !chan_ok(C, x_cstride, x_coff) || !chan_ok(C, d_cstride, d_coff) || beta_bstride % 4)
+    return set_error(LASS_ERR_ARG, "lass_bn_bwd_reduce: bad argument");
+  cudaStream_t s = (cudaStream_t)stream_v;
+  cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)B * C, s);
+  const int R = kRedThreads / (C / 8);
+  int gx = grid_for(pix_per_clip, R * 8, (148 * 4 + B - 1) / B);
+  dim3 grid((unsigned)gx, (unsigned)B);
+  bn_bwd_reduce_kernel<<<grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), s>>>(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff,
+                                                                                    pix_per_clip, C, bnp, beta, beta_bstride, sums);
+  LASS_LAUNCH_CHECK("bn_bwd_reduce launch");
+}
+
+int lass_bn_bwd_finalize(const float* sums, int B, int C, double count, const float* gamma, float* bnp, float* dgamma, float* dbeta,
+                         float* dfilm, int dfilm_bstride, void* stream_v) {
+  if (!sums || !gamma || !bnp || !dgamma || !dbeta || B <= 0 || C <= 0 || count <= 0) return set_error(LASS_ERR_ARG, "lass_bn_bwd_finalize: bad argument");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(sums, B, C, count, gamma, bnp, dgamma, dbeta, dfilm, dfilm_bstride);
+  LASS_LAUNCH_CHECK("bn_bwd_finalize launch");
+}
+
+int lass_bn_bwd_apply(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride, int x_coff, const void* add,
+                      int add_cstride, int add_coff, void* dx, int dx_cstride, int dx_coff, int B, long long pix_per_clip, int C,
+                      const float* bnp, const float* beta, int beta_bstride, void* stream_v) {
+  if (!dact || !x || !dx || !bnp || !beta || B <= 0 || pix_per_clip <= 0 || !chan_ok(C, x_cstride, x_coff) || !chan_ok(C, d_cstride, d_coff) ||
+      !chan_ok(C, dx_cstride, dx_coff) || (add && !chan_ok(C, add_cstride, add_coff)) || beta_bstride % 4)
+    return set_error(LASS_ERR_ARG, "lass_bn_bwd_apply: bad argument");
+  const long long nvec = (long long)B * pix_per_clip * (C / 8);
+  bn_bwd_apply_kernel<<<grid_for(nvec, 256), 256, 0, (cudaStream_t)stream_v>>>(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff, add,
+                                                                               add_cstride, add_coff, dx, dx_cstride, dx_coff, pix_per_clip,
+                                                                               nvec, C, bnp, beta, beta_bstride);
+  LASS_LAUNCH_CHECK("bn_bwd_apply launch");
+}
+
+int lass_pool_bwd(const void* dpool, const void* dskip, int dskip_cstride, int dskip_coff, void* dy, int B, int H, int W, int C, int ph,
+                  int pw, void* stream_v) {
+  if (!dpool || !dy || B <= 0 || H <= 0 || W <= 0 || C % 8 || ph < 1 || pw < 1 || H % ph || W % pw || (dskip && !chan_ok(C, dskip_cstride, dskip_coff)))
+    return set_error(LASS_ERR_ARG, "lass_pool_bwd: bad argument");
+  const long long nvec = (long long)B * H * W * (C / 8);
+  pool_bwd_kernel<<<grid_for(nvec, 256), 256, 0, (cudaStream_t)stream_v>>>(dpool, dskip, dskip_cstride, dskip_coff, dy, B, H, W, C, ph, pw);
+  LASS_LAUNCH_CHECK("pool_bwd launch");
+}
+
+int lass_unshuffle(const void* src, int src_cstride, int src_coff, void* dst, int B, int H, int W, int C, int uh, int uw, void* stream_v) {
+  if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || uh < 1 || uw < 1 || C % 8 || src_cstride % 8 || src_coff % 8 || src_coff + C > src_cstride)
+    return set_error(LASS_ERR_ARG, "lass_unshuffle: bad argument");
+  const long long nvec = (long long)B * H * W * uh * uw * (C / 8);
+  unshuffle_kernel<<<grid_for(nvec, 256), 256, 0, (cudaStream_t)stream_v>>>(reinterpret_cast<const uint16_t*>(src), src_cstride, src_coff,
+                                                                            reinterpret_cast<uint16_t*>(dst), B, H, W, C, uh, uw);
+  LASS_LAUNCH_CHECK("unshuffle launch");
+}
+
+int lass_channel_sum(const void* x, long long npix, int C, int cstride, int coff, float* out, void* stream_v) {
+  if (!x || !out || npix <= 0 || !chan_ok(C, cstride, coff)) return set_error(LASS_ERR_ARG, "lass_channel_sum: bad argument");
+  cudaStream_t s = (cudaStream_t)stream_v;
+  cudaMemsetAsync(out, 0, sizeof(float) * C, s);
+  const int R = kRedThreads / (C / 8);
+  channel_sum_kernel<<<grid_for(npix, R * 8, 148 * 4), kRedThreads, (size_t)R * C * sizeof(float), s>>>(x, npix, C, cstride, coff, out);
+  LASS_LAUNCH_CHECK("channel_sum launch");
+}
+
+int lass_pre_fwd(const float* mag, int B, int T, int F, int Tp, int Fp, const float* bnp0, const float* pre_w, const float* pre_b, void* x0,
+                 void* stream_v) {
+  if (!mag || !bnp0 || !pre_w || !pre_b || !x0 || B <= 0 || T <= 0 || Tp < T || Fp <= 0 || Fp > F) return set_error(LASS_ERR_ARG, "lass_pre_fwd: bad argument");
+  const long long nvec = (long long)B * Tp * Fp * 4;
+  pre_fwd_kernel<<<grid_for(nvec, 256), 256, 0, (cudaStream_t)stream_v>>>(mag, B, T, F, Tp, Fp, bnp0, pre_w, pre_b, x0);
+  LASS_LAUNCH_CHECK("pre_fwd launch");
+}
+
+int lass_pre_bwd(const void* dx0, const float* mag, int B, int T, int F, int Tp, int Fp, const float* bnp0, const float* pre_w, float* dpre_w,
+                 float* dpre_b, float* dgamma0, float* dbeta0, void* stream_v) {
+  if (!dx0 || !mag || !bnp0 || !pre_w || !dpre_w || !dpre_b || !dgamma0 || !dbeta0 || B <= 0 || T <= 0 || Tp < T || Fp <= 0 || Fp > F)
+    return set_error(LASS_ERR_ARG, "lass_pre_bwd: bad argument");
+  cudaStream_t s = (cudaStream_t)stream_v;
+  cudaMemsetAsync(dpre_w, 0, 32 * sizeof(float), s);
+  cudaMemsetAsync(dpre_b, 0, 32 * sizeof(float), s);
+  cudaMemsetAsync(dgamma0, 0, F * sizeof(float), s);
+  cudaMemsetAsync(dbeta0, 0, F * sizeof(float), s);
+  dim3 grid((unsigned)((Fp + 63) / 64), (unsigned)((Tp + kPreRows - 1) / kPreRows), (unsigned)B);
+  pre_bwd_kernel<<<grid, 256, 0, s>>>(dx0, mag, B, T, F, Tp, Fp, bnp0, pre_w, dpre_w, dpre_b, dgamma0, dbeta0);
+  LASS_LAUNCH_CHECK("pre_bwd launch");
+}
+
+int lass_after_bwd(const float* dfeat, const void* y, const float* after_w, void* dy, float* dw, float* db, int B, long long npix, void* stream_v) {
+  if (!dfeat || !y || !after_w || !dy || !dw || !db || B <= 0 || npix <= 0) return set_error(LASS_ERR_ARG, "lass_after_bwd: bad argument");
+  cudaStream_t s = (cudaStream_t)stream_v;
+  cudaMemsetAsync(dw, 0, 96 * sizeof(float), s);
+  cudaMemsetAsync(db, 0, 3 * sizeof(float), s);
+  after_bwd_kernel<<<grid_for((long long)B * npix, 64, 148 * 4), 256, 0, s>>>(dfeat, y, after_w, dy, dw, db, B, npix);
+  LASS_LAUNCH_CHECK("after_bwd launch");
+}
+
+int lass_mask_bwd(const float* feat, const float* mag, const float* cos, const float* sin, const float* dre, const float* dim, float* dfeat,
+                  int B, int T, int F, int Tp, int Fp, int n_fft, void* stream_v) {
+  if (!feat || !mag || !cos || !sin || !dre || !dim || !dfeat || B <= 0 || T <= 0 || Tp < T || F != n_fft / 2 + 1 || Fp != n_fft / 2)
+    return set_error(LASS_ERR_ARG, "lass_mask_bwd: bad argument");
+  const long long total = (long long)B * Tp * Fp;
+  mask_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_v>>>(feat, mag, cos, sin, dre, dim, dfeat, B, T, F, Tp, Fp, 1.0f / (float)n_fft);
+  LASS_LAUNCH_CHECK("mask_bwd launch");
+}
+
+int lass_l1_loss(const float* wave, const float* target, long long n, float* loss_sum, float* dwave, float scale, void* stream_v) {
+  if (!wave || !target || !loss_sum || !dwave || n <= 0) return set_error(LASS_ERR_ARG, "lass_l1_loss: bad argument");
+  l1_loss_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, (cudaStream_t)stream_v>>>(wave, target, n, loss_sum, dwave, scale);
+  LASS_LAUNCH_CHECK("l1_loss launch");
+}
+
+int lass_film_bwd(const float* dbeta, const float* cond, float* dw, float* db, int B, int J, int K, void* stream_v) {
+  if (!dbeta || !cond || !dw || !db || B <= 0 || J <= 0 || K <= 0 || K % 4) return set_error(LASS_ERR_ARG, "lass_film_bwd: bad argument");
+  film_bwd_kernel<<<J, 128, 0, (cudaStream_t)stream_v>>>(dbeta, cond, dw, db, B, J, K);
+  LASS_LAUNCH_CHECK("film_bwd launch");
+}
+
+int lass_adamw_amsgrad(float* p, const float* g, float* m, float* v, float* vmax, long long n, float lr, float beta1, float beta2, float eps,
+                       float weight_decay, int step, float grad_scale, void* stream_v) {
+  if (!p || !g || !m || !v || !vmax || n <= 0 || step < 1) return set_error(LASS_ERR_ARG, "lass_adamw_amsgrad: bad argument");
+  // host scalars exactly as torch.optim.adamw computes them (python floats = doubles, then cast)
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float decay = (float)(1.0 - (double)lr * (double)weight_decay);
+  const float neg_step = (float)(-((double)lr / bc1));
+  adamw_amsgrad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_v>>>(p, g, m, v, vmax, n, decay, (float)(1.0 - (double)beta1), beta2,
+                                                                             (float)(1.0 - (double)beta2), (float)sqrt(bc2), eps, neg_step,
+                                                                             grad_scale);
+  LASS_LAUNCH_CHECK("adamw launch");
+}
+
+int lass_pack_weight(const float* w, int kind, int co, int ci, int taps, void* fwd, int fwd_fp16, void* dgrad, void* stream_v) {
+  if (!w || (!fwd && !dgrad) || co <= 0 || ci <= 0 || taps <= 0 || (kind != 0 && kind != 1)) return set_error(LASS_ERR_ARG, "lass_pack_weight: bad argument");
+  pack_weight_kernel<<<grid_for((long long)co * ci * taps, 256), 256, 0, (cudaStream_t)stream_v>>>(w, kind, co, ci, taps, fwd, fwd_fp16, dgrad);
+  LASS_LAUNCH_CHECK("pack_weight launch");
+}
+
+int lass_unpack_grad(const float* dw, int kind, int co, int ci, int taps, float* grad, void* stream_v) {
+  if (!dw || !grad || co <= 0 || ci <= 0 || taps <= 0 || (kind != 0 && kind != 1)) return set_error(LASS_ERR_ARG, "lass_unpack_grad: bad argument");
+  unpack_grad_kernel<<<grid_for((long long)co * ci * taps, 256), 256, 0, (cudaStream_t)stream_v>>>(dw, kind, co, ci, taps, grad);
+  LASS_LAUNCH_CHECK("unpack_grad launch");
+}
+
+}  // extern "C"

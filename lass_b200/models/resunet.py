@@ -13,9 +13,9 @@ What differs is where the arithmetic runs: the sub-modules below only own parame
 computation to the sm_100a kernels behind the C ABI (``lass_b200.engine.Engine`` -> ``lass_resunet30_forward``).
 There is no PyTorch / CPU fallback: without a CUDA device or without the built library the call raises.
 
-Scope of this round: eval-mode inference with ``input_channels == output_channels == 1`` (the reference's only
-shipped configuration, ``config/audiosep_base.yaml:25-28``).  Training-mode forward (batch-statistics BatchNorm +
-autograd) is listed as next in SURVEY.md §8(f) and raises ``NotImplementedError``.
+Scope: ``input_channels == output_channels == 1`` (the reference's only shipped configuration,
+``config/audiosep_base.yaml:25-28``).  ``.eval()``: the inference engine (``lass_b200/engine.py``).  ``.train()``: the
+training-step engine (``lass_b200/training.py``): batch-statistics BatchNorm, hand-written backward, autograd bridge.
 """
 import weakref
 from typing import Dict
@@ -27,6 +27,7 @@ import torch.nn as nn
 from .spectral import ISTFT, STFT
 
 _ENGINES = weakref.WeakKeyDictionary()
+_TRAIN_ENGINES = weakref.WeakKeyDictionary()
 
 
 def init_layer(layer):
@@ -234,8 +235,26 @@ class ResUNet30(nn.Module):
         (reference ``models/resunet.py:640-653``); all work on the current CUDA stream of the inputs' device."""
         mixtures = input_dict["mixture"]
         conditions = input_dict["condition"]
+        if self.training:
+            # reference models/audiosep.py:99-100: the module is called in .train() with autograd on.  BatchNorm runs on batch
+            # statistics (running stats updated, momentum 0.01) and the returned waveform is connected to the parameters, so
+            # loss.backward() / optimizer.step() work as with the reference (lass_b200/training.py)
+            from .. import training
+            if not mixtures.is_cuda:
+                raise RuntimeError("lass_b200 has no CPU path: move the module and its inputs to a CUDA device")
+            return {"waveform": training.train_forward(self.train_engine(), mixtures, conditions)}
         engine = self.base._get_engine(self.film)
         return {"waveform": engine.forward(mixtures, conditions)}
+
+    def train_engine(self):
+        """The training-step engine of this module (flat fp32 parameter / gradient buffers; created on first use — the
+        module's parameters become views of its flat buffer, values unchanged)."""
+        from .. import training
+        eng = _TRAIN_ENGINES.get(self)
+        if eng is None or eng.device != self.base.pre_conv.weight.device:
+            eng = training.TrainEngine(self)
+            _TRAIN_ENGINES[self] = eng
+        return eng
 
     @torch.no_grad()
     def chunk_inference(self, input_dict, rate=None):

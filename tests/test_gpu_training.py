@@ -1,0 +1,384 @@
+"""Training step on the GPU: every CUDA kernel of the step against its pure-torch emulation
+(tests/train_emul.py, same interface), then the whole step — train-mode forward, loss, gradients, running statistics,
+fused AdamW-amsgrad — against the autograd oracle (oracle/train_oracle.py, pinned to the unmodified reference in .train())."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+import train_emul as E
+from oracle import factory, train_oracle
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def K():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from lass_b200 import train_kernels
+    E.set_exact(False)
+    return train_kernels
+
+
+def _rand16(shape, dtype, scale=1.0, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype)
+
+
+def _close(a, b, rtol, atol, what=""):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    err = (a - b).abs()
+    bound = atol + rtol * b.abs()
+    assert bool((err <= bound).all()), "%s: max err %.3e (ref max %.3e)" % (what, float(err.max()), float(b.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------- kernels
+@pytest.mark.parametrize("C,cstride,coff,fp16", [(32, 32, 0, True), (64, 128, 64, True), (384, 768, 0, False), (768, 768, 0, True)])
+def test_bn_stats_finalize_act(K, C, cstride, coff, fp16):
+    B, H, W = 3, 12, 20
+    x = _rand16((B, H, W, cstride), torch.float16 if fp16 else torch.bfloat16, 2.0, 1) + 0.5
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C) * 0.1
+    rm, rv = torch.randn(C) * 0.1, torch.rand(C) + 0.5
+    film = torch.randn(B, C + 8)
+    outs = []
+    for k, dev in ((E, "cpu"), (K, "cuda")):
+        xs, sums, bnp = x.to(dev), torch.zeros(2, C, dtype=torch.float64, device=dev), torch.zeros(6 * C, device=dev)
+        rm_, rv_ = rm.clone().to(dev), rv.clone().to(dev)
+        k.bn_stats(xs, coff, C, sums)
+        k.bn_finalize(sums, B * H * W, gamma.to(dev), beta.to(dev), rm_, rv_, 0.01, 1e-5, bnp)
+        out = torch.zeros(B, H, W, C + 16, dtype=torch.float16, device=dev)
+        k.bn_act(xs, coff, out, 8, C, bnp, film.to(dev)[:, :C])
+        outs.append((sums, bnp, rm_, rv_, out))
+    _close(outs[1][0], outs[0][0], 1e-5, 1e-3, "sums")
+    _close(outs[1][1][:4 * C], outs[0][1][:4 * C], 1e-4, 1e-5, "bnp")
+    _close(outs[1][2], outs[0][2], 1e-5, 1e-6, "running_mean")
+    _close(outs[1][3], outs[0][3], 1e-5, 1e-6, "running_var")
+    _close(outs[1][4], outs[0][4], 2e-3, 2e-3, "act")
+    assert float(outs[1][4][..., :8].abs().max()) == 0.0 and float(outs[1][4][..., 8 + C:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("C,with_add", [(32, True), (128, False), (768, True)])
+def test_bn_backward_kernels(K, C, with_add):
+    B, H, W = 2, 10, 24
+    x = _rand16((B, H, W, C), torch.float16, 1.5, 2)
+    dact = _rand16((B, H, W, C), torch.bfloat16, 1e-4, 3)
+    add = _rand16((B, H, W, 2 * C), torch.bfloat16, 1e-4, 4) if with_add else None
+    gamma = torch.rand(C) + 0.5
+    film = torch.randn(B, C) * 0.3
+    res = []
+    for k, dev in ((E, "cpu"), (K, "cuda")):
+        xs, ds = x.to(dev), dact.to(dev)
+        sums, bnp = torch.zeros(2, C, dtype=torch.float64, device=dev), torch.zeros(6 * C, device=dev)
+        k.bn_stats(xs, 0, C, sums)
+        k.bn_finalize(sums, B * H * W, gamma.to(dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev),
+                      torch.ones(C, device=dev), 0.01, 1e-5, bnp)
+        bs = torch.zeros(B, C, 2, device=dev)
+        fb = film.to(dev)
+        k.bn_bwd_reduce(ds, xs, 0, C, bnp, fb, bs)
+        dg, db, dfilm = torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(B, C + 32, device=dev)
+        k.bn_bwd_finalize(bs, B * H * W, gamma.to(dev), bnp, dg, db, dfilm[:, 32:])
+        dx = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=dev)
+        k.bn_bwd_apply(ds, xs, 0, C, bnp, fb, add.to(dev) if with_add else None, C if with_add else 0, dx, 0)
+        res.append((bs, dg, db, dfilm, bnp, dx))
+    scale = 1e-4 * (B * H * W) ** 0.5
+    _close(res[1][0], res[0][0], 1e-3, 1e-4 * scale, "bwd sums")
+    _close(res[1][1], res[0][1], 1e-3, 1e-3 * scale, "dgamma")
+    _close(res[1][2], res[0][2], 1e-3, 1e-3 * scale, "dbeta")
+    _close(res[1][3], res[0][3], 1e-3, 1e-3 * scale, "dfilm")
+    _close(res[1][5], res[0][5], 1e-2, 2e-6, "dx")
+
+
+def test_pool_unshuffle_channel_sum(K):
+    B, H, W, C = 2, 8, 12, 64
+    dpool = _rand16((B, H // 2, W // 2, C), torch.bfloat16, 1.0, 5)
+    dcat = _rand16((B, H, W, 2 * C), torch.bfloat16, 1.0, 6)
+    for ph, pw, dp in ((2, 2, dpool), (1, 2, _rand16((B, H, W // 2, C), torch.bfloat16, 1.0, 7))):
+        r = []
+        for k, dev in ((E, "cpu"), (K, "cuda")):
+            dy = torch.zeros(B, H, W, C, dtype=torch.bfloat16, device=dev)
+            k.pool_bwd(dp.to(dev), dcat.to(dev), C, dy, ph, pw)
+            r.append(dy)
+        _close(r[1], r[0], 1e-2, 1e-3, "pool_bwd")
+    for uh, uw in ((2, 2), (1, 2)):
+        r = []
+        for k, dev in ((E, "cpu"), (K, "cuda")):
+            dst = torch.zeros(B, H // uh, W // uw, uh * uw * C, dtype=torch.bfloat16, device=dev)
+            k.unshuffle(dcat.to(dev), 0, C, dst, uh, uw)
+            r.append(dst)
+        assert torch.equal(r[1].cpu(), r[0]), "unshuffle"
+    r = []
+    for k, dev in ((E, "cpu"), (K, "cuda")):
+        out = torch.zeros(C, device=dev)
+        k.channel_sum(dcat.to(dev), C, C, out)
+        r.append(out)
+    _close(r[1], r[0], 1e-4, 1e-3, "channel_sum")
+
+
+WGRAD_CASES = [  # co, ci, taps, B, H, W, x fp16
+    (32, 32, 9, 2, 24, 40, False), (64, 32, 9, 2, 16, 32, True), (32, 64, 9, 1, 16, 16, False), (64, 64, 9, 2, 9, 19, True),
+    (128, 64, 9, 2, 8, 16, False), (384, 768, 9, 1, 4, 8, True), (256, 128, 1, 2, 8, 16, True), (64, 32, 1, 2, 16, 32, True),
+    (1536, 384, 1, 1, 4, 8, False), (32, 64, 1, 1, 16, 48, True), (128, 64, 1, 2, 8, 8, False),
+]
+
+
+@pytest.mark.parametrize("co,ci,taps,B,H,W,xfp16", WGRAD_CASES)
+def test_wgrad(K, co, ci, taps, B, H, W, xfp16):
+    dy = _rand16((B, H, W, co + 32), torch.bfloat16, 1e-3, 8)
+    x = _rand16((B, H, W, ci + 64), torch.float16 if xfp16 else torch.bfloat16, 1.0, 9)
+    r = []
+    for k, dev in ((E, "cpu"), (K, "cuda")):
+        dw = torch.full((taps * co * ci,), 7.0, device=dev)
+        k.wgrad(dy.to(dev), 32, co, x.to(dev), 64, ci, taps, dw)
+        r.append(dw)
+    _close(r[1], r[0], 1e-3, 1e-3 * 1e-3 * (B * H * W) ** 0.5 * 1e-1, "wgrad")
+
+
+def test_pre_after_mask_loss_film_kernels(K):
+    B, T, n_fft = 2, 37, 1024
+    F, Fp, Tp = n_fft // 2 + 1, n_fft // 2, 64
+    g = torch.Generator().manual_seed(11)
+    mag = torch.rand(B, T, F, generator=g) + 0.01
+    ang = torch.rand(B, T, F, generator=g) * 6.28
+    cos, sin = torch.cos(ang), torch.sin(ang)
+    gamma0, beta0 = torch.rand(F, generator=g) + 0.5, torch.randn(F, generator=g) * 0.1
+    pre_w, pre_b = torch.randn(32, generator=g), torch.randn(32, generator=g) * 0.1
+    dx0 = _rand16((B, Tp, Fp, 32), torch.bfloat16, 1e-4, 12)
+    feat = torch.randn(B, 3, Tp, Fp, generator=g)
+    dre, dim = torch.randn(B, T, F, generator=g) * 1e-3, torch.randn(B, T, F, generator=g) * 1e-3
+    dfeat_in = torch.randn(B, 3, Tp, Fp, generator=g) * 1e-4
+    y = _rand16((B, Tp, Fp, 32), torch.float16, 1.0, 13)
+    aw = torch.randn(3, 32, generator=g)
+    res = []
+    for k, dev in ((E, "cpu"), (K, "cuda")):
+        d = lambda t: t.to(dev)
+        sums0, bnp0 = torch.zeros(2, F, dtype=torch.float64, device=dev), torch.zeros(6 * F, device=dev)
+        k.bn0_stats(d(mag), sums0)
+        k.bn_finalize(sums0, B * T, d(gamma0), d(beta0), torch.zeros(F, device=dev), torch.ones(F, device=dev), 0.01, 1e-5, bnp0)
+        x0 = torch.zeros(B, Tp, Fp, 32, dtype=torch.float16, device=dev)
+        k.pre_fwd(d(mag), bnp0, d(pre_w), d(pre_b), x0)
+        dpw, dpb, dg0, db0 = (torch.zeros(n, device=dev) for n in (32, 32, F, F))
+        k.pre_bwd(d(dx0), d(mag), bnp0, d(pre_w), dpw, dpb, dg0, db0)
+        dfeat = torch.zeros(B, 3, Tp, Fp, device=dev)
+        k.mask_bwd(d(feat), d(mag), d(cos), d(sin), d(dre), d(dim), dfeat, n_fft)
+        dy = torch.zeros(B, Tp, Fp, 32, dtype=torch.bfloat16, device=dev)
+        daw, dab = torch.zeros(3, 32, device=dev), torch.zeros(3, device=dev)
+        k.after_bwd(d(dfeat_in), d(y), d(aw), dy, daw, dab)
+        wave, tgt = d(dre.reshape(B, -1)[:, :8000].contiguous()), d(dim.reshape(B, -1)[:, :8000].contiguous())
+        dwave, ls = torch.zeros(B, 8000, device=dev), torch.zeros(1, device=dev)
+        k.l1_loss(wave, tgt, dwave, ls)
+        dbt, cond = d(torch.randn(B, 96, generator=torch.Generator().manual_seed(3))), d(torch.randn(B, 512, generator=torch.Generator().manual_seed(4)))
+        fdw, fdb = torch.zeros(96, 512, device=dev), torch.zeros(96, device=dev)
+        k.film_bwd(dbt, cond, fdw, fdb)
+        res.append(dict(sums0=sums0, bnp0=bnp0[:4 * F], x0=x0, dpw=dpw, dpb=dpb, dg0=dg0, db0=db0, dfeat=dfeat, dy=dy, daw=daw,
+                        dab=dab, dwave=dwave, ls=ls, fdw=fdw, fdb=fdb))
+    tol = dict(sums0=(1e-5, 1e-4), bnp0=(1e-4, 1e-5), x0=(2e-3, 2e-3), dpw=(1e-3, 1e-5), dpb=(1e-3, 1e-5), dg0=(1e-3, 1e-6),
+               db0=(1e-3, 1e-6), dfeat=(2e-3, 1e-9), dy=(1e-2, 1e-7), daw=(1e-3, 1e-5), dab=(1e-3, 1e-5), dwave=(0, 0),
+               ls=(1e-5, 1e-6), fdw=(1e-4, 1e-5), fdb=(1e-4, 1e-5))
+    for name, (rt, at) in tol.items():
+        _close(res[1][name], res[0][name], rt, at, name)
+
+
+def test_istft_adjoint_and_pack(K):
+    from lass_b200 import packing
+    from lass_b200.models.spectral import STFT
+    n_fft, hop, B, L = 1024, 160, 2, 12000
+    T = L // hop + 1
+    stft = STFT(n_fft=n_fft, hop_length=hop, win_length=n_fft)
+    window, _ = packing.istft_tables(n_fft)
+    dwave = torch.randn(B, L, generator=torch.Generator().manual_seed(5)) * 1e-5
+    dre_e, dim_e = torch.zeros(B, T, n_fft // 2 + 1), torch.zeros(B, T, n_fft // 2 + 1)
+    E.istft_bwd(dwave, window, None, None, n_fft, hop, T, None, dre_e, dim_e)
+    hi, lo = packing.pack_stft_basis(stft.conv_real.weight.data.cuda(), stft.conv_imag.weight.data.cuda())
+    from lass_b200 import _cabi
+    ws = torch.empty(_cabi.load().lass_stft_workspace_bytes(B, L, n_fft, hop) + 256, dtype=torch.uint8, device="cuda")
+    dre, dim = torch.zeros(B, T, n_fft // 2 + 1, device="cuda"), torch.zeros(B, T, n_fft // 2 + 1, device="cuda")
+    K.istft_bwd(dwave.cuda(), window.cuda(), hi, lo, n_fft, hop, T, ws, dre, dim)
+    m = float(dre_e.abs().max())
+    assert float((dre.cpu() - dre_e).abs().max()) <= 1e-4 * m and float((dim.cpu() - dim_e).abs().max()) <= 1e-4 * m
+    # weight packing / gradient unpacking round trip against the emulation
+    for kind, shape in ((K.KIND_CONV, (64, 32, 3, 3)), (K.KIND_CONV, (96, 64, 1, 1)), (K.KIND_CONVT, (64, 32, 2, 2)), (K.KIND_CONVT, (32, 64, 1, 2))):
+        w = torch.randn(shape, generator=torch.Generator().manual_seed(6))
+        taps = shape[2] * shape[3]
+        co, ci = (shape[0], shape[1]) if kind == K.KIND_CONV else (shape[1], shape[0])
+        fshape = (taps, co, ci) if kind == K.KIND_CONV else (1, taps * co, ci)
+        dshape = (taps, ci, co) if kind == K.KIND_CONV else (1, ci, taps * co)
+        r = []
+        for k, dev in ((E, "cpu"), (K, "cuda")):
+            fwd, dg = torch.zeros(fshape, dtype=torch.float16, device=dev), torch.zeros(dshape, dtype=torch.bfloat16, device=dev)
+            k.pack_weight(w.to(dev), kind, fwd, dg)
+            packed = torch.randn(taps * co * ci, generator=torch.Generator().manual_seed(7)).to(dev)
+            grad = torch.zeros(shape, device=dev)
+            k.unpack_grad(packed, kind, grad)
+            r.append((fwd, dg, grad))
+        for a, b in zip(r[1], r[0]):
+            assert torch.equal(a.cpu(), b)
+
+
+def test_adamw_kernel_matches_torch(K):
+    n = 100003
+    g0 = torch.Generator().manual_seed(8)
+    p0 = torch.randn(n, generator=g0)
+    ref = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.AdamW([ref], lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=True, foreach=False)
+    p, m, v, vm = p0.clone().cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    for step in range(1, 5):
+        g = torch.randn(n, generator=g0) * (10.0 if step == 2 else 0.1)
+        ref.grad = g.clone()
+        opt.step()
+        K.adamw_amsgrad(p, g.cuda(), m, v, vm, 1e-3, 0.9, 0.999, 1e-8, 0.0, step)
+        d = (p.cpu() - ref.detach()).abs()
+        assert float(d.max()) <= 2e-7 * float(ref.detach().abs().max()), (step, float(d.max()))
+
+
+# ------------------------------------------------------------------------------------------------- the whole step
+def _inputs(B, L):
+    mix, cond = factory.make_inputs(B, L, seed=1234, edge_clips=False)
+    tgt, _ = factory.make_inputs(B, L, seed=4321, edge_clips=False)
+    return mix, cond, 0.5 * tgt
+
+
+def _rel_l2(a, b):
+    return float((a.double() - b.double()).norm()) / max(float(b.double().norm()), 1e-30)
+
+
+@pytest.fixture(scope="module")
+def step_state(K):
+    from lass_b200 import training
+    B, L = 2, 16000
+    model, sd = helpers.build_module()
+    mix, cond, tgt = _inputs(B, L)
+    o_loss, o_wave, o_grads, o_buf = train_oracle.training_forward_backward(sd, mix, cond, tgt)
+    model = model.cuda().train()
+    eng = training.TrainEngine(model)
+    with torch.no_grad():
+        wave = eng.forward(mix.cuda(), cond.cuda())
+        loss = torch.mean(torch.abs(wave - tgt.cuda()))
+        eng.backward(torch.sign(wave - tgt.cuda()) / wave.numel())
+        torch.cuda.synchronize()
+    return dict(model=model, eng=eng, sd=sd, wave=wave.cpu(), loss=float(loss), o_loss=o_loss, o_wave=o_wave, o_grads=o_grads,
+                o_buf=o_buf, mix=mix, cond=cond, tgt=tgt)
+
+
+def test_train_forward_matches_reference_train_mode(step_state):
+    s = step_state
+    snr = factory.snr_db(s["o_wave"], s["wave"])
+    assert float(snr.min()) >= 40.0, snr                       # the bar of the bf16 path (BASELINE.json north_star)
+    assert abs(s["loss"] - s["o_loss"]) <= 1e-3 * s["o_loss"]
+    new_sd = s["model"].state_dict()
+    for k, v in s["o_buf"].items():
+        if k.endswith("num_batches_tracked"):
+            assert int(new_sd[k]) == int(v)
+        else:
+            assert torch.allclose(new_sd[k].cpu().float(), v.float(), rtol=2e-3, atol=2e-4), k
+
+
+def test_train_gradients_against_reference_and_its_own_sensitivity(step_state):
+    """See tests/test_training_cpu.py::test_training_step_16bit_storage_model for why the bound is relative to the movement
+    of the reference's OWN gradients under fp16 rounding of its conv weights (the network's gradient is chaotic)."""
+    s = step_state
+    sd, o_grads = s["sd"], s["o_grads"]
+    sd_r = {k: (v.to(torch.float16).float() if (k.endswith("weight") and "conv" in k and "stft" not in k) else v) for k, v in sd.items()}
+    _, _, r_grads, _ = train_oracle.training_forward_backward(sd_r, s["mix"], s["cond"], s["tgt"])
+    own = float(np.median([_rel_l2(r_grads[k], o_grads[k]) for k in o_grads]))
+    names = {id(p): n for n, p in s["model"].named_parameters()}
+    got = {names[id(p)]: g.cpu() for p, g in s["eng"].grads().items()}
+    assert sorted(got) == sorted(o_grads)
+    rel = {k: _rel_l2(got[k], o_grads[k]) for k in o_grads}
+    ours = float(np.median(list(rel.values())))
+    print("median rel-L2 gradient error vs fp32 reference: %.3f (reference's own movement under fp16 weight rounding: %.3f)" % (ours, own))
+    assert ours <= 2.0 * own + 0.02, (ours, own)
+    cos = [float((got[k].double() * o_grads[k].double()).sum() / (got[k].double().norm() * o_grads[k].double().norm() + 1e-300))
+           for k in o_grads if float(o_grads[k].abs().max()) > 1e-7]
+    assert float(np.median(cos)) >= 0.9 and float(np.min(cos)) >= 0.3, (float(np.median(cos)), float(np.min(cos)))
+    # the CPU emulation of the same kernel sequence with the same storage types agrees with the CUDA path at least as well
+    from lass_b200 import training
+    E.set_exact(False)
+    model_e, _ = helpers.build_module()
+    model_e.train()
+    with torch.no_grad():
+        eng_e = training.TrainEngine(model_e, kernels=E)
+        wave_e = eng_e.forward(s["mix"], s["cond"])
+        eng_e.backward(torch.sign(wave_e - s["tgt"]) / wave_e.numel())
+    names_e = {id(p): n for n, p in model_e.named_parameters()}
+    emu = {names_e[id(p)]: g for p, g in eng_e.grads().items()}
+    vs_emu = float(np.median([_rel_l2(got[k], emu[k]) for k in o_grads]))
+    print("median rel-L2 CUDA vs emulation (same rounding points): %.3f" % vs_emu)
+    assert vs_emu <= 2.0 * own + 0.02
+
+
+def test_directional_derivative_self_consistency(step_state):
+    """The gradient the engine returns is the gradient of ITS OWN forward: loss(theta - eta g / |g|) - loss(theta) ~ -eta |g|
+    for the full gradient and for parameter groups (a missing or mis-scaled term of the backward shows up here whatever the
+    conditioning of the comparison with fp32 autograd)."""
+    s = step_state
+    eng, model = s["eng"], s["model"]
+    mix, cond, tgt = s["mix"].cuda(), s["cond"].cuda(), s["tgt"].cuda()
+    P0 = eng.P.clone()
+    bufs0 = {k: v.clone() for k, v in model.state_dict().items() if "running" in k or "num_batches" in k}
+
+    def loss_at(P):
+        with torch.no_grad():
+            eng.P.copy_(P)
+            eng.refresh_weights()
+            w = eng.forward(mix, cond)
+            return float(torch.mean(torch.abs(w - tgt)).double())
+
+    base = loss_at(P0)
+    G = eng.G.clone()
+    groups = {"all": (0, eng.live_end), "decoder+after (bucket A)": (0, eng.bucket_a_end),
+              "encoder+pre+bn0": (eng.bucket_a_end, eng.film_w_off), "film": (eng.film_w_off, eng.live_end)}
+    for gname, (lo, hi) in groups.items():
+        d = torch.zeros_like(G)
+        d[lo:hi] = G[lo:hi]
+        nrm = float(d.double().norm())
+        assert nrm > 0
+        d = d / nrm
+        # central difference along the normalised gradient direction; step sized so the loss moves by ~1e-3 relative
+        eta = 2e-3 * base / nrm
+        lp, lm = loss_at(P0 + eta * d), loss_at(P0 - eta * d)
+        fd = (lp - lm) / (2 * eta)
+        print("%s: predicted slope %.4e, finite difference %.4e" % (gname, nrm, fd))
+        assert abs(fd - nrm) <= 0.15 * nrm, (gname, fd, nrm)
+    with torch.no_grad():
+        eng.P.copy_(P0)
+        eng.refresh_weights()
+        model.load_state_dict({**model.state_dict(), **bufs0})
+
+
+def test_fused_training_step_and_module_api(K):
+    """ResUNet30 in .train(): forward + l1 + backward through autograd (reference models/audiosep.py:99-111), torch AdamW;
+    and the fused step (one AdamW-amsgrad launch over the flat buffers) lands on the same parameters."""
+    from lass_b200 import training
+    B, L = 2, 16000
+    mix, cond, tgt = _inputs(B, L)
+    mix, cond, tgt = mix.cuda(), cond.cuda(), tgt.cuda()
+    model_a, _ = helpers.build_module()
+    model_a = model_a.cuda().train()
+    opt = torch.optim.AdamW(model_a.parameters(), lr=1e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=True)
+    out = model_a({"mixture": mix, "condition": cond})["waveform"]
+    loss_a = torch.mean(torch.abs(out.squeeze() - tgt.squeeze()))
+    loss_a.backward()
+    dead = [n for n, p in model_a.named_parameters() if p.requires_grad and p.grad is None]
+    assert sorted(dead) == sorted(n for n, p in model_a.named_parameters() if train_oracle.is_dead_key(n))
+    opt.step()
+    model_b, _ = helpers.build_module()
+    model_b = model_b.cuda().train()
+    eng = training.TrainEngine(model_b)
+    with torch.no_grad():
+        loss_b = eng.training_step(mix, cond, tgt, lr=1e-5)
+    assert abs(float(loss_a) - float(loss_b)) <= 1e-5 * float(loss_a)
+    # (the first AdamW step moves every element by ~lr * sign(g): elements whose gradient is accumulation-order noise may
+    #  flip between the two runs -- fp32 atomics -- so the comparison counts elements)
+    pa, pb = dict(model_a.named_parameters()), dict(model_b.named_parameters())
+    same = total = 0
+    for n in pa:
+        a, b = pa[n].detach(), pb[n].detach()
+        same += int(((a - b).abs() <= 1e-7 + 1e-6 * a.abs()).sum())
+        total += a.numel()
+    assert same >= 0.95 * total, (same, total)
+    # a second step runs on the refreshed 16-bit weights and reduces the loss on the same batch
+    with torch.no_grad():
+        l2 = float(eng.training_step(mix, cond, tgt, lr=1e-5))
+        l3 = float(eng.training_step(mix, cond, tgt, lr=1e-5))
+    assert l3 < float(loss_b), (float(loss_b), l2, l3)
