@@ -220,6 +220,11 @@ LASS_API int lass_channel_sum(const void* x, long long npix, int C, int cstride,
  * dy bf16, x bf16 or fp16 (x_fp16); co, ci multiples of 32.  mma.sync bf16, fp32 accumulate, split over pixel ranges. */
 LASS_API int lass_wgrad(const void* dy, int dy_cstride, int dy_coff, int co, const void* x, int x_fp16, int x_cstride,
                         int x_coff, int ci, int B, int H, int W, int taps, float* dw, void* stream);
+/* The same contract on the 5th-generation tensor cores (tcgen05, accumulators in TMEM, TMA-fed; csrc/wgrad_tc.cu): both
+ * operands are the NHWC tiles as they lie in memory (MN-major descriptors, the pixel index is the GEMM K), horizontal taps
+ * fill the M = 128 rows, fp16 x tiles are converted to bf16 in shared memory, split over pixel ranges with fp32 red.global. */
+LASS_API int lass_wgrad_tc(const void* dy, int dy_cstride, int dy_coff, int co, const void* x, int x_fp16, int x_cstride,
+                           int x_coff, int ci, int B, int H, int W, int taps, float* dw, void* stream);
 /* bn0 + zero time padding + Nyquist drop + pre_conv (models/resunet.py:537-555): x0 (B, Tp, Fp, 32) fp16; and its backward
  * from dx0 (bf16): dpre_w, dpre_b (32), dgamma0, dbeta0 (F; the dropped Nyquist bin gets 0).  bnp0 = 6*F block of bn0. */
 LASS_API int lass_pre_fwd(const float* mag, int B, int T, int F, int Tp, int Fp, const float* bnp0, const float* pre_w,
@@ -380,6 +385,14 @@ LASS_API void lass_resunet30_plan_destroy(lass_plan* plan);
 LASS_API int lass_debug_umma_probe(const void* A, int a_rows, const void* Bm, int n, int kc, int swizzle_mode,
                                    int a_start_bytes, int a_sbo, int a_base_offset, int b_sbo, int fmt_fp16,
                                    float* out, void* stream);
+
+/* Debug: the same for MN-major operands (rows of the tile = contraction index K; the weight-gradient kernel's layouts): A
+ * (a_rows, 64 | 32) and Bm (b_rows, 64 | 32) 16-bit (64 elements per row with swizzle 2 = 128 B, 32 with 4 = 64 B); `ksteps`
+ * MMAs (M = 128, N = n, K = 16) with start = tile + *_start + ks * *_kstep bytes, leading / stride byte offsets *_lbo /
+ * *_sbo; the two operands may differ in format (fp16 / bf16).  out (128, n) fp32. */
+LASS_API int lass_debug_umma_probe_mn(const void* A, int a_rows, int a_swz, const void* Bm, int b_rows, int b_swz, int n,
+                                      int ksteps, int a_start, int a_lbo, int a_sbo, int a_kstep, int b_start, int b_lbo,
+                                      int b_sbo, int b_kstep, int a_fp16, int b_fp16, float* out, void* stream);
 
 /* Debug: tcgen05.mma issue/execute throughput for a given operand layout: `iters` back-to-back MMAs (M = 128,
  * N = n, K = 16) over zeroed shared memory, `nacc` accumulators round-robin; cycles_out[grid] receives the SM

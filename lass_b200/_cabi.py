@@ -179,3 +179,5 @@ SIGNATURES.update({
     "lass_unpack_grad": (_i, [_v, _i, _i, _i, _i, _v, _v]),
     "lass_debug_set_istft_v1": (_i, [_i]),
 })
+SIGNATURES["lass_wgrad_tc"] = SIGNATURES["lass_wgrad"]
+SIGNATURES["lass_debug_umma_probe_mn"] = (_i, [_v, _i, _i, _v, _i, _i, _i, _i] + [_i] * 10 + [_v, _v])

@@ -76,6 +76,73 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constan
   }
 }
 
+// MN-major probe: A (a_rows x wa) and B (b_rows x wb) 16-bit tiles whose ROWS are the contraction index K (wa / wb = 64
+// elements with SWIZZLE_128B, 32 with SWIZZLE_64B), one TMA box each; `ksteps` MMAs (M = 128, K = 16) with
+//   desc_a = make_smem_desc_mn(A_smem + a_start + ks*a_kstep, a_lbo, a_sbo, a_swz), desc_b likewise; out (128, n) fp32.
+struct ProbeMnParams {
+  CUtensorMap tmA, tmB;
+  float* out;
+  int a_rows, b_rows, wa, wb, n, ksteps;
+  int a_swz, a_start, a_lbo, a_sbo, a_kstep, b_swz, b_start, b_lbo, b_sbo, b_kstep, fmt_a, fmt_b;
+};
+
+__global__ void __launch_bounds__(128, 1) umma_probe_mn_kernel(const __grid_constant__ ProbeMnParams p) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + 64 * 1024;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sB + 64 * 1024);
+  uint64_t* acc_bar = bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < 128 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    mbar_init(acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_acc = *tmem_slot;
+  if (threadIdx.x == 0) {
+    fence_proxy_async_smem();
+    mbar_arrive_expect_tx(bar, (uint32_t)((p.a_rows * p.wa + p.b_rows * p.wb) * 2));
+    tma_load_2d(sA, &p.tmA, bar, 0, 0);
+    tma_load_2d(sB, &p.tmB, bar, 0, 0);
+    mbar_wait(bar, 0);
+    tc_fence_after_sync();
+    const uint32_t idesc = make_idesc_f16_mn(p.fmt_a, p.fmt_b, 128, p.n);
+    for (int ks = 0; ks < p.ksteps; ++ks) {
+      const uint64_t da = make_smem_desc_mn(smem_u32(sA) + p.a_start + ks * p.a_kstep, p.a_lbo, p.a_sbo, p.a_swz);
+      const uint64_t db = make_smem_desc_mn(smem_u32(sB) + p.b_start + ks * p.b_kstep, p.b_lbo, p.b_sbo, p.b_swz);
+      umma_f16(tmem_acc, da, db, idesc, ks != 0);
+    }
+    umma_commit(acc_bar);
+  }
+  __syncwarp();
+  mbar_wait(acc_bar, 0);
+  tc_fence_after_sync();
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(warp * 32) << 16);
+  for (int c = 0; c < p.n; c += 16) {
+    float v[16];
+    tmem_ld_x16(taddr + c, v);
+    tmem_ld_wait();
+    for (int j = 0; j < 16; ++j) p.out[(size_t)(warp * 32 + lane) * p.n + c + j] = v[j];
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_acc, 256);
+  }
+}
+
 // Throughput microbenchmark: `iters` back-to-back tcgen05.mma (M = 128) with the given operand layout, alternating
 // between `nacc` accumulators and advancing K by 32 B per instruction like a real k-loop (4 steps, then wrap).
 __global__ void __launch_bounds__(128, 1) umma_bench_kernel(int n, int kc, int swizzle, int a_start_bytes, int a_sbo,
@@ -365,4 +432,52 @@ extern "C" int lass_debug_umma_bench3(int mt, int bn, int ksteps, int mode, int 
   LASS_B3(1, 256, 4)
 #undef LASS_B3
   return set_error(LASS_ERR_ARG, "umma_bench3: unsupported configuration");
+}
+
+extern "C" int lass_debug_umma_probe_mn(const void* A, int a_rows, int a_swz, const void* Bm, int b_rows, int b_swz, int n, int ksteps,
+                                        int a_start, int a_lbo, int a_sbo, int a_kstep, int b_start, int b_lbo, int b_sbo, int b_kstep,
+                                        int a_fp16, int b_fp16, float* out, void* stream) {
+  if (!A || !Bm || !out) return set_error(LASS_ERR_ARG, "probe_mn: null pointer");
+  if ((a_swz != 2 && a_swz != 4) || (b_swz != 2 && b_swz != 4) || n % 16 || n < 16 || n > 256 || a_rows < 8 || a_rows > 256 || b_rows < 8 ||
+      b_rows > 256 || ksteps < 1)
+    return set_error(LASS_ERR_ARG, "probe_mn: bad shape");
+  ProbeMnParams p;
+  p.wa = a_swz == 2 ? 64 : 32;
+  p.wb = b_swz == 2 ? 64 : 32;
+  {
+    uint64_t dims[2] = {(uint64_t)p.wa, (uint64_t)a_rows};
+    uint64_t strides[1] = {(uint64_t)p.wa * 2};
+    uint32_t box[2] = {(uint32_t)p.wa, (uint32_t)a_rows};
+    int e = make_tensor_map(&p.tmA, A, 2, 2, dims, strides, box, a_swz == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (e) return e;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)p.wb, (uint64_t)b_rows};
+    uint64_t strides[1] = {(uint64_t)p.wb * 2};
+    uint32_t box[2] = {(uint32_t)p.wb, (uint32_t)b_rows};
+    int e = make_tensor_map(&p.tmB, Bm, 2, 2, dims, strides, box, b_swz == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
+    if (e) return e;
+  }
+  p.out = out;
+  p.a_rows = a_rows;
+  p.b_rows = b_rows;
+  p.n = n;
+  p.ksteps = ksteps;
+  p.a_swz = a_swz;
+  p.a_start = a_start;
+  p.a_lbo = a_lbo;
+  p.a_sbo = a_sbo;
+  p.a_kstep = a_kstep;
+  p.b_swz = b_swz;
+  p.b_start = b_start;
+  p.b_lbo = b_lbo;
+  p.b_sbo = b_sbo;
+  p.b_kstep = b_kstep;
+  p.fmt_a = a_fp16 ? kFmtF16 : kFmtBF16;
+  p.fmt_b = b_fp16 ? kFmtF16 : kFmtBF16;
+  const size_t smem = 1024 + 128 * 1024 + 256;
+  cudaError_t e = cudaFuncSetAttribute(umma_probe_mn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return set_cuda_error(e, "probe_mn smem attribute");
+  umma_probe_mn_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(p);
+  return set_cuda_error(cudaGetLastError(), "probe_mn launch");
 }

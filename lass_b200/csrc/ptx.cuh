@@ -296,6 +296,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
   return d;
 }
 
+// MN-major operands (the contraction index K is the SLOW one: rows of the tile are K, the 16-bit elements of a row are M / N
+// -- an NHWC activation tile as it lies in memory is MN-major for a GEMM over pixels).  Canonical layout (cute
+// mma_sm100_desc: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units for SWIZZLE_128B): one swizzle atom = 8 K-rows x 128 B
+// (64 elements of M / N; 64 B = 32 elements with SWIZZLE_64B); LBO = byte distance between atoms along M / N, SBO = byte
+// distance between 8-row groups along K.  Pinned on hardware by tests/test_gpu_umma_probe.py (MN-major cases).
+__host__ __device__ constexpr uint32_t make_idesc_f16_mn(uint32_t fmt_a, uint32_t fmt_b, uint32_t M, uint32_t N) {
+  return (1u << 4) | (fmt_a << 7) | (fmt_b << 10) | (1u << 15) | (1u << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t swizzle) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= static_cast<uint64_t>(1u) << 46;
+  d |= static_cast<uint64_t>(swizzle & 7u) << 61;
+  return d;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {

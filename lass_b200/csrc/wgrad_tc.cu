@@ -1,0 +1,261 @@
+// Training step: weight gradients on tcgen05 (bf16 operands, fp32 accumulation in TMEM, TMA-fed).
+//
+//   dW[tap][co][ci] = sum over pixels p of dY[p][co] * X[p + tap][ci]      (zero padding; tap = ky*3 + kx)
+//
+// GEMM per kernel row ky:  D[(dx, ci), co] = sum_p X[p + (ky-1, dx-1)][ci] * dY[p][co]  with M = (dx, ci), N = co, K = pixels.
+// Both operands are NHWC tiles exactly as TMA delivers them ([pixel][channel], hardware swizzle): MN-major operands of
+// tcgen05.mma (the contraction index is the row).  The M dimension is filled with HORIZONTAL TAPS of the same channel chunk:
+// the X halo tile (18 x 10 pixels of CIW channels) lies in shared memory one pixel per row, so the tile shifted by one pixel is
+// the same memory one row further — an MN-major descriptor whose leading byte offset (distance between swizzle atoms along M)
+// is ONE ROW reads [dx = 0 | dx = 1 (| dx = 2 | dx = 3)] as one 128-row operand: 2 taps x 64 channels (SWIZZLE_128B) or
+// 4 taps x 32 channels (SWIZZLE_64B; the 4th "tap" is discarded).  The vertical tap is a start-address shift of 10 rows and
+// the 8-pixel rows of the 16 x 8 pixel tile are the descriptor's 8-row K groups with a stride of 10 rows — the descriptor
+// rules are pinned on hardware by tests/test_gpu_umma_probe.py::test_mn_major_descriptors.  So a 32-channel layer still
+// issues full M = 128 MMAs, and no operand is ever transposed or copied.
+//
+// One CTA = one (CIW-channel chunk of ci, NB-channel tile of co) output tile over a contiguous range of pixel tiles
+// (split-K; few weights + many pixels -> many ranges): all 3 x 3 taps accumulate in TMEM (3 ky x G dx-groups x NB columns),
+// then the epilogue adds the valid rows to dW with fp32 red.global.  Warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.
+#include "lass_internal.cuh"
+#include "ptx.cuh"
+
+namespace lass {
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kStages = 4;
+constexpr int kTH = 16, kTW = 8, kHaloH = 18, kHaloW = 10;
+
+struct WgradTcParams {
+  CUtensorMap tmX, tmY;
+  float* dw;
+  int co, ci, taps, x_fp16;
+  int tiles_h, tiles_w, num_pix_tiles;
+  int n_ci_chunks, n_co_tiles, splits;
+};
+
+template <int CIW, int NB>
+__global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
+  constexpr int RA = CIW * 2, RB = NB * 2;                       // bytes per pixel row of the X / dY tiles
+  constexpr uint32_t SWA = CIW == 64 ? kSwizzle128B : kSwizzle64B, SWB = NB == 64 ? kSwizzle128B : kSwizzle64B;
+  constexpr int XBYTES = kHaloH * kHaloW * RA, YBYTES = kTH * kTW * RB;
+  constexpr int XALLOC = (XBYTES + 1023) & ~1023;
+  constexpr int STAGE = XALLOC + YBYTES;
+  constexpr int TPM = 128 / CIW;                                 // horizontal taps per MMA (2 or 4)
+  constexpr int G = CIW == 64 ? 2 : 1;                           // MMAs (dx groups) per kernel row
+  constexpr int ACC_COLS = 3 * G * NB;
+  constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);
+  static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
+
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * STAGE + 1024);   // (+1024: garbage-tap reads run one row past a tile)
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* conv_bar = empty_bar + kStages;      // fp16 X tile converted to bf16 in place (x_fp16 launches only)
+  uint64_t* acc_bar = conv_bar + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int item = blockIdx.x;
+  const int split = item % p.splits;
+  item /= p.splits;
+  const int co_tile = item % p.n_co_tiles, ci_chunk = item / p.n_co_tiles;
+  const int t_begin = (int)((long long)p.num_pix_tiles * split / p.splits);
+  const int t_end = (int)((long long)p.num_pix_tiles * (split + 1) / p.splits);
+  const bool one_tap = p.taps == 1;
+  const int nky = one_tap ? 1 : 3, ng = one_tap ? 1 : G;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmX);
+    tma_prefetch_desc(&p.tmY);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+      mbar_init(&conv_bar[s], 4);
+    }
+    mbar_init(acc_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+        const int tw = tile % p.tiles_w;
+        const int r = tile / p.tiles_w;
+        const int th = r % p.tiles_h, b = r / p.tiles_h;
+        unsigned char* st = smem + s * STAGE;
+        mbar_arrive_expect_tx(&full_bar[s], XBYTES + YBYTES);
+        tma_load_4d(st, &p.tmX, &full_bar[s], ci_chunk * CIW, tw * kTW - 1, th * kTH - 1, b);
+        tma_load_4d(st + XALLOC, &p.tmY, &full_bar[s], co_tile * NB, tw * kTW, th * kTH, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16_mn(kFmtBF16, kFmtBF16, 128, NB);
+      uint32_t it = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+        const int s = it % kStages;
+        mbar_wait(p.x_fp16 ? &conv_bar[s] : &full_bar[s], (it / kStages) & 1);
+        tc_fence_after_sync();
+        const uint32_t xs = smem_u32(smem + s * STAGE), ys = xs + XALLOC;
+        for (int ky = 0; ky < nky; ++ky) {
+          const int kyr = one_tap ? 1 : ky;
+          for (int g = 0; g < ng; ++g) {
+            const int dx0 = one_tap ? 1 : g * TPM;
+            const uint32_t acc = tmem_base + (uint32_t)((ky * G + g) * NB);
+#pragma unroll
+            for (int ks = 0; ks < kTH / 2; ++ks) {
+              const uint64_t da = make_smem_desc_mn(xs + (uint32_t)(((2 * ks + kyr) * kHaloW + dx0) * RA), RA, kHaloW * RA, SWA);
+              const uint64_t db = make_smem_desc_mn(ys + (uint32_t)(ks * 2 * kTW * RB), 0, kTW * RB, SWB);
+              umma_f16(acc, da, db, idesc, (it | (uint32_t)ks) != 0u);
+            }
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(acc_bar);
+    }
+  } else {
+    // ---- fp16 activations: tcgen05 kind::f16 takes ONE 16-bit format for both operands (a mixed fp16 x bf16 descriptor is an
+    // illegal instruction on sm_100a), and the gradients need bf16's range, so the X tile is converted in place, element by
+    // element (the swizzle does not matter), by the warps that otherwise only wait for the epilogue ----
+    if (p.x_fp16) {
+      const int ct = threadIdx.x - 64;
+      uint32_t it = 0;
+      for (int tile = t_begin; tile < t_end; ++tile, ++it) {
+        const int s = it % kStages;
+        mbar_wait(&full_bar[s], (it / kStages) & 1);
+        unsigned char* st = smem + s * STAGE;
+        for (int off = ct * 16; off < XBYTES; off += 128 * 16) {
+          uint4 v = *reinterpret_cast<uint4*>(st + off);
+          uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+            const __nv_bfloat162 b = __float22bfloat162_rn(f);
+            w[j] = *reinterpret_cast<const uint32_t*>(&b);
+          }
+          *reinterpret_cast<uint4*>(st + off) = v;
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv_bar[s]);
+      }
+    }
+    // ---- epilogue: TMEM lane = (tap within the MMA) * CIW + channel; warp w reads lane quarter w % 4 ----
+    mbar_wait(acc_bar, 0);
+    tc_fence_after_sync();
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int a = row / CIW, cl = row % CIW;
+    const int ci = ci_chunk * CIW + cl;
+    if (t_begin < t_end) {
+      for (int ky = 0; ky < nky; ++ky)
+        for (int g = 0; g < ng; ++g) {
+          const int dx = one_tap ? (a == 0 ? 1 : 3) : g * TPM + a;
+          const bool valid = dx <= 2;
+          const int tap = one_tap ? 0 : ky * 3 + dx;
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)((ky * G + g) * NB);
+#pragma unroll 1
+          for (int c0 = 0; c0 < NB; c0 += 32) {
+            float v[32];
+            tmem_ld_x32(taddr + c0, v);
+            tmem_ld_wait();
+            if (valid) {
+              float* dst = p.dw + ((size_t)tap * p.co + co_tile * NB + c0) * p.ci + ci;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)j * p.ci, v[j]);
+            }
+          }
+        }
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after_sync();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+typedef void (*WgradTcFn)(const WgradTcParams);
+
+template <int CIW, int NB>
+size_t smem_bytes() {
+  constexpr int RA = CIW * 2, RB = NB * 2;
+  constexpr int XALLOC = (kHaloH * kHaloW * RA + 1023) & ~1023;
+  return 1024 + (size_t)kStages * (XALLOC + kTH * kTW * RB) + 1024 + 512;
+}
+
+}  // namespace
+}  // namespace lass
+
+using namespace lass;
+
+extern "C" int lass_wgrad_tc(const void* dy, int dy_cstride, int dy_coff, int co, const void* x, int x_fp16, int x_cstride, int x_coff, int ci,
+                             int B, int H, int W, int taps, float* dw, void* stream_v) {
+  if (!dy || !x || !dw) return set_error(LASS_ERR_ARG, "lass_wgrad_tc: null pointer");
+  if (B <= 0 || H <= 0 || W <= 0 || (taps != 9 && taps != 1) || co <= 0 || ci <= 0 || co % 32 || ci % 32 || dy_cstride % 8 || dy_coff % 8 ||
+      x_cstride % 8 || x_coff % 8 || dy_coff + co > dy_cstride || x_coff + ci > x_cstride)
+    return set_error(LASS_ERR_ARG, "lass_wgrad_tc: bad shape co=%d ci=%d taps=%d B=%d H=%d W=%d", co, ci, taps, B, H, W);
+  cudaStream_t s = (cudaStream_t)stream_v;
+  const int ciw = ci % 64 == 0 ? 64 : 32;
+  const int nb = co % 64 == 0 ? 64 : 32;
+  WgradTcParams p;
+  int e;
+  {
+    const char* base = reinterpret_cast<const char*>(x) + (size_t)x_coff * 2;
+    uint64_t dims[4] = {(uint64_t)ci, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)x_cstride * 2, (uint64_t)x_cstride * 2 * W, (uint64_t)x_cstride * 2 * W * H};
+    uint32_t box[4] = {(uint32_t)ciw, (uint32_t)kHaloW, (uint32_t)kHaloH, 1};
+    if ((e = make_tensor_map(&p.tmX, base, 2, 4, dims, strides, box, ciw == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))) return e;
+  }
+  {
+    const char* base = reinterpret_cast<const char*>(dy) + (size_t)dy_coff * 2;
+    uint64_t dims[4] = {(uint64_t)co, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)dy_cstride * 2, (uint64_t)dy_cstride * 2 * W, (uint64_t)dy_cstride * 2 * W * H};
+    uint32_t box[4] = {(uint32_t)nb, (uint32_t)kTW, (uint32_t)kTH, 1};
+    if ((e = make_tensor_map(&p.tmY, base, 2, 4, dims, strides, box, nb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))) return e;
+  }
+  p.dw = dw;
+  p.co = co;
+  p.ci = ci;
+  p.taps = taps;
+  p.x_fp16 = x_fp16 ? 1 : 0;
+  p.tiles_h = (H + kTH - 1) / kTH;
+  p.tiles_w = (W + kTW - 1) / kTW;
+  p.num_pix_tiles = B * p.tiles_h * p.tiles_w;
+  p.n_ci_chunks = ci / ciw;
+  p.n_co_tiles = co / nb;
+  const int out_tiles = p.n_ci_chunks * p.n_co_tiles;
+  const int sms = device_sm_count();
+  int splits = (2 * sms + out_tiles - 1) / out_tiles;
+  if (out_tiles >= sms) splits = 1;
+  if (splits > p.num_pix_tiles) splits = p.num_pix_tiles;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  WgradTcFn fn;
+  size_t smem;
+  if (ciw == 64 && nb == 64) { fn = wgrad_tc_kernel<64, 64>; smem = smem_bytes<64, 64>(); }
+  else if (ciw == 64) { fn = wgrad_tc_kernel<64, 32>; smem = smem_bytes<64, 32>(); }
+  else if (nb == 64) { fn = wgrad_tc_kernel<32, 64>; smem = smem_bytes<32, 64>(); }
+  else { fn = wgrad_tc_kernel<32, 32>; smem = smem_bytes<32, 32>(); }
+  if (smem < 120 * 1024) smem = 120 * 1024;       // one CTA per SM: two could not both hold their TMEM accumulators
+  cudaError_t ce = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)taps * co * ci, s);
+  if (ce != cudaSuccess) return set_cuda_error(ce, "wgrad_tc memset");
+  ce = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (ce != cudaSuccess) return set_cuda_error(ce, "wgrad_tc smem attribute");
+  fn<<<out_tiles * splits, kThreads, smem, s>>>(p);
+  return set_cuda_error(cudaGetLastError(), "wgrad_tc launch");
+}

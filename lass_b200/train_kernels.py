@@ -19,6 +19,8 @@ from . import _cabi
 RAW_DTYPE = torch.float16
 ACT_DTYPE = torch.float16
 GRAD_DTYPE = torch.bfloat16
+# weight gradients: tcgen05 kernel (csrc/wgrad_tc.cu); False selects the mma.sync kernel it replaced (csrc/wgrad.cu, kept for A/B)
+WGRAD_TENSOR_CORE = True
 
 
 def _p(t):
@@ -204,8 +206,10 @@ def wgrad(dy, dy_coff, co, x, x_coff, ci, taps, dw):
     _need_cuda(dy, x, dw)
     B, H, W, _ = dy.shape
     assert x.shape[:3] == dy.shape[:3] and dw.numel() == taps * co * ci and dw.dtype == torch.float32
-    _chk(_cabi.load().lass_wgrad(_p(dy), dy.shape[3], dy_coff, co, _p(x), 1 if x.dtype == torch.float16 else 0, x.shape[3],
-                                 x_coff, ci, B, H, W, taps, _p(dw), _stream()))
+    lib = _cabi.load()
+    fn = lib.lass_wgrad_tc if WGRAD_TENSOR_CORE else lib.lass_wgrad
+    _chk(fn(_p(dy), dy.shape[3], dy_coff, co, _p(x), 1 if x.dtype == torch.float16 else 0, x.shape[3], x_coff, ci, B, H, W,
+            taps, _p(dw), _stream()))
 
 
 def pre_fwd(mag, bnp0, pre_w, pre_b, x0):

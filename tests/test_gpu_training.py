@@ -122,8 +122,10 @@ WGRAD_CASES = [  # co, ci, taps, B, H, W, x fp16
 ]
 
 
+@pytest.mark.parametrize("tensor_core", [True, False], ids=["tcgen05", "mma_sync"])
 @pytest.mark.parametrize("co,ci,taps,B,H,W,xfp16", WGRAD_CASES)
-def test_wgrad(K, co, ci, taps, B, H, W, xfp16):
+def test_wgrad(K, co, ci, taps, B, H, W, xfp16, tensor_core, monkeypatch):
+    monkeypatch.setattr(K, "WGRAD_TENSOR_CORE", tensor_core)
     dy = _rand16((B, H, W, co + 32), torch.bfloat16, 1e-3, 8)
     x = _rand16((B, H, W, ci + 64), torch.float16 if xfp16 else torch.bfloat16, 1.0, 9)
     r = []
