@@ -16,9 +16,12 @@ Output: ONE JSON line on rank 0 (see the keys below; contract in the task descri
   roofline the dominant kernel class (tcgen05 implicit-GEMM conv, 32 launches / step): algorithmic FLOPs of the
            UNet / CUDA-event time of the UNET stage, against the measured bf16 peak of MEASURED_PEAKS.json
   spectral BASELINE config 2 (STFT -> mask -> iSTFT round trip, 64 x 10 s): achieved HBM GB/s of K1 and K5
-  cpu_baseline  the oracle port of the reference forward timed on this box's host cores (1 clip, best of 3)
-``--impl reference`` times the reference's CPU implementation of the path (oracle port: /root/reference does not
-exist on the GPU box and a Python reference cannot travel) with all host threads, one 10 s clip per step.
+  cpu_baseline  the reference forward timed on this box's host cores (1 clip, best of 3): the UNMODIFIED reference when
+           oracle/_ref travelled with the snapshot (kind "reference"), else the oracle port (kind "port")
+  train    BASELINE config 4: one optimisation step (train-mode forward, l1_wav, backward, NCCL gradient all-reduce,
+           fused AdamW-amsgrad) on 16 clips x 5 s per GPU, host inputs, loss read back; all-reduce timed alone as well
+  north_star_shape / latency / strong_scaling / clap_standin  the other configurations SURVEY.md §8(d) asks for
+``--impl reference`` times the reference's CPU implementation of the path with all host threads, one 10 s clip per step.
 """
 import argparse
 import json
@@ -137,20 +140,40 @@ def make_batch(batch, seed):
 
 
 def cpu_reference_forward_time(repeats, threads=None):
-    """Oracle port of the reference forward (fp32, eval, no_grad) on the host cores: seconds per 10 s clip."""
+    """The reference forward (fp32, eval, no_grad) on the host cores: (seconds per 10 s clip list, kind, description).
+    kind "reference": the unmodified models/resunet.py of the reference (oracle/_ref, see oracle/build_ref.py) over the
+    restated torchlibrosa; kind "port": the functional restatement oracle/resunet_oracle.py (same aten ops, same order)."""
     from lass_b200.models.resunet import ResUNet30
-    from oracle import resunet_oracle
+    from oracle import reference_loader, resunet_oracle
     if threads:
         torch.set_num_threads(threads)
     torch.manual_seed(0)
     sd = {k: v.clone() for k, v in ResUNet30(1, 1, 512).state_dict().items()}
     mix, cond = make_batch(1, 1234)
+    kind, what, fn = "port", "oracle port of the reference (oracle/resunet_oracle.py)", None
+    if reference_loader.reference_available():
+        try:
+            ref_mod = reference_loader.import_reference_resunet()
+            ref = ref_mod.ResUNet30(input_channels=1, output_channels=1, condition_size=512).eval()
+            ref.load_state_dict(sd)
+            kind, what = "reference", "unmodified reference models/resunet.py (%s) over the restated torchlibrosa" % (
+                os.path.relpath(reference_loader.REFERENCE_ROOT, ROOT) if reference_loader.REFERENCE_ROOT.startswith(ROOT)
+                else reference_loader.REFERENCE_ROOT)
+
+            def fn():
+                with torch.no_grad():
+                    return ref({"mixture": mix, "condition": cond})["waveform"]
+        except Exception as exc:                         # noqa: BLE001 - any import problem falls back to the port, and says so
+            what += " (reference import failed: %s)" % repr(exc)[:120]
+    if fn is None:
+        def fn():
+            return resunet_oracle.resunet30_forward(sd, mix, cond, hop=HOP)
     times = []
     for i in range(repeats + 1):          # first pass is the warm-up
         t0 = time.perf_counter()
-        resunet_oracle.resunet30_forward(sd, mix, cond, hop=HOP)
+        fn()
         times.append(time.perf_counter() - t0)
-    return times[1:]
+    return times[1:], kind, what
 
 
 def run_reference(args, rank, world):
@@ -158,7 +181,8 @@ def run_reference(args, rank, world):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    t = cpu_reference_forward_time(args.warmup + args.steps - 1)[-(args.steps):]
+    t, kind, what = cpu_reference_forward_time(args.warmup + args.steps - 1)
+    t = t[-(args.steps):]
     per_step = sum(t) / len(t)
     value = CLIP_SECONDS / per_step
     line = {
@@ -168,9 +192,8 @@ def run_reference(args, rank, world):
         "config": {"workload": "ResUNet30 separation forward, 10 s @ 16 kHz clips, n_fft 1024 / hop 160 "
                                "(BASELINE.json configs[2] shape; reference arm runs 1 clip per step on the CPU)",
                    "clip_seconds": CLIP_SECONDS, "sample_rate": SAMPLE_RATE, "batch_per_step": 1},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                         "sample": "1 clip (10 s) per step, fp32 eval forward of the oracle port "
-                                   "(oracle/resunet_oracle.py; /root/reference is not present on the GPU box)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                         "sample": "1 clip (10 s) per step, fp32 eval forward: " + what},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -219,6 +242,159 @@ def time_spectral(device, peaks):
     return out
 
 
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Extra configurations of SURVEY.md §8(d) carried in the same JSON line
+# ---------------------------------------------------------------------------------------------------------------------
+TRAIN_CLIPS_PER_GPU = 16          # BASELINE config 4: 16 x 5 s mixtures per rank
+TRAIN_SAMPLES = 80000
+
+
+def clap_conditions(batch, device):
+    """BASELINE config 3 'as stated': the 512-d conditions come from the random-init CLAP text stand-in (RoBERTa-base
+    geometry, 124.6 M parameters, 512-token captions; PyTorch, off the hot path) — computed once, outside the timed hot path,
+    and its time reported.  Returns (cond (batch, 512) on device, info dict)."""
+    from lass_b200.models.clap_standin import RandomInitCLAPTextEncoder
+    t0 = time.perf_counter()
+    enc = RandomInitCLAPTextEncoder().to(device)
+    build_s = time.perf_counter() - t0
+    words = ("dog", "rain", "engine", "speech", "piano", "siren", "wind", "crowd", "bird", "door", "water", "drum")
+    captions = ["the sound of a %s and a %s number %d" % (words[i % 12], words[(i * 5 + 3) % 12], i) for i in range(batch)]
+    enc.get_query_embed(modality="text", text=captions[:2])          # warm-up (cuDNN / cuBLAS handles), then drop the cache
+    enc._cache.clear()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cond = enc.get_query_embed(modality="text", text=captions)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) * 1e3
+    info = {"ms_for_batch": ms, "captions": batch, "tokens_per_caption": 512, "build_s": build_s,
+            "note": "random-init RoBERTa-base text tower + projection in PyTorch fp32, one pass per distinct caption, "
+                    "outside the timed hot path"}
+    del enc
+    torch.cuda.empty_cache()
+    return cond.contiguous(), info
+
+
+def time_forward(model, batch, length, steps, warmup, device, sync_each=False):
+    """audio-s/s of `steps` module forwards on device-resident inputs (CUDA events); sync_each = latency mode."""
+    g = torch.Generator().manual_seed(99)
+    mix = (0.1 * torch.randn(batch, 1, length, generator=g)).to(device)
+    cond = torch.nn.functional.normalize(torch.randn(batch, 512, generator=g), dim=-1).to(device)
+    inp = {"mixture": mix, "condition": cond}
+    for _ in range(warmup):
+        model(inp)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(steps):
+        out = model(inp)["waveform"]
+        if sync_each:
+            out[0, 0, :1].cpu()                         # the caller waits for every result (what dcase_evaluator.py does)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    return e0.elapsed_time(e1) * 1e-3 / steps, wall / steps
+
+
+def time_train(device, rank, world, steps, warmup, peaks):
+    """BASELINE config 4 through TrainEngine.training_step: per step H2D of mixture / condition / target from pinned host
+    memory, train-mode forward, l1_wav, backward, NCCL all-reduce of the flat gradient (two buckets, overlapped with the
+    encoder's backward), fused AdamW-amsgrad + weight re-pack, loss copied back to the host."""
+    import torch.distributed as dist
+    from lass_b200 import sharding, train_kernels, training
+    from lass_b200.models.resunet import ResUNet30
+    torch.manual_seed(0)
+    model = ResUNet30(input_channels=1, output_channels=1, condition_size=512, window_size=N_FFT, hop_size=HOP).to(device).train()
+    eng = training.TrainEngine(model)
+    B, Ls = TRAIN_CLIPS_PER_GPU, TRAIN_SAMPLES
+    g = torch.Generator().manual_seed(4321 + rank)
+    mix_h = (0.1 * torch.randn(B, 1, Ls, generator=g)).pin_memory()
+    tgt_h = (0.05 * torch.randn(B, 1, Ls, generator=g)).pin_memory()
+    cond_h = torch.nn.functional.normalize(torch.randn(B, 512, generator=g), dim=-1).pin_memory()
+    loss_h = torch.zeros(steps + warmup, dtype=torch.float32).pin_memory()
+
+    def step(i):
+        mix, tgt, cond = (t.to(device, non_blocking=True) for t in (mix_h, tgt_h, cond_h))
+        with torch.no_grad():
+            loss = eng.training_step(mix, cond, tgt, lr=1e-5)
+        loss_h[i:i + 1].copy_(loss.reshape(1), non_blocking=True)
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    c0 = train_kernels.CALLS
+    step(0)
+    calls_per_step = train_kernels.CALLS - c0
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i)
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    step_s = sharding.max_over_ranks(e0.elapsed_time(e1) * 1e-3 / steps, device)
+    # phases without the collective (this rank), CUDA events
+    mix, tgt, cond = (t.to(device) for t in (mix_h, tgt_h, cond_h))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ph = [0.0, 0.0, 0.0]
+    reps = 3
+    with torch.no_grad():
+        for _ in range(reps):
+            ev[0].record()
+            eng.forward(mix, cond)
+            ev[1].record()
+            ws = eng._last
+            ws.loss_sum.zero_()
+            eng.k.l1_loss(ws.wave, tgt.reshape(B, Ls), ws.dwave, ws.loss_sum)
+            eng.backward(ws.dwave)
+            ev[2].record()
+            eng.optimizer_step(1e-5)
+            ev[3].record()
+            torch.cuda.synchronize()
+            for j in range(3):
+                ph[j] += ev[j].elapsed_time(ev[j + 1]) / reps
+    out = {"workload": "AudioSep training step (BASELINE.json configs[3]): %d clips x 5 s @ 16 kHz per GPU, n_fft %d / hop %d, "
+                       "train-mode BatchNorm (batch statistics), l1_wav, backward, AdamW(amsgrad)" % (B, N_FFT, HOP),
+           "clips_per_gpu": B, "global_clips": B * world, "ms_per_step": step_s * 1e3, "steps_per_s": 1.0 / step_s,
+           "audio_s_per_s": B * world * Ls / SAMPLE_RATE / step_s, "steps": steps,
+           "phases_ms_no_collective": {"forward": ph[0], "loss_backward": ph[1], "adamw_repack": ph[2]},
+           "cabi_calls_per_step": calls_per_step, "loss_first": float(loss_h[0]), "loss_last": float(loss_h[steps + warmup - 1]),
+           "h2d_bytes_per_step": (mix_h.numel() + tgt_h.numel() + cond_h.numel()) * 4, "d2h_bytes_per_step": 4,
+           "grad_elements": int(eng.live_end), "storage": "forward tensors fp16, gradients bf16, parameters / optimizer state / "
+                                                          "statistics fp32",
+           "mem_gb": torch.cuda.max_memory_allocated(device) / 1e9}
+    # algorithmic conv FLOPs of the step: forward + dgrad + wgrad = 3 x the UNet forward of 16 x 5 s
+    flops = 3.0 * UNET_GFLOP_PER_CLIP * 1e9 * (B * Ls / float(L))
+    out["conv_tflops_algorithmic"] = flops / step_s / 1e12
+    out["frac_of_bf16_sustained"] = flops / step_s / 1e12 / peaks["bf16_tflops_sustained"]
+    if world > 1:
+        n = int(eng.live_end)
+        for _ in range(2):
+            dist.all_reduce(eng.G[:n])
+        torch.cuda.synchronize()
+        dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(5):
+            dist.all_reduce(eng.G[:n])
+        a1.record()
+        torch.cuda.synchronize()
+        ar_s = sharding.max_over_ranks(a0.elapsed_time(a1) * 1e-3 / 5, device)
+        out["allreduce"] = {"bytes": n * 4, "ms_alone": ar_s * 1e3, "algbw_gbs": n * 4 / ar_s / 1e9,
+                            "busbw_gbs": n * 4 / ar_s / 1e9 * 2.0 * (world - 1) / world,
+                            "exposed_ms_in_step": max(0.0, step_s * 1e3 - sum(ph)),
+                            "note": "NCCL sum over NVLink of the flat fp32 gradient (two buckets in the step: decoder bucket "
+                                    "overlaps the encoder backward); 1/world folded into the AdamW kernel"}
+    del eng, model
+    torch.cuda.empty_cache()
+    return out
+
+
 # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints "NCCL version ..." to fd 1 when NCCL_DEBUG is
 # set in the environment), so the process keeps a private copy of the real stdout for the result line and points fd 1 at stderr.
 _RESULT_FD = None
@@ -251,6 +427,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-spectral", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip train / north-star shape / latency / strong scaling / CLAP")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -279,6 +456,11 @@ def main():
     n_clips_total = B * world
     lo, hi = sharding.shard_bounds(n_clips_total, rank, world)       # this rank's slab of the global batch
     mix_h, cond_h = make_batch(hi - lo, 1234 + rank)
+    clap = None
+    if not args.no_extras:
+        cond_d0, clap = clap_conditions(hi - lo, device)          # config 3 as stated: conditions from the CLAP stand-in
+        cond_h = cond_d0.cpu()
+        del cond_d0
     mix_h, cond_h = mix_h.pin_memory(), cond_h.pin_memory()
     mix_d, cond_d = mix_h.to(device), cond_h.to(device)
     out_h = torch.empty(hi - lo, 1, L, dtype=torch.float32).pin_memory()
@@ -330,7 +512,25 @@ def main():
         torch.cuda.synchronize()
         for i in range(3):
             stage_ms[i] += ev[i].elapsed_time(ev[i + 1]) / args.steps
-    unet_s = sharding.max_over_ranks(stage_ms[1] * 1e-3, device)
+    # roofline region: the UNet stage alone, looped for >= 2 s so that "sustained" clocks apply (a 0.4 s region runs at burst
+    # clocks and would flatter the fraction); clocks sampled over exactly this region
+    n_roof = max(args.steps, int(2.0 / max(stage_ms[1] * 1e-3, 1e-4)) + 1)
+    sampler_r = ClockSampler(local_rank)
+    sampler_r.start()
+    t_s = time.time()
+    while not sampler_r.samples and time.time() - t_s < 3.0:
+        time.sleep(0.05)
+    barrier()
+    t_r0 = time.time()
+    r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    r0.record()
+    for _ in range(n_roof):
+        engine.forward_stages(mix_d, cond_d, out_d, 2)
+    r1.record()
+    barrier()
+    t_r1 = time.time()
+    clocks_roof = sampler_r.stop(t_r0, t_r1)
+    unet_s = sharding.max_over_ranks(r0.elapsed_time(r1) * 1e-3 / n_roof, device)
     n_conv_launches = launches_per_step - 4      # stft_prep, stft_gemm, film, mask_istft are the others
     achieved_tflops = unet_flops / unet_s / 1e12
 
@@ -384,17 +584,58 @@ def main():
     h2d = mix_h.numel() * 4 + cond_h.numel() * 4
     d2h = out_h.numel() * 4
 
+    # ---------------- the other configurations (every rank takes part where ranks matter) ----------------
+    extras = {}
+    if not args.no_extras:
+        if world > 1 and BATCH_PER_GPU % world == 0:
+            # strong scaling: the SAME 64 global clips split over the ranks
+            bs = BATCH_PER_GPU // world
+            dev_t, _ = time_forward(model, bs, L, args.steps, args.warmup, device)
+            barrier()
+            dev_t = sharding.max_over_ranks(dev_t, device)
+            extras["strong_scaling"] = {"global_clips": BATCH_PER_GPU, "clips_per_gpu": bs, "ms_per_step": dev_t * 1e3,
+                                        "audio_s_per_s": BATCH_PER_GPU * CLIP_SECONDS / dev_t}
+        extras["train"] = time_train(device, rank, world, args.steps, args.warmup, peaks)
+
     spectral = None
     cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        # latency (the reference's shipped driver runs batch 1, dcase_evaluator.py:99-104) and small batches, through the module
+        lat = {}
+        for bsz in (1, 8):
+            dev_t, wall_t = time_forward(model, bsz, L, 50 if bsz == 1 else 20, 5, device, sync_each=True)
+            lat["batch%d" % bsz] = {"ms_per_call_wall": wall_t * 1e3, "ms_per_call_device": dev_t * 1e3,
+                                    "audio_s_per_s": bsz * CLIP_SECONDS / wall_t}
+        g = torch.Generator().manual_seed(7)
+        long_mix = (0.1 * torch.randn(1, 1, 60 * SAMPLE_RATE, generator=g)).to(device)
+        long_in = {"mixture": long_mix, "condition": cond_d[:1]}
+        model.chunk_inference(long_in, rate=SAMPLE_RATE)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        model.chunk_inference(long_in, rate=SAMPLE_RATE)
+        lat["chunk_inference_60s"] = {"ms": (time.perf_counter() - t0) * 1e3,
+                                      "note": "60 s clip, 5 s windows hopping 3 s stacked on the batch axis, result as numpy"}
+        extras["latency"] = lat
+        # the north_star's STFT shape (n_fft 2048 / hop 320): whole forward, 64 x 10 s
+        from lass_b200.models.resunet import ResUNet30
+        engine.release()                                   # plans + workspace of the 1024 / 160 model (rebuilt on next use)
+        torch.cuda.empty_cache()
+        torch.manual_seed(0)
+        m2 = ResUNet30(input_channels=1, output_channels=1, condition_size=512, window_size=2048, hop_size=320).eval().to(device)
+        dev_t, _ = time_forward(m2, BATCH_PER_GPU, L, args.steps, args.warmup, device)
+        extras["north_star_shape"] = {"n_fft": 2048, "hop": 320, "clips": BATCH_PER_GPU, "ms_per_step": dev_t * 1e3,
+                                      "audio_s_per_s": BATCH_PER_GPU * CLIP_SECONDS / dev_t}
+        del m2
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1:
         if not args.no_spectral:
             spectral = time_spectral(device, peaks)
         if not args.no_cpu_baseline:
-            t = cpu_reference_forward_time(3)
+            t, kind, what = cpu_reference_forward_time(3)
             best = min(t)
-            cpu_baseline = {"value": CLIP_SECONDS / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                            "sample": "1 clip (10 s @ 16 kHz) of the same workload, fp32 eval forward of the oracle port of "
-                                      "the reference (oracle/resunet_oracle.py), 1 warm-up + best of 3",
+            cpu_baseline = {"value": CLIP_SECONDS / best, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                            "sample": "1 clip (10 s @ 16 kHz) of the same workload, fp32 eval forward, 1 warm-up + best of 3: "
+                                      + what,
                             "seconds_per_clip": best}
 
     traffic = None
@@ -412,9 +653,10 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_s / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "ResUNet30 separation forward (BASELINE.json configs[2] minus the off-path CLAP encoder): "
-                                   "%d clips x 10 s @ 16 kHz per GPU, n_fft %d / hop %d, random-init weights, fixed unit-norm "
-                                   "512-d conditions" % (B, N_FFT, HOP),
+            "config": {"workload": "ResUNet30 separation forward (BASELINE.json configs[2]): "
+                                   "%d clips x 10 s @ 16 kHz per GPU, n_fft %d / hop %d, random-init weights, unit-norm 512-d "
+                                   "conditions %s" % (B, N_FFT, HOP, "from the random-init CLAP text stand-in (computed once, "
+                                                      "outside the timed region)" if clap else "(fixed random)"),
                        "clips_per_gpu": B, "global_clips": n_clips_total, "clip_seconds": CLIP_SECONDS,
                        "sample_rate": SAMPLE_RATE, "n_fft": N_FFT, "hop": HOP, "sharding": "clips across ranks, no collective",
                        "l2": "inputs_exceed_l2 (per-step activations are GBs, L2 is 126 MB)",
@@ -427,14 +669,23 @@ def main():
             "stage_ms": {"front_stft_film": stage_ms[0], "unet_convs": stage_ms[1], "mask_istft": stage_ms[2]},
             "roofline": {"kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, %d launches per step)" % n_conv_launches,
                          "bound": "tensor", "achieved": achieved_tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": achieved_tflops / peak, "traffic": traffic,
-                         "peak_source": "%s bf16_tflops_sustained (kernel timed inside a long step)" % peaks["source"],
+                         "frac": achieved_tflops / peak, "frac_burst": achieved_tflops / peaks["bf16_tflops"],
+                         "peak_burst": peaks["bf16_tflops"], "traffic": traffic,
+                         "traffic_source": "offline constant: ncu --set full capture of the 32 conv launches "
+                                           "(profiles/traffic.json), NOT measured in this run",
+                         "peak_source": "%s bf16_tflops_sustained (stage looped %d x = %.1f s, clocks below)" % (
+                             peaks["source"], n_roof, unet_s * n_roof),
+                         "region_clocks": clocks_roof,
                          "algorithmic_gflop_per_clip": unet_flops / (hi - lo) / 1e9,
                          "layerwise_roofline_us_per_clip": 227.8,
                          "layerwise_frac": 227.8e-6 * (hi - lo) / unet_s},
             "cpu_baseline": cpu_baseline,
             "spectral": spectral,
+            "clap_standin": clap,
         }
+        line.update(extras)
+        if "train" in extras:
+            line["gpu_launches_train_calls_per_step"] = extras["train"]["cabi_calls_per_step"]
         emit(line)
     if world > 1:
         dist.destroy_process_group()

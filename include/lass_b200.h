@@ -141,9 +141,7 @@ typedef struct lass_conv_desc {
   const float* resid_w;
   const float* resid_b;
   int resid_T, resid_F;
-  /* 0: taps accumulated over K (weights (taps, ncols, cin)).  1: "dx-in-N" formulation for 3x3 convs with 32 or 64 output
-   * channels: the three horizontal taps become output columns (N = 3*Cout, K = 3*Cin, a third of the MMAs) and are summed
-   * by lane shuffles in the epilogue; seg[0].weights is then (3 [ky], 3*Cout [kx, co], cin), seg[1] (optional 1x1) as before. */
+  /* Reserved, must be 0 (taps accumulate over K, weights (taps, ncols, cin)).  1 selected a retired "dx-in-N" kernel. */
   int algo;
   /* Optional GENERATED A operand for seg[0] (the first conv of encoder_block1, whose input is the activated pre_conv output
    * of the 1-channel magnitude, reference models/resunet.py:537-556 + ConvBlockRes.bn1): instead of reading seg[0].src the
@@ -329,10 +327,7 @@ typedef struct lass_resunet30_weights {
   } dec[6];
   const float* after_w;        /* (3, 32) */
   const float* after_b;        /* (3) */
-  /* Bit mask of 3x3 convolutions whose weights are packed in the "dx-in-N" layout (3, 3*cout, cin) and run with
-   * lass_conv_desc.algo = 1: bit 2k + i = encoder block k conv(i+1); bit 14 + 2j + i = decoder block j conv_block2.conv(i+1).
-   * Only layers with cout in {32, 64} qualify (encoder blocks 0-1, decoder blocks 4-5). */
-  unsigned int dxn_mask;
+  unsigned int dxn_mask;       /* reserved, must be 0 */
 } lass_resunet30_weights;
 
 typedef struct lass_plan lass_plan;
@@ -376,37 +371,6 @@ LASS_API int lass_resunet30_num_launches(const lass_plan* plan);
  * "d_act1".."d_act6"}; returns a device pointer or NULL; dims = {d0,d1,d2,d3} elements, *elem_bytes 2 or 4. */
 LASS_API void* lass_resunet30_buffer(const lass_plan* plan, const char* name, int dims[4], int* elem_bytes);
 LASS_API void lass_resunet30_plan_destroy(lass_plan* plan);
-
-/* ------------------------------------------------------------------------------------------------------
- * Debug: one tcgen05.mma tile (M = 128) with caller-controlled shared-memory descriptors; used by the GPU
- * tests to pin the descriptor rules the conv kernel relies on.  A (a_rows, kc) and Bm (n, kc) are 16-bit
- * K-major; out (128, n) fp32.  swizzle_mode: 0 none, 2 = 128 B, 4 = 64 B, 6 = 32 B.
- * ---------------------------------------------------------------------------------------------------- */
-LASS_API int lass_debug_umma_probe(const void* A, int a_rows, const void* Bm, int n, int kc, int swizzle_mode,
-                                   int a_start_bytes, int a_sbo, int a_base_offset, int b_sbo, int fmt_fp16,
-                                   float* out, void* stream);
-
-/* Debug: the same for MN-major operands (rows of the tile = contraction index K; the weight-gradient kernel's layouts): A
- * (a_rows, 64 | 32) and Bm (b_rows, 64 | 32) 16-bit (64 elements per row with swizzle 2 = 128 B, 32 with 4 = 64 B); `ksteps`
- * MMAs (M = 128, N = n, K = 16) with start = tile + *_start + ks * *_kstep bytes, leading / stride byte offsets *_lbo /
- * *_sbo; the two operands may differ in format (fp16 / bf16).  out (128, n) fp32. */
-LASS_API int lass_debug_umma_probe_mn(const void* A, int a_rows, int a_swz, const void* Bm, int b_rows, int b_swz, int n,
-                                      int ksteps, int a_start, int a_lbo, int a_sbo, int a_kstep, int b_start, int b_lbo,
-                                      int b_sbo, int b_kstep, int a_fp16, int b_fp16, float* out, void* stream);
-
-/* Debug: tcgen05.mma issue/execute throughput for a given operand layout: `iters` back-to-back MMAs (M = 128,
- * N = n, K = 16) over zeroed shared memory, `nacc` accumulators round-robin; cycles_out[grid] receives the SM
- * clock cycles from first issue to completion. */
-LASS_API int lass_debug_umma_bench(int n, int kc, int swizzle_mode, int a_start_bytes, int a_sbo, int iters, int nacc,
-                                   int grid, long long* cycles_out, void* stream);
-/* Same measurement with the issue loop unrolled 8x (about two instructions per MMA from the issuing thread), so
- * that MMAs shorter than the first version's loop overhead are resolved.  nacc in {1, 2}; iters % 8 == 0. */
-LASS_API int lass_debug_umma_bench2(int n, int kc, int swizzle_mode, int a_start_bytes, int a_sbo, int iters, int nacc,
-                                    int grid, long long* cycles_out, void* stream);
-/* Issue-rate benchmark of the conv kernel's own steady-state MMA issue code (one halo chunk = 9 taps x mt m-tiles x
- * ksteps k-steps per item, nothing else running); mode 0 = running descriptors, 1 = per-tap re-derived descriptors. */
-LASS_API int lass_debug_umma_bench3(int mt, int bn, int ksteps, int mode, int iters, int grid, long long* cycles_out,
-                                    void* stream);
 
 #ifdef __cplusplus
 }

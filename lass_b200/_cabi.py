@@ -35,6 +35,10 @@ SIGNATURES = {
                               c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "lass_mask_istft": (c_int, [c_void_p, c_longlong, c_longlong, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+}
+# liblass_b200_debug.so (include/lass_b200_debug.h): descriptor probes / microbenchmarks, not in the product library
+DEBUG_LIB_PATH = os.path.join(_HERE, "_lib", "liblass_b200_debug.so")
+DEBUG_SIGNATURES = {
     "lass_debug_umma_probe": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                       c_int, c_void_p, c_void_p]),
 }
@@ -67,9 +71,28 @@ def load():
     return _lib
 
 
-def check(code):
+_dbg = None
+
+
+def load_debug():
+    """The probe / microbenchmark library (tests and tools only)."""
+    global _dbg
+    if _dbg is None:
+        with _lock:
+            if _dbg is None:
+                if not os.path.isfile(DEBUG_LIB_PATH):
+                    raise LassLibraryError("%s not found: build it with `make`" % DEBUG_LIB_PATH)
+                lib = ctypes.CDLL(DEBUG_LIB_PATH)
+                for name, (restype, argtypes) in list(DEBUG_SIGNATURES.items()) + [("lass_last_error", (ctypes.c_char_p, []))]:
+                    fn = getattr(lib, name)
+                    fn.restype, fn.argtypes = restype, argtypes
+                _dbg = lib
+    return _dbg
+
+
+def check(code, lib=None):
     if code != 0:
-        msg = load().lass_last_error()
+        msg = (lib or load()).lass_last_error()
         raise LassError(code, msg.decode("utf-8", "replace") if msg else "")
 
 
@@ -99,9 +122,9 @@ class ConvDesc(ctypes.Structure):
 SIGNATURES["lass_conv_igemm"] = (c_int, [ctypes.POINTER(ConvDesc), c_void_p])
 SIGNATURES["lass_debug_set_conv_flags"] = (c_int, [c_int])
 SIGNATURES["lass_debug_set_conv_profile"] = (c_int, [c_void_p])
-SIGNATURES["lass_debug_umma_bench"] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
-SIGNATURES["lass_debug_umma_bench3"] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
-SIGNATURES["lass_debug_umma_bench2"] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
+DEBUG_SIGNATURES["lass_debug_umma_bench"] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
+DEBUG_SIGNATURES["lass_debug_umma_bench3"] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
+DEBUG_SIGNATURES["lass_debug_umma_bench2"] = (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p])
 
 
 # ---- whole-model entry (lass_resunet30_*) ----
@@ -180,4 +203,4 @@ SIGNATURES.update({
     "lass_debug_set_istft_v1": (_i, [_i]),
 })
 SIGNATURES["lass_wgrad_tc"] = SIGNATURES["lass_wgrad"]
-SIGNATURES["lass_debug_umma_probe_mn"] = (_i, [_v, _i, _i, _v, _i, _i, _i, _i] + [_i] * 10 + [_v, _v])
+DEBUG_SIGNATURES["lass_debug_umma_probe_mn"] = (_i, [_v, _i, _i, _v, _i, _i, _i, _i] + [_i] * 10 + [_v, _v])

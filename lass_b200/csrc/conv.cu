@@ -50,7 +50,6 @@ enum : uint32_t {
   kFUpDirect = kFRaw | kFAct | kFUp,                     // the last one (32 channels): 32-byte direct stores
   kFAfterBias = kFAfter | kFBias,                        // decoder_block6 conv2 + after_conv
 };
-constexpr int kThreads = 320;   // conv_dxn_kernel: warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 / 6-9 two epilogue groups
 constexpr int kThreadsK = 384;  // conv_igemm_kernel: warps 0-1 TMA producers, 2-3 MMA issuers, 4-7 / 8-11 epilogue groups
 // accumulator stages / TMEM columns of conv_igemm_kernel<BN, MT>
 constexpr int acc_stages(int BN, int MT) { return (4 * MT * BN <= 256) ? 4 : (2 * MT * BN <= 512) ? 2 : 1; }
@@ -1131,376 +1130,6 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
   }
 }
 
-// =====================================================================================================================
-// "dx-in-N" variant for 3x3 convolutions with few output channels (Cout = 32 / 64).
-//
-// Measured on B200 (tools/gpu_umma_bench.py): an M = 128, K = 16 tcgen05.mma with shared-memory operands costs
-// max(~80, N/2) cycles, so the tap-in-K formulation above pays ~80 cycles per (tap, 16 channels) even for N = 32.  Here the
-// three horizontal taps are folded into N instead:
-//     D[q, (dx, co)] = sum_{dy, ci} in[q + (dy-1, 0), ci] * W[co, ci, dy, dx]          (N = 3*Cout, K = 3*Cin)
-//     out[(h, w), co] = D[(h, w-1), (0, co)] + D[(h, w), (1, co)] + D[(h, w+1), (2, co)]
-// which needs a third of the MMAs.  A tile: positions of 8*MT image rows x 16 columns (one halo column on each side,
-// 14 output columns); the dy taps are whole-row shifts of a dense shared-memory tile (10*MT.. rows x 16 positions).  The
-// dx sum is done in the epilogue with lane shuffles (a warp owns two image rows of 16 positions).  The optional 1x1
-// shortcut segment accumulates into the centre (dx = 1) column block only.
-// =====================================================================================================================
-constexpr int kDxnTileW = 16;   // positions per image row of a tile (14 outputs + 2 halo)
-constexpr int kDxnOutW = 14;
-
-template <int MT>
-__device__ __forceinline__ Item decode_item_dxn(const ConvParams& p, int item) {
-  Item it;
-  const int per_img = p.tiles_h * p.tiles_w;
-  it.b = item / per_img;
-  const int pix = item - it.b * per_img;
-  const int th = pix / p.tiles_w;
-  it.h0 = th * (8 * MT);
-  it.w0 = (pix - th * p.tiles_w) * kDxnOutW;
-  it.n0 = 0;
-  return it;
-}
-
-template <int COUT, int MT>
-__global__ void __launch_bounds__(kThreads, 1) conv_dxn_kernel(const __grid_constant__ ConvParams p) {
-  constexpr int N3 = 3 * COUT;                 // accumulator columns per m-tile
-  constexpr int AS = 2;
-  static_assert(AS * MT * N3 <= 512, "TMEM budget");
-  constexpr int kTmemCols = 512;
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char* a_buf = smem;
-  unsigned char* b_buf = smem + (size_t)p.a_stages * p.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(b_buf + (size_t)p.b_stages * p.b_stage_bytes);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + kMaxA;
-  uint64_t* b_full = a_empty + kMaxA;
-  uint64_t* acc_full = b_full + kMaxB;
-  uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  EpiTables<COUT>* tabs = reinterpret_cast<EpiTables<COUT>*>(reinterpret_cast<unsigned char*>(tmem_slot) + 16);  // [group][2]
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const bool prof = LASS_PROF_ON(p);
-  long long pc[kProfSlots];
-#pragma unroll
-  for (int i = 0; i < kProfSlots; ++i) pc[i] = 0;
-  const long long t_start = prof ? clock64() : 0;
-
-  if (warp == 0 && lane == 0) {
-    for (int s = 0; s < p.nseg; ++s) {
-      tma_prefetch_desc(&p.seg[s].tmA);
-      tma_prefetch_desc(&p.seg[s].tmB);
-    }
-    for (int s = 0; s < p.a_stages; ++s) {
-      mbar_init(&a_full[s], 1);
-      mbar_init(&a_empty[s], 1);
-    }
-    for (int s = 0; s < p.b_stages; ++s) mbar_init(&b_full[s], 1);
-    for (int s = 0; s < AS; ++s) {
-      mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 4);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // =========================== TMA producer ===========================
-    uint32_t a_it = 0;
-    bool first_item = true;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      const Item it = decode_item_dxn<MT>(p, item);
-      uint32_t b_slot = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const SegDev& sg = p.seg[s];
-        const uint32_t row_bytes = sg.kc * 2;
-        const bool halo = sg.taps == 9;
-        const uint32_t a_bytes = (uint32_t)(8 * MT + (halo ? 2 : 0)) * kDxnTileW * row_bytes;
-        const uint32_t b_bytes = (uint32_t)(halo ? N3 : COUT) * row_bytes;
-        for (int ch = 0; ch < sg.nchunks; ++ch) {
-          const uint32_t sa = a_it % p.a_stages;
-          LASS_TIMED_WAIT(&a_empty[sa], ((a_it / p.a_stages) & 1) ^ 1, kProfProdAEmpty);
-          if (elect_one()) {
-            if (p.debug_flags & 4) {
-              mbar_arrive(&a_full[sa]);
-            } else {
-              mbar_arrive_expect_tx(&a_full[sa], a_bytes);
-              tma_load_4d(a_buf + (size_t)sa * p.a_stage_bytes, &sg.tmA, &a_full[sa], ch * sg.kc, it.w0 - 1,
-                          halo ? it.h0 - 1 : it.h0, it.b);
-            }
-          }
-          __syncwarp();
-          ++a_it;
-          if (first_item) {
-            const int nb = halo ? 3 : 1;   // one weight tile per vertical tap (all three dx folded into its rows)
-            for (int tp = 0; tp < nb; ++tp, ++b_slot) {
-              if (elect_one()) {
-                mbar_arrive_expect_tx(&b_full[b_slot], b_bytes);
-                tma_load_3d(b_buf + (size_t)b_slot * p.b_stage_bytes, &sg.tmB, &b_full[b_slot], ch * sg.kc, 0, tp);
-              }
-              __syncwarp();
-            }
-          }
-        }
-      }
-      first_item = false;
-    }
-    if (prof && lane == 0) {
-      long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
-      dst[kProfProdAEmpty] = pc[kProfProdAEmpty];
-      dst[kProfProdTotal] = clock64() - t_start;
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
-    constexpr uint32_t kLbo = 1u << 16;
-    const uint32_t a_base16 = smem_u32(a_buf) >> 4, a_stage16 = p.a_stage_bytes >> 4;
-    const uint32_t b_base16 = smem_u32(b_buf) >> 4, b_stage16 = p.b_stage_bytes >> 4;
-    const uint32_t n_a = p.a_stages;
-    uint32_t sa = 0, pa = 0, as = 0, pacc = 0;
-    uint32_t n_items = 0;
-    const bool no_mma = (p.debug_flags & 2) != 0;
-    bool first_item = true;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-      LASS_TIMED_WAIT(&acc_empty[as], pacc ^ 1, kProfMmaAccEmpty);
-      tc_fence_after_sync();
-      const uint32_t acc_addr = tmem_base + as * (MT * N3);
-      uint32_t b_slot = 0;
-      uint32_t accumulate = 0;
-#pragma unroll 1
-      for (int s = 0; s < p.nseg; ++s) {
-        const uint32_t kc = p.seg[s].kc;
-        const bool halo = p.seg[s].taps == 9;
-        const uint32_t row16 = kc >> 3;
-        const uint32_t swz = kc == 64 ? kSwizzle128B : kSwizzle64B;
-        SegMma gs;
-        gs.a_hi = static_cast<uint32_t>(make_smem_desc(0, 8 * kc * 2, swz) >> 32);      // dense tile: 8-row groups are contiguous
-        gs.b_hi = gs.a_hi;
-        gs.idesc = make_idesc_f16(p.seg[s].fmt, p.seg[s].fmt, 128, halo ? N3 : COUT);
-        const uint32_t mt_step16 = 8 * kDxnTileW * row16;      // 8 image rows of 16 positions
-        const uint32_t dy_step16 = kDxnTileW * row16;          // one image row
-        const uint32_t acc_col = halo ? 0u : (uint32_t)COUT;   // the 1x1 shortcut feeds the centre (dx = 1) block
-        const uint32_t nchunks = p.seg[s].nchunks;
-#pragma unroll 1
-        for (uint32_t ch = 0; ch < nchunks; ++ch) {
-          LASS_TIMED_WAIT(&a_full[sa], pa, kProfMmaAFull);
-          tc_fence_after_sync();
-          const uint32_t a_lo = (a_base16 + sa * a_stage16) | kLbo;
-          const uint32_t ndy = halo ? 3u : 1u;
-          if (first_item) {
-            for (uint32_t dy = 0; dy < ndy; ++dy) mbar_wait(&b_full[b_slot + dy], 0);
-            tc_fence_after_sync();
-          }
-          if (!no_mma && elect_one()) {
-#pragma unroll 1
-            for (uint32_t dy = 0; dy < ndy; ++dy) {
-              const uint32_t b_lo = (b_base16 + (b_slot + dy) * b_stage16) | kLbo;
-              const uint32_t acc0 = (dy == 0) ? accumulate : 1u;
-              if (kc == 64) issue_tap<MT, N3, 4>(acc_addr + acc_col, a_lo + dy * dy_step16, mt_step16, b_lo, gs, halo ? acc0 : 1u);
-              else issue_tap<MT, N3, 2>(acc_addr + acc_col, a_lo + dy * dy_step16, mt_step16, b_lo, gs, halo ? acc0 : 1u);
-            }
-          }
-          __syncwarp();
-          accumulate = 1;
-          b_slot += ndy;
-          if (elect_one()) umma_commit(&a_empty[sa]);
-          __syncwarp();
-          if (++sa == n_a) {
-            sa = 0;
-            pa ^= 1;
-          }
-        }
-      }
-      if (elect_one()) umma_commit(&acc_full[as]);
-      __syncwarp();
-      if (++as == AS) {
-        as = 0;
-        pacc ^= 1;
-      }
-      first_item = false;
-      ++n_items;
-    }
-    if (prof && lane == 0) {
-      long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
-      dst[kProfMmaAccEmpty] = pc[kProfMmaAccEmpty];
-      dst[kProfMmaAFull] = pc[kProfMmaAFull];
-      dst[kProfMmaTotal] = clock64() - t_start;
-      dst[kProfItems] = n_items;
-    }
-  } else {
-    // =========================== epilogue ===========================
-    const int grp = (warp - 2) >> 2;
-    const int q = warp & 3;
-    const int et = (threadIdx.x - 64) & 127;
-    const int hr = 2 * q + (lane >> 4);              // image row of this lane inside the 8-row m-tile
-    const int wp = lane & 15;                        // position inside the 16-wide tile row; outputs are wp = 1..14
-    const bool col_ok = (wp >= 1) && (wp <= kDxnOutW);
-    const int Hp = p.H >> 1, Wp = p.W >> 1;
-    const bool pooling = (p.pool_raw.ptr != nullptr) || (p.pool_act.ptr != nullptr);
-    const uint32_t as = (uint32_t)grp;
-    EpiTables<COUT>* gtabs = tabs + 2 * grp;
-    uint32_t uses = 0;
-    int tab_b = -1;
-    uint32_t tab_sel = 0;
-    // horizontal pooling partner: outputs (wp = 1, 2), (3, 4), ... form the 2-wide windows (w0 is even)
-    const bool first_w = (wp & 1) != 0;
-    const int partner_w = first_w ? (lane + 1) & 31 : (lane + 31) & 31;
-    for (int item = blockIdx.x + grp * (int)gridDim.x; item < p.num_items; item += 2 * (int)gridDim.x) {
-      const Item it = decode_item_dxn<MT>(p, item);
-      if (it.b != tab_b) {
-        tab_sel ^= 1u;
-        EpiTables<COUT>& t = gtabs[tab_sel];
-        for (int c = et; c < COUT; c += 128) {
-          t.bias[c] = (p.bias ? __ldg(p.bias + c) : 0.0f) + (p.resid_src ? __ldg(p.resid_b + c) : 0.0f);
-          t.resid_w[c] = p.resid_src ? __ldg(p.resid_w + c) : 0.0f;
-          t.sc_full[c] = p.full_act.scale ? __ldg(p.full_act.scale + c) : 0.0f;
-          t.sh_full[c] = p.full_act.scale ? __ldg(p.full_act.shift + (size_t)it.b * p.full_act.shift_bstride + c) : 0.0f;
-          t.sc_pool[c] = p.pool_act.scale ? __ldg(p.pool_act.scale + c) : 0.0f;
-          t.sh_pool[c] = p.pool_act.scale ? __ldg(p.pool_act.shift + (size_t)it.b * p.pool_act.shift_bstride + c) : 0.0f;
-        }
-        if (p.after_w != nullptr && et < 3 * 32) t.after_w[et] = (et % 32 < COUT) ? __ldg(p.after_w + (et / 32) * COUT + et % 32) : 0.0f;
-        if (p.after_w != nullptr && et < 3) t.after_b[et] = __ldg(p.after_b + et);
-        tab_b = it.b;
-        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-        else asm volatile("bar.sync 2, 128;" ::: "memory");
-      }
-      const EpiTables<COUT>& tb = gtabs[tab_sel];
-      const int w = it.w0 + wp - 1;
-      float resid_xs[MT];
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
-        resid_xs[mt] = 0.0f;
-        const int hh = it.h0 + mt * 8 + hr;
-        if (p.resid_src != nullptr && col_ok && hh < p.resid_T && w < p.W)
-          resid_xs[mt] = fmaf(__ldg(p.resid_in_scale + w), __ldg(p.resid_src + ((size_t)it.b * p.resid_T + hh) * p.resid_F + w),
-                              __ldg(p.resid_in_shift + w));
-      }
-      if (q == 0 && lane == 0 && grp == 0) {
-        LASS_TIMED_WAIT(&acc_full[as], uses & 1, kProfEpiAccFull);
-      }
-      __syncwarp();
-      mbar_wait(&acc_full[as], uses & 1);
-      tc_fence_after_sync();
-#pragma unroll 1
-      for (int mt = 0; mt < MT; ++mt) {
-        const int h = it.h0 + mt * 8 + hr;
-        const bool valid = col_ok && (h < p.H) && (w < p.W) && !(p.debug_flags & 16);
-        const uint32_t taddr = tmem_base + as * (MT * N3) + mt * N3 + (static_cast<uint32_t>(q * 32) << 16);
-        const float resid_x = (MT == 2 && mt == 1) ? resid_xs[MT - 1] : resid_xs[0];
-        float fa0 = 0.0f, fa1 = 0.0f, fa2 = 0.0f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < COUT; c0 += 32) {
-          float v[32], t[32];
-          tmem_ld_x32(taddr + COUT + c0, v);         // dx = 1: this position
-          tmem_ld_x32(taddr + c0, t);                // dx = 0: contribution computed at the left neighbour
-          tmem_ld_wait();
-          if (p.debug_flags & 1) continue;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __shfl_up_sync(0xffffffffu, t[j], 1);
-          tmem_ld_x32(taddr + 2 * COUT + c0, t);     // dx = 2: right neighbour
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] += __shfl_down_sync(0xffffffffu, t[j], 1);
-          if (p.resid_src != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaf(tb.resid_w[c0 + j], resid_x, v[j]);
-          }
-          if (p.bias != nullptr || p.resid_src != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += tb.bias[c0 + j];
-          }
-          if (p.full_raw.ptr != nullptr) {
-            uint32_t wv[16];
-            pack_raw32(v, wv);
-            store32(p.full_raw, it.b, h, w, p.H, p.W, c0, wv, valid);
-          }
-          if (p.full_act.ptr != nullptr) {
-            uint32_t wv[16];
-            pack_act32(tb.sc_full + c0, tb.sh_full + c0, v, wv);
-            store32(p.full_act, it.b, h, w, p.H, p.W, c0, wv, valid);
-          }
-          if (p.after_w != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              fa0 = fmaf(tb.after_w[j], v[j], fa0);
-              fa1 = fmaf(tb.after_w[32 + j], v[j], fa1);
-              fa2 = fmaf(tb.after_w[64 + j], v[j], fa2);
-            }
-          }
-          if (pooling) {
-            // 2x2 average pooling, butterfly transpose-reduce: horizontal partner = the other column of the window
-            // (lane +-1), vertical partner = the other image row of this warp (lane ^ 16)
-            float s1[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float send = first_w ? v[16 + j] : v[j];
-              const float mine = first_w ? v[j] : v[16 + j];
-              s1[j] = mine + __shfl_sync(0xffffffffu, send, partner_w);
-            }
-            const bool odd_h = (lane & 16) != 0;
-            float s2[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float send = odd_h ? s1[j] : s1[8 + j];
-              const float mine = odd_h ? s1[8 + j] : s1[j];
-              s2[j] = (mine + __shfl_xor_sync(0xffffffffu, send, 16)) * 0.25f;
-            }
-            const int cb = (first_w ? 0 : 16) + (odd_h ? 8 : 0);
-            if (valid) {
-              const size_t po = (((size_t)it.b * Hp + (h >> 1)) * Wp + (w >> 1));
-              if (p.pool_raw.ptr != nullptr)
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.pool_raw.ptr) + po * p.pool_raw.cstride + p.pool_raw.coff + c0 + cb) =
-                    make_uint4(pack_f16x2_sat(s2[0], s2[1]), pack_f16x2_sat(s2[2], s2[3]), pack_f16x2_sat(s2[4], s2[5]),
-                               pack_f16x2_sat(s2[6], s2[7]));
-              if (p.pool_act.ptr != nullptr) {
-                uint32_t wv[4];
-#pragma unroll
-                for (int j = 0; j < 8; j += 2) {
-                  const float t0 = fmaf(tb.sc_pool[c0 + cb + j], s2[j], tb.sh_pool[c0 + cb + j]);
-                  const float t1 = fmaf(tb.sc_pool[c0 + cb + j + 1], s2[j + 1], tb.sh_pool[c0 + cb + j + 1]);
-                  wv[j / 2] = pack_bf16x2(fmaxf(t0, kSlope * t0), fmaxf(t1, kSlope * t1));
-                }
-                *reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.pool_act.ptr) + po * p.pool_act.cstride + p.pool_act.coff + c0 + cb) =
-                    make_uint4(wv[0], wv[1], wv[2], wv[3]);
-              }
-            }
-          }
-        }
-        if (p.after_w != nullptr && valid) {
-          const size_t plane = (size_t)p.H * p.W;
-          float* fp = p.feat + (size_t)it.b * 3 * plane + (size_t)h * p.W + w;
-          fp[0] = fa0 + tb.after_b[0];
-          fp[plane] = fa1 + tb.after_b[1];
-          fp[2 * plane] = fa2 + tb.after_b[2];
-        }
-      }
-      tc_fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
-      ++uses;
-    }
-    if (prof && q == 0 && lane == 0 && grp == 0) {
-      long long* dst = p.prof + (size_t)blockIdx.x * kProfSlots;
-      dst[kProfEpiAccFull] = pc[kProfEpiAccFull];
-      dst[kProfEpiTotal] = clock64() - t_start;
-    }
-  }
-  tc_fence_before_sync();
-  __syncthreads();
-  if (warp == 1) {
-    __syncwarp();
-    tc_fence_after_sync();
-    tmem_dealloc(tmem_base, kTmemCols);
-  }
-}
-
 typedef void (*ConvKernelFn)(const ConvParams);
 
 struct KernelChoice {
@@ -1564,124 +1193,6 @@ static int check_out(const ConvOut& o, const char* name, int ncols_eff) {
   return 0;
 }
 
-// dx-in-N variant (conv_dxn_kernel): 3x3 conv with Cout in {32, 64}, optional 1x1 shortcut segment, resident weights.
-static int conv_prepare_dxn(const ConvLaunch& l, ConvPrepared** out) {
-  const int cout = l.ncols;
-  if ((cout != 32 && cout != 64) || l.up_h * l.up_w != 1 || l.seg[0].taps != 9 || (l.nseg == 2 && l.seg[1].taps != 1))
-    return set_error(LASS_ERR_ARG, "conv(dxn): needs a 3x3 segment with 32 or 64 output channels (+ optional 1x1 segment)");
-  const bool pooled = l.pool_raw.ptr || l.pool_act.ptr;
-  if (pooled && (l.pool_h != 2 || l.pool_w != 2 || (l.W & 1) || (l.H & 1)))
-    return set_error(LASS_ERR_ARG, "conv(dxn): pooled outputs need 2x2 pooling of an even grid");
-  if (l.after_w && cout != 32) return set_error(LASS_ERR_ARG, "conv(dxn): fused after_conv needs 32 output channels");
-  const int MT = cout == 32 ? 2 : 1;
-  const int N3 = 3 * cout;
-  ConvPrepared* cp = new (std::nothrow) ConvPrepared();
-  if (!cp) return set_error(LASS_ERR_ARG, "conv: out of host memory");
-  ConvParams& p = cp->params;
-  memset(&p, 0, sizeof(p));
-  p.nseg = l.nseg;
-  p.B = l.B;
-  p.H = l.H;
-  p.W = l.W;
-  p.ncols = cout;
-  p.tiles_h = (l.H + 8 * MT - 1) / (8 * MT);
-  p.tiles_w = (l.W + kDxnOutW - 1) / kDxnOutW;
-  p.pix_tiles = l.B * p.tiles_h * p.tiles_w;
-  p.n_tiles = 1;
-  p.num_items = p.pix_tiles;
-  p.bias = l.bias;
-  p.up_h = p.up_w = 1;
-  p.group_c = cout;
-  p.pool_h = l.pool_h;
-  p.pool_w = l.pool_w;
-  p.after_w = l.after_w;
-  p.after_b = l.after_b;
-  p.feat = l.feat;
-  p.resid_src = l.resid_src;
-  p.resid_in_scale = l.resid_in_scale;
-  p.resid_in_shift = l.resid_in_shift;
-  p.resid_w = l.resid_w;
-  p.resid_b = l.resid_b;
-  p.resid_T = l.resid_T;
-  p.resid_F = l.resid_F;
-  p.debug_flags = g_debug_flags;
-  p.prof = g_prof_buffer;
-  fill_out(p.full_raw, l.full_raw);
-  fill_out(p.full_act, l.full_act);
-  fill_out(p.pool_raw, l.pool_raw);
-  fill_out(p.pool_act, l.pool_act);
-  int e;
-  uint32_t a_stage = 0, b_stage = 0;
-  int b_tiles = 0;
-  for (int s = 0; s < l.nseg; ++s) {
-    const ConvSegment& sg = l.seg[s];
-    if (!sg.src || !sg.weights || (sg.kc != 32 && sg.kc != 64) || sg.cin <= 0 || sg.cin % sg.kc || sg.src_cstride % 8 ||
-        sg.src_coff % 8 || sg.src_coff + sg.cin > sg.src_cstride) {
-      delete cp;
-      return set_error(LASS_ERR_ARG, "conv(dxn): bad segment %d", s);
-    }
-    SegDev& d = p.seg[s];
-    d.nchunks = sg.cin / sg.kc;
-    d.taps = sg.taps;
-    d.kc = sg.kc;
-    d.fmt = sg.fp16 ? kFmtF16 : kFmtBF16;
-    const CUtensorMapSwizzle swz = sg.kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
-    const bool halo = sg.taps == 9;
-    const int rows = 8 * MT + (halo ? 2 : 0);
-    {
-      const char* base = reinterpret_cast<const char*>(sg.src) + (size_t)sg.src_coff * 2;
-      uint64_t dims[4] = {(uint64_t)sg.cin, (uint64_t)l.W, (uint64_t)l.H, (uint64_t)l.B};
-      uint64_t strides[3] = {(uint64_t)sg.src_cstride * 2, (uint64_t)sg.src_cstride * 2 * l.W,
-                             (uint64_t)sg.src_cstride * 2 * l.W * l.H};
-      uint32_t box[4] = {(uint32_t)sg.kc, (uint32_t)kDxnTileW, (uint32_t)rows, 1};
-      if ((e = make_tensor_map(&d.tmA, base, 2, 4, dims, strides, box, swz))) {
-        delete cp;
-        return e;
-      }
-    }
-    {
-      // weights: 3x3 segment (3 [dy], 3*cout [dx, co], cin); 1x1 segment (1, cout, cin)
-      const int nrows = halo ? N3 : cout;
-      uint64_t dims[3] = {(uint64_t)sg.cin, (uint64_t)nrows, (uint64_t)(halo ? 3 : 1)};
-      uint64_t strides[2] = {(uint64_t)sg.cin * 2, (uint64_t)sg.cin * 2 * nrows};
-      uint32_t box[3] = {(uint32_t)sg.kc, (uint32_t)nrows, 1};
-      if ((e = make_tensor_map(&d.tmB, sg.weights, 2, 3, dims, strides, box, swz))) {
-        delete cp;
-        return e;
-      }
-      const uint32_t bt = (uint32_t)nrows * sg.kc * 2;
-      if (bt > b_stage) b_stage = bt;
-    }
-    const uint32_t at = (uint32_t)rows * kDxnTileW * sg.kc * 2;
-    if (at > a_stage) a_stage = at;
-    b_tiles += d.nchunks * (halo ? 3 : 1);
-  }
-  p.a_stage_bytes = (a_stage + 1023u) & ~1023u;
-  p.b_stage_bytes = (b_stage + 1023u) & ~1023u;
-  p.b_resident = 1;
-  p.b_stages = b_tiles;
-  const size_t kBudget = 220 * 1024;
-  const size_t fixed = 1024 + (2 * kMaxA + 2 * kMaxB + 8) * 8 + 64 + 4 * ((size_t)6 * cout + 3 * 32 + 4) * sizeof(float) + 64;
-  if (b_tiles > kMaxB || fixed + (size_t)b_tiles * p.b_stage_bytes + 2 * (size_t)p.a_stage_bytes > kBudget) {
-    delete cp;
-    return set_error(LASS_ERR_ARG, "conv(dxn): weights (%d tiles of %u B) do not fit in shared memory", b_tiles, p.b_stage_bytes);
-  }
-  p.a_stages = (int)((kBudget - fixed - (size_t)b_tiles * p.b_stage_bytes) / p.a_stage_bytes);
-  if (p.a_stages > 4) p.a_stages = 4;
-  cp->smem = fixed + (size_t)p.a_stages * p.a_stage_bytes + (size_t)p.b_stages * p.b_stage_bytes;
-  cp->fn = cout == 32 ? conv_dxn_kernel<32, 2> : conv_dxn_kernel<64, 1>;
-  cp->threads = kThreads;
-  const int g_num_sms = device_sm_count();   // of the current device (per-device cache in api.cu)
-  cudaError_t ce = cudaFuncSetAttribute(reinterpret_cast<const void*>(cp->fn), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-  if (ce != cudaSuccess) {
-    delete cp;
-    return set_cuda_error(ce, "conv(dxn) smem attribute");
-  }
-  cp->grid = p.num_items < g_num_sms ? p.num_items : g_num_sms;
-  *out = cp;
-  return 0;
-}
-
 int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   *out = nullptr;
   if (l.B <= 0 || l.H <= 0 || l.W <= 0 || l.ncols <= 0 || l.ncols % 16 || l.nseg < 1 || l.nseg > 2)
@@ -1698,13 +1209,13 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   if (l.resid_src && (!l.resid_in_scale || !l.resid_in_shift || !l.resid_w || !l.resid_b || up > 1 || l.resid_T <= 0 ||
                       l.resid_T > l.H || l.resid_F < l.W))
     return set_error(LASS_ERR_ARG, "conv: bad rank-1 residual spec");
+  if (l.algo != 0) return set_error(LASS_ERR_ARG, "conv: lass_conv_desc.algo is reserved and must be 0");
   int e;
   if ((e = check_out(l.full_raw, "full_raw", l.group_c))) return e;
   if ((e = check_out(l.full_act, "full_act", l.group_c))) return e;
   if ((e = check_out(l.pool_raw, "pool_raw", l.group_c))) return e;
   if ((e = check_out(l.pool_act, "pool_act", l.group_c))) return e;
 
-  if (l.algo == 1) return conv_prepare_dxn(l, out);
   // ---- tile configuration ----
   int BN;
   if (l.ncols <= 32) BN = 32;

@@ -234,14 +234,12 @@ int build_launches(lass_plan* p) {
         l.gen_T = p->T;
         l.gen_F = p->F;
       }
-      l.algo = (p->w.dxn_mask >> (2 * k)) & 1u;
       l.full_act = out_spec(p->a2[k], 0, false, p, 2 * k + 1, 0);
       if ((e = add_conv(p, l))) return e;
     }
     {  // conv2 + shortcut(raw x): block output
       ConvLaunch l = base_launch(p, k, cout);
       l.seg[0] = seg_spec(p->a2[k], cout, 9, false, p->w.enc[k].conv2_w);
-      l.algo = (p->w.dxn_mask >> (2 * k + 1)) & 1u;
       if (k == 0) {
         // encoder_block1 has no shortcut conv and its input is pre_conv(bn0(mag)): the identity residual is regenerated
         // in the epilogue from the 1-channel magnitude (exact fp32), so x_raw[0] is never written or read
@@ -295,7 +293,6 @@ int build_launches(lass_plan* p) {
       ConvLaunch l = base_launch(p, lo, cout);
       l.nseg = 1;
       l.seg[0] = seg_spec(p->cat_act[lo], 2 * cout, 9, false, p->w.dec[j].conv1_w);
-      l.algo = (p->w.dxn_mask >> (14 + 2 * j)) & 1u;
       l.full_act = out_spec(p->a2[lo], 0, false, p, 14 + 3 * j + 2, 0);
       if ((e = add_conv(p, l))) return e;
     }
@@ -303,7 +300,6 @@ int build_launches(lass_plan* p) {
       ConvLaunch l = base_launch(p, lo, cout);
       l.nseg = 2;
       l.seg[0] = seg_spec(p->a2[lo], cout, 9, false, p->w.dec[j].conv2_w);
-      l.algo = (p->w.dxn_mask >> (14 + 2 * j + 1)) & 1u;
       l.seg[1] = seg_spec(p->cat_raw[lo], 2 * cout, 1, true, p->w.dec[j].sc_w);
       l.bias = p->w.dec[j].sc_b;
       if (j < 5) {

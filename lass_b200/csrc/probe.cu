@@ -8,6 +8,7 @@
 // and the 128 x n fp32 accumulator is written to `out`.
 #include "conv_issue.cuh"
 #include "lass_internal.cuh"
+#include "../../include/lass_b200_debug.h"
 #include "ptx.cuh"
 
 namespace lass {

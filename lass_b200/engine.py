@@ -7,7 +7,7 @@
 * runs the forward on the current CUDA stream.  No CPU path: inputs must be CUDA tensors.
 """
 import ctypes
-import os
+import weakref
 
 import torch
 
@@ -17,7 +17,9 @@ _ENC = ("encoder_block1", "encoder_block2", "encoder_block3", "encoder_block4", 
         "conv_block7a")
 _DEC = ("decoder_block1", "decoder_block2", "decoder_block3", "decoder_block4", "decoder_block5", "decoder_block6")
 BN_EPS = 1e-5
-DEFAULT_DXN_MASK = 0   # dx-in-N kernel off: since the dual-issuer tap-in-K kernel it loses on every layer (tools/gpu_layer_times.py)
+# Batches up to this many samples (batch x length) are replayed from a CUDA graph captured per (batch, length): at batch 1 the
+# 36 launches + 4 tensor-map encodes of a forward cost more host time than the kernels take on the GPU.
+GRAPH_MAX_SAMPLES = 4 * 160000
 
 
 def _dev_key(device):
@@ -50,6 +52,7 @@ def film_sites(base):
 class _Plan:
     def __init__(self, handle, workspace, B, L):
         self.handle, self.workspace, self.B, self.L = handle, workspace, B, L
+        self.graph = None             # (torch.cuda.CUDAGraph, static mixture, static condition / shift, static output)
 
     def __del__(self):
         try:
@@ -60,26 +63,48 @@ class _Plan:
 
 
 class Engine:
+    """One engine per (base module, FiLM module or None).  The engine does not keep its modules alive (weak references:
+    ``models.resunet._ENGINES`` is keyed weakly by the base module, so dropping the model frees the packed weights, plans
+    and workspace).  Single-stream use: all plans of an engine share ONE workspace, so forwards of the same engine must be
+    issued on one stream at a time (what the reference's one-thread-per-process callers do)."""
+
     def __init__(self, base, film):
-        self.base = base
-        self.film = film
+        self._base_ref = weakref.ref(base)
+        self._film_ref = weakref.ref(film) if film is not None else None
         self._packed = None
         self._packed_key = None
         self._plans = {}
+        self._tensors = None
         self.stft_precision_mode = 0
-        # 3x3 convs run in the "dx-in-N" formulation (lass_conv_desc.algo = 1): bit 2k+i = encoder block k conv(i+1),
-        # bit 14+2j+i = decoder block j conv(i+1).  Default = the layers where it measured faster on B200
-        # (tools/gpu_dxn_sweep.sh): encoder_block1 conv1, decoder_block5 conv1/conv2, decoder_block6 conv1/conv2.
-        self.dxn_mask = int(os.environ.get("LASS_DXN_MASK", str(DEFAULT_DXN_MASK)), 0)
+        self.use_graphs = True
+
+    @property
+    def base(self):
+        b = self._base_ref()
+        if b is None:
+            raise RuntimeError("the module this engine was built for no longer exists")
+        return b
+
+    @property
+    def film(self):
+        return self._film_ref() if self._film_ref is not None else None
 
     # ------------------------------------------------------------------ packing
+    def invalidate(self):
+        """Forget the cached parameter list (call after REPLACING parameter objects by hand; load_state_dict, .to() and
+        in-place updates are detected without it)."""
+        self._tensors = None
+
     def _version_key(self, device):
-        mods = [self.base] + ([self.film] if self.film is not None else [])
-        key = [_dev_key(device)]
-        for m in mods:
-            for t in list(m.parameters()) + list(m.buffers()):
-                key.append((t.data_ptr(), t._version))
-        return tuple(key)
+        # (data_ptr, version) of every parameter / buffer: in-place updates bump the version, .to() / load_state_dict(assign)
+        # change the pointer.  Walking the module tree costs ~0.8 ms per call, so the tensor list itself is cached and
+        # rebuilt when the module's structure epoch changes (models/resunet.py bumps it in _apply / load_state_dict hooks).
+        base, film = self.base, self.film
+        epoch = (getattr(base, "_lass_epoch", 0), getattr(film, "_lass_epoch", 0) if film is not None else 0)
+        if self._tensors is None or self._tensors[0] != epoch:
+            mods = [base] + ([film] if film is not None else [])
+            self._tensors = (epoch, [t for m in mods for t in list(m.parameters()) + list(m.buffers())])
+        return (_dev_key(device), tuple([(t.data_ptr(), t._version) for t in self._tensors[1]]))
 
     def _pack(self, device):
         base = self.base
@@ -133,13 +158,9 @@ class Engine:
         w.pre_w, w.pre_b = keep["pre"][0].data_ptr(), keep["pre"][1].data_ptr()
         w.film_w, w.film_b, w.act_scale = film_w.data_ptr(), film_b.data_ptr(), act_scale.data_ptr()
 
-        dxn_mask = self.dxn_mask
-
-        def block_weights(cb, cin, cout, bit):
-            pk1 = packing.pack_conv_weight_dxn if (dxn_mask >> bit) & 1 else packing.pack_conv_weight
-            pk2 = packing.pack_conv_weight_dxn if (dxn_mask >> (bit + 1)) & 1 else packing.pack_conv_weight
-            c1 = pk1(dev(cb.conv1.weight), torch.bfloat16)
-            c2 = pk2(dev(cb.conv2.weight), torch.bfloat16)
+        def block_weights(cb, cin, cout):
+            c1 = packing.pack_conv_weight(dev(cb.conv1.weight), torch.bfloat16)
+            c2 = packing.pack_conv_weight(dev(cb.conv2.weight), torch.bfloat16)
             if cb.is_shortcut:
                 sc = packing.pack_conv_weight(dev(cb.shortcut.weight), torch.float16)
                 sb = dev(cb.shortcut.bias)
@@ -150,7 +171,7 @@ class Engine:
 
         for k, name in enumerate(_ENC):
             cb = getattr(base, name).conv_block1
-            c1, c2, sc, sb = block_weights(cb, cb.conv1.in_channels, cb.conv1.out_channels, 2 * k)
+            c1, c2, sc, sb = block_weights(cb, cb.conv1.in_channels, cb.conv1.out_channels)
             keep["enc%d" % k] = (c1, c2, sc, sb)
             w.enc[k].conv1_w, w.enc[k].conv2_w, w.enc[k].sc_w = c1.data_ptr(), c2.data_ptr(), sc.data_ptr()
             w.enc[k].sc_b = sb.data_ptr() if sb is not None else None
@@ -158,14 +179,14 @@ class Engine:
             blk = getattr(base, name)
             up = packing.pack_convT_weight(dev(blk.conv1.weight), torch.bfloat16)
             cb = blk.conv_block2
-            c1, c2, sc, sb = block_weights(cb, cb.conv1.in_channels, cb.conv1.out_channels, 14 + 2 * j)
+            c1, c2, sc, sb = block_weights(cb, cb.conv1.in_channels, cb.conv1.out_channels)
             keep["dec%d" % j] = (up, c1, c2, sc, sb)
             w.dec[j].up_w, w.dec[j].conv1_w, w.dec[j].conv2_w = up.data_ptr(), c1.data_ptr(), c2.data_ptr()
             w.dec[j].sc_w = sc.data_ptr()
             w.dec[j].sc_b = sb.data_ptr() if sb is not None else None
         keep["after"] = (dev(base.after_conv.weight.reshape(3, 32)), dev(base.after_conv.bias))
         w.after_w, w.after_b = keep["after"][0].data_ptr(), keep["after"][1].data_ptr()
-        w.dxn_mask = dxn_mask
+        w.dxn_mask = 0
         keep["struct"] = w
         keep["bn_shift_rows"] = None
         return keep
@@ -177,6 +198,13 @@ class Engine:
             self._packed_key = key
             self._plans = {}          # plans hold pointers into the packed weights
         return self._packed
+
+    def release(self):
+        """Free the packed weights, plans (and their CUDA graphs) and the workspace; the next forward rebuilds them."""
+        self._plans = {}
+        self._packed = None
+        self._packed_key = None
+        self._ws = None
 
     # ------------------------------------------------------------------ plans
     def _get_plan(self, B, L, device):
@@ -208,31 +236,60 @@ class Engine:
     # ------------------------------------------------------------------ forward
     def _check_inputs(self, mixtures):
         if self.base.training:
-            raise NotImplementedError(
-                "lass_b200 implements the eval-mode separation forward; training-mode forward (batch-statistics "
-                "BatchNorm + autograd) is the next tier (SURVEY.md §8f). Call .eval() first.")
+            raise RuntimeError(
+                "the inference engine runs eval-mode BatchNorm; in .train() call the ResUNet30 module itself "
+                "(batch-statistics forward + backward: lass_b200/training.py) or switch to .eval() first")
         if not mixtures.is_cuda:
             raise RuntimeError("lass_b200 has no CPU path: move the module and its inputs to a CUDA device")
         if mixtures.dim() != 3 or mixtures.shape[1] != 1:
             raise ValueError("mixture must be (batch, 1, samples); got %s" % (tuple(mixtures.shape),))
+
+    def _launch(self, plan, x_ptr, cond_ptr, shift_ptr, out_ptr):
+        _cabi.check(_cabi.load().lass_resunet30_forward(plan.handle, x_ptr, cond_ptr, shift_ptr, out_ptr,
+                                                        self.stft_precision_mode, torch.cuda.current_stream().cuda_stream))
+
+    def _run(self, plan, x, cond, shift, device):
+        """One forward over contiguous fp32 CUDA tensors (cond XOR shift); returns a fresh (B, 1, L) tensor."""
+        B, L = plan.B, plan.L
+        aux = cond if cond is not None else shift
+        graphable = (self.use_graphs and B * L <= GRAPH_MAX_SAMPLES and not torch.cuda.is_current_stream_capturing())
+        if not graphable:
+            out = torch.empty(B, 1, L, dtype=torch.float32, device=device)
+            self._launch(plan, x.data_ptr(), cond.data_ptr() if cond is not None else None,
+                         shift.data_ptr() if shift is not None else None, out.data_ptr())
+            return out
+        # small batches: replay the whole forward (36 launches) from a CUDA graph over static buffers
+        g = plan.graph
+        if g is None or g[4] != (cond is not None) or g[2].shape != aux.shape:
+            sx, sa = torch.empty_like(x), torch.empty_like(aux)
+            so = torch.empty(B, 1, L, dtype=torch.float32, device=device)
+            sx.copy_(x)
+            sa.copy_(aux)
+            args = (plan, sx.data_ptr(), sa.data_ptr() if cond is not None else None,
+                    sa.data_ptr() if cond is None else None, so.data_ptr())
+            self._launch(*args)                       # warm-up outside capture (module loading, attribute opt-ins)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                self._launch(*args)
+            g = plan.graph = (graph, sx, sa, so, cond is not None)
+        g[1].copy_(x)
+        g[2].copy_(aux)
+        g[0].replay()
+        return g[3].clone()
 
     @torch.no_grad()
     def forward(self, mixtures, conditions):
         self._check_inputs(mixtures)
         B, _, L = mixtures.shape
         device = mixtures.device
-        plan = self._get_plan(B, L, device)
-        x = mixtures.detach().to(torch.float32).contiguous()
-        c = conditions.detach().to(device=device, dtype=torch.float32).contiguous()
-        if c.shape != (B, self._packed["struct"].condition_size):
-            raise ValueError("condition must be (batch, %d); got %s" % (self._packed["struct"].condition_size,
-                                                                       tuple(c.shape)))
-        out = torch.empty(B, 1, L, dtype=torch.float32, device=device)
-        with torch.cuda.device(device):
-            _cabi.check(_cabi.load().lass_resunet30_forward(plan.handle, x.data_ptr(), c.data_ptr(), None,
-                                                            out.data_ptr(), self.stft_precision_mode,
-                                                            torch.cuda.current_stream().cuda_stream))
-        return out
+        with torch.cuda.device(device):               # plan creation sets per-device kernel attributes; launches go to this device
+            plan = self._get_plan(B, L, device)
+            x = mixtures.detach().to(torch.float32).contiguous()
+            c = conditions.detach().to(device=device, dtype=torch.float32).contiguous()
+            if c.shape != (B, self._packed["struct"].condition_size):
+                raise ValueError("condition must be (batch, %d); got %s" % (self._packed["struct"].condition_size,
+                                                                           tuple(c.shape)))
+            return self._run(plan, x, c, None, device)
 
     @torch.no_grad()
     def forward_film_dict(self, mixtures, film_dict):
@@ -240,8 +297,6 @@ class Engine:
         self._check_inputs(mixtures)
         B, _, L = mixtures.shape
         device = mixtures.device
-        plan = self._get_plan(B, L, device)
-        packed = self._packed
         if self.film is not None:
             raise RuntimeError("engine built with a FiLM module; use forward()")
         betas = []
@@ -251,25 +306,29 @@ class Engine:
         for name in _DEC:
             d = film_dict[name]
             betas += [d["beta1"], d["conv_block2"]["beta1"], d["conv_block2"]["beta2"]]
-        beta = torch.cat([b.reshape(b.shape[0], -1).to(device=device, dtype=torch.float32).expand(B, -1)
-                          for b in betas], dim=1)
-        shift = (beta + packed["film"][1][None, :]).contiguous()      # + folded BN shift
-        x = mixtures.detach().to(torch.float32).contiguous()
-        out = torch.empty(B, 1, L, dtype=torch.float32, device=device)
         with torch.cuda.device(device):
-            _cabi.check(_cabi.load().lass_resunet30_forward(plan.handle, x.data_ptr(), None, shift.data_ptr(),
-                                                            out.data_ptr(), self.stft_precision_mode,
-                                                            torch.cuda.current_stream().cuda_stream))
-        return out
+            plan = self._get_plan(B, L, device)
+            packed = self._packed
+            beta = torch.cat([b.reshape(b.shape[0], -1).to(device=device, dtype=torch.float32).expand(B, -1)
+                              for b in betas], dim=1)
+            shift = (beta + packed["film"][1][None, :]).contiguous()      # + folded BN shift
+            x = mixtures.detach().to(torch.float32).contiguous()
+            return self._run(plan, x, None, shift, device)
 
     @torch.no_grad()
     def forward_stages(self, mixtures, conditions, out, stage_mask):
-        """Run a subset of the stages (bench.py brackets them with CUDA events). Inputs as in forward()."""
+        """Run a subset of the stages (bench.py brackets them with CUDA events). Inputs as in forward(): contiguous fp32
+        CUDA tensors, module in eval mode."""
+        self._check_inputs(mixtures)
+        for t in (mixtures, conditions, out):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.device == mixtures.device):
+                raise ValueError("forward_stages takes contiguous fp32 CUDA tensors on one device")
         B, _, L = mixtures.shape
-        plan = self._get_plan(B, L, mixtures.device)
-        _cabi.check(_cabi.load().lass_resunet30_forward_stages(
-            plan.handle, stage_mask, mixtures.data_ptr(), conditions.data_ptr(), None, out.data_ptr(),
-            self.stft_precision_mode, torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(mixtures.device):
+            plan = self._get_plan(B, L, mixtures.device)
+            _cabi.check(_cabi.load().lass_resunet30_forward_stages(
+                plan.handle, stage_mask, mixtures.data_ptr(), conditions.data_ptr(), None, out.data_ptr(),
+                self.stft_precision_mode, torch.cuda.current_stream().cuda_stream))
 
     def unet_flops(self, B, L, device):
         return _cabi.load().lass_resunet30_unet_flops(self._get_plan(B, L, device).handle)

@@ -30,6 +30,21 @@ _ENGINES = weakref.WeakKeyDictionary()
 _TRAIN_ENGINES = weakref.WeakKeyDictionary()
 
 
+class _EpochMixin:
+    """Bumps ``_lass_epoch`` whenever parameter OBJECTS may have been replaced (``.to()`` / ``.cuda()`` / ``.half()`` through
+    ``_apply``, ``load_state_dict(assign=True)``), so the engine's cached parameter list (``Engine._version_key``) is rebuilt.
+    In-place value changes are detected by the tensors' version counters and need no hook."""
+    _lass_epoch = 0
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._lass_epoch += 1
+        return out
+
+    def _lass_bump_epoch(self, *_args):
+        self._lass_epoch += 1
+
+
 def init_layer(layer):
     """Xavier-uniform weight, zero bias (reference ``models/base.py:9-15``)."""
     nn.init.xavier_uniform_(layer.weight)
@@ -43,7 +58,7 @@ def init_bn(bn):
     bn.weight.data.fill_(1.0)
 
 
-class FiLM(nn.Module):
+class FiLM(_EpochMixin, nn.Module):
     """FiLM generator: one ``nn.Linear(condition_size, C)`` per (block, beta) named
     ``'encoder_block1->conv_block1->beta1'`` ... (reference ``models/resunet.py:10-81``).
 
@@ -55,6 +70,7 @@ class FiLM(nn.Module):
 
     def __init__(self, film_meta, condition_size):
         super().__init__()
+        self.register_load_state_dict_post_hook(lambda module, _keys: module._lass_bump_epoch())
         self.condition_size = condition_size
         self.modules, _ = self.create_film_modules(film_meta=film_meta, ancestor_names=[])
 
@@ -155,11 +171,12 @@ _DECODERS = (  # name, cin, cout, upsample     (reference models/resunet.py:371-
 )
 
 
-class ResUNet30_Base(nn.Module):
+class ResUNet30_Base(_EpochMixin, nn.Module):
     """STFT -> bn0 -> UNet -> mask -> ISTFT (reference ``models/resunet.py:267-595``)."""
 
     def __init__(self, input_channels, output_channels, window_size=1024, hop_size=160):
         super().__init__()
+        self.register_load_state_dict_post_hook(lambda module, _keys: module._lass_bump_epoch())
         # reference models/resunet.py:271-282 hard-codes 1024 / 160; the kernels are parametric (BASELINE config 2
         # uses 2048 / 320), so the sizes are constructor keywords with the reference's values as defaults.
         momentum = 0.01

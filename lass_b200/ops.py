@@ -64,14 +64,15 @@ def mask_istft(feat: torch.Tensor, mag: torch.Tensor, cos: torch.Tensor, sin: to
 
 def umma_probe(A: torch.Tensor, Bm: torch.Tensor, swizzle_mode: int, a_start_bytes: int, a_sbo: int,
                a_base_offset: int, b_sbo: int):
-    lib = _cabi.load()
+    """One tcgen05.mma tile through caller-chosen descriptors (liblass_b200_debug.so; tests only)."""
+    lib = _cabi.load_debug()
     _require_cuda(A, Bm)
     a_rows, kc = A.shape
     n = Bm.shape[0]
     out = torch.zeros(128, n, dtype=torch.float32, device=A.device)
     _cabi.check(lib.lass_debug_umma_probe(_ptr(A), a_rows, _ptr(Bm), n, kc, swizzle_mode, a_start_bytes, a_sbo,
                                           a_base_offset, b_sbo, 1 if A.dtype == torch.float16 else 0, _ptr(out),
-                                          _stream()))
+                                          _stream()), lib)
     return out
 
 

@@ -67,11 +67,3 @@ def pack_convT_weight(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
     GEMM column n = (dy*sw + dx)*Cout + co."""
     cin, cout, sh, sw = w.shape
     return w.permute(2, 3, 1, 0).reshape(1, sh * sw * cout, cin).to(dtype).contiguous()
-
-
-def pack_conv_weight_dxn(w: torch.Tensor, dtype=torch.bfloat16) -> torch.Tensor:
-    """conv2d 3x3 weight (Cout, Cin, 3, 3) -> (3 [ky], 3*Cout [kx, co], Cin): the "dx-in-N" layout of the conv kernel
-    (horizontal taps folded into the GEMM N dimension)."""
-    cout, cin, kh, kw = w.shape
-    assert kh == 3 and kw == 3
-    return w.permute(2, 3, 0, 1).reshape(3, 3 * cout, cin).to(dtype).contiguous()

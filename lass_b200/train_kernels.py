@@ -31,7 +31,12 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+CALLS = 0          # kernel-launching C-ABI calls issued through this module (bench.py reports calls per step)
+
+
 def _chk(code):
+    global CALLS
+    CALLS += 1
     _cabi.check(code)
 
 

@@ -11,8 +11,12 @@ The reference's ``models/resunet.py:6`` imports ``torchlibrosa.stft``; the resta
 import os
 import sys
 
-REFERENCE_ROOT = os.environ.get("LASS_REFERENCE_ROOT", "/root/reference")
 _ORACLE_DIR = os.path.dirname(os.path.abspath(__file__))
+# /root/reference in the build container; on the GPU box the byte-identical copy of the path's files that oracle/build_ref.py
+# put under the git-ignored oracle/_ref (it travels with the snapshot)
+_REF_COPY = os.path.join(_ORACLE_DIR, "_ref")
+REFERENCE_ROOT = os.environ.get("LASS_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isfile("/root/reference/models/resunet.py") else _REF_COPY)
 
 
 def reference_available() -> bool:

@@ -1,5 +1,6 @@
-"""GPU bring-up diagnostics for the tcgen05 implicit-GEMM conv kernel: many small cases against torch fp32
-convolutions on the same 16-bit operands.  Usage: python tools/gpu_conv_probe.py <pitch> [case ...]"""
+"""Case table + runner for the tcgen05 implicit-GEMM conv kernel (K3 / K4): many small cases against torch fp32
+convolutions on the same 16-bit operands (tests/test_gpu_conv.py parametrises over CASES).
+Stand-alone bring-up use: python tests/conv_cases.py <tag> [case ...] -> gpurun_out/conv_probe_p<tag>.json"""
 import json
 import os
 import sys
@@ -40,7 +41,7 @@ def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0,
     nup = up[0] * up[1]
     if taps == 9:
         w = (r(cout, cin, 3, 3) / (3.0 * cin ** 0.5)).to(src_dtype)
-        wp = (packing.pack_conv_weight_dxn if algo == 1 else packing.pack_conv_weight)(w.float(), src_dtype).to(dev)
+        wp = packing.pack_conv_weight(w.float(), src_dtype).to(dev)
         ref = F.conv2d(x, w.float().to(dev), None, padding=1)
     else:
         w = (r(cin, cout, up[0], up[1]) / cin ** 0.5).to(src_dtype)
@@ -173,13 +174,6 @@ CASES = {
     "gen_a": dict(B=3, H=64, W=24, cin=32, cout=32, gen=True, want_raw=False),
     "gen_a_mt1": dict(B=2, H=48, W=12, cin=32, cout=32, gen=True, want_raw=False),
 }
-
-# the same cases through the dx-in-N formulation where it applies (3x3, Cout in {32, 64}, no upsampling, 2x2 pooling)
-for _name in ("c32_32", "c32_32_mt1", "c32_64", "c64_64", "c64_32", "pool32_wide", "resid_pool", "sc_pool", "slice_out", "after",
-              "partial", "fp16src"):
-    CASES["dxn_" + _name] = dict(CASES[_name], algo=1)
-CASES["dxn_c128_64"] = dict(B=1, H=32, W=32, cin=128, cout=64, algo=1)
-CASES["dxn_sc128_64"] = dict(B=2, H=16, W=48, cin=64, cout=64, shortcut_cin=128, bias=True, want_raw=False, algo=1)
 
 # Streamed weights with N >= 128 run as CTA pairs (tcgen05 cta_group::2) when the pixel tiles pair up: longer item
 # sequences per pair, several N tiles, pooled / sliced / transposed outputs -- and the single-CTA streamed path (debug flag 4096)

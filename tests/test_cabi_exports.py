@@ -9,8 +9,8 @@ import pytest
 from lass_b200 import _cabi
 
 
-def _declared(repo_root):
-    text = open(os.path.join(repo_root, "include", "lass_b200.h")).read()
+def _declared(repo_root, header="lass_b200.h"):
+    text = open(os.path.join(repo_root, "include", header)).read()
     return sorted(set(re.findall(r"LASS_API\s+[\w\s\*]+?\b(lass_\w+)\s*\(", text)))
 
 
@@ -27,6 +27,19 @@ def test_header_symbols_are_exported_and_bound(repo_root):
     out = subprocess.check_output(["nm", "-D", "--defined-only", _cabi.LIB_PATH]).decode()
     exported = sorted(set(re.findall(r"\bT (lass_\w+)", out)))
     assert exported == declared, "library exports %s, header declares %s" % (exported, declared)
+
+
+def test_debug_library_is_separate(repo_root):
+    """The probes / microbenchmarks are declared in their own header and exported by their own library only."""
+    declared = _declared(repo_root, "lass_b200_debug.h")
+    assert declared and all(n.startswith("lass_debug_umma_") for n in declared)
+    assert sorted(_cabi.DEBUG_SIGNATURES) == declared
+    lib = _cabi.load_debug()
+    for name in declared:
+        assert hasattr(lib, name)
+        assert name not in _cabi.SIGNATURES
+    out = subprocess.check_output(["nm", "-D", "--defined-only", _cabi.LIB_PATH]).decode()
+    assert "lass_debug_umma_" not in out, "probe code leaked into the product library"
 
 
 def test_version_and_error_calls_work_without_gpu():

@@ -37,10 +37,11 @@ def _probe_mn(A, Bm, a_swz, b_swz, n, ksteps, a_start, a_lbo, a_sbo, a_kstep, b_
     import ctypes
     from lass_b200 import _cabi
     out = torch.zeros(128, n, device="cuda")
-    _cabi.check(_cabi.load().lass_debug_umma_probe_mn(
+    lib = _cabi.load_debug()
+    _cabi.check(lib.lass_debug_umma_probe_mn(
         A.data_ptr(), A.shape[0], a_swz, Bm.data_ptr(), Bm.shape[0], b_swz, n, ksteps, a_start, a_lbo, a_sbo, a_kstep,
         b_start, b_lbo, b_sbo, b_kstep, 1 if A.dtype == torch.float16 else 0, 1 if Bm.dtype == torch.float16 else 0,
-        out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+        out.data_ptr(), torch.cuda.current_stream().cuda_stream), lib)
     torch.cuda.synchronize()
     return out.cpu()
 
@@ -61,15 +62,15 @@ def _expect_mn(A, Bm, n, ksteps, a_start, a_lbo, a_sbo, a_kstep, b_start, b_lbo,
     return D.float()
 
 
+# Both operands share ONE 16-bit format: a descriptor with a_format != b_format (fp16 x bf16) raised cudaErrorIllegalInstruction
+# on B200 and poisons the context, so that case cannot be kept as a test; csrc/wgrad_tc.cu converts fp16 tiles to bf16 instead.
 MN_CASES = [
     # name, dtype A, dtype B, a_swz, b_swz, a_rows, b_rows, n, ksteps, a_start, a_lbo, a_sbo, a_kstep, b_start, b_lbo, b_sbo, b_kstep
     ("sw128 overlapped atoms (2 dx taps x 64 ch), shifted start", torch.bfloat16, torch.bfloat16, 2, 2, 64, 32, 64, 2,
      3 * 128, 128, 10 * 128, 20 * 128, 0, 0, 8 * 128, 16 * 128),
-    ("sw128 mixed fp16 x bf16", torch.float16, torch.bfloat16, 2, 2, 64, 32, 64, 2, 3 * 128, 128, 10 * 128, 20 * 128, 0, 0,
-     8 * 128, 16 * 128),
     ("sw64 four overlapped atoms (4 dx taps x 32 ch)", torch.bfloat16, torch.bfloat16, 4, 4, 64, 32, 32, 2, 5 * 64, 64,
      10 * 64, 20 * 64, 0, 0, 8 * 64, 16 * 64),
-    ("sw64 mixed, N = 64 over two separate atoms", torch.float16, torch.bfloat16, 4, 4, 64, 96, 64, 1, 11 * 64, 64, 10 * 64, 0,
+    ("sw64 fp16, N = 64 over two separate atoms", torch.float16, torch.float16, 4, 4, 64, 96, 64, 1, 11 * 64, 64, 10 * 64, 0,
      0, 32 * 64, 8 * 64, 0),
     ("sw128 atoms in separate regions, N = 128", torch.bfloat16, torch.bfloat16, 2, 2, 128, 128, 128, 1, 0, 64 * 128, 8 * 128,
      0, 0, 64 * 128, 8 * 128, 0),

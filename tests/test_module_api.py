@@ -100,3 +100,36 @@ def test_chunk_inference_stitching_equals_reference_loop(monkeypatch, L):
             ref[:, cur + NL:cur + chunk.shape[1]] = chunk[:, NL:]
     assert out.shape == (1, L) and out.dtype == np.float64
     np.testing.assert_allclose(out, ref, rtol=0, atol=1e-7)
+
+
+def test_engine_does_not_keep_the_module_alive():
+    """The per-module engine registry is weak: dropping the model drops its engine (packed weights, plans, workspace)."""
+    import gc
+    import weakref
+    from lass_b200.models import resunet as R
+    m = ResUNet30(input_channels=1, output_channels=1, condition_size=512)
+    eng = m.base._get_engine(m.film)
+    assert m.base._get_engine(m.film) is eng and eng.base is m.base and eng.film is m.film
+    n_before = len(R._ENGINES)
+    ref_m, ref_e = weakref.ref(m.base), weakref.ref(eng)
+    del m, eng
+    gc.collect()
+    assert ref_m() is None and ref_e() is None and len(R._ENGINES) == n_before - 1
+
+
+def test_engine_parameter_key_tracks_updates_without_walking_the_module(monkeypatch):
+    from lass_b200 import engine as E
+    m = ResUNet30(input_channels=1, output_channels=1, condition_size=512)
+    eng = E.Engine(m.base, m.film)
+    monkeypatch.setattr(E, "_dev_key", lambda device: ("cpu", 0))    # no CUDA here: the device part of the key is not under test
+    k0 = eng._version_key("cpu")
+    assert eng._version_key("cpu") == k0
+    with torch.no_grad():
+        m.base.after_conv.bias.add_(1.0)                # in-place update -> version counter
+    k1 = eng._version_key("cpu")
+    assert k1 != k0
+    m.load_state_dict(m.state_dict())                   # load_state_dict -> epoch hook + versions
+    k2 = eng._version_key("cpu")
+    assert k2 != k1
+    m.double()                                          # _apply -> epoch bump, new storage
+    assert eng._version_key("cpu") != k2

@@ -4,7 +4,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from lass_b200 import _cabi
-lib = _cabi.load()
+lib = _cabi.load_debug()
 out = torch.zeros(148, dtype=torch.int64, device="cuda")
 res = {}
 iters = 512
