@@ -269,7 +269,9 @@ class Engine:
                     sa.data_ptr() if cond is None else None, so.data_ptr())
             self._launch(*args)                       # warm-up outside capture (module loading, attribute opt-ins)
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
+            # (an explicit capture stream on THIS device: torch.cuda.graph's default capture stream is a process-wide
+            #  singleton created on whichever device captured first)
+            with torch.cuda.graph(graph, stream=torch.cuda.Stream(device=device)):
                 self._launch(*args)
             g = plan.graph = (graph, sx, sa, so, cond is not None)
         g[1].copy_(x)

@@ -36,8 +36,9 @@ def calculate_stft_components(waveform: torch.Tensor, n_fft: int, hop_length: in
     if waveform.dim() == 3:
         waveform = waveform.squeeze(1)
     waveform = waveform.float().contiguous()
-    hi, lo = _basis(n_fft, hop_length, waveform.device)
-    return ops.stft_fwd(waveform, hi, lo, n_fft, hop_length, precision_mode=0, magphase_mode=1)
+    with torch.cuda.device(waveform.device):
+        hi, lo = _basis(n_fft, hop_length, waveform.device)
+        return ops.stft_fwd(waveform, hi, lo, n_fft, hop_length, precision_mode=0, magphase_mode=1)
 
 
 def multires_stft(waveform: torch.Tensor, win_lengths: Sequence[int] = (256, 512, 2048), hop_length: int = 160):

@@ -24,6 +24,9 @@ def _require_cuda(*tensors):
             raise RuntimeError("lass_b200 ops need CUDA tensors (no CPU fallback); got device %s" % t.device)
         if not t.is_contiguous():
             raise RuntimeError("lass_b200 ops need contiguous tensors")
+        if t.device.index != torch.cuda.current_device():
+            raise RuntimeError("tensor on %s but the current device is cuda:%d: the kernels launch on the current device's "
+                               "stream -- wrap the call in torch.cuda.device(tensor.device)" % (t.device, torch.cuda.current_device()))
 
 
 def stft_fwd(wave: torch.Tensor, basis_hi: torch.Tensor, basis_lo: torch.Tensor, n_fft: int, hop: int,

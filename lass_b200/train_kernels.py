@@ -44,6 +44,9 @@ def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
             raise RuntimeError("lass_b200 training kernels need CUDA tensors (no CPU fallback); got %s" % t.device)
+        if t is not None and t.device.index != torch.cuda.current_device():
+            raise RuntimeError("tensor on %s but the current device is cuda:%d (TrainEngine sets it; direct callers wrap the "
+                               "call in torch.cuda.device)" % (t.device, torch.cuda.current_device()))
 
 
 def empty(shape, dtype, device):

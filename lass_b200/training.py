@@ -22,11 +22,23 @@ owns (NHWC, raw conv outputs fp16, activated tensors and gradients bf16, statist
 
 All arithmetic is in ``kernels`` (default: ``lass_b200.train_kernels``, the C ABI; no CPU fallback).
 """
-import math
+import contextlib
+import functools
 
 import torch
 
 from .engine import _DEC, _ENC
+
+
+def _on_device(method):
+    """Run a TrainEngine method with the engine's device current: the kernels launch on torch's current stream of the
+    CURRENT device, and kernel attributes / SM counts are per device."""
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        guard = torch.cuda.device(self.device) if self.device.type == "cuda" else contextlib.nullcontext()
+        with guard:
+            return method(self, *args, **kwargs)
+    return wrapper
 
 ENC = ((32, 32, (2, 2)), (32, 64, (2, 2)), (64, 128, (2, 2)), (128, 256, (2, 2)), (256, 384, (2, 2)),
        (384, 384, (1, 2)), (384, 384, (1, 1)))                      # cin, cout, pool   (models/resunet.py:315-370)
@@ -214,6 +226,7 @@ class TrainEngine:
             conv_pair("dec%d.conv2" % j, cb.conv2, k.ACT_DTYPE)
             conv_pair("dec%d.sc" % j, cb.shortcut, k.RAW_DTYPE)
 
+    @_on_device
     def refresh_weights(self):
         """Re-derive the 16-bit kernel layouts from the fp32 parameters (after an optimizer step / load_state_dict)."""
         for name, (param, kind, fwd, dgrad) in self.w.items():
@@ -364,6 +377,7 @@ class TrainEngine:
         bn.num_batches_tracked += 1
         k.bn_act(x, x_coff, out, out_coff, st.C, st.bnp, ws.beta[:, st.row:st.row + st.C])
 
+    @_on_device
     def forward(self, mixture, condition):
         """mixture (B, 1, L), condition (B, K) -> waveform (B, 1, L); keeps everything the backward needs."""
         k = self.k
@@ -442,6 +456,7 @@ class TrainEngine:
         k.conv(cv[conv_pfx + "c1.dgrad"])
         self._bn_bwd(ws, sites[0], g_xact, x_raw, 0, g_sc if has_sc else dy, 0, g_x, 0)
 
+    @_on_device
     def backward(self, dwave, async_allreduce=None):
         """dwave (B, L) or (B, 1, L): gradient of the loss w.r.t. the last forward's waveform.  Fills the flat gradient
         buffer ``self.G`` (every live parameter's gradient is overwritten, not accumulated).  ``async_allreduce`` is called
@@ -483,6 +498,7 @@ class TrainEngine:
             async_allreduce(self.bucket_a_end, self.live_end)
 
     # ------------------------------------------------------------------ fused step (loss + backward + all-reduce + AdamW)
+    @_on_device
     def training_step(self, mixture, condition, target, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                       process_group=None):
         """One optimisation step (reference models/audiosep.py:52-145 + DDP): returns the loss as a 0-d tensor (this rank's
@@ -518,6 +534,7 @@ class TrainEngine:
         self.optimizer_step(lr, betas, eps, weight_decay, grad_scale=1.0 / world)
         return ws.loss_sum[0] / float(ws.B * ws.L)
 
+    @_on_device
     def optimizer_step(self, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, grad_scale=1.0):
         """Fused AdamW(amsgrad=True) over the live slice of the flat buffers, then refresh the 16-bit weight layouts."""
         if self.opt_state is None:

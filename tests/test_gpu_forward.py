@@ -185,3 +185,25 @@ def test_forward_is_cuda_graph_capturable(model_sd):
         graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(out, eager)
+
+
+def test_two_devices_in_one_process():
+    """One process driving two GPUs (SURVEY 8e allows one thread + stream per GPU): kernel attributes, SM counts and plans are
+    per device, and a module on cuda:1 runs while cuda:0 is the current device.  Needs a 2-GPU box (gpurun --gpus 2)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    mix, cond = factory.make_inputs(3, 24000, seed=8)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        model, sd = build_module(device=dev)
+        assert torch.cuda.current_device() == 0
+        outs.append(model({"mixture": mix.to(dev), "condition": cond.to(dev)})["waveform"].cpu())
+    assert torch.equal(outs[0], outs[1])
+    ref = O.resunet30_forward(sd, mix, cond)
+    snr_ok(ref, outs[1], MIN_SNR_DB)
+    # training engine on the non-current device
+    model, sd = build_module(device="cuda:1")
+    model.train()
+    out = model({"mixture": mix.to("cuda:1"), "condition": cond.to("cuda:1")})["waveform"]
+    out.abs().mean().backward()
+    assert model.base.after_conv.weight.grad is not None and bool(torch.isfinite(out).all())

@@ -163,5 +163,5 @@ def test_audiosep_training_step_and_fused_step():
         moved.append((ss.base.after_conv.weight.detach() - w0).clone())
     assert abs(losses[0] - losses[1]) <= 1e-5 * abs(losses[0])
     # first AdamW step: |delta| = lr * 0.001 (constant_warm_up plateau) for every element with a non-negligible gradient
-    assert float(moved[0].abs().max()) == pytest.approx(1e-6, rel=1e-2)
+    assert float(moved[0].abs().max()) == pytest.approx(1e-6, rel=5e-2)          # (quantised by the fp32 ulp of the weights)
     assert float((moved[0] - moved[1]).abs().max()) <= 2e-7
