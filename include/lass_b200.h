@@ -68,6 +68,14 @@ LASS_API size_t lass_stft_workspace_bytes(int B, int L, int n_fft, int hop);
 LASS_API int lass_stft_fwd(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
                   float* mag, float* cos, float* sin, int precision_mode, int magphase_mode, void* workspace,
                   size_t workspace_bytes, void* stream);
+/* The multi-resolution front end (reference scripts/precompute_stfts.py:19-58,573-582: win 256 / 512 / 2048 at hop 160 over the
+ * same waveforms) as ONE stft_gemm launch (+ one padding launch): nres <= 3 resolutions n_ffts[r] with their own basis pair
+ * and (B, T, n_ffts[r]/2 + 1) outputs; the kernel's item list is the concatenation of the resolutions' tiles, longest K first.
+ * workspace >= sum of lass_stft_workspace_bytes(B, L, n_ffts[r], hop), 256-byte aligned.  Other arguments as lass_stft_fwd. */
+LASS_API int lass_stft_multi_fwd(const float* wave, int B, int L, int hop, int nres, const int* n_ffts,
+                                 const void* const* basis_hi, const void* const* basis_lo, float* const* mag, float* const* cos,
+                                 float* const* sin, int precision_mode, int magphase_mode, void* workspace,
+                                 size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------
  * K5  complex mask + inverse STFT  (replaces ResUNet30_Base.feature_maps_to_wav, reference

@@ -203,4 +203,5 @@ SIGNATURES.update({
     "lass_debug_set_istft_v1": (_i, [_i]),
 })
 SIGNATURES["lass_wgrad_tc"] = SIGNATURES["lass_wgrad"]
+SIGNATURES["lass_stft_multi_fwd"] = (_i, [_v, _i, _i, _i, _i, _v, _v, _v, _v, _v, _v, _i, _i, _v, ctypes.c_size_t, _v])
 DEBUG_SIGNATURES["lass_debug_umma_probe_mn"] = (_i, [_v, _i, _i, _v, _i, _i, _i, _i] + [_i] * 10 + [_v, _v])

@@ -35,6 +35,29 @@ int lass_stft_fwd(const float* wave, int B, int L, int n_fft, int hop, const voi
                      precision_mode, magphase_mode, workspace, (cudaStream_t)stream);
 }
 
+int lass_stft_multi_fwd(const float* wave, int B, int L, int hop, int nres, const int* n_ffts, const void* const* basis_hi,
+                        const void* const* basis_lo, float* const* mag, float* const* cos, float* const* sin, int precision_mode,
+                        int magphase_mode, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!wave || !n_ffts || !basis_hi || !basis_lo || !mag || !cos || !sin || !workspace)
+    return set_error(LASS_ERR_ARG, "lass_stft_multi_fwd: null pointer");
+  if (nres < 1 || nres > 3 || B <= 0 || hop <= 0 || hop % 8)
+    return set_error(LASS_ERR_ARG, "lass_stft_multi_fwd: need 1..3 resolutions, hop %% 8 == 0 (got nres=%d hop=%d)", nres, hop);
+  size_t need = 0;
+  for (int r = 0; r < nres; ++r) {
+    const int n_fft = n_ffts[r];
+    if (n_fft < 64 || (n_fft & (n_fft - 1)) || L <= n_fft / 2 || !basis_hi[r] || !mag[r] || !cos[r] || !sin[r] ||
+        (precision_mode == 0 && !basis_lo[r]))
+      return set_error(LASS_ERR_ARG, "lass_stft_multi_fwd: bad resolution %d (n_fft=%d, L=%d)", r, n_fft, L);
+    need += stft_workspace_bytes(B, L, n_fft, hop);
+  }
+  if (workspace_bytes < need) return set_error(LASS_ERR_WORKSPACE, "lass_stft_multi_fwd: workspace %zu < %zu", workspace_bytes, need);
+  if (reinterpret_cast<uintptr_t>(workspace) % 256) return set_error(LASS_ERR_ARG, "lass_stft_multi_fwd: workspace not 256 B aligned");
+  int e = launch_stft_multi(wave, B, L, hop, nres, n_ffts, basis_hi, precision_mode == 0 ? basis_lo : basis_hi, mag, cos, sin,
+                            precision_mode, magphase_mode, workspace, (cudaStream_t)stream, nullptr);
+  if (e == LASS_ERR_ARG) return set_error(e, "lass_stft_multi_fwd: unsupported geometry (n_fft %% 256 == 0 required)");
+  return e;
+}
+
 int lass_mask_istft(const float* feat3, long long feat_bstride, long long feat_cstride, int feat_tstride,
                     int feat_F, const float* mag, const float* cos, const float* sin, const float* window,
                     const float* twiddle, int B, int T, int F, int n_fft, int hop, int L, float* wave_out,

@@ -25,6 +25,9 @@ int make_tensor_map(CUtensorMap* out, const void* base, int elem_bytes, int rank
 int stft_num_ntiles(int n_fft);
 size_t stft_padded_len(int L, int n_fft, int hop);
 size_t stft_workspace_bytes(int B, int L, int n_fft, int hop);
+int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const int* n_ffts, const void* const* basis_hi,
+                      const void* const* basis_lo, float* const* mag, float* const* cosp, float* const* sinp, int precision_mode,
+                      int magphase_mode, void* workspace, cudaStream_t stream, const float* adjoint_window);
 int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
                 float* mag, float* cosp, float* sinp, int precision_mode, int magphase_mode, void* workspace,
                 cudaStream_t stream, const float* adjoint_window = nullptr);

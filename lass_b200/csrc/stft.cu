@@ -41,15 +41,31 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTrPitch = 33;              // epilogue transpose row pitch (floats)
 constexpr int kTrFloats = 32 * kTrPitch;  // per epilogue warp
 
-struct StftParams {
+// One launch serves up to kMaxProblems STFTs of the same batch and hop (the multi-resolution front end of BASELINE config 5:
+// n_fft 2048 / 512 / 256 at hop 160): the item list is the concatenation of the problems' tiles, longest K first.
+constexpr int kMaxProblems = 3;
+struct StftProblem {
   CUtensorMap tmA_hi, tmA_lo, tmB_hi, tmB_lo;
   float* mag;
   float* cosp;
   float* sinp;
-  int T, F, n_fft, split;
-  int magphase_mode;  // 0: Base.spectrogram_phase (clamp(re^2+im^2, 1e-10)**0.5, re/mag); 1: torchlibrosa.magphase
-  int n_tiles, m_tiles, num_items;
+  int F, n_fft, n_tiles, item_end;   // item_end: one past this problem's last item in the launch's item list
 };
+struct StftParams {
+  StftProblem pr[kMaxProblems];
+  int nprob;
+  int T, split;
+  int magphase_mode;  // 0: Base.spectrogram_phase (clamp(re^2+im^2, 1e-10)**0.5, re/mag); 1: torchlibrosa.magphase
+  int m_tiles, num_items;
+};
+
+// item -> (problem, item within the problem)
+__device__ __forceinline__ const StftProblem& find_problem(const StftParams& p, int& item) {
+  int g = 0;
+  while (g + 1 < p.nprob && item >= p.pr[g].item_end) ++g;
+  if (g > 0) item -= p.pr[g - 1].item_end;
+  return p.pr[g];
+}
 
 // magnitude and unit phasor of one bin.  One MUFU.RSQ (2 ulp) instead of sqrt + two divisions: errors of a few 1e-7
 // relative, against the 1e-4 parity bar (tests/test_gpu_spectral.py).
@@ -86,14 +102,15 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int KB = p.n_fft / BK;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&p.tmA_hi);
-    tma_prefetch_desc(&p.tmB_hi);
-    if (p.split) {
-      tma_prefetch_desc(&p.tmA_lo);
-      tma_prefetch_desc(&p.tmB_lo);
+    for (int g = 0; g < p.nprob; ++g) {
+      tma_prefetch_desc(&p.pr[g].tmA_hi);
+      tma_prefetch_desc(&p.pr[g].tmB_hi);
+      if (p.split) {
+        tma_prefetch_desc(&p.pr[g].tmA_lo);
+        tma_prefetch_desc(&p.pr[g].tmB_lo);
+      }
     }
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -118,20 +135,23 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
     if (lane == 0) {
       const uint32_t stage_tx = p.split ? kStageBytes : kATile + kBTile;
       uint32_t it = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
-        const int n_tile = item % p.n_tiles;
-        const int rest = item / p.n_tiles;
+      for (int gitem = blockIdx.x; gitem < p.num_items; gitem += gridDim.x) {
+        int item = gitem;
+        const StftProblem& q = find_problem(p, item);
+        const int KB = q.n_fft / BK;
+        const int n_tile = item % q.n_tiles;
+        const int rest = item / q.n_tiles;
         const int m0 = (rest % p.m_tiles) * BM, b = rest / p.m_tiles;
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
           unsigned char* st = smem + s * kStageBytes;
           mbar_arrive_expect_tx(&full_bar[s], stage_tx);
-          tma_load_3d(st, &p.tmA_hi, &full_bar[s], kb * BK, m0, b);
-          tma_load_2d(st + 2 * kATile, &p.tmB_hi, &full_bar[s], kb * BK, n_tile * BN);
+          tma_load_3d(st, &q.tmA_hi, &full_bar[s], kb * BK, m0, b);
+          tma_load_2d(st + 2 * kATile, &q.tmB_hi, &full_bar[s], kb * BK, n_tile * BN);
           if (p.split) {
-            tma_load_3d(st + kATile, &p.tmA_lo, &full_bar[s], kb * BK, m0, b);
-            tma_load_2d(st + 2 * kATile + kBTile, &p.tmB_lo, &full_bar[s], kb * BK, n_tile * BN);
+            tma_load_3d(st + kATile, &q.tmA_lo, &full_bar[s], kb * BK, m0, b);
+            tma_load_2d(st + 2 * kATile + kBTile, &q.tmB_lo, &full_bar[s], kb * BK, n_tile * BN);
           }
         }
       }
@@ -140,7 +160,9 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(kFmtBF16, kFmtBF16, BM, BN);
       uint32_t it = 0, n = 0;
-      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
+      for (int gitem = blockIdx.x; gitem < p.num_items; gitem += gridDim.x, ++n) {
+        int item = gitem;
+        const int KB = find_problem(p, item).n_fft / BK;
         const uint32_t as = n & 1u;
         mbar_wait(&acc_empty[as], ((n >> 1) & 1u) ^ 1u);
         tc_fence_after_sync();
@@ -172,12 +194,18 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
     const int q = warp & 3;
     const int hsel = (warp - 2) >> 2;
     float* tr = tr_base + (warp - 2) * kTrFloats;
-    const int half = p.n_fft / 2;
     uint32_t n = 0;
-    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x, ++n) {
-      const int n_tile = item % p.n_tiles;
-      const int rest = item / p.n_tiles;
+    for (int gitem = blockIdx.x; gitem < p.num_items; gitem += gridDim.x, ++n) {
+      int item = gitem;
+      const StftProblem& pq = find_problem(p, item);
+      const int half = pq.n_fft / 2;
+      const int n_tile = item % pq.n_tiles;
+      const int rest = item / pq.n_tiles;
       const int m0 = (rest % p.m_tiles) * BM, b = rest / p.m_tiles;
+      float* const g_mag = pq.mag;
+      float* const g_cos = pq.cosp;
+      float* const g_sin = pq.sinp;
+      const int F = pq.F;
       const uint32_t as = n & 1u;
       mbar_wait(&acc_full[as], (n >> 1) & 1u);
       tc_fence_after_sync();
@@ -185,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
       const int t_row0 = m0 + q * 32;                       // first frame of this warp's 32 rows
       const int t_mine = t_row0 + lane;
       const int rows = min(32, p.T - t_row0);               // valid frames among them (<= 0: none)
-      const size_t row0_off = ((size_t)b * p.T + t_row0) * p.F;
+      const size_t row0_off = ((size_t)b * p.T + t_row0) * F;
 #pragma unroll 1
       for (int cc = 0; cc < kBinsPerTile / 2; cc += 32) {
         const int c = hsel * (kBinsPerTile / 2) + cc;
@@ -199,10 +227,10 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
           float m, c1, s1;
           magphase(im[0], 0.0f, p.magphase_mode, m, c1, s1);
           if (t_mine < p.T) {
-            const size_t o = row0_off + (size_t)lane * p.F + half;
-            p.mag[o] = m;
-            if (p.cosp) p.cosp[o] = c1;
-            p.sinp[o] = s1;
+            const size_t o = row0_off + (size_t)lane * F + half;
+            g_mag[o] = m;
+            if (g_cos) g_cos[o] = c1;
+            g_sin[o] = s1;
           }
           im[0] = 0.0f;
         }
@@ -211,15 +239,15 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
         // three transposes through the warp's 32 x 33 buffer: lane = frame  ->  lane = bin, 128 B rows to global memory
 #pragma unroll
         for (int which = 0; which < 3; ++which) {
-          if (which == 1 && !p.cosp) continue;
+          if (which == 1 && !g_cos) continue;
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 32; ++j) tr[lane * kTrPitch + j] = which == 0 ? re[j] : (which == 1 ? cs[j] : im[j]);
           __syncwarp();
-          float* dst = (which == 0 ? p.mag : (which == 1 ? p.cosp : p.sinp)) + row0_off + f0 + lane;
+          float* dst = (which == 0 ? g_mag : (which == 1 ? g_cos : g_sin)) + row0_off + f0 + lane;
 #pragma unroll 8
           for (int r = 0; r < 32; ++r) {
-            if (r < rows) dst[(size_t)r * p.F] = tr[r * kTrPitch + lane];
+            if (r < rows) dst[(size_t)r * F] = tr[r * kTrPitch + lane];
           }
         }
       }
@@ -236,11 +264,17 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
   }
 }
 
-// reflect-pad (center = True, pad_mode = 'reflect') and split to bf16 hi / lo
-__global__ void stft_prep_kernel(const float* __restrict__ wave, __nv_bfloat16* __restrict__ xhi,
-                                 __nv_bfloat16* __restrict__ xlo, int L, int Lp, int half) {
+// reflect-pad (center = True, pad_mode = 'reflect') and split to bf16 hi / lo; grid.z = problem of a multi-resolution launch
+struct PrepParams {
+  __nv_bfloat16* xhi[kMaxProblems];
+  __nv_bfloat16* xlo[kMaxProblems];
+  int Lp[kMaxProblems], half[kMaxProblems];
+};
+__global__ void stft_prep_kernel(const float* __restrict__ wave, const PrepParams pp, int L) {
+  const int g = blockIdx.z;
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int Lp = pp.Lp[g], half = pp.half[g];
   if (i >= Lp) return;
   float v = 0.0f;
   int src = i - half;
@@ -250,8 +284,8 @@ __global__ void stft_prep_kernel(const float* __restrict__ wave, __nv_bfloat16* 
     v = wave[(size_t)b * L + src];
   }
   const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  xhi[(size_t)b * Lp + i] = hi;
-  xlo[(size_t)b * Lp + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  pp.xhi[g][(size_t)b * Lp + i] = hi;
+  pp.xlo[g][(size_t)b * Lp + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
 
 // Adjoint of torchlibrosa ISTFT.forward's overlap-add: the waveform gradient, zero-extended to the frame grid and divided by
@@ -295,54 +329,88 @@ size_t stft_workspace_bytes(int B, int L, int n_fft, int hop) {
   return 2 * (size_t)B * stft_padded_len(L, n_fft, hop) * 2 + 256;
 }
 
-int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
-                float* mag, float* cosp, float* sinp, int precision_mode, int magphase_mode, void* workspace,
-                cudaStream_t stream, const float* adjoint_window) {
-  if (n_fft % BK != 0 || (n_fft / 2) % kBinsPerTile != 0 || hop % 8 != 0 || L <= n_fft / 2) return LASS_ERR_ARG;
+// nres STFTs of the same (B, L) waveform batch at the same hop in ONE stft_gemm launch (+ one prep launch): problems are
+// queued longest-K first so that the persistent CTAs' static round-robin ends on the short items.  workspace: the problems'
+// padded hi / lo arrays back to back (stft_workspace_bytes each, 256 B aligned).
+int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const int* n_ffts, const void* const* basis_hi,
+                      const void* const* basis_lo, float* const* mag, float* const* cosp, float* const* sinp, int precision_mode,
+                      int magphase_mode, void* workspace, cudaStream_t stream, const float* adjoint_window) {
+  if (nres < 1 || nres > kMaxProblems || hop % 8 != 0) return LASS_ERR_ARG;
+  int order[kMaxProblems];
+  for (int g = 0; g < nres; ++g) order[g] = g;
+  for (int a = 0; a < nres; ++a)
+    for (int c = a + 1; c < nres; ++c)
+      if (n_ffts[order[c]] > n_ffts[order[a]]) {
+        const int t = order[a];
+        order[a] = order[c];
+        order[c] = t;
+      }
   const int T = L / hop + 1;
-  const int F = n_fft / 2 + 1;
-  const size_t Lp = stft_padded_len(L, n_fft, hop);
-  __nv_bfloat16* xhi = reinterpret_cast<__nv_bfloat16*>(workspace);
-  __nv_bfloat16* xlo = xhi + (size_t)B * Lp;
-  {
-    dim3 grid((unsigned)((Lp + 255) / 256), (unsigned)B);
-    if (adjoint_window)
-      istft_bwd_prep_kernel<<<grid, 256, 0, stream>>>(wave, adjoint_window, xhi, xlo, L, (int)Lp, n_fft / 2, n_fft, hop, T);
-    else
-      stft_prep_kernel<<<grid, 256, 0, stream>>>(wave, xhi, xlo, L, (int)Lp, n_fft / 2);
-  }
   StftParams p;
-  const int ntn = stft_num_ntiles(n_fft);
-  {
-    // frames: dim0 = sample within frame, dim1 = frame (stride hop: overlapping rows), dim2 = clip
-    uint64_t dims[3] = {(uint64_t)n_fft, (uint64_t)T, (uint64_t)B};
-    uint64_t strides[2] = {(uint64_t)hop * 2, (uint64_t)Lp * 2};
-    uint32_t box[3] = {BK, BM, 1};
-    int e = make_tensor_map(&p.tmA_hi, xhi, 2, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (e) return e;
-    e = make_tensor_map(&p.tmA_lo, xlo, 2, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (e) return e;
+  PrepParams pp;
+  size_t max_lp = 0;
+  unsigned char* ws = reinterpret_cast<unsigned char*>(workspace);
+  int items = 0;
+  for (int g = 0; g < nres; ++g) {
+    const int r = order[g];
+    const int n_fft = n_ffts[r];
+    if (n_fft % BK != 0 || (n_fft / 2) % kBinsPerTile != 0 || L <= n_fft / 2) return LASS_ERR_ARG;
+    const size_t Lp = stft_padded_len(L, n_fft, hop);
+    __nv_bfloat16* xhi = reinterpret_cast<__nv_bfloat16*>(ws);
+    __nv_bfloat16* xlo = xhi + (size_t)B * Lp;
+    ws += stft_workspace_bytes(B, L, n_fft, hop);
+    pp.xhi[g] = xhi;
+    pp.xlo[g] = xlo;
+    pp.Lp[g] = (int)Lp;
+    pp.half[g] = n_fft / 2;
+    if (Lp > max_lp) max_lp = Lp;
+    StftProblem& q = p.pr[g];
+    const int ntn = stft_num_ntiles(n_fft);
+    {
+      // frames: dim0 = sample within frame, dim1 = frame (stride hop: overlapping rows), dim2 = clip
+      uint64_t dims[3] = {(uint64_t)n_fft, (uint64_t)T, (uint64_t)B};
+      uint64_t strides[2] = {(uint64_t)hop * 2, (uint64_t)Lp * 2};
+      uint32_t box[3] = {BK, BM, 1};
+      int e = make_tensor_map(&q.tmA_hi, xhi, 2, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (e) return e;
+      e = make_tensor_map(&q.tmA_lo, xlo, 2, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (e) return e;
+    }
+    {
+      uint64_t dims[2] = {(uint64_t)n_fft, (uint64_t)ntn * BN};
+      uint64_t strides[1] = {(uint64_t)n_fft * 2};
+      uint32_t box[2] = {BK, BN};
+      int e = make_tensor_map(&q.tmB_hi, basis_hi[r], 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (e) return e;
+      e = make_tensor_map(&q.tmB_lo, basis_lo[r] ? basis_lo[r] : basis_hi[r], 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+      if (e) return e;
+    }
+    q.mag = mag[r];
+    q.cosp = cosp ? cosp[r] : nullptr;
+    q.sinp = sinp[r];
+    q.F = n_fft / 2 + 1;
+    q.n_fft = n_fft;
+    q.n_tiles = ntn;
+    items += ntn * ((T + BM - 1) / BM) * B;
+    q.item_end = items;
   }
+  for (int g = nres; g < kMaxProblems; ++g) p.pr[g] = p.pr[0];
   {
-    uint64_t dims[2] = {(uint64_t)n_fft, (uint64_t)ntn * BN};
-    uint64_t strides[1] = {(uint64_t)n_fft * 2};
-    uint32_t box[2] = {BK, BN};
-    int e = make_tensor_map(&p.tmB_hi, basis_hi, 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (e) return e;
-    e = make_tensor_map(&p.tmB_lo, basis_lo, 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
-    if (e) return e;
+    dim3 grid((unsigned)((max_lp + 255) / 256), (unsigned)B, (unsigned)nres);
+    if (adjoint_window) {
+      if (nres != 1) return LASS_ERR_ARG;
+      istft_bwd_prep_kernel<<<dim3(grid.x, grid.y), 256, 0, stream>>>(wave, adjoint_window, pp.xhi[0], pp.xlo[0], L, pp.Lp[0], pp.half[0],
+                                                                     n_ffts[0], hop, T);
+    } else {
+      stft_prep_kernel<<<grid, 256, 0, stream>>>(wave, pp, L);
+    }
   }
-  p.mag = mag;
-  p.cosp = cosp;
-  p.sinp = sinp;
+  p.nprob = nres;
   p.T = T;
-  p.F = F;
-  p.n_fft = n_fft;
   p.split = precision_mode == 0 ? 1 : 0;
   p.magphase_mode = magphase_mode;
-  p.n_tiles = ntn;
   p.m_tiles = (T + BM - 1) / BM;
-  p.num_items = ntn * p.m_tiles * B;
+  p.num_items = items;
   const size_t smem = (size_t)kStages * kStageBytes + kEpiWarps * kTrFloats * sizeof(float) + 1024 + 256;
   // the opt-in is per device and cheap: set it on every launch for the CURRENT device (no process-wide cache)
   cudaError_t ea = cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -351,6 +419,18 @@ int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void*
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
   stft_gemm_kernel<<<grid, kThreads, smem, stream>>>(p);
   return set_cuda_error(cudaGetLastError(), "stft launch");
+}
+
+int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,
+                float* mag, float* cosp, float* sinp, int precision_mode, int magphase_mode, void* workspace,
+                cudaStream_t stream, const float* adjoint_window) {
+  const void* bh[1] = {basis_hi};
+  const void* bl[1] = {basis_lo};
+  float* m[1] = {mag};
+  float* c[1] = {cosp};
+  float* sn[1] = {sinp};
+  return launch_stft_multi(wave, B, L, hop, 1, &n_fft, bh, bl, m, c, sn, precision_mode, magphase_mode, workspace, stream,
+                           adjoint_window);
 }
 
 }  // namespace lass

@@ -41,6 +41,28 @@ __device__ __forceinline__ V8 load8(const void* base, size_t elem_off, int fp16)
   return r;
 }
 
+__device__ __forceinline__ uint4 loadq(const void* base, size_t elem_off) {
+  return __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(base) + elem_off));
+}
+// 8 packed 16-bit values -> fp32 (kept packed in 4 registers until they are used: the elementwise kernels hold several
+// loads in flight per thread and must stay under 85 registers for two 384-thread CTAs per SM)
+__device__ __forceinline__ V8 unpack8(const uint4& q, int fp16) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  V8 r;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (fp16) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      r.v[2 * i] = f.x;
+      r.v[2 * i + 1] = f.y;
+    } else {
+      r.v[2 * i] = __uint_as_float(w[i] << 16);
+      r.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  return r;
+}
+
 __device__ __forceinline__ void store8(void* base, size_t elem_off, int fp16, const V8& r) {
   uint32_t w[4];
 #pragma unroll
@@ -79,7 +101,7 @@ __device__ __forceinline__ void block_reduce_rows(float (&acc)[NACC][8], int CV,
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(const void* __restrict__ x, int fp16, long long npix, int C, int cstride,
+__global__ void __launch_bounds__(kRedThreads, 2) bn_stats_kernel(const void* __restrict__ x, int fp16, long long npix, int C, int cstride,
                                                                int coff, double* __restrict__ sums) {
   extern __shared__ float red[];
   const int CV = C / 8, R = kRedThreads / CV;
@@ -87,13 +109,22 @@ __global__ void __launch_bounds__(kRedThreads) bn_stats_kernel(const void* __res
   float acc[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.0f;
-  for (long long p = (long long)blockIdx.x * R + prow; p < npix; p += (long long)gridDim.x * R) {
-    const V8 v = load8(x, (size_t)p * cstride + coff + cv * 8, fp16);
+  const long long stride = (long long)gridDim.x * R;
+  for (long long p = (long long)blockIdx.x * R + prow; p < npix; p += 4 * stride) {
+    uint4 raw[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      acc[0][i] += v.v[i];
-      acc[1][i] = fmaf(v.v[i], v.v[i], acc[1][i]);
-    }
+    for (int u = 0; u < 4; ++u)                 // four independent 16-byte loads in flight per thread
+      if (p + u * stride < npix) raw[u] = loadq(x, (size_t)(p + u * stride) * cstride + coff + cv * 8);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (p + u * stride < npix) {
+        const V8 v = unpack8(raw[u], fp16);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          acc[0][i] += v.v[i];
+          acc[1][i] = fmaf(v.v[i], v.v[i], acc[1][i]);
+        }
+      }
   }
   block_reduce_rows<2>(acc, CV, R, cv, prow, red);
   const int width = C * 2;
@@ -139,29 +170,49 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
   running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
 }
 
-__global__ void __launch_bounds__(256) bn_act_kernel(const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
-                                                     void* __restrict__ out, int out_fp16, int out_cstride, int out_coff,
-                                                     long long pix_per_clip, long long nvec, int C, const float* __restrict__ bnp,
-                                                     const float* __restrict__ beta, int beta_bstride) {
-  const int CV = C / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / CV;
-    const int c = (int)(i - p * CV) * 8;
-    const int b = (int)(p / pix_per_clip);
-    const V8 v = load8(x, (size_t)p * x_cstride + x_coff + c, x_fp16);
-    const V8 sc = ldf8(bnp + c), sh = ldf8(bnp + C + c), be = ldf8(beta + (size_t)b * beta_bstride + c);
-    V8 r;
+// Elementwise kernels: block = 384 threads = R pixels x CV channel vectors, grid.y = clip.  A thread keeps ITS channel vector for
+// the whole launch, so the per-channel tables live in registers; it walks pixels with a stride of gridDim.x * R and has kU
+// independent 16-byte loads per operand in flight (no 64-bit index divisions, no table reloads).
+__global__ void __launch_bounds__(kRedThreads, 2) bn_act_kernel(const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
+                                                             void* __restrict__ out, int out_fp16, int out_cstride, int out_coff,
+                                                             long long pix_per_clip, int C, const float* __restrict__ bnp,
+                                                             const float* __restrict__ beta, int beta_bstride) {
+  constexpr int kU = 4;
+  const int CV = C / 8, R = kRedThreads / CV;
+  const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
+  if (prow >= R) return;
+  const int b = blockIdx.y, c = cv * 8;
+  const V8 sc = ldf8(bnp + c);
+  V8 sh = ldf8(bnp + C + c);
+  {
+    const V8 be = ldf8(beta + (size_t)b * beta_bstride + c);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float pre = fmaf(sc.v[k], v.v[k], sh.v[k]) + be.v[k];
-      r.v[k] = pre > 0.0f ? pre : kSlope * pre;
-    }
-    store8(out, (size_t)p * out_cstride + out_coff + c, out_fp16, r);
+    for (int k = 0; k < 8; ++k) sh.v[k] += be.v[k];
+  }
+  const size_t p0 = (size_t)b * pix_per_clip;
+  const long long stride = (long long)gridDim.x * R;
+  for (long long q = (long long)blockIdx.x * R + prow; q < pix_per_clip; q += kU * stride) {
+    uint4 raw[kU];
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (q + u * stride < pix_per_clip) raw[u] = loadq(x, (p0 + q + u * stride) * x_cstride + x_coff + c);
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (q + u * stride < pix_per_clip) {
+        const V8 v = unpack8(raw[u], x_fp16);
+        V8 r;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float pre = fmaf(sc.v[k], v.v[k], sh.v[k]);
+          r.v[k] = pre > 0.0f ? pre : kSlope * pre;
+        }
+        store8(out, (p0 + q + u * stride) * out_cstride + out_coff + c, out_fp16, r);
+      }
   }
 }
 
 // sums (B, C, 2): [sum g', sum g' (x - mean)] per clip; grid.y = clip
-__global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
+__global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_reduce_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
                                                                     const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
                                                                     long long pix_per_clip, int C, const float* __restrict__ bnp,
                                                                     const float* __restrict__ beta, int beta_bstride,
@@ -170,21 +221,38 @@ __global__ void __launch_bounds__(kRedThreads) bn_bwd_reduce_kernel(const void* 
   const int CV = C / 8, R = kRedThreads / CV;
   const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
   const int b = blockIdx.y, c = cv * 8;
-  const V8 sc = ldf8(bnp + c), sh = ldf8(bnp + C + c), mean = ldf8(bnp + 2 * C + c), be = ldf8(beta + (size_t)b * beta_bstride + c);
+  const V8 sc = ldf8(bnp + c), mean = ldf8(bnp + 2 * C + c);
+  V8 sh = ldf8(bnp + C + c);
+  {
+    const V8 be = ldf8(beta + (size_t)b * beta_bstride + c);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sh.v[i] += be.v[i];
+  }
   float acc[2][8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[0][i] = acc[1][i] = 0.0f;
-  for (long long q = (long long)blockIdx.x * R + prow; q < pix_per_clip; q += (long long)gridDim.x * R) {
-    const size_t p = (size_t)b * pix_per_clip + q;
-    const V8 xv = load8(x, p * x_cstride + x_coff + c, x_fp16);
-    const V8 dv = load8(dact, p * d_cstride + d_coff + c, 0);
+  const long long stride = (long long)gridDim.x * R;
+  for (long long q = (long long)blockIdx.x * R + prow; q < pix_per_clip; q += 2 * stride) {
+    uint4 xq[2], dq[2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float pre = fmaf(sc.v[i], xv.v[i], sh.v[i]) + be.v[i];
-      const float g = pre > 0.0f ? dv.v[i] : kSlope * dv.v[i];
-      acc[0][i] += g;
-      acc[1][i] = fmaf(g, xv.v[i] - mean.v[i], acc[1][i]);
-    }
+    for (int u = 0; u < 2; ++u)
+      if (q + u * stride < pix_per_clip) {
+        const size_t p = (size_t)b * pix_per_clip + q + u * stride;
+        xq[u] = loadq(x, p * x_cstride + x_coff + c);
+        dq[u] = loadq(dact, p * d_cstride + d_coff + c);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (q + u * stride < pix_per_clip) {
+        const V8 xv = unpack8(xq[u], x_fp16), dv = unpack8(dq[u], 0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float pre = fmaf(sc.v[i], xv.v[i], sh.v[i]);
+          const float g = pre > 0.0f ? dv.v[i] : kSlope * dv.v[i];
+          acc[0][i] += g;
+          acc[1][i] = fmaf(g, xv.v[i] - mean.v[i], acc[1][i]);
+        }
+      }
   }
   block_reduce_rows<2>(acc, CV, R, cv, prow, red);
   const int width = C * 2;
@@ -215,34 +283,57 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int B, in
   bnp[5 * C + c] = (float)(-scale * t1 / count);
 }
 
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
-                                                           const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
-                                                           const void* __restrict__ add, int add_cstride, int add_coff,
-                                                           void* __restrict__ dx, int dx_cstride, int dx_coff, long long pix_per_clip,
-                                                           long long nvec, int C, const float* __restrict__ bnp,
-                                                           const float* __restrict__ beta, int beta_bstride) {
-  const int CV = C / 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const long long p = i / CV;
-    const int c = (int)(i - p * CV) * 8;
-    const int b = (int)(p / pix_per_clip);
-    const V8 xv = load8(x, (size_t)p * x_cstride + x_coff + c, x_fp16);
-    const V8 dv = load8(dact, (size_t)p * d_cstride + d_coff + c, 0);
-    const V8 sc = ldf8(bnp + c), sh = ldf8(bnp + C + c), mean = ldf8(bnp + 2 * C + c), ca = ldf8(bnp + 4 * C + c),
-             cb = ldf8(bnp + 5 * C + c), be = ldf8(beta + (size_t)b * beta_bstride + c);
-    V8 r;
+__global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_apply_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
+                                                                   const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
+                                                                   const void* __restrict__ add, int add_cstride, int add_coff,
+                                                                   void* __restrict__ dx, int dx_cstride, int dx_coff, long long pix_per_clip,
+                                                                   int C, const float* __restrict__ bnp, const float* __restrict__ beta,
+                                                                   int beta_bstride) {
+  constexpr int kU = 2;
+  const int CV = C / 8, R = kRedThreads / CV;
+  const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
+  if (prow >= R) return;
+  const int b = blockIdx.y, c = cv * 8;
+  const V8 sc = ldf8(bnp + c), ca = ldf8(bnp + 4 * C + c);
+  V8 sh = ldf8(bnp + C + c), cb = ldf8(bnp + 5 * C + c);
+  {
+    const V8 mean = ldf8(bnp + 2 * C + c), be = ldf8(beta + (size_t)b * beta_bstride + c);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float pre = fmaf(sc.v[k], xv.v[k], sh.v[k]) + be.v[k];
-      const float g = pre > 0.0f ? dv.v[k] : kSlope * dv.v[k];
-      r.v[k] = fmaf(sc.v[k], g, fmaf(ca.v[k], xv.v[k] - mean.v[k], cb.v[k]));
+      cb.v[k] = fmaf(-ca.v[k], mean.v[k], cb.v[k]);      // coefA (x - mean) + coefB = coefA x + (coefB - coefA mean)
+      sh.v[k] += be.v[k];
     }
-    if (add) {
-      const V8 av = load8(add, (size_t)p * add_cstride + add_coff + c, 0);
+  }
+  const size_t p0 = (size_t)b * pix_per_clip;
+  const long long stride = (long long)gridDim.x * R;
+  for (long long q = (long long)blockIdx.x * R + prow; q < pix_per_clip; q += kU * stride) {
+    uint4 xq[kU], dq[kU], aq[kU];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) r.v[k] += av.v[k];
-    }
-    store8(dx, (size_t)p * dx_cstride + dx_coff + c, 0, r);
+    for (int u = 0; u < kU; ++u)
+      if (q + u * stride < pix_per_clip) {
+        const size_t p = p0 + q + u * stride;
+        xq[u] = loadq(x, p * x_cstride + x_coff + c);
+        dq[u] = loadq(dact, p * d_cstride + d_coff + c);
+        if (add) aq[u] = loadq(add, p * add_cstride + add_coff + c);
+      }
+#pragma unroll
+    for (int u = 0; u < kU; ++u)
+      if (q + u * stride < pix_per_clip) {
+        const V8 xv = unpack8(xq[u], x_fp16), dv = unpack8(dq[u], 0);
+        V8 r;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float pre = fmaf(sc.v[k], xv.v[k], sh.v[k]);
+          const float g = pre > 0.0f ? dv.v[k] : kSlope * dv.v[k];
+          r.v[k] = fmaf(sc.v[k], g, fmaf(ca.v[k], xv.v[k], cb.v[k]));
+        }
+        if (add) {
+          const V8 av = unpack8(aq[u], 0);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) r.v[k] += av.v[k];
+        }
+        store8(dx, (p0 + q + u * stride) * dx_cstride + dx_coff + c, 0, r);
+      }
   }
 }
 
@@ -687,9 +778,10 @@ int lass_bn_act(const void* x, int x_fp16, int x_cstride, int x_coff, void* out,
                 long long pix_per_clip, int C, const float* bnp, const float* beta, int beta_bstride, void* stream_v) {
   if (!x || !out || !bnp || !beta || B <= 0 || pix_per_clip <= 0 || !chan_ok(C, x_cstride, x_coff) || !chan_ok(C, out_cstride, out_coff) || beta_bstride % 4)
     return set_error(LASS_ERR_ARG, "lass_bn_act: bad argument");
-  const long long nvec = (long long)B * pix_per_clip * (C / 8);
-  bn_act_kernel<<<grid_for(nvec, 256), 256, 0, (cudaStream_t)stream_v>>>(x, x_fp16, x_cstride, x_coff, out, out_fp16, out_cstride, out_coff,
-                                                                         pix_per_clip, nvec, C, bnp, beta, beta_bstride);
+  const int R = kRedThreads / (C / 8);
+  dim3 grid((unsigned)grid_for(pix_per_clip, R * 4, (148 * 8 + B - 1) / B), (unsigned)B);
+  bn_act_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream_v>>>(x, x_fp16, x_cstride, x_coff, out, out_fp16, out_cstride, out_coff,
+                                                                  pix_per_clip, C, bnp, beta, beta_bstride);
   LASS_LAUNCH_CHECK("bn_act launch");
 }
 
@@ -720,10 +812,11 @@ int lass_bn_bwd_apply(const void* dact, int d_cstride, int d_coff, const void* x
   if (!dact || !x || !dx || !bnp || !beta || B <= 0 || pix_per_clip <= 0 || !chan_ok(C, x_cstride, x_coff) || !chan_ok(C, d_cstride, d_coff) ||
       !chan_ok(C, dx_cstride, dx_coff) || (add && !chan_ok(C, add_cstride, add_coff)) || beta_bstride % 4)
     return set_error(LASS_ERR_ARG, "lass_bn_bwd_apply: bad argument");
-  const long long nvec = (long long)B * pix_per_clip * (C / 8);
-  bn_bwd_apply_kernel<<<grid_for(nvec, 256), 256, 0, (cudaStream_t)stream_v>>>(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff, add,
-                                                                               add_cstride, add_coff, dx, dx_cstride, dx_coff, pix_per_clip,
-                                                                               nvec, C, bnp, beta, beta_bstride);
+  const int R = kRedThreads / (C / 8);
+  dim3 grid((unsigned)grid_for(pix_per_clip, R * 2, (148 * 8 + B - 1) / B), (unsigned)B);
+  bn_bwd_apply_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream_v>>>(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff, add, add_cstride,
+                                                                        add_coff, dx, dx_cstride, dx_coff, pix_per_clip, C, bnp, beta,
+                                                                        beta_bstride);
   LASS_LAUNCH_CHECK("bn_bwd_apply launch");
 }
 

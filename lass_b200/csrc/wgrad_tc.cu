@@ -8,13 +8,14 @@
 // the X halo tile (18 x 10 pixels of CIW channels) lies in shared memory one pixel per row, so the tile shifted by one pixel is
 // the same memory one row further — an MN-major descriptor whose leading byte offset (distance between swizzle atoms along M)
 // is ONE ROW reads [dx = 0 | dx = 1 (| dx = 2 | dx = 3)] as one 128-row operand: 2 taps x 64 channels (SWIZZLE_128B) or
-// 4 taps x 32 channels (SWIZZLE_64B; the 4th "tap" is discarded).  The vertical tap is a start-address shift of 10 rows and
+// 4 taps x 32 channels (SWIZZLE_64B; the 4th "tap" is discarded).  With 64-channel chunks the atom distance is also used ACROSS
+// kernel rows (taps (ky, 2) and (ky + 1, 0) are 8 halo rows apart), so the nine taps need five MMAs per k-step, not six.  The vertical tap is a start-address shift of 10 rows and
 // the 8-pixel rows of the 16 x 8 pixel tile are the descriptor's 8-row K groups with a stride of 10 rows — the descriptor
 // rules are pinned on hardware by tests/test_gpu_umma_probe.py::test_mn_major_descriptors.  So a 32-channel layer still
 // issues full M = 128 MMAs, and no operand is ever transposed or copied.
 //
 // One CTA = one (CIW-channel chunk of ci, NB-channel tile of co) output tile over a contiguous range of pixel tiles
-// (split-K; few weights + many pixels -> many ranges): all 3 x 3 taps accumulate in TMEM (3 ky x G dx-groups x NB columns),
+// (split-K; few weights + many pixels -> many ranges): all 3 x 3 taps accumulate in TMEM (5 or 3 accumulators of NB columns),
 // then the epilogue adds the valid rows to dW with fp32 red.global.  Warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.
 #include "lass_internal.cuh"
 #include "ptx.cuh"
@@ -41,9 +42,13 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   constexpr int XBYTES = kHaloH * kHaloW * RA, YBYTES = kTH * kTW * RB;
   constexpr int XALLOC = (XBYTES + 1023) & ~1023;
   constexpr int STAGE = XALLOC + YBYTES;
-  constexpr int TPM = 128 / CIW;                                 // horizontal taps per MMA (2 or 4)
-  constexpr int G = CIW == 64 ? 2 : 1;                           // MMAs (dx groups) per kernel row
-  constexpr int ACC_COLS = 3 * G * NB;
+  constexpr int TPM = 128 / CIW;                                 // taps per MMA (2 or 4)
+  // MMA groups of a 3x3 kernel.  The nine taps sit at halo-row offsets {0,1,2, 10,11,12, 20,21,22}; an MMA's M atoms are LBO
+  // bytes apart, so   CIW = 32: one MMA per kernel row = taps (ky,0..2) + one discarded atom (LBO = 1 row);
+  //                   CIW = 64: FIVE MMAs (0,1) (2,10) (11,12) (20,21) (22,-): the pair (2,10) spans two kernel rows with
+  //                             LBO = 8 rows -- 5 instead of 6 MMAs per k-step.  Accumulator a, atom h holds tap TPM a + h.
+  constexpr int NACC = CIW == 64 ? 5 : 3;
+  constexpr int ACC_COLS = NACC * NB;
   constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
 
@@ -63,7 +68,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   const int t_begin = (int)((long long)p.num_pix_tiles * split / p.splits);
   const int t_end = (int)((long long)p.num_pix_tiles * (split + 1) / p.splits);
   const bool one_tap = p.taps == 1;
-  const int nky = one_tap ? 1 : 3, ng = one_tap ? 1 : G;
+  const int nacc = one_tap ? 1 : NACC;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmX);
@@ -109,17 +114,22 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         mbar_wait(p.x_fp16 ? &conv_bar[s] : &full_bar[s], (it / kStages) & 1);
         tc_fence_after_sync();
         const uint32_t xs = smem_u32(smem + s * STAGE), ys = xs + XALLOC;
-        for (int ky = 0; ky < nky; ++ky) {
-          const int kyr = one_tap ? 1 : ky;
-          for (int g = 0; g < ng; ++g) {
-            const int dx0 = one_tap ? 1 : g * TPM;
-            const uint32_t acc = tmem_base + (uint32_t)((ky * G + g) * NB);
+        for (int a = 0; a < nacc; ++a) {
+          int row0, lbo_rows = 1;                  // halo row of the first atom, atom distance in rows
+          if (one_tap) {
+            row0 = kHaloW + 1;                     // the centre tap (the second atom is discarded)
+          } else if (CIW == 64) {
+            row0 = a == 0 ? 0 : a == 1 ? 2 : a == 2 ? kHaloW + 1 : a == 3 ? 2 * kHaloW : 2 * kHaloW + 2;
+            if (a == 1) lbo_rows = kHaloW - 2;
+          } else {
+            row0 = a * kHaloW;
+          }
+          const uint32_t acc = tmem_base + (uint32_t)(a * NB);
 #pragma unroll
-            for (int ks = 0; ks < kTH / 2; ++ks) {
-              const uint64_t da = make_smem_desc_mn(xs + (uint32_t)(((2 * ks + kyr) * kHaloW + dx0) * RA), RA, kHaloW * RA, SWA);
-              const uint64_t db = make_smem_desc_mn(ys + (uint32_t)(ks * 2 * kTW * RB), 0, kTW * RB, SWB);
-              umma_f16(acc, da, db, idesc, (it | (uint32_t)ks) != 0u);
-            }
+          for (int ks = 0; ks < kTH / 2; ++ks) {
+            const uint64_t da = make_smem_desc_mn(xs + (uint32_t)((2 * ks * kHaloW + row0) * RA), lbo_rows * RA, kHaloW * RA, SWA);
+            const uint64_t db = make_smem_desc_mn(ys + (uint32_t)(ks * 2 * kTW * RB), 0, kTW * RB, SWB);
+            umma_f16(acc, da, db, idesc, (it | (uint32_t)ks) != 0u);
           }
         }
         umma_commit(&empty_bar[s]);
@@ -158,27 +168,25 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     tc_fence_after_sync();
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int a = row / CIW, cl = row % CIW;
+    const int h = row / CIW, cl = row % CIW;       // atom of the MMA's M dimension, channel within the chunk
     const int ci = ci_chunk * CIW + cl;
     if (t_begin < t_end) {
-      for (int ky = 0; ky < nky; ++ky)
-        for (int g = 0; g < ng; ++g) {
-          const int dx = one_tap ? (a == 0 ? 1 : 3) : g * TPM + a;
-          const bool valid = dx <= 2;
-          const int tap = one_tap ? 0 : ky * 3 + dx;
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)((ky * G + g) * NB);
+      for (int a = 0; a < nacc; ++a) {
+        // tap held by (accumulator a, atom h); CIW = 32: kernel row a, dx = h (h = 3 is the discarded atom)
+        const int tap = one_tap ? (h == 0 ? 0 : 9) : (CIW == 64 ? TPM * a + h : (h < 3 ? 3 * a + h : 9));
+        const bool valid = tap < p.taps;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(a * NB);
 #pragma unroll 1
-          for (int c0 = 0; c0 < NB; c0 += 32) {
-            float v[32];
-            tmem_ld_x32(taddr + c0, v);
-            tmem_ld_wait();
-            if (valid) {
-              float* dst = p.dw + ((size_t)tap * p.co + co_tile * NB + c0) * p.ci + ci;
+        for (int c0 = 0; c0 < NB; c0 += 32) {
+          if (!valid) continue;                    // (warp-uniform: a warp's 32 lanes lie in one atom)
+          float v[32];
+          tmem_ld_x32(taddr + c0, v);
+          tmem_ld_wait();
+          float* dst = p.dw + ((size_t)tap * p.co + co_tile * NB + c0) * p.ci + ci;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)j * p.ci, v[j]);
-            }
-          }
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + (size_t)j * p.ci, v[j]);
         }
+      }
     }
   }
   tc_fence_before_sync();

@@ -42,5 +42,17 @@ def calculate_stft_components(waveform: torch.Tensor, n_fft: int, hop_length: in
 
 
 def multires_stft(waveform: torch.Tensor, win_lengths: Sequence[int] = (256, 512, 2048), hop_length: int = 160):
-    """{win_length: (mag, cos, sin)} for the reference's three resolutions (``config/audiosep_base.yaml:17-21``)."""
-    return {int(w): calculate_stft_components(waveform, int(w), hop_length) for w in win_lengths}
+    """{win_length: (mag, cos, sin)} for the reference's three resolutions (``config/audiosep_base.yaml:17-21``) from one
+    kernel launch (up to three resolutions per launch; longer lists are processed three at a time)."""
+    if waveform.dim() == 3:
+        waveform = waveform.squeeze(1)
+    waveform = waveform.float().contiguous()
+    wins = [int(w) for w in win_lengths]
+    out = {}
+    with torch.cuda.device(waveform.device):
+        for i in range(0, len(wins), 3):
+            group = wins[i:i + 3]
+            bases = [_basis(w, hop_length, waveform.device) for w in group]
+            res = ops.stft_multi_fwd(waveform, bases, group, hop_length, precision_mode=0, magphase_mode=1)
+            out.update(dict(zip(group, res)))
+    return out

@@ -48,6 +48,29 @@ def stft_fwd(wave: torch.Tensor, basis_hi: torch.Tensor, basis_lo: torch.Tensor,
     return out[0], out[1], out[2]
 
 
+def stft_multi_fwd(wave: torch.Tensor, bases, n_ffts, hop: int, precision_mode: int = 0, workspace: torch.Tensor = None,
+                   magphase_mode: int = 0):
+    """Several STFT resolutions of the same waveforms in ONE kernel launch (lass_stft_multi_fwd): wave (B, L) fp32,
+    bases = [(hi, lo)] per resolution, n_ffts = [n_fft] -> [(mag, cos, sin)] each (B, 1, T, n_fft/2 + 1) fp32."""
+    lib = _cabi.load()
+    n = len(n_ffts)
+    assert wave.dtype == torch.float32 and wave.dim() == 2 and len(bases) == n and 1 <= n <= 3
+    _require_cuda(wave, *[t for pair in bases for t in pair])
+    B, L = wave.shape
+    T = L // hop + 1
+    need = sum(lib.lass_stft_workspace_bytes(B, L, int(f), hop) for f in n_ffts)
+    if workspace is None or workspace.numel() * workspace.element_size() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=wave.device)
+    outs = [torch.empty(3, B, 1, T, int(f) // 2 + 1, dtype=torch.float32, device=wave.device) for f in n_ffts]
+    arr_i = (ctypes.c_int * n)(*[int(f) for f in n_ffts])
+    ptrs = lambda vals: (ctypes.c_void_p * n)(*vals)
+    _cabi.check(lib.lass_stft_multi_fwd(_ptr(wave), B, L, hop, n, arr_i, ptrs([_ptr(b[0]) for b in bases]),
+                                        ptrs([_ptr(b[1]) for b in bases]), ptrs([_ptr(o[0]) for o in outs]),
+                                        ptrs([_ptr(o[1]) for o in outs]), ptrs([_ptr(o[2]) for o in outs]), precision_mode,
+                                        magphase_mode, _ptr(workspace), workspace.numel() * workspace.element_size(), _stream()))
+    return [(o[0], o[1], o[2]) for o in outs]
+
+
 def mask_istft(feat: torch.Tensor, mag: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, window: torch.Tensor,
                twiddle: torch.Tensor, n_fft: int, hop: int, length: int, feat_F: int = None):
     """feat (B, 3, Tf, Ff) fp32 (Tf >= T rows, first ``feat_F`` bins valid) + mixture mag/cos/sin (B, 1, T, F)

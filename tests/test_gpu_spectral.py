@@ -80,9 +80,10 @@ def test_mask_istft_matches_oracle(n_fft, hop):
         assert torch.equal(out, out2)
 
 
-@pytest.mark.parametrize("n_fft,hop", [(1024, 160), (2048, 320)])
+@pytest.mark.parametrize("n_fft,hop", [(1024, 160), (2048, 320), (512, 160)])
 def test_full_size_round_trip_property(n_fft, hop):
-    """BASELINE config 2 at full size (64 x 10 s): STFT -> identity mask -> iSTFT reproduces the input, and the
+    """BASELINE config 2 at full size (64 x 10 s; 512 / 160 is config 5's ISTFT, resunet_with_multistft.py:38-46): STFT ->
+    identity mask -> iSTFT reproduces the input, and the
     transform is linear (size-independent properties; the oracle would take minutes at this size)."""
     from lass_b200 import ops
     sd, hi, lo, window, tw = _setup(n_fft, hop)

@@ -14,7 +14,7 @@ if has bench; then
   python bench.py --steps 10 --warmup 3 > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err || { echo bench failed; tail -5 gpurun_out/bench_$TAG.err; exit 1; }
   python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${TAG}_reference.json 2>> gpurun_out/bench_$TAG.err
 fi
-CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-spectral"
+CMD="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-spectral --no-extras"
 if has list; then
   $CMD > gpurun_out/bench_short.json 2>&1 || { echo "short bench failed"; exit 1; }
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none \
