@@ -123,6 +123,18 @@ class Engine:
         keep["basis"] = (hi, lo)
         win, tw = packing.istft_tables(base.window_size, device=device)
         keep["istft"] = (win, tw)
+        # K5 computes the inverse DFT with an FFT and this analytic Hann window instead of multiplying by the module's frozen
+        # istft.conv_real / conv_imag matrices; a checkpoint whose matrices are NOT the analytic ones (another window, a
+        # trained ISTFT) must not be separated silently with the wrong synthesis -- compare a few rows and fail loudly
+        n = base.window_size
+        rows = torch.tensor([0, 1, n // 4 + 3, n // 2, n - 1], device=device)
+        ang = 2.0 * torch.pi * (rows.double()[:, None] * torch.arange(n, device=device, dtype=torch.float64)[None, :] % n) / n
+        want_re = (torch.cos(ang) * win.double()[None, :] / n).float()        # (bins x in rows, samples y)
+        got = dev(base.istft.conv_real.weight)[:, :, 0][:, rows].t()          # weight[y, x, 0] = cos(2 pi x y / n) / n * w[y]
+        if float((got - want_re).abs().max()) > 64e-6 / n or \
+                float((dev(base.istft.ola_window) - win * win).abs().max()) > 1e-6:
+            raise ValueError("istft.conv_real / ola_window differ from the analytic periodic-Hann inverse DFT that kernel K5 "
+                             "implements (reference torchlibrosa ISTFT); this checkpoint cannot run on the fused iSTFT")
         s0, b0 = fold_bn(base.bn0)
         keep["bn0"] = (dev(s0), dev(b0))
         keep["pre"] = (dev(base.pre_conv.weight.reshape(-1)), dev(base.pre_conv.bias))
@@ -345,6 +357,13 @@ class Engine:
         if n < 0:
             _cabi.check(n)
         return [(ms[i], fl[i]) for i in range(n)]
+
+    def raw_stream_peak(self, B, L, device):
+        """Largest |value| in the saturating-fp16 raw residual / skip tensors of the LAST forward with this (B, L) (run it with
+        ``use_graphs = False``).  Values approaching 65504 mean a checkpoint's activations do not fit the fp16 raw stream
+        (DESIGN §2; tests/test_gpu_forward.py::test_raw_stream_fp16_headroom): the output would clip silently."""
+        names = ["x_raw%d" % k for k in range(1, 7)] + ["cat_raw%d" % k for k in range(6)]
+        return max(float(self.debug_buffer(B, L, device, n).float().abs().max()) for n in names)
 
     def num_launches(self, B, L, device):
         return _cabi.load().lass_resunet30_num_launches(self._get_plan(B, L, device).handle)

@@ -156,7 +156,7 @@ def test_raw_stream_fp16_headroom():
     eng = model.base._get_engine(model.film)
     eng.use_graphs = False
     model({"mixture": mix.cuda(), "condition": cond.cuda()})
-    peak = max(float(eng.debug_buffer(3, 16000, "cuda", "x_raw%d" % k).float().abs().max()) for k in range(1, 4))
+    peak = eng.raw_stream_peak(3, 16000, "cuda")
     print("largest |x_raw| = %.0f" % peak)
     assert 2e3 <= peak < 3e4
     snr_ok(ref, out, MIN_SNR_DB)
@@ -207,3 +207,13 @@ def test_two_devices_in_one_process():
     out = model({"mixture": mix.to("cuda:1"), "condition": cond.to("cuda:1")})["waveform"]
     out.abs().mean().backward()
     assert model.base.after_conv.weight.grad is not None and bool(torch.isfinite(out).all())
+
+
+def test_non_analytic_istft_weights_are_rejected():
+    """K5 implements the analytic periodic-Hann inverse DFT; a module whose frozen istft matrices differ must fail loudly."""
+    model, sd = build_module(device="cuda")
+    with torch.no_grad():
+        model.base.istft.conv_real.weight.mul_(1.01)
+    mix, cond = factory.make_inputs(1, 16000, edge_clips=False)
+    with pytest.raises(ValueError, match="analytic"):
+        model({"mixture": mix.cuda(), "condition": cond.cuda()})
