@@ -203,6 +203,13 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* d
 
 // cta_group::2 loads: executed by BOTH CTAs of a pair, each into its own shared memory; the transaction bytes are
 // counted on the mbarrier given as a shared::cluster address (the leader CTA's barrier)
+__device__ __forceinline__ void tma_load_2d_cg2(void* smem_dst, const CUtensorMap* desc, uint32_t bar_cluster_addr,
+                                                int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_3d_cg2(void* smem_dst, const CUtensorMap* desc, uint32_t bar_cluster_addr,
                                                 int32_t c0, int32_t c1, int32_t c2) {
   asm volatile(
@@ -322,6 +329,20 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ".reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// CTA pair (cta_group::2): M = 256 = 128 rows from each CTA's shared memory at these offsets, each CTA holds half of the N rows
+// of B; issued by ONE thread of the leader CTA.
+__device__ __forceinline__ void umma_f16_cg2(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(tmem_d),
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");

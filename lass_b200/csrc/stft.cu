@@ -32,10 +32,18 @@ constexpr int BM = 128;   // frames per tile
 constexpr int BN = 256;   // 128 bins x (re, im)
 constexpr int BK = 64;    // samples per pipeline stage (128 B rows, SWIZZLE_128B)
 constexpr int kBinsPerTile = BN / 2;
-constexpr int kStages = 2;
 constexpr int kATile = BM * BK * 2;       // 16 KiB
-constexpr int kBTile = BN * BK * 2;       // 32 KiB
-constexpr int kStageBytes = 2 * kATile + 2 * kBTile;   // A hi | A lo | B hi | B lo = 96 KiB
+// Single CTA: stage = A hi | A lo | B hi | B lo = 96 KiB, two stages.  CTA pair (cta_group::2, M = 256 = two neighbouring frame
+// tiles): each CTA holds HALF of the basis tile (128 of the 256 rows), stage = 64 KiB, three stages.  The kernel is bound by the
+// L2 -> shared-memory rate (~43 B/clk per SM chip-wide, /opt/skills/guides/B300_MICROARCH.md "LTS throughput cap"): an item
+// moves 1.5 MiB per SM alone, 1.0 MiB per SM in a pair, against 24.6 k cycles of MMA.
+template <bool CG2>
+struct StageCfg {
+  static constexpr int kStages = CG2 ? 3 : 2;
+  static constexpr int kBRows = CG2 ? BN / 2 : BN;
+  static constexpr int kBTile = kBRows * BK * 2;
+  static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;
+};
 constexpr int kEpiWarps = 8;              // two per TMEM lane quarter, each takes half of the tile's bins
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTrPitch = 33;              // epilogue transpose row pitch (floats)
@@ -89,7 +97,16 @@ __device__ __forceinline__ void magphase(float re, float im, int mode, float& m,
 // Persistent CTAs over (clip, 128-frame tile, 128-bin tile) items, bin tile fastest so that the CTAs running
 // concurrently share the frame tile in L2.  Warp 0 TMA producer, warp 1 TMEM alloc + MMA issue (two 256-column
 // accumulator stages: the epilogue of item i overlaps the MMAs of item i + 1), warps 2..9 epilogue.
+// CG2: thread-block cluster of 2; an item is a PAIR of frame tiles (p.m_tiles counts pairs), the leader CTA (rank 0) issues
+// every MMA for both (M = 256: rows 0-127 from its shared memory into its TMEM, rows 128-255 from / into the peer's), both CTAs
+// load their own frames and their half of the basis rows (transaction bytes counted on the leader's barrier), tcgen05.commit
+// multicasts the stage-free / accumulator-full arrivals to both, the peer's epilogue warps arrive remotely on the leader's
+// acc_empty.
+template <bool CG2>
 __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_constant__ StftParams p) {
+  constexpr int kStages = StageCfg<CG2>::kStages;
+  constexpr int kBTile = StageCfg<CG2>::kBTile;
+  constexpr int kStageBytes = StageCfg<CG2>::kStageBytes;
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B tiles need 1024 B alignment
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -102,6 +119,9 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
+  const int vbid = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int vgrid = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < p.nprob; ++g) {
@@ -118,13 +138,19 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kEpiWarps);
+      mbar_init(&acc_empty[s], kEpiWarps * (CG2 ? 2 : 1));     // pair: the epilogue warps of both CTAs arrive on the leader's
     }
     fence_mbar_init();
   }
+  if (CG2) cluster_sync_all();      // both CTAs' barriers exist before any remote arrive / transaction lands on them
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BN);
-    tmem_relinquish();
+    if (CG2) {
+      tmem_alloc_cg2(tmem_slot, 2 * BN);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, 2 * BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before_sync();
   __syncthreads();
@@ -133,34 +159,46 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t stage_tx = p.split ? kStageBytes : kATile + kBTile;
+      const uint32_t stage_tx = (p.split ? kStageBytes : kATile + kBTile) * (CG2 ? 2u : 1u);
       uint32_t it = 0;
-      for (int gitem = blockIdx.x; gitem < p.num_items; gitem += gridDim.x) {
+      for (int gitem = vbid; gitem < p.num_items; gitem += vgrid) {
         int item = gitem;
         const StftProblem& q = find_problem(p, item);
         const int KB = q.n_fft / BK;
         const int n_tile = item % q.n_tiles;
         const int rest = item / q.n_tiles;
-        const int m0 = (rest % p.m_tiles) * BM, b = rest / p.m_tiles;
+        const int m0 = ((rest % p.m_tiles) * (CG2 ? 2 : 1) + (int)crank) * BM, b = rest / p.m_tiles;
+        const int brow = n_tile * BN + (int)crank * (BN / 2);          // pair: this CTA's half of the basis rows
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % kStages;
           mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
           unsigned char* st = smem + s * kStageBytes;
-          mbar_arrive_expect_tx(&full_bar[s], stage_tx);
-          tma_load_3d(st, &q.tmA_hi, &full_bar[s], kb * BK, m0, b);
-          tma_load_2d(st + 2 * kATile, &q.tmB_hi, &full_bar[s], kb * BK, n_tile * BN);
-          if (p.split) {
-            tma_load_3d(st + kATile, &q.tmA_lo, &full_bar[s], kb * BK, m0, b);
-            tma_load_2d(st + 2 * kATile + kBTile, &q.tmB_lo, &full_bar[s], kb * BK, n_tile * BN);
+          if (CG2) {
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+            const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
+            tma_load_3d_cg2(st, &q.tmA_hi, bar, kb * BK, m0, b);
+            tma_load_2d_cg2(st + 2 * kATile, &q.tmB_hi, bar, kb * BK, brow);
+            if (p.split) {
+              tma_load_3d_cg2(st + kATile, &q.tmA_lo, bar, kb * BK, m0, b);
+              tma_load_2d_cg2(st + 2 * kATile + kBTile, &q.tmB_lo, bar, kb * BK, brow);
+            }
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+            tma_load_3d(st, &q.tmA_hi, &full_bar[s], kb * BK, m0, b);
+            tma_load_2d(st + 2 * kATile, &q.tmB_hi, &full_bar[s], kb * BK, brow);
+            if (p.split) {
+              tma_load_3d(st + kATile, &q.tmA_lo, &full_bar[s], kb * BK, m0, b);
+              tma_load_2d(st + 2 * kATile + kBTile, &q.tmB_lo, &full_bar[s], kb * BK, brow);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(kFmtBF16, kFmtBF16, BM, BN);
+    if (lane == 0 && crank == 0) {
+      const uint32_t idesc = make_idesc_f16(kFmtBF16, kFmtBF16, CG2 ? 2 * BM : BM, BN);
       uint32_t it = 0, n = 0;
-      for (int gitem = blockIdx.x; gitem < p.num_items; gitem += gridDim.x, ++n) {
+      for (int gitem = vbid; gitem < p.num_items; gitem += vgrid, ++n) {
         int item = gitem;
         const int KB = find_problem(p, item).n_fft / BK;
         const uint32_t as = n & 1u;
@@ -176,17 +214,27 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
           for (int ks = 0; ks < BK / 16; ++ks) {
             const uint64_t a_hi = make_smem_desc(st + ks * 32, 1024, kSwizzle128B);
             const uint64_t b_hi = make_smem_desc(st + 2 * kATile + ks * 32, 1024, kSwizzle128B);
-            umma_f16(tmem_acc, a_hi, b_hi, idesc, (kb | ks) != 0);
+            if (CG2) umma_f16_cg2(tmem_acc, a_hi, b_hi, idesc, (kb | ks) != 0);
+            else umma_f16(tmem_acc, a_hi, b_hi, idesc, (kb | ks) != 0);
             if (p.split) {
               const uint64_t a_lo = make_smem_desc(st + kATile + ks * 32, 1024, kSwizzle128B);
               const uint64_t b_lo = make_smem_desc(st + 2 * kATile + kBTile + ks * 32, 1024, kSwizzle128B);
-              umma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
-              umma_f16(tmem_acc, a_lo, b_hi, idesc, 1);
+              if (CG2) {
+                umma_f16_cg2(tmem_acc, a_hi, b_lo, idesc, 1);
+                umma_f16_cg2(tmem_acc, a_lo, b_hi, idesc, 1);
+              } else {
+                umma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
+                umma_f16(tmem_acc, a_lo, b_hi, idesc, 1);
+              }
             }
           }
-          umma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
+          if (CG2) umma_commit_cg2(&empty_bar[s]);
+          else umma_commit(&empty_bar[s]);
         }
-        umma_commit(&acc_full[as]);    // accumulator complete
+        // accumulator complete (published in both CTAs of a pair)
+        if (CG2) umma_commit_cg2(&acc_full[as]);
+        else umma_commit(&acc_full[as]);
       }
     }
   } else {
@@ -195,13 +243,13 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
     const int hsel = (warp - 2) >> 2;
     float* tr = tr_base + (warp - 2) * kTrFloats;
     uint32_t n = 0;
-    for (int gitem = blockIdx.x; gitem < p.num_items; gitem += gridDim.x, ++n) {
+    for (int gitem = vbid; gitem < p.num_items; gitem += vgrid, ++n) {
       int item = gitem;
       const StftProblem& pq = find_problem(p, item);
       const int half = pq.n_fft / 2;
       const int n_tile = item % pq.n_tiles;
       const int rest = item / pq.n_tiles;
-      const int m0 = (rest % p.m_tiles) * BM, b = rest / p.m_tiles;
+      const int m0 = ((rest % p.m_tiles) * (CG2 ? 2 : 1) + (int)crank) * BM, b = rest / p.m_tiles;
       float* const g_mag = pq.mag;
       float* const g_cos = pq.cosp;
       float* const g_sin = pq.sinp;
@@ -253,14 +301,19 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
       }
       tc_fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      if (lane == 0) {
+        if (CG2 && crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[as]), 0));    // the leader's barrier
+        else mbar_arrive(&acc_empty[as]);
+      }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
+  if (CG2) cluster_sync_all();      // neither CTA leaves while the other may still touch its shared memory / barriers / TMEM
   if (warp == 1) {
     tc_fence_after_sync();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if (CG2) tmem_dealloc_cg2(tmem_base, 2 * BN);
+    else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
@@ -346,6 +399,9 @@ int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const 
         order[c] = t;
       }
   const int T = L / hop + 1;
+  const int m_tiles = (T + BM - 1) / BM;
+  const bool pairs = m_tiles >= 2;                                   // CTA pairs over two neighbouring frame tiles
+  const int m_units = pairs ? (m_tiles + 1) / 2 : m_tiles;           // (an odd last tile pairs with an all-padding tile)
   StftParams p;
   PrepParams pp;
   size_t max_lp = 0;
@@ -379,7 +435,7 @@ int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const 
     {
       uint64_t dims[2] = {(uint64_t)n_fft, (uint64_t)ntn * BN};
       uint64_t strides[1] = {(uint64_t)n_fft * 2};
-      uint32_t box[2] = {BK, BN};
+      uint32_t box[2] = {BK, (uint32_t)(pairs ? BN / 2 : BN)};
       int e = make_tensor_map(&q.tmB_hi, basis_hi[r], 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (e) return e;
       e = make_tensor_map(&q.tmB_lo, basis_lo[r] ? basis_lo[r] : basis_hi[r], 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -391,7 +447,7 @@ int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const 
     q.F = n_fft / 2 + 1;
     q.n_fft = n_fft;
     q.n_tiles = ntn;
-    items += ntn * ((T + BM - 1) / BM) * B;
+    items += ntn * m_units * B;
     q.item_end = items;
   }
   for (int g = nres; g < kMaxProblems; ++g) p.pr[g] = p.pr[0];
@@ -409,15 +465,34 @@ int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const 
   p.T = T;
   p.split = precision_mode == 0 ? 1 : 0;
   p.magphase_mode = magphase_mode;
-  p.m_tiles = (T + BM - 1) / BM;
+  p.m_tiles = m_units;
   p.num_items = items;
-  const size_t smem = (size_t)kStages * kStageBytes + kEpiWarps * kTrFloats * sizeof(float) + 1024 + 256;
-  // the opt-in is per device and cheap: set it on every launch for the CURRENT device (no process-wide cache)
-  cudaError_t ea = cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (ea != cudaSuccess) return set_cuda_error(ea, "stft smem attribute");
   const int num_sms = device_sm_count();
+  if (pairs) {
+    const size_t smem = (size_t)StageCfg<true>::kStages * StageCfg<true>::kStageBytes + kEpiWarps * kTrFloats * sizeof(float) + 1024 + 256;
+    // the opt-in is per device and cheap: set it on every launch for the CURRENT device (no process-wide cache)
+    cudaError_t ea = cudaFuncSetAttribute(stft_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (ea != cudaSuccess) return set_cuda_error(ea, "stft smem attribute");
+    const int npairs = num_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (unsigned)(items < npairs ? items : npairs), 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return set_cuda_error(cudaLaunchKernelEx(&cfg, stft_gemm_kernel<true>, p), "stft launch (CTA pairs)");
+  }
+  const size_t smem = (size_t)StageCfg<false>::kStages * StageCfg<false>::kStageBytes + kEpiWarps * kTrFloats * sizeof(float) + 1024 + 256;
+  cudaError_t ea = cudaFuncSetAttribute(stft_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (ea != cudaSuccess) return set_cuda_error(ea, "stft smem attribute");
   const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  stft_gemm_kernel<<<grid, kThreads, smem, stream>>>(p);
+  stft_gemm_kernel<false><<<grid, kThreads, smem, stream>>>(p);
   return set_cuda_error(cudaGetLastError(), "stft launch");
 }
 
