@@ -30,20 +30,23 @@ namespace {
 
 constexpr int BM = 128;   // frames per tile
 constexpr int BN = 256;   // 128 bins x (re, im)
-constexpr int BK = 64;    // samples per pipeline stage (128 B rows, SWIZZLE_128B)
+constexpr int BK = 64;    // samples per k-stage (128 B rows, SWIZZLE_128B)
 constexpr int kBinsPerTile = BN / 2;
-constexpr int kATile = BM * BK * 2;       // 16 KiB
-// Single CTA: stage = A hi | A lo | B hi | B lo = 96 KiB, two stages.  CTA pair (cta_group::2, M = 256 = two neighbouring frame
-// tiles): each CTA holds HALF of the basis tile (128 of the 256 rows), stage = 64 KiB, three stages.  The kernel is bound by the
-// L2 -> shared-memory rate (~43 B/clk per SM chip-wide, /opt/skills/guides/B300_MICROARCH.md "LTS throughput cap"): an item
-// moves 1.5 MiB per SM alone, 1.0 MiB per SM in a pair, against 24.6 k cycles of MMA.
-template <bool CG2>
-struct StageCfg {
-  static constexpr int kStages = CG2 ? 3 : 2;
-  static constexpr int kBRows = CG2 ? BN / 2 : BN;
-  static constexpr int kBTile = kBRows * BK * 2;
-  static constexpr int kStageBytes = 2 * kATile + 2 * kBTile;
-};
+// Shared-memory rings.  The kernel always runs as CTA pairs (cta_group::2, M = 256 = two neighbouring frame tiles): each CTA
+// holds its own 128 frames and HALF of the basis tile (128 of the 256 rows).
+//   A ring: "base tiles" of up to kARowsMax frame rows x 64 samples (hi | lo).  Consecutive frames start `hop` samples apart,
+//           so k-stage kb + P of frame m holds the SAME samples as k-stage kb of frame m + S whenever S * hop = P * 64 (hop 160:
+//           P = 5, S = 2; hop 320: P = 5, S = 1): one base tile of 128 + S (uses - 1) rows serves every k-stage kb = r, r + P,
+//           r + 2P, ... through descriptors whose start address is shifted by whole rows (the swizzle is a function of the
+//           absolute address bits, as for the conv kernel's taps).  The frames are fetched n_fft / (64 P) times less often.
+//   B ring: one k-stage of the basis rows per stage (hi | lo), streamed.
+constexpr int kARowsMax = 144;
+constexpr int kABase = kARowsMax * BK * 2;   // 18 KiB
+constexpr int kAStage = 2 * kABase;
+constexpr int kAStages = 2;
+constexpr int kBTile = (BN / 2) * BK * 2;    // 16 KiB
+constexpr int kBStage = 2 * kBTile;
+constexpr int kBStages = 3;
 constexpr int kEpiWarps = 8;              // two per TMEM lane quarter, each takes half of the tile's bins
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr int kTrPitch = 33;              // epilogue transpose row pitch (floats)
@@ -58,6 +61,7 @@ struct StftProblem {
   float* cosp;
   float* sinp;
   int F, n_fft, n_tiles, item_end;   // item_end: one past this problem's last item in the launch's item list
+  int period, shift_rows, a_rows;    // A base-tile re-use: k-stages r, r + period, ... share one tile, shifted by shift_rows rows
 };
 struct StftParams {
   StftProblem pr[kMaxProblems];
@@ -94,34 +98,32 @@ __device__ __forceinline__ void magphase(float re, float im, int mode, float& m,
   sn = im * r;
 }
 
-// Persistent CTAs over (clip, 128-frame tile, 128-bin tile) items, bin tile fastest so that the CTAs running
-// concurrently share the frame tile in L2.  Warp 0 TMA producer, warp 1 TMEM alloc + MMA issue (two 256-column
-// accumulator stages: the epilogue of item i overlaps the MMAs of item i + 1), warps 2..9 epilogue.
-// CG2: thread-block cluster of 2; an item is a PAIR of frame tiles (p.m_tiles counts pairs), the leader CTA (rank 0) issues
-// every MMA for both (M = 256: rows 0-127 from its shared memory into its TMEM, rows 128-255 from / into the peer's), both CTAs
-// load their own frames and their half of the basis rows (transaction bytes counted on the leader's barrier), tcgen05.commit
-// multicasts the stage-free / accumulator-full arrivals to both, the peer's epilogue warps arrive remotely on the leader's
-// acc_empty.
-template <bool CG2>
+// Persistent CTA PAIRS (thread-block cluster of 2) over (clip, pair of 128-frame tiles, 128-bin tile) items, bin tile fastest
+// so that the pairs running concurrently share the frames in L2.  Warp 0 TMA producer, warp 1 TMEM alloc + MMA issue (two
+// 256-column accumulator stages: the epilogue of item i overlaps the MMAs of item i + 1), warps 2..9 epilogue.
+// The leader CTA (rank 0) issues every MMA for both (M = 256: rows 0-127 from its shared memory into its TMEM, rows 128-255
+// from / into the peer's); both CTAs load their own frames and their half of the basis rows (transaction bytes counted on the
+// leader's barriers), tcgen05.commit multicasts the stage-free / accumulator-full arrivals to both, the peer's epilogue warps
+// arrive remotely on the leader's acc_empty.
 __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_constant__ StftParams p) {
-  constexpr int kStages = StageCfg<CG2>::kStages;
-  constexpr int kBTile = StageCfg<CG2>::kBTile;
-  constexpr int kStageBytes = StageCfg<CG2>::kStageBytes;
   extern __shared__ unsigned char smem_dyn[];
   // SWIZZLE_128B tiles need 1024 B alignment
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  float* tr_base = reinterpret_cast<float*>(smem + kStages * kStageBytes);                 // [kEpiWarps][32][33]
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(tr_base + kEpiWarps * kTrFloats);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* acc_full = empty_bar + kStages;
+  unsigned char* a_ring = smem;
+  unsigned char* b_ring = smem + kAStages * kAStage;
+  float* tr_base = reinterpret_cast<float*>(b_ring + kBStages * kBStage);                  // [kEpiWarps][32][33]
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(tr_base + kEpiWarps * kTrFloats);
+  uint64_t* a_empty = a_full + kAStages;
+  uint64_t* b_full = a_empty + kAStages;
+  uint64_t* b_empty = b_full + kBStages;
+  uint64_t* acc_full = b_empty + kBStages;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t crank = CG2 ? cluster_ctarank() : 0u;
-  const int vbid = CG2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int vgrid = CG2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t crank = cluster_ctarank();
+  const int vbid = (int)(blockIdx.x >> 1), vgrid = (int)(gridDim.x >> 1);
 
   if (warp == 0 && lane == 0) {
     for (int g = 0; g < p.nprob; ++g) {
@@ -132,109 +134,109 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
         tma_prefetch_desc(&p.pr[g].tmB_lo);
       }
     }
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], kEpiWarps * (CG2 ? 2 : 1));     // pair: the epilogue warps of both CTAs arrive on the leader's
+      mbar_init(&acc_empty[s], kEpiWarps * 2);     // the epilogue warps of both CTAs arrive on the leader's
     }
     fence_mbar_init();
   }
-  if (CG2) cluster_sync_all();      // both CTAs' barriers exist before any remote arrive / transaction lands on them
+  cluster_sync_all();               // both CTAs' barriers exist before any remote arrive / transaction lands on them
   if (warp == 1) {
-    if (CG2) {
-      tmem_alloc_cg2(tmem_slot, 2 * BN);
-      tmem_relinquish_cg2();
-    } else {
-      tmem_alloc(tmem_slot, 2 * BN);
-      tmem_relinquish();
-    }
+    tmem_alloc_cg2(tmem_slot, 2 * BN);
+    tmem_relinquish_cg2();
   }
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t nsplit = p.split ? 2u : 1u;
 
   if (warp == 0) {
     if (lane == 0) {
-      const uint32_t stage_tx = (p.split ? kStageBytes : kATile + kBTile) * (CG2 ? 2u : 1u);
-      uint32_t it = 0;
+      uint32_t a_it = 0, b_it = 0;
       for (int gitem = vbid; gitem < p.num_items; gitem += vgrid) {
         int item = gitem;
         const StftProblem& q = find_problem(p, item);
         const int KB = q.n_fft / BK;
         const int n_tile = item % q.n_tiles;
         const int rest = item / q.n_tiles;
-        const int m0 = ((rest % p.m_tiles) * (CG2 ? 2 : 1) + (int)crank) * BM, b = rest / p.m_tiles;
-        const int brow = n_tile * BN + (int)crank * (BN / 2);          // pair: this CTA's half of the basis rows
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
-          unsigned char* st = smem + s * kStageBytes;
-          if (CG2) {
-            if (crank == 0) mbar_arrive_expect_tx(&full_bar[s], stage_tx);
-            const uint32_t bar = mapa_shared(smem_u32(&full_bar[s]), 0);
-            tma_load_3d_cg2(st, &q.tmA_hi, bar, kb * BK, m0, b);
-            tma_load_2d_cg2(st + 2 * kATile, &q.tmB_hi, bar, kb * BK, brow);
-            if (p.split) {
-              tma_load_3d_cg2(st + kATile, &q.tmA_lo, bar, kb * BK, m0, b);
-              tma_load_2d_cg2(st + 2 * kATile + kBTile, &q.tmB_lo, bar, kb * BK, brow);
-            }
-          } else {
-            mbar_arrive_expect_tx(&full_bar[s], stage_tx);
-            tma_load_3d(st, &q.tmA_hi, &full_bar[s], kb * BK, m0, b);
-            tma_load_2d(st + 2 * kATile, &q.tmB_hi, &full_bar[s], kb * BK, brow);
-            if (p.split) {
-              tma_load_3d(st + kATile, &q.tmA_lo, &full_bar[s], kb * BK, m0, b);
-              tma_load_2d(st + 2 * kATile + kBTile, &q.tmB_lo, &full_bar[s], kb * BK, brow);
-            }
+        const int m0 = ((rest % p.m_tiles) * 2 + (int)crank) * BM, b = rest / p.m_tiles;
+        const int brow = n_tile * BN + (int)crank * (BN / 2);          // this CTA's half of the basis rows
+        const uint32_t a_tx = 2u * nsplit * (uint32_t)q.a_rows * (BK * 2);   // both CTAs' boxes land on the leader's barrier
+        const int nres = q.period < KB ? q.period : KB;
+        for (int r = 0; r < nres; ++r) {
+          {
+            const uint32_t sa = a_it % kAStages;
+            mbar_wait(&a_empty[sa], ((a_it / kAStages) & 1) ^ 1);
+            unsigned char* st = a_ring + sa * kAStage;
+            if (crank == 0) mbar_arrive_expect_tx(&a_full[sa], a_tx);
+            const uint32_t bar = mapa_shared(smem_u32(&a_full[sa]), 0);
+            tma_load_3d_cg2(st, &q.tmA_hi, bar, r * BK, m0, b);
+            if (p.split) tma_load_3d_cg2(st + kABase, &q.tmA_lo, bar, r * BK, m0, b);
+            ++a_it;
+          }
+          for (int kb = r; kb < KB; kb += q.period, ++b_it) {
+            const uint32_t sb = b_it % kBStages;
+            mbar_wait(&b_empty[sb], ((b_it / kBStages) & 1) ^ 1);
+            unsigned char* st = b_ring + sb * kBStage;
+            if (crank == 0) mbar_arrive_expect_tx(&b_full[sb], 2u * nsplit * kBTile);
+            const uint32_t bar = mapa_shared(smem_u32(&b_full[sb]), 0);
+            tma_load_2d_cg2(st, &q.tmB_hi, bar, kb * BK, brow);
+            if (p.split) tma_load_2d_cg2(st + kBTile, &q.tmB_lo, bar, kb * BK, brow);
           }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && crank == 0) {
-      const uint32_t idesc = make_idesc_f16(kFmtBF16, kFmtBF16, CG2 ? 2 * BM : BM, BN);
-      uint32_t it = 0, n = 0;
+      const uint32_t idesc = make_idesc_f16(kFmtBF16, kFmtBF16, 2 * BM, BN);
+      uint32_t a_it = 0, b_it = 0, n = 0;
       for (int gitem = vbid; gitem < p.num_items; gitem += vgrid, ++n) {
         int item = gitem;
-        const int KB = find_problem(p, item).n_fft / BK;
+        const StftProblem& q = find_problem(p, item);
+        const int KB = q.n_fft / BK;
+        const int nres = q.period < KB ? q.period : KB;
         const uint32_t as = n & 1u;
         mbar_wait(&acc_empty[as], ((n >> 1) & 1u) ^ 1u);
         tc_fence_after_sync();
         const uint32_t tmem_acc = tmem_base + as * BN;
-        for (int kb = 0; kb < KB; ++kb, ++it) {
-          const int s = it % kStages;
-          mbar_wait(&full_bar[s], (it / kStages) & 1);
+        uint32_t accumulate = 0;
+        for (int r = 0; r < nres; ++r, ++a_it) {
+          const uint32_t sa = a_it % kAStages;
+          mbar_wait(&a_full[sa], (a_it / kAStages) & 1);
           tc_fence_after_sync();
-          const uint32_t st = smem_u32(smem + s * kStageBytes);
+          uint32_t a_addr = smem_u32(a_ring + sa * kAStage);
+          for (int kb = r; kb < KB; kb += q.period, ++b_it, a_addr += (uint32_t)q.shift_rows * (BK * 2)) {
+            const uint32_t sb = b_it % kBStages;
+            mbar_wait(&b_full[sb], (b_it / kBStages) & 1);
+            tc_fence_after_sync();
+            const uint32_t bst = smem_u32(b_ring + sb * kBStage);
 #pragma unroll
-          for (int ks = 0; ks < BK / 16; ++ks) {
-            const uint64_t a_hi = make_smem_desc(st + ks * 32, 1024, kSwizzle128B);
-            const uint64_t b_hi = make_smem_desc(st + 2 * kATile + ks * 32, 1024, kSwizzle128B);
-            if (CG2) umma_f16_cg2(tmem_acc, a_hi, b_hi, idesc, (kb | ks) != 0);
-            else umma_f16(tmem_acc, a_hi, b_hi, idesc, (kb | ks) != 0);
-            if (p.split) {
-              const uint64_t a_lo = make_smem_desc(st + kATile + ks * 32, 1024, kSwizzle128B);
-              const uint64_t b_lo = make_smem_desc(st + 2 * kATile + kBTile + ks * 32, 1024, kSwizzle128B);
-              if (CG2) {
+            for (int ks = 0; ks < BK / 16; ++ks) {
+              const uint64_t a_hi = make_smem_desc(a_addr + ks * 32, 1024, kSwizzle128B);
+              const uint64_t b_hi = make_smem_desc(bst + ks * 32, 1024, kSwizzle128B);
+              umma_f16_cg2(tmem_acc, a_hi, b_hi, idesc, accumulate);
+              accumulate = 1;
+              if (p.split) {
+                const uint64_t a_lo = make_smem_desc(a_addr + kABase + ks * 32, 1024, kSwizzle128B);
+                const uint64_t b_lo = make_smem_desc(bst + kBTile + ks * 32, 1024, kSwizzle128B);
                 umma_f16_cg2(tmem_acc, a_hi, b_lo, idesc, 1);
                 umma_f16_cg2(tmem_acc, a_lo, b_hi, idesc, 1);
-              } else {
-                umma_f16(tmem_acc, a_hi, b_lo, idesc, 1);
-                umma_f16(tmem_acc, a_lo, b_hi, idesc, 1);
               }
             }
+            umma_commit_cg2(&b_empty[sb]);   // frees the basis stage in both CTAs once these MMAs have read it
           }
-          // frees the smem stage (in both CTAs of a pair) once these MMAs have read it
-          if (CG2) umma_commit_cg2(&empty_bar[s]);
-          else umma_commit(&empty_bar[s]);
+          umma_commit_cg2(&a_empty[sa]);     // ... and the frame tile after its last k-stage
         }
-        // accumulator complete (published in both CTAs of a pair)
-        if (CG2) umma_commit_cg2(&acc_full[as]);
-        else umma_commit(&acc_full[as]);
+        umma_commit_cg2(&acc_full[as]);      // accumulator complete (published in both CTAs)
       }
     }
   } else {
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
       const int half = pq.n_fft / 2;
       const int n_tile = item % pq.n_tiles;
       const int rest = item / pq.n_tiles;
-      const int m0 = ((rest % p.m_tiles) * (CG2 ? 2 : 1) + (int)crank) * BM, b = rest / p.m_tiles;
+      const int m0 = ((rest % p.m_tiles) * 2 + (int)crank) * BM, b = rest / p.m_tiles;
       float* const g_mag = pq.mag;
       float* const g_cos = pq.cosp;
       float* const g_sin = pq.sinp;
@@ -302,18 +304,17 @@ __global__ void __launch_bounds__(kThreads, 1) stft_gemm_kernel(const __grid_con
       tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) {
-        if (CG2 && crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[as]), 0));    // the leader's barrier
+        if (crank != 0) mbar_arrive_cluster(mapa_shared(smem_u32(&acc_empty[as]), 0));    // the leader's barrier
         else mbar_arrive(&acc_empty[as]);
       }
     }
   }
   tc_fence_before_sync();
   __syncthreads();
-  if (CG2) cluster_sync_all();      // neither CTA leaves while the other may still touch its shared memory / barriers / TMEM
+  cluster_sync_all();               // neither CTA leaves while the other may still touch its shared memory / barriers / TMEM
   if (warp == 1) {
     tc_fence_after_sync();
-    if (CG2) tmem_dealloc_cg2(tmem_base, 2 * BN);
-    else tmem_dealloc(tmem_base, 2 * BN);
+    tmem_dealloc_cg2(tmem_base, 2 * BN);
   }
 }
 
@@ -378,8 +379,10 @@ int stft_num_ntiles(int n_fft) { return (n_fft / 2 + kBinsPerTile - 1) / kBinsPe
 // of the preceding stride, so the clip pitch is rounded up to a multiple of hop (hop % 8 == 0).
 size_t stft_padded_len(int L, int n_fft, int hop) { return (((size_t)L + n_fft + hop - 1) / hop) * hop; }
 
+// (+4 KiB: the re-used frame tiles are fetched with the largest row count of any k-stage residue, which can run up to
+//  (period - 1) * 64 samples past the last clip's padded signal; those rows are never used by an MMA of a valid frame)
 size_t stft_workspace_bytes(int B, int L, int n_fft, int hop) {
-  return 2 * (size_t)B * stft_padded_len(L, n_fft, hop) * 2 + 256;
+  return (2 * (size_t)B * stft_padded_len(L, n_fft, hop) * 2 + 4096 + 255) / 256 * 256;
 }
 
 // nres STFTs of the same (B, L) waveform batch at the same hop in ONE stft_gemm launch (+ one prep launch): problems are
@@ -400,8 +403,13 @@ int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const 
       }
   const int T = L / hop + 1;
   const int m_tiles = (T + BM - 1) / BM;
-  const bool pairs = m_tiles >= 2;                                   // CTA pairs over two neighbouring frame tiles
-  const int m_units = pairs ? (m_tiles + 1) / 2 : m_tiles;           // (an odd last tile pairs with an all-padding tile)
+  const int m_units = (m_tiles + 1) / 2;      // CTA pairs over two neighbouring frame tiles (an odd last tile pairs with padding)
+  int gcd_hk = hop, gb = BK;
+  while (gb) {
+    const int t = gcd_hk % gb;
+    gcd_hk = gb;
+    gb = t;
+  }
   StftParams p;
   PrepParams pp;
   size_t max_lp = 0;
@@ -423,10 +431,25 @@ int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const 
     StftProblem& q = p.pr[g];
     const int ntn = stft_num_ntiles(n_fft);
     {
-      // frames: dim0 = sample within frame, dim1 = frame (stride hop: overlapping rows), dim2 = clip
-      uint64_t dims[3] = {(uint64_t)n_fft, (uint64_t)T, (uint64_t)B};
+      // frame-tile re-use across k-stages: S * hop = P * 64 samples
+      const int KB = n_fft / BK;
+      int period = hop / gcd_hk, shift = BK / gcd_hk;
+      int rows = BM + shift * ((KB + period - 1) / period - 1);
+      if (rows > kARowsMax || period >= KB) {
+        period = KB;
+        shift = 0;
+        rows = BM;
+      }
+      q.period = period;
+      q.shift_rows = shift;
+      q.a_rows = rows;
+    }
+    {
+      // frames: dim0 = sample within frame, dim1 = frame (stride hop: overlapping rows; the shifted re-use reads up to
+      // a_rows - BM rows past the last frame, all inside the padded signal), dim2 = clip
+      uint64_t dims[3] = {(uint64_t)n_fft, (uint64_t)(T + q.a_rows - BM), (uint64_t)B};
       uint64_t strides[2] = {(uint64_t)hop * 2, (uint64_t)Lp * 2};
-      uint32_t box[3] = {BK, BM, 1};
+      uint32_t box[3] = {BK, (uint32_t)q.a_rows, 1};
       int e = make_tensor_map(&q.tmA_hi, xhi, 2, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (e) return e;
       e = make_tensor_map(&q.tmA_lo, xlo, 2, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -435,7 +458,7 @@ int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const 
     {
       uint64_t dims[2] = {(uint64_t)n_fft, (uint64_t)ntn * BN};
       uint64_t strides[1] = {(uint64_t)n_fft * 2};
-      uint32_t box[2] = {BK, (uint32_t)(pairs ? BN / 2 : BN)};
+      uint32_t box[2] = {BK, BN / 2};
       int e = make_tensor_map(&q.tmB_hi, basis_hi[r], 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
       if (e) return e;
       e = make_tensor_map(&q.tmB_lo, basis_lo[r] ? basis_lo[r] : basis_hi[r], 2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
@@ -468,32 +491,24 @@ int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const 
   p.m_tiles = m_units;
   p.num_items = items;
   const int num_sms = device_sm_count();
-  if (pairs) {
-    const size_t smem = (size_t)StageCfg<true>::kStages * StageCfg<true>::kStageBytes + kEpiWarps * kTrFloats * sizeof(float) + 1024 + 256;
-    // the opt-in is per device and cheap: set it on every launch for the CURRENT device (no process-wide cache)
-    cudaError_t ea = cudaFuncSetAttribute(stft_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (ea != cudaSuccess) return set_cuda_error(ea, "stft smem attribute");
-    const int npairs = num_sms / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * (unsigned)(items < npairs ? items : npairs), 1, 1);
-    cfg.blockDim = dim3(kThreads, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return set_cuda_error(cudaLaunchKernelEx(&cfg, stft_gemm_kernel<true>, p), "stft launch (CTA pairs)");
-  }
-  const size_t smem = (size_t)StageCfg<false>::kStages * StageCfg<false>::kStageBytes + kEpiWarps * kTrFloats * sizeof(float) + 1024 + 256;
-  cudaError_t ea = cudaFuncSetAttribute(stft_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)kAStages * kAStage + (size_t)kBStages * kBStage + kEpiWarps * kTrFloats * sizeof(float) + 1024 + 256;
+  // the opt-in is per device and cheap: set it on every launch for the CURRENT device (no process-wide cache)
+  cudaError_t ea = cudaFuncSetAttribute(stft_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (ea != cudaSuccess) return set_cuda_error(ea, "stft smem attribute");
-  const int grid = p.num_items < num_sms ? p.num_items : num_sms;
-  stft_gemm_kernel<false><<<grid, kThreads, smem, stream>>>(p);
-  return set_cuda_error(cudaGetLastError(), "stft launch");
+  const int npairs = num_sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (unsigned)(items < npairs ? items : npairs), 1, 1);
+  cfg.blockDim = dim3(kThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return set_cuda_error(cudaLaunchKernelEx(&cfg, stft_gemm_kernel, p), "stft launch (CTA pairs)");
 }
 
 int launch_stft(const float* wave, int B, int L, int n_fft, int hop, const void* basis_hi, const void* basis_lo,

@@ -310,9 +310,16 @@ def test_train_gradients_against_reference_and_its_own_sensitivity(step_state):
 
 
 def test_directional_derivative_self_consistency(step_state):
-    """The gradient the engine returns is the gradient of ITS OWN forward: loss(theta - eta g / |g|) - loss(theta) ~ -eta |g|
-    for the full gradient and for parameter groups (a missing or mis-scaled term of the backward shows up here whatever the
-    conditioning of the comparison with fp32 autograd)."""
+    """The gradient the engine returns is the gradient of ITS OWN forward.  For the full parameter vector and for parameter
+    groups, along the FIXED direction d = (fp32 autograd gradient of the group) / |.| -- independent of the engine's own rounding
+    noise, so <G, d> carries no cos^2 bias -- the central difference of the engine's loss must match <G, d>; a missing or
+    mis-scaled term of the backward shows up here whatever the conditioning of the tensor-wise comparison above.
+
+    The step is the smallest one the run-to-run noise of the forward allows (loss moves by 5e-4 relative): the loss of this
+    LeakyReLU / L1 network along a line is piecewise smooth with kinks at every scale, and the measured ratio fd / <G, d> falls
+    monotonically with the step (tools sweep on B200, three builds: 0.84-1.08 at 5e-4, 0.85-1.01 at 1e-3, 0.79-0.98 at 2e-3,
+    0.76-0.97 at 4e-3), hence the asymmetric band.  The same groups are also compared with fp32 autograd directly: cosine and
+    norm ratio of the concatenated gradients (measured 0.975-0.998 and 0.93-1.00)."""
     s = step_state
     eng, model = s["eng"], s["model"]
     mix, cond, tgt = s["mix"].cuda(), s["cond"].cuda(), s["tgt"].cuda()
@@ -328,20 +335,29 @@ def test_directional_derivative_self_consistency(step_state):
 
     base = loss_at(P0)
     G = eng.G.clone()
+    names = {id(p): n for n, p in model.named_parameters()}
+    O = torch.zeros_like(G)
+    for name, (off, p) in eng.index.items():
+        if not name.startswith("dead."):
+            O[off:off + p.numel()] = s["o_grads"][names[id(p)]].reshape(-1).cuda()
     groups = {"all": (0, eng.live_end), "decoder+after (bucket A)": (0, eng.bucket_a_end),
               "encoder+pre+bn0": (eng.bucket_a_end, eng.film_w_off), "film": (eng.film_w_off, eng.live_end)}
     for gname, (lo, hi) in groups.items():
+        g, o = G[lo:hi].double(), O[lo:hi].double()
+        cos, ratio = float((g * o).sum() / (g.norm() * o.norm())), float(g.norm() / o.norm())
         d = torch.zeros_like(G)
-        d[lo:hi] = G[lo:hi]
+        d[lo:hi] = O[lo:hi]
         nrm = float(d.double().norm())
         assert nrm > 0
         d = d / nrm
-        # central difference along the normalised gradient direction; step sized so the loss moves by ~1e-3 relative
-        eta = 2e-3 * base / nrm
+        pred = float((G.double() * d.double()).sum())
+        eta = 5e-4 * base / nrm
         lp, lm = loss_at(P0 + eta * d), loss_at(P0 - eta * d)
         fd = (lp - lm) / (2 * eta)
-        print("%s: predicted slope %.4e, finite difference %.4e" % (gname, nrm, fd))
-        assert abs(fd - nrm) <= 0.15 * nrm, (gname, fd, nrm)
+        print("%s: <G,d> %.4e, finite difference %.4e (ratio %.3f); vs fp32 autograd: cos %.4f, |G|/|O| %.3f"
+              % (gname, pred, fd, fd / pred, cos, ratio))
+        assert 0.75 * pred <= fd <= 1.15 * pred, (gname, fd, pred)
+        assert cos >= 0.95 and 0.88 <= ratio <= 1.08, (gname, cos, ratio)
     with torch.no_grad():
         eng.P.copy_(P0)
         eng.refresh_weights()
