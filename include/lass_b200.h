@@ -195,6 +195,8 @@ LASS_API int lass_bn0_stats(const float* mag, int B, int T, int F, double* sums,
  * running_mean / running_var updated in place with `momentum` and the unbiased variance, like nn.BatchNorm2d in train(). */
 LASS_API int lass_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
                               float* running_var, float momentum, float eps, int C, float* bnp, void* stream);
+/* lass_bn_stats ADDED into `sums` (no memset inside): the training step zeroes the sums of all its sites with one memset. */
+LASS_API int lass_bn_stats_acc(const void* x, int fp16, long long npix, int C, int cstride, int coff, double* sums, void* stream);
 /* out = leaky_relu(scale*x + shift + beta[b]) (slope 0.01): BatchNorm + FiLM beta + activation, models/resunet.py:159-160. */
 LASS_API int lass_bn_act(const void* x, int x_fp16, int x_cstride, int x_coff, void* out, int out_fp16, int out_cstride,
                          int out_coff, int B, long long pix_per_clip, int C, const float* bnp, const float* beta,
@@ -209,6 +211,17 @@ LASS_API int lass_bn_bwd_reduce(const void* dact, int d_cstride, int d_coff, con
                                 int beta_bstride, float* sums, void* stream);
 LASS_API int lass_bn_bwd_finalize(const float* sums, int B, int C, double count, const float* gamma, float* bnp,
                                   float* dgamma, float* dbeta, float* dfilm, int dfilm_bstride, void* stream);
+/* lass_bn_bwd_reduce ADDED into `sums` (no memset inside; the caller zeroes a step's sums at once). */
+LASS_API int lass_bn_bwd_reduce_acc(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride,
+                                    int x_coff, int B, long long pix_per_clip, int C, const float* bnp, const float* beta,
+                                    int beta_bstride, float* sums, void* stream);
+/* A/B variant, NOT used by the training step (measured slower than reduce + the one-block finalize launch, csrc/train.cu):
+ * reduce + finalize in ONE launch (count = B * pix_per_clip): the last block to finish (ticket `counter`, one uint32 per site)
+ * finalizes.  `sums` and `counter` must be ZERO on entry and are left dirty (the caller clears a step's with one memset each). */
+LASS_API int lass_bn_bwd_reduce_finalize(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride,
+                                         int x_coff, int B, long long pix_per_clip, int C, float* bnp, const float* beta,
+                                         int beta_bstride, float* sums, unsigned int* counter, const float* gamma,
+                                         float* dgamma, float* dbeta, float* dfilm, int dfilm_bstride, void* stream);
 LASS_API int lass_bn_bwd_apply(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride,
                                int x_coff, const void* add, int add_cstride, int add_coff, void* dx, int dx_cstride,
                                int dx_coff, int B, long long pix_per_clip, int C, const float* bnp, const float* beta,
@@ -264,6 +277,13 @@ LASS_API int lass_adamw_amsgrad(float* p, const float* g, float* m, float* v, fl
 LASS_API int lass_pack_weight(const float* w, int kind, int co, int ci, int taps, void* fwd, int fwd_fp16, void* dgrad,
                               void* stream);
 LASS_API int lass_unpack_grad(const float* dw, int kind, int co, int ci, int taps, float* grad, void* stream);
+/* Multi-tensor forms: ONE launch for every convolution weight of the model (re-pack after the optimizer step) / every weight
+ * gradient of an all-reduce bucket.  table_dev: DEVICE array of 8 x int64 per tensor --
+ *   pack:   {w, fwd, dgrad, kind, co, ci, taps | fwd_fp16 << 16, first_block}     unpack: {dw, grad, 0, kind, co, ci, taps, first_block}
+ * where tensor i owns blocks [first_block_i, first_block_i + ceil(co*ci*taps / lass_multi_chunk())) and nblocks is their total. */
+LASS_API int lass_pack_weights_multi(const long long* table_dev, int nitems, int nblocks, void* stream);
+LASS_API int lass_unpack_grads_multi(const long long* table_dev, int nitems, int nblocks, void* stream);
+LASS_API int lass_multi_chunk(void);
 /* Debug: 1 = the shared-memory Stockham iSTFT kernel for every n_fft (default: register-FFT kernel for 1024 / 2048). */
 LASS_API int lass_debug_set_istft_v1(int on);
 

@@ -201,6 +201,12 @@ SIGNATURES.update({
     "lass_pack_weight": (_i, [_v, _i, _i, _i, _i, _v, _i, _v, _v]),
     "lass_unpack_grad": (_i, [_v, _i, _i, _i, _i, _v, _v]),
     "lass_debug_set_istft_v1": (_i, [_i]),
+    "lass_bn_stats_acc": (_i, [_v, _i, _ll, _i, _i, _i, _v, _v]),
+    "lass_bn_bwd_reduce_acc": (_i, [_v, _i, _i, _v, _i, _i, _i, _i, _ll, _i, _v, _v, _i, _v, _v]),
+    "lass_bn_bwd_reduce_finalize": (_i, [_v, _i, _i, _v, _i, _i, _i, _i, _ll, _i, _v, _v, _i, _v, _v, _v, _v, _v, _v, _i, _v]),
+    "lass_pack_weights_multi": (_i, [_v, _i, _i, _v]),
+    "lass_unpack_grads_multi": (_i, [_v, _i, _i, _v]),
+    "lass_multi_chunk": (_i, []),
 })
 SIGNATURES["lass_wgrad_tc"] = SIGNATURES["lass_wgrad"]
 SIGNATURES["lass_stft_multi_fwd"] = (_i, [_v, _i, _i, _i, _i, _v, _v, _v, _v, _v, _v, _i, _i, _v, ctypes.c_size_t, _v])

@@ -11,6 +11,8 @@
 //
 // Tensors: NHWC 16-bit with a channel stride / offset (slices of the concat buffers), fp16 or bf16 per flag; all math fp32.
 // Every kernel maps one thread to a 16-byte vector of 8 channels, consecutive threads to consecutive vectors.
+#include <string.h>
+
 #include "lass_internal.cuh"
 
 namespace lass {
@@ -101,6 +103,37 @@ __device__ __forceinline__ void block_reduce_rows(float (&acc)[NACC][8], int CV,
   __syncthreads();
 }
 
+// Optional tail of bn_bwd_reduce (kept for A/B, lass_bn_bwd_reduce_finalize): the LAST block to finish (ticket counter,
+// __threadfence) finalizes.  Measured on B200 it is SLOWER than the separate one-block finalize launch it replaces (+8.5 us per
+// site against ~5 us for kernel + launch gap), and so is deriving the forward tables in bn_act's prologue (+12 us: the fp64
+// divisions / square roots repeated by every block) -- the training step therefore keeps the separate finalize launches.
+__device__ __forceinline__ bool last_block_done(unsigned int* counter, unsigned int nblocks) {
+  __shared__ unsigned int ticket;
+  __threadfence();                                  // this block's atomics are visible before its ticket
+  __syncthreads();
+  if (threadIdx.x == 0) ticket = atomicAdd(counter, 1u);
+  __syncthreads();
+  const bool last = ticket == nblocks - 1;
+  if (last) __threadfence();
+  return last;
+}
+
+__device__ __forceinline__ void bn_finalize_channel(double s, double q, int c, int C, double count, const float* gamma, const float* beta,
+                                                    float* running_mean, float* running_var, float momentum, float eps, float* bnp) {
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const double rstd = 1.0 / sqrt(var + (double)eps);
+  const double scale = (double)gamma[c] * rstd;
+  bnp[c] = (float)scale;
+  bnp[C + c] = (float)((double)beta[c] - mean * scale);
+  bnp[2 * C + c] = (float)mean;
+  bnp[3 * C + c] = (float)rstd;
+  const double unbiased = var * (count / fmax(count - 1.0, 1.0));
+  running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+  running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+}
+
 __global__ void __launch_bounds__(kRedThreads, 2) bn_stats_kernel(const void* __restrict__ x, int fp16, long long npix, int C, int cstride,
                                                                int coff, double* __restrict__ sums) {
   extern __shared__ float red[];
@@ -156,18 +189,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
                                    float* __restrict__ running_var, float momentum, float eps, int C, float* __restrict__ bnp) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double mean = sums[c] / count;
-  double var = sums[C + c] / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const double rstd = 1.0 / sqrt(var + (double)eps);
-  const double scale = (double)gamma[c] * rstd;
-  bnp[c] = (float)scale;
-  bnp[C + c] = (float)((double)beta[c] - mean * scale);
-  bnp[2 * C + c] = (float)mean;
-  bnp[3 * C + c] = (float)rstd;
-  const double unbiased = var * (count / fmax(count - 1.0, 1.0));
-  running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
-  running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+  bn_finalize_channel(sums[c], sums[C + c], c, C, count, gamma, beta, running_mean, running_var, momentum, eps, bnp);
 }
 
 // Elementwise kernels: block = 384 threads = R pixels x CV channel vectors, grid.y = clip.  A thread keeps ITS channel vector for
@@ -211,12 +233,44 @@ __global__ void __launch_bounds__(kRedThreads, 2) bn_act_kernel(const void* __re
   }
 }
 
+struct BnBwdFinalize {
+  unsigned int* counter;
+  double count;
+  const float* gamma;
+  float* bnp;           // reads scale / rstd, writes coefA / coefB
+  float* dgamma;
+  float* dbeta;
+  float* dfilm;         // (B, dfilm_bstride) or nullptr
+  int dfilm_bstride;
+};
+
+__device__ __forceinline__ void bn_bwd_finalize_totals(double t1, double t2, int c, int C, double count, float* bnp, float* dgamma,
+                                                       float* dbeta) {
+  const double scale = (double)bnp[c], rstd = (double)bnp[3 * C + c];
+  dbeta[c] = (float)t1;
+  dgamma[c] = (float)(rstd * t2);
+  bnp[4 * C + c] = (float)(-scale * rstd * rstd * t2 / count);
+  bnp[5 * C + c] = (float)(-scale * t1 / count);
+}
+
+__device__ __forceinline__ void bn_bwd_finalize_channel(const float* sums, int c, int B, int C, double count, float* bnp, float* dgamma,
+                                                        float* dbeta, float* dfilm, int dfilm_bstride) {
+  double t1 = 0.0, t2 = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float s1 = sums[((size_t)b * C + c) * 2], s2 = sums[((size_t)b * C + c) * 2 + 1];
+    t1 += (double)s1;
+    t2 += (double)s2;
+    if (dfilm) dfilm[(size_t)b * dfilm_bstride + c] = s1;
+  }
+  bn_bwd_finalize_totals(t1, t2, c, C, count, bnp, dgamma, dbeta);
+}
+
 // sums (B, C, 2): [sum g', sum g' (x - mean)] per clip; grid.y = clip
 __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_reduce_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
                                                                     const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
                                                                     long long pix_per_clip, int C, const float* __restrict__ bnp,
                                                                     const float* __restrict__ beta, int beta_bstride,
-                                                                    float* __restrict__ sums) {
+                                                                    float* __restrict__ sums, const BnBwdFinalize fin) {
   extern __shared__ float red[];
   const int CV = C / 8, R = kRedThreads / CV;
   const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
@@ -262,6 +316,23 @@ __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_reduce_kernel(const voi
     const int a = e / C, ch = e - a * C;
     atomicAdd(&sums[((size_t)b * C + ch) * 2 + a], s);
   }
+  if (fin.counter == nullptr) return;
+  if (!last_block_done(fin.counter, gridDim.x * gridDim.y)) return;
+  // phase 1: every (clip, channel) pair is an independent 8-byte load (no chain of L2 round trips); per-channel totals in shared memory
+  double* tot = reinterpret_cast<double*>(red);           // [C][2]; red holds R * C * 2 floats with R >= 4
+  for (int e = threadIdx.x; e < 2 * C; e += kRedThreads) tot[e] = 0.0;
+  __syncthreads();
+  const int nb = gridDim.y;
+  for (int i = threadIdx.x; i < nb * C; i += kRedThreads) {
+    const float2 v = __ldcg(reinterpret_cast<const float2*>(sums) + i);
+    const int bb = i / C, ch = i - bb * C;
+    if (fin.dfilm) fin.dfilm[(size_t)bb * fin.dfilm_bstride + ch] = v.x;
+    atomicAdd(&tot[2 * ch], (double)v.x);
+    atomicAdd(&tot[2 * ch + 1], (double)v.y);
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < C; ch += kRedThreads)
+    bn_bwd_finalize_totals(tot[2 * ch], tot[2 * ch + 1], ch, C, fin.count, fin.bnp, fin.dgamma, fin.dbeta);
 }
 
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int B, int C, double count, const float* __restrict__ gamma,
@@ -269,18 +340,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int B, in
                                        float* __restrict__ dfilm, int dfilm_bstride) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  double t1 = 0.0, t2 = 0.0;
-  for (int b = 0; b < B; ++b) {
-    const float s1 = sums[((size_t)b * C + c) * 2], s2 = sums[((size_t)b * C + c) * 2 + 1];
-    t1 += (double)s1;
-    t2 += (double)s2;
-    if (dfilm) dfilm[(size_t)b * dfilm_bstride + c] = s1;
-  }
-  const double scale = (double)bnp[c], rstd = (double)bnp[3 * C + c];
-  dbeta[c] = (float)t1;
-  dgamma[c] = (float)(rstd * t2);
-  bnp[4 * C + c] = (float)(-scale * rstd * rstd * t2 / count);
-  bnp[5 * C + c] = (float)(-scale * t1 / count);
+  bn_bwd_finalize_channel(sums, c, B, C, count, bnp, dgamma, dbeta, dfilm, dfilm_bstride);
 }
 
 __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_apply_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
@@ -729,6 +789,78 @@ __global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restric
   }
 }
 
+// Multi-tensor forms of the two kernels above: ONE launch re-packs every convolution weight after the optimizer step (42 tensors)
+// / un-packs every weight gradient of a bucket.  table: 8 x int64 per tensor
+//   pack:   [w, fwd, dgrad, kind, co, ci, taps | fwd_fp16 << 16, first block]      unpack: [dw, grad, 0, kind, co, ci, taps, first block]
+// a block handles kMultiChunk consecutive source (pack) / destination (unpack) elements of its tensor.
+constexpr int kMultiChunk = 2048;
+__device__ __forceinline__ int multi_find(const long long* __restrict__ table, int nitems, int block) {
+  int lo = 0, hi = nitems - 1;
+  while (lo < hi) {                       // last tensor whose first block <= block
+    const int mid = (lo + hi + 1) >> 1;
+    if ((int)table[mid * 8 + 7] <= block) lo = mid;
+    else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const long long* __restrict__ table, int nitems) {
+  const int it = multi_find(table, nitems, blockIdx.x);
+  const long long* e = table + it * 8;
+  const float* w = reinterpret_cast<const float*>(e[0]);
+  void* fwd = reinterpret_cast<void*>(e[1]);
+  void* dgrad = reinterpret_cast<void*>(e[2]);
+  const int kind = (int)e[3], co = (int)e[4], ci = (int)e[5], taps = (int)(e[6] & 0xffff), fwd_fp16 = (int)(e[6] >> 16);
+  const long long n = (long long)co * ci * taps;
+  const long long i0 = (long long)(blockIdx.x - (int)e[7]) * kMultiChunk;
+  for (long long i = i0 + threadIdx.x; i < i0 + kMultiChunk && i < n; i += 256) {
+    const int t = (int)(i % taps);
+    const long long r = i / taps;
+    int o, c;
+    size_t fi, di;
+    if (kind == 0) {
+      c = (int)(r % ci);
+      o = (int)(r / ci);
+      fi = ((size_t)t * co + o) * ci + c;
+      di = ((size_t)(taps - 1 - t) * ci + c) * co + o;
+    } else {
+      o = (int)(r % co);
+      c = (int)(r / co);
+      fi = ((size_t)t * co + o) * ci + c;
+      di = (size_t)c * taps * co + (size_t)t * co + o;
+    }
+    const float val = w[i];
+    if (fwd) {
+      if (fwd_fp16) reinterpret_cast<__half*>(fwd)[fi] = __float2half_rn(fminf(fmaxf(val, -65504.0f), 65504.0f));
+      else reinterpret_cast<__nv_bfloat16*>(fwd)[fi] = __float2bfloat16_rn(val);
+    }
+    if (dgrad) reinterpret_cast<__nv_bfloat16*>(dgrad)[di] = __float2bfloat16_rn(val);
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_grads_multi_kernel(const long long* __restrict__ table, int nitems) {
+  const int it = multi_find(table, nitems, blockIdx.x);
+  const long long* e = table + it * 8;
+  const float* dw = reinterpret_cast<const float*>(e[0]);
+  float* grad = reinterpret_cast<float*>(e[1]);
+  const int kind = (int)e[3], co = (int)e[4], ci = (int)e[5], taps = (int)e[6];
+  const long long n = (long long)co * ci * taps;
+  const long long i0 = (long long)(blockIdx.x - (int)e[7]) * kMultiChunk;
+  for (long long i = i0 + threadIdx.x; i < i0 + kMultiChunk && i < n; i += 256) {
+    const int t = (int)(i % taps);
+    const long long r = i / taps;
+    int o, c;
+    if (kind == 0) {
+      c = (int)(r % ci);
+      o = (int)(r / ci);
+    } else {
+      o = (int)(r % co);
+      c = (int)(r / co);
+    }
+    grad[i] = dw[((size_t)t * co + o) * ci + c];
+  }
+}
+
 int grid_for(long long work_items, int threads, int max_blocks = 148 * 8) {
   long long b = (work_items + threads - 1) / threads;
   if (b < 1) b = 1;
@@ -754,6 +886,15 @@ int lass_bn_stats(const void* x, int fp16, long long npix, int C, int cstride, i
   const int R = kRedThreads / (C / 8);
   const int grid = grid_for(npix, R * 8, 148 * 4);
   bn_stats_kernel<<<grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), s>>>(x, fp16, npix, C, cstride, coff, sums);
+  LASS_LAUNCH_CHECK("bn_stats launch");
+}
+
+// the same reduction into sums the CALLER zeroed (one memset for all of a step's sites)
+int lass_bn_stats_acc(const void* x, int fp16, long long npix, int C, int cstride, int coff, double* sums, void* stream_v) {
+  if (!x || !sums || npix <= 0 || !chan_ok(C, cstride, coff)) return set_error(LASS_ERR_ARG, "lass_bn_stats_acc: bad argument (C=%d cstride=%d coff=%d)", C, cstride, coff);
+  const int R = kRedThreads / (C / 8);
+  const int grid = grid_for(npix, R * 8, 148 * 4);
+  bn_stats_kernel<<<grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), (cudaStream_t)stream_v>>>(x, fp16, npix, C, cstride, coff, sums);
   LASS_LAUNCH_CHECK("bn_stats launch");
 }
 
@@ -785,18 +926,57 @@ int lass_bn_act(const void* x, int x_fp16, int x_cstride, int x_coff, void* out,
   LASS_LAUNCH_CHECK("bn_act launch");
 }
 
+static int bn_bwd_reduce_launch(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride, int x_coff, int B,
+                                long long pix_per_clip, int C, const float* bnp, const float* beta, int beta_bstride, float* sums,
+                                const BnBwdFinalize& fin, cudaStream_t s) {
+  const int R = kRedThreads / (C / 8);
+  int gx = grid_for(pix_per_clip, R * 8, (148 * 4 + B - 1) / B);
+  dim3 grid((unsigned)gx, (unsigned)B);
+  bn_bwd_reduce_kernel<<<grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), s>>>(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff,
+                                                                                    pix_per_clip, C, bnp, beta, beta_bstride, sums, fin);
+  LASS_LAUNCH_CHECK("bn_bwd_reduce launch");
+}
+
 int lass_bn_bwd_reduce(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride, int x_coff, int B,
                        long long pix_per_clip, int C, const float* bnp, const float* beta, int beta_bstride, float* sums, void* stream_v) {
   if (!dact || !x || !bnp || !beta || !sums || B <= 0 || pix_per_clip <= 0 || !chan_ok(C, x_cstride, x_coff) || !chan_ok(C, d_cstride, d_coff) || beta_bstride % 4)
     return set_error(LASS_ERR_ARG, "lass_bn_bwd_reduce: bad argument");
   cudaStream_t s = (cudaStream_t)stream_v;
   cudaMemsetAsync(sums, 0, sizeof(float) * 2 * (size_t)B * C, s);
-  const int R = kRedThreads / (C / 8);
-  int gx = grid_for(pix_per_clip, R * 8, (148 * 4 + B - 1) / B);
-  dim3 grid((unsigned)gx, (unsigned)B);
-  bn_bwd_reduce_kernel<<<grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), s>>>(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff,
-                                                                                    pix_per_clip, C, bnp, beta, beta_bstride, sums);
-  LASS_LAUNCH_CHECK("bn_bwd_reduce launch");
+  BnBwdFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  return bn_bwd_reduce_launch(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff, B, pix_per_clip, C, bnp, beta, beta_bstride, sums, fin, s);
+}
+
+// the same reduction into sums the CALLER zeroed (one memset for all of a step's sites)
+int lass_bn_bwd_reduce_acc(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride, int x_coff, int B,
+                           long long pix_per_clip, int C, const float* bnp, const float* beta, int beta_bstride, float* sums, void* stream_v) {
+  if (!dact || !x || !bnp || !beta || !sums || B <= 0 || pix_per_clip <= 0 || !chan_ok(C, x_cstride, x_coff) || !chan_ok(C, d_cstride, d_coff) || beta_bstride % 4)
+    return set_error(LASS_ERR_ARG, "lass_bn_bwd_reduce_acc: bad argument");
+  BnBwdFinalize fin;
+  memset(&fin, 0, sizeof(fin));
+  return bn_bwd_reduce_launch(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff, B, pix_per_clip, C, bnp, beta, beta_bstride, sums, fin,
+                              (cudaStream_t)stream_v);
+}
+
+int lass_bn_bwd_reduce_finalize(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride, int x_coff, int B,
+                                long long pix_per_clip, int C, float* bnp, const float* beta, int beta_bstride, float* sums,
+                                unsigned int* counter, const float* gamma, float* dgamma, float* dbeta, float* dfilm, int dfilm_bstride,
+                                void* stream_v) {
+  if (!dact || !x || !bnp || !beta || !sums || !counter || !gamma || !dgamma || !dbeta || B <= 0 || pix_per_clip <= 0 ||
+      !chan_ok(C, x_cstride, x_coff) || !chan_ok(C, d_cstride, d_coff) || beta_bstride % 4)
+    return set_error(LASS_ERR_ARG, "lass_bn_bwd_reduce_finalize: bad argument");
+  BnBwdFinalize fin;
+  fin.counter = counter;
+  fin.count = (double)B * (double)pix_per_clip;
+  fin.gamma = gamma;
+  fin.bnp = bnp;
+  fin.dgamma = dgamma;
+  fin.dbeta = dbeta;
+  fin.dfilm = dfilm;
+  fin.dfilm_bstride = dfilm_bstride;
+  return bn_bwd_reduce_launch(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff, B, pix_per_clip, C, bnp, beta, beta_bstride, sums, fin,
+                              (cudaStream_t)stream_v);
 }
 
 int lass_bn_bwd_finalize(const float* sums, int B, int C, double count, const float* gamma, float* bnp, float* dgamma, float* dbeta,
@@ -924,5 +1104,19 @@ int lass_unpack_grad(const float* dw, int kind, int co, int ci, int taps, float*
   unpack_grad_kernel<<<grid_for((long long)co * ci * taps, 256), 256, 0, (cudaStream_t)stream_v>>>(dw, kind, co, ci, taps, grad);
   LASS_LAUNCH_CHECK("unpack_grad launch");
 }
+
+int lass_pack_weights_multi(const long long* table_dev, int nitems, int nblocks, void* stream_v) {
+  if (!table_dev || nitems <= 0 || nblocks <= 0) return set_error(LASS_ERR_ARG, "lass_pack_weights_multi: bad argument");
+  pack_weights_multi_kernel<<<nblocks, 256, 0, (cudaStream_t)stream_v>>>(table_dev, nitems);
+  LASS_LAUNCH_CHECK("pack_weights_multi launch");
+}
+
+int lass_unpack_grads_multi(const long long* table_dev, int nitems, int nblocks, void* stream_v) {
+  if (!table_dev || nitems <= 0 || nblocks <= 0) return set_error(LASS_ERR_ARG, "lass_unpack_grads_multi: bad argument");
+  unpack_grads_multi_kernel<<<nblocks, 256, 0, (cudaStream_t)stream_v>>>(table_dev, nitems);
+  LASS_LAUNCH_CHECK("unpack_grads_multi launch");
+}
+
+int lass_multi_chunk(void) { return kMultiChunk; }
 
 }  // extern "C"

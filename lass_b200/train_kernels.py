@@ -151,6 +151,14 @@ def bn_finalize(sums, count, gamma, beta, running_mean, running_var, momentum, e
                                        float(momentum), float(eps), C, _p(bnp), _stream()))
 
 
+def bn_stats_acc(x, coff, C, sums):
+    """bn_stats ADDED into ``sums`` (2, C) float64, which the caller zeroed (one memset for all sites of a step)."""
+    _need_cuda(x, sums)
+    npix = x.shape[0] * x.shape[1] * x.shape[2]
+    _chk(_cabi.load().lass_bn_stats_acc(_p(x), 1 if x.dtype == torch.float16 else 0, npix, C, x.shape[3], coff, _p(sums),
+                                        _stream()))
+
+
 def bn_act(x, x_coff, out, out_coff, C, bnp, beta):
     """out[..., out_coff:out_coff+C] = leaky_relu(scale*x + shift + beta[b]) in out's 16-bit type;  beta (B, C) row-strided view."""
     _need_cuda(x, out, bnp, beta)
@@ -176,6 +184,26 @@ def bn_bwd_finalize(sums, count, gamma, bnp, dgamma, dbeta, dfilm):
     B, C = sums.shape[0], sums.shape[1]
     _chk(_cabi.load().lass_bn_bwd_finalize(_p(sums), B, C, float(count), _p(gamma), _p(bnp), _p(dgamma), _p(dbeta),
                                            _p(dfilm), dfilm.stride(0) if dfilm is not None else 0, _stream()))
+
+
+def bn_bwd_reduce_acc(dact, x, x_coff, C, bnp, beta, sums):
+    """bn_bwd_reduce ADDED into ``sums`` (B, C, 2) fp32, which the caller zeroed."""
+    _need_cuda(dact, x, bnp, beta, sums)
+    B, pix = x.shape[0], x.shape[1] * x.shape[2]
+    _chk(_cabi.load().lass_bn_bwd_reduce_acc(_p(dact), dact.shape[3], 0, _p(x), 1 if x.dtype == torch.float16 else 0,
+                                             x.shape[3], x_coff, B, pix, C, _p(bnp), _p(beta), beta.stride(0), _p(sums),
+                                             _stream()))
+
+
+def bn_bwd_reduce_finalize(dact, x, x_coff, C, bnp, beta, sums, counter, gamma, dgamma, dbeta, dfilm):
+    """A/B variant (not used by the engine: slower than reduce + finalize as two launches).  bn_bwd_reduce + bn_bwd_finalize in
+    one launch; ``sums`` (B, C, 2) fp32 and ``counter`` zero on entry, left dirty."""
+    _need_cuda(dact, x, bnp, beta, sums, counter, gamma, dgamma, dbeta)
+    B, pix = x.shape[0], x.shape[1] * x.shape[2]
+    _chk(_cabi.load().lass_bn_bwd_reduce_finalize(_p(dact), dact.shape[3], 0, _p(x), 1 if x.dtype == torch.float16 else 0,
+                                                  x.shape[3], x_coff, B, pix, C, _p(bnp), _p(beta), beta.stride(0), _p(sums),
+                                                  _p(counter), _p(gamma), _p(dgamma), _p(dbeta), _p(dfilm),
+                                                  dfilm.stride(0) if dfilm is not None else 0, _stream()))
 
 
 def bn_bwd_apply(dact, x, x_coff, C, bnp, beta, add, add_coff, dx, dx_coff):
@@ -312,3 +340,53 @@ def unpack_grad(dw, kind, grad):
     else:
         ci, co, taps = grad.shape[0], grad.shape[1], grad.shape[2] * grad.shape[3]
     _chk(_cabi.load().lass_unpack_grad(_p(dw), kind, co, ci, taps, _p(grad), _stream()))
+
+
+class MultiTable:
+    """Device table of a multi-tensor pack / unpack launch (8 x int64 per tensor, see include/lass_b200.h); keeps the tensors
+    it points to alive."""
+
+    def __init__(self, rows, keep, device):
+        chunk = _cabi.load().lass_multi_chunk()
+        flat, block = [], 0
+        for a, b, c, kind, co, ci, taps_word in rows:
+            flat += [a, b, c, kind, co, ci, taps_word, block]
+            block += (co * ci * (taps_word & 0xffff) + chunk - 1) // chunk
+        self.table = torch.tensor(flat, dtype=torch.int64).to(device)
+        self.nitems, self.nblocks, self.keep = len(rows), block, keep
+
+
+def _dims(w, kind):
+    taps = w.shape[2] * w.shape[3]
+    return (w.shape[0], w.shape[1], taps) if kind == KIND_CONV else (w.shape[1], w.shape[0], taps)
+
+
+def pack_weights_table(items, device):
+    """items: [(w fp32 torch layout, kind, fwd 16-bit or None, dgrad bf16 or None)] -> table for pack_weights."""
+    rows = []
+    for w, kind, fwd, dgrad in items:
+        _need_cuda(w, fwd, dgrad)
+        co, ci, taps = _dims(w, kind)
+        rows.append((_p(w), _p(fwd) or 0, _p(dgrad) or 0, kind, co, ci,
+                     taps | ((1 if (fwd is not None and fwd.dtype == torch.float16) else 0) << 16)))
+    return MultiTable(rows, items, device)
+
+
+def pack_weights(table):
+    """pack_weight for every tensor of the table in one launch."""
+    _chk(_cabi.load().lass_pack_weights_multi(_p(table.table), table.nitems, table.nblocks, _stream()))
+
+
+def unpack_grads_table(items, device):
+    """items: [(packed dw fp32 flat, kind, grad fp32 in the parameter's torch layout)] -> table for unpack_grads."""
+    rows = []
+    for dw, kind, grad in items:
+        _need_cuda(dw, grad)
+        co, ci, taps = _dims(grad, kind)
+        rows.append((_p(dw), _p(grad), 0, kind, co, ci, taps))
+    return MultiTable(rows, items, device)
+
+
+def unpack_grads(table):
+    """unpack_grad for every tensor of the table in one launch."""
+    _chk(_cabi.load().lass_unpack_grads_multi(_p(table.table), table.nitems, table.nblocks, _stream()))

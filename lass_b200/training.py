@@ -188,12 +188,27 @@ class TrainEngine:
                 "dec%d.bn1" % j, "dec%d.cb2.bn1" % j, "dec%d.cb2.bn2" % j
         self.site_name = names
         dev = self.device
-        for s, st in self.site.items():
+        # One flat buffer each for the forward sums and num_batches_tracked: cleared / incremented ONCE per step, not per site.
+        order = sorted(self.site)
+        self._sums_flat = torch.zeros(sum(2 * self.site[s].C for s in order), dtype=torch.float64, device=dev)
+        self._nbt = torch.zeros(len(order) + 1, dtype=torch.int64, device=dev)
+        o = 0
+        for i, s in enumerate(order):
+            st = self.site[s]
             st.bnp = torch.zeros(6 * st.C, dtype=torch.float32, device=dev)
-            st.sums = torch.zeros(2, st.C, dtype=torch.float64, device=dev)
+            st.sums = self._sums_flat[o:o + 2 * st.C].view(2, st.C)
+            o += 2 * st.C
+            self._adopt_nbt(st.bn, i)
+        self._adopt_nbt(base.bn0, len(order))
         F = self.n_fft // 2 + 1
         self.bnp0 = torch.zeros(6 * F, dtype=torch.float32, device=dev)
         self.sums0 = torch.zeros(2, F, dtype=torch.float64, device=dev)
+
+    def _adopt_nbt(self, bn, i):
+        """bn.num_batches_tracked becomes a view of the flat counter buffer (one `+= 1` per step for all 34 BatchNorms)."""
+        with torch.no_grad():
+            self._nbt[i] = bn.num_batches_tracked.to(self._nbt.device)
+            bn.num_batches_tracked.data = self._nbt[i]
 
     # ------------------------------------------------------------------ 16-bit kernel layouts of the conv weights
     def _alloc_weights(self):
@@ -226,12 +241,27 @@ class TrainEngine:
             conv_pair("dec%d.conv2" % j, cb.conv2, k.ACT_DTYPE)
             conv_pair("dec%d.sc" % j, cb.shortcut, k.RAW_DTYPE)
 
+        # multi-tensor tables: every conv weight is re-packed by ONE launch after the optimizer step; the weight gradients the
+        # tcgen05 kernel leaves in its packed (taps, co, ci) layout (in Gp, at the parameter's offset) are un-packed into G by one
+        # launch per all-reduce bucket
+        self._pack_table = k.pack_weights_table([(param.data, kind, fwd, dgrad) for (param, kind, fwd, dgrad) in self.w.values()
+                                                 if param is not None], dev)
+        self.Gp = torch.zeros_like(self.G)
+        items_a, items_b = [], []
+        for name, (off, p) in self.index.items():
+            if p.dim() != 4 or name.startswith(("dead.", "after.", "pre.")):
+                continue
+            kind = k.KIND_CONVT if name.endswith(".up") else k.KIND_CONV
+            if kind == k.KIND_CONV and p.shape[2] * p.shape[3] == 1:
+                continue                                           # (co, ci, 1, 1) IS the packed layout: wgrad writes G directly
+            n = p.numel()
+            (items_a if off < self.bucket_a_end else items_b).append((self.Gp[off:off + n], kind, self.G[off:off + n].view(p.shape)))
+        self._unpack_a, self._unpack_b = k.unpack_grads_table(items_a, dev), k.unpack_grads_table(items_b, dev)
+
     @_on_device
     def refresh_weights(self):
         """Re-derive the 16-bit kernel layouts from the fp32 parameters (after an optimizer step / load_state_dict)."""
-        for name, (param, kind, fwd, dgrad) in self.w.items():
-            if param is not None:
-                self.k.pack_weight(param.data, kind, fwd, dgrad)
+        self.k.pack_weights(self._pack_table)
 
     # ------------------------------------------------------------------ per-(B, L) workspace
     def _workspace(self, B, L):
@@ -273,7 +303,11 @@ class TrainEngine:
         ws.d_raw = [buf(kk, ENC[kk][1], R) for kk in range(7)]      # [6] = conv_block7a output, [5..0] = decoder block outputs
         ws.xin_act = [None] + [buf(6 - j, DEC[j][0], A) for j in reversed(range(6))]     # indexed by the level it lives on
         ws.feat = torch.zeros(B, 3, Tp, Fp, dtype=torch.float32, device=dev)
-        ws.bsums = {s: torch.zeros(B, st.C, 2, dtype=torch.float32, device=dev) for s, st in self.site.items()}
+        ws.bsums_flat = torch.zeros(sum(B * st.C * 2 for st in self.site.values()), dtype=torch.float32, device=dev)
+        ws.bsums, o = {}, 0
+        for s, st in self.site.items():
+            ws.bsums[s] = ws.bsums_flat[o:o + B * st.C * 2].view(B, st.C, 2)
+            o += B * st.C * 2
         # gradients (bf16)
         ws.g_y = [buf(kk, ENC[kk][1], G) for kk in range(7)]
         ws.g_a2 = [buf(kk, ENC[kk][1], G) for kk in range(7)]
@@ -295,7 +329,6 @@ class TrainEngine:
         ws.dim = torch.zeros(B, T, F, dtype=torch.float32, device=dev)
         ws.dwave = torch.zeros(B, L, dtype=torch.float32, device=dev)
         ws.loss_sum = torch.zeros(1, dtype=torch.float32, device=dev)
-        ws.wscratch = torch.zeros(9 * 384 * 768, dtype=torch.float32, device=dev)
         ws.stft_ws = self._stft_workspace(B, L)
         self._build_convs(ws)
         if len(self._ws) >= 2:
@@ -370,11 +403,10 @@ class TrainEngine:
         """Batch statistics of x[..., x_coff:+C] -> scale / shift, running-stat update, out = lrelu(bn(x) + beta)."""
         k, st = self.k, self.site[site]
         bn = st.bn
-        k.bn_stats(x, x_coff, st.C, st.sums)
+        k.bn_stats_acc(x, x_coff, st.C, st.sums)
         count = x.shape[0] * x.shape[1] * x.shape[2]
         k.bn_finalize(st.sums, count, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS,
                       st.bnp)
-        bn.num_batches_tracked += 1
         k.bn_act(x, x_coff, out, out_coff, st.C, st.bnp, ws.beta[:, st.row:st.row + st.C])
 
     @_on_device
@@ -385,6 +417,8 @@ class TrainEngine:
         ws = self._workspace(B, L)
         base = self.model.base
         hi, lo, window, tw = self._spectral_tables()
+        self._sums_flat.zero_()          # bn_stats_acc adds into the sums of all sites: one memset per step
+        self._nbt += 1                   # every BatchNorm's num_batches_tracked (views of this buffer)
         ws.cond = condition.detach().to(torch.float32).contiguous()
         wave_in = mixture.detach().to(torch.float32).reshape(B, L).contiguous()
         ws.mag, ws.cos, ws.sin = k.stft(wave_in, hi, lo, self.n_fft, self.hop, ws.stft_ws)
@@ -397,7 +431,6 @@ class TrainEngine:
         k.bn0_stats(ws.mag, self.sums0)
         k.bn_finalize(self.sums0, B * ws.T, bn0.weight.data, bn0.bias.data, bn0.running_mean, bn0.running_var,
                       BN_MOMENTUM, BN_EPS, self.bnp0)
-        bn0.num_batches_tracked += 1
         k.pre_fwd(ws.mag, self.bnp0, base.pre_conv.weight.data.view(32), base.pre_conv.bias.data, ws.x_raw[0])
         cv = ws.conv
         for kk in range(7):
@@ -425,7 +458,7 @@ class TrainEngine:
         name = self.site_name[site]
         beta = ws.beta[:, st.row:st.row + st.C]
         sums = ws.bsums[site]
-        k.bn_bwd_reduce(dact, x, x_coff, st.C, st.bnp, beta, sums)
+        k.bn_bwd_reduce_acc(dact, x, x_coff, st.C, st.bnp, beta, sums)
         count = x.shape[0] * x.shape[1] * x.shape[2]
         k.bn_bwd_finalize(sums, count, st.bn.weight.data, st.bnp, self.g(name + ".weight"), self.g(name + ".bias"),
                           ws.dbeta[:, st.row:st.row + st.C])
@@ -437,9 +470,7 @@ class TrainEngine:
         if taps == 1 and kind == k.KIND_CONV:
             k.wgrad(dy, 0, co, x, 0, ci, 1, self.G[off:off + p.numel()])        # (co, ci, 1, 1) is the packed layout
             return
-        scratch = ws.wscratch[:taps * co * ci]
-        k.wgrad(dy, 0, co, x, 0, ci, taps, scratch)
-        k.unpack_grad(scratch, kind, self.G[off:off + p.numel()].view(p.shape))
+        k.wgrad(dy, 0, co, x, 0, ci, taps, self.Gp[off:off + p.numel()])       # packed layout; un-packed per bucket (backward)
 
     def _block_bwd(self, ws, pfx, sites, dy, x_raw, x_act, h_raw, a2, g_a2, g_h, g_xact, g_sc, g_x, cin, cout, has_sc,
                    conv_pfx):
@@ -466,6 +497,7 @@ class TrainEngine:
         base = self.model.base
         hi, lo, window, tw = self._spectral_tables()
         dwave = dwave.detach().to(torch.float32).reshape(B, L).contiguous()
+        ws.bsums_flat.zero_()
         k.istft_bwd(dwave, window, hi, lo, self.n_fft, self.hop, ws.T, ws.stft_ws, ws.dre, ws.dim)
         k.mask_bwd(ws.feat, ws.mag, ws.cos, ws.sin, ws.dre, ws.dim, ws.dfeat, self.n_fft)
         k.after_bwd(ws.dfeat, ws.d_raw[0], self._after_w, ws.g_y[0], self.g("after.w").view(3, 32), self.g("after.b"))
@@ -481,6 +513,7 @@ class TrainEngine:
             self._wgrad(ws, "dec%d.up" % j, k.KIND_CONVT, ws.dU[lin], uh * uw * cout, ws.xin_act[lin], cin, 1)
             k.conv(cv["dec%d.up.dgrad" % j])
             self._bn_bwd(ws, s0, ws.g_xinact[lin], ws.d_raw[lin], 0, None, 0, ws.g_y[lin], 0)
+        k.unpack_grads(self._unpack_a)
         if async_allreduce is not None:
             async_allreduce(0, self.bucket_a_end)
         for kk in reversed(range(7)):
@@ -490,6 +523,7 @@ class TrainEngine:
             self._block_bwd(ws, "enc%d." % kk, (2 * kk, 2 * kk + 1), ws.g_y[kk], ws.x_raw[kk], ws.x_act[kk], ws.h_raw[kk],
                             ws.a2[kk], ws.g_a2[kk], ws.g_h[kk], ws.g_xact[kk], ws.g_sc_e[kk], ws.g_xraw[kk], cin, cout,
                             cin != cout, "enc%d." % kk)
+        k.unpack_grads(self._unpack_b)
         k.pre_bwd(ws.g_xraw[0], ws.mag, self.bnp0, base.pre_conv.weight.data.view(32), self.g("pre.w").view(32),
                   self.g("pre.b"), self.g("bn0.weight"), self.g("bn0.bias"))
         k.film_bwd(ws.dbeta, ws.cond, self.G[self.film_w_off:self.film_w_off + self.J * self.K].view(self.J, self.K),

@@ -89,6 +89,75 @@ def test_bn_backward_kernels(K, C, with_add):
     _close(res[1][5], res[0][5], 1e-2, 2e-6, "dx")
 
 
+@pytest.mark.parametrize("C,B,H,W", [(32, 2, 64, 128), (128, 3, 10, 24), (768, 2, 8, 8)])
+def test_fused_reduce_finalize_launches_match_the_separate_ones(K, C, B, H, W):
+    """The accumulate-into-zeroed-sums forms the engine uses (lass_bn_stats_acc, lass_bn_bwd_reduce_acc) and the one-launch
+    reduce + finalize A/B variant (the last block finalizes) against the self-zeroing separate launches: same tables, running
+    statistics and gradients (the sums are fp64 / fp32 atomics in a different order)."""
+    x = _rand16((B, H, W, C), torch.float16, 1.5, 12).cuda() + 0.25
+    dact = _rand16((B, H, W, C), torch.bfloat16, 1e-4, 13).cuda()
+    gamma, beta = (torch.rand(C) + 0.5).cuda(), torch.randn(C).cuda()
+    film = (torch.randn(B, C) * 0.3).cuda()
+    res = []
+    for fused in (False, True):
+        sums, bnp = torch.zeros(2, C, dtype=torch.float64, device="cuda"), torch.zeros(6 * C, device="cuda")
+        rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+        cnt = torch.zeros(1, dtype=torch.int32, device="cuda")
+        act = torch.zeros(B, H, W, C, dtype=torch.float16, device="cuda")
+        bs = torch.zeros(B, C, 2, device="cuda")
+        dg, db, dfilm = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda"), torch.zeros(B, C + 32, device="cuda")
+        for rep in range(2):            # twice: the caller's zeroing contract (sums / counters cleared between uses)
+            if fused:
+                sums.zero_(); cnt.zero_(); bs.zero_()
+                K.bn_stats_acc(x, 0, C, sums)
+                K.bn_finalize(sums, B * H * W, gamma, beta, rm, rv, 0.01, 1e-5, bnp)
+                K.bn_act(x, 0, act, 0, C, bnp, film)
+                if rep == 0:
+                    K.bn_bwd_reduce_finalize(dact, x, 0, C, bnp, film, bs, cnt, gamma, dg, db, dfilm[:, 32:])
+                else:
+                    K.bn_bwd_reduce_acc(dact, x, 0, C, bnp, film, bs)
+                    K.bn_bwd_finalize(bs, B * H * W, gamma, bnp, dg, db, dfilm[:, 32:])
+            else:
+                K.bn_stats(x, 0, C, sums)
+                K.bn_finalize(sums, B * H * W, gamma, beta, rm, rv, 0.01, 1e-5, bnp)
+                K.bn_act(x, 0, act, 0, C, bnp, film)
+                K.bn_bwd_reduce(dact, x, 0, C, bnp, film, bs)
+                K.bn_bwd_finalize(bs, B * H * W, gamma, bnp, dg, db, dfilm[:, 32:])
+        torch.cuda.synchronize()
+        res.append([t.clone().float() for t in (bnp, rm, rv, dg, db, dfilm, act)])
+    for name, a, b in zip(("bnp", "running_mean", "running_var", "dgamma", "dbeta", "dfilm", "act"), res[1], res[0]):
+        _close(a, b, 1e-5 if name != "act" else 1e-3, 1e-6 * float(b.abs().max()) + 1e-12, name)
+
+
+def test_multi_tensor_pack_and_unpack_match_the_single_tensor_kernels(K):
+    shapes = [(K.KIND_CONV, (64, 32, 3, 3)), (K.KIND_CONV, (96, 64, 1, 1)), (K.KIND_CONVT, (64, 32, 2, 2)), (K.KIND_CONVT, (32, 64, 1, 2)),
+              (K.KIND_CONV, (384, 768, 3, 3)), (K.KIND_CONV, (8, 8, 3, 3))]
+    g = torch.Generator().manual_seed(21)
+    ws, singles, items, uitems, usingles = [], [], [], [], []
+    for i, (kind, shape) in enumerate(shapes):
+        w = torch.randn(shape, generator=g).cuda()
+        taps = shape[2] * shape[3]
+        co, ci = (shape[0], shape[1]) if kind == K.KIND_CONV else (shape[1], shape[0])
+        fshape = (taps, co, ci) if kind == K.KIND_CONV else (1, taps * co, ci)
+        dshape = (taps, ci, co) if kind == K.KIND_CONV else (1, ci, taps * co)
+        fdt = torch.float16 if i % 2 == 0 else torch.bfloat16
+        f1, d1 = torch.zeros(fshape, dtype=fdt, device="cuda"), torch.zeros(dshape, dtype=torch.bfloat16, device="cuda")
+        f2, d2 = torch.zeros_like(f1), (torch.zeros_like(d1) if i != 1 else None)
+        K.pack_weight(w, kind, f1, d1)
+        items.append((w, kind, f2, d2))
+        singles.append((f1, d1))
+        packed = torch.randn(taps * co * ci, generator=g).cuda()
+        g1, g2 = torch.zeros(shape, device="cuda"), torch.zeros(shape, device="cuda")
+        K.unpack_grad(packed, kind, g1)
+        uitems.append((packed, kind, g2))
+        usingles.append(g1)
+    K.pack_weights(K.pack_weights_table(items, "cuda"))
+    K.unpack_grads(K.unpack_grads_table(uitems, "cuda"))
+    torch.cuda.synchronize()
+    for (f1, d1), (_w, _k, f2, d2), g1, (_p, _k2, g2) in zip(singles, items, usingles, uitems):
+        assert torch.equal(f1, f2) and (d2 is None or torch.equal(d1, d2)) and torch.equal(g1, g2)
+
+
 def test_pool_unshuffle_channel_sum(K):
     B, H, W, C = 2, 8, 12, 64
     dpool = _rand16((B, H // 2, W // 2, C), torch.bfloat16, 1.0, 5)

@@ -330,3 +330,40 @@ def unpack_grad(dw, kind, grad):
     else:
         ci, co, kh, kw = grad.shape
         grad.copy_(dw.view(kh * kw, co, ci).permute(2, 1, 0).reshape(ci, co, kh, kw))
+
+
+# ---- fused / multi-tensor forms of the interface (same semantics as the separate calls) ----
+def bn_stats_acc(x, coff, C, sums):
+    v = x[..., coff:coff + C].double().reshape(-1, C)
+    sums[0] += v.sum(0)
+    sums[1] += (v * v).sum(0)
+
+
+def bn_bwd_reduce_acc(dact, x, x_coff, C, bnp, beta, sums):
+    xv, pre = _pre(x, x_coff, C, bnp, beta)
+    g = dact[..., :C].float() * torch.where(pre > 0, 1.0, SLOPE)
+    sums[:, :, 0] += g.sum(dim=(1, 2))
+    sums[:, :, 1] += (g * (xv - bnp[2 * C:3 * C])).sum(dim=(1, 2))
+
+
+def bn_bwd_reduce_finalize(dact, x, x_coff, C, bnp, beta, sums, counter, gamma, dgamma, dbeta, dfilm):
+    bn_bwd_reduce(dact, x, x_coff, C, bnp, beta, sums)
+    bn_bwd_finalize(sums, x.shape[0] * x.shape[1] * x.shape[2], gamma, bnp, dgamma, dbeta, dfilm)
+
+
+def pack_weights_table(items, device):
+    return items
+
+
+def pack_weights(table):
+    for w, kind, fwd, dgrad in table:
+        pack_weight(w, kind, fwd, dgrad)
+
+
+def unpack_grads_table(items, device):
+    return items
+
+
+def unpack_grads(table):
+    for dw, kind, grad in table:
+        unpack_grad(dw, kind, grad)
