@@ -296,13 +296,20 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
   constexpr int M = 32 * E, N = 2 * M;
   constexpr int kPitch = 33;                      // transposition rows of 32 lanes, padded
   constexpr int kBuf = kPitch * E;                // complex slots per warp buffer (>= M + 1)
-  constexpr int kLoadBatch = 8;                   // bins per lane whose 6 loads each are in flight together
+  // Loads are software-pipelined in batches of kLoadBatch bins per lane (6 planes each): batch i + 1 -- for the last batch of
+  // a frame: batch 0 of the warp's NEXT frame, which then flies during the whole FFT / overlap-add of this one -- is issued
+  // before batch i is consumed (ncu r2c: 29 % of the warp samples sat on the first use of a just-issued load).
+  constexpr int kLoadBatch = 4;
+  constexpr bool kCrossFrame = (E == 16);         // E = 32: the 24 prefetch registers do not fit next to the 64 of the frame
+  constexpr bool kTables = (E == 16);             // Hermitian-pack twiddles + synthesis window in shared memory (E = 32: no room)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int hop = a.hop;
   const int S = a.FR * hop;
   cpx* tw2 = reinterpret_cast<cpx*>(smem_raw);    // [E][32]: exp(+2 pi i b n1 / M)
-  float* ola = reinterpret_cast<float*>(tw2 + E * 32);     // S (a multiple of 8)
-  float* wsum = ola + S;                                   // hop: window-sum of the interior, by position mod hop
+  cpx* twh = tw2 + E * 32;                        // [M]: exp(+2 pi i k / N) (kTables)
+  float2* wins = reinterpret_cast<float2*>(twh + (kTables ? M : 0));   // [M] window pairs (kTables)
+  float* ola = reinterpret_cast<float*>(wins + (kTables ? M : 0));     // S (a multiple of 8)
+  float* wsum = ola + S;                                   // hop: 1 / (N * window-sum) of the interior, by position mod hop
   cpx* bufs = reinterpret_cast<cpx*>(wsum + hop);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   cpx* buf = bufs + (size_t)warp * kBuf;
@@ -314,14 +321,21 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
     const float2 w = __ldg(reinterpret_cast<const float2*>(a.tw) + ((2 * (i & 31) * (i >> 5)) & (N - 1)));
     tw2[i] = cpx{w.x, w.y};
   }
+  if (kTables)
+    for (int i = tid; i < M; i += kThreads) {
+      const float2 w = __ldg(reinterpret_cast<const float2*>(a.tw) + i);
+      twh[i] = cpx{w.x, w.y};
+      wins[i] = __ldg(win2 + i);
+    }
   for (int i = tid; i < S; i += kThreads) ola[i] = 0.0f;
+  const float invN = 1.0f / (float)N;
   for (int r = tid; r < hop; r += kThreads) {
     float ws = 0.0f;
     for (int n = r; n < N; n += hop) {
       const float w = __ldg(a.window + n);
       ws += w * w;
     }
-    wsum[r] = ws;
+    wsum[r] = invN / fmaxf(ws, 1e-11f);
   }
   const uint32_t hop_magic = (uint32_t)((0x100000000ull + (uint32_t)hop - 1) / (uint32_t)hop);   // x / hop == umulhi(x, magic) for x * hop < 2^32
   long long t_lo = (pos0 - N) / hop + 1;
@@ -335,41 +349,57 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
   const float* sinb = a.sinp + (size_t)b * a.T * a.F;
   const float* featb = a.feat + (size_t)b * a.feat_bstride;
 
+  struct Batch {
+    float x0[kLoadBatch], x1[kLoadBatch], x2[kLoadBatch], sp[kLoadBatch], cs[kLoadBatch], sn[kLoadBatch];
+  };
+  // bins 32 (a0 + u) + lane of frame t; batch 0 also brings the Nyquist bin k = M (lane 0) in slot `ny`
+  float ny[6];
+  auto load_batch = [&](Batch& q, long long t, int a0) {
+    const float* fp = featb + (size_t)t * a.feat_tstride;
+    const size_t o = (size_t)t * a.F;
+#pragma unroll
+    for (int u = 0; u < kLoadBatch; ++u) {
+      const int k = 32 * (a0 + u) + lane;
+      const bool inX = k < a.feat_F;
+      q.x0[u] = inX ? __ldg(fp + k) : 0.0f;
+      q.x1[u] = inX ? __ldg(fp + a.feat_cstride + k) : 0.0f;
+      q.x2[u] = inX ? __ldg(fp + 2 * a.feat_cstride + k) : 0.0f;
+      q.sp[u] = __ldg(magb + o + k);
+      q.cs[u] = __ldg(cosb + o + k);
+      q.sn[u] = __ldg(sinb + o + k);
+    }
+    if (a0 == 0 && lane == 0) {
+      const bool inX = M < a.feat_F;
+      ny[0] = inX ? __ldg(fp + M) : 0.0f;
+      ny[1] = inX ? __ldg(fp + a.feat_cstride + M) : 0.0f;
+      ny[2] = inX ? __ldg(fp + 2 * a.feat_cstride + M) : 0.0f;
+      ny[3] = __ldg(magb + o + M);
+      ny[4] = __ldg(cosb + o + M);
+      ny[5] = __ldg(sinb + o + M);
+    }
+  };
+  Batch pre;
+  if (kCrossFrame && t_lo + warp <= t_hi) load_batch(pre, t_lo + warp, 0);
+
   for (long long tb = t_lo; tb <= t_hi; tb += kWarps) {
     const long long t = tb + warp;
     if (t <= t_hi) {
       float zr[E], zi[E];
-      const float* fp = featb + (size_t)t * a.feat_tstride;
-      const size_t o = (size_t)t * a.F;
       // ---- 1. masked half spectrum X[32 a + lane]; bins >= feat_F behave as x = 0, bins >= F (never for k < M) as mag = 0 ----
+      if (!kCrossFrame) load_batch(pre, t, 0);
+      if (lane == 0) buf[M] = mask_bin(ny[0], ny[1], ny[2], ny[3], ny[4], ny[5]);     // Nyquist bin k = M
 #pragma unroll
       for (int a0 = 0; a0 < E; a0 += kLoadBatch) {
-        float x0[kLoadBatch], x1[kLoadBatch], x2[kLoadBatch], sp[kLoadBatch], cs[kLoadBatch], sn[kLoadBatch];
+        const Batch cur = pre;
+        if (a0 + kLoadBatch < E) load_batch(pre, t, a0 + kLoadBatch);
+        else if (kCrossFrame && t + kWarps <= t_hi) load_batch(pre, t + kWarps, 0);
 #pragma unroll
         for (int u = 0; u < kLoadBatch; ++u) {
-          const int k = 32 * (a0 + u) + lane;
-          const bool inX = k < a.feat_F;
-          x0[u] = inX ? __ldg(fp + k) : 0.0f;
-          x1[u] = inX ? __ldg(fp + a.feat_cstride + k) : 0.0f;
-          x2[u] = inX ? __ldg(fp + 2 * a.feat_cstride + k) : 0.0f;
-          sp[u] = __ldg(magb + o + k);
-          cs[u] = __ldg(cosb + o + k);
-          sn[u] = __ldg(sinb + o + k);
-        }
-#pragma unroll
-        for (int u = 0; u < kLoadBatch; ++u) {
-          const cpx X = mask_bin(x0[u], x1[u], x2[u], sp[u], cs[u], sn[u]);
+          const cpx X = mask_bin(cur.x0[u], cur.x1[u], cur.x2[u], cur.sp[u], cur.cs[u], cur.sn[u]);
           zr[a0 + u] = X.x;
           zi[a0 + u] = X.y;
           buf[32 * (a0 + u) + lane] = X;
         }
-      }
-      if (lane == 0) {   // Nyquist bin k = M
-        const bool inX = M < a.feat_F;
-        const cpx X = mask_bin(inX ? __ldg(fp + M) : 0.0f, inX ? __ldg(fp + a.feat_cstride + M) : 0.0f,
-                               inX ? __ldg(fp + 2 * a.feat_cstride + M) : 0.0f, __ldg(magb + o + M), __ldg(cosb + o + M),
-                               __ldg(sinb + o + M));
-        buf[M] = X;
       }
       __syncwarp();
       // ---- 2. Hermitian pack Z[k] = (X[k] + conj X[M-k]) + i tw[k] (X[k] - conj X[M-k]) ----
@@ -382,7 +412,13 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
           xa.y = 0.0f;
           xb.y = 0.0f;
         }
-        const float2 w = __ldg(reinterpret_cast<const float2*>(a.tw) + k);
+        float2 w;
+        if (kTables) {
+          const cpx wc = twh[k];
+          w = make_float2(wc.x, wc.y);
+        } else {
+          w = __ldg(reinterpret_cast<const float2*>(a.tw) + k);
+        }
         const float er = xa.x + xb.x, ei = xa.y - xb.y;      // X[k] + conj(X[M-k])
         const float dr = xa.x - xb.x, di = xa.y + xb.y;      // X[k] - conj(X[M-k])
         const float orr = w.x * dr - w.y * di, oi = w.x * di + w.y * dr;
@@ -411,7 +447,7 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
 #pragma unroll
         for (int n2 = 0; n2 < 32; ++n2) {
           const int m = lane + 32 * n2;
-          const float2 w = __ldg(win2 + m);
+          const float2 w = kTables ? wins[m] : __ldg(win2 + m);
           buf[m] = cpx{zr[n2] * w.x, zi[n2] * w.y};
         }
       } else {
@@ -441,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
           const float pr = __shfl_xor_sync(0xffffffffu, gr, 16), pi = __shfl_xor_sync(0xffffffffu, gi, 16);
           const float vr = h ? pr - gr : gr + pr, vi = h ? pi - gi : gi + pi;
           const int m = n1 + 16 * (n2 + 16 * h);
-          const float2 w = __ldg(win2 + m);
+          const float2 w = kTables ? wins[m] : __ldg(win2 + m);
           buf[m] = cpx{vr * w.x, vi * w.y};
         }
       }
@@ -475,36 +511,53 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
   }
 
   // ---- 6. window-sum normalisation (folded hann^2, clamp 1e-11), 1/N, trim n_fft/2 ----
-  const float invN = 1.0f / (float)N;
   const long long interior_hi = (long long)a.T * hop;
-  for (int pos = tid; pos < S; pos += kThreads) {
+  auto edge_scale = [&](long long np) {       // positions some frame that would cover them does not exist for
+    long long ta = (np - N) / hop + 1;
+    if (np - N < 0) ta = 0;
+    long long tz = np / hop;
+    if (tz > a.T - 1) tz = a.T - 1;
+    float ws = 0.0f;
+    for (long long t = ta; t <= tz; ++t) {
+      const float w = __ldg(a.window + (np - t * hop));
+      ws += w * w;
+    }
+    return invN / fmaxf(ws, 1e-11f);
+  };
+  float* const outb = a.out + (size_t)b * a.L;
+  // four samples per thread: pos0, hop and N / 2 are multiples of 4, so a quad lies in one hop and (for L % 4 == 0) is one
+  // aligned 16-byte store
+  const bool vec_ok = (a.L & 3) == 0;
+  for (int pos = 4 * tid; pos < S; pos += 4 * kThreads) {
     const long long np = pos0 + pos;
     const long long no = np - (N >> 1);
-    if (no < 0 || no >= a.L) continue;
-    float ws;
-    if (np >= N - hop && np < interior_hi) {
-      // every frame that can cover this sample exists: the sum depends on the position modulo hop only
+    if (no + 3 < 0 || no >= a.L) continue;
+    const float4 v = *reinterpret_cast<const float4*>(ola + pos);
+    float4 sc;
+    if (np >= N - hop && np + 3 < interior_hi) {
+      // every frame that can cover these samples exists: the scale depends on the position modulo hop only
       const uint32_t q = __umulhi((uint32_t)pos, hop_magic);
-      ws = wsum[pos - (int)q * hop];                       // pos0 is a multiple of hop
+      sc = *reinterpret_cast<const float4*>(wsum + (pos - (int)q * hop));        // pos0 is a multiple of hop
     } else {
-      long long ta = (np - N) / hop + 1;
-      if (np - N < 0) ta = 0;
-      long long tz = np / hop;
-      if (tz > a.T - 1) tz = a.T - 1;
-      ws = 0.0f;
-      for (long long t = ta; t <= tz; ++t) {
-        const float w = __ldg(a.window + (np - t * hop));
-        ws += w * w;
-      }
+      sc = make_float4(edge_scale(np), edge_scale(np + 1), edge_scale(np + 2), edge_scale(np + 3));
     }
-    a.out[(size_t)b * a.L + no] = (ola[pos] * invN) / fmaxf(ws, 1e-11f);
+    const float4 r = make_float4(v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w);
+    if (vec_ok && no >= 0 && no + 3 < a.L) {
+      *reinterpret_cast<float4*>(outb + no) = r;
+    } else {
+      const float rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (no + i >= 0 && no + i < a.L) outb[no + i] = rr[i];
+    }
   }
 }
 
 template <int E>
 cudaError_t launch_v2(MaskIstftArgs a, int B, int T, cudaStream_t stream) {
   constexpr int N = 64 * E;
-  const size_t fixed = (size_t)E * 32 * sizeof(cpx) + (size_t)kWarps * 33 * E * sizeof(cpx) + 16;
+  const size_t fixed = (size_t)E * 32 * sizeof(cpx) + (E == 16 ? (size_t)32 * E * (sizeof(cpx) + sizeof(float2)) : 0) +
+                       (size_t)kWarps * 33 * E * sizeof(cpx) + 16;
   // CTA = FR hops of output, as many as keep two CTAs per SM (halo frames are recomputed: ~n_fft/hop per CTA)
   a.FR = 64;
   while (fixed + (size_t)(a.FR * a.hop + a.hop) * 4 > 112 * 1024 && a.FR > 8) a.FR -= 8;
