@@ -291,8 +291,11 @@ __device__ __forceinline__ cpx mask_bin(float x0, float x1, float x2, float sp, 
   return cpx{om * (cs * mc - sn * ms), om * (sn * mc + cs * ms)};
 }
 
-template <int E>
-__global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIstftArgs a) {
+// NW warps per CTA: 8 with two CTAs per SM (n_fft 1024), 16 with one (n_fft 2048: the per-warp buffers leave a pair of CTAs only
+// 24 hops of output each, i.e. 27 % recomputed halo frames; one CTA of 16 warps holds 64 hops, 10 %)
+template <int E, int NW>
+__global__ void __launch_bounds__(NW * 32, 16 / NW) mask_istft_v2_kernel(const MaskIstftArgs a) {
+  constexpr int kWarps = NW, kThreads = NW * 32;
   constexpr int M = 32 * E, N = 2 * M;
   constexpr int kPitch = 33;                      // transposition rows of 32 lanes, padded
   constexpr int kBuf = kPitch * E;                // complex slots per warp buffer (>= M + 1)
@@ -553,24 +556,40 @@ __global__ void __launch_bounds__(kThreads, 2) mask_istft_v2_kernel(const MaskIs
   }
 }
 
-template <int E>
+template <int E, int NW>
 cudaError_t launch_v2(MaskIstftArgs a, int B, int T, cudaStream_t stream) {
   constexpr int N = 64 * E;
   const size_t fixed = (size_t)E * 32 * sizeof(cpx) + (E == 16 ? (size_t)32 * E * (sizeof(cpx) + sizeof(float2)) : 0) +
-                       (size_t)kWarps * 33 * E * sizeof(cpx) + 16;
-  // CTA = FR hops of output, as many as keep two CTAs per SM (halo frames are recomputed: ~n_fft/hop per CTA)
-  a.FR = 64;
-  while (fixed + (size_t)(a.FR * a.hop + a.hop) * 4 > 112 * 1024 && a.FR > 8) a.FR -= 8;
+                       (size_t)NW * 33 * E * sizeof(cpx) + 16;
+  // CTA = FR hops of output, as many as the SM's shared memory holds for 16 warps (halo frames are recomputed: ~n_fft/hop per CTA)
+  const size_t budget = (NW == 16 ? 227 : 112) * 1024;
+  const long long P = (long long)(T - 1) * a.hop + N;
+  {
+    // Among the sizes that fit, the one with the least work on the busiest SM: waves of resident CTAs x frames per CTA
+    // (FR + the ~n_fft/hop recomputed halo frames).  64 x 10 s at 1024 / 160: FR = 56 runs 4 waves of 61 frames, FR = 64 4 of 69.
+    const long long slots = (long long)device_sm_count() * (16 / NW);
+    const int halo = (N + a.hop - 1) / a.hop - 1;
+    long long best = -1;
+    a.FR = 8;
+    for (int fr = 64; fr >= 8; fr -= 8) {
+      if (fixed + (size_t)(fr * a.hop + a.hop) * 4 > budget) continue;
+      const long long ctas = ((P + (long long)fr * a.hop - 1) / ((long long)fr * a.hop)) * B;
+      const long long cost = ((ctas + slots - 1) / slots) * (fr + halo);
+      if (best < 0 || cost < best) {
+        best = cost;
+        a.FR = fr;
+      }
+    }
+  }
   const size_t smem = fixed + (size_t)(a.FR * a.hop + a.hop) * 4;
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   {  // per-device attribute, cheap: opted in to the full 227 KiB on every launch for the current device (no process-wide cache)
-    cudaError_t e = cudaFuncSetAttribute(mask_istft_v2_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(mask_istft_v2_kernel<E, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
   }
-  const long long P = (long long)(T - 1) * a.hop + N;
   const int S = a.FR * a.hop;
   dim3 grid((unsigned)((P + S - 1) / S), (unsigned)B);
-  mask_istft_v2_kernel<E><<<grid, kThreads, smem, stream>>>(a);
+  mask_istft_v2_kernel<E, NW><<<grid, NW * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -612,8 +631,8 @@ cudaError_t launch_mask_istft(const float* feat, long long feat_bstride, long lo
   a.FR = 0;
   // register-FFT kernel for the two model shapes (hop must keep the window-table reads 8-byte aligned: always true)
   if (!g_force_v1) {
-    if (N == 1024) return launch_v2<16>(a, B, T, stream);
-    if (N == 2048) return launch_v2<32>(a, B, T, stream);
+    if (N == 1024) return launch_v2<16, 8>(a, B, T, stream);
+    if (N == 2048) return launch_v2<32, 16>(a, B, T, stream);
   }
   // CTA = FR hops of output; as large as fits two CTAs per SM (halo frames are recomputed: ~n_fft/hop per CTA)
   a.FR = 64;
