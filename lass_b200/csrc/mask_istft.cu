@@ -36,7 +36,7 @@ struct MaskIstftArgs {
   const float* window;  // [N] synthesis window (periodic Hann), NOT scaled
   const cpx* tw;        // [N] exp(+2 pi i j / N)
   float* out;           // (B, L)
-  int T, F, N, log2M, hop, L, FR;
+  int T, F, N, log2M, hop, L, FR, B;
 };
 
 // Fast-math forms (errors ~1e-6 relative, far inside the 1e-4 bar; checked by tests/test_gpu_spectral.py).
@@ -308,16 +308,15 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mask_istft_v2_kernel(const M
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int hop = a.hop;
   const int S = a.FR * hop;
+  const int SO = S + N - hop;                     // the CTA's samples: its range + the spill of its last frames
   cpx* tw2 = reinterpret_cast<cpx*>(smem_raw);    // [E][32]: exp(+2 pi i b n1 / M)
   cpx* twh = tw2 + E * 32;                        // [M]: exp(+2 pi i k / N) (kTables)
   float2* wins = reinterpret_cast<float2*>(twh + (kTables ? M : 0));   // [M] window pairs (kTables)
-  float* ola = reinterpret_cast<float*>(wins + (kTables ? M : 0));     // S (a multiple of 8)
-  float* wsum = ola + S;                                   // hop: 1 / (N * window-sum) of the interior, by position mod hop
+  float* ola = reinterpret_cast<float*>(wins + (kTables ? M : 0));     // SO (a multiple of 8)
+  float* wsum = ola + SO;                                  // hop: 1 / (N * window-sum) of the interior, by position mod hop
   cpx* bufs = reinterpret_cast<cpx*>(wsum + hop);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   cpx* buf = bufs + (size_t)warp * kBuf;
-  const int b = blockIdx.y;
-  const long long pos0 = (long long)blockIdx.x * S;
   const float2* win2 = reinterpret_cast<const float2*>(a.window);
 
   for (int i = tid; i < E * 32; i += kThreads) {
@@ -330,7 +329,6 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mask_istft_v2_kernel(const M
       twh[i] = cpx{w.x, w.y};
       wins[i] = __ldg(win2 + i);
     }
-  for (int i = tid; i < S; i += kThreads) ola[i] = 0.0f;
   const float invN = 1.0f / (float)N;
   for (int r = tid; r < hop; r += kThreads) {
     float ws = 0.0f;
@@ -341,25 +339,35 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mask_istft_v2_kernel(const M
     wsum[r] = invN / fmaxf(ws, 1e-11f);
   }
   const uint32_t hop_magic = (uint32_t)((0x100000000ull + (uint32_t)hop - 1) / (uint32_t)hop);   // x / hop == umulhi(x, magic) for x * hop < 2^32
-  long long t_lo = (pos0 - N) / hop + 1;
-  if (pos0 - N < 0) t_lo = 0;
-  long long t_hi = (pos0 + S - 1) / hop;
-  if (t_hi > a.T - 1) t_hi = a.T - 1;
-  __syncthreads();
-
-  const float* magb = a.mag + (size_t)b * a.T * a.F;
-  const float* cosb = a.cosp + (size_t)b * a.T * a.F;
-  const float* sinb = a.sinp + (size_t)b * a.T * a.F;
-  const float* featb = a.feat + (size_t)b * a.feat_bstride;
+  // Persistent CTAs over (clip, chunk of FR frames) items, item i on CTA i mod grid: FR is a constant of the shape (NOT of the
+  // batch size: clips come out bit-identical whatever batch they run in), small enough that the static round-robin ends level.
+  // An item owns the FR frames that START in [pos0, pos0 + S) -- no halo frames are recomputed.  Their samples reach N - hop past
+  // the range: that spill is added to the output with red.global, like the first N - hop samples of the range (which the previous
+  // chunk spills into); everything else is stored.  The output is zeroed before the launch, and a sample receives at most two such
+  // additions (S >= N - hop), so the result does not depend on their order: 0 + x + y == 0 + y + x in floating point.
+  const int chunks = (a.T + a.FR - 1) / a.FR, n_items = chunks * a.B;
+  const long long interior_hi = (long long)a.T * hop;
+  const bool vec_ok = (a.L & 3) == 0;
+  // first frame of this warp in round r of an item (-1: none)
+  auto item_frame = [&](int item, int r, int& bb) -> long long {
+    if (item >= n_items) return -1;
+    bb = item / chunks;
+    const long long lo = (long long)(item - bb * chunks) * a.FR;
+    long long hi = lo + a.FR - 1;
+    if (hi > a.T - 1) hi = a.T - 1;
+    const long long t = lo + (long long)r * kWarps + warp;
+    return t <= hi ? t : -1;
+  };
 
   struct Batch {
     float x0[kLoadBatch], x1[kLoadBatch], x2[kLoadBatch], sp[kLoadBatch], cs[kLoadBatch], sn[kLoadBatch];
   };
   // bins 32 (a0 + u) + lane of frame t; batch 0 also brings the Nyquist bin k = M (lane 0) in slot `ny`
   float ny[6];
-  auto load_batch = [&](Batch& q, long long t, int a0) {
-    const float* fp = featb + (size_t)t * a.feat_tstride;
-    const size_t o = (size_t)t * a.F;
+  auto load_batch = [&](Batch& q, int bb, long long t, int a0) {
+    const float* fp = a.feat + (size_t)bb * a.feat_bstride + (size_t)t * a.feat_tstride;
+    const size_t o = ((size_t)bb * a.T + (size_t)t) * a.F;
+    const float *magb = a.mag, *cosb = a.cosp, *sinb = a.sinp;
 #pragma unroll
     for (int u = 0; u < kLoadBatch; ++u) {
       const int k = 32 * (a0 + u) + lane;
@@ -382,20 +390,45 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mask_istft_v2_kernel(const M
     }
   };
   Batch pre;
-  if (kCrossFrame && t_lo + warp <= t_hi) load_batch(pre, t_lo + warp, 0);
+  long long pre_tag = -1;          // clip * T + frame whose batch 0 `pre` holds (a warp without a frame in some item breaks the chain)
+  if (kCrossFrame) {
+    int bb;
+    const long long t = item_frame(blockIdx.x, 0, bb);
+    if (t >= 0) {
+      load_batch(pre, bb, t, 0);
+      pre_tag = (long long)bb * a.T + t;
+    }
+  }
 
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+  const int b = item / chunks;
+  const long long t_lo = (long long)(item - b * chunks) * a.FR;
+  long long t_hi = t_lo + a.FR - 1;
+  if (t_hi > a.T - 1) t_hi = a.T - 1;
+  const long long pos0 = t_lo * hop;
+  for (int i = tid; i < SO; i += kThreads) ola[i] = 0.0f;
+  __syncthreads();
   for (long long tb = t_lo; tb <= t_hi; tb += kWarps) {
     const long long t = tb + warp;
     if (t <= t_hi) {
       float zr[E], zi[E];
       // ---- 1. masked half spectrum X[32 a + lane]; bins >= feat_F behave as x = 0, bins >= F (never for k < M) as mag = 0 ----
-      if (!kCrossFrame) load_batch(pre, t, 0);
+      if (!kCrossFrame || pre_tag != (long long)b * a.T + t) load_batch(pre, b, t, 0);
       if (lane == 0) buf[M] = mask_bin(ny[0], ny[1], ny[2], ny[3], ny[4], ny[5]);     // Nyquist bin k = M
 #pragma unroll
       for (int a0 = 0; a0 < E; a0 += kLoadBatch) {
         const Batch cur = pre;
-        if (a0 + kLoadBatch < E) load_batch(pre, t, a0 + kLoadBatch);
-        else if (kCrossFrame && t + kWarps <= t_hi) load_batch(pre, t + kWarps, 0);
+        if (a0 + kLoadBatch < E) {
+          load_batch(pre, b, t, a0 + kLoadBatch);
+        } else if (kCrossFrame) {
+          // this warp's next frame: next round of the item, else round 0 of the CTA's next item
+          int bb = b;
+          const long long tn = t + kWarps <= t_hi ? t + kWarps : item_frame(item + (int)gridDim.x, 0, bb);
+          if (tn >= 0) {
+            load_batch(pre, bb, tn, 0);
+            pre_tag = (long long)bb * a.T + tn;
+          }
+        }
 #pragma unroll
         for (int u = 0; u < kLoadBatch; ++u) {
           const cpx X = mask_bin(cur.x0[u], cur.x1[u], cur.x2[u], cur.sp[u], cur.cs[u], cur.sn[u]);
@@ -488,10 +521,8 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mask_istft_v2_kernel(const M
     __syncthreads();
     // ---- 5. overlap-add of this round's (already windowed) frames; each thread owns its positions: deterministic ----
     const int cnt = (int)((t_hi - tb + 1 < kWarps) ? (t_hi - tb + 1) : kWarps);
-    long long w0 = tb * hop - pos0;
-    if (w0 < 0) w0 = 0;
-    long long w1 = (tb + cnt - 1) * hop + N - pos0;
-    if (w1 > S) w1 = S;
+    const long long w0 = tb * hop - pos0;
+    const long long w1 = (tb + cnt - 1) * hop + N - pos0;       // <= SO
     const float* zbase = reinterpret_cast<const float*>(bufs);
     constexpr int zstride = 2 * kBuf;
     // four consecutive samples per thread and step: hop, N and every frame offset are multiples of 4
@@ -514,7 +545,6 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mask_istft_v2_kernel(const M
   }
 
   // ---- 6. window-sum normalisation (folded hann^2, clamp 1e-11), 1/N, trim n_fft/2 ----
-  const long long interior_hi = (long long)a.T * hop;
   auto edge_scale = [&](long long np) {       // positions some frame that would cover them does not exist for
     long long ta = (np - N) / hop + 1;
     if (np - N < 0) ta = 0;
@@ -530,11 +560,11 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mask_istft_v2_kernel(const M
   float* const outb = a.out + (size_t)b * a.L;
   // four samples per thread: pos0, hop and N / 2 are multiples of 4, so a quad lies in one hop and (for L % 4 == 0) is one
   // aligned 16-byte store
-  const bool vec_ok = (a.L & 3) == 0;
-  for (int pos = 4 * tid; pos < S; pos += 4 * kThreads) {
+  for (int pos = 4 * tid; pos < SO; pos += 4 * kThreads) {
     const long long np = pos0 + pos;
     const long long no = np - (N >> 1);
     if (no + 3 < 0 || no >= a.L) continue;
+    const bool shared_with_neighbour = pos < N - hop || pos >= S;
     const float4 v = *reinterpret_cast<const float4*>(ola + pos);
     float4 sc;
     if (np >= N - hop && np + 3 < interior_hi) {
@@ -545,14 +575,20 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mask_istft_v2_kernel(const M
       sc = make_float4(edge_scale(np), edge_scale(np + 1), edge_scale(np + 2), edge_scale(np + 3));
     }
     const float4 r = make_float4(v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w);
-    if (vec_ok && no >= 0 && no + 3 < a.L) {
+    const float rr[4] = {r.x, r.y, r.z, r.w};
+    if (shared_with_neighbour) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (no + i >= 0 && no + i < a.L) atomicAdd(outb + no + i, rr[i]);
+    } else if (vec_ok && no >= 0 && no + 3 < a.L) {
       *reinterpret_cast<float4*>(outb + no) = r;
     } else {
-      const float rr[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
         if (no + i >= 0 && no + i < a.L) outb[no + i] = rr[i];
     }
+  }
+  __syncthreads();      // the accumulator is re-zeroed for the next item
   }
 }
 
@@ -561,34 +597,23 @@ cudaError_t launch_v2(MaskIstftArgs a, int B, int T, cudaStream_t stream) {
   constexpr int N = 64 * E;
   const size_t fixed = (size_t)E * 32 * sizeof(cpx) + (E == 16 ? (size_t)32 * E * (sizeof(cpx) + sizeof(float2)) : 0) +
                        (size_t)NW * 33 * E * sizeof(cpx) + 16;
-  // CTA = FR hops of output, as many as the SM's shared memory holds for 16 warps (halo frames are recomputed: ~n_fft/hop per CTA)
-  const size_t budget = (NW == 16 ? 227 : 112) * 1024;
-  const long long P = (long long)(T - 1) * a.hop + N;
-  {
-    // Among the sizes that fit, the one with the least work on the busiest SM: waves of resident CTAs x frames per CTA
-    // (FR + the ~n_fft/hop recomputed halo frames).  64 x 10 s at 1024 / 160: FR = 56 runs 4 waves of 61 frames, FR = 64 4 of 69.
-    const long long slots = (long long)device_sm_count() * (16 / NW);
-    const int halo = (N + a.hop - 1) / a.hop - 1;
-    long long best = -1;
-    a.FR = 8;
-    for (int fr = 64; fr >= 8; fr -= 8) {
-      if (fixed + (size_t)(fr * a.hop + a.hop) * 4 > budget) continue;
-      const long long ctas = ((P + (long long)fr * a.hop - 1) / ((long long)fr * a.hop)) * B;
-      const long long cost = ((ctas + slots - 1) / slots) * (fr + halo);
-      if (best < 0 || cost < best) {
-        best = cost;
-        a.FR = fr;
-      }
-    }
-  }
-  const size_t smem = fixed + (size_t)(a.FR * a.hop + a.hop) * 4;
+  // item = 32 frames (4 rounds of 8 warps / 2 of 16), more where the spill rule S >= N - hop wants it
+  a.FR = 32;
+  while (a.FR * a.hop < N - a.hop) a.FR += NW;
+  const size_t smem = fixed + (size_t)(a.FR * a.hop + N) * 4;      // ola: FR hops + the spill (N - hop), + the scale table (hop)
   if (smem > 227 * 1024) return cudaErrorInvalidValue;
   {  // per-device attribute, cheap: opted in to the full 227 KiB on every launch for the current device (no process-wide cache)
     cudaError_t e = cudaFuncSetAttribute(mask_istft_v2_kernel<E, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return e;
   }
-  const int S = a.FR * a.hop;
-  dim3 grid((unsigned)((P + S - 1) / S), (unsigned)B);
+  a.B = B;
+  const long long n_items = (long long)((T + a.FR - 1) / a.FR) * B;
+  const long long slots = (long long)device_sm_count() * (16 / NW);
+  dim3 grid((unsigned)(n_items < slots ? n_items : slots));
+  {
+    cudaError_t e = cudaMemsetAsync(a.out, 0, (size_t)B * a.L * sizeof(float), stream);    // the CTAs ADD their boundary samples
+    if (e != cudaSuccess) return e;
+  }
   mask_istft_v2_kernel<E, NW><<<grid, NW * 32, smem, stream>>>(a);
   return cudaGetLastError();
 }
