@@ -167,3 +167,59 @@ def test_audiosep_training_step_and_fused_step():
     # first AdamW step: |delta| = lr * 0.001 (constant_warm_up plateau) for every element with a non-negligible gradient
     assert float(moved[0].abs().max()) == pytest.approx(1e-6, rel=5e-2)          # (quantised by the fp32 ulp of the weights)
     assert float((moved[0] - moved[1]).abs().max()) <= 2e-7
+
+
+def test_precomputed_shard_format_matches_the_reference_writer(tmp_path):
+    """The .pt shard layout of reference scripts/precompute_stfts.py:60-123 / :596-622 (list of item dicts, CPU tensors, file
+    name) written by lass_b200.multires.save_batch_precomputed_data and read back; no GPU needed for the format itself."""
+    from lass_b200 import multires
+    wins, T, L = [256, 512, 2048], 11, 1600
+    items = []
+    for k in range(3):
+        st = {src: {w: tuple(torch.randn(1, 1, T, w // 2 + 1) for _ in range(3)) for w in wins} for src in ("mixture", "segment")}
+        items.append({"stfts": st, "target_waveform": torch.randn(1, L), "text": "caption %d" % k,
+                      "mixture_component_texts": ["caption %d" % k, "other"], "stft_common_params": multires.shard_common_params(160),
+                      "stft_win_lengths": wins})
+    assert multires.save_batch_precomputed_data(tmp_path, 7, []) == 0 and not list(tmp_path.iterdir())
+    assert multires.save_batch_precomputed_data(tmp_path, 7, items) == 3
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert files == ["batch_000007.pt"]
+    back = multires.load_batch_precomputed_data(tmp_path / files[0])
+    assert isinstance(back, list) and len(back) == 3
+    for a, b in zip(items, back):
+        assert sorted(b) == ["mixture_component_texts", "stft_common_params", "stft_win_lengths", "stfts", "target_waveform", "text"]
+        assert b["text"] == a["text"] and b["mixture_component_texts"] == a["mixture_component_texts"]
+        assert b["stft_common_params"] == {"hop_length": 160, "window": "hann", "center": True, "pad_mode": "reflect"}
+        assert b["stft_win_lengths"] == wins and sorted(b["stfts"]) == ["mixture", "segment"]
+        for src in ("mixture", "segment"):
+            assert sorted(b["stfts"][src]) == wins
+            for w in wins:
+                tup = b["stfts"][src][w]
+                assert isinstance(tup, tuple) and len(tup) == 3
+                for x, y in zip(tup, a["stfts"][src][w]):
+                    assert x.device.type == "cpu" and x.shape == (1, 1, T, w // 2 + 1) and torch.equal(x, y)
+        assert torch.equal(b["target_waveform"], a["target_waveform"])
+
+
+@pytest.mark.gpu
+def test_shard_items_hold_the_reference_stft_components():
+    """build_shard_items: item k's tuples are the [k:k+1] slices of calculate_stft_components (reference
+    scripts/precompute_stfts.py:573-607), checked against the torchlibrosa restatement."""
+    from lass_b200 import multires
+    from oracle.torchlibrosa import stft as tl
+    g = torch.Generator().manual_seed(3)
+    mix, seg = 0.1 * torch.randn(3, 1, 16000, generator=g), 0.1 * torch.randn(3, 1, 16000, generator=g)
+    items = multires.build_shard_items(mix.cuda(), seg.cuda(), ["a", "b", "c"], [["a", "x"], ["b"], ["c", "y", "z"]])
+    assert len(items) == 3 and items[1]["text"] == "b" and items[2]["mixture_component_texts"] == ["c", "y", "z"]
+    for w in (256, 512, 2048):
+        ext = tl.STFT(n_fft=w, hop_length=160, win_length=w, window="hann", center=True, pad_mode="reflect", freeze_parameters=True)
+        for src, wave in (("mixture", mix), ("segment", seg)):
+            real, imag = ext(wave[:, 0])
+            mag, cos, sin = tl.magphase(real, imag)
+            for k in range(3):
+                m, c, s_ = (t.cpu() for t in items[k]["stfts"][src][w])
+                assert m.shape == (1, 1, 101, w // 2 + 1)
+                assert float((m - mag[k:k + 1]).abs().max()) <= 1e-4 * float(mag.abs().max())
+                big = mag[k:k + 1] > 1e-3 * float(mag.max())
+                assert float(((c - cos[k:k + 1]).abs() * big).max()) <= 2e-3 and float(((s_ - sin[k:k + 1]).abs() * big).max()) <= 2e-3
+        assert torch.equal(items[0]["target_waveform"].cpu(), seg[0])
