@@ -280,10 +280,12 @@ LASS_API int lass_unpack_grad(const float* dw, int kind, int co, int ci, int tap
 /* Multi-tensor forms: ONE launch for every convolution weight of the model (re-pack after the optimizer step) / every weight
  * gradient of an all-reduce bucket.  table_dev: DEVICE array of 8 x int64 per tensor --
  *   pack:   {w, fwd, dgrad, kind, co, ci, taps | fwd_fp16 << 16, first_block}     unpack: {dw, grad, 0, kind, co, ci, taps, first_block}
- * where tensor i owns blocks [first_block_i, first_block_i + ceil(co*ci*taps / lass_multi_chunk())) and nblocks is their total. */
+ * where tensor i owns blocks [first_block_i, first_block_i + n_i) and nblocks is their total; n_i = lass_pack_blocks(kind, co, ci)
+ * for pack (32 x 32 tiles of the two leading dimensions) and ceil(co*ci*taps / lass_multi_chunk()) for unpack. */
 LASS_API int lass_pack_weights_multi(const long long* table_dev, int nitems, int nblocks, void* stream);
 LASS_API int lass_unpack_grads_multi(const long long* table_dev, int nitems, int nblocks, void* stream);
 LASS_API int lass_multi_chunk(void);
+LASS_API int lass_pack_blocks(int kind, int co, int ci);
 /* Debug: 1 = the shared-memory Stockham iSTFT kernel for every n_fft (default: register-FFT kernel for 1024 / 2048). */
 LASS_API int lass_debug_set_istft_v1(int on);
 

@@ -207,6 +207,7 @@ SIGNATURES.update({
     "lass_pack_weights_multi": (_i, [_v, _i, _i, _v]),
     "lass_unpack_grads_multi": (_i, [_v, _i, _i, _v]),
     "lass_multi_chunk": (_i, []),
+    "lass_pack_blocks": (_i, [_i, _i, _i]),
 })
 SIGNATURES["lass_wgrad_tc"] = SIGNATURES["lass_wgrad"]
 SIGNATURES["lass_stft_multi_fwd"] = (_i, [_v, _i, _i, _i, _i, _v, _v, _v, _v, _v, _v, _i, _i, _v, ctypes.c_size_t, _v])

@@ -346,12 +346,13 @@ class MultiTable:
     """Device table of a multi-tensor pack / unpack launch (8 x int64 per tensor, see include/lass_b200.h); keeps the tensors
     it points to alive."""
 
-    def __init__(self, rows, keep, device):
-        chunk = _cabi.load().lass_multi_chunk()
+    def __init__(self, rows, keep, device, pack):
+        lib = _cabi.load()
+        chunk = lib.lass_multi_chunk()
         flat, block = [], 0
         for a, b, c, kind, co, ci, taps_word in rows:
             flat += [a, b, c, kind, co, ci, taps_word, block]
-            block += (co * ci * (taps_word & 0xffff) + chunk - 1) // chunk
+            block += lib.lass_pack_blocks(kind, co, ci) if pack else (co * ci * (taps_word & 0xffff) + chunk - 1) // chunk
         self.table = torch.tensor(flat, dtype=torch.int64).to(device)
         self.nitems, self.nblocks, self.keep = len(rows), block, keep
 
@@ -369,7 +370,7 @@ def pack_weights_table(items, device):
         co, ci, taps = _dims(w, kind)
         rows.append((_p(w), _p(fwd) or 0, _p(dgrad) or 0, kind, co, ci,
                      taps | ((1 if (fwd is not None and fwd.dtype == torch.float16) else 0) << 16)))
-    return MultiTable(rows, items, device)
+    return MultiTable(rows, items, device, True)
 
 
 def pack_weights(table):
@@ -384,7 +385,7 @@ def unpack_grads_table(items, device):
         _need_cuda(dw, grad)
         co, ci, taps = _dims(grad, kind)
         rows.append((_p(dw), _p(grad), 0, kind, co, ci, taps))
-    return MultiTable(rows, items, device)
+    return MultiTable(rows, items, device, False)
 
 
 def unpack_grads(table):
