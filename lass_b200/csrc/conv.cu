@@ -1251,6 +1251,25 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
     const size_t bw = (size_t)tiles * b_stage_max;
     if (tiles <= kMaxB && 2 * a2 + bw > avail && 2 * a1 + bw <= avail) MT = 1;
   }
+  // Small grids (small batches, the deep levels): a launch whose items cover less than half of the SMs streams its weights
+  // through a handful of CTAs, each at the ~50 B/clk one SM gets from L2 -- 30-47 us for the 384-channel levels at batch 1 against
+  // 1-5 us of tensor work.  Narrower tiles (one m-tile, N down to 32) spread the same weight bytes over up to 8x as many SMs;
+  // the accumulation order of an output element does not depend on the tile, so results stay bit-identical across batch sizes.
+  // Streamed-weight convolutions only (ncols >= 128; resident weights want their single N tile); debug flag 262144 = off.
+  // (not the decoder conv2 launches: their 1x1 shortcut segment over the 2C-channel concat makes an item a chain of
+  //  activation-tile loads that every additional N tile repeats -- measured 33 -> 41 us at batch 1)
+  const bool a_bound = l.nseg == 2 && l.seg[1].cin > l.seg[0].cin;
+  if (!(g_debug_flags & 262144) && up == 1 && !l.after_w && !l.gen_src && l.ncols >= 128 && !a_bound) {
+    const long long sms = device_sm_count();
+    auto n_items = [&](int bn, int mt) {
+      return (long long)l.B * ((l.H + 16 * mt - 1) / (16 * mt)) * ((l.W + TW - 1) / TW) * ((l.ncols + bn - 1) / bn);
+    };
+    while (n_items(BN, MT) * 2 <= sms) {
+      if (MT == 2) MT = 1;
+      else if (BN > 32 && l.ncols % (BN / 2) == 0) BN /= 2;
+      else break;
+    }
+  }
   if (l.after_w && BN < l.ncols) return set_error(LASS_ERR_ARG, "conv: fused after_conv needs ncols <= BN");
   KernelChoice kc;
   if (BN == 32) kc = MT == 2 ? make_choice<32, 2>() : make_choice<32, 1>();

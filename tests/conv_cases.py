@@ -28,7 +28,7 @@ def lrelu_affine(v, scale, shift):  # v (B,C,H,W); scale (C); shift (B,C)
 
 def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0, up=(1, 1), pool=(1, 1),
              want_raw=True, want_act=True, want_pool=False, after=False, bias=False, out_cstride_mult=1, out_coff=0,
-             src_extra=0, seed=0, resid=False, algo=0, gen=False, flags=0):
+             src_extra=0, seed=0, resid=False, algo=0, gen=False, flags=0, shrink=False):
     g = torch.Generator(device="cpu").manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=g)
     taps = 9 if up == (1, 1) else 1
@@ -117,6 +117,9 @@ def run_case(name, B, H, W, cin, cout, src_dtype=torch.bfloat16, shortcut_cin=0,
         outs["feat"] = torch.full((B, 3, H, W), 7.0, dtype=torch.float32, device=dev)
         kw.update(after_w=aw, after_b=ab, feat=outs["feat"])
     # shift tensor must be addressable with a row stride: pass the strided view directly
+    # the cases are small grids: without `shrink` they keep the tile the layer gets at the bench size (flag 262144); the
+    # "shrink_" cases run the narrower small-grid tiles the same shapes get at small batches
+    flags = flags | (0 if shrink else 262144)
     if flags:
         _cabi.check(_cabi.load().lass_debug_set_conv_flags(flags))   # e.g. 4096: no CTA pairs (the single-CTA streamed path)
     try:
@@ -194,6 +197,12 @@ for _name in ("c32_32", "c64_64", "c64_32", "pool32_wide", "resid_pool", "sc_poo
     CASES["respair_" + _name] = dict(CASES[_name], flags=32768)
 CASES["respair_c128_64_long"] = dict(B=4, H=64, W=64, cin=128, cout=64, want_raw=False, flags=32768)
 CASES["respair_c64_32_long"] = dict(B=4, H=128, W=64, cin=64, cout=32, want_raw=False, flags=32768)
+
+# small-grid tiles (one m-tile, N down to 32) for streamed-weight layers: plain, shortcut segment, pooled / sliced outputs, fp16
+for _name in ("c128_128", "c256_384", "c768_384", "c256_256", "sc_pool12", "sc_big", "pair_c384_384_sc", "pair_c512_256", "pair_slice"):
+    CASES["shrink_" + _name] = dict(CASES[_name], shrink=True)
+CASES["shrink_c384_384_b1"] = dict(B=1, H=32, W=8, cin=384, cout=384, shortcut_cin=384, bias=True, shrink=True)
+CASES["shrink_c128_256_pool"] = dict(B=1, H=64, W=32, cin=128, cout=256, shortcut_cin=128, bias=True, want_pool=True, pool=(2, 2), shrink=True)
 
 if __name__ == "__main__":
     pitch = int(sys.argv[1])   # kept for the log name; the halo pitch is fixed at 10 pixels
