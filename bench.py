@@ -299,7 +299,7 @@ def time_forward(model, batch, length, steps, warmup, device, sync_each=False):
 
 def time_train(device, rank, world, steps, warmup, peaks):
     """BASELINE config 4 through TrainEngine.training_step: per step H2D of mixture / condition / target from pinned host
-    memory, train-mode forward, l1_wav, backward, NCCL all-reduce of the flat gradient (two buckets, overlapped with the
+    memory, train-mode forward, l1_wav, backward, NCCL all-reduce of the flat gradient (three buckets, overlapped with the
     encoder's backward), fused AdamW-amsgrad + weight re-pack, loss copied back to the host."""
     import torch.distributed as dist
     from lass_b200 import sharding, train_kernels, training
@@ -388,7 +388,7 @@ def time_train(device, rank, world, steps, warmup, peaks):
         out["allreduce"] = {"bytes": n * 4, "ms_alone": ar_s * 1e3, "algbw_gbs": n * 4 / ar_s / 1e9,
                             "busbw_gbs": n * 4 / ar_s / 1e9 * 2.0 * (world - 1) / world,
                             "exposed_ms_in_step": max(0.0, step_s * 1e3 - sum(ph)),
-                            "note": "NCCL sum over NVLink of the flat fp32 gradient (two buckets in the step: decoder bucket "
+                            "note": "NCCL sum over NVLink of the flat fp32 gradient (three buckets in the step: the decoder and deep-encoder buckets "
                                     "overlaps the encoder backward); 1/world folded into the AdamW kernel"}
     del eng, model
     torch.cuda.empty_cache()

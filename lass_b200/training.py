@@ -17,7 +17,7 @@ owns (NHWC, raw conv outputs fp16, activated tensors and gradients bf16, statist
 * BatchNorm batch statistics, activation, backward reductions: memory-bound kernels (``lass_bn_*``);
 * spectral ends: K1 / K5 forward, ``lass_istft_bwd`` (the adjoint of the ISTFT is an STFT of the window-sum-normalised
   gradient) + ``lass_mask_bwd``;
-* parameters, gradients and optimizer state live in flat fp32 buffers: ONE (two-bucket) NCCL all-reduce, one fused
+* parameters, gradients and optimizer state live in flat fp32 buffers: ONE (three-bucket) NCCL all-reduce, one fused
   AdamW-amsgrad launch, then the 16-bit kernel layouts of the conv weights are refreshed.
 
 All arithmetic is in ``kernels`` (default: ``lass_b200.train_kernels``, the C ABI; no CPU fallback).
@@ -46,6 +46,9 @@ DEC = ((384, 384, (1, 2)), (384, 384, (2, 2)), (384, 256, (2, 2)), (256, 128, (2
        (64, 32, (2, 2)))                                            # cin, cout, upsample (models/resunet.py:371-418)
 BN_MOMENTUM = 0.01
 BN_EPS = 1e-5
+# all-reduce bucket B1 = encoder blocks 6 .. _B1_LAST_LEVEL (10.8 of the encoder's 11.7 M parameters): reduced while the high-resolution
+# blocks' backward (most of the encoder's time) still runs
+_B1_LAST_LEVEL = 4
 
 
 def film_row_offsets():
@@ -118,8 +121,11 @@ class TrainEngine:
             add("dec%d.bn1.weight" % j, blk.bn1.weight)
             add("dec%d.bn1.bias" % j, blk.bn1.bias)
         n_a = len(entries)
-        # bucket B: encoder, pre_conv, bn0, FiLM
+        # bucket B1: the deep encoder blocks (most of the encoder's bytes, final early in its backward); B2: the rest, pre_conv, bn0, FiLM
+        n_b1 = None
         for k in reversed(range(7)):
+            if k == _B1_LAST_LEVEL - 1:
+                n_b1 = len(entries)
             add_block("enc%d." % k, encb[k])
         add("pre.w", base.pre_conv.weight)
         add("pre.b", base.pre_conv.bias)
@@ -156,6 +162,7 @@ class TrainEngine:
                 self.index[name] = (off, p)
                 self.params.append(p)
         self.bucket_a_end = offs[n_a]
+        self.bucket_b1_end = offs[n_b1]
         self.live_end = offs[n_live] if n_live < len(entries) else total
         self.film_w_off, self.film_b_off = offs[film_w_first], offs[film_b_first]
         assert offs[film_b_first] - offs[film_w_first] == self.J * self.K, "FiLM weights must be contiguous"
@@ -247,7 +254,7 @@ class TrainEngine:
         self._pack_table = k.pack_weights_table([(param.data, kind, fwd, dgrad) for (param, kind, fwd, dgrad) in self.w.values()
                                                  if param is not None], dev)
         self.Gp = torch.zeros_like(self.G)
-        items_a, items_b = [], []
+        items = ([], [], [])
         for name, (off, p) in self.index.items():
             if p.dim() != 4 or name.startswith(("dead.", "after.", "pre.")):
                 continue
@@ -255,8 +262,9 @@ class TrainEngine:
             if kind == k.KIND_CONV and p.shape[2] * p.shape[3] == 1:
                 continue                                           # (co, ci, 1, 1) IS the packed layout: wgrad writes G directly
             n = p.numel()
-            (items_a if off < self.bucket_a_end else items_b).append((self.Gp[off:off + n], kind, self.G[off:off + n].view(p.shape)))
-        self._unpack_a, self._unpack_b = k.unpack_grads_table(items_a, dev), k.unpack_grads_table(items_b, dev)
+            bucket = 0 if off < self.bucket_a_end else (1 if off < self.bucket_b1_end else 2)
+            items[bucket].append((self.Gp[off:off + n], kind, self.G[off:off + n].view(p.shape)))
+        self._unpack_a, self._unpack_b1, self._unpack_b2 = (k.unpack_grads_table(it, dev) for it in items)
 
     @_on_device
     def refresh_weights(self):
@@ -523,13 +531,17 @@ class TrainEngine:
             self._block_bwd(ws, "enc%d." % kk, (2 * kk, 2 * kk + 1), ws.g_y[kk], ws.x_raw[kk], ws.x_act[kk], ws.h_raw[kk],
                             ws.a2[kk], ws.g_a2[kk], ws.g_h[kk], ws.g_xact[kk], ws.g_sc_e[kk], ws.g_xraw[kk], cin, cout,
                             cin != cout, "enc%d." % kk)
-        k.unpack_grads(self._unpack_b)
+            if kk == _B1_LAST_LEVEL:
+                k.unpack_grads(self._unpack_b1)
+                if async_allreduce is not None:
+                    async_allreduce(self.bucket_a_end, self.bucket_b1_end)
+        k.unpack_grads(self._unpack_b2)
         k.pre_bwd(ws.g_xraw[0], ws.mag, self.bnp0, base.pre_conv.weight.data.view(32), self.g("pre.w").view(32),
                   self.g("pre.b"), self.g("bn0.weight"), self.g("bn0.bias"))
         k.film_bwd(ws.dbeta, ws.cond, self.G[self.film_w_off:self.film_w_off + self.J * self.K].view(self.J, self.K),
                    self.G[self.film_b_off:self.film_b_off + self.J])
         if async_allreduce is not None:
-            async_allreduce(self.bucket_a_end, self.live_end)
+            async_allreduce(self.bucket_b1_end, self.live_end)
 
     # ------------------------------------------------------------------ fused step (loss + backward + all-reduce + AdamW)
     @_on_device
