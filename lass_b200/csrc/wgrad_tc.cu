@@ -14,6 +14,12 @@
 // rules are pinned on hardware by tests/test_gpu_umma_probe.py::test_mn_major_descriptors.  So a 32-channel layer still
 // issues full M = 128 MMAs, and no operand is ever transposed or copied.
 //
+// NB = 128 (co % 128 == 0, 64-channel ci chunks): an MN-major operand is read from shared memory at ~53 B/clk, so the MMA time
+// follows the operand BYTES -- per 128 x 64 x 16 MMA 4 KiB of X + 2 KiB of dY (~115 cycles), per 128 x 128 x 16 MMA 4 + 4 KiB
+// (~150 cycles) for twice the work.  Five 128-column accumulators do not fit TMEM's 512 columns, so the five MMA groups of the
+// 3 x 3 kernel are split over TWO sets of CTAs (groups 0-2 / 3-4, pixel ranges divided 3 : 2 so both finish together); the dY
+// tile arrives as two 64-channel boxes one atom (16 KiB) apart, which the N-side descriptor hops with its leading byte offset.
+//
 // One CTA = one (CIW-channel chunk of ci, NB-channel tile of co) output tile over a contiguous range of pixel tiles
 // (split-K; few weights + many pixels -> many ranges): all 3 x 3 taps accumulate in TMEM (5 or 3 accumulators of NB columns),
 // then the epilogue adds the valid rows to dW with fp32 red.global.  Warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 epilogue.
@@ -24,7 +30,6 @@ namespace lass {
 namespace {
 
 constexpr int kThreads = 192;
-constexpr int kStages = 4;
 constexpr int kTH = 16, kTW = 8, kHaloH = 18, kHaloW = 10;
 
 struct WgradTcParams {
@@ -33,22 +38,27 @@ struct WgradTcParams {
   int co, ci, taps, x_fp16;
   int tiles_h, tiles_w, num_pix_tiles;
   int n_ci_chunks, n_co_tiles, splits;
+  int splits0;       // NB = 128, 3 x 3: CTAs [0, splits0) of an output tile run MMA groups 0-2, the rest groups 3-4 (else == splits)
 };
 
 template <int CIW, int NB>
 __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_constant__ WgradTcParams p) {
-  constexpr int RA = CIW * 2, RB = NB * 2;                       // bytes per pixel row of the X / dY tiles
-  constexpr uint32_t SWA = CIW == 64 ? kSwizzle128B : kSwizzle64B, SWB = NB == 64 ? kSwizzle128B : kSwizzle64B;
-  constexpr int XBYTES = kHaloH * kHaloW * RA, YBYTES = kTH * kTW * RB;
+  constexpr int NBOX = NB == 128 ? 64 : NB;                      // channels per dY TMA box (one 128-byte swizzle atom at most)
+  constexpr int RA = CIW * 2, RB = NBOX * 2;                     // bytes per pixel row of the X / dY tiles
+  constexpr uint32_t SWA = CIW == 64 ? kSwizzle128B : kSwizzle64B, SWB = NBOX == 64 ? kSwizzle128B : kSwizzle64B;
+  constexpr int YBOX = kTH * kTW * RB;                           // one dY box (the N = 128 tile is two of them, YBOX apart)
+  constexpr int XBYTES = kHaloH * kHaloW * RA, YBYTES = (NB / NBOX) * YBOX;
   constexpr int XALLOC = (XBYTES + 1023) & ~1023;
   constexpr int STAGE = XALLOC + YBYTES;
+  constexpr int kStages = NB == 128 ? 3 : 4;
   constexpr int TPM = 128 / CIW;                                 // taps per MMA (2 or 4)
   // MMA groups of a 3x3 kernel.  The nine taps sit at halo-row offsets {0,1,2, 10,11,12, 20,21,22}; an MMA's M atoms are LBO
   // bytes apart, so   CIW = 32: one MMA per kernel row = taps (ky,0..2) + one discarded atom (LBO = 1 row);
   //                   CIW = 64: FIVE MMAs (0,1) (2,10) (11,12) (20,21) (22,-): the pair (2,10) spans two kernel rows with
   //                             LBO = 8 rows -- 5 instead of 6 MMAs per k-step.  Accumulator a, atom h holds tap TPM a + h.
   constexpr int NACC = CIW == 64 ? 5 : 3;
-  constexpr int ACC_COLS = NACC * NB;
+  constexpr int NACC_CTA = NB == 128 ? 3 : NACC;                  // accumulators one CTA holds
+  constexpr int ACC_COLS = NACC_CTA * NB;
   constexpr int TMEM_COLS = ACC_COLS <= 128 ? 128 : (ACC_COLS <= 256 ? 256 : 512);
   static_assert(ACC_COLS <= 512, "accumulators exceed TMEM");
 
@@ -62,13 +72,25 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int item = blockIdx.x;
-  const int split = item % p.splits;
+  int split = item % p.splits;
   item /= p.splits;
   const int co_tile = item % p.n_co_tiles, ci_chunk = item / p.n_co_tiles;
-  const int t_begin = (int)((long long)p.num_pix_tiles * split / p.splits);
-  const int t_end = (int)((long long)p.num_pix_tiles * (split + 1) / p.splits);
   const bool one_tap = p.taps == 1;
-  const int nacc = one_tap ? 1 : NACC;
+  // MMA groups [acc0, acc0 + nacc) of this CTA and its share of the pixel tiles
+  int acc0 = 0, nacc = one_tap ? 1 : NACC, nsplit = p.splits;
+  if (p.splits0 < p.splits) {
+    if (split < p.splits0) {
+      nacc = 3;
+      nsplit = p.splits0;
+    } else {
+      acc0 = 3;
+      nacc = NACC - 3;
+      split -= p.splits0;
+      nsplit = p.splits - p.splits0;
+    }
+  }
+  const int t_begin = (int)((long long)p.num_pix_tiles * split / nsplit);
+  const int t_end = (int)((long long)p.num_pix_tiles * (split + 1) / nsplit);
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmX);
@@ -103,6 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         mbar_arrive_expect_tx(&full_bar[s], XBYTES + YBYTES);
         tma_load_4d(st, &p.tmX, &full_bar[s], ci_chunk * CIW, tw * kTW - 1, th * kTH - 1, b);
         tma_load_4d(st + XALLOC, &p.tmY, &full_bar[s], co_tile * NB, tw * kTW, th * kTH, b);
+        if (NB == 128) tma_load_4d(st + XALLOC + YBOX, &p.tmY, &full_bar[s], co_tile * NB + NBOX, tw * kTW, th * kTH, b);
       }
     }
   } else if (warp == 1) {
@@ -114,7 +137,7 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
         mbar_wait(p.x_fp16 ? &conv_bar[s] : &full_bar[s], (it / kStages) & 1);
         tc_fence_after_sync();
         const uint32_t xs = smem_u32(smem + s * STAGE), ys = xs + XALLOC;
-        for (int a = 0; a < nacc; ++a) {
+        for (int a = acc0; a < acc0 + nacc; ++a) {
           int row0, lbo_rows = 1;                  // halo row of the first atom, atom distance in rows
           if (one_tap) {
             row0 = kHaloW + 1;                     // the centre tap (the second atom is discarded)
@@ -124,11 +147,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
           } else {
             row0 = a * kHaloW;
           }
-          const uint32_t acc = tmem_base + (uint32_t)(a * NB);
+          const uint32_t acc = tmem_base + (uint32_t)((a - acc0) * NB);
 #pragma unroll
           for (int ks = 0; ks < kTH / 2; ++ks) {
             const uint64_t da = make_smem_desc_mn(xs + (uint32_t)((2 * ks * kHaloW + row0) * RA), lbo_rows * RA, kHaloW * RA, SWA);
-            const uint64_t db = make_smem_desc_mn(ys + (uint32_t)(ks * 2 * kTW * RB), 0, kTW * RB, SWB);
+            const uint64_t db = make_smem_desc_mn(ys + (uint32_t)(ks * 2 * kTW * RB), NB == 128 ? YBOX : 0, kTW * RB, SWB);
             umma_f16(acc, da, db, idesc, (it | (uint32_t)ks) != 0u);
           }
         }
@@ -171,11 +194,11 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
     const int h = row / CIW, cl = row % CIW;       // atom of the MMA's M dimension, channel within the chunk
     const int ci = ci_chunk * CIW + cl;
     if (t_begin < t_end) {
-      for (int a = 0; a < nacc; ++a) {
-        // tap held by (accumulator a, atom h); CIW = 32: kernel row a, dx = h (h = 3 is the discarded atom)
+      for (int a = acc0; a < acc0 + nacc; ++a) {
+        // tap held by (MMA group a, atom h); CIW = 32: kernel row a, dx = h (h = 3 is the discarded atom)
         const int tap = one_tap ? (h == 0 ? 0 : 9) : (CIW == 64 ? TPM * a + h : (h < 3 ? 3 * a + h : 9));
         const bool valid = tap < p.taps;
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)(a * NB);
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)((a - acc0) * NB);
 #pragma unroll 1
         for (int c0 = 0; c0 < NB; c0 += 32) {
           if (!valid) continue;                    // (warp-uniform: a warp's 32 lanes lie in one atom)
@@ -203,6 +226,7 @@ template <int CIW, int NB>
 size_t smem_bytes() {
   constexpr int RA = CIW * 2, RB = NB * 2;
   constexpr int XALLOC = (kHaloH * kHaloW * RA + 1023) & ~1023;
+  constexpr int kStages = NB == 128 ? 3 : 4;
   return 1024 + (size_t)kStages * (XALLOC + kTH * kTW * RB) + 1024 + 512;
 }
 
@@ -219,7 +243,8 @@ extern "C" int lass_wgrad_tc(const void* dy, int dy_cstride, int dy_coff, int co
     return set_error(LASS_ERR_ARG, "lass_wgrad_tc: bad shape co=%d ci=%d taps=%d B=%d H=%d W=%d", co, ci, taps, B, H, W);
   cudaStream_t s = (cudaStream_t)stream_v;
   const int ciw = ci % 64 == 0 ? 64 : 32;
-  const int nb = co % 64 == 0 ? 64 : 32;
+  const int nb = (co % 128 == 0 && ciw == 64) ? 128 : (co % 64 == 0 ? 64 : 32);
+  const int nbox = nb == 128 ? 64 : nb;
   WgradTcParams p;
   int e;
   {
@@ -233,8 +258,8 @@ extern "C" int lass_wgrad_tc(const void* dy, int dy_cstride, int dy_coff, int co
     const char* base = reinterpret_cast<const char*>(dy) + (size_t)dy_coff * 2;
     uint64_t dims[4] = {(uint64_t)co, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)dy_cstride * 2, (uint64_t)dy_cstride * 2 * W, (uint64_t)dy_cstride * 2 * W * H};
-    uint32_t box[4] = {(uint32_t)nb, (uint32_t)kTW, (uint32_t)kTH, 1};
-    if ((e = make_tensor_map(&p.tmY, base, 2, 4, dims, strides, box, nb == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))) return e;
+    uint32_t box[4] = {(uint32_t)nbox, (uint32_t)kTW, (uint32_t)kTH, 1};
+    if ((e = make_tensor_map(&p.tmY, base, 2, 4, dims, strides, box, nbox == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B))) return e;
   }
   p.dw = dw;
   p.co = co;
@@ -253,9 +278,24 @@ extern "C" int lass_wgrad_tc(const void* dy, int dy_cstride, int dy_coff, int co
   if (splits > p.num_pix_tiles) splits = p.num_pix_tiles;
   if (splits < 1) splits = 1;
   p.splits = splits;
+  p.splits0 = splits;
+  if (nb == 128 && taps == 9) {
+    // two CTA sets per output tile (MMA groups 0-2 / 3-4): at least one CTA each, pixel ranges 3 : 2
+    if (splits < 2) splits = 2;
+    if (splits > 2 * p.num_pix_tiles) splits = 2 * p.num_pix_tiles;
+    if (splits < 2) return set_error(LASS_ERR_ARG, "lass_wgrad_tc: empty problem");
+    int s0 = (3 * splits + 2) / 5;
+    if (s0 < 1) s0 = 1;
+    if (s0 > splits - 1) s0 = splits - 1;
+    if (s0 > p.num_pix_tiles) s0 = p.num_pix_tiles;
+    if (splits - s0 > p.num_pix_tiles) splits = s0 + p.num_pix_tiles;
+    p.splits = splits;
+    p.splits0 = s0;
+  }
   WgradTcFn fn;
   size_t smem;
-  if (ciw == 64 && nb == 64) { fn = wgrad_tc_kernel<64, 64>; smem = smem_bytes<64, 64>(); }
+  if (nb == 128) { fn = wgrad_tc_kernel<64, 128>; smem = smem_bytes<64, 128>(); }
+  else if (ciw == 64 && nb == 64) { fn = wgrad_tc_kernel<64, 64>; smem = smem_bytes<64, 64>(); }
   else if (ciw == 64) { fn = wgrad_tc_kernel<64, 32>; smem = smem_bytes<64, 32>(); }
   else if (nb == 64) { fn = wgrad_tc_kernel<32, 64>; smem = smem_bytes<32, 64>(); }
   else { fn = wgrad_tc_kernel<32, 32>; smem = smem_bytes<32, 32>(); }
