@@ -324,22 +324,45 @@ struct PrepParams {
   __nv_bfloat16* xlo[kMaxProblems];
   int Lp[kMaxProblems], half[kMaxProblems];
 };
-__global__ void stft_prep_kernel(const float* __restrict__ wave, const PrepParams pp, int L) {
+// Reflect padding + bf16 hi / lo split of the waveform; a thread owns 8 consecutive padded samples (Lp, n_fft / 2 are multiples
+// of 8): two 16-byte loads in the interior (clip length a multiple of 4), one 16-byte store per output array.
+__global__ void __launch_bounds__(256) stft_prep_kernel(const float* __restrict__ wave, const PrepParams pp, int L, int vec_ok) {
   const int g = blockIdx.z;
   const int b = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
   const int Lp = pp.Lp[g], half = pp.half[g];
-  if (i >= Lp) return;
-  float v = 0.0f;
-  int src = i - half;
-  if (i < L + 2 * half) {
-    if (src < 0) src = -src;
-    if (src >= L) src = 2 * (L - 1) - src;
-    v = wave[(size_t)b * L + src];
+  if (i0 >= Lp) return;
+  const float* wb = wave + (size_t)b * L;
+  float v[8];
+  const int s0 = i0 - half;
+  if (vec_ok && s0 >= 0 && s0 + 8 <= L) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(wb + s0)), c = __ldg(reinterpret_cast<const float4*>(wb + s0) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = c.x; v[5] = c.y; v[6] = c.z; v[7] = c.w;
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + j;
+      v[j] = 0.0f;
+      if (i < L + 2 * half) {
+        int src = i - half;
+        if (src < 0) src = -src;
+        if (src >= L) src = 2 * (L - 1) - src;
+        v[j] = __ldg(wb + src);
+      }
+    }
   }
-  const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-  pp.xhi[g][(size_t)b * Lp + i] = hi;
-  pp.xlo[g][(size_t)b * Lp + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]), h1 = __float2bfloat16_rn(v[2 * j + 1]);
+    const __nv_bfloat162 hh = __halves2bfloat162(h0, h1);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(v[2 * j] - __bfloat162float(h0), v[2 * j + 1] - __bfloat162float(h1));
+    hi[j] = *reinterpret_cast<const uint32_t*>(&hh);
+    lo[j] = *reinterpret_cast<const uint32_t*>(&ll);
+  }
+  *reinterpret_cast<uint4*>(pp.xhi[g] + (size_t)b * Lp + i0) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(pp.xlo[g] + (size_t)b * Lp + i0) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // Adjoint of torchlibrosa ISTFT.forward's overlap-add: the waveform gradient, zero-extended to the frame grid and divided by
@@ -476,12 +499,13 @@ int launch_stft_multi(const float* wave, int B, int L, int hop, int nres, const 
   for (int g = nres; g < kMaxProblems; ++g) p.pr[g] = p.pr[0];
   {
     dim3 grid((unsigned)((max_lp + 255) / 256), (unsigned)B, (unsigned)nres);
+    const dim3 grid8((unsigned)((max_lp / 8 + 255) / 256), (unsigned)B, (unsigned)nres);       // stft_prep: 8 samples per thread
     if (adjoint_window) {
       if (nres != 1) return LASS_ERR_ARG;
       istft_bwd_prep_kernel<<<dim3(grid.x, grid.y), 256, 0, stream>>>(wave, adjoint_window, pp.xhi[0], pp.xlo[0], L, pp.Lp[0], pp.half[0],
                                                                      n_ffts[0], hop, T);
     } else {
-      stft_prep_kernel<<<grid, 256, 0, stream>>>(wave, pp, L);
+      stft_prep_kernel<<<grid8, 256, 0, stream>>>(wave, pp, L, (L % 4 == 0 && reinterpret_cast<uintptr_t>(wave) % 16 == 0) ? 1 : 0);
     }
   }
   p.nprob = nres;
