@@ -506,20 +506,30 @@ __global__ void __launch_bounds__(kRedThreads) channel_sum_kernel(const void* __
 __global__ void __launch_bounds__(256) pre_fwd_kernel(const float* __restrict__ mag, int B, int T, int F, int Tp, int Fp,
                                                       const float* __restrict__ bnp0, const float* __restrict__ pre_w,
                                                       const float* __restrict__ pre_b, void* __restrict__ x0) {
-  const long long nvec = (long long)B * Tp * Fp * 4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
-    const int cv = (int)(i & 3);
-    const long long p = i >> 2;
-    const int w = (int)(p % Fp);
-    const long long t = p / Fp;
-    const int h = (int)(t % Tp), b = (int)(t / Tp);
-    float xbn = 0.0f;
-    if (h < T) xbn = fmaf(__ldg(bnp0 + w), __ldg(mag + ((size_t)b * T + h) * F + w), __ldg(bnp0 + F + w));
-    const V8 wv = ldf8(pre_w + cv * 8), bv = ldf8(pre_b + cv * 8);
-    V8 r;
+  // grid.y = output row (b, h); a thread keeps its 8-channel vector of the pre_conv weights, walks the row's pixels
+  const int row = blockIdx.y, b = row / Tp, h = row - b * Tp;
+  const int cv = threadIdx.x & 3;
+  const V8 wv = ldf8(pre_w + cv * 8), bv = ldf8(pre_b + cv * 8);
+  const float* mrow = mag + ((size_t)b * T + h) * F;
+  const bool live = h < T;                                   // zero time padding AFTER bn0 (models/resunet.py:548)
+  const int stride = gridDim.x * 64;
+  for (int w0 = blockIdx.x * 64 + (threadIdx.x >> 2); w0 < Fp; w0 += 4 * stride) {
+    float xb[4];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) r.v[k] = fmaf(wv.v[k], xbn, bv.v[k]);
-    store8(x0, (size_t)p * 32 + cv * 8, 1, r);
+    for (int u = 0; u < 4; ++u) {
+      const int w = w0 + u * stride;
+      xb[u] = (live && w < Fp) ? fmaf(__ldg(bnp0 + w), __ldg(mrow + w), __ldg(bnp0 + F + w)) : 0.0f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int w = w0 + u * stride;
+      if (w < Fp) {
+        V8 r;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r.v[k] = fmaf(wv.v[k], xb[u], bv.v[k]);
+        store8(x0, ((size_t)row * Fp + w) * 32 + cv * 8, 1, r);
+      }
+    }
   }
 }
 
@@ -612,23 +622,40 @@ __global__ void __launch_bounds__(256) after_bwd_kernel(const float* __restrict_
   for (int k = 0; k < 3; ++k)
 #pragma unroll
     for (int i = 0; i < 8; ++i) aw[k][i] = 0.0f;
-  const long long total = (long long)B * npix;
-  for (long long p = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); p < total; p += (long long)gridDim.x * 64) {
-    const long long b = p / npix, q = p - b * npix;
-    float df[3];
+  // grid.y = clip; two pixels per thread and step so that eight loads are in flight
+  const int b = blockIdx.y;
+  const float* dfb = dfeat + (size_t)b * 3 * npix;
+  const size_t pix0 = (size_t)b * npix;
+  const long long stride = (long long)gridDim.x * 64;
+  for (long long q0 = (long long)blockIdx.x * 64 + (threadIdx.x >> 2); q0 < npix; q0 += 2 * stride) {
+    float df[2][3];
+    uint4 yq[2];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) df[k] = __ldg(dfeat + ((size_t)b * 3 + k) * npix + q);
-    const V8 yv = load8(y, (size_t)p * 32 + cv * 8, 1);
-    V8 r;
+    for (int u = 0; u < 2; ++u) {
+      const long long q = q0 + u * stride;
+      if (q < npix) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      r.v[i] = df[0] * w[0].v[i] + df[1] * w[1].v[i] + df[2] * w[2].v[i];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) aw[k][i] = fmaf(df[k], yv.v[i], aw[k][i]);
+        for (int k = 0; k < 3; ++k) df[u][k] = __ldg(dfb + (size_t)k * npix + q);
+        yq[u] = loadq(y, (pix0 + q) * 32 + cv * 8);
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) ab[k] += df[k];
-    store8(dy, (size_t)p * 32 + cv * 8, 0, r);
+    for (int u = 0; u < 2; ++u) {
+      const long long q = q0 + u * stride;
+      if (q < npix) {
+        const V8 yv = unpack8(yq[u], 1);
+        V8 r;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          r.v[i] = df[u][0] * w[0].v[i] + df[u][1] * w[1].v[i] + df[u][2] * w[2].v[i];
+#pragma unroll
+          for (int k = 0; k < 3; ++k) aw[k][i] = fmaf(df[u][k], yv.v[i], aw[k][i]);
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ab[k] += df[u][k];
+        store8(dy, (pix0 + q) * 32 + cv * 8, 0, r);
+      }
+    }
   }
   // reduce over the 8 pixels of a warp (lanes with equal cv), then over warps
 #pragma unroll
@@ -1112,8 +1139,9 @@ int lass_channel_sum(const void* x, long long npix, int C, int cstride, int coff
 int lass_pre_fwd(const float* mag, int B, int T, int F, int Tp, int Fp, const float* bnp0, const float* pre_w, const float* pre_b, void* x0,
                  void* stream_v) {
   if (!mag || !bnp0 || !pre_w || !pre_b || !x0 || B <= 0 || T <= 0 || Tp < T || Fp <= 0 || Fp > F) return set_error(LASS_ERR_ARG, "lass_pre_fwd: bad argument");
-  const long long nvec = (long long)B * Tp * Fp * 4;
-  pre_fwd_kernel<<<grid_for(nvec, 256), 256, 0, (cudaStream_t)stream_v>>>(mag, B, T, F, Tp, Fp, bnp0, pre_w, pre_b, x0);
+  if ((long long)B * Tp > 65535) return set_error(LASS_ERR_ARG, "lass_pre_fwd: more than 65535 image rows (B * Tp)");
+  pre_fwd_kernel<<<dim3((unsigned)grid_for(Fp, 64 * 4, 16), (unsigned)(B * Tp)), 256, 0, (cudaStream_t)stream_v>>>(mag, B, T, F, Tp, Fp, bnp0, pre_w,
+                                                                                                         pre_b, x0);
   LASS_LAUNCH_CHECK("pre_fwd launch");
 }
 
@@ -1136,7 +1164,7 @@ int lass_after_bwd(const float* dfeat, const void* y, const float* after_w, void
   cudaStream_t s = (cudaStream_t)stream_v;
   cudaMemsetAsync(dw, 0, 96 * sizeof(float), s);
   cudaMemsetAsync(db, 0, 3 * sizeof(float), s);
-  after_bwd_kernel<<<grid_for((long long)B * npix, 64, 148 * 4), 256, 0, s>>>(dfeat, y, after_w, dy, dw, db, B, npix);
+  after_bwd_kernel<<<dim3((unsigned)grid_for(npix, 64 * 2, (148 * 4 + B - 1) / B), (unsigned)B), 256, 0, s>>>(dfeat, y, after_w, dy, dw, db, B, npix);
   LASS_LAUNCH_CHECK("after_bwd launch");
 }
 
