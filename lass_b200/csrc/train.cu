@@ -784,20 +784,40 @@ __global__ void __launch_bounds__(128) film_bwd_kernel(const float* __restrict__
 }
 
 // Same operation order as torch.optim.adamw's single-tensor path (see oracle/train_oracle.py::adamw_amsgrad_step).
+__device__ __forceinline__ void adamw_one(float& pi, float gi, float& mi, float& vi, float& vm, float decay, float one_minus_b1, float b2,
+                                          float one_minus_b2, float bc2_sqrt, float eps, float neg_step_size, float grad_scale) {
+  gi = __fmul_rn(gi, grad_scale);
+  pi = __fmul_rn(pi, decay);
+  mi = __fadd_rn(mi, __fmul_rn(one_minus_b1, __fsub_rn(gi, mi)));                         // lerp_
+  vi = __fmul_rn(vi, b2);
+  vi = __fadd_rn(vi, __fmul_rn(__fmul_rn(one_minus_b2, gi), gi));                         // addcmul_
+  vm = fmaxf(vm, vi);
+  const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vm), bc2_sqrt), eps);
+  pi = __fadd_rn(pi, __fmul_rn(neg_step_size, __fdiv_rn(mi, denom)));                     // addcdiv_
+}
+
+// n4 float4 groups (16-byte loads / stores), then the scalar tail
 __global__ void __launch_bounds__(256) adamw_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                            float* __restrict__ v, float* __restrict__ vmax, long long n, float decay,
-                                                            float one_minus_b1, float b2, float one_minus_b2, float bc2_sqrt, float eps,
-                                                            float neg_step_size, float grad_scale) {
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = __fmul_rn(g[i], grad_scale);
-    float pi = __fmul_rn(p[i], decay);
-    float mi = m[i];
-    mi = __fadd_rn(mi, __fmul_rn(one_minus_b1, __fsub_rn(gi, mi)));                         // lerp_
-    float vi = __fmul_rn(v[i], b2);
-    vi = __fadd_rn(vi, __fmul_rn(__fmul_rn(one_minus_b2, gi), gi));                         // addcmul_
-    const float vm = fmaxf(vmax[i], vi);
-    const float denom = __fadd_rn(__fdiv_rn(__fsqrt_rn(vm), bc2_sqrt), eps);
-    pi = __fadd_rn(pi, __fmul_rn(neg_step_size, __fdiv_rn(mi, denom)));                     // addcdiv_
+                                                            float* __restrict__ v, float* __restrict__ vmax, long long n, long long n4,
+                                                            float decay, float one_minus_b1, float b2, float one_minus_b2, float bc2_sqrt,
+                                                            float eps, float neg_step_size, float grad_scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = t0; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i],
+           xv = reinterpret_cast<float4*>(vmax)[i];
+    const float4 gv = reinterpret_cast<const float4*>(g)[i];
+    adamw_one(pv.x, gv.x, mv.x, vv.x, xv.x, decay, one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step_size, grad_scale);
+    adamw_one(pv.y, gv.y, mv.y, vv.y, xv.y, decay, one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step_size, grad_scale);
+    adamw_one(pv.z, gv.z, mv.z, vv.z, xv.z, decay, one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step_size, grad_scale);
+    adamw_one(pv.w, gv.w, mv.w, vv.w, xv.w, decay, one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step_size, grad_scale);
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    reinterpret_cast<float4*>(vmax)[i] = xv;
+  }
+  for (long long i = 4 * n4 + t0; i < n; i += stride) {
+    float pi = p[i], mi = m[i], vi = v[i], vm = vmax[i];
+    adamw_one(pi, g[i], mi, vi, vm, decay, one_minus_b1, b2, one_minus_b2, bc2_sqrt, eps, neg_step_size, grad_scale);
     p[i] = pi;
     m[i] = mi;
     v[i] = vi;
@@ -1197,7 +1217,10 @@ int lass_adamw_amsgrad(float* p, const float* g, float* m, float* v, float* vmax
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   const float decay = (float)(1.0 - (double)lr * (double)weight_decay);
   const float neg_step = (float)(-((double)lr / bc1));
-  adamw_amsgrad_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream_v>>>(p, g, m, v, vmax, n, decay, (float)(1.0 - (double)beta1), beta2,
+  const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                         reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(vmax)) & 15) == 0;
+  const long long n4 = aligned ? n / 4 : 0;
+  adamw_amsgrad_kernel<<<grid_for(n4 > 0 ? n4 : n, 256), 256, 0, (cudaStream_t)stream_v>>>(p, g, m, v, vmax, n, n4, decay, (float)(1.0 - (double)beta1), beta2,
                                                                              (float)(1.0 - (double)beta2), (float)sqrt(bc2), eps, neg_step,
                                                                              grad_scale);
   LASS_LAUNCH_CHECK("adamw launch");
