@@ -404,12 +404,13 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const void* __restrict__ 
                                                        int s_coff, void* __restrict__ dy, int B, int H, int W, int C, int ph, int pw) {
   constexpr int kU = 4;
   const int CV = C / 8;
-  const int row = blockIdx.y, b = row / H, h = row - b * H;
   const float inv = 1.0f / (float)(ph * pw);
   const int Hp = H / ph, Wp = W / pw;
+  const int nv = W * CV, stride = gridDim.x * 256;
+  for (int row = blockIdx.y; row < B * H; row += gridDim.y) {
+  const int b = row / H, h = row - b * H;
   const size_t prow = ((size_t)b * Hp + h / ph) * Wp;      // first pooled pixel of the source row
   const size_t orow = (size_t)row * W;                      // first output pixel of this row
-  const int nv = W * CV, stride = gridDim.x * 256;
   for (int i0 = blockIdx.x * 256 + threadIdx.x; i0 < nv; i0 += kU * stride) {
     uint4 dp[kU], ds[kU];
 #pragma unroll
@@ -438,6 +439,7 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const void* __restrict__ 
       }
     }
   }
+  }
 }
 
 // dst (B, H, W, uh*uw*C)[(dy*uw + dx)*C + c] = src (B, H*uh, W*uw, cstride)[h*uh + dy, w*uw + dx, coff + c]   (16-byte copies)
@@ -445,9 +447,10 @@ __global__ void __launch_bounds__(256) unshuffle_kernel(const uint16_t* __restri
                                                         int B, int H, int W, int C, int uh, int uw) {
   constexpr int kU = 4;
   const int CV = C / 8, G = uh * uw;
-  const int row = blockIdx.y, b = row / H, h = row - b * H;      // destination row
   const int nv = W * G * CV, stride = gridDim.x * 256;
   const size_t Ws = (size_t)W * uw;
+  for (int row = blockIdx.y; row < B * H; row += gridDim.y) {      // destination rows
+  const int b = row / H, h = row - b * H;
   const size_t srow = ((size_t)b * H + h) * uh * Ws;              // first source pixel of source row h * uh
   uint4* drow = reinterpret_cast<uint4*>(dst) + (size_t)row * nv;
   for (int i0 = blockIdx.x * 256 + threadIdx.x; i0 < nv; i0 += kU * stride) {
@@ -467,6 +470,7 @@ __global__ void __launch_bounds__(256) unshuffle_kernel(const uint16_t* __restri
       const int i = i0 + u * stride;
       if (i < nv) drow[i] = q[u];
     }
+  }
   }
 }
 
@@ -507,12 +511,13 @@ __global__ void __launch_bounds__(256) pre_fwd_kernel(const float* __restrict__ 
                                                       const float* __restrict__ bnp0, const float* __restrict__ pre_w,
                                                       const float* __restrict__ pre_b, void* __restrict__ x0) {
   // grid.y = output row (b, h); a thread keeps its 8-channel vector of the pre_conv weights, walks the row's pixels
-  const int row = blockIdx.y, b = row / Tp, h = row - b * Tp;
   const int cv = threadIdx.x & 3;
   const V8 wv = ldf8(pre_w + cv * 8), bv = ldf8(pre_b + cv * 8);
+  const int stride = gridDim.x * 64;
+  for (int row = blockIdx.y; row < B * Tp; row += gridDim.y) {
+  const int b = row / Tp, h = row - b * Tp;
   const float* mrow = mag + ((size_t)b * T + h) * F;
   const bool live = h < T;                                   // zero time padding AFTER bn0 (models/resunet.py:548)
-  const int stride = gridDim.x * 64;
   for (int w0 = blockIdx.x * 64 + (threadIdx.x >> 2); w0 < Fp; w0 += 4 * stride) {
     float xb[4];
 #pragma unroll
@@ -530,6 +535,7 @@ __global__ void __launch_bounds__(256) pre_fwd_kernel(const float* __restrict__ 
         store8(x0, ((size_t)row * Fp + w) * 32 + cv * 8, 1, r);
       }
     }
+  }
   }
 }
 
@@ -1131,18 +1137,16 @@ int lass_pool_bwd(const void* dpool, const void* dskip, int dskip_cstride, int d
                   int pw, void* stream_v) {
   if (!dpool || !dy || B <= 0 || H <= 0 || W <= 0 || C % 8 || ph < 1 || pw < 1 || H % ph || W % pw || (dskip && !chan_ok(C, dskip_cstride, dskip_coff)))
     return set_error(LASS_ERR_ARG, "lass_pool_bwd: bad argument");
-  if ((long long)B * H > 65535) return set_error(LASS_ERR_ARG, "lass_pool_bwd: more than 65535 image rows (B * H)");
   const int nv = W * (C / 8);
-  pool_bwd_kernel<<<dim3((unsigned)grid_for(nv, 256 * 4, 64), (unsigned)(B * H)), 256, 0, (cudaStream_t)stream_v>>>(dpool, dskip, dskip_cstride, dskip_coff, dy, B, H, W, C, ph, pw);
+  pool_bwd_kernel<<<dim3((unsigned)grid_for(nv, 256 * 4, 64), (unsigned)(B * H < 65535 ? B * H : 65535)), 256, 0, (cudaStream_t)stream_v>>>(dpool, dskip, dskip_cstride, dskip_coff, dy, B, H, W, C, ph, pw);
   LASS_LAUNCH_CHECK("pool_bwd launch");
 }
 
 int lass_unshuffle(const void* src, int src_cstride, int src_coff, void* dst, int B, int H, int W, int C, int uh, int uw, void* stream_v) {
   if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || uh < 1 || uw < 1 || C % 8 || src_cstride % 8 || src_coff % 8 || src_coff + C > src_cstride)
     return set_error(LASS_ERR_ARG, "lass_unshuffle: bad argument");
-  if ((long long)B * H > 65535) return set_error(LASS_ERR_ARG, "lass_unshuffle: more than 65535 image rows (B * H)");
   const int nv = W * uh * uw * (C / 8);
-  unshuffle_kernel<<<dim3((unsigned)grid_for(nv, 256 * 4, 64), (unsigned)(B * H)), 256, 0, (cudaStream_t)stream_v>>>(
+  unshuffle_kernel<<<dim3((unsigned)grid_for(nv, 256 * 4, 64), (unsigned)(B * H < 65535 ? B * H : 65535)), 256, 0, (cudaStream_t)stream_v>>>(
       reinterpret_cast<const uint16_t*>(src), src_cstride, src_coff, reinterpret_cast<uint16_t*>(dst), B, H, W, C, uh, uw);
   LASS_LAUNCH_CHECK("unshuffle launch");
 }
@@ -1159,8 +1163,7 @@ int lass_channel_sum(const void* x, long long npix, int C, int cstride, int coff
 int lass_pre_fwd(const float* mag, int B, int T, int F, int Tp, int Fp, const float* bnp0, const float* pre_w, const float* pre_b, void* x0,
                  void* stream_v) {
   if (!mag || !bnp0 || !pre_w || !pre_b || !x0 || B <= 0 || T <= 0 || Tp < T || Fp <= 0 || Fp > F) return set_error(LASS_ERR_ARG, "lass_pre_fwd: bad argument");
-  if ((long long)B * Tp > 65535) return set_error(LASS_ERR_ARG, "lass_pre_fwd: more than 65535 image rows (B * Tp)");
-  pre_fwd_kernel<<<dim3((unsigned)grid_for(Fp, 64 * 4, 16), (unsigned)(B * Tp)), 256, 0, (cudaStream_t)stream_v>>>(mag, B, T, F, Tp, Fp, bnp0, pre_w,
+  pre_fwd_kernel<<<dim3((unsigned)grid_for(Fp, 64 * 4, 16), (unsigned)(B * Tp < 65535 ? B * Tp : 65535)), 256, 0, (cudaStream_t)stream_v>>>(mag, B, T, F, Tp, Fp, bnp0, pre_w,
                                                                                                          pre_b, x0);
   LASS_LAUNCH_CHECK("pre_fwd launch");
 }
