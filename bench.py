@@ -18,6 +18,8 @@ Output: ONE JSON line on rank 0 (see the keys below; contract in the task descri
   spectral BASELINE config 2 (STFT -> mask -> iSTFT round trip, 64 x 10 s): achieved HBM GB/s of K1 and K5
   cpu_baseline  the reference forward timed on this box's host cores (1 clip, best of 3): the UNMODIFIED reference when
            oracle/_ref travelled with the snapshot (kind "reference"), else the oracle port (kind "port")
+  reference_on_this_gpu  a second baseline leg (N = 1): the UNMODIFIED reference module (oracle/_ref, PyTorch eager / cuDNN) on
+           the same GPU with the same weights and 64 x 10 s batch, fp32 / TF32 / bf16 autocast; never the product path
   train    BASELINE config 4: one optimisation step (train-mode forward, l1_wav, backward, NCCL gradient all-reduce,
            fused AdamW-amsgrad) on 16 clips x 5 s per GPU, host inputs, loss read back; all-reduce timed alone as well
   north_star_shape / latency / strong_scaling / clap_standin  the other configurations SURVEY.md §8(d) asks for
@@ -137,6 +139,54 @@ def make_batch(batch, seed):
     mix = (0.1 * torch.randn(batch, 1, L, generator=g)).clamp_(-1.0, 1.0)
     cond = torch.nn.functional.normalize(torch.randn(batch, 512, generator=g), dim=-1)
     return mix, cond
+
+
+def time_reference_on_gpu(model, device):
+    """A second BASELINE leg beside cpu_baseline (never the product path): the UNMODIFIED reference module (oracle/_ref, PyTorch
+    eager / cuDNN) on THIS GPU with the weights of `model`, same 64 x 10 s batch -- fp32, TF32 and bf16 autocast, CUDA events, one
+    warm-up + 2 timed forwards each.  {"unavailable": why} when the reference files did not travel."""
+    from oracle import reference_loader
+    if not reference_loader.reference_available():
+        return {"unavailable": "oracle/_ref (the reference's own files, copied by __graft_entry__.build()) is not on this box"}
+    try:
+        ref = reference_loader.import_reference_resunet().ResUNet30(input_channels=1, output_channels=1, condition_size=512).eval()
+        ref.load_state_dict(model.state_dict())
+        ref = ref.to(device)
+        mix, cond = make_batch(BATCH_PER_GPU, 0)
+        inp = {"mixture": mix.to(device), "condition": cond.to(device)}
+        out = {"batch": BATCH_PER_GPU, "note": "unmodified reference models/resunet.py, PyTorch eager / cuDNN, same weights and batch"}
+
+        def timed():
+            ref(inp)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(2):
+                ref(inp)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / 2
+
+        with torch.no_grad():
+            for name, tf32, ac in (("fp32", False, False), ("tf32", True, False), ("bf16_autocast", True, True)):
+                torch.backends.cudnn.allow_tf32 = tf32
+                torch.backends.cuda.matmul.allow_tf32 = tf32
+                torch.backends.cudnn.benchmark = ac
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                    ms = timed()
+                out[name] = {"ms_per_step": ms, "audio_s_per_s": BATCH_PER_GPU * CLIP_SECONDS / (ms * 1e-3)}
+    except Exception as exc:                                 # a baseline leg must never take the bench line down
+        out = {"unavailable": "%s: %s" % (type(exc).__name__, str(exc)[:200])}
+    finally:
+        torch.backends.cudnn.benchmark = False
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        del ref, inp
+    except NameError:
+        pass
+    torch.cuda.empty_cache()
+    return out
 
 
 def cpu_reference_forward_time(repeats, threads=None):
@@ -630,6 +680,8 @@ def main():
                                       "audio_s_per_s": BATCH_PER_GPU * CLIP_SECONDS / dev_t}
         del m2
         torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_extras and not args.no_cpu_baseline:
+        extras["reference_on_this_gpu"] = time_reference_on_gpu(model, device)
     if rank == 0 and world == 1:
         if not args.no_spectral:
             spectral = time_spectral(device, peaks)
