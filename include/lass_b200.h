@@ -296,7 +296,8 @@ LASS_API int lass_debug_set_istft_v1(int on);
  * stores instead of TMA stores, 128 = single MMA issuer, 256 = generic (unspecialised) epilogue, 512 / 2048 = staged outputs
  * through coalesced / hybrid st.global, 1024 = N 256 x 2 m-tiles, 4096 = no CTA pairs (tcgen05 cta_group::2), 8192 = one tap
  * per streamed weight stage, 16384 = 16-byte instead of 32-byte direct stores, 32768 = CTA pairs for every resident-weight
- * launch, 65536 = the 32-channel transposed conv through TMA stores, 262144 = keep the large tiles for small grids (default: a
+ * launch, 65536 = the 32-channel transposed conv through TMA stores, 4194304 = conv launches without programmatic dependent launch (default: each conv launch may
+ * overlap its prologue with the previous launch's tail and waits with griddepcontrol.wait before it reads anything), 262144 = keep the large tiles for small grids (default: a
  * streamed-weight conv whose items cover less than half of the SMs takes one m-tile and N down to 32). */
 LASS_API int lass_debug_set_conv_flags(int flags);
 /* Debug: per-CTA role profile of subsequently PREPARED conv launches.  device_counters: >= 16 int64 per CTA

@@ -368,6 +368,11 @@ __global__ void __launch_bounds__(kThreadsK, 1) conv_igemm_kernel(const __grid_c
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (conv_run): everything above -- barriers, TMEM, tensor-map prefetch -- touches nothing a
+  // previous launch writes and may overlap its tail; the NEXT conv launch may now be scheduled onto free SMs and do the same.
+  // Nothing below runs before every earlier launch of the stream has completed.
+  griddep_launch_dependents();
+  griddep_wait();
 
   const bool mma_only = (p.debug_flags & 64) != 0;   // timing experiment: the MMA issuer runs free, nothing else runs
   if (warp < 2) {
@@ -1153,6 +1158,7 @@ struct ConvPrepared {
   int grid;
   int threads;
   int cluster;   // 2: launched as thread-block clusters of two CTAs (params.cg2)
+  int pdl;       // launched with programmatic stream serialization (debug flag 4194304: off)
   size_t smem;
 };
 
@@ -1605,6 +1611,7 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
   const int tmem_need = tmem_cols(BN, MT);
   int per_sm = 1;
   cp->threads = kThreadsK;
+  cp->pdl = (g_debug_flags & 4194304) ? 0 : 1;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(kc.fn), kThreadsK, cp->smem) != cudaSuccess || per_sm < 1)
     per_sm = 1;
   if (per_sm > 512 / tmem_need) per_sm = 512 / tmem_need;
@@ -1640,24 +1647,31 @@ int conv_prepare(const ConvLaunch& l, ConvPrepared** out) {
 }
 
 int conv_run(const ConvPrepared* cp, cudaStream_t stream) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)cp->grid, 1, 1);
+  cfg.blockDim = dim3((unsigned)cp->threads, 1, 1);
+  cfg.dynamicSmemBytes = cp->smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int na = 0;
   if (cp->cluster == 2) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3((unsigned)cp->grid, 1, 1);
-    cfg.blockDim = dim3((unsigned)cp->threads, 1, 1);
-    cfg.dynamicSmemBytes = cp->smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return set_cuda_error(cudaLaunchKernelEx(&cfg, cp->fn, cp->params), "conv launch (CTA pairs)");
+    at[na].id = cudaLaunchAttributeClusterDimension;
+    at[na].val.clusterDim.x = 2;
+    at[na].val.clusterDim.y = 1;
+    at[na].val.clusterDim.z = 1;
+    ++na;
   }
-  cp->fn<<<cp->grid, cp->threads, cp->smem, stream>>>(cp->params);
-  return set_cuda_error(cudaGetLastError(), "conv launch");
+  if (cp->pdl) {
+    // the kernel's prologue may overlap the tail of the previous launch in the stream (it calls griddepcontrol.wait before
+    // it touches anything that launch wrote); a predecessor without griddepcontrol.launch_dependents releases it on completion
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = (unsigned)na;
+  return set_cuda_error(cudaLaunchKernelEx(&cfg, cp->fn, cp->params), cp->cluster == 2 ? "conv launch (CTA pairs)" : "conv launch");
 }
 
 void conv_free(ConvPrepared* p) { delete p; }
