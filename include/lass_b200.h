@@ -244,6 +244,11 @@ LASS_API int lass_wgrad(const void* dy, int dy_cstride, int dy_coff, int co, con
  * fill the M = 128 rows, fp16 x tiles are converted to bf16 in shared memory, split over pixel ranges with fp32 red.global. */
 LASS_API int lass_wgrad_tc(const void* dy, int dy_cstride, int dy_coff, int co, const void* x, int x_fp16, int x_cstride,
                            int x_coff, int ci, int B, int H, int W, int taps, float* dw, void* stream);
+/* lass_wgrad_tc ADDED to dw / lass_channel_sum ADDED to out (no memset inside; the training step clears its gradient buffers
+ * with one memset per step). */
+LASS_API int lass_wgrad_tc_acc(const void* dy, int dy_cstride, int dy_coff, int co, const void* x, int x_fp16, int x_cstride,
+                               int x_coff, int ci, int B, int H, int W, int taps, float* dw, void* stream);
+LASS_API int lass_channel_sum_acc(const void* x, long long npix, int C, int cstride, int coff, float* out, void* stream);
 /* bn0 + zero time padding + Nyquist drop + pre_conv (models/resunet.py:537-555): x0 (B, Tp, Fp, 32) fp16; and its backward
  * from dx0 (bf16): dpre_w, dpre_b (32), dgamma0, dbeta0 (F; the dropped Nyquist bin gets 0).  bnp0 = 6*F block of bn0. */
 LASS_API int lass_pre_fwd(const float* mag, int B, int T, int F, int Tp, int Fp, const float* bnp0, const float* pre_w,

@@ -210,5 +210,7 @@ SIGNATURES.update({
     "lass_pack_blocks": (_i, [_i, _i, _i]),
 })
 SIGNATURES["lass_wgrad_tc"] = SIGNATURES["lass_wgrad"]
+SIGNATURES["lass_wgrad_tc_acc"] = SIGNATURES["lass_wgrad"]
+SIGNATURES["lass_channel_sum_acc"] = SIGNATURES["lass_channel_sum"]
 SIGNATURES["lass_stft_multi_fwd"] = (_i, [_v, _i, _i, _i, _i, _v, _v, _v, _v, _v, _v, _i, _i, _v, ctypes.c_size_t, _v])
 DEBUG_SIGNATURES["lass_debug_umma_probe_mn"] = (_i, [_v, _i, _i, _v, _i, _i, _i, _i] + [_i] * 10 + [_v, _v])

@@ -7,6 +7,7 @@
 #include <stddef.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 
 #include "../../include/lass_b200.h"
 
@@ -42,5 +43,32 @@ cudaError_t launch_mask_istft(const float* feat, long long feat_bstride, long lo
                               int hop, int L, cudaStream_t stream);
 
 void mask_istft_force_v1(int on);
+
+// ---- programmatic dependent launch ----
+// launch_pdl(kernel, grid, block, smem, stream, args...) launches with cudaLaunchAttributeProgrammaticStreamSerialization: the
+// grid may be SCHEDULED while its predecessor in the stream still runs (once all of the predecessor's CTAs have executed
+// griddepcontrol.launch_dependents or exited), so launch latency and prologues overlap the predecessor's tail.  Every kernel
+// launched this way starts with griddep_launch_dependents(); griddep_wait(); -- nothing it reads or writes is touched before
+// every earlier launch of the stream has completed and its memory is visible.
+#ifdef __CUDACC__
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace lass

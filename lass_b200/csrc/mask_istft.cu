@@ -339,6 +339,9 @@ __global__ void __launch_bounds__(NW * 32, 16 / NW) mask_istft_v2_kernel(const M
     wsum[r] = invN / fmaxf(ws, 1e-11f);
   }
   const uint32_t hop_magic = (uint32_t)((0x100000000ull + (uint32_t)hop - 1) / (uint32_t)hop);   // x / hop == umulhi(x, magic) for x * hop < 2^32
+  // programmatic dependent launch: the tables above are constants of the model; everything below waits for the previous launches
+  griddep_launch_dependents();
+  griddep_wait();
   // Persistent CTAs over (clip, chunk of FR frames) items, item i on CTA i mod grid: FR is a constant of the shape (NOT of the
   // batch size: clips come out bit-identical whatever batch they run in), small enough that the static round-robin ends level.
   // An item owns the FR frames that START in [pos0, pos0 + S) -- no halo frames are recomputed.  Their samples reach N - hop past
@@ -614,8 +617,7 @@ cudaError_t launch_v2(MaskIstftArgs a, int B, int T, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(a.out, 0, (size_t)B * a.L * sizeof(float), stream);    // the CTAs ADD their boundary samples
     if (e != cudaSuccess) return e;
   }
-  mask_istft_v2_kernel<E, NW><<<grid, NW * 32, smem, stream>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(mask_istft_v2_kernel<E, NW>, grid, dim3(NW * 32), smem, stream, a);
 }
 
 }  // namespace

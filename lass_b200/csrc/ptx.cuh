@@ -392,14 +392,6 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, float* v) {
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// Programmatic dependent launch (a launch carrying cudaLaunchAttributeProgrammaticStreamSerialization may start while its
-// predecessor in the stream still runs): launch_dependents lets the successor's CTAs be scheduled, wait blocks until every
-// prerequisite grid has completed and its memory is visible.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
-// ------------------------------------------------------------------------------------------------
 // 16-bit packing
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -136,6 +136,8 @@ __device__ __forceinline__ void bn_finalize_channel(double s, double q, int c, i
 
 __global__ void __launch_bounds__(kRedThreads, 2) bn_stats_kernel(const void* __restrict__ x, int fp16, long long npix, int C, int cstride,
                                                                int coff, double* __restrict__ sums) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   extern __shared__ float red[];
   const int CV = C / 8, R = kRedThreads / CV;
   const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
@@ -169,6 +171,8 @@ __global__ void __launch_bounds__(kRedThreads, 2) bn_stats_kernel(const void* __
 }
 
 __global__ void bn0_stats_kernel(const float* __restrict__ mag, int rows, int F, int rows_per_block, double* __restrict__ sums) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= F) return;
   const int r0 = blockIdx.y * rows_per_block;
@@ -187,6 +191,8 @@ __global__ void bn0_stats_kernel(const float* __restrict__ mag, int rows, int F,
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ running_mean,
                                    float* __restrict__ running_var, float momentum, float eps, int C, float* __restrict__ bnp) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   bn_finalize_channel(sums[c], sums[C + c], c, C, count, gamma, beta, running_mean, running_var, momentum, eps, bnp);
@@ -199,6 +205,8 @@ __global__ void __launch_bounds__(kRedThreads, 2) bn_act_kernel(const void* __re
                                                              void* __restrict__ out, int out_fp16, int out_cstride, int out_coff,
                                                              long long pix_per_clip, int C, const float* __restrict__ bnp,
                                                              const float* __restrict__ beta, int beta_bstride) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   constexpr int kU = 4;
   const int CV = C / 8, R = kRedThreads / CV;
   const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
@@ -271,6 +279,8 @@ __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_reduce_kernel(const voi
                                                                     long long pix_per_clip, int C, const float* __restrict__ bnp,
                                                                     const float* __restrict__ beta, int beta_bstride,
                                                                     float* __restrict__ sums, const BnBwdFinalize fin) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   extern __shared__ float red[];
   const int CV = C / 8, R = kRedThreads / CV;
   const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
@@ -338,6 +348,8 @@ __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_reduce_kernel(const voi
 __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int B, int C, double count, const float* __restrict__ gamma,
                                        float* __restrict__ bnp, float* __restrict__ dgamma, float* __restrict__ dbeta,
                                        float* __restrict__ dfilm, int dfilm_bstride) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   bn_bwd_finalize_channel(sums, c, B, C, count, bnp, dgamma, dbeta, dfilm, dfilm_bstride);
@@ -349,6 +361,8 @@ __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_apply_kernel(const void
                                                                    void* __restrict__ dx, int dx_cstride, int dx_coff, long long pix_per_clip,
                                                                    int C, const float* __restrict__ bnp, const float* __restrict__ beta,
                                                                    int beta_bstride) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   constexpr int kU = 2;
   const int CV = C / 8, R = kRedThreads / CV;
   const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
@@ -402,6 +416,8 @@ __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_apply_kernel(const void
 // 3.7-4.0 TB/s).
 __global__ void __launch_bounds__(256) pool_bwd_kernel(const void* __restrict__ dpool, const void* __restrict__ dskip, int s_cstride,
                                                        int s_coff, void* __restrict__ dy, int B, int H, int W, int C, int ph, int pw) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   constexpr int kU = 4;
   const int CV = C / 8;
   const float inv = 1.0f / (float)(ph * pw);
@@ -445,6 +461,8 @@ __global__ void __launch_bounds__(256) pool_bwd_kernel(const void* __restrict__ 
 // dst (B, H, W, uh*uw*C)[(dy*uw + dx)*C + c] = src (B, H*uh, W*uw, cstride)[h*uh + dy, w*uw + dx, coff + c]   (16-byte copies)
 __global__ void __launch_bounds__(256) unshuffle_kernel(const uint16_t* __restrict__ src, int cstride, int coff, uint16_t* __restrict__ dst,
                                                         int B, int H, int W, int C, int uh, int uw) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   constexpr int kU = 4;
   const int CV = C / 8, G = uh * uw;
   const int nv = W * G * CV, stride = gridDim.x * 256;
@@ -476,6 +494,8 @@ __global__ void __launch_bounds__(256) unshuffle_kernel(const uint16_t* __restri
 
 __global__ void __launch_bounds__(kRedThreads) channel_sum_kernel(const void* __restrict__ x, long long npix, int C, int cstride, int coff,
                                                                   float* __restrict__ out) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   extern __shared__ float red[];
   const int CV = C / 8, R = kRedThreads / CV;
   const int cv = threadIdx.x % CV, prow = threadIdx.x / CV;
@@ -510,6 +530,8 @@ __global__ void __launch_bounds__(kRedThreads) channel_sum_kernel(const void* __
 __global__ void __launch_bounds__(256) pre_fwd_kernel(const float* __restrict__ mag, int B, int T, int F, int Tp, int Fp,
                                                       const float* __restrict__ bnp0, const float* __restrict__ pre_w,
                                                       const float* __restrict__ pre_b, void* __restrict__ x0) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   // grid.y = output row (b, h); a thread keeps its 8-channel vector of the pre_conv weights, walks the row's pixels
   const int cv = threadIdx.x & 3;
   const V8 wv = ldf8(pre_w + cv * 8), bv = ldf8(pre_b + cv * 8);
@@ -546,6 +568,8 @@ __global__ void __launch_bounds__(256) pre_bwd_kernel(const void* __restrict__ d
                                                       int Fp, const float* __restrict__ bnp0, const float* __restrict__ pre_w,
                                                       float* __restrict__ dpre_w, float* __restrict__ dpre_b,
                                                       float* __restrict__ dgamma0, float* __restrict__ dbeta0) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   __shared__ float red[2][8][32];     // [w|b][warp][channel]
   const int cv = threadIdx.x & 3, col = threadIdx.x >> 2;
   const int w = blockIdx.x * 64 + col;
@@ -618,6 +642,8 @@ __global__ void __launch_bounds__(256) pre_bwd_kernel(const void* __restrict__ d
 __global__ void __launch_bounds__(256) after_bwd_kernel(const float* __restrict__ dfeat, const void* __restrict__ y,
                                                         const float* __restrict__ after_w, void* __restrict__ dy,
                                                         float* __restrict__ dw, float* __restrict__ db, int B, long long npix) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   __shared__ float red[8][4][27];
   const int cv = threadIdx.x & 3;
   V8 w[3];
@@ -703,6 +729,8 @@ __global__ void __launch_bounds__(256) mask_bwd_kernel(const float* __restrict__
                                                        const float* __restrict__ cosp, const float* __restrict__ sinp,
                                                        const float* __restrict__ dre, const float* __restrict__ dim_,
                                                        float* __restrict__ dfeat, int B, int T, int F, int Tp, int Fp, float inv_n) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   const long long total = (long long)B * Tp * Fp;
   const size_t plane = (size_t)Tp * Fp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -748,6 +776,8 @@ __global__ void __launch_bounds__(256) mask_bwd_kernel(const float* __restrict__
 
 __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ wave, const float* __restrict__ target, long long n,
                                                       float* __restrict__ loss_sum, float* __restrict__ dwave, float scale) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   __shared__ float red[8];
   float s = 0.0f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -769,6 +799,8 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float* __restrict__ 
 // dw (J, K) = dbeta^T cond ; db (J) = column sums of dbeta.  Thread = (j, 4 consecutive k).
 __global__ void __launch_bounds__(128) film_bwd_kernel(const float* __restrict__ dbeta, const float* __restrict__ cond,
                                                        float* __restrict__ dw, float* __restrict__ db, int B, int J, int K) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   const int j = blockIdx.x;
   float s = 0.0f;
   for (int k0 = threadIdx.x * 4; k0 < K; k0 += 128 * 4) {
@@ -807,6 +839,8 @@ __global__ void __launch_bounds__(256) adamw_amsgrad_kernel(float* __restrict__ 
                                                             float* __restrict__ v, float* __restrict__ vmax, long long n, long long n4,
                                                             float decay, float one_minus_b1, float b2, float one_minus_b2, float bc2_sqrt,
                                                             float eps, float neg_step_size, float grad_scale) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   const long long stride = (long long)gridDim.x * blockDim.x, t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   for (long long i = t0; i < n4; i += stride) {
     float4 pv = reinterpret_cast<float4*>(p)[i], mv = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i],
@@ -834,6 +868,8 @@ __global__ void __launch_bounds__(256) adamw_amsgrad_kernel(float* __restrict__ 
 // fp32 parameter (torch layout) -> 16-bit kernel layouts; thread per source element
 __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, int kind, int co, int ci, int taps,
                                                           void* __restrict__ fwd, int fwd_fp16, void* __restrict__ dgrad) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   const long long n = (long long)co * ci * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % taps);
@@ -863,6 +899,8 @@ __global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restric
 // packed fp32 gradient (taps, co, ci) -> torch layout; thread per destination element
 __global__ void __launch_bounds__(256) unpack_grad_kernel(const float* __restrict__ dw, int kind, int co, int ci, int taps,
                                                           float* __restrict__ grad) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   const long long n = (long long)co * ci * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(i % taps);
@@ -901,6 +939,8 @@ __device__ __forceinline__ int multi_find(const long long* __restrict__ table, i
 // weights; this form ~3x faster).  first block / block count per tensor: ceil(d0 / 32) * ceil(d1 / 32) (lass_pack_blocks).
 constexpr int kPackTile = 32;
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const long long* __restrict__ table, int nitems) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   constexpr int kRow = kPackTile * 9 + 1;                // odd row pitch: lanes along a tile ROW hit 32 different banks
   __shared__ float tile[kPackTile * kRow];
   const int it = multi_find(table, nitems, blockIdx.x);
@@ -972,6 +1012,8 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const long long
 }
 
 __global__ void __launch_bounds__(256) unpack_grads_multi_kernel(const long long* __restrict__ table, int nitems) {
+  griddep_launch_dependents();   // programmatic dependent launch: see launch_pdl (lass_internal.cuh)
+  griddep_wait();
   const int it = multi_find(table, nitems, blockIdx.x);
   const long long* e = table + it * 8;
   const float* dw = reinterpret_cast<const float*>(e[0]);
@@ -1018,7 +1060,7 @@ int lass_bn_stats(const void* x, int fp16, long long npix, int C, int cstride, i
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, s);
   const int R = kRedThreads / (C / 8);
   const int grid = grid_for(npix, R * 8, 148 * 4);
-  bn_stats_kernel<<<grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), s>>>(x, fp16, npix, C, cstride, coff, sums);
+  launch_pdl(bn_stats_kernel, grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), s, x, fp16, npix, C, cstride, coff, sums);
   LASS_LAUNCH_CHECK("bn_stats launch");
 }
 
@@ -1027,7 +1069,7 @@ int lass_bn_stats_acc(const void* x, int fp16, long long npix, int C, int cstrid
   if (!x || !sums || npix <= 0 || !chan_ok(C, cstride, coff)) return set_error(LASS_ERR_ARG, "lass_bn_stats_acc: bad argument (C=%d cstride=%d coff=%d)", C, cstride, coff);
   const int R = kRedThreads / (C / 8);
   const int grid = grid_for(npix, R * 8, 148 * 4);
-  bn_stats_kernel<<<grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), (cudaStream_t)stream_v>>>(x, fp16, npix, C, cstride, coff, sums);
+  launch_pdl(bn_stats_kernel, grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), (cudaStream_t)stream_v, x, fp16, npix, C, cstride, coff, sums);
   LASS_LAUNCH_CHECK("bn_stats launch");
 }
 
@@ -1037,14 +1079,14 @@ int lass_bn0_stats(const float* mag, int B, int T, int F, double* sums, void* st
   cudaMemsetAsync(sums, 0, sizeof(double) * 2 * F, s);
   const int rows = B * T, rpb = 64;
   dim3 grid((unsigned)((F + 127) / 128), (unsigned)((rows + rpb - 1) / rpb));
-  bn0_stats_kernel<<<grid, 128, 0, s>>>(mag, rows, F, rpb, sums);
+  launch_pdl(bn0_stats_kernel, grid, 128, 0, s, mag, rows, F, rpb, sums);
   LASS_LAUNCH_CHECK("bn0_stats launch");
 }
 
 int lass_bn_finalize(const double* sums, double count, const float* gamma, const float* beta, float* running_mean,
                      float* running_var, float momentum, float eps, int C, float* bnp, void* stream_v) {
   if (!sums || !gamma || !beta || !running_mean || !running_var || !bnp || C <= 0 || count <= 0) return set_error(LASS_ERR_ARG, "lass_bn_finalize: bad argument");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(sums, count, gamma, beta, running_mean, running_var, momentum, eps, C, bnp);
+  launch_pdl(bn_finalize_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream_v, sums, count, gamma, beta, running_mean, running_var, momentum, eps, C, bnp);
   LASS_LAUNCH_CHECK("bn_finalize launch");
 }
 
@@ -1054,7 +1096,7 @@ int lass_bn_act(const void* x, int x_fp16, int x_cstride, int x_coff, void* out,
     return set_error(LASS_ERR_ARG, "lass_bn_act: bad argument");
   const int R = kRedThreads / (C / 8);
   dim3 grid((unsigned)grid_for(pix_per_clip, R * 4, (148 * 8 + B - 1) / B), (unsigned)B);
-  bn_act_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream_v>>>(x, x_fp16, x_cstride, x_coff, out, out_fp16, out_cstride, out_coff,
+  launch_pdl(bn_act_kernel, grid, kRedThreads, 0, (cudaStream_t)stream_v, x, x_fp16, x_cstride, x_coff, out, out_fp16, out_cstride, out_coff,
                                                                   pix_per_clip, C, bnp, beta, beta_bstride);
   LASS_LAUNCH_CHECK("bn_act launch");
 }
@@ -1065,7 +1107,7 @@ static int bn_bwd_reduce_launch(const void* dact, int d_cstride, int d_coff, con
   const int R = kRedThreads / (C / 8);
   int gx = grid_for(pix_per_clip, R * 8, (148 * 4 + B - 1) / B);
   dim3 grid((unsigned)gx, (unsigned)B);
-  bn_bwd_reduce_kernel<<<grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), s>>>(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff,
+  launch_pdl(bn_bwd_reduce_kernel, grid, kRedThreads, (size_t)R * C * 2 * sizeof(float), s, dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff,
                                                                                     pix_per_clip, C, bnp, beta, beta_bstride, sums, fin);
   LASS_LAUNCH_CHECK("bn_bwd_reduce launch");
 }
@@ -1115,7 +1157,7 @@ int lass_bn_bwd_reduce_finalize(const void* dact, int d_cstride, int d_coff, con
 int lass_bn_bwd_finalize(const float* sums, int B, int C, double count, const float* gamma, float* bnp, float* dgamma, float* dbeta,
                          float* dfilm, int dfilm_bstride, void* stream_v) {
   if (!sums || !gamma || !bnp || !dgamma || !dbeta || B <= 0 || C <= 0 || count <= 0) return set_error(LASS_ERR_ARG, "lass_bn_bwd_finalize: bad argument");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream_v>>>(sums, B, C, count, gamma, bnp, dgamma, dbeta, dfilm, dfilm_bstride);
+  launch_pdl(bn_bwd_finalize_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream_v, sums, B, C, count, gamma, bnp, dgamma, dbeta, dfilm, dfilm_bstride);
   LASS_LAUNCH_CHECK("bn_bwd_finalize launch");
 }
 
@@ -1127,7 +1169,7 @@ int lass_bn_bwd_apply(const void* dact, int d_cstride, int d_coff, const void* x
     return set_error(LASS_ERR_ARG, "lass_bn_bwd_apply: bad argument");
   const int R = kRedThreads / (C / 8);
   dim3 grid((unsigned)grid_for(pix_per_clip, R * 2, (148 * 8 + B - 1) / B), (unsigned)B);
-  bn_bwd_apply_kernel<<<grid, kRedThreads, 0, (cudaStream_t)stream_v>>>(dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff, add, add_cstride,
+  launch_pdl(bn_bwd_apply_kernel, grid, kRedThreads, 0, (cudaStream_t)stream_v, dact, d_cstride, d_coff, x, x_fp16, x_cstride, x_coff, add, add_cstride,
                                                                         add_coff, dx, dx_cstride, dx_coff, pix_per_clip, C, bnp, beta,
                                                                         beta_bstride);
   LASS_LAUNCH_CHECK("bn_bwd_apply launch");
@@ -1138,7 +1180,7 @@ int lass_pool_bwd(const void* dpool, const void* dskip, int dskip_cstride, int d
   if (!dpool || !dy || B <= 0 || H <= 0 || W <= 0 || C % 8 || ph < 1 || pw < 1 || H % ph || W % pw || (dskip && !chan_ok(C, dskip_cstride, dskip_coff)))
     return set_error(LASS_ERR_ARG, "lass_pool_bwd: bad argument");
   const int nv = W * (C / 8);
-  pool_bwd_kernel<<<dim3((unsigned)grid_for(nv, 256 * 4, 64), (unsigned)(B * H < 65535 ? B * H : 65535)), 256, 0, (cudaStream_t)stream_v>>>(dpool, dskip, dskip_cstride, dskip_coff, dy, B, H, W, C, ph, pw);
+  launch_pdl(pool_bwd_kernel, dim3((unsigned)grid_for(nv, 256 * 4, 64), (unsigned)(B * H < 65535 ? B * H : 65535)), 256, 0, (cudaStream_t)stream_v, dpool, dskip, dskip_cstride, dskip_coff, dy, B, H, W, C, ph, pw);
   LASS_LAUNCH_CHECK("pool_bwd launch");
 }
 
@@ -1146,9 +1188,17 @@ int lass_unshuffle(const void* src, int src_cstride, int src_coff, void* dst, in
   if (!src || !dst || B <= 0 || H <= 0 || W <= 0 || uh < 1 || uw < 1 || C % 8 || src_cstride % 8 || src_coff % 8 || src_coff + C > src_cstride)
     return set_error(LASS_ERR_ARG, "lass_unshuffle: bad argument");
   const int nv = W * uh * uw * (C / 8);
-  unshuffle_kernel<<<dim3((unsigned)grid_for(nv, 256 * 4, 64), (unsigned)(B * H < 65535 ? B * H : 65535)), 256, 0, (cudaStream_t)stream_v>>>(
+  launch_pdl(unshuffle_kernel, dim3((unsigned)grid_for(nv, 256 * 4, 64), (unsigned)(B * H < 65535 ? B * H : 65535)), 256, 0, (cudaStream_t)stream_v, 
       reinterpret_cast<const uint16_t*>(src), src_cstride, src_coff, reinterpret_cast<uint16_t*>(dst), B, H, W, C, uh, uw);
   LASS_LAUNCH_CHECK("unshuffle launch");
+}
+
+int lass_channel_sum_acc(const void* x, long long npix, int C, int cstride, int coff, float* out, void* stream_v) {
+  if (!x || !out || npix <= 0 || !chan_ok(C, cstride, coff)) return set_error(LASS_ERR_ARG, "lass_channel_sum_acc: bad argument");
+  const int R = kRedThreads / (C / 8);
+  launch_pdl(channel_sum_kernel, grid_for(npix, R * 8, 148 * 4), kRedThreads, (size_t)R * C * sizeof(float), (cudaStream_t)stream_v, x, npix, C, cstride,
+             coff, out);
+  LASS_LAUNCH_CHECK("channel_sum launch");
 }
 
 int lass_channel_sum(const void* x, long long npix, int C, int cstride, int coff, float* out, void* stream_v) {
@@ -1156,14 +1206,14 @@ int lass_channel_sum(const void* x, long long npix, int C, int cstride, int coff
   cudaStream_t s = (cudaStream_t)stream_v;
   cudaMemsetAsync(out, 0, sizeof(float) * C, s);
   const int R = kRedThreads / (C / 8);
-  channel_sum_kernel<<<grid_for(npix, R * 8, 148 * 4), kRedThreads, (size_t)R * C * sizeof(float), s>>>(x, npix, C, cstride, coff, out);
+  launch_pdl(channel_sum_kernel, grid_for(npix, R * 8, 148 * 4), kRedThreads, (size_t)R * C * sizeof(float), s, x, npix, C, cstride, coff, out);
   LASS_LAUNCH_CHECK("channel_sum launch");
 }
 
 int lass_pre_fwd(const float* mag, int B, int T, int F, int Tp, int Fp, const float* bnp0, const float* pre_w, const float* pre_b, void* x0,
                  void* stream_v) {
   if (!mag || !bnp0 || !pre_w || !pre_b || !x0 || B <= 0 || T <= 0 || Tp < T || Fp <= 0 || Fp > F) return set_error(LASS_ERR_ARG, "lass_pre_fwd: bad argument");
-  pre_fwd_kernel<<<dim3((unsigned)grid_for(Fp, 64 * 4, 16), (unsigned)(B * Tp < 65535 ? B * Tp : 65535)), 256, 0, (cudaStream_t)stream_v>>>(mag, B, T, F, Tp, Fp, bnp0, pre_w,
+  launch_pdl(pre_fwd_kernel, dim3((unsigned)grid_for(Fp, 64 * 4, 16), (unsigned)(B * Tp < 65535 ? B * Tp : 65535)), 256, 0, (cudaStream_t)stream_v, mag, B, T, F, Tp, Fp, bnp0, pre_w,
                                                                                                          pre_b, x0);
   LASS_LAUNCH_CHECK("pre_fwd launch");
 }
@@ -1178,7 +1228,7 @@ int lass_pre_bwd(const void* dx0, const float* mag, int B, int T, int F, int Tp,
   cudaMemsetAsync(dgamma0, 0, F * sizeof(float), s);
   cudaMemsetAsync(dbeta0, 0, F * sizeof(float), s);
   dim3 grid((unsigned)((Fp + 63) / 64), (unsigned)((Tp + kPreRows - 1) / kPreRows), (unsigned)B);
-  pre_bwd_kernel<<<grid, 256, 0, s>>>(dx0, mag, B, T, F, Tp, Fp, bnp0, pre_w, dpre_w, dpre_b, dgamma0, dbeta0);
+  launch_pdl(pre_bwd_kernel, grid, 256, 0, s, dx0, mag, B, T, F, Tp, Fp, bnp0, pre_w, dpre_w, dpre_b, dgamma0, dbeta0);
   LASS_LAUNCH_CHECK("pre_bwd launch");
 }
 
@@ -1187,7 +1237,7 @@ int lass_after_bwd(const float* dfeat, const void* y, const float* after_w, void
   cudaStream_t s = (cudaStream_t)stream_v;
   cudaMemsetAsync(dw, 0, 96 * sizeof(float), s);
   cudaMemsetAsync(db, 0, 3 * sizeof(float), s);
-  after_bwd_kernel<<<dim3((unsigned)grid_for(npix, 64 * 2, (148 * 4 + B - 1) / B), (unsigned)B), 256, 0, s>>>(dfeat, y, after_w, dy, dw, db, B, npix);
+  launch_pdl(after_bwd_kernel, dim3((unsigned)grid_for(npix, 64 * 2, (148 * 4 + B - 1) / B), (unsigned)B), 256, 0, s, dfeat, y, after_w, dy, dw, db, B, npix);
   LASS_LAUNCH_CHECK("after_bwd launch");
 }
 
@@ -1196,19 +1246,19 @@ int lass_mask_bwd(const float* feat, const float* mag, const float* cos, const f
   if (!feat || !mag || !cos || !sin || !dre || !dim || !dfeat || B <= 0 || T <= 0 || Tp < T || F != n_fft / 2 + 1 || Fp != n_fft / 2)
     return set_error(LASS_ERR_ARG, "lass_mask_bwd: bad argument");
   const long long total = (long long)B * Tp * Fp;
-  mask_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream_v>>>(feat, mag, cos, sin, dre, dim, dfeat, B, T, F, Tp, Fp, 1.0f / (float)n_fft);
+  launch_pdl(mask_bwd_kernel, grid_for(total, 256), 256, 0, (cudaStream_t)stream_v, feat, mag, cos, sin, dre, dim, dfeat, B, T, F, Tp, Fp, 1.0f / (float)n_fft);
   LASS_LAUNCH_CHECK("mask_bwd launch");
 }
 
 int lass_l1_loss(const float* wave, const float* target, long long n, float* loss_sum, float* dwave, float scale, void* stream_v) {
   if (!wave || !target || !loss_sum || !dwave || n <= 0) return set_error(LASS_ERR_ARG, "lass_l1_loss: bad argument");
-  l1_loss_kernel<<<grid_for(n, 256, 148 * 4), 256, 0, (cudaStream_t)stream_v>>>(wave, target, n, loss_sum, dwave, scale);
+  launch_pdl(l1_loss_kernel, grid_for(n, 256, 148 * 4), 256, 0, (cudaStream_t)stream_v, wave, target, n, loss_sum, dwave, scale);
   LASS_LAUNCH_CHECK("l1_loss launch");
 }
 
 int lass_film_bwd(const float* dbeta, const float* cond, float* dw, float* db, int B, int J, int K, void* stream_v) {
   if (!dbeta || !cond || !dw || !db || B <= 0 || J <= 0 || K <= 0 || K % 4) return set_error(LASS_ERR_ARG, "lass_film_bwd: bad argument");
-  film_bwd_kernel<<<J, 128, 0, (cudaStream_t)stream_v>>>(dbeta, cond, dw, db, B, J, K);
+  launch_pdl(film_bwd_kernel, J, 128, 0, (cudaStream_t)stream_v, dbeta, cond, dw, db, B, J, K);
   LASS_LAUNCH_CHECK("film_bwd launch");
 }
 
@@ -1223,7 +1273,7 @@ int lass_adamw_amsgrad(float* p, const float* g, float* m, float* v, float* vmax
   const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                          reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(vmax)) & 15) == 0;
   const long long n4 = aligned ? n / 4 : 0;
-  adamw_amsgrad_kernel<<<grid_for(n4 > 0 ? n4 : n, 256), 256, 0, (cudaStream_t)stream_v>>>(p, g, m, v, vmax, n, n4, decay, (float)(1.0 - (double)beta1), beta2,
+  launch_pdl(adamw_amsgrad_kernel, grid_for(n4 > 0 ? n4 : n, 256), 256, 0, (cudaStream_t)stream_v, p, g, m, v, vmax, n, n4, decay, (float)(1.0 - (double)beta1), beta2,
                                                                              (float)(1.0 - (double)beta2), (float)sqrt(bc2), eps, neg_step,
                                                                              grad_scale);
   LASS_LAUNCH_CHECK("adamw launch");
@@ -1231,25 +1281,25 @@ int lass_adamw_amsgrad(float* p, const float* g, float* m, float* v, float* vmax
 
 int lass_pack_weight(const float* w, int kind, int co, int ci, int taps, void* fwd, int fwd_fp16, void* dgrad, void* stream_v) {
   if (!w || (!fwd && !dgrad) || co <= 0 || ci <= 0 || taps <= 0 || (kind != 0 && kind != 1)) return set_error(LASS_ERR_ARG, "lass_pack_weight: bad argument");
-  pack_weight_kernel<<<grid_for((long long)co * ci * taps, 256), 256, 0, (cudaStream_t)stream_v>>>(w, kind, co, ci, taps, fwd, fwd_fp16, dgrad);
+  launch_pdl(pack_weight_kernel, grid_for((long long)co * ci * taps, 256), 256, 0, (cudaStream_t)stream_v, w, kind, co, ci, taps, fwd, fwd_fp16, dgrad);
   LASS_LAUNCH_CHECK("pack_weight launch");
 }
 
 int lass_unpack_grad(const float* dw, int kind, int co, int ci, int taps, float* grad, void* stream_v) {
   if (!dw || !grad || co <= 0 || ci <= 0 || taps <= 0 || (kind != 0 && kind != 1)) return set_error(LASS_ERR_ARG, "lass_unpack_grad: bad argument");
-  unpack_grad_kernel<<<grid_for((long long)co * ci * taps, 256), 256, 0, (cudaStream_t)stream_v>>>(dw, kind, co, ci, taps, grad);
+  launch_pdl(unpack_grad_kernel, grid_for((long long)co * ci * taps, 256), 256, 0, (cudaStream_t)stream_v, dw, kind, co, ci, taps, grad);
   LASS_LAUNCH_CHECK("unpack_grad launch");
 }
 
 int lass_pack_weights_multi(const long long* table_dev, int nitems, int nblocks, void* stream_v) {
   if (!table_dev || nitems <= 0 || nblocks <= 0) return set_error(LASS_ERR_ARG, "lass_pack_weights_multi: bad argument");
-  pack_weights_multi_kernel<<<nblocks, 256, 0, (cudaStream_t)stream_v>>>(table_dev, nitems);
+  launch_pdl(pack_weights_multi_kernel, nblocks, 256, 0, (cudaStream_t)stream_v, table_dev, nitems);
   LASS_LAUNCH_CHECK("pack_weights_multi launch");
 }
 
 int lass_unpack_grads_multi(const long long* table_dev, int nitems, int nblocks, void* stream_v) {
   if (!table_dev || nitems <= 0 || nblocks <= 0) return set_error(LASS_ERR_ARG, "lass_unpack_grads_multi: bad argument");
-  unpack_grads_multi_kernel<<<nblocks, 256, 0, (cudaStream_t)stream_v>>>(table_dev, nitems);
+  launch_pdl(unpack_grads_multi_kernel, nblocks, 256, 0, (cudaStream_t)stream_v, table_dev, nitems);
   LASS_LAUNCH_CHECK("unpack_grads_multi launch");
 }
 

@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(kThreads, 1) wgrad_tc_kernel(const __grid_cons
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch_dependents();     // programmatic dependent launch (lass_internal.cuh): the prologue above may overlap the
+  griddep_wait();                  // previous launch's tail; nothing below runs before every earlier launch has completed
 
   if (warp == 0) {
     if (lane == 0) {
@@ -235,8 +237,8 @@ size_t smem_bytes() {
 
 using namespace lass;
 
-extern "C" int lass_wgrad_tc(const void* dy, int dy_cstride, int dy_coff, int co, const void* x, int x_fp16, int x_cstride, int x_coff, int ci,
-                             int B, int H, int W, int taps, float* dw, void* stream_v) {
+static int wgrad_tc_impl(const void* dy, int dy_cstride, int dy_coff, int co, const void* x, int x_fp16, int x_cstride, int x_coff, int ci,
+                         int B, int H, int W, int taps, float* dw, void* stream_v, bool zero_first) {
   if (!dy || !x || !dw) return set_error(LASS_ERR_ARG, "lass_wgrad_tc: null pointer");
   if (B <= 0 || H <= 0 || W <= 0 || (taps != 9 && taps != 1) || co <= 0 || ci <= 0 || co % 32 || ci % 32 || dy_cstride % 8 || dy_coff % 8 ||
       x_cstride % 8 || x_coff % 8 || dy_coff + co > dy_cstride || x_coff + ci > x_cstride)
@@ -300,10 +302,21 @@ extern "C" int lass_wgrad_tc(const void* dy, int dy_cstride, int dy_coff, int co
   else if (nb == 64) { fn = wgrad_tc_kernel<32, 64>; smem = smem_bytes<32, 64>(); }
   else { fn = wgrad_tc_kernel<32, 32>; smem = smem_bytes<32, 32>(); }
   if (smem < 120 * 1024) smem = 120 * 1024;       // one CTA per SM: two could not both hold their TMEM accumulators
-  cudaError_t ce = cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)taps * co * ci, s);
+  cudaError_t ce = zero_first ? cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)taps * co * ci, s) : cudaSuccess;
   if (ce != cudaSuccess) return set_cuda_error(ce, "wgrad_tc memset");
   ce = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (ce != cudaSuccess) return set_cuda_error(ce, "wgrad_tc smem attribute");
-  fn<<<out_tiles * splits, kThreads, smem, s>>>(p);
-  return set_cuda_error(cudaGetLastError(), "wgrad_tc launch");
+  return set_cuda_error(launch_pdl(fn, dim3((unsigned)(out_tiles * splits)), dim3(kThreads), smem, s, p), "wgrad_tc launch");
+}
+
+extern "C" int lass_wgrad_tc(const void* dy, int dy_cstride, int dy_coff, int co, const void* x, int x_fp16, int x_cstride, int x_coff, int ci,
+                             int B, int H, int W, int taps, float* dw, void* stream_v) {
+  return wgrad_tc_impl(dy, dy_cstride, dy_coff, co, x, x_fp16, x_cstride, x_coff, ci, B, H, W, taps, dw, stream_v, true);
+}
+
+// the same sums ADDED to dw (no memset inside: the training step clears its whole gradient buffer with one memset, and a launch
+// that is not preceded by a memset node can overlap its predecessor's tail -- programmatic dependent launch)
+extern "C" int lass_wgrad_tc_acc(const void* dy, int dy_cstride, int dy_coff, int co, const void* x, int x_fp16, int x_cstride, int x_coff,
+                                 int ci, int B, int H, int W, int taps, float* dw, void* stream_v) {
+  return wgrad_tc_impl(dy, dy_cstride, dy_coff, co, x, x_fp16, x_cstride, x_coff, ci, B, H, W, taps, dw, stream_v, false);
 }

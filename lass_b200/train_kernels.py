@@ -230,20 +230,24 @@ def unshuffle(src, src_coff, C, dst, uh, uw):
     _chk(_cabi.load().lass_unshuffle(_p(src), src.shape[3], src_coff, _p(dst), B, H, W, C, uh, uw, _stream()))
 
 
-def channel_sum(x, coff, C, out):
-    """out (C) fp32 = sum over pixels of x[..., coff:coff+C] (overwrites)."""
+def channel_sum(x, coff, C, out, acc=False):
+    """out (C) fp32 = sum over pixels of x[..., coff:coff+C] (overwrites; acc: added to a pre-zeroed out, no memset inside)."""
     _need_cuda(x, out)
     npix = x.shape[0] * x.shape[1] * x.shape[2]
-    _chk(_cabi.load().lass_channel_sum(_p(x), npix, C, x.shape[3], coff, _p(out), _stream()))
+    lib = _cabi.load()
+    _chk((lib.lass_channel_sum_acc if acc else lib.lass_channel_sum)(_p(x), npix, C, x.shape[3], coff, _p(out), _stream()))
 
 
-def wgrad(dy, dy_coff, co, x, x_coff, ci, taps, dw):
-    """dw (taps, co, ci) fp32 (overwritten) = sum_p dy[p, co] * x[p + tap, ci] (zero padding; tap = ky*3+kx, centre 4)."""
+def wgrad(dy, dy_coff, co, x, x_coff, ci, taps, dw, acc=False):
+    """dw (taps, co, ci) fp32 (overwritten) = sum_p dy[p, co] * x[p + tap, ci] (zero padding; tap = ky*3+kx, centre 4).
+    acc: ADDED to a pre-zeroed dw (tcgen05 kernel only; no memset inside)."""
     _need_cuda(dy, x, dw)
     B, H, W, _ = dy.shape
     assert x.shape[:3] == dy.shape[:3] and dw.numel() == taps * co * ci and dw.dtype == torch.float32
     lib = _cabi.load()
-    fn = lib.lass_wgrad_tc if WGRAD_TENSOR_CORE else lib.lass_wgrad
+    if acc and not WGRAD_TENSOR_CORE:
+        dw.zero_()
+    fn = (lib.lass_wgrad_tc_acc if acc else lib.lass_wgrad_tc) if WGRAD_TENSOR_CORE else lib.lass_wgrad
     _chk(fn(_p(dy), dy.shape[3], dy_coff, co, _p(x), 1 if x.dtype == torch.float16 else 0, x.shape[3], x_coff, ci, B, H, W,
             taps, _p(dw), _stream()))
 

@@ -476,16 +476,16 @@ class TrainEngine:
         k = self.k
         off, p = self.index[name]
         if taps == 1 and kind == k.KIND_CONV:
-            k.wgrad(dy, 0, co, x, 0, ci, 1, self.G[off:off + p.numel()])        # (co, ci, 1, 1) is the packed layout
+            k.wgrad(dy, 0, co, x, 0, ci, 1, self.G[off:off + p.numel()], acc=True)        # (co, ci, 1, 1) is the packed layout
             return
-        k.wgrad(dy, 0, co, x, 0, ci, taps, self.Gp[off:off + p.numel()])       # packed layout; un-packed per bucket (backward)
+        k.wgrad(dy, 0, co, x, 0, ci, taps, self.Gp[off:off + p.numel()], acc=True)       # packed layout; un-packed per bucket (backward)
 
     def _block_bwd(self, ws, pfx, sites, dy, x_raw, x_act, h_raw, a2, g_a2, g_h, g_xact, g_sc, g_x, cin, cout, has_sc,
                    conv_pfx):
         """Backward of one ConvBlockRes (reference models/resunet.py:147-165).  dy: gradient of the block output."""
         k, cv = self.k, ws.conv
         if has_sc:
-            k.channel_sum(dy, 0, cout, self.g(pfx + "shortcut.bias"))
+            k.channel_sum(dy, 0, cout, self.g(pfx + "shortcut.bias"), acc=True)
             self._wgrad(ws, pfx + "shortcut.weight", k.KIND_CONV, dy, cout, x_raw, cin, 1)
             k.conv(cv[conv_pfx + "sc.dgrad"])
         self._wgrad(ws, pfx + "conv2.weight", k.KIND_CONV, dy, cout, a2, cout, 9)
@@ -506,6 +506,10 @@ class TrainEngine:
         hi, lo, window, tw = self._spectral_tables()
         dwave = dwave.detach().to(torch.float32).reshape(B, L).contiguous()
         ws.bsums_flat.zero_()
+        # the weight-gradient and bias-sum launches ADD into the gradient buffers: one memset each per step instead of one per
+        # launch (a launch behind a memset node cannot overlap its predecessor's tail)
+        self.G[:self.live_end].zero_()
+        self.Gp.zero_()
         k.istft_bwd(dwave, window, hi, lo, self.n_fft, self.hop, ws.T, ws.stft_ws, ws.dre, ws.dim)
         k.mask_bwd(ws.feat, ws.mag, ws.cos, ws.sin, ws.dre, ws.dim, ws.dfeat, self.n_fft)
         k.after_bwd(ws.dfeat, ws.d_raw[0], self._after_w, ws.g_y[0], self.g("after.w").view(3, 32), self.g("after.b"))

@@ -169,11 +169,17 @@ def unshuffle(src, src_coff, C, dst, uh, uw):
     dst.copy_(s.reshape(B, H, W, uh * uw * C))
 
 
-def channel_sum(x, coff, C, out):
-    out.copy_(x[..., coff:coff + C].float().reshape(-1, C).sum(0))
+def channel_sum(x, coff, C, out, acc=False):
+    v = x[..., coff:coff + C].float().reshape(-1, C).sum(0)
+    out.add_(v) if acc else out.copy_(v)
 
 
-def wgrad(dy, dy_coff, co, x, x_coff, ci, taps, dw):
+def wgrad(dy, dy_coff, co, x, x_coff, ci, taps, dw, acc=False):
+    if acc:                                          # added to the pre-zeroed buffer
+        tmp = torch.zeros_like(dw)
+        wgrad(dy, dy_coff, co, x, x_coff, ci, taps, tmp)
+        dw.add_(tmp)
+        return
     g = dy[..., dy_coff:dy_coff + co].float()
     xv = x[..., x_coff:x_coff + ci].float()
     if x.dtype == torch.float16 and dy.dtype == torch.bfloat16:
