@@ -349,6 +349,50 @@ def time_forward(model, batch, length, steps, warmup, device, sync_each=False):
     return e0.elapsed_time(e1) * 1e-3 / steps, wall / steps
 
 
+def time_segment_mixer(device, B, Ls, peaks):
+    """The step in front of the training path (reference data/waveform_mixers.py:9-62, called at models/audiosep.py:76-78):
+    lass_b200.data.waveform_mixers.SegmentMixer (C-ABI lass_segment_mix, two launches) on the training batch, device time per
+    call, beside the UNMODIFIED reference module on this GPU (PyTorch eager, a Python loop over the batch) when oracle/_ref
+    travels with the snapshot."""
+    import random
+    from lass_b200.data.waveform_mixers import SegmentMixer
+    g = torch.Generator().manual_seed(99)
+    wave = (0.1 * torch.randn(B, 1, Ls, generator=g)).to(device)
+    mixer = SegmentMixer(max_mix_num=2, lower_db=-10, higher_db=10)      # config/audiosep_base.yaml: max_mix_num 2, -10 .. 10 dB
+    random.seed(0)
+    for _ in range(5):
+        mixer(waveforms=wave)
+    torch.cuda.synchronize()
+    n = 100
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        mixer(waveforms=wave)
+    b.record()
+    torch.cuda.synchronize()
+    us = a.elapsed_time(b) * 1e3 / n
+    nbytes = 3 * B * Ls * 4                                             # read the batch once, write mixture and segment
+    res = {"us_per_call": us, "launches_per_call": 2, "algorithmic_bytes": nbytes, "gbs": nbytes / us / 1e3,
+           "frac_of_hbm": nbytes / us / 1e3 / peaks["hbm_gbs"],
+           "note": "15 MB per call: launch- / host-bound (two launches + the host-side random draws), not HBM-bound"}
+    try:
+        from oracle import reference_loader                             # baseline leg only (the unmodified reference)
+        if reference_loader.mixers_available():
+            ref = reference_loader.import_reference_mixers().SegmentMixer(max_mix_num=2, lower_db=-10, higher_db=10)
+            for _ in range(2):
+                ref(wave)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                ref(wave)
+            torch.cuda.synchronize()
+            res["reference_on_this_gpu_us"] = (time.perf_counter() - t0) * 1e6 / 5
+    except Exception as exc:                                            # the baseline leg must never break the bench line
+        res["reference_on_this_gpu_us"] = None
+        res["reference_error"] = repr(exc)[:200]
+    return res
+
+
 def time_train(device, rank, world, steps, warmup, peaks):
     """BASELINE config 4 through TrainEngine.training_step: per step H2D of mixture / condition / target from pinned host
     memory, train-mode forward, l1_wav, backward, NCCL all-reduce of the flat gradient (three buckets, overlapped with the
@@ -420,6 +464,7 @@ def time_train(device, rank, world, steps, warmup, peaks):
            "grad_elements": int(eng.live_end), "storage": "forward tensors fp16, gradients bf16, parameters / optimizer state / "
                                                           "statistics fp32",
            "mem_gb": torch.cuda.max_memory_allocated(device) / 1e9}
+    out["segment_mixer"] = time_segment_mixer(device, B, Ls, peaks)
     # algorithmic conv FLOPs of the step: forward + dgrad + wgrad = 3 x the UNet forward of 16 x 5 s
     flops = 3.0 * UNET_GFLOP_PER_CLIP * 1e9 * (B * Ls / float(L))
     out["conv_tflops_algorithmic"] = flops / step_s / 1e12

@@ -291,6 +291,14 @@ LASS_API int lass_pack_weights_multi(const long long* table_dev, int nitems, int
 LASS_API int lass_unpack_grads_multi(const long long* table_dev, int nitems, int nblocks, void* stream);
 LASS_API int lass_multi_chunk(void);
 LASS_API int lass_pack_blocks(int kind, int co, int ci);
+/* SegmentMixer.__call__ (data/waveform_mixers.py:19-62, dynamic_loudnorm / get_energy_ratio :65-95), the step in front of the
+ * training path (models/audiosep.py:76-78): wave (B, L) fp32 -> mixture, segment (B, L) fp32 (must not alias each other or wave).
+ * The reference's random draws are made by the caller in the reference's order and passed as plan (B, max_mix_num + 1) fp32 on the
+ * DEVICE: plan[n][0] = mix_num of clip n (2..max_mix_num), plan[n][i] (i = 1..mix_num-1) = gain 10^(dB/20) of the i-th mixed-in
+ * clip (n + i) % B, plan[n][max_mix_num] = gain of the summed noise.  scratch: lass_segment_mix_scratch_bytes(B) bytes. */
+LASS_API size_t lass_segment_mix_scratch_bytes(int B);
+LASS_API int lass_segment_mix(const float* wave, int B, int L, int max_mix_num, const float* plan, float* mixture,
+                              float* segment, void* scratch, size_t scratch_bytes, void* stream);
 /* Debug: 1 = the shared-memory Stockham iSTFT kernel for every n_fft (default: register-FFT kernel for 1024 / 2048). */
 LASS_API int lass_debug_set_istft_v1(int on);
 

@@ -209,6 +209,8 @@ SIGNATURES.update({
     "lass_multi_chunk": (_i, []),
     "lass_pack_blocks": (_i, [_i, _i, _i]),
 })
+SIGNATURES["lass_segment_mix_scratch_bytes"] = (ctypes.c_size_t, [_i])
+SIGNATURES["lass_segment_mix"] = (_i, [_v, _i, _i, _i, _v, _v, _v, _v, ctypes.c_size_t, _v])
 SIGNATURES["lass_wgrad_tc"] = SIGNATURES["lass_wgrad"]
 SIGNATURES["lass_wgrad_tc_acc"] = SIGNATURES["lass_wgrad"]
 SIGNATURES["lass_channel_sum_acc"] = SIGNATURES["lass_channel_sum"]

@@ -17,7 +17,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
-FILES = ("models/resunet.py", "models/base.py", "losses.py", "optimizers/lr_schedulers.py")
+FILES = ("models/resunet.py", "models/base.py", "losses.py", "optimizers/lr_schedulers.py", "data/waveform_mixers.py")
 
 
 def build(reference_root="/root/reference"):

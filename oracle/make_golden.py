@@ -100,5 +100,24 @@ def make_train_golden(ref_mod=None):
                         waveform=out.detach().numpy(), meta=np.array([B, L, 1234, 4321]))
 
 
+def make_mixer_golden():
+    """``SegmentMixer`` of the UNMODIFIED reference (data/waveform_mixers.py:9-62) on a seeded batch with ``random.seed(7)``."""
+    import random
+    from .reference_loader import import_reference_mixers
+    from .segment_mixer_oracle import make_waveforms
+    ref = import_reference_mixers()
+    B, L, max_mix_num, lower_db, higher_db, seed = 6, 4000, 4, -10, 10, 7
+    wave = make_waveforms(B, L, seed=3)
+    random.seed(seed)
+    mixture, segment = ref.SegmentMixer(max_mix_num=max_mix_num, lower_db=lower_db, higher_db=higher_db)(wave)
+    np.savez_compressed(os.path.join(GOLDEN_DIR, "segment_mixer_b6_l4000.npz"), mixture=mixture.numpy(), segment=segment.numpy(),
+                        meta=np.array([B, L, max_mix_num, lower_db, higher_db, seed, 3]))
+
+
 if __name__ == "__main__":
-    main()
+    import sys
+    if "--mixer-only" in sys.argv:
+        make_mixer_golden()
+    else:
+        main()
+        make_mixer_golden()

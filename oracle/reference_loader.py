@@ -33,3 +33,26 @@ def import_reference_resunet():
         sys.path.insert(1, REFERENCE_ROOT)       # `models` is a namespace package in the reference
     import importlib
     return importlib.import_module("models.resunet")
+
+
+def mixers_available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "data", "waveform_mixers.py"))
+
+
+def import_reference_mixers():
+    """Return the reference's ``data.waveform_mixers`` module (unmodified source).  Its module-level ``import pyloudnorm``
+    (used only by the retired ``random_loudness_norm``) resolves to the stub under ``oracle/pyloudnorm``; the file is loaded by
+    path so that the rest of the reference's ``data`` package (lightning, pyloudnorm-using datasets) is never imported."""
+    if not mixers_available():
+        raise RuntimeError("reference data/waveform_mixers.py not present under %s" % REFERENCE_ROOT)
+    if _ORACLE_DIR not in sys.path:
+        sys.path.insert(0, _ORACLE_DIR)
+    import importlib.util
+    import warnings
+    spec = importlib.util.spec_from_file_location("_lass_reference_waveform_mixers",
+                                                  os.path.join(REFERENCE_ROOT, "data", "waveform_mixers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)      # `import sre_compile` at data/waveform_mixers.py:2
+        spec.loader.exec_module(mod)
+    return mod
