@@ -470,6 +470,25 @@ def time_train(device, rank, world, steps, warmup, peaks):
     out["conv_tflops_algorithmic"] = flops / step_s / 1e12
     out["frac_of_bf16_sustained"] = flops / step_s / 1e12 / peaks["bf16_tflops_sustained"]
     if world > 1:
+        # the reference's own DDP configuration: sync_batchnorm True (config/audiosep_base.yaml:38) = one small all-reduce per
+        # BatchNorm site in the forward (33) and in the backward (32) on top of the gradient buckets
+        eng.sync_batchnorm = True
+        for i in range(2):
+            step(i)
+        dist.barrier()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(steps):
+            step(warmup + i)
+        s1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        sync_s = sharding.max_over_ranks(s0.elapsed_time(s1) * 1e-3 / steps, device)
+        eng.sync_batchnorm = False
+        out["sync_batchnorm"] = {"ms_per_step": sync_s * 1e3, "steps_per_s": 1.0 / sync_s, "small_allreduces_per_step": 65,
+                                 "note": "BatchNorm statistics over all ranks (torch.nn.SyncBatchNorm semantics), NCCL all-reduce "
+                                         "of (2, C) fp64 sums per site; the headline ms_per_step above is with per-rank statistics"}
         n = int(eng.live_end)
         for _ in range(2):
             dist.all_reduce(eng.G[:n])

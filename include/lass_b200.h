@@ -215,6 +215,16 @@ LASS_API int lass_bn_bwd_finalize(const float* sums, int B, int C, double count,
 LASS_API int lass_bn_bwd_reduce_acc(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride,
                                     int x_coff, int B, long long pix_per_clip, int C, const float* bnp, const float* beta,
                                     int beta_bstride, float* sums, void* stream);
+/* SyncBatchNorm backward (the reference trains with sync_batchnorm: True, config/audiosep_base.yaml:38, train.py:255-283 ->
+ * torch.nn.SyncBatchNorm): lass_bn_bwd_totals = this rank's per-channel totals (C, 2) fp64 of the per-clip sums (B, C, 2), which
+ * the caller all-reduces over the ranks; lass_bn_bwd_finalize_sync = lass_bn_bwd_finalize with the input-gradient coefficients
+ * from those all-reduced totals and the GLOBAL pixel count, while dgamma / dbeta / dfilm stay this rank's sums (DDP averages
+ * parameter gradients afterwards).  The forward needs no extra entry: the (2, C) fp64 sums of lass_bn_stats are all-reduced
+ * before lass_bn_finalize is called with the global count. */
+LASS_API int lass_bn_bwd_totals(const float* sums, int B, int C, double* totals, void* stream);
+LASS_API int lass_bn_bwd_finalize_sync(const float* sums, int B, int C, double count_total, const double* totals,
+                                       const float* gamma, float* bnp, float* dgamma, float* dbeta, float* dfilm,
+                                       int dfilm_bstride, void* stream);
 /* A/B variant, NOT used by the training step (measured slower than reduce + the one-block finalize launch, csrc/train.cu):
  * reduce + finalize in ONE launch (count = B * pix_per_clip): the last block to finish (ticket `counter`, one uint32 per site)
  * finalizes.  `sums` and `counter` must be ZERO on entry and are left dirty (the caller clears a step's with one memset each). */

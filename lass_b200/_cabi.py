@@ -209,6 +209,8 @@ SIGNATURES.update({
     "lass_multi_chunk": (_i, []),
     "lass_pack_blocks": (_i, [_i, _i, _i]),
 })
+SIGNATURES["lass_bn_bwd_totals"] = (_i, [_v, _i, _i, _v, _v])
+SIGNATURES["lass_bn_bwd_finalize_sync"] = (_i, [_v, _i, _i, _d, _v, _v, _v, _v, _v, _v, _i, _v])
 SIGNATURES["lass_segment_mix_scratch_bytes"] = (ctypes.c_size_t, [_i])
 SIGNATURES["lass_segment_mix"] = (_i, [_v, _i, _i, _i, _v, _v, _v, _v, ctypes.c_size_t, _v])
 SIGNATURES["lass_wgrad_tc"] = SIGNATURES["lass_wgrad"]

@@ -355,6 +355,45 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int B, in
   bn_bwd_finalize_channel(sums, c, B, C, count, bnp, dgamma, dbeta, dfilm, dfilm_bstride);
 }
 
+// SyncBatchNorm backward (the reference trains with sync_batchnorm: True, config/audiosep_base.yaml:38 -> torch.nn.SyncBatchNorm):
+// the input gradient needs the two sums over ALL ranks' pixels, the parameter gradients (dgamma, dbeta, dFiLM) stay this rank's
+// (DDP averages them afterwards).  bn_bwd_totals = this rank's per-channel totals (C, 2) fp64 for the all-reduce;
+// bn_bwd_finalize_sync = the finalize with coefficients from the all-reduced totals and the global pixel count.
+__global__ void bn_bwd_totals_kernel(const float* __restrict__ sums, int B, int C, double* __restrict__ totals) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double t1 = 0.0, t2 = 0.0;
+  for (int b = 0; b < B; ++b) {
+    t1 += (double)sums[((size_t)b * C + c) * 2];
+    t2 += (double)sums[((size_t)b * C + c) * 2 + 1];
+  }
+  totals[2 * c] = t1;
+  totals[2 * c + 1] = t2;
+}
+
+__global__ void bn_bwd_finalize_sync_kernel(const float* __restrict__ sums, int B, int C, double count_total,
+                                            const double* __restrict__ totals, float* __restrict__ bnp, float* __restrict__ dgamma,
+                                            float* __restrict__ dbeta, float* __restrict__ dfilm, int dfilm_bstride) {
+  griddep_launch_dependents();
+  griddep_wait();
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double t1 = 0.0, t2 = 0.0;
+  for (int b = 0; b < B; ++b) {
+    const float s1 = sums[((size_t)b * C + c) * 2], s2 = sums[((size_t)b * C + c) * 2 + 1];
+    t1 += (double)s1;
+    t2 += (double)s2;
+    if (dfilm) dfilm[(size_t)b * dfilm_bstride + c] = s1;
+  }
+  const double scale = (double)bnp[c], rstd = (double)bnp[3 * C + c];
+  dbeta[c] = (float)t1;                                  // this rank's share (DDP averages the parameter gradients)
+  dgamma[c] = (float)(rstd * t2);
+  bnp[4 * C + c] = (float)(-scale * rstd * rstd * totals[2 * c + 1] / count_total);
+  bnp[5 * C + c] = (float)(-scale * totals[2 * c] / count_total);
+}
+
 __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_apply_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
                                                                    const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
                                                                    const void* __restrict__ add, int add_cstride, int add_coff,
@@ -1159,6 +1198,21 @@ int lass_bn_bwd_finalize(const float* sums, int B, int C, double count, const fl
   if (!sums || !gamma || !bnp || !dgamma || !dbeta || B <= 0 || C <= 0 || count <= 0) return set_error(LASS_ERR_ARG, "lass_bn_bwd_finalize: bad argument");
   launch_pdl(bn_bwd_finalize_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream_v, sums, B, C, count, gamma, bnp, dgamma, dbeta, dfilm, dfilm_bstride);
   LASS_LAUNCH_CHECK("bn_bwd_finalize launch");
+}
+
+int lass_bn_bwd_totals(const float* sums, int B, int C, double* totals, void* stream_v) {
+  if (!sums || !totals || B <= 0 || C <= 0) return set_error(LASS_ERR_ARG, "lass_bn_bwd_totals: bad argument");
+  launch_pdl(bn_bwd_totals_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream_v, sums, B, C, totals);
+  LASS_LAUNCH_CHECK("bn_bwd_totals launch");
+}
+
+int lass_bn_bwd_finalize_sync(const float* sums, int B, int C, double count_total, const double* totals, const float* gamma, float* bnp,
+                              float* dgamma, float* dbeta, float* dfilm, int dfilm_bstride, void* stream_v) {
+  if (!sums || !totals || !gamma || !bnp || !dgamma || !dbeta || B <= 0 || C <= 0 || count_total <= 0)
+    return set_error(LASS_ERR_ARG, "lass_bn_bwd_finalize_sync: bad argument");
+  launch_pdl(bn_bwd_finalize_sync_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream_v, sums, B, C, count_total, totals, bnp, dgamma, dbeta,
+             dfilm, dfilm_bstride);
+  LASS_LAUNCH_CHECK("bn_bwd_finalize_sync launch");
 }
 
 int lass_bn_bwd_apply(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride, int x_coff, const void* add,

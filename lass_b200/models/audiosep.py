@@ -94,17 +94,18 @@ class AudioSep(nn.Module):
         sep_segment = self.ss_model(input_dict)["waveform"].squeeze()
         return self.loss_function({"segment": sep_segment}, {"segment": segments.squeeze(1).squeeze()})
 
-    def fused_training_step(self, batch_data_dict, batch_idx, process_group=None):
+    def fused_training_step(self, batch_data_dict, batch_idx, process_group=None, sync_batchnorm=None):
         """``training_step`` + backward + gradient all-reduce (NCCL, when torch.distributed is initialised) + AdamW(amsgrad)
         + the per-step LambdaLR factor, as ONE kernel sequence without autograd.  Only ``l1_wav`` / ``AdamW`` (the reference's
-        configuration, ``config/audiosep_base.yaml``).  Returns the loss of this rank as a 0-d tensor."""
+        configuration, ``config/audiosep_base.yaml``).  ``sync_batchnorm=True`` = the reference Trainer's flag of the same name
+        (BatchNorm statistics over all ranks).  Returns the loss of this rank as a 0-d tensor."""
         if self.loss_function is not l1_wav or self.optimizer_type != "AdamW":
             raise NotImplementedError("the fused step implements l1_wav + AdamW(amsgrad=True)")
         input_dict, segments = self._prepare(batch_data_dict, batch_idx)
         self.ss_model.train()
         scale = self.lr_lambda_func(self.global_step) if self.lr_lambda_func is not None else 1.0
         with torch.no_grad():
-            loss = self.ss_model.train_engine().training_step(input_dict["mixture"], input_dict["condition"],
+            loss = self.ss_model.train_engine(sync_batchnorm, process_group).training_step(input_dict["mixture"], input_dict["condition"],
                                                               segments.reshape(input_dict["mixture"].shape),
                                                               lr=self.learning_rate * scale, process_group=process_group)
         self.global_step += 1

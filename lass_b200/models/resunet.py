@@ -263,14 +263,20 @@ class ResUNet30(nn.Module):
         engine = self.base._get_engine(self.film)
         return {"waveform": engine.forward(mixtures, conditions)}
 
-    def train_engine(self):
+    def train_engine(self, sync_batchnorm=None, process_group=None):
         """The training-step engine of this module (flat fp32 parameter / gradient buffers; created on first use — the
-        module's parameters become views of its flat buffer, values unchanged)."""
+        module's parameters become views of its flat buffer, values unchanged).  ``sync_batchnorm`` (when given) switches
+        BatchNorm statistics over all ranks on or off — the reference's ``sync_batchnorm: True`` Trainer flag
+        (config/audiosep_base.yaml:38, train.py:255-283)."""
         from .. import training
         eng = _TRAIN_ENGINES.get(self)
         if eng is None or eng.device != self.base.pre_conv.weight.device:
             eng = training.TrainEngine(self)
             _TRAIN_ENGINES[self] = eng
+        if sync_batchnorm is not None:
+            eng.sync_batchnorm = bool(sync_batchnorm)
+        if process_group is not None:
+            eng.process_group = process_group
         return eng
 
     @torch.no_grad()

@@ -186,6 +186,21 @@ def bn_bwd_finalize(sums, count, gamma, bnp, dgamma, dbeta, dfilm):
                                            _p(dfilm), dfilm.stride(0) if dfilm is not None else 0, _stream()))
 
 
+def bn_bwd_totals(sums, totals):
+    """This rank's per-channel totals (C, 2) float64 of the per-clip sums (B, C, 2): the SyncBatchNorm all-reduce payload."""
+    _need_cuda(sums, totals)
+    _chk(_cabi.load().lass_bn_bwd_totals(_p(sums), sums.shape[0], sums.shape[1], _p(totals), _stream()))
+
+
+def bn_bwd_finalize_sync(sums, count_total, totals, gamma, bnp, dgamma, dbeta, dfilm):
+    """bn_bwd_finalize for SyncBatchNorm: coefA / coefB from the all-reduced ``totals`` and the global count; dgamma, dbeta,
+    dfilm from this rank's ``sums``."""
+    _need_cuda(sums, totals, gamma, bnp, dgamma, dbeta)
+    B, C = sums.shape[0], sums.shape[1]
+    _chk(_cabi.load().lass_bn_bwd_finalize_sync(_p(sums), B, C, float(count_total), _p(totals), _p(gamma), _p(bnp), _p(dgamma),
+                                                _p(dbeta), _p(dfilm), dfilm.stride(0) if dfilm is not None else 0, _stream()))
+
+
 def bn_bwd_reduce_acc(dact, x, x_coff, C, bnp, beta, sums):
     """bn_bwd_reduce ADDED into ``sums`` (B, C, 2) fp32, which the caller zeroed."""
     _need_cuda(dact, x, bnp, beta, sums)

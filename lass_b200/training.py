@@ -72,11 +72,18 @@ class _Site:
 
 
 class TrainEngine:
-    def __init__(self, model, kernels=None):
+    def __init__(self, model, kernels=None, sync_batchnorm=False, process_group=None):
+        """``sync_batchnorm=True`` = the reference's training configuration (``sync_batchnorm: True``,
+        config/audiosep_base.yaml:38 -> ``torch.nn.SyncBatchNorm`` under DDP, train.py:255-283): every BatchNorm's batch
+        statistics (and the two sums of its backward) are taken over the clips of ALL ranks of ``process_group`` -- one small
+        all-reduce per BatchNorm site in the forward and one in the backward.  Without torch.distributed (or world size 1)
+        it changes nothing.  Default False: statistics per rank (what plain DDP does)."""
         if kernels is None:
             from . import train_kernels as kernels
         self.k = kernels
         self.model = model
+        self.sync_batchnorm = bool(sync_batchnorm)
+        self.process_group = process_group
         base, film = model.base, model.film
         if base.input_channels != 1 or base.output_channels != 1:
             raise NotImplementedError("training is implemented for input_channels == output_channels == 1")
@@ -316,6 +323,9 @@ class TrainEngine:
         for s, st in self.site.items():
             ws.bsums[s] = ws.bsums_flat[o:o + B * st.C * 2].view(B, st.C, 2)
             o += B * st.C * 2
+        # SyncBatchNorm backward: per-channel totals (C, 2) fp64 of every site, the all-reduce payloads
+        ws.btotals = {s: torch.zeros(st.C, 2, dtype=torch.float64, device=dev) for s, st in self.site.items()}
+        ws.sync_world = 1
         # gradients (bf16)
         ws.g_y = [buf(kk, ENC[kk][1], G) for kk in range(7)]
         ws.g_a2 = [buf(kk, ENC[kk][1], G) for kk in range(7)]
@@ -406,6 +416,37 @@ class TrainEngine:
             cv["dec%d.up.dgrad" % j] = C(B, H[lin], W[lin], cin, [(ws.dU[lin], 0, uh * uw * cout, wu[3], 1)],
                                          full_raw=ws.g_xinact[lin])
 
+    # ------------------------------------------------------------------ SyncBatchNorm plumbing
+    def _sync_world(self):
+        """Number of ranks whose clips share BatchNorm statistics (1 = statistics per rank)."""
+        if not self.sync_batchnorm:
+            return 1
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.process_group)
+
+    def _collective_stream(self):
+        """The ONE stream every collective of this engine is issued on (gradient buckets and BatchNorm statistics alike): NCCL
+        operations of one communicator must not run concurrently from two streams -- a bucket all-reduce in flight on a side
+        stream while a statistics all-reduce starts on the compute stream deadlocks (seen on 2 x B200)."""
+        comm = getattr(self, "_comm_stream", None)
+        if comm is None:
+            comm = self._comm_stream = torch.cuda.Stream(device=self.device)
+        return comm
+
+    def _all_reduce_sums(self, t):
+        """Sum a small fp64 statistics tensor over the ranks, in stream order with the kernels around it."""
+        import torch.distributed as dist
+        if self.device.type != "cuda":
+            dist.all_reduce(t, group=self.process_group)
+            return
+        comm, cur = self._collective_stream(), torch.cuda.current_stream()
+        comm.wait_stream(cur)
+        with torch.cuda.stream(comm):
+            dist.all_reduce(t, group=self.process_group)
+        cur.wait_stream(comm)
+
     # ------------------------------------------------------------------ forward (train mode)
     def _bn_fwd(self, ws, site, x, x_coff, out, out_coff):
         """Batch statistics of x[..., x_coff:+C] -> scale / shift, running-stat update, out = lrelu(bn(x) + beta)."""
@@ -413,6 +454,9 @@ class TrainEngine:
         bn = st.bn
         k.bn_stats_acc(x, x_coff, st.C, st.sums)
         count = x.shape[0] * x.shape[1] * x.shape[2]
+        if ws.sync_world > 1:                 # torch.nn.SyncBatchNorm: mean / variance over every rank's pixels
+            self._all_reduce_sums(st.sums)
+            count *= ws.sync_world
         k.bn_finalize(st.sums, count, bn.weight.data, bn.bias.data, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS,
                       st.bnp)
         k.bn_act(x, x_coff, out, out_coff, st.C, st.bnp, ws.beta[:, st.row:st.row + st.C])
@@ -425,6 +469,7 @@ class TrainEngine:
         ws = self._workspace(B, L)
         base = self.model.base
         hi, lo, window, tw = self._spectral_tables()
+        ws.sync_world = self._sync_world()
         self._sums_flat.zero_()          # bn_stats_acc adds into the sums of all sites: one memset per step
         self._nbt += 1                   # every BatchNorm's num_batches_tracked (views of this buffer)
         ws.cond = condition.detach().to(torch.float32).contiguous()
@@ -437,7 +482,9 @@ class TrainEngine:
         # bn0 (per frequency bin over batch x time) + zero time padding + Nyquist drop + pre_conv
         bn0 = base.bn0
         k.bn0_stats(ws.mag, self.sums0)
-        k.bn_finalize(self.sums0, B * ws.T, bn0.weight.data, bn0.bias.data, bn0.running_mean, bn0.running_var,
+        if ws.sync_world > 1:
+            self._all_reduce_sums(self.sums0)
+        k.bn_finalize(self.sums0, B * ws.T * ws.sync_world, bn0.weight.data, bn0.bias.data, bn0.running_mean, bn0.running_var,
                       BN_MOMENTUM, BN_EPS, self.bnp0)
         k.pre_fwd(ws.mag, self.bnp0, base.pre_conv.weight.data.view(32), base.pre_conv.bias.data, ws.x_raw[0])
         cv = ws.conv
@@ -468,8 +515,17 @@ class TrainEngine:
         sums = ws.bsums[site]
         k.bn_bwd_reduce_acc(dact, x, x_coff, st.C, st.bnp, beta, sums)
         count = x.shape[0] * x.shape[1] * x.shape[2]
-        k.bn_bwd_finalize(sums, count, st.bn.weight.data, st.bnp, self.g(name + ".weight"), self.g(name + ".bias"),
-                          ws.dbeta[:, st.row:st.row + st.C])
+        if ws.sync_world > 1:
+            # SyncBatchNorm backward: the input gradient takes the two sums over ALL ranks, the parameter gradients stay local
+            # (the gradient all-reduce averages them like every other parameter's)
+            totals = ws.btotals[site]
+            k.bn_bwd_totals(sums, totals)
+            self._all_reduce_sums(totals)
+            k.bn_bwd_finalize_sync(sums, count * ws.sync_world, totals, st.bn.weight.data, st.bnp, self.g(name + ".weight"),
+                                   self.g(name + ".bias"), ws.dbeta[:, st.row:st.row + st.C])
+        else:
+            k.bn_bwd_finalize(sums, count, st.bn.weight.data, st.bnp, self.g(name + ".weight"), self.g(name + ".bias"),
+                              ws.dbeta[:, st.row:st.row + st.C])
         k.bn_bwd_apply(dact, x, x_coff, st.C, st.bnp, beta, add, add_coff, dx, dx_coff)
 
     def _wgrad(self, ws, name, kind, dy, co, x, ci, taps):
@@ -556,6 +612,8 @@ class TrainEngine:
         buckets — the first overlaps the encoder's backward — and divided by the world size inside the optimizer kernel."""
         import torch.distributed as dist
         k = self.k
+        if process_group is not None:
+            self.process_group = process_group
         wave = self.forward(mixture, condition)
         ws = self._last
         ws.loss_sum.zero_()
@@ -563,9 +621,7 @@ class TrainEngine:
         world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
         works = []
         if world > 1 and self.device.type == "cuda":
-            comm = getattr(self, "_comm_stream", None)
-            if comm is None:
-                comm = self._comm_stream = torch.cuda.Stream(device=self.device)
+            comm = self._collective_stream()
 
             def launch(lo_, hi_):
                 ev = torch.cuda.Event()

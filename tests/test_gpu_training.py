@@ -89,6 +89,38 @@ def test_bn_backward_kernels(K, C, with_add):
     _close(res[1][5], res[0][5], 1e-2, 2e-6, "dx")
 
 
+@pytest.mark.parametrize("C", [32, 384])
+def test_sync_batchnorm_backward_kernels(K, C):
+    """lass_bn_bwd_totals / lass_bn_bwd_finalize_sync (SyncBatchNorm backward) against the emulation; with the totals of ONE rank and
+    its own count they must reproduce the plain finalize, with 'all-reduced' totals only the input-gradient coefficients move."""
+    B, count = 3, 1000
+    g = torch.Generator().manual_seed(C)
+    sums = torch.randn(B, C, 2, generator=g) * 1e-3
+    other = torch.randn(C, 2, generator=g).double() * 1e-3            # what the other ranks would add
+    gamma = torch.rand(C, generator=g) + 0.5
+    bnp0 = torch.rand(6 * C, generator=g) + 0.5
+    outs = {}
+    for name, k, dev in (("emul", E, "cpu"), ("cuda", K, "cuda")):
+        s, ga = sums.to(dev), gamma.to(dev)
+        tot = torch.zeros(C, 2, dtype=torch.float64, device=dev)
+        k.bn_bwd_totals(s, tot)
+        plain = [bnp0.clone().to(dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(B, C, device=dev)]
+        k.bn_bwd_finalize(s, count, ga, *plain)
+        one = [bnp0.clone().to(dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(B, C, device=dev)]
+        k.bn_bwd_finalize_sync(s, count, tot, ga, *one)
+        two = [bnp0.clone().to(dev), torch.zeros(C, device=dev), torch.zeros(C, device=dev), torch.zeros(B, C, device=dev)]
+        k.bn_bwd_finalize_sync(s, 2 * count, tot + other.to(dev), ga, *two)
+        outs[name] = (tot, plain, one, two)
+    _close(outs["cuda"][0], outs["emul"][0], 1e-6, 1e-9, "totals")
+    for i in range(4):
+        _close(outs["cuda"][2][i], outs["cuda"][1][i], 1e-6, 1e-9, "one rank == plain finalize [%d]" % i)
+        _close(outs["cuda"][3][i], outs["emul"][3][i], 1e-5, 1e-9, "two ranks vs emulation [%d]" % i)
+    # parameter gradients stay this rank's; the coefficients take the global sums
+    for i in (1, 2, 3):
+        assert torch.equal(outs["cuda"][3][i], outs["cuda"][2][i])
+    assert not torch.allclose(outs["cuda"][3][0][4 * C:], outs["cuda"][2][0][4 * C:])
+
+
 @pytest.mark.parametrize("C,B,H,W", [(32, 2, 64, 128), (128, 3, 10, 24), (768, 2, 8, 8)])
 def test_fused_reduce_finalize_launches_match_the_separate_ones(K, C, B, H, W):
     """The accumulate-into-zeroed-sums forms the engine uses (lass_bn_stats_acc, lass_bn_bwd_reduce_acc) and the one-launch

@@ -146,6 +146,22 @@ def bn_bwd_finalize(sums, count, gamma, bnp, dgamma, dbeta, dfilm):
     bnp[5 * C:6 * C] = (-scale * t1 / count).float()
 
 
+def bn_bwd_totals(sums, totals):
+    totals.copy_(sums.double().sum(0))
+
+
+def bn_bwd_finalize_sync(sums, count_total, totals, gamma, bnp, dgamma, dbeta, dfilm):
+    B, C = sums.shape[0], sums.shape[1]
+    rstd = bnp[3 * C:4 * C].double()
+    scale = bnp[0:C].double()
+    dbeta.copy_(sums[:, :, 0].double().sum(0).float())
+    dgamma.copy_((rstd * sums[:, :, 1].double().sum(0)).float())
+    if dfilm is not None:
+        dfilm.copy_(sums[:, :, 0])
+    bnp[4 * C:5 * C] = (-scale * rstd * rstd * totals[:, 1] / count_total).float()
+    bnp[5 * C:6 * C] = (-scale * totals[:, 0] / count_total).float()
+
+
 def bn_bwd_apply(dact, x, x_coff, C, bnp, beta, add, add_coff, dx, dx_coff):
     xv, pre = _pre(x, x_coff, C, bnp, beta)
     g = dact[..., :C].float() * torch.where(pre > 0, 1.0, SLOPE)
