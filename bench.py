@@ -470,7 +470,7 @@ def time_train(device, rank, world, steps, warmup, peaks):
     out["conv_tflops_algorithmic"] = flops / step_s / 1e12
     out["frac_of_bf16_sustained"] = flops / step_s / 1e12 / peaks["bf16_tflops_sustained"]
     if world > 1:
-        # the reference's own DDP configuration: sync_batchnorm True (config/audiosep_base.yaml:38) = one small all-reduce per
+        # the reference's own DDP configuration: sync_batchnorm True (config/audiosep_base.yaml:42) = one small all-reduce per
         # BatchNorm site in the forward (33) and in the backward (32) on top of the gradient buckets
         eng.sync_batchnorm = True
         for i in range(2):

@@ -215,7 +215,7 @@ LASS_API int lass_bn_bwd_finalize(const float* sums, int B, int C, double count,
 LASS_API int lass_bn_bwd_reduce_acc(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride,
                                     int x_coff, int B, long long pix_per_clip, int C, const float* bnp, const float* beta,
                                     int beta_bstride, float* sums, void* stream);
-/* SyncBatchNorm backward (the reference trains with sync_batchnorm: True, config/audiosep_base.yaml:38, train.py:255-283 ->
+/* SyncBatchNorm backward (the reference trains with sync_batchnorm: True, config/audiosep_base.yaml:42, train.py:176,266-283 ->
  * torch.nn.SyncBatchNorm): lass_bn_bwd_totals = this rank's per-channel totals (C, 2) fp64 of the per-clip sums (B, C, 2), which
  * the caller all-reduces over the ranks; lass_bn_bwd_finalize_sync = lass_bn_bwd_finalize with the input-gradient coefficients
  * from those all-reduced totals and the GLOBAL pixel count, while dgamma / dbeta / dfilm stay this rank's sums (DDP averages

@@ -355,7 +355,7 @@ __global__ void bn_bwd_finalize_kernel(const float* __restrict__ sums, int B, in
   bn_bwd_finalize_channel(sums, c, B, C, count, bnp, dgamma, dbeta, dfilm, dfilm_bstride);
 }
 
-// SyncBatchNorm backward (the reference trains with sync_batchnorm: True, config/audiosep_base.yaml:38 -> torch.nn.SyncBatchNorm):
+// SyncBatchNorm backward (the reference trains with sync_batchnorm: True, config/audiosep_base.yaml:42 -> torch.nn.SyncBatchNorm):
 // the input gradient needs the two sums over ALL ranks' pixels, the parameter gradients (dgamma, dbeta, dFiLM) stay this rank's
 // (DDP averages them afterwards).  bn_bwd_totals = this rank's per-channel totals (C, 2) fp64 for the all-reduce;
 // bn_bwd_finalize_sync = the finalize with coefficients from the all-reduced totals and the global pixel count.

@@ -267,7 +267,7 @@ class ResUNet30(nn.Module):
         """The training-step engine of this module (flat fp32 parameter / gradient buffers; created on first use — the
         module's parameters become views of its flat buffer, values unchanged).  ``sync_batchnorm`` (when given) switches
         BatchNorm statistics over all ranks on or off — the reference's ``sync_batchnorm: True`` Trainer flag
-        (config/audiosep_base.yaml:38, train.py:255-283)."""
+        (config/audiosep_base.yaml:42, train.py:176,266-283)."""
         from .. import training
         eng = _TRAIN_ENGINES.get(self)
         if eng is None or eng.device != self.base.pre_conv.weight.device:

@@ -74,7 +74,7 @@ class _Site:
 class TrainEngine:
     def __init__(self, model, kernels=None, sync_batchnorm=False, process_group=None):
         """``sync_batchnorm=True`` = the reference's training configuration (``sync_batchnorm: True``,
-        config/audiosep_base.yaml:38 -> ``torch.nn.SyncBatchNorm`` under DDP, train.py:255-283): every BatchNorm's batch
+        config/audiosep_base.yaml:42 -> ``torch.nn.SyncBatchNorm`` under DDP, train.py:176,266-283): every BatchNorm's batch
         statistics (and the two sums of its backward) are taken over the clips of ALL ranks of ``process_group`` -- one small
         all-reduce per BatchNorm site in the forward and one in the backward.  Without torch.distributed (or world size 1)
         it changes nothing.  Default False: statistics per rank (what plain DDP does)."""

@@ -106,7 +106,7 @@ def _sync_worker(rank, world, port, ret):
 
 
 def test_two_rank_sync_batchnorm_equals_one_rank_with_the_whole_batch():
-    """``sync_batchnorm: True`` (reference config/audiosep_base.yaml:38 -> torch.nn.SyncBatchNorm under DDP): two ranks with one
+    """``sync_batchnorm: True`` (reference config/audiosep_base.yaml:42 -> torch.nn.SyncBatchNorm under DDP): two ranks with one
     clip each must reproduce ONE rank training on both clips -- same running statistics, gradient sum = 2 x the whole-batch
     gradient (each rank's loss is the mean over ITS clip), same parameters after the step."""
     with socket.socket() as s:
