@@ -221,6 +221,22 @@ LASS_API int lass_bn_bwd_reduce_acc(const void* dact, int d_cstride, int d_coff,
  * from those all-reduced totals and the GLOBAL pixel count, while dgamma / dbeta / dfilm stay this rank's sums (DDP averages
  * parameter gradients afterwards).  The forward needs no extra entry: the (2, C) fp64 sums of lass_bn_stats are all-reduced
  * before lass_bn_finalize is called with the global count. */
+/* SyncBatchNorm with the statistics exchange fused into the finalize kernels, over NVLink peer memory (no NCCL call, one launch
+ * per site and direction).  peer_sums[p] / peer_flags[p] (HOST arrays of `world` device pointers, p = rank): every rank's flat sums
+ * buffer and flag table (lass_syncbn_max_peers() x 8-byte epochs per flag_index, zero-initialised once), all mapped on this
+ * device (symmetric memory).  The kernel publishes `epoch` (> 0, growing from step to step) to every peer's table, waits for all
+ * peers' epochs, then adds every rank's sums at element `sums_offset` in rank order and finalizes like lass_bn_finalize (sums
+ * (2, C) fp64) / lass_bn_bwd_finalize_sync (sums (B, C, 2) fp32; same B on every rank).  The sums must have been written by
+ * earlier work of `stream`.  *status (device int, may be NULL) is set to 1 if a peer never arrived (spin limit). */
+LASS_API int lass_syncbn_max_peers(void);
+LASS_API int lass_bn_finalize_p2p(const void* const* peer_sums, void* const* peer_flags, int world, int rank,
+                                  long long sums_offset, int flag_index, unsigned long long epoch, double count_total,
+                                  const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                  float momentum, float eps, int C, float* bnp, int* status, void* stream);
+LASS_API int lass_bn_bwd_finalize_p2p(const void* const* peer_sums, void* const* peer_flags, int world, int rank,
+                                      long long sums_offset, int flag_index, unsigned long long epoch, int B, int C,
+                                      double count_total, const float* gamma, float* bnp, float* dgamma, float* dbeta,
+                                      float* dfilm, int dfilm_bstride, int* status, void* stream);
 LASS_API int lass_bn_bwd_totals(const float* sums, int B, int C, double* totals, void* stream);
 LASS_API int lass_bn_bwd_finalize_sync(const float* sums, int B, int C, double count_total, const double* totals,
                                        const float* gamma, float* bnp, float* dgamma, float* dbeta, float* dfilm,

@@ -394,6 +394,105 @@ __global__ void bn_bwd_finalize_sync_kernel(const float* __restrict__ sums, int 
   bnp[5 * C + c] = (float)(-scale * totals[2 * c] / count_total);
 }
 
+// ---- SyncBatchNorm over NVLink peer memory: the statistics exchange fused INTO the finalize kernels ----
+// Every rank keeps its per-site sums in a symmetric-memory buffer that all ranks of the node have mapped (peer pointers over
+// NVLink / NVSwitch).  Instead of [all-reduce launch -> finalize launch] the finalize kernel itself (i) tells every peer "my sums
+// of this site are complete" by writing the step's epoch number into its slot of the peer's flag table (st.release.sys after a
+// system fence; the sums were written by the previous kernel of this stream), (ii) waits until all peers' epochs have arrived
+// in its own table (ld.acquire.sys), (iii) loads every rank's sums through the peer pointers and adds them IN RANK ORDER in fp64
+// -- the same numbers in the same order on every rank, so all ranks derive bit-identical tables -- and (iv) finalizes.
+// One launch per site and direction, no NCCL call, ~2 NVLink round trips of latency.  Flags only ever grow (epoch = step
+// counter), so nothing is reset; the sums are double-buffered by epoch parity, so a fast rank's memset for step t + 1 cannot
+// touch what a slow rank still reads for step t.  A spin that exceeds kSpinLimit polls sets *status and gives up (wrong numbers,
+// loudly reported by the host) rather than hanging the GPU.
+constexpr int kMaxPeers = 16;
+constexpr long long kSpinLimit = 1ll << 26;
+struct PeerTable {
+  const void* sums[kMaxPeers];            // base of every rank's flat sums buffer
+  unsigned long long* flags[kMaxPeers];   // base of every rank's flag table: [flag_index][kMaxPeers] epochs
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// publish this rank's epoch to all peers (block 0 only) and wait for all peers' epochs (every block); false on timeout
+__device__ __forceinline__ bool peer_exchange(const PeerTable& pt, int world, int rank, int flag_index, unsigned long long epoch, int* status) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  if (threadIdx.x < world) {
+    const int p = threadIdx.x;
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      st_release_sys(pt.flags[p] + (size_t)flag_index * kMaxPeers + rank, epoch);
+    }
+    const unsigned long long* mine = pt.flags[rank] + (size_t)flag_index * kMaxPeers + p;
+    long long spins = 0;
+    while (ld_acquire_sys(mine) < epoch) {
+      if (++spins > kSpinLimit) {
+        ok = 0;
+        if (status) atomicExch(status, 1);
+        break;
+      }
+    }
+  }
+  __syncthreads();
+  return ok != 0;
+}
+
+__global__ void bn_finalize_p2p_kernel(PeerTable pt, int world, int rank, long long sums_offset, int flag_index, unsigned long long epoch,
+                                       double count_total, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps, int C,
+                                       float* __restrict__ bnp, int* __restrict__ status) {
+  griddep_launch_dependents();
+  griddep_wait();
+  peer_exchange(pt, world, rank, flag_index, epoch, status);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int p = 0; p < world; ++p) {
+    const double* ps = reinterpret_cast<const double*>(pt.sums[p]) + sums_offset;     // (2, C) of this site
+    s += __ldcv(ps + c);
+    q += __ldcv(ps + C + c);
+  }
+  bn_finalize_channel(s, q, c, C, count_total, gamma, beta, running_mean, running_var, momentum, eps, bnp);
+}
+
+__global__ void bn_bwd_finalize_p2p_kernel(PeerTable pt, int world, int rank, long long sums_offset, int flag_index, unsigned long long epoch,
+                                           int B, int C, double count_total, float* __restrict__ bnp, float* __restrict__ dgamma,
+                                           float* __restrict__ dbeta, float* __restrict__ dfilm, int dfilm_bstride, int* __restrict__ status) {
+  griddep_launch_dependents();
+  griddep_wait();
+  peer_exchange(pt, world, rank, flag_index, epoch, status);
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double g1 = 0.0, g2 = 0.0, l1 = 0.0, l2 = 0.0;
+  for (int p = 0; p < world; ++p) {
+    const float* ps = reinterpret_cast<const float*>(pt.sums[p]) + sums_offset;       // (B, C, 2) of this site
+    double t1 = 0.0, t2 = 0.0;
+    for (int b = 0; b < B; ++b) {
+      const float2 v = __ldcv(reinterpret_cast<const float2*>(ps) + (size_t)b * C + c);
+      t1 += (double)v.x;
+      t2 += (double)v.y;
+      if (p == rank && dfilm) dfilm[(size_t)b * dfilm_bstride + c] = v.x;
+    }
+    g1 += t1;
+    g2 += t2;
+    if (p == rank) l1 = t1, l2 = t2;
+  }
+  const double scale = (double)bnp[c], rstd = (double)bnp[3 * C + c];
+  dbeta[c] = (float)l1;                                  // this rank's share (the gradient all-reduce averages parameter gradients)
+  dgamma[c] = (float)(rstd * l2);
+  bnp[4 * C + c] = (float)(-scale * rstd * rstd * g2 / count_total);
+  bnp[5 * C + c] = (float)(-scale * g1 / count_total);
+}
+
 __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_apply_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
                                                                    const void* __restrict__ x, int x_fp16, int x_cstride, int x_coff,
                                                                    const void* __restrict__ add, int add_cstride, int add_coff,
@@ -1213,6 +1312,44 @@ int lass_bn_bwd_finalize_sync(const float* sums, int B, int C, double count_tota
   launch_pdl(bn_bwd_finalize_sync_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream_v, sums, B, C, count_total, totals, bnp, dgamma, dbeta,
              dfilm, dfilm_bstride);
   LASS_LAUNCH_CHECK("bn_bwd_finalize_sync launch");
+}
+
+static int fill_peer_table(PeerTable* pt, const void* const* peer_sums, void* const* peer_flags, int world, int rank, const char* who) {
+  if (!peer_sums || !peer_flags || world < 1 || world > kMaxPeers || rank < 0 || rank >= world)
+    return set_error(LASS_ERR_ARG, "%s: bad peer table (world %d, rank %d, at most %d peers)", who, world, rank, kMaxPeers);
+  memset(pt, 0, sizeof(*pt));
+  for (int p = 0; p < world; ++p) {
+    if (!peer_sums[p] || !peer_flags[p]) return set_error(LASS_ERR_ARG, "%s: null peer pointer %d", who, p);
+    pt->sums[p] = peer_sums[p];
+    pt->flags[p] = reinterpret_cast<unsigned long long*>(peer_flags[p]);
+  }
+  return LASS_OK;
+}
+
+int lass_syncbn_max_peers(void) { return kMaxPeers; }
+
+int lass_bn_finalize_p2p(const void* const* peer_sums, void* const* peer_flags, int world, int rank, long long sums_offset, int flag_index,
+                         unsigned long long epoch, double count_total, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float momentum, float eps, int C, float* bnp, int* status, void* stream_v) {
+  PeerTable pt;
+  if (int e = fill_peer_table(&pt, peer_sums, peer_flags, world, rank, "lass_bn_finalize_p2p")) return e;
+  if (!gamma || !beta || !running_mean || !running_var || !bnp || C <= 0 || count_total <= 0 || sums_offset < 0 || flag_index < 0 || epoch == 0)
+    return set_error(LASS_ERR_ARG, "lass_bn_finalize_p2p: bad argument");
+  launch_pdl(bn_finalize_p2p_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream_v, pt, world, rank, sums_offset, flag_index, epoch, count_total,
+             gamma, beta, running_mean, running_var, momentum, eps, C, bnp, status);
+  LASS_LAUNCH_CHECK("bn_finalize_p2p launch");
+}
+
+int lass_bn_bwd_finalize_p2p(const void* const* peer_sums, void* const* peer_flags, int world, int rank, long long sums_offset, int flag_index,
+                             unsigned long long epoch, int B, int C, double count_total, const float* gamma, float* bnp, float* dgamma,
+                             float* dbeta, float* dfilm, int dfilm_bstride, int* status, void* stream_v) {
+  PeerTable pt;
+  if (int e = fill_peer_table(&pt, peer_sums, peer_flags, world, rank, "lass_bn_bwd_finalize_p2p")) return e;
+  if (!gamma || !bnp || !dgamma || !dbeta || B <= 0 || C <= 0 || count_total <= 0 || sums_offset < 0 || flag_index < 0 || epoch == 0)
+    return set_error(LASS_ERR_ARG, "lass_bn_bwd_finalize_p2p: bad argument");
+  launch_pdl(bn_bwd_finalize_p2p_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream_v, pt, world, rank, sums_offset, flag_index, epoch, B, C,
+             count_total, bnp, dgamma, dbeta, dfilm, dfilm_bstride, status);
+  LASS_LAUNCH_CHECK("bn_bwd_finalize_p2p launch");
 }
 
 int lass_bn_bwd_apply(const void* dact, int d_cstride, int d_coff, const void* x, int x_fp16, int x_cstride, int x_coff, const void* add,

@@ -186,6 +186,37 @@ def bn_bwd_finalize(sums, count, gamma, bnp, dgamma, dbeta, dfilm):
                                            _p(dfilm), dfilm.stride(0) if dfilm is not None else 0, _stream()))
 
 
+class PeerTable:
+    """Every rank's flat sums buffer and flag table as the HOST pointer arrays the ``*_p2p`` entry points take."""
+
+    def __init__(self, sums_ptrs, flag_ptrs, rank, status):
+        import ctypes
+        self.world, self.rank = len(sums_ptrs), int(rank)
+        if self.world > _cabi.load().lass_syncbn_max_peers():
+            raise RuntimeError("at most %d ranks share BatchNorm statistics over peer memory" % _cabi.load().lass_syncbn_max_peers())
+        self.sums = (ctypes.c_void_p * self.world)(*[int(p) for p in sums_ptrs])
+        self.flags = (ctypes.c_void_p * self.world)(*[int(p) for p in flag_ptrs])
+        self.status = status
+
+
+def bn_finalize_p2p(table, sums_offset, flag_index, epoch, count_total, gamma, beta, running_mean, running_var, momentum, eps, bnp):
+    """bn_finalize over the sums of ALL ranks, the exchange fused into the kernel (NVLink peer memory, no collective call)."""
+    _need_cuda(gamma, beta, running_mean, running_var, bnp, table.status)
+    _chk(_cabi.load().lass_bn_finalize_p2p(table.sums, table.flags, table.world, table.rank, int(sums_offset), int(flag_index),
+                                           int(epoch), float(count_total), _p(gamma), _p(beta), _p(running_mean),
+                                           _p(running_var), float(momentum), float(eps), gamma.numel(), _p(bnp),
+                                           _p(table.status), _stream()))
+
+
+def bn_bwd_finalize_p2p(table, sums_offset, flag_index, epoch, B, count_total, gamma, bnp, dgamma, dbeta, dfilm):
+    """bn_bwd_finalize_sync with the totals taken from every rank's per-clip sums through peer memory inside the kernel."""
+    _need_cuda(gamma, bnp, dgamma, dbeta, table.status)
+    _chk(_cabi.load().lass_bn_bwd_finalize_p2p(table.sums, table.flags, table.world, table.rank, int(sums_offset),
+                                               int(flag_index), int(epoch), int(B), gamma.numel(), float(count_total),
+                                               _p(gamma), _p(bnp), _p(dgamma), _p(dbeta), _p(dfilm),
+                                               dfilm.stride(0) if dfilm is not None else 0, _p(table.status), _stream()))
+
+
 def bn_bwd_totals(sums, totals):
     """This rank's per-channel totals (C, 2) float64 of the per-clip sums (B, C, 2): the SyncBatchNorm all-reduce payload."""
     _need_cuda(sums, totals)

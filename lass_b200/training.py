@@ -72,18 +72,25 @@ class _Site:
 
 
 class TrainEngine:
-    def __init__(self, model, kernels=None, sync_batchnorm=False, process_group=None):
+    def __init__(self, model, kernels=None, sync_batchnorm=False, process_group=None, sync_transport="nccl"):
         """``sync_batchnorm=True`` = the reference's training configuration (``sync_batchnorm: True``,
         config/audiosep_base.yaml:42 -> ``torch.nn.SyncBatchNorm`` under DDP, train.py:176,266-283): every BatchNorm's batch
         statistics (and the two sums of its backward) are taken over the clips of ALL ranks of ``process_group`` -- one small
         all-reduce per BatchNorm site in the forward and one in the backward.  Without torch.distributed (or world size 1)
-        it changes nothing.  Default False: statistics per rank (what plain DDP does)."""
+        it changes nothing.  Default False: statistics per rank (what plain DDP does).  ``sync_transport="p2p"`` (CUDA, one
+        node): the exchange is fused into the finalize kernels over NVLink peer memory (symmetric memory; one launch per site
+        and direction, no collective call) instead of one NCCL all-reduce per site (``"nccl"``)."""
         if kernels is None:
             from . import train_kernels as kernels
         self.k = kernels
         self.model = model
         self.sync_batchnorm = bool(sync_batchnorm)
         self.process_group = process_group
+        if sync_transport not in ("nccl", "p2p"):
+            raise ValueError("sync_transport: 'nccl' or 'p2p'")
+        self.sync_transport = sync_transport
+        self._p2p = None              # forward-side symmetric buffers (created collectively on first use)
+        self._epoch = 0               # forward calls so far: the flag value peers wait for, its parity picks the sums half
         base, film = model.base, model.film
         if base.input_channels != 1 or base.output_channels != 1:
             raise NotImplementedError("training is implemented for input_channels == output_channels == 1")
@@ -447,13 +454,90 @@ class TrainEngine:
             dist.all_reduce(t, group=self.process_group)
         cur.wait_stream(comm)
 
+    # flag_index of the peer exchange: forward site s -> s, bn0 -> 32, backward site s -> 64 + s
+    _FLAG_ROWS = 128
+
+    def _p2p_active(self, ws):
+        return ws.sync_world > 1 and self.sync_transport == "p2p" and self.device.type == "cuda"
+
+    def _p2p_group(self):
+        import torch.distributed as dist
+        return self.process_group if self.process_group is not None else dist.group.WORLD
+
+    def _p2p_setup(self):
+        """COLLECTIVE (every rank, same point of the program): the forward sums of all sites (+ bn0), twice (epoch parity), and
+        the flag table, in symmetric memory mapped by every rank of the node."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        from types import SimpleNamespace
+        group, dev = self._p2p_group(), self.device
+        order = sorted(self.site)
+        F = self.n_fft // 2 + 1
+        total = sum(2 * self.site[s].C for s in order) + 2 * F
+        buf = symm.empty(2 * total, dtype=torch.float64, device=dev)
+        flags = symm.empty(self._FLAG_ROWS * 16, dtype=torch.int64, device=dev)
+        buf.zero_()
+        flags.zero_()
+        torch.cuda.synchronize(dev)
+        h_buf, h_fl = symm.rendezvous(buf, group), symm.rendezvous(flags, group)
+        dist.barrier(group)                     # every rank's flags are zero before anyone publishes an epoch
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        p = SimpleNamespace(buf=buf, flags=flags, handles=(h_buf, h_fl), total=total, status=status, offsets={}, views=[],
+                            flag_ptrs=list(h_fl.buffer_ptrs), rank=dist.get_rank(group),
+                            table=self.k.PeerTable(h_buf.buffer_ptrs, h_fl.buffer_ptrs, dist.get_rank(group), status))
+        for h in range(2):
+            flat = buf[h * total:(h + 1) * total]
+            sites, o = {}, 0
+            for s_ in order:
+                C = self.site[s_].C
+                sites[s_] = flat[o:o + 2 * C].view(2, C)
+                p.offsets[s_] = o
+                o += 2 * C
+            p.offsets["bn0"] = o
+            p.views.append(SimpleNamespace(flat=flat, sites=sites, sums0=flat[o:o + 2 * F].view(2, F)))
+        self._p2p = p
+
+    def _p2p_setup_ws(self, ws):
+        """COLLECTIVE: this workspace's backward sums (B, C, 2) of all sites, twice, in symmetric memory."""
+        import torch.distributed._symmetric_memory as symm
+        from types import SimpleNamespace
+        total = sum(ws.B * st.C * 2 for st in self.site.values())
+        buf = symm.empty(2 * total, dtype=torch.float32, device=self.device)
+        buf.zero_()
+        torch.cuda.synchronize(self.device)
+        h_buf = symm.rendezvous(buf, self._p2p_group())
+        p = SimpleNamespace(buf=buf, handle=h_buf, total=total, offsets={}, views=[],
+                            table=self.k.PeerTable(h_buf.buffer_ptrs, self._p2p.flag_ptrs, self._p2p.rank, self._p2p.status))
+        for h in range(2):
+            flat = buf[h * total:(h + 1) * total]
+            sites, o = {}, 0
+            for s_, st in self.site.items():
+                sites[s_] = flat[o:o + ws.B * st.C * 2].view(ws.B, st.C, 2)
+                p.offsets[s_] = o
+                o += ws.B * st.C * 2
+            p.views.append(SimpleNamespace(flat=flat, sites=sites))
+        ws.p2p = p
+
+    def check_sync_status(self):
+        """Raise if a peer-memory exchange ever timed out (a rank that never arrived); synchronises the device."""
+        if self._p2p is not None and int(self._p2p.status.item()) != 0:
+            raise RuntimeError("sync_batchnorm over peer memory: a rank never published its statistics (spin limit reached)")
+
     # ------------------------------------------------------------------ forward (train mode)
     def _bn_fwd(self, ws, site, x, x_coff, out, out_coff):
         """Batch statistics of x[..., x_coff:+C] -> scale / shift, running-stat update, out = lrelu(bn(x) + beta)."""
         k, st = self.k, self.site[site]
         bn = st.bn
-        k.bn_stats_acc(x, x_coff, st.C, st.sums)
         count = x.shape[0] * x.shape[1] * x.shape[2]
+        if self._p2p_active(ws):              # statistics exchange fused into the finalize kernel (NVLink peer memory)
+            p = self._p2p
+            h = ws.epoch & 1
+            k.bn_stats_acc(x, x_coff, st.C, p.views[h].sites[site])
+            k.bn_finalize_p2p(p.table, h * p.total + p.offsets[site], site, ws.epoch, count * ws.sync_world, bn.weight.data,
+                              bn.bias.data, bn.running_mean, bn.running_var, BN_MOMENTUM, BN_EPS, st.bnp)
+            k.bn_act(x, x_coff, out, out_coff, st.C, st.bnp, ws.beta[:, st.row:st.row + st.C])
+            return
+        k.bn_stats_acc(x, x_coff, st.C, st.sums)
         if ws.sync_world > 1:                 # torch.nn.SyncBatchNorm: mean / variance over every rank's pixels
             self._all_reduce_sums(st.sums)
             count *= ws.sync_world
@@ -470,7 +554,16 @@ class TrainEngine:
         base = self.model.base
         hi, lo, window, tw = self._spectral_tables()
         ws.sync_world = self._sync_world()
-        self._sums_flat.zero_()          # bn_stats_acc adds into the sums of all sites: one memset per step
+        self._epoch += 1
+        ws.epoch = self._epoch
+        if self._p2p_active(ws):
+            if self._p2p is None:
+                self._p2p_setup()
+            if getattr(ws, "p2p", None) is None:
+                self._p2p_setup_ws(ws)
+            self._p2p.views[ws.epoch & 1].flat.zero_()
+        else:
+            self._sums_flat.zero_()      # bn_stats_acc adds into the sums of all sites: one memset per step
         self._nbt += 1                   # every BatchNorm's num_batches_tracked (views of this buffer)
         ws.cond = condition.detach().to(torch.float32).contiguous()
         wave_in = mixture.detach().to(torch.float32).reshape(B, L).contiguous()
@@ -481,11 +574,18 @@ class TrainEngine:
         k.film(ws.cond, film_w, film_b, ws.beta)
         # bn0 (per frequency bin over batch x time) + zero time padding + Nyquist drop + pre_conv
         bn0 = base.bn0
-        k.bn0_stats(ws.mag, self.sums0)
-        if ws.sync_world > 1:
-            self._all_reduce_sums(self.sums0)
-        k.bn_finalize(self.sums0, B * ws.T * ws.sync_world, bn0.weight.data, bn0.bias.data, bn0.running_mean, bn0.running_var,
-                      BN_MOMENTUM, BN_EPS, self.bnp0)
+        if self._p2p_active(ws):
+            p = self._p2p
+            h = ws.epoch & 1
+            k.bn0_stats(ws.mag, p.views[h].sums0)
+            k.bn_finalize_p2p(p.table, h * p.total + p.offsets["bn0"], 32, ws.epoch, B * ws.T * ws.sync_world, bn0.weight.data,
+                              bn0.bias.data, bn0.running_mean, bn0.running_var, BN_MOMENTUM, BN_EPS, self.bnp0)
+        else:
+            k.bn0_stats(ws.mag, self.sums0)
+            if ws.sync_world > 1:
+                self._all_reduce_sums(self.sums0)
+            k.bn_finalize(self.sums0, B * ws.T * ws.sync_world, bn0.weight.data, bn0.bias.data, bn0.running_mean,
+                          bn0.running_var, BN_MOMENTUM, BN_EPS, self.bnp0)
         k.pre_fwd(ws.mag, self.bnp0, base.pre_conv.weight.data.view(32), base.pre_conv.bias.data, ws.x_raw[0])
         cv = ws.conv
         for kk in range(7):
@@ -512,9 +612,18 @@ class TrainEngine:
         k, st = self.k, self.site[site]
         name = self.site_name[site]
         beta = ws.beta[:, st.row:st.row + st.C]
+        count = x.shape[0] * x.shape[1] * x.shape[2]
+        if self._p2p_active(ws):
+            p = ws.p2p
+            h = ws.epoch & 1
+            k.bn_bwd_reduce_acc(dact, x, x_coff, st.C, st.bnp, beta, p.views[h].sites[site])
+            k.bn_bwd_finalize_p2p(p.table, h * p.total + p.offsets[site], 64 + site, ws.epoch, ws.B, count * ws.sync_world,
+                                  st.bn.weight.data, st.bnp, self.g(name + ".weight"), self.g(name + ".bias"),
+                                  ws.dbeta[:, st.row:st.row + st.C])
+            k.bn_bwd_apply(dact, x, x_coff, st.C, st.bnp, beta, add, add_coff, dx, dx_coff)
+            return
         sums = ws.bsums[site]
         k.bn_bwd_reduce_acc(dact, x, x_coff, st.C, st.bnp, beta, sums)
-        count = x.shape[0] * x.shape[1] * x.shape[2]
         if ws.sync_world > 1:
             # SyncBatchNorm backward: the input gradient takes the two sums over ALL ranks, the parameter gradients stay local
             # (the gradient all-reduce averages them like every other parameter's)
@@ -561,7 +670,10 @@ class TrainEngine:
         base = self.model.base
         hi, lo, window, tw = self._spectral_tables()
         dwave = dwave.detach().to(torch.float32).reshape(B, L).contiguous()
-        ws.bsums_flat.zero_()
+        if self._p2p_active(ws):
+            ws.p2p.views[ws.epoch & 1].flat.zero_()
+        else:
+            ws.bsums_flat.zero_()
         # the weight-gradient and bias-sum launches ADD into the gradient buffers: one memset each per step instead of one per
         # launch (a launch behind a memset node cannot overlap its predecessor's tail)
         self.G[:self.live_end].zero_()

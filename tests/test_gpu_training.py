@@ -121,6 +121,66 @@ def test_sync_batchnorm_backward_kernels(K, C):
     assert not torch.allclose(outs["cuda"][3][0][4 * C:], outs["cuda"][2][0][4 * C:])
 
 
+@pytest.mark.parametrize("C,world", [(32, 2), (384, 3)])
+def test_sync_batchnorm_peer_memory_kernels(K, C, world):
+    """lass_bn_finalize_p2p / lass_bn_bwd_finalize_p2p: `world` ranks played on ONE GPU (peer pointers are just device pointers
+    here) -- each kernel publishes its epoch, finds the others' already there, adds everybody's sums in rank order.  All
+    ranks must produce identical tables = the plain finalize of the summed sums; parameter gradients stay per rank."""
+    B, count, epoch, off = 2, 500, 7, 64
+    g = torch.Generator().manual_seed(C + world)
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    fsums = [torch.cat([torch.randn(C, generator=g) * 30, torch.rand(C, generator=g) * 900 + 500]).double().view(2, C) for _ in range(world)]
+    bsums = [torch.randn(B, C, 2, generator=g) * 1e-3 for _ in range(world)]
+    # emulation of the result: finalize over the summed sums with the global count
+    bnp_ref, rm_ref, rv_ref = torch.zeros(6 * C), torch.zeros(C), torch.ones(C)
+    E.bn_finalize(sum(fsums), world * count, gamma, beta, rm_ref, rv_ref, 0.01, 1e-5, bnp_ref)
+    tot = sum(b.double().sum(0) for b in bsums)
+    dev = "cuda"
+    flags = [torch.zeros(128 * 16, dtype=torch.int64, device=dev) for _ in range(world)]
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    fbuf = [torch.zeros(off + 2 * C, dtype=torch.float64, device=dev) for _ in range(world)]
+    bbuf = [torch.zeros(off + B * C * 2, dtype=torch.float32, device=dev) for _ in range(world)]
+    for r in range(world):
+        fbuf[r][off:] = fsums[r].reshape(-1).to(dev)
+        bbuf[r][off:] = bsums[r].reshape(-1).to(dev)
+    outs = []
+    # the peers "have arrived": their epochs are already in every rank's table (the waiting itself -- ranks that really run
+    # concurrently -- is what tools/gpu_syncbn_check.py covers on two GPUs); each rank's own slot is written by its kernel
+    for r in range(world):
+        for p_ in range(world):
+            if p_ != r:
+                flags[r][3 * 16 + p_] = epoch
+                flags[r][(64 + 3) * 16 + p_] = epoch
+    torch.cuda.synchronize()
+    for r in range(world):
+        ft = K.PeerTable([b.data_ptr() for b in fbuf], [f.data_ptr() for f in flags], r, status)
+        bt = K.PeerTable([b.data_ptr() for b in bbuf], [f.data_ptr() for f in flags], r, status)
+        o = dict(bnp=torch.zeros(6 * C, device=dev), rm=torch.zeros(C, device=dev), rv=torch.ones(C, device=dev),
+                 dg=torch.zeros(C, device=dev), db=torch.zeros(C, device=dev), dfilm=torch.zeros(B, C, device=dev))
+        K.bn_finalize_p2p(ft, off, 3, epoch, world * count, gamma.to(dev), beta.to(dev), o["rm"], o["rv"], 0.01, 1e-5, o["bnp"])
+        K.bn_bwd_finalize_p2p(bt, off, 64 + 3, epoch, B, world * count, gamma.to(dev), o["bnp"], o["dg"], o["db"], o["dfilm"])
+        outs.append(o)
+    torch.cuda.synchronize()
+    for r in range(world):                       # every rank published its epoch into its slot of every table, nothing else
+        want = torch.zeros(128 * 16, dtype=torch.int64)
+        want[3 * 16:3 * 16 + world] = epoch
+        want[(64 + 3) * 16:(64 + 3) * 16 + world] = epoch
+        assert torch.equal(flags[r].cpu(), want)
+    assert int(status.item()) == 0, "a rank never arrived"
+    for r in range(world):
+        o = outs[r]
+        _close(o["bnp"][:4 * C], bnp_ref[:4 * C], 1e-6, 1e-7, "forward tables, rank %d" % r)
+        _close(o["rm"], rm_ref, 1e-6, 1e-8, "running mean")
+        _close(o["rv"], rv_ref, 1e-6, 1e-8, "running var")
+        assert torch.equal(o["bnp"], outs[0]["bnp"])                            # bit-identical tables on every rank
+        ref = [bnp_ref.clone(), torch.zeros(C), torch.zeros(C), torch.zeros(B, C)]
+        E.bn_bwd_finalize_sync(bsums[r], world * count, tot, gamma, *ref)
+        _close(o["bnp"][4 * C:], ref[0][4 * C:], 1e-5, 1e-9, "backward coefficients, rank %d" % r)
+        _close(o["dg"], ref[1], 1e-5, 1e-9, "dgamma (this rank's)")
+        _close(o["db"], ref[2], 1e-5, 1e-9, "dbeta (this rank's)")
+        assert torch.equal(o["dfilm"].cpu(), bsums[r][:, :, 0])
+
+
 @pytest.mark.parametrize("C,B,H,W", [(32, 2, 64, 128), (128, 3, 10, 24), (768, 2, 8, 8)])
 def test_fused_reduce_finalize_launches_match_the_separate_ones(K, C, B, H, W):
     """The accumulate-into-zeroed-sums forms the engine uses (lass_bn_stats_acc, lass_bn_bwd_reduce_acc) and the one-launch

@@ -69,6 +69,35 @@ def main():
                  "swapped_vs_first": float(cs(rep["swapped"], res[True]["G"], dim=0))}
         print(json.dumps({"sync_run_reproducibility": repro}))
         assert min(repro.values()) > 0.9999, repro          # no race, no rank asymmetry
+    # The peer-memory transport (exchange fused into the finalize kernels) against the NCCL one: same sums added in the same
+    # order for two ranks, so the forward must agree bit for bit and the gradient to the atomics' noise; then a second step
+    # (epoch 2: the other half of the double-buffered sums, flags never reset).
+    p2p = {}
+    for transport in ("p2p", "nccl"):
+        model, _ = helpers.build_module(device=dev)
+        model.train()
+        eng = training.TrainEngine(model, sync_batchnorm=True, sync_transport=transport)
+        with torch.no_grad():
+            eng.training_step(mix[sl].to(dev), cond[sl].to(dev), tgt[sl].to(dev), lr=0.0)
+            g1, w1 = eng.G[:eng.live_end].clone(), eng._last.wave.clone()
+            # lr = 0: the parameters stay put (AdamW's first steps are sign-like, so 1e-5 gradient noise would otherwise send the
+            # two runs down different paths), the train-mode forward must then repeat itself exactly
+            eng.training_step(mix[sl].to(dev), cond[sl].to(dev), tgt[sl].to(dev), lr=0.0)
+            eng.training_step(mix[sl].to(dev), cond[sl].to(dev), tgt[sl].to(dev), lr=0.0)
+        eng.check_sync_status()
+        p2p[transport] = (g1, w1, eng.G[:eng.live_end].clone(), eng._last.wave.clone(), eng.P[:eng.live_end].clone())
+    torch.cuda.synchronize()
+    if rank == 0:
+        cs = torch.nn.functional.cosine_similarity
+        a, b = p2p["p2p"], p2p["nccl"]
+        out_p = {"step1_wave_snr_db": float(factory.snr_db(b[1].cpu()[None], a[1].cpu()[None])[0]),
+                 "step1_grad_cosine": float(cs(a[0], b[0], dim=0)),
+                 "step3_wave_snr_db": float(factory.snr_db(b[3].cpu()[None], a[3].cpu()[None])[0]),
+                 "step3_grad_cosine": float(cs(a[2], b[2], dim=0)),
+                 "step3_param_maxabs_diff": float((a[4] - b[4]).abs().max())}
+        print(json.dumps({"peer_memory_transport_vs_nccl": out_p}))
+        assert out_p["step1_wave_snr_db"] > 100.0 and out_p["step1_grad_cosine"] > 0.9999, out_p
+        assert out_p["step3_wave_snr_db"] > 100.0 and out_p["step3_grad_cosine"] > 0.9999, out_p
     # Plumbing check free of batch-size effects: when every rank holds the SAME clips, the all-reduced sums are exactly `world` x
     # the local ones and the global count `world` x the local count (exact in fp64), so sync on / off must agree to the run-to-run
     # noise of the fp32 atomics.
