@@ -507,10 +507,32 @@ def time_train(device, rank, world, steps, warmup, peaks):
         dist.barrier()
         torch.cuda.synchronize()
         sync_s = sharding.max_over_ranks(s0.elapsed_time(s1) * 1e-3 / steps, device)
-        eng.sync_batchnorm = False
         out["sync_batchnorm"] = {"ms_per_step": sync_s * 1e3, "steps_per_s": 1.0 / sync_s, "small_allreduces_per_step": 65,
                                  "note": "BatchNorm statistics over all ranks (torch.nn.SyncBatchNorm semantics), NCCL all-reduce "
                                          "of (2, C) fp64 sums per site; the headline ms_per_step above is with per-rank statistics"}
+        # the same with the exchange fused into the finalize kernels over NVLink peer memory (no NCCL call per site)
+        try:
+            eng.sync_transport = "p2p"
+            for i in range(2):
+                step(i)
+            dist.barrier()
+            torch.cuda.synchronize()
+            s0.record()
+            for i in range(steps):
+                step(warmup + i)
+            s1.record()
+            dist.barrier()
+            torch.cuda.synchronize()
+            p2p_s = sharding.max_over_ranks(s0.elapsed_time(s1) * 1e-3 / steps, device)
+            eng.check_sync_status()
+            out["sync_batchnorm"]["peer_memory"] = {
+                "ms_per_step": p2p_s * 1e3, "steps_per_s": 1.0 / p2p_s, "collective_calls_per_step_for_statistics": 0,
+                "note": "lass_bn_finalize_p2p / lass_bn_bwd_finalize_p2p: every rank's sums read through NVLink peer pointers "
+                        "(torch symmetric memory) inside the finalize kernel, epoch flags instead of a collective"}
+        except Exception as exc:          # e.g. symmetric memory unavailable on this box: report, keep the line
+            out["sync_batchnorm"]["peer_memory"] = {"unavailable": repr(exc)[:300]}
+        eng.sync_transport = "nccl"
+        eng.sync_batchnorm = False
         n = int(eng.live_end)
         for _ in range(2):
             dist.all_reduce(eng.G[:n])

@@ -226,7 +226,9 @@ LASS_API int lass_bn_bwd_reduce_acc(const void* dact, int d_cstride, int d_coff,
  * buffer and flag table (lass_syncbn_max_peers() x 8-byte epochs per flag_index, zero-initialised once), all mapped on this
  * device (symmetric memory).  The kernel publishes `epoch` (> 0, growing from step to step) to every peer's table, waits for all
  * peers' epochs, then adds every rank's sums at element `sums_offset` in rank order and finalizes like lass_bn_finalize (sums
- * (2, C) fp64) / lass_bn_bwd_finalize_sync (sums (B, C, 2) fp32; same B on every rank).  The sums must have been written by
+ * (2, C) fp64) / lass_bn_bwd_finalize_sync.  Backward: the rank first adds ITS per-clip sums (B, C, 2) fp32 at float element
+ * `sums_offset` to per-channel totals (C, 2) fp64 which it writes at double element `totals_offset` of its own buffer, publishes,
+ * and then reads only the peers' totals (C <= 1024).  The sums must have been written by
  * earlier work of `stream`.  *status (device int, may be NULL) is set to 1 if a peer never arrived (spin limit). */
 LASS_API int lass_syncbn_max_peers(void);
 LASS_API int lass_bn_finalize_p2p(const void* const* peer_sums, void* const* peer_flags, int world, int rank,
@@ -234,9 +236,10 @@ LASS_API int lass_bn_finalize_p2p(const void* const* peer_sums, void* const* pee
                                   const float* gamma, const float* beta, float* running_mean, float* running_var,
                                   float momentum, float eps, int C, float* bnp, int* status, void* stream);
 LASS_API int lass_bn_bwd_finalize_p2p(const void* const* peer_sums, void* const* peer_flags, int world, int rank,
-                                      long long sums_offset, int flag_index, unsigned long long epoch, int B, int C,
-                                      double count_total, const float* gamma, float* bnp, float* dgamma, float* dbeta,
-                                      float* dfilm, int dfilm_bstride, int* status, void* stream);
+                                      long long sums_offset, long long totals_offset, int flag_index,
+                                      unsigned long long epoch, int B, int C, double count_total, const float* gamma,
+                                      float* bnp, float* dgamma, float* dbeta, float* dfilm, int dfilm_bstride, int* status,
+                                      void* stream);
 LASS_API int lass_bn_bwd_totals(const float* sums, int B, int C, double* totals, void* stream);
 LASS_API int lass_bn_bwd_finalize_sync(const float* sums, int B, int C, double count_total, const double* totals,
                                        const float* gamma, float* bnp, float* dgamma, float* dbeta, float* dfilm,

@@ -211,7 +211,7 @@ SIGNATURES.update({
 })
 SIGNATURES["lass_syncbn_max_peers"] = (_i, [])
 SIGNATURES["lass_bn_finalize_p2p"] = (_i, [_v, _v, _i, _i, _ll, _i, ctypes.c_ulonglong, _d, _v, _v, _v, _v, _f, _f, _i, _v, _v, _v])
-SIGNATURES["lass_bn_bwd_finalize_p2p"] = (_i, [_v, _v, _i, _i, _ll, _i, ctypes.c_ulonglong, _i, _i, _d, _v, _v, _v, _v, _v, _i, _v, _v])
+SIGNATURES["lass_bn_bwd_finalize_p2p"] = (_i, [_v, _v, _i, _i, _ll, _ll, _i, ctypes.c_ulonglong, _i, _i, _d, _v, _v, _v, _v, _v, _i, _v, _v])
 SIGNATURES["lass_bn_bwd_totals"] = (_i, [_v, _i, _i, _v, _v])
 SIGNATURES["lass_bn_bwd_finalize_sync"] = (_i, [_v, _i, _i, _d, _v, _v, _v, _v, _v, _v, _i, _v])
 SIGNATURES["lass_segment_mix_scratch_bytes"] = (ctypes.c_size_t, [_i])

@@ -446,6 +446,14 @@ __device__ __forceinline__ bool peer_exchange(const PeerTable& pt, int world, in
   return ok != 0;
 }
 
+// one 8-byte load from every peer, all in flight before the first use (a peer load is an NVLink round trip)
+template <typename T>
+__device__ __forceinline__ void load_peers(const T* const (&ptr)[kMaxPeers], int world, T (&v)[kMaxPeers]) {
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; ++p)
+    if (p < world) v[p] = __ldcv(ptr[p]);
+}
+
 __global__ void bn_finalize_p2p_kernel(PeerTable pt, int world, int rank, long long sums_offset, int flag_index, unsigned long long epoch,
                                        double count_total, const float* __restrict__ gamma, const float* __restrict__ beta,
                                        float* __restrict__ running_mean, float* __restrict__ running_var, float momentum, float eps, int C,
@@ -455,42 +463,80 @@ __global__ void bn_finalize_p2p_kernel(PeerTable pt, int world, int rank, long l
   peer_exchange(pt, world, rank, flag_index, epoch, status);
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int p = 0; p < world; ++p) {
-    const double* ps = reinterpret_cast<const double*>(pt.sums[p]) + sums_offset;     // (2, C) of this site
-    s += __ldcv(ps + c);
-    q += __ldcv(ps + C + c);
+  const double* ps[kMaxPeers];
+  const double* pq[kMaxPeers];
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; ++p) {
+    const double* base = reinterpret_cast<const double*>(pt.sums[p < world ? p : 0]) + sums_offset;     // (2, C) of this site
+    ps[p] = base + c;
+    pq[p] = base + C + c;
   }
+  double vs[kMaxPeers], vq[kMaxPeers];
+  load_peers(ps, world, vs);
+  load_peers(pq, world, vq);
+  double s = 0.0, q = 0.0;
+#pragma unroll
+  for (int p = 0; p < kMaxPeers; ++p)
+    if (p < world) s += vs[p], q += vq[p];               // rank order: the same sum on every rank
   bn_finalize_channel(s, q, c, C, count_total, gamma, beta, running_mean, running_var, momentum, eps, bnp);
 }
 
-__global__ void bn_bwd_finalize_p2p_kernel(PeerTable pt, int world, int rank, long long sums_offset, int flag_index, unsigned long long epoch,
-                                           int B, int C, double count_total, float* __restrict__ bnp, float* __restrict__ dgamma,
-                                           float* __restrict__ dbeta, float* __restrict__ dfilm, int dfilm_bstride, int* __restrict__ status) {
+// ONE block: (i) this rank's per-channel totals of its per-clip sums (local loads) -> its totals area, (ii) publish / wait,
+// (iii) every rank's totals through the peer pointers (world loads per channel instead of world x B), finalize.
+constexpr int kP2PBwdThreads = 256;
+constexpr int kP2PBwdMaxPerThread = 4;        // C <= 1024
+__global__ void __launch_bounds__(kP2PBwdThreads) bn_bwd_finalize_p2p_kernel(
+    PeerTable pt, int world, int rank, long long sums_offset, long long totals_offset, int flag_index, unsigned long long epoch, int B, int C,
+    double count_total, float* __restrict__ bnp, float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dfilm,
+    int dfilm_bstride, int* __restrict__ status) {
   griddep_launch_dependents();
   griddep_wait();
-  peer_exchange(pt, world, rank, flag_index, epoch, status);
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double g1 = 0.0, g2 = 0.0, l1 = 0.0, l2 = 0.0;
-  for (int p = 0; p < world; ++p) {
-    const float* ps = reinterpret_cast<const float*>(pt.sums[p]) + sums_offset;       // (B, C, 2) of this site
-    double t1 = 0.0, t2 = 0.0;
-    for (int b = 0; b < B; ++b) {
-      const float2 v = __ldcv(reinterpret_cast<const float2*>(ps) + (size_t)b * C + c);
-      t1 += (double)v.x;
-      t2 += (double)v.y;
-      if (p == rank && dfilm) dfilm[(size_t)b * dfilm_bstride + c] = v.x;
+  const float2* mine = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(pt.sums[rank]) + sums_offset);   // (B, C) x [g, g (x - mean)]
+  double* mytot = reinterpret_cast<double*>(const_cast<void*>(pt.sums[rank])) + totals_offset;                        // (C, 2)
+  double l1[kP2PBwdMaxPerThread], l2[kP2PBwdMaxPerThread];
+#pragma unroll
+  for (int i = 0; i < kP2PBwdMaxPerThread; ++i) {
+    const int c = threadIdx.x + i * kP2PBwdThreads;
+    l1[i] = l2[i] = 0.0;
+    if (c < C) {
+      for (int b = 0; b < B; ++b) {
+        const float2 v = __ldcg(mine + (size_t)b * C + c);
+        l1[i] += (double)v.x;
+        l2[i] += (double)v.y;
+        if (dfilm) dfilm[(size_t)b * dfilm_bstride + c] = v.x;
+      }
+      mytot[2 * c] = l1[i];
+      mytot[2 * c + 1] = l2[i];
     }
-    g1 += t1;
-    g2 += t2;
-    if (p == rank) l1 = t1, l2 = t2;
   }
-  const double scale = (double)bnp[c], rstd = (double)bnp[3 * C + c];
-  dbeta[c] = (float)l1;                                  // this rank's share (the gradient all-reduce averages parameter gradients)
-  dgamma[c] = (float)(rstd * l2);
-  bnp[4 * C + c] = (float)(-scale * rstd * rstd * g2 / count_total);
-  bnp[5 * C + c] = (float)(-scale * g1 / count_total);
+  __threadfence_system();
+  __syncthreads();                    // all totals of this rank are written (and fenced) before its epoch is published
+  peer_exchange(pt, world, rank, flag_index, epoch, status);
+#pragma unroll
+  for (int i = 0; i < kP2PBwdMaxPerThread; ++i) {
+    const int c = threadIdx.x + i * kP2PBwdThreads;
+    if (c >= C) continue;
+    const double* p1[kMaxPeers];
+    const double* p2[kMaxPeers];
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p) {
+      const double* base = reinterpret_cast<const double*>(pt.sums[p < world ? p : 0]) + totals_offset;
+      p1[p] = base + 2 * c;
+      p2[p] = base + 2 * c + 1;
+    }
+    double v1[kMaxPeers], v2[kMaxPeers];
+    load_peers(p1, world, v1);
+    load_peers(p2, world, v2);
+    double g1 = 0.0, g2 = 0.0;
+#pragma unroll
+    for (int p = 0; p < kMaxPeers; ++p)
+      if (p < world) g1 += v1[p], g2 += v2[p];
+    const double scale = (double)bnp[c], rstd = (double)bnp[3 * C + c];
+    dbeta[c] = (float)l1[i];                              // this rank's share (the gradient all-reduce averages parameter gradients)
+    dgamma[c] = (float)(rstd * l2[i]);
+    bnp[4 * C + c] = (float)(-scale * rstd * rstd * g2 / count_total);
+    bnp[5 * C + c] = (float)(-scale * g1 / count_total);
+  }
 }
 
 __global__ void __launch_bounds__(kRedThreads, 2) bn_bwd_apply_kernel(const void* __restrict__ dact, int d_cstride, int d_coff,
@@ -1340,15 +1386,17 @@ int lass_bn_finalize_p2p(const void* const* peer_sums, void* const* peer_flags, 
   LASS_LAUNCH_CHECK("bn_finalize_p2p launch");
 }
 
-int lass_bn_bwd_finalize_p2p(const void* const* peer_sums, void* const* peer_flags, int world, int rank, long long sums_offset, int flag_index,
-                             unsigned long long epoch, int B, int C, double count_total, const float* gamma, float* bnp, float* dgamma,
-                             float* dbeta, float* dfilm, int dfilm_bstride, int* status, void* stream_v) {
+int lass_bn_bwd_finalize_p2p(const void* const* peer_sums, void* const* peer_flags, int world, int rank, long long sums_offset,
+                             long long totals_offset, int flag_index, unsigned long long epoch, int B, int C, double count_total,
+                             const float* gamma, float* bnp, float* dgamma, float* dbeta, float* dfilm, int dfilm_bstride, int* status,
+                             void* stream_v) {
   PeerTable pt;
   if (int e = fill_peer_table(&pt, peer_sums, peer_flags, world, rank, "lass_bn_bwd_finalize_p2p")) return e;
-  if (!gamma || !bnp || !dgamma || !dbeta || B <= 0 || C <= 0 || count_total <= 0 || sums_offset < 0 || flag_index < 0 || epoch == 0)
+  if (!gamma || !bnp || !dgamma || !dbeta || B <= 0 || C <= 0 || C > kP2PBwdThreads * kP2PBwdMaxPerThread || count_total <= 0 || sums_offset < 0 ||
+      (sums_offset & 1) || totals_offset < 0 || flag_index < 0 || epoch == 0)
     return set_error(LASS_ERR_ARG, "lass_bn_bwd_finalize_p2p: bad argument");
-  launch_pdl(bn_bwd_finalize_p2p_kernel, (C + 127) / 128, 128, 0, (cudaStream_t)stream_v, pt, world, rank, sums_offset, flag_index, epoch, B, C,
-             count_total, bnp, dgamma, dbeta, dfilm, dfilm_bstride, status);
+  launch_pdl(bn_bwd_finalize_p2p_kernel, 1, kP2PBwdThreads, 0, (cudaStream_t)stream_v, pt, world, rank, sums_offset, totals_offset, flag_index, epoch,
+             B, C, count_total, bnp, dgamma, dbeta, dfilm, dfilm_bstride, status);
   LASS_LAUNCH_CHECK("bn_bwd_finalize_p2p launch");
 }
 

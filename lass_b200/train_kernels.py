@@ -208,11 +208,13 @@ def bn_finalize_p2p(table, sums_offset, flag_index, epoch, count_total, gamma, b
                                            _p(table.status), _stream()))
 
 
-def bn_bwd_finalize_p2p(table, sums_offset, flag_index, epoch, B, count_total, gamma, bnp, dgamma, dbeta, dfilm):
-    """bn_bwd_finalize_sync with the totals taken from every rank's per-clip sums through peer memory inside the kernel."""
+def bn_bwd_finalize_p2p(table, sums_offset, totals_offset, flag_index, epoch, B, count_total, gamma, bnp, dgamma, dbeta, dfilm):
+    """bn_bwd_finalize_sync with the exchange inside the kernel: this rank's per-clip sums (float element ``sums_offset``) ->
+    its per-channel totals (double element ``totals_offset``) -> every rank's totals through peer memory."""
     _need_cuda(gamma, bnp, dgamma, dbeta, table.status)
     _chk(_cabi.load().lass_bn_bwd_finalize_p2p(table.sums, table.flags, table.world, table.rank, int(sums_offset),
-                                               int(flag_index), int(epoch), int(B), gamma.numel(), float(count_total),
+                                               int(totals_offset), int(flag_index), int(epoch), int(B), gamma.numel(),
+                                               float(count_total),
                                                _p(gamma), _p(bnp), _p(dgamma), _p(dbeta), _p(dfilm),
                                                dfilm.stride(0) if dfilm is not None else 0, _p(table.status), _stream()))
 

@@ -501,12 +501,13 @@ class TrainEngine:
         """COLLECTIVE: this workspace's backward sums (B, C, 2) of all sites, twice, in symmetric memory."""
         import torch.distributed._symmetric_memory as symm
         from types import SimpleNamespace
-        total = sum(ws.B * st.C * 2 for st in self.site.values())
+        n_sums = sum(ws.B * st.C * 2 for st in self.site.values())          # per-clip sums, fp32 (even: 8-byte aligned end)
+        total = n_sums + sum(st.C * 4 for st in self.site.values())          # + per-channel totals (C, 2) fp64 = 4 floats per channel
         buf = symm.empty(2 * total, dtype=torch.float32, device=self.device)
         buf.zero_()
         torch.cuda.synchronize(self.device)
         h_buf = symm.rendezvous(buf, self._p2p_group())
-        p = SimpleNamespace(buf=buf, handle=h_buf, total=total, offsets={}, views=[],
+        p = SimpleNamespace(buf=buf, handle=h_buf, total=total, offsets={}, tot_offsets={}, views=[],
                             table=self.k.PeerTable(h_buf.buffer_ptrs, self._p2p.flag_ptrs, self._p2p.rank, self._p2p.status))
         for h in range(2):
             flat = buf[h * total:(h + 1) * total]
@@ -515,7 +516,11 @@ class TrainEngine:
                 sites[s_] = flat[o:o + ws.B * st.C * 2].view(ws.B, st.C, 2)
                 p.offsets[s_] = o
                 o += ws.B * st.C * 2
-            p.views.append(SimpleNamespace(flat=flat, sites=sites))
+            p.views.append(SimpleNamespace(flat=flat[:n_sums], sites=sites))
+        o = n_sums
+        for s_, st in self.site.items():                                     # float offsets of the totals areas inside a half
+            p.tot_offsets[s_] = o
+            o += st.C * 4
         ws.p2p = p
 
     def check_sync_status(self):
@@ -617,7 +622,8 @@ class TrainEngine:
             p = ws.p2p
             h = ws.epoch & 1
             k.bn_bwd_reduce_acc(dact, x, x_coff, st.C, st.bnp, beta, p.views[h].sites[site])
-            k.bn_bwd_finalize_p2p(p.table, h * p.total + p.offsets[site], 64 + site, ws.epoch, ws.B, count * ws.sync_world,
+            k.bn_bwd_finalize_p2p(p.table, h * p.total + p.offsets[site], (h * p.total + p.tot_offsets[site]) // 2, 64 + site,
+                                  ws.epoch, ws.B, count * ws.sync_world,
                                   st.bn.weight.data, st.bnp, self.g(name + ".weight"), self.g(name + ".bias"),
                                   ws.dbeta[:, st.row:st.row + st.C])
             k.bn_bwd_apply(dact, x, x_coff, st.C, st.bnp, beta, add, add_coff, dx, dx_coff)

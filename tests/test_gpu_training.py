@@ -139,10 +139,13 @@ def test_sync_batchnorm_peer_memory_kernels(K, C, world):
     flags = [torch.zeros(128 * 16, dtype=torch.int64, device=dev) for _ in range(world)]
     status = torch.zeros(1, dtype=torch.int32, device=dev)
     fbuf = [torch.zeros(off + 2 * C, dtype=torch.float64, device=dev) for _ in range(world)]
-    bbuf = [torch.zeros(off + B * C * 2, dtype=torch.float32, device=dev) for _ in range(world)]
+    tot_off = (off + B * C * 2) // 2                 # double-element offset of the per-channel totals area behind the per-clip sums
+    bbuf = [torch.zeros(off + B * C * 2 + 4 * C, dtype=torch.float32, device=dev) for _ in range(world)]
     for r in range(world):
         fbuf[r][off:] = fsums[r].reshape(-1).to(dev)
-        bbuf[r][off:] = bsums[r].reshape(-1).to(dev)
+        bbuf[r][off:off + B * C * 2] = bsums[r].reshape(-1).to(dev)
+        # the peers "have arrived": their totals are already in their areas (this rank's kernel writes its own)
+        bbuf[r][off + B * C * 2:] = bsums[r].double().sum(0).reshape(-1).to(dev).view(torch.float32)
     outs = []
     # the peers "have arrived": their epochs are already in every rank's table (the waiting itself -- ranks that really run
     # concurrently -- is what tools/gpu_syncbn_check.py covers on two GPUs); each rank's own slot is written by its kernel
@@ -158,7 +161,7 @@ def test_sync_batchnorm_peer_memory_kernels(K, C, world):
         o = dict(bnp=torch.zeros(6 * C, device=dev), rm=torch.zeros(C, device=dev), rv=torch.ones(C, device=dev),
                  dg=torch.zeros(C, device=dev), db=torch.zeros(C, device=dev), dfilm=torch.zeros(B, C, device=dev))
         K.bn_finalize_p2p(ft, off, 3, epoch, world * count, gamma.to(dev), beta.to(dev), o["rm"], o["rv"], 0.01, 1e-5, o["bnp"])
-        K.bn_bwd_finalize_p2p(bt, off, 64 + 3, epoch, B, world * count, gamma.to(dev), o["bnp"], o["dg"], o["db"], o["dfilm"])
+        K.bn_bwd_finalize_p2p(bt, off, tot_off, 64 + 3, epoch, B, world * count, gamma.to(dev), o["bnp"], o["dg"], o["db"], o["dfilm"])
         outs.append(o)
     torch.cuda.synchronize()
     for r in range(world):                       # every rank published its epoch into its slot of every table, nothing else
