@@ -434,7 +434,9 @@ __device__ __forceinline__ bool peer_exchange(const PeerTable& pt, int world, in
     }
     const unsigned long long* mine = pt.flags[rank] + (size_t)flag_index * kMaxPeers + p;
     long long spins = 0;
-    while (ld_acquire_sys(mine) < epoch) {
+    // once an exchange has timed out (*status set) no later one waits again: the step is lost, but it ends
+    const bool dead = status != nullptr && *reinterpret_cast<volatile int*>(status) != 0;
+    while (!dead && ld_acquire_sys(mine) < epoch) {
       if (++spins > kSpinLimit) {
         ok = 0;
         if (status) atomicExch(status, 1);
