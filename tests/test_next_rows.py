@@ -139,8 +139,9 @@ def test_audiosep_training_step_and_fused_step():
     from lass_b200.models.clap_standin import RandomInitCLAPTextEncoder
     from lass_b200.models.resunet import ResUNet30
 
-    def mixer(waveforms):                            # stand-in for data/waveform_mixers.SegmentMixer (out of scope): (B,1,L) -> mixtures (B,1,L), segments (B,1,L)
-        return waveforms + 0.5 * waveforms.roll(1, 0), waveforms
+    from lass_b200.data.waveform_mixers import SegmentMixer
+    mixer = SegmentMixer(max_mix_num=2, lower_db=-10, higher_db=10)       # the reference's own step in front (train.py:217-221), on the GPU;
+                                                                         # random.seed(batch_idx) inside the step pins its draws
 
     enc = RandomInitCLAPTextEncoder(hidden_size=64, num_hidden_layers=2, num_attention_heads=4, intermediate_size=128).cuda()
     wave, _ = factory.make_inputs(4, 16000, edge_clips=False)
